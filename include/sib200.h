@@ -1,0 +1,148 @@
+/* sib200.h — C ABI of libsib200.so, the sm_100a (B200) kernels behind sota_imagenet_b200.
+ *
+ * The reference (bonlime/sota_imagenet) ships no native code: every kernel of its training
+ * step is reached through torch (cuDNN / cuBLAS / ATen), NVIDIA DALI or pytorch_tools.  This
+ * header is therefore the boundary a maintainer would bind *instead of* those library calls;
+ * each entry point cites the reference call site whose kernel it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - activations are NHWC bf16 (channel count a multiple of 8, 16-byte aligned base);
+ *   - conv filters are [Cout][R][S][Cin] bf16 ("KRSC" = torch channels_last memory format);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value 0 = success; otherwise sib_last_error() describes the failure.  Nothing
+ *     falls back to the CPU: without an sm_100a device every compute call fails.
+ */
+#ifndef SIB200_H_
+#define SIB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIB_ABI_VERSION 1
+
+/* activation codes (pytorch_tools ABN `activation=`; BResNet50_encoder.yaml:49 leaky_relu) */
+#define SIB_ACT_NONE 0
+#define SIB_ACT_RELU 1
+#define SIB_ACT_LEAKY 2
+
+/* margin kinds of the fused head */
+#define SIB_MARGIN_NONE 0
+#define SIB_MARGIN_ARC 1 /* AdditiveAngularMarginLoss, angular_losses.py:128-146 */
+#define SIB_MARGIN_COS 2 /* CosFace, angular_losses.py:186-198 and :332-333      */
+
+/* conv flags */
+#define SIB_FLAG_FORCE_IM2COL 1 /* use the im2col TMA path even for plain 1x1 (testing) */
+
+const char* sib_last_error(void);
+int sib_abi_version(void);
+int sib_device_check(void); /* 0 iff the current device is sm_100 */
+
+/* ---- convolution: replaces F.conv2d fwd / autograd dgrad / wgrad (cuDNN) reached from
+ *      pytorch_tools.models.resnet50, reference train.py:64; in-repo call model.py:106 ---- */
+
+/* y[N][OH][OW][K] = conv(x[N][H][W][C], w[K][R][S][C]); optional bias[K];
+ * stats (optional, [2][K] fp32) receives per-channel sum and sum-of-squares of y (BN fusion). */
+int sib_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W, int C, int K,
+                     int R, int S, int stride, int pad_h, int pad_w, int OH, int OW,
+                     const float* bias, float* stats, int flags, void* stream);
+
+/* dx[N][H][W][C] (+)= dgrad(dy[N][OH][OW][K]); w_dgrad is the tap-flipped transposed filter
+ * [C][R][S][K] produced by sib_pack_dgrad_weights.  stride 1, or stride>1 with a 1x1 filter
+ * (accumulate must be 1: only every stride-th pixel is touched). */
+int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int C,
+                     int K, int R, int S, int stride, int pad, int accumulate, int flags,
+                     void* stream);
+/* strided RxS dgrad; workspace holds N*((OH-1)*stride+1)*((OW-1)*stride+1)*K bf16 */
+int sib_conv2d_dgrad_strided(const void* dy, const void* w_dgrad, void* dx, void* workspace, int N,
+                             int H, int W, int C, int K, int R, int S, int stride, int pad,
+                             int accumulate, int flags, void* stream);
+/* dw[K][R][S][C] (fp32) += wgrad(x, dy).  dw must be initialised (zero_grad). */
+int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int K,
+                     int R, int S, int stride, int pad_h, int pad_w, int OH, int OW, int flags,
+                     void* stream);
+int sib_upsample_zero(const void* dy, void* up, int N, int OH, int OW, int C, int UH, int UW,
+                      int stride, void* stream);
+
+/* ---- BatchNorm (+ReLU, +residual): replaces nn.BatchNorm2d / pytorch_tools ABN kernels
+ *      (cuDNN BN + ATen relu/add), momentum patched by reference train.py:76 ---- */
+int sib_bn_stats(const void* x, long M, int C, float* stats, void* stream);
+int sib_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float* mean_invstd, float* scale_shift, int C,
+                    double count, float eps, float momentum, void* stream);
+int sib_bn_eval_scale(const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, float* scale_shift, int C, float eps, void* stream);
+/* y = act(x*scale + shift [+ res] [res*scale2 + shift2]) */
+int sib_bn_apply(const void* x, const float* scale_shift, const void* res,
+                 const float* scale_shift2, void* y, long M, int C, int act, float slope,
+                 void* stream);
+/* sums[0..1][C] = (sum g, sum g*xhat), g = dy * act'(out); with x2: sums[2..3] for the 2nd BN */
+int sib_bn_bwd_reduce(const void* dy, const void* out, const void* x, const float* mean_invstd,
+                      const void* x2, const float* mean_invstd2, long M, int C, int act,
+                      float slope, float* sums, void* stream);
+int sib_bn_bwd_apply(const void* dy, const void* out, const void* x, const float* mean_invstd,
+                     const float* gamma, const float* sums, const void* x2,
+                     const float* mean_invstd2, const float* gamma2, void* dx, void* dx2,
+                     void* gout, long M, int C, double count, int act, float slope, void* stream);
+int sib_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int accumulate,
+                      void* stream);
+
+/* ---- pooling (stem max-pool, head global average pool) ---- */
+int sib_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C,
+                         void* stream);
+int sib_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C,
+                         void* stream);
+int sib_gap_fwd(const void* x, void* y, int N, int HW, int C, void* stream);
+int sib_gap_bwd(const void* dy, void* dx, int N, int HW, int C, void* stream);
+
+/* ---- heads: pytorch_tools.losses.smooth.CrossEntropyLoss (arg_parser.py:140-142),
+ *      angular_losses.py AdditiveAngularMarginLoss / CosFace / SphereLinearLayer ---- */
+int sib_ce_fwd_bwd(const void* logits, int logits_fp32, const long* labels,
+                   const float* dense_targets, int B, int C, int ld, float smoothing,
+                   float temperature, int margin_kind, float s, float m, float* loss_rows,
+                   float* loss_mean, void* dlogits, float grad_scale, void* stream);
+int sib_sphere_linear_fwd(const float* x, const float* w, float* cosv, float* xn, float* wn,
+                          float* xnorm, float* wnorm, int B, int C, int D, int normalize_x,
+                          void* stream);
+int sib_sphere_linear_bwd(const float* dcos, const float* x_or_xn, const float* wn,
+                          const float* xnorm, const float* wnorm, float* dx, float* dw,
+                          float* scratch, int B, int C, int D, int normalize_x, void* stream);
+
+/* ---- optimizer: torch.optim._multi_tensor.SGD (arg_parser.py:136-138), ModelEma
+ *      (train.py:112), weight standardisation (train.py:66-67, model.py:91-100) ---- */
+/* segs_dev: nseg x {long end; float lr, weight_decay, momentum, dampening; int nesterov, pad} */
+int sib_sgd_step(float* params, const float* grads, float* momentum_buf, void* params_bf16,
+                 float* ema, float ema_decay, const void* segs_dev, int nseg, long n,
+                 int first_step, void* stream);
+int sib_cast_bf16(const float* src, void* dst, long n, void* stream);
+/* table_dev: nent x {long src_off, dst_off; int K, RS, C, block_begin} */
+int sib_pack_dgrad_weights(const void* w_bf16, void* w_dgrad, const void* table_dev, int nent,
+                           int total_blocks, void* stream);
+int sib_weight_standardize(const float* w, const float* gain, void* out_bf16, float* mean_invstd,
+                           int out_channels, int fan, float eps, void* stream);
+int sib_weight_standardize_bwd(const float* w, const float* gain, const float* mean_invstd,
+                               const float* g, float* dw, int out_channels, int fan, void* stream);
+
+/* ---- data: DALI train pipeline (dali_dataloader.py:65-74,113-123) on synthetic uint8 ---- */
+int sib_rrc_boxes(int* boxes_dev, int B, int H, int W, double min_area, double max_area,
+                  unsigned long long seed, unsigned long long first_sample, int do_flip,
+                  void* stream);
+void sib_rrc_box_host(int H, int W, double min_area, double max_area, unsigned long long seed,
+                      unsigned long long sample, int* box5_host);
+/* out_mode 0: NHWC bf16, 4 channels (4th zero); 1: NCHW fp32 (the reference layout) */
+int sib_augment(const void* src_u8, const int* boxes_dev, void* out, int B, int SH, int SW, int S,
+                float mean, float std, int out_mode, void* stream);
+int sib_one_hot(const long* labels, float* out, int B, int C, void* stream);
+/* stem packing (see csrc/augment.cu): src_mode 0 = NHWC4 bf16, 1 = NCHW fp32 */
+int sib_stem_pack(const void* src, void* xq, int N, int H, int W, int KW, int pad_w, int src_mode,
+                  void* stream);
+int sib_stem_pack_weight(const float* w_oihw, void* wq, int K, int KH, int KW, int NA, int off,
+                         void* stream);
+int sib_stem_unpack_wgrad(const float* dwq, float* dw_oihw, int K, int KH, int KW, int NA, int off,
+                          int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIB200_H_ */

@@ -1,0 +1,561 @@
+// NHWC bf16 implicit-GEMM convolution on sm_100a tensor cores.
+//
+//   fprop / dgrad : D[M = pixels][N = out channels] = sum_k A[pixels][k] * B[out ch][k]
+//                   A gathered by TMA im2col loads (one filter tap x 64 channels per k-block),
+//                   B = packed weights [Cout][R*S*Cin] (K-major), both 128B-swizzled in smem,
+//                   tcgen05.mma (M=128, N=BN, K=16) accumulating fp32 in TMEM.
+//   wgrad         : dW[Cout][tap][Cin] = sum_pixels dY[pixel][Cout] * X_im2col[pixel][tap, Cin]
+//                   both operands MN-major, split over pixel ranges, fp32 red.add to dW.
+//
+// Replaces what the reference reaches through cuDNN: F.conv2d / autograd conv backward
+// inside pytorch_tools.models.resnet50 (reference train.py:64).
+#include "common.cuh"
+#include "host.h"
+#include "../../include/sib200.h"
+
+namespace sib {
+
+constexpr int kBM = 128;        // GEMM-M tile (output pixels / wgrad out channels)
+constexpr int kBK = 64;         // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int kABytes = kBM * kBK * 2;
+constexpr int kThreads = 192;   // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
+
+struct IgemmParams {
+  int M_total;       // GEMM M (pixels of the traversal space)
+  int Cout;          // GEMM N
+  int num_kblocks;   // taps * Cin/64
+  int cin_blocks;    // Cin / 64
+  int S;             // filter width (tap = r * S + s)
+  int trav_hw, trav_w;  // traversal space: pixels per image, pixels per row
+  int stride, pad_h, pad_w;   // base pixel = (p*stride - pad_h, q*stride - pad_w)
+  int OH, OW, ostride;  // output tensor spatial extent and pixel step (2 = strided scatter)
+  int ldc;           // output row pitch in elements
+  int accumulate;    // out += result
+  int tiled_a;       // A is a plain [M][K] matrix (1x1 stride-1)
+  const float* bias; // optional [Cout]
+  float* stats;      // optional [2][Cout]: sum, sum of squares of the stored bf16 values
+};
+
+// Column sums across the 32 lanes of a warp: lane l returns sum over lanes of v[l].
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32]) {
+  const uint32_t lane = lane_id();
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = upper ? v[i] : v[i + off];
+      float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             __nv_bfloat16* __restrict__ out, const IgemmParams p) {
+  constexpr int kBBytes = BN * kBK * 2;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_stats[2][BN];
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * kABytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kBM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 2 * BN; i += kThreads) (&s_stats[0][0])[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer ----
+      int n_img = m0 / p.trav_hw;
+      int rem = m0 - n_img * p.trav_hw;
+      int pp = rem / p.trav_w;
+      int qq = rem - pp * p.trav_w;
+      const int w_base = qq * p.stride - p.pad_w;
+      const int h_base = pp * p.stride - p.pad_h;
+      int stage = 0;
+      uint32_t phase = 0;
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
+        if (p.tiled_a) {
+          tma_load_2d(smem_a + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m0);
+        } else {
+          const int r = tap / p.S;
+          const int s = tap - r * p.S;
+          tma_load_im2col_4d(smem_a + stage * kABytes, &tmA, &full_bar[stage], cb * kBK, w_base,
+                             h_base, n_img, (uint16_t)s, (uint16_t)r);
+        }
+        tma_load_2d(smem_b + stage * kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
+        if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- MMA issuer ----
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t a_desc =
+            umma_smem_desc(smem_u32(smem_a + stage * kABytes), 16, 1024, kSwizzle128B);
+        const uint64_t b_desc =
+            umma_smem_desc(smem_u32(smem_b + stage * kBBytes), 16, 1024, kSwizzle128B);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // +32 bytes along K inside the 128B swizzle row = +2 in 16-byte address units
+          umma_bf16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ---- epilogue: TMEM -> registers -> (bias, accumulate, stats) -> global ----
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const int m = m0 + row;
+    const bool valid = m < p.M_total;
+    long pix = m;
+    if (p.ostride != 1 || p.OH * p.OW != p.trav_hw) {
+      int n_img = m / p.trav_hw;
+      int rem = m - n_img * p.trav_hw;
+      int pp = rem / p.trav_w;
+      int qq = rem - pp * p.trav_w;
+      pix = ((long)n_img * p.OH + (long)pp * p.ostride) * p.OW + (long)qq * p.ostride;
+    }
+    __nv_bfloat16* orow = out + pix * (long)p.ldc;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + chunk * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      const int col0 = n0 + chunk * 32;
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = col0 + g * 8;
+        if (valid && c < p.Cout) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c);
+          if (p.accumulate) {
+            float prev[8];
+            unpack8(*dst, prev);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
+          }
+          *dst = pack8(&v[g * 8]);
+        }
+      }
+      if (p.stats != nullptr) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          // statistics of the values as stored (bf16-rounded)
+          float t = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+          s1[j] = t;
+          s2[j] = t * t;
+        }
+        float a = warp_transpose_reduce32(s1);
+        float b = warp_transpose_reduce32(s2);
+        atomicAdd(&s_stats[0][chunk * 32 + lane], a);
+        atomicAdd(&s_stats[1][chunk * 32 + lane], b);
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = threadIdx.x - 64;
+      for (int c = t; c < BN; c += 128) {
+        if (n0 + c < p.Cout) {
+          atomicAdd(p.stats + n0 + c, s_stats[0][c]);
+          atomicAdd(p.stats + p.Cout + n0 + c, s_stats[1][c]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// wgrad
+// ----------------------------------------------------------------------------
+struct WgradParams {
+  int M_total;       // pixels (reduction length)
+  int Cout, Cin;
+  int S;
+  int trav_hw, trav_w;
+  int stride, pad_h, pad_w;
+  int kblocks_per_split;   // 64-pixel blocks handled by one CTA
+  int total_kblocks;
+  int ldw;           // dW row pitch = R*S*Cin
+  int cin_tiles;     // Cin / BNC
+};
+
+constexpr int kWgPix = 64;  // pixels per k-block
+
+template <int BNC, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+             float* __restrict__ dw, const WgradParams p) {
+  constexpr int kABytesW = kWgPix * kBM * 2;   // dY tile: 64 pixels x 128 out channels
+  constexpr int kBBytesW = kWgPix * BNC * 2;   // X tile : 64 pixels x BNC in channels
+  constexpr uint32_t kTmemCols = BNC < 32 ? 32 : BNC;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * kABytesW;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * kBM;                 // out-channel tile
+  const int tap = blockIdx.y / p.cin_tiles;        // filter tap
+  const int c0 = (blockIdx.y % p.cin_tiles) * BNC; // in-channel tile
+  const int kb_begin = blockIdx.z * p.kblocks_per_split;
+  int kb_end = kb_begin + p.kblocks_per_split;
+  if (kb_end > p.total_kblocks) kb_end = p.total_kblocks;
+  const int nkb = kb_end - kb_begin;
+  const int a_boxes = (p.Cout - k0 > 64) ? 2 : 1;  // second 64-channel half may not exist
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (nkb <= 0) {
+    // nothing to do for this split (uniform across the CTA); fall through to teardown
+  } else if (warp == 0) {
+    if (lane == 0) {
+      const int r = tap / p.S;
+      const int s = tap - r * p.S;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int m0 = kb * kWgPix;
+        int n_img = m0 / p.trav_hw;
+        int rem = m0 - n_img * p.trav_hw;
+        int pp = rem / p.trav_w;
+        int qq = rem - pp * p.trav_w;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], a_boxes * (kWgPix * 64 * 2) + kBBytesW);
+        uint8_t* a_dst = smem_a + stage * kABytesW;
+        for (int h = 0; h < a_boxes; ++h)
+          tma_load_2d(a_dst + h * (kWgPix * 128), &tmDy, &full_bar[stage], k0 + h * 64, m0);
+        uint8_t* b_dst = smem_b + stage * kBBytesW;
+#pragma unroll
+        for (int h = 0; h < BNC / 64; ++h)
+          tma_load_im2col_4d(b_dst + h * (kWgPix * 128), &tmX, &full_bar[stage], c0 + h * 64,
+                             qq * p.stride - p.pad_w, pp * p.stride - p.pad_h, n_img, (uint16_t)s,
+                             (uint16_t)r);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // both operands MN-major: 64-element groups along M/N are kWgPix*128 bytes apart (LBO),
+      // 8-pixel groups along K are 1024 bytes apart (SBO)
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BNC, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a + stage * kABytesW),
+                                               kWgPix * 128, 1024, kSwizzle128B);
+        const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + stage * kBBytesW),
+                                               kWgPix * 128, 1024, kSwizzle128B);
+#pragma unroll
+        for (int k = 0; k < kWgPix / 16; ++k) {
+          // 16 pixels along K = two 1024-byte groups = +128 in 16-byte address units
+          umma_bf16_ss(tmem_base, a_desc + 128 * k, b_desc + 128 * k, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;   // out channel within the tile
+    const int k = k0 + row;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    float* drow = dw + (long)k * p.ldw + (long)tap * p.Cin + c0;
+#pragma unroll 1
+    for (int chunk = 0; chunk < BNC / 32; ++chunk) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + chunk * 32, r);
+      tmem_ld_wait();
+      if (k < p.Cout) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (c0 + chunk * 32 + g * 4 < p.Cin) {
+            float* d = drow + chunk * 32 + g * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d),
+                         "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
+                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                         : "memory");
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// host launchers
+// ----------------------------------------------------------------------------
+template <int BN, int STAGES>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* out,
+                        const IgemmParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.Cout + BN - 1) / BN, (p.M_total + kBM - 1) / kBM);
+  igemm_kernel<BN, STAGES><<<grid, kThreads, smem, stream>>>(
+      tmA, tmB, static_cast<__nv_bfloat16*>(out), p);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Shared by fprop and dgrad.  `in` is [N][IH][IW][Cin] NHWC bf16, `w` is [Cout][R][S][Cin].
+// The traversal space (GEMM rows) is [N][TH][TW]; row (n,p,q) reads taps starting at
+// (p*stride - pad, q*stride - pad) and is stored at out[n][p*ostride][q*ostride][:].
+static int run_igemm(const void* in, const void* w, void* out, int N, int IH, int IW, int Cin,
+                     int Cout, int R, int S, int stride, int pad_h, int pad_w, int TH, int TW,
+                     int OH, int OW,
+                     int ostride, int accumulate, const float* bias, float* stats, int flags,
+                     cudaStream_t stream) {
+  SIB_CHECK(Cin % 64 == 0, "igemm: Cin must be a multiple of 64 (got %d)", Cin);
+  SIB_CHECK(Cout % 8 == 0, "igemm: Cout must be a multiple of 8 (got %d)", Cout);
+  SIB_CHECK((long)N * TH * TW < (1l << 31), "igemm: too many pixels");
+  IgemmParams p{};
+  p.M_total = N * TH * TW;
+  p.Cout = Cout;
+  p.cin_blocks = Cin / 64;
+  p.num_kblocks = R * S * p.cin_blocks;
+  p.S = S;
+  p.trav_hw = TH * TW;
+  p.trav_w = TW;
+  p.stride = stride;
+  p.pad_h = pad_h;
+  p.pad_w = pad_w;
+  p.OH = OH;
+  p.OW = OW;
+  p.ostride = ostride;
+  p.ldc = Cout;
+  p.accumulate = accumulate;
+  p.bias = bias;
+  p.stats = stats;
+  const bool plain =
+      (R == 1 && S == 1 && stride == 1 && pad_h == 0 && pad_w == 0 && TH == IH && TW == IW);
+  p.tiled_a = (plain && !(flags & SIB_FLAG_FORCE_IM2COL)) ? 1 : 0;
+
+  const int BN = (Cout <= 64) ? 64 : 128;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (p.tiled_a) {
+    rc = make_tmap_2d_bf16(&tmA, in, (uint64_t)p.M_total, Cin, Cin, kBM, kBK, true);
+  } else {
+    // base pixel range: [-pad, -pad + (T-1)*stride]  =>  upper corner = that max - (I-1)
+    const int up_w = -pad_w + (TW - 1) * stride - (IW - 1);
+    const int up_h = -pad_h + (TH - 1) * stride - (IH - 1);
+    rc = make_tmap_im2col_bf16(&tmA, in, N, IH, IW, Cin, -pad_w, -pad_h, up_w, up_h, stride,
+                               stride, kBK, kBM, true);
+  }
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, BN, kBK,
+                         true);
+  if (rc) return rc;
+  if (stats != nullptr) SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, stream));
+  if (BN == 64) return launch_igemm<64, 4>(tmA, tmB, out, p, stream);
+  return launch_igemm<128, 3>(tmA, tmB, out, p, stream);
+}
+
+template <int BNC, int STAGES>
+static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, float* dw,
+                        const WgradParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kWgPix * kBM * 2 + kWgPix * BNC * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SIB_CUDA(cudaFuncSetAttribute(wgrad_kernel<BNC, STAGES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  wgrad_kernel<BNC, STAGES><<<grid, kThreads, smem, stream>>>(tmDy, tmX, dw, p);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sib
+
+using namespace sib;
+
+extern "C" int sib_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W,
+                                int C, int K, int R, int S, int stride, int pad_h, int pad_w,
+                                int OH, int OW, const float* bias, float* stats, int flags,
+                                void* stream) {
+  SIB_CHECK(OH >= 1 && OW >= 1 && (OH - 1) * stride - pad_h < H && (OW - 1) * stride - pad_w < W,
+            "fprop: output extent %dx%d inconsistent with input %dx%d", OH, OW, H, W);
+  return run_igemm(x, w, y, N, H, W, C, K, R, S, stride, pad_h, pad_w, OH, OW, OH, OW, 1, 0, bias,
+                   stats, flags, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx, int N, int H,
+                                int W, int C, int K, int R, int S, int stride, int pad,
+                                int accumulate, int flags, void* stream) {
+  const int OH = (H + 2 * pad - R) / stride + 1;
+  const int OW = (W + 2 * pad - S) / stride + 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stride == 1) {
+    // full correlation of dY with the tap-flipped, transposed filter
+    return run_igemm(dy, w_dgrad, dx, N, OH, OW, K, C, R, S, 1, R - 1 - pad, S - 1 - pad, H, W, H,
+                     W, 1, accumulate, nullptr, nullptr, flags, st);
+  }
+  if (R == 1 && S == 1 && pad == 0) {
+    // strided 1x1: only pixels (p*stride, q*stride) receive gradient
+    SIB_CHECK(accumulate, "strided 1x1 dgrad only supports accumulate=1 (dx must be initialised)");
+    return run_igemm(dy, w_dgrad, dx, N, OH, OW, K, C, 1, 1, 1, 0, 0, OH, OW, H, W, stride, 1,
+                     nullptr, nullptr, flags, st);
+  }
+  return fail(1, "dgrad: stride %d with %dx%d filter must go through sib_conv2d_dgrad_strided",
+              stride, R, S);
+}
+
+extern "C" int sib_upsample_zero(const void* dy, void* up, int N, int OH, int OW, int C, int UH,
+                                 int UW, int stride, void* stream);
+
+// Strided RxS dgrad: zero-insert dY into `workspace` ([N][UH][UW][K], UH = (OH-1)*stride+1) and
+// run the stride-1 full correlation over it (TMA zero-fills everything outside the workspace).
+extern "C" int sib_conv2d_dgrad_strided(const void* dy, const void* w_dgrad, void* dx,
+                                        void* workspace, int N, int H, int W, int C, int K, int R,
+                                        int S, int stride, int pad, int accumulate, int flags,
+                                        void* stream) {
+  const int OH = (H + 2 * pad - R) / stride + 1;
+  const int OW = (W + 2 * pad - S) / stride + 1;
+  const int UH = (OH - 1) * stride + 1, UW = (OW - 1) * stride + 1;
+  if (int rc = sib_upsample_zero(dy, workspace, N, OH, OW, K, UH, UW, stride, stream)) return rc;
+  return run_igemm(workspace, w_dgrad, dx, N, UH, UW, K, C, R, S, 1, R - 1 - pad, S - 1 - pad, H,
+                   W, H, W, 1, accumulate, nullptr, nullptr, flags,
+                   static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W,
+                                int C, int K, int R, int S, int stride, int pad_h, int pad_w,
+                                int OH, int OW, int flags, void* stream) {
+  (void)flags;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SIB_CHECK(C % 64 == 0, "wgrad: Cin must be a multiple of 64 (got %d)", C);
+  SIB_CHECK(K % 8 == 0, "wgrad: Cout must be a multiple of 8 (got %d)", K);
+  WgradParams p{};
+  p.M_total = N * OH * OW;
+  p.Cout = K;
+  p.Cin = C;
+  p.S = S;
+  p.trav_hw = OH * OW;
+  p.trav_w = OW;
+  p.stride = stride;
+  p.pad_h = pad_h;
+  p.pad_w = pad_w;
+  p.total_kblocks = (p.M_total + kWgPix - 1) / kWgPix;
+  p.ldw = R * S * C;
+  const int BNC = (C % 128 == 0) ? 128 : 64;
+  p.cin_tiles = C / BNC;
+  const int tiles = ((K + kBM - 1) / kBM) * R * S * p.cin_tiles;
+  // enough splits for ~4 waves, at least 4 k-blocks each
+  int splits = (4 * sm_count() + tiles - 1) / tiles;
+  int max_splits = (p.total_kblocks + 3) / 4;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.kblocks_per_split = (p.total_kblocks + splits - 1) / splits;
+  splits = (p.total_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+
+  CUtensorMap tmDy, tmX;
+  int rc = make_tmap_2d_bf16(&tmDy, dy, (uint64_t)p.M_total, K, K, kWgPix, 64, true);
+  if (rc) return rc;
+  const int up_w = -pad_w + (OW - 1) * stride - (W - 1);
+  const int up_h = -pad_h + (OH - 1) * stride - (H - 1);
+  rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, C, -pad_w, -pad_h, up_w, up_h, stride, stride, 64,
+                             kWgPix, true);
+  if (rc) return rc;
+  dim3 grid((K + kBM - 1) / kBM, R * S * p.cin_tiles, splits);
+  if (BNC == 128) return launch_wgrad<128, 4>(tmDy, tmX, dw, p, grid, st);
+  return launch_wgrad<64, 4>(tmDy, tmX, dw, p, grid, st);
+}

@@ -1,0 +1,48 @@
+// Host-side plumbing shared by the C-ABI entry points: error reporting and
+// CUtensorMap construction through the driver entry points (no -lcuda link).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sib {
+
+// Records a message retrievable through sib_last_error() and returns `code`.
+int fail(int code, const char* fmt, ...);
+
+#define SIB_CHECK(cond, ...)                      \
+  do {                                            \
+    if (!(cond)) return ::sib::fail(1, __VA_ARGS__); \
+  } while (0)
+
+#define SIB_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return ::sib::fail(2, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                         __FILE__, __LINE__);                                       \
+  } while (0)
+
+#define SIB_LAUNCH_CHECK() SIB_CUDA(cudaGetLastError())
+
+int sm_count();
+
+// 2-D row-major bf16 matrix [rows][cols] (cols contiguous); box = box_rows x box_cols.
+// swizzle128: inner box extent must be 64 elements (128 bytes).
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
+                      uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols,
+                      bool swizzle128);
+
+// 3-D view used for the no-swizzle K-major "core matrix" layout:
+// dims (inner=8 elems, rows, kchunks) with strides (1, row_stride, 8) elements.
+int make_tmap_kchunk_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
+                          uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_kchunks);
+
+// im2col map over an NHWC bf16 tensor.  Base-pixel bounding box:
+//   lower = {lo_w, lo_h}, upper = {up_w, up_h}; traversal strides {sw, sh};
+// each load gathers `pixels` pixels x `channels` channels.
+int make_tmap_im2col_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, int C,
+                          int lo_w, int lo_h, int up_w, int up_h, int sw, int sh,
+                          uint32_t channels, uint32_t pixels, bool swizzle128);
+
+}  // namespace sib

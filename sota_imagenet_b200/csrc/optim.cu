@@ -1,0 +1,240 @@
+// Optimizer + weight packing kernels.
+//   * sib_sgd_step: coupled-L2 SGD with momentum / Nesterov over one flat fp32 parameter arena
+//     (torch/optim/sgd.py semantics, reference arg_parser.py:136-138: torch.optim._multi_tensor.SGD);
+//     one launch for all 161 tensors, also emits the bf16 copy the conv kernels read and an
+//     optional EMA stream (pt_clb.ModelEma, reference train.py:112).
+//   * sib_pack_dgrad_weights: table-driven repack of every conv filter from KRSC to the
+//     tap-flipped [C][R][S][K] layout the dgrad implicit GEMM consumes.
+//   * sib_weight_standardize: per-out-channel (w - mean) / sqrt(var + eps) (reference
+//     model.py:91-100 analogue of pytorch_tools conv_to_ws_conv, train.py:66-67).
+#include "common.cuh"
+#include "host.h"
+#include "../../include/sib200.h"
+
+namespace sib {
+
+// per-segment hyper-parameters: segment i covers elements [seg_end[i-1], seg_end[i])
+struct SgdSeg {
+  long end;
+  float lr, weight_decay, momentum, dampening;
+  int nesterov;
+  int pad;
+};
+
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+           __nv_bfloat16* __restrict__ p_bf16, float* __restrict__ ema, float ema_decay,
+           const SgdSeg* __restrict__ segs, int nseg, long n4, int first_step) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long)gridDim.x * blockDim.x) {
+    const long e = i * 4;
+    // segment lookup (few groups: linear scan)
+    int sidx = 0;
+    while (sidx + 1 < nseg && e >= segs[sidx].end) ++sidx;
+    const SgdSeg sg = segs[sidx];
+    float4 pv = *reinterpret_cast<float4*>(p + e);
+    const float4 gv = *reinterpret_cast<const float4*>(g + e);
+    float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+    float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+    float ba[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sg.momentum != 0.f && !first_step) {
+      const float4 bv = *reinterpret_cast<const float4*>(buf + e);
+      ba[0] = bv.x; ba[1] = bv.y; ba[2] = bv.z; ba[3] = bv.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float grad = ga[j] + sg.weight_decay * pa[j];
+      if (sg.momentum != 0.f) {
+        // first step: buf = grad (torch clones the gradient), afterwards buf = mu*buf + (1-damp)*grad
+        ba[j] = first_step ? grad : sg.momentum * ba[j] + (1.f - sg.dampening) * grad;
+        grad = sg.nesterov ? grad + sg.momentum * ba[j] : ba[j];
+      }
+      pa[j] -= sg.lr * grad;
+    }
+    *reinterpret_cast<float4*>(p + e) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    if (sg.momentum != 0.f)
+      *reinterpret_cast<float4*>(buf + e) = make_float4(ba[0], ba[1], ba[2], ba[3]);
+    if (p_bf16 != nullptr) {
+      uint2 o;
+      o.x = pack2(pa[0], pa[1]);
+      o.y = pack2(pa[2], pa[3]);
+      *reinterpret_cast<uint2*>(p_bf16 + e) = o;
+    }
+    if (ema != nullptr) {
+      float4 ev = *reinterpret_cast<float4*>(ema + e);
+      ev.x = ema_decay * ev.x + (1.f - ema_decay) * pa[0];
+      ev.y = ema_decay * ev.y + (1.f - ema_decay) * pa[1];
+      ev.z = ema_decay * ev.z + (1.f - ema_decay) * pa[2];
+      ev.w = ema_decay * ev.w + (1.f - ema_decay) * pa[3];
+      *reinterpret_cast<float4*>(ema + e) = ev;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long)gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
+    uint2 o;
+    o.x = pack2(v.x, v.y);
+    o.y = pack2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + i * 4) = o;
+  }
+}
+
+// one entry per conv filter
+struct PackEntry {
+  long src_off;    // element offset of the KRSC filter in the bf16 arena
+  long dst_off;    // element offset of the [C][R][S][K] flipped copy in the dgrad arena
+  int K, RS, C;
+  int block_begin; // first block of this entry
+};
+
+// 32x32 tile transpose per (tap): dst[c][RS-1-tap][k] = src[k][tap][c]
+__global__ void __launch_bounds__(256)
+pack_dgrad_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                  const PackEntry* __restrict__ tab, int nent) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  int lo = 0, hi = nent - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackEntry e = tab[lo];
+  int b = blockIdx.x - e.block_begin;
+  const int ct = (e.C + 31) / 32, kt = (e.K + 31) / 32;
+  const int tap = b / (ct * kt);
+  b -= tap * ct * kt;
+  const int k0 = (b / ct) * 32, c0 = (b % ct) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const __nv_bfloat16* s = src + e.src_off;
+  __nv_bfloat16* d = dst + e.dst_off;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, c = c0 + tx;
+    if (k < e.K && c < e.C) tile[r][tx] = s[((long)k * e.RS + tap) * e.C + c];
+  }
+  __syncthreads();
+  const int ftap = e.RS - 1 - tap;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, k = k0 + tx;
+    if (k < e.K && c < e.C) d[((long)c * e.RS + ftap) * e.K + k] = tile[tx][r];
+  }
+}
+
+// one CTA per output channel: w_std = (w - mean) / sqrt(var_biased + eps) * gain
+__global__ void __launch_bounds__(256)
+weight_std_kernel(const float* __restrict__ w, const float* __restrict__ gain,
+                  __nv_bfloat16* __restrict__ out, float* __restrict__ mean_invstd, int fan,
+                  float eps) {
+  __shared__ float sh[2][32];
+  const long o = blockIdx.x;
+  float s = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < fan; i += blockDim.x) {
+    const float v = w[o * fan + i];
+    s += v;
+    s2 += v * v;
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  s = 0.f; s2 = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) { s += sh[0][i]; s2 += sh[1][i]; }
+  const float mean = s / fan;
+  const float var = fmaxf(s2 / fan - mean * mean, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  const float gn = gain ? gain[o] : 1.f;
+  if (threadIdx.x == 0 && mean_invstd) { mean_invstd[2 * o] = mean; mean_invstd[2 * o + 1] = invstd; }
+  for (int i = threadIdx.x; i < fan; i += blockDim.x)
+    out[o * fan + i] = __float2bfloat16_rn((w[o * fan + i] - mean) * invstd * gn);
+}
+
+// backward of weight standardisation: dw = invstd*gain * (g - mean(g) - what * mean(g*what))
+__global__ void __launch_bounds__(256)
+weight_std_bwd_kernel(const float* __restrict__ w, const float* __restrict__ gain,
+                      const float* __restrict__ mean_invstd, const float* __restrict__ g,
+                      float* __restrict__ dw, int fan) {
+  __shared__ float sh[2][32];
+  const long o = blockIdx.x;
+  const float mean = mean_invstd[2 * o], invstd = mean_invstd[2 * o + 1];
+  float s = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < fan; i += blockDim.x) {
+    const float gv = g[o * fan + i];
+    const float wh = (w[o * fan + i] - mean) * invstd;
+    s += gv;
+    s2 += gv * wh;
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  s = 0.f; s2 = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) { s += sh[0][i]; s2 += sh[1][i]; }
+  const float gn = gain ? gain[o] : 1.f;
+  for (int i = threadIdx.x; i < fan; i += blockDim.x) {
+    const float wh = (w[o * fan + i] - mean) * invstd;
+    dw[o * fan + i] = gn * invstd * (g[o * fan + i] - s / fan - wh * s2 / fan);
+  }
+}
+
+static inline int ew_grid(long n, int threads) {
+  long b = (n + threads - 1) / threads;
+  long cap = (long)sm_count() * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace sib
+
+using namespace sib;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+// segs_dev: device array of nseg records {long end; float lr, wd, momentum, dampening; int nesterov, pad}
+extern "C" int sib_sgd_step(float* params, const float* grads, float* momentum_buf,
+                            void* params_bf16, float* ema, float ema_decay, const void* segs_dev,
+                            int nseg, long n, int first_step, void* stream) {
+  SIB_CHECK(n % 4 == 0, "sgd: arena length must be a multiple of 4 (pad the arena)");
+  SIB_CHECK(nseg >= 1, "sgd: need at least one segment");
+  const long n4 = n / 4;
+  sgd_kernel<<<ew_grid(n4, 256), 256, 0, ST(stream)>>>(
+      params, grads, momentum_buf, static_cast<__nv_bfloat16*>(params_bf16), ema, ema_decay,
+      static_cast<const SgdSeg*>(segs_dev), nseg, n4, first_step);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_cast_bf16(const float* src, void* dst, long n, void* stream) {
+  SIB_CHECK(n % 4 == 0, "cast: length must be a multiple of 4");
+  cast_bf16_kernel<<<ew_grid(n / 4, 256), 256, 0, ST(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n / 4);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// table_dev: device array of nent records {long src_off, dst_off; int K, RS, C, block_begin}
+extern "C" int sib_pack_dgrad_weights(const void* w_bf16, void* w_dgrad, const void* table_dev,
+                                      int nent, int total_blocks, void* stream) {
+  if (nent == 0 || total_blocks == 0) return 0;
+  pack_dgrad_kernel<<<total_blocks, 256, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(w_bf16), static_cast<__nv_bfloat16*>(w_dgrad),
+      static_cast<const PackEntry*>(table_dev), nent);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_weight_standardize(const float* w, const float* gain, void* out_bf16,
+                                      float* mean_invstd, int out_channels, int fan, float eps,
+                                      void* stream) {
+  weight_std_kernel<<<out_channels, 256, 0, ST(stream)>>>(
+      w, gain, static_cast<__nv_bfloat16*>(out_bf16), mean_invstd, fan, eps);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_weight_standardize_bwd(const float* w, const float* gain,
+                                          const float* mean_invstd, const float* g, float* dw,
+                                          int out_channels, int fan, void* stream) {
+  weight_std_bwd_kernel<<<out_channels, 256, 0, ST(stream)>>>(w, gain, mean_invstd, g, dw, fan);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}

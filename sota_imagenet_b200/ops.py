@@ -1,0 +1,349 @@
+"""Functional wrappers: torch tensors in, C-ABI kernel launches on the current stream.
+
+Activations are torch tensors of logical shape [N, C, H, W], dtype bfloat16, in
+torch.channels_last memory format (= NHWC in memory).  Conv filters are [K, C, R, S]
+channels_last (= KRSC in memory).  PyTorch is only the allocator / stream provider here.
+"""
+import torch
+
+from . import _lib
+from ._lib import c_void_p, call
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+MARGIN_NONE, MARGIN_ARC, MARGIN_COS = 0, 1, 2
+FLAG_FORCE_IM2COL = 1
+ACT_CODES = {None: ACT_NONE, "identity": ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU,
+             "leaky_relu": ACT_LEAKY}
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_act(t, name="activation"):
+    if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
+        raise _lib.SibError("%s must be a 4-D CUDA bfloat16 tensor, got %s %s" % (name, t.dtype, tuple(t.shape)))
+    if not t.permute(0, 2, 3, 1).is_contiguous():
+        raise _lib.SibError("%s must be channels_last (NHWC) contiguous" % name)
+
+
+def new_act(n, c, h, w, device, dtype=torch.bfloat16):
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def to_nhwc_bf16(x):
+    """Any float NCHW tensor -> channels_last bf16 (a torch copy; test / glue use only)."""
+    n, c, h, w = x.shape
+    out = new_act(n, c, h, w, x.device)
+    out.copy_(x)
+    return out
+
+
+def conv_out_hw(h, w, r, s, stride, pad):
+    return (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
+
+
+# ------------------------------------------------------------------ convolution
+def conv2d_fprop(x, w, stride=1, pad=0, stats=None, bias=None, flags=0, pad_hw=None, out_hw=None):
+    _lib.require_device()
+    _check_act(x, "x")
+    n, c, h, wd = x.shape
+    k, c2, r, s = w.shape
+    assert c2 == c, "filter/input channel mismatch"
+    ph, pw = pad_hw if pad_hw is not None else (pad, pad)
+    oh, ow = out_hw if out_hw is not None else conv_out_hw(h, wd, r, s, stride, pad)
+    y = new_act(n, k, oh, ow, x.device)
+    call("sib_conv2d_fprop", _p(x), _p(w), _p(y), n, h, wd, c, k, r, s, stride, ph, pw, oh, ow,
+         _p(bias), _p(stats), flags, _stream())
+    return y
+
+
+def conv2d_dgrad(dy, w_dgrad, x_shape, r, s, stride=1, pad=0, out=None, accumulate=False, flags=0):
+    """dx for conv(x, w); `w_dgrad` is the [C][R][S][K] flipped pack of w."""
+    _lib.require_device()
+    _check_act(dy, "dy")
+    n, c, h, wd = x_shape
+    k = dy.shape[1]
+    if out is None:
+        assert not accumulate
+        if stride > 1 and r == 1:
+            out = torch.zeros((n, h, wd, c), dtype=torch.bfloat16, device=dy.device).permute(0, 3, 1, 2)
+            accumulate = True
+        else:
+            out = new_act(n, c, h, wd, dy.device)
+    if stride == 1 or (r == 1 and s == 1):
+        call("sib_conv2d_dgrad", _p(dy), _p(w_dgrad), _p(out), n, h, wd, c, k, r, s, stride, pad,
+             int(accumulate), flags, _stream())
+    else:
+        oh, ow = dy.shape[2], dy.shape[3]
+        uh, uw = (oh - 1) * stride + 1, (ow - 1) * stride + 1
+        ws = torch.empty((n, uh, uw, k), dtype=torch.bfloat16, device=dy.device)
+        call("sib_conv2d_dgrad_strided", _p(dy), _p(w_dgrad), _p(out), _p(ws), n, h, wd, c, k, r, s,
+             stride, pad, int(accumulate), flags, _stream())
+    return out
+
+
+def conv2d_wgrad(x, dy, dw, stride=1, pad=0, flags=0, pad_hw=None):
+    """dw[K][R][S][C] (fp32, channels_last view of [K,C,R,S]) += wgrad(x, dy)."""
+    _lib.require_device()
+    _check_act(x, "x")
+    _check_act(dy, "dy")
+    n, c, h, wd = x.shape
+    k, c2, r, s = dw.shape
+    assert c2 == c and dy.shape[1] == k
+    assert dw.dtype == torch.float32 and dw.permute(0, 2, 3, 1).is_contiguous()
+    ph, pw = pad_hw if pad_hw is not None else (pad, pad)
+    call("sib_conv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, wd, c, k, r, s, stride, ph, pw,
+         dy.shape[2], dy.shape[3], flags, _stream())
+    return dw
+
+
+def pack_dgrad_weight(w):
+    """Single-filter helper (tests / generic modules): KRSC bf16 -> flipped [C][R][S][K]."""
+    k, c, r, s = w.shape
+    src = w.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty((c, r, s, k), dtype=torch.bfloat16, device=w.device)
+    table = pack_table([(0, 0, k, r * s, c)], w.device)
+    call("sib_pack_dgrad_weights", _p(src), _p(out), _p(table[0]), 1, table[1], _stream())
+    return out
+
+
+def pack_table(entries, device):
+    """entries: (src_off, dst_off, K, RS, C) -> (device table, total_blocks)."""
+    import numpy as np
+    rec = np.zeros(len(entries), dtype=np.dtype([("src", "<i8"), ("dst", "<i8"), ("K", "<i4"),
+                                                 ("RS", "<i4"), ("C", "<i4"), ("bb", "<i4")]))
+    blocks = 0
+    for i, (so, do, k, rs, c) in enumerate(entries):
+        rec[i] = (so, do, k, rs, c, blocks)
+        blocks += rs * ((k + 31) // 32) * ((c + 31) // 32)
+    t = torch.from_numpy(rec.view(np.uint8).copy()).to(device)
+    return t, blocks
+
+
+# ------------------------------------------------------------------ batch norm family
+def bn_stats(x):
+    _check_act(x)
+    n, c, h, w = x.shape
+    stats = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    call("sib_bn_stats", _p(x), n * h * w, c, _p(stats), _stream())
+    return stats
+
+
+def bn_finalize(stats, gamma, beta, running_mean, running_var, count, eps, momentum):
+    c = stats.shape[1]
+    mean_invstd = torch.empty((2, c), dtype=torch.float32, device=stats.device)
+    scale_shift = torch.empty((2, c), dtype=torch.float32, device=stats.device)
+    call("sib_bn_finalize", _p(stats), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+         _p(mean_invstd), _p(scale_shift), c, float(count), float(eps), float(momentum), _stream())
+    return mean_invstd, scale_shift
+
+
+def bn_eval_scale(gamma, beta, running_mean, running_var, eps):
+    c = running_mean.shape[0]
+    scale_shift = torch.empty((2, c), dtype=torch.float32, device=running_mean.device)
+    call("sib_bn_eval_scale", _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+         _p(scale_shift), c, float(eps), _stream())
+    return scale_shift
+
+
+def bn_apply(x, scale_shift, act=ACT_NONE, slope=0.01, res=None, scale_shift2=None, out=None):
+    _check_act(x)
+    n, c, h, w = x.shape
+    y = out if out is not None else new_act(n, c, h, w, x.device)
+    call("sib_bn_apply", _p(x), _p(scale_shift), _p(res), _p(scale_shift2), _p(y), n * h * w, c,
+         act, float(slope), _stream())
+    return y
+
+
+def bn_bwd_reduce(dy, out, x, mean_invstd, act, slope=0.01, x2=None, mean_invstd2=None):
+    n, c, h, w = x.shape
+    sums = torch.empty((4 if x2 is not None else 2, c), dtype=torch.float32, device=x.device)
+    call("sib_bn_bwd_reduce", _p(dy), _p(out), _p(x), _p(mean_invstd), _p(x2), _p(mean_invstd2),
+         n * h * w, c, act, float(slope), _p(sums), _stream())
+    return sums
+
+
+def bn_bwd_apply(dy, out, x, mean_invstd, gamma, sums, count, act, slope=0.01, x2=None,
+                 mean_invstd2=None, gamma2=None, want_g=False, dx_out=None):
+    n, c, h, w = x.shape
+    dx = dx_out if dx_out is not None else new_act(n, c, h, w, x.device)
+    dx2 = new_act(n, c, h, w, x.device) if x2 is not None else None
+    g = new_act(n, c, h, w, x.device) if want_g else None
+    call("sib_bn_bwd_apply", _p(dy), _p(out), _p(x), _p(mean_invstd), _p(gamma), _p(sums), _p(x2),
+         _p(mean_invstd2), _p(gamma2), _p(dx), _p(dx2), _p(g), n * h * w, c, float(count), act,
+         float(slope), _stream())
+    return dx, dx2, g
+
+
+def bn_param_grad(sums, dgamma, dbeta, accumulate=True):
+    c = sums.shape[1]
+    call("sib_bn_param_grad", _p(sums), _p(dgamma), _p(dbeta), c, int(accumulate), _stream())
+
+
+# ------------------------------------------------------------------ pooling
+def maxpool3x3s2_fwd(x, want_idx=True):
+    _check_act(x)
+    n, c, h, w = x.shape
+    oh, ow = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    y = new_act(n, c, oh, ow, x.device)
+    idx = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    call("sib_maxpool3x3s2_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
+    return y, idx
+
+
+def maxpool3x3s2_bwd(dy, idx, x_shape):
+    n, c, h, w = x_shape
+    dx = new_act(n, c, h, w, dy.device)
+    call("sib_maxpool3x3s2_bwd", _p(dy), _p(idx), _p(dx), n, h, w, c, _stream())
+    return dx
+
+
+def gap_fwd(x):
+    _check_act(x)
+    n, c, h, w = x.shape
+    y = new_act(n, c, 1, 1, x.device)
+    call("sib_gap_fwd", _p(x), _p(y), n, h * w, c, _stream())
+    return y
+
+
+def gap_bwd(dy, x_shape):
+    n, c, h, w = x_shape
+    dx = new_act(n, c, h, w, dy.device)
+    call("sib_gap_bwd", _p(dy), _p(dx), n, h * w, c, _stream())
+    return dx
+
+
+# ------------------------------------------------------------------ heads
+def ce_fwd_bwd(logits, target, smoothing=0.0, temperature=1.0, margin_kind=MARGIN_NONE, s=1.0,
+               m=0.0, want_grad=True, grad_scale=1.0):
+    """Returns (mean loss [0-dim fp32], per-row loss, dlogits or None)."""
+    _lib.require_device()
+    assert logits.dim() == 2 and logits.is_cuda and logits.stride(1) == 1
+    b, c = logits.shape
+    fp32 = logits.dtype == torch.float32
+    if not fp32 and logits.dtype != torch.bfloat16:
+        raise _lib.SibError("logits must be float32 or bfloat16")
+    labels = dense = None
+    if target.dim() == 1:
+        labels = target.to(torch.int64).contiguous()
+    else:
+        dense = target.to(torch.float32).contiguous()
+    loss_rows = torch.empty((b,), dtype=torch.float32, device=logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits) if want_grad else None
+    call("sib_ce_fwd_bwd", _p(logits), int(fp32), _p(labels), _p(dense), b, c, logits.stride(0),
+         float(smoothing), float(temperature), margin_kind, float(s), float(m), _p(loss_rows),
+         _p(loss), _p(dlogits), float(grad_scale), _stream())
+    return loss, loss_rows, dlogits
+
+
+def sphere_linear_fwd(x, w, normalize_x=True):
+    b, d = x.shape
+    c = w.shape[0]
+    dev = x.device
+    cosv = torch.empty((b, c), dtype=torch.float32, device=dev)
+    xn = torch.empty_like(x) if normalize_x else None
+    wn = torch.empty_like(w)
+    xnorm = torch.empty((b,), dtype=torch.float32, device=dev) if normalize_x else None
+    wnorm = torch.empty((c,), dtype=torch.float32, device=dev)
+    call("sib_sphere_linear_fwd", _p(x), _p(w), _p(cosv), _p(xn), _p(wn), _p(xnorm), _p(wnorm), b,
+         c, d, int(normalize_x), _stream())
+    return cosv, (xn if normalize_x else x, wn, xnorm, wnorm)
+
+
+def sphere_linear_bwd(dcos, saved, need_dx=True, need_dw=True, normalize_x=True):
+    xn, wn, xnorm, wnorm = saved
+    b, d = xn.shape
+    c = wn.shape[0]
+    dx = torch.empty_like(xn) if need_dx else None
+    dw = torch.empty_like(wn) if need_dw else None
+    scratch = torch.empty((max(b, c), d), dtype=torch.float32, device=xn.device)
+    call("sib_sphere_linear_bwd", _p(dcos), _p(xn), _p(wn), _p(xnorm), _p(wnorm), _p(dx), _p(dw),
+         _p(scratch), b, c, d, int(normalize_x), _stream())
+    return dx, dw
+
+
+# ------------------------------------------------------------------ optimizer helpers
+def sgd_segments(records, device):
+    """records: (end, lr, weight_decay, momentum, dampening, nesterov) -> device byte tensor."""
+    import numpy as np
+    rec = np.zeros(len(records), dtype=np.dtype([("end", "<i8"), ("lr", "<f4"), ("wd", "<f4"),
+                                                 ("mom", "<f4"), ("damp", "<f4"), ("nest", "<i4"),
+                                                 ("pad", "<i4")]))
+    for i, r in enumerate(records):
+        rec[i] = (r[0], r[1], r[2], r[3], r[4], int(r[5]), 0)
+    return torch.from_numpy(rec.view(np.uint8).copy()).to(device, non_blocking=True)
+
+
+def sgd_step(params, grads, buf, params_bf16, segs, nseg, first_step, ema=None, ema_decay=0.0):
+    call("sib_sgd_step", _p(params), _p(grads), _p(buf), _p(params_bf16), _p(ema), float(ema_decay),
+         _p(segs), nseg, params.numel(), int(first_step), _stream())
+
+
+def cast_bf16(src, dst):
+    call("sib_cast_bf16", _p(src), _p(dst), src.numel(), _stream())
+
+
+# ------------------------------------------------------------------ data
+def rrc_boxes(batch, h, w, min_area, max_area, seed, first_sample, do_flip, device):
+    boxes = torch.empty((batch, 5), dtype=torch.int32, device=device)
+    call("sib_rrc_boxes", _p(boxes), batch, h, w, float(min_area), float(max_area), int(seed),
+         int(first_sample), int(do_flip), _stream())
+    return boxes
+
+
+def rrc_box_host(h, w, min_area, max_area, seed, sample):
+    import ctypes
+    box = (ctypes.c_int * 5)()
+    _lib.load().sib_rrc_box_host(h, w, float(min_area), float(max_area), int(seed), int(sample), box)
+    return list(box)
+
+
+def augment(src_u8, boxes, size, mean=127.5, std=51.0, out_mode=0):
+    b, sh, sw, ch = src_u8.shape
+    assert ch == 3 and src_u8.dtype == torch.uint8 and src_u8.is_contiguous()
+    if out_mode == 0:
+        out = new_act(b, 4, size, size, src_u8.device)
+    else:
+        out = torch.empty((b, 3, size, size), dtype=torch.float32, device=src_u8.device)
+    call("sib_augment", _p(src_u8), _p(boxes), _p(out), b, sh, sw, size, float(mean), float(std),
+         out_mode, _stream())
+    return out
+
+
+def one_hot(labels, num_classes):
+    out = torch.empty((labels.shape[0], num_classes), dtype=torch.float32, device=labels.device)
+    call("sib_one_hot", _p(labels), _p(out), labels.shape[0], num_classes, _stream())
+    return out
+
+
+def stem_pack(x, kw, pad_w):
+    """[N,3,H,W] fp32 NCHW or [N,4,H,W] bf16 channels_last -> [N,64,H/2,W/2] packed rows."""
+    n, c, h, w = x.shape
+    if x.dtype == torch.float32 and c == 3 and x.is_contiguous():
+        mode = 1
+    elif x.dtype == torch.bfloat16 and c == 4 and x.permute(0, 2, 3, 1).is_contiguous():
+        mode = 0
+    else:
+        raise _lib.SibError("stem input must be fp32 NCHW [N,3,H,W] or bf16 channels_last [N,4,H,W]")
+    xq = new_act(n, 64, h // 2, w // 2, x.device)
+    call("sib_stem_pack", _p(x), _p(xq), n, h, w, kw, pad_w, mode, _stream())
+    return xq
+
+
+def stem_pack_weight(w, na, off, out=None):
+    k, c, kh, kw = w.shape
+    assert c == 3 and w.is_contiguous() and w.dtype == torch.float32
+    wq = out if out is not None else torch.empty((k, na, 1, 64), dtype=torch.bfloat16, device=w.device)
+    call("sib_stem_pack_weight", _p(w), _p(wq), k, kh, kw, na, off, _stream())
+    return wq
+
+
+def stem_unpack_wgrad(dwq, dw, na, off, accumulate=True):
+    k, c, kh, kw = dw.shape
+    call("sib_stem_unpack_wgrad", _p(dwq), _p(dw), k, kh, kw, na, off, int(accumulate), _stream())
