@@ -1,0 +1,126 @@
+"""Flat parameter arena: one fp32 buffer for all parameters of a model (plus gradient, bf16
+shadow and dgrad-packed filter buffers), with the nn.Parameters re-pointed at views of it.
+
+Why: the fused SGD kernel updates all 161 ResNet-50 tensors in one launch and refreshes the
+bf16 filters the conv kernels read (reference path: torch.optim._multi_tensor.SGD foreach
+launches, arg_parser.py:136-138); gradient buckets for the data-parallel all-reduce are
+contiguous slices of the gradient buffer.
+"""
+import torch
+
+from . import ops
+
+ALIGN = 128  # elements; keeps every tensor 256B (bf16) / 512B (fp32) aligned for TMA
+
+
+def _round_up(n, a=ALIGN):
+    return (n + a - 1) // a * a
+
+
+class ParamArena:
+    def __init__(self, named_params, device):
+        self.device = device
+        self.entries = []   # (name, param, offset, numel, layout)
+        off = 0
+        for name, p in named_params:
+            layout = getattr(p, "_sib_layout", "plain")
+            self.entries.append((name, p, off, p.numel(), layout))
+            off += _round_up(p.numel())
+        self.total = max(off, ALIGN)
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.shadow = torch.zeros(self.total, dtype=torch.bfloat16, device=device)
+        self.momentum = None       # allocated by the optimizer
+        self.ema = None
+        self.offset_of = {}
+        # dgrad-pack arena for conv filters that need a data gradient
+        pack_entries, doff = [], 0
+        self.dgrad_offset = {}
+        for name, p, o, n, layout in self.entries:
+            view = self.view_of(self.flat, o, p.shape, layout)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.view_of(self.grad, o, p.shape, layout)
+            p._sib_arena = self
+            p._sib_offset = o
+            self.offset_of[id(p)] = o
+            if layout == "krsc" and getattr(p, "_sib_needs_dgrad", False):
+                k, c, r, s = p.shape
+                pack_entries.append((o, doff, k, r * s, c))
+                self.dgrad_offset[id(p)] = doff
+                doff += _round_up(n)
+        self.wdgrad = torch.zeros(max(doff, ALIGN), dtype=torch.bfloat16, device=device)
+        self.pack_table, self.pack_blocks = ops.pack_table(pack_entries, device)
+        self.pack_count = len(pack_entries)
+        self._sig = None
+
+    @staticmethod
+    def view_of(buf, off, shape, layout):
+        n = 1
+        for d in shape:
+            n *= d
+        flat = buf[off:off + n]
+        if layout == "krsc" and len(shape) == 4:
+            k, c, r, s = shape
+            return flat.view(k, r, s, c).permute(0, 3, 1, 2)
+        return flat.view(shape)
+
+    # ---- bf16 shadow maintenance -------------------------------------------------
+    def signature(self):
+        return sum(p._version for _, p, _, _, _ in self.entries)
+
+    def refresh_shadow(self, force=False):
+        """Recast fp32 -> bf16 + repack dgrad filters when parameters were modified by anything
+        other than the fused optimizer (load_state_dict, init, a foreign optimizer)."""
+        sig = self.signature()
+        if force or sig != self._sig:
+            ops.cast_bf16(self.flat, self.shadow)
+            self.repack_dgrad()
+            self._sig = sig
+
+    def repack_dgrad(self):
+        if self.pack_count:
+            ops.call("sib_pack_dgrad_weights", ops._p(self.shadow), ops._p(self.wdgrad),
+                     ops._p(self.pack_table), self.pack_count, self.pack_blocks, ops._stream())
+
+    def mark_fresh(self):
+        """Called by the fused optimizer after it rewrote params + shadow itself."""
+        self.repack_dgrad()
+        self._sig = self.signature()
+
+    def shadow_view(self, p):
+        o = self.offset_of[id(p)]
+        return self.view_of(self.shadow, o, p.shape, getattr(p, "_sib_layout", "plain"))
+
+    def dgrad_view(self, p):
+        k, c, r, s = p.shape
+        o = self.dgrad_offset[id(p)]
+        return self.wdgrad[o:o + p.numel()].view(c, r, s, k)
+
+    def grad_view(self, p):
+        o = self.offset_of[id(p)]
+        return self.view_of(self.grad, o, p.shape, getattr(p, "_sib_layout", "plain"))
+
+    # ---- gradient bookkeeping ------------------------------------------------------
+    def prepare_grads(self):
+        """Start of a backward pass: if grads were dropped (zero_grad(set_to_none=True)) clear the
+        flat buffer with one memset and re-attach the views; otherwise keep accumulating."""
+        first = self.entries[0][1]
+        if first.grad is None:
+            self.grad.zero_()
+            for _, p, o, _, layout in self.entries:
+                p.grad = self.view_of(self.grad, o, p.shape, layout)
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for _, p, o, _, layout in self.entries:
+            if p.grad is None:
+                p.grad = self.view_of(self.grad, o, p.shape, layout)
+
+    def intact(self):
+        """True while every parameter still aliases the arena (a later .to()/.cuda() breaks it)."""
+        base = self.flat.data_ptr()
+        for _, p, o, _, _ in self.entries:
+            if p.data_ptr() != base + 4 * o:
+                return False
+        return True

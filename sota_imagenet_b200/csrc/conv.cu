@@ -403,13 +403,15 @@ static int run_igemm(const void* in, const void* w, void* out, int N, int IH, in
                      int OH, int OW,
                      int ostride, int accumulate, const float* bias, float* stats, int flags,
                      cudaStream_t stream) {
-  SIB_CHECK(Cin % 64 == 0, "igemm: Cin must be a multiple of 64 (got %d)", Cin);
+  // 1x1 filters may have a ragged K: TMA zero-fills both operands past Cin
+  SIB_CHECK(Cin % 64 == 0 || (R == 1 && S == 1 && Cin % 8 == 0),
+            "igemm: Cin must be a multiple of 64 (or of 8 for 1x1 filters), got %d", Cin);
   SIB_CHECK(Cout % 8 == 0, "igemm: Cout must be a multiple of 8 (got %d)", Cout);
   SIB_CHECK((long)N * TH * TW < (1l << 31), "igemm: too many pixels");
   IgemmParams p{};
   p.M_total = N * TH * TW;
   p.Cout = Cout;
-  p.cin_blocks = Cin / 64;
+  p.cin_blocks = (Cin + 63) / 64;
   p.num_kblocks = R * S * p.cin_blocks;
   p.S = S;
   p.trav_hw = TH * TW;
