@@ -31,6 +31,7 @@ extern "C" {
 #define SIB_MARGIN_NONE 0
 #define SIB_MARGIN_ARC 1 /* AdditiveAngularMarginLoss, angular_losses.py:128-146 */
 #define SIB_MARGIN_COS 2 /* CosFace, angular_losses.py:186-198 and :332-333      */
+#define SIB_MARGIN_ARC_PURE 3 /* cos(theta + m) without fallback, angular_losses.py:78-83 */
 
 /* conv flags */
 #define SIB_FLAG_FORCE_IM2COL 1 /* use the im2col TMA path even for plain 1x1 (testing) */

@@ -1,0 +1,107 @@
+"""numpy restatement of the train-pipeline augmentation (reference dali_dataloader.py:65-74
+image_random_crop with random_aspect_ratio=[0.75,1.25], random_area=[min_area,1], 100 attempts;
+:74 resize to SxS INTERP_TRIANGULAR; :113-122 crop_mirror_normalize mean 127.5 std 51, coin
+flip; :123 one_hot).  DALI itself is absent (closed GPU library) so its RNG stream cannot be
+reproduced; the crop RNG is specified here as Philox4x32-10 keyed by (seed, sample index) and
+the CUDA kernel must match it bit-exactly.  Parity unpinned by the reference (no DALI vectors).
+"""
+import math
+
+import numpy as np
+
+M32 = 0xFFFFFFFF
+LOG_R_LO = -0.2876820724517809   # ln 0.75
+LOG_R_HI = 0.22314355131420976   # ln 1.25
+
+
+def philox4x32_10(counter, key):
+    c0, c1, c2, c3 = [int(c) & M32 for c in counter]
+    k0, k1 = [int(k) & M32 for k in key]
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        n0 = ((p1 >> 32) ^ c1 ^ k0) & M32
+        n1 = p1 & M32
+        n2 = ((p0 >> 32) ^ c3 ^ k1) & M32
+        n3 = p0 & M32
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + 0x9E3779B9) & M32
+        k1 = (k1 + 0xBB67AE85) & M32
+    return c0, c1, c2, c3
+
+
+def rrc_box(H, W, min_area, max_area, seed, sample):
+    """-> [x0, y0, w, h, flip] (dali_dataloader.py:65-72 crop, :113-116 mirror coin)."""
+    key = (seed & M32, (seed >> 32) & M32)
+    s0, s1 = sample & M32, (sample >> 32) & M32
+    box = None
+    for attempt in range(100):
+        r = philox4x32_10((s0, s1, attempt, 0), key)
+        ua = r[0] * (1.0 / 4294967296.0)
+        ur = r[1] * (1.0 / 4294967296.0)
+        area = (min_area + (max_area - min_area) * ua) * float(H) * float(W)
+        ratio = math.exp(LOG_R_LO + (LOG_R_HI - LOG_R_LO) * ur)
+        w = int(math.floor(math.sqrt(area * ratio) + 0.5))
+        h = int(math.floor(math.sqrt(area / ratio) + 0.5))
+        if 0 < w <= W and 0 < h <= H:
+            box = [r[2] % (W - w + 1), r[3] % (H - h + 1), w, h]
+            break
+    if box is None:
+        in_ratio = W / H
+        if in_ratio < 0.75:
+            w, h = W, int(math.floor(W / 0.75 + 0.5))
+        elif in_ratio > 1.25:
+            h, w = H, int(math.floor(H * 1.25 + 0.5))
+        else:
+            w, h = W, H
+        h, w = min(h, H), min(w, W)
+        box = [(W - w) // 2, (H - h) // 2, w, h]
+    r = philox4x32_10((s0, s1, 100, 1), key)
+    return box + [r[0] & 1]
+
+
+def _tri_weights(out_size, crop, flip):
+    """Per output index: list of (source index inside crop, weight) for the triangular filter
+    whose support scales with the down-scale factor (anti-aliased bilinear)."""
+    f32 = np.float32
+    scale = f32(crop) / f32(out_size)
+    sup = max(scale, f32(1.0))
+    taps = []
+    for o in range(out_size):
+        so = (out_size - 1 - o) if flip else o
+        c = (f32(so) + f32(0.5)) * scale
+        lo = int(math.floor(c - sup))
+        hi = int(math.ceil(c + sup))
+        row = []
+        for i in range(lo, hi):
+            w = max(f32(0.0), f32(1.0) - abs((f32(i) + f32(0.5) - c) / sup))
+            if w > 0:
+                row.append((min(max(i, 0), crop - 1), f32(w)))
+        taps.append(row)
+    return taps
+
+
+def augment_image(img, box, size, mean=127.5, std=51.0):
+    """img uint8 [H,W,3] -> float32 [size,size,3] normalised (before bf16 rounding)."""
+    x0, y0, cw, ch, flip = box
+    tx = _tri_weights(size, cw, flip)
+    ty = _tri_weights(size, ch, False)
+    crop = img[y0:y0 + ch, x0:x0 + cw].astype(np.float32)
+    out = np.zeros((size, size, 3), np.float32)
+    for oy in range(size):
+        for ox in range(size):
+            acc = np.zeros(3, np.float64)
+            ws = 0.0
+            for (sy, wy) in ty[oy]:
+                for (sx, wx) in tx[ox]:
+                    w = float(wx) * float(wy)
+                    acc += w * crop[sy, sx]
+                    ws += w
+            out[oy, ox] = (acc / ws - mean) / std
+    return out
+
+
+def one_hot(labels, num_classes):
+    out = np.zeros((len(labels), num_classes), np.float32)
+    out[np.arange(len(labels)), labels] = 1.0
+    return out

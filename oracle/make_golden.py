@@ -1,0 +1,149 @@
+"""Generate tests/golden/*.pt by running the REFERENCE's own code (angular_losses.py,
+torch.optim SGD, torch CrossEntropyLoss) and the oracle restatements on seeded inputs.
+Run in the build container (needs /root/reference):  python -m oracle.make_golden
+"""
+import os
+
+import numpy as np
+import torch
+
+from oracle import augment_ref, torch_ref
+from oracle.reference_stub import load_reference_modules
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def heads():
+    ang, _, RefCE = load_reference_modules()
+    torch.manual_seed(0)
+    b, d, c = 16, 64, 40
+    x = torch.randn(b, d)
+    w = torch.randn(c, d)
+    y = torch.randint(0, c, (b,))
+    out = {"x": x, "w": w, "y": y}
+    # SphereLinearLayer + AdditiveAngularMarginLoss (ArcFace), reference classes
+    layer = ang.SphereLinearLayer(d, c)
+    layer.weight.data.copy_(w)
+    for name, crit in (
+        ("arc", ang.AdditiveAngularMarginLoss(final_criterion=RefCE(smoothing=0.1), s=10.0, m=0.2)),
+        ("arc_s64", ang.AdditiveAngularMarginLoss(final_criterion=RefCE(), s=64.0, m=0.5)),
+        ("adacos_fixed", ang.AdaCos(final_criterion=RefCE(smoothing=0.1), margin=0.2, fixed_s=10)),
+    ):
+        xr = x.clone().requires_grad_(True)
+        layer.weight.grad = None
+        cos = layer(xr)
+        loss = crit(cos, y)
+        loss.backward()
+        out[name] = {"cos": cos.detach(), "loss": loss.detach(), "dx": xr.grad.clone(),
+                     "dw": layer.weight.grad.clone()}
+    # LargeMarginCosineLoss owns W, normalises only W
+    lm = ang.LargeMarginCosineLoss(d, c, s=30.0, m=0.4)
+    lm.weight.data.copy_(w)
+    xn = torch.nn.functional.normalize(x).requires_grad_(True)
+    loss = lm(xn, y)
+    loss.backward()
+    out["cosface_lm"] = {"xn": xn.detach().clone(), "loss": loss.detach(), "dx": xn.grad.clone(),
+                         "dw": lm.weight.grad.clone()}
+    # AngularPenaltySMLoss arcface / cosface
+    for lt in ("arcface", "cosface"):
+        ap = ang.AngularPenaltySMLoss(d, c, loss_type=lt)
+        ap.weight.data.copy_(w)
+        xr = x.clone().requires_grad_(True)
+        loss = ap(xr, y)
+        loss.backward()
+        out["aps_" + lt] = {"loss": loss.detach(), "dx": xr.grad.clone(), "dw": ap.weight.grad.clone()}
+    # adaptive AdaCos: three steps of the running statistics
+    ada = ang.AdaCos(final_criterion=RefCE(smoothing=0.1), margin=0.1)
+    trace = []
+    for step in range(3):
+        xr = (x * (1 + 0.1 * step)).requires_grad_(True)
+        loss = ada(layer(xr), y)
+        trace.append({"loss": loss.detach(), "s": float(ada.prev_s), "B": float(ada.running_B),
+                      "cos": float(ada.running_cos)})
+    out["adacos_adaptive"] = trace
+    # restatements must agree with the reference classes
+    cos = torch_ref.sphere_linear(x, w)
+    l_arc = torch_ref.smooth_cross_entropy(torch_ref.arcface_logits(cos, y, 10.0, 0.2), y, 0.1)
+    assert torch.allclose(l_arc, out["arc"]["loss"], atol=1e-6), (l_arc, out["arc"]["loss"])
+    l_cos = torch_ref.smooth_cross_entropy(torch_ref.cosface_logits(cos, y, 10.0, 0.2), y, 0.1)
+    assert torch.allclose(l_cos, out["adacos_fixed"]["loss"], atol=1e-6)
+    torch.save(out, os.path.join(OUT, "heads.pt"))
+
+
+def cross_entropy():
+    torch.manual_seed(1)
+    b, c = 12, 50
+    logits = torch.randn(b, c) * 3
+    y = torch.randint(0, c, (b,))
+    soft = torch.softmax(torch.randn(b, c), 1)
+    out = {"logits": logits, "y": y, "soft": soft, "cases": []}
+    for sm, temp in ((0.0, 1.0), (0.1, 1.0), (0.1, 0.15)):
+        lr = logits.clone().requires_grad_(True)
+        loss = torch_ref.smooth_cross_entropy(lr, y, sm, temp)
+        loss.backward()
+        if temp == 1.0:   # anchor the restatement on torch.nn.CrossEntropyLoss
+            ref = torch.nn.functional.cross_entropy(logits, y, label_smoothing=sm)
+            assert torch.allclose(loss, ref, atol=1e-6)
+        ls = logits.clone().requires_grad_(True)
+        loss_soft = torch_ref.smooth_cross_entropy(ls, soft, sm, temp)
+        loss_soft.backward()
+        out["cases"].append({"smoothing": sm, "temperature": temp, "loss": loss.detach(),
+                             "grad": lr.grad.clone(), "loss_soft": loss_soft.detach(),
+                             "grad_soft": ls.grad.clone()})
+    torch.save(out, os.path.join(OUT, "cross_entropy.pt"))
+
+
+def sgd():
+    torch.manual_seed(2)
+    n = 1000
+    p0 = torch.randn(n)
+    grads = [torch.randn(n) for _ in range(5)]
+    lrs = [0.1, 0.2, 0.05, 0.4, 0.01]
+    out = {"p0": p0, "grads": grads, "lrs": lrs, "runs": {}}
+    for nesterov in (False, True):
+        p = p0.clone().requires_grad_(True)
+        from torch.optim._multi_tensor import SGD as MultiTensorSGD  # the reference optimizer class
+        opt = MultiTensorSGD([p], lr=0.0, momentum=0.9, weight_decay=3e-5,
+                             nesterov=nesterov)
+        traj = []
+        for g, lr in zip(grads, lrs):
+            opt.param_groups[0]["lr"] = lr
+            p.grad = g.clone()
+            opt.step()
+            traj.append(p.detach().clone())
+        out["runs"]["nesterov" if nesterov else "plain"] = traj
+    torch.save(out, os.path.join(OUT, "sgd.pt"))
+
+
+def augment():
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, size=(4, 48, 64, 3), dtype=np.uint8)
+    boxes = [augment_ref.rrc_box(48, 64, 0.08, 1.0, 1234, i) for i in range(4)]
+    outs = np.stack([augment_ref.augment_image(img[i], boxes[i], 32) for i in range(4)])
+    many = np.array([augment_ref.rrc_box(256, 256, 0.08, 1.0, 42, i) for i in range(256)], np.int32)
+    wide = np.array([augment_ref.rrc_box(100, 400, 0.9, 1.0, 7, i) for i in range(64)], np.int32)
+    torch.save({"img": torch.from_numpy(img), "boxes": torch.tensor(boxes, dtype=torch.int32),
+                "out": torch.from_numpy(outs), "boxes_256_seed42": torch.from_numpy(many),
+                "boxes_100x400_seed7_minarea09": torch.from_numpy(wide)},
+               os.path.join(OUT, "augment.pt"))
+
+
+def resnet_step():
+    """Tiny pin of the whole-step oracle: torchvision ResNet-50, B=2, 64x64, seed 0."""
+    model = torch_ref.resnet50(seed=0)
+    opt = torch_ref.make_sgd(model.parameters(), lr=0.1)
+    x, y = torch_ref.synthetic_batch(2, 64, seed=0)
+    losses = [torch_ref.train_step(model, opt, x, y) for _ in range(2)]
+    torch.save({"losses": losses, "fc_bias_after": model.fc.bias.detach().clone(),
+                "bn1_running_mean": model.bn1.running_mean.clone()},
+               os.path.join(OUT, "resnet50_step.pt"))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    heads()
+    cross_entropy()
+    sgd()
+    augment()
+    resnet_step()
+    print("golden vectors written to", os.path.abspath(OUT))

@@ -1,0 +1,79 @@
+"""fp32 PyTorch restatement of the training step (oracle; see oracle/__init__.py).
+
+  * ResNet-50            = torchvision.models.resnet50(weights=None): BASELINE.json config #1 and
+                           reference README.md:42 ("default torchvision version of Resnet50");
+                           the reference builds it through pytorch_tools.models.resnet50
+                           (train.py:64, configs/hydra_exp/1.r50_baseline.yaml:22-23) — absent.
+  * smooth_cross_entropy = pytorch_tools.losses.smooth.CrossEntropyLoss restated from SURVEY.md
+                           App. C.1 (call sites: arg_parser.py:140-142, angular_losses.py:572-576).
+  * sgd                  = torch.optim.SGD(foreach=True) == torch.optim._multi_tensor.SGD
+                           (arg_parser.py:136-138).
+  * angular heads        = restated line by line from reference angular_losses.py and pinned to
+                           the reference file itself by oracle/make_golden.py.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def smooth_cross_entropy(y_pred, y_true, smoothing=0.0, temperature=1.0):
+    """App. C.1: one-hot via scatter for index targets, dense targets used as is."""
+    logp = F.log_softmax(y_pred.float() / temperature, dim=1)
+    if y_true.dim() == 1:
+        onehot = torch.zeros_like(logp).scatter_(1, y_true[:, None].long(), 1.0)
+    else:
+        onehot = y_true.float()
+    nll = -(logp * onehot).sum(1)
+    smooth = -logp.mean(1)
+    return ((1 - smoothing) * nll + smoothing * smooth).mean()
+
+
+def sphere_linear(x, weight):
+    """angular_losses.py:212-214"""
+    return F.linear(F.normalize(x), F.normalize(weight))
+
+
+def arcface_logits(cosine, y_true, s=10.0, m=0.2):
+    """angular_losses.py:118-143 (AdditiveAngularMarginLoss up to final_criterion)."""
+    cos_m, sin_m = math.cos(m), math.sin(m)
+    th, mm = math.cos(math.pi - m), math.sin(math.pi - m) * m
+    sine = torch.sqrt(1.0 - torch.pow(cosine, 2))
+    phi = cosine * cos_m - sine * sin_m
+    phi = torch.where(cosine > th, phi, cosine - mm)
+    one_hot = torch.zeros_like(cosine).scatter_(1, y_true[..., None].long(), 1.0)
+    return ((one_hot * phi) + ((1.0 - one_hot) * cosine)) * s
+
+
+def cosface_logits(cosine, y_true, s=30.0, m=0.4):
+    """angular_losses.py:189-196 (LargeMarginCosineLoss) == AdaCos fixed_s path :332-333."""
+    one_hot = torch.zeros_like(cosine).scatter_(1, y_true.view(-1, 1).long(), 1.0)
+    return ((one_hot * (cosine - m)) + ((1.0 - one_hot) * cosine)) * s
+
+
+def resnet50(num_classes=1000, seed=0):
+    import torchvision
+    torch.manual_seed(seed)
+    return torchvision.models.resnet50(weights=None, num_classes=num_classes)
+
+
+def make_sgd(params, lr, momentum=0.9, weight_decay=3e-5, nesterov=False):
+    return torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay,
+                           nesterov=nesterov, foreach=True)
+
+
+def train_step(model, opt, x, y, smoothing=0.1):
+    """One fwd + bwd + SGD step; returns the loss (float)."""
+    opt.zero_grad(set_to_none=True)
+    loss = smooth_cross_entropy(model(x), y, smoothing)
+    loss.backward()
+    opt.step()
+    return float(loss.detach())
+
+
+def synthetic_batch(batch, size, num_classes=1000, seed=0):
+    """x ~ randn (DALI output range), y ~ randint."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 3, size, size, generator=g)
+    y = torch.randint(0, num_classes, (batch,), generator=g)
+    return x, y

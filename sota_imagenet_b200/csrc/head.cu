@@ -59,10 +59,10 @@ ce_kernel(const T* __restrict__ logits, const long* __restrict__ labels,
     float v = to_f<T>(x[c]);
     if (mp.kind != SIB_MARGIN_NONE) {
       if (c == y) {
-        if (mp.kind == SIB_MARGIN_ARC) {
+        if (mp.kind == SIB_MARGIN_ARC || mp.kind == SIB_MARGIN_ARC_PURE) {
           const float sine = sqrtf(fmaxf(1.f - v * v, 0.f));
           const float phi = v * mp.cos_m - sine * mp.sin_m;
-          if (v > mp.th) {
+          if (v > mp.th || mp.kind == SIB_MARGIN_ARC_PURE) {
             dphi = mp.cos_m + mp.sin_m * v / fmaxf(sine, 1e-6f);
             v = phi;
           } else {
@@ -71,6 +71,9 @@ ce_kernel(const T* __restrict__ logits, const long* __restrict__ labels,
         } else {
           v = v - mp.m;
         }
+      } else if (mp.kind == SIB_MARGIN_COS && labels == nullptr && dense_t != nullptr &&
+                 dense_t[(long)row * C + c] != 0.f) {
+        v = v - mp.m;   // soft / one-hot targets: margin on every column with target mass
       }
       v *= mp.s;
     }
@@ -215,7 +218,7 @@ static MarginParams make_margin(int kind, float s, float m) {
   mp.kind = kind;
   mp.s = s;
   mp.m = m;
-  if (kind == SIB_MARGIN_ARC) {
+  if (kind == SIB_MARGIN_ARC || kind == SIB_MARGIN_ARC_PURE) {
     const double pi = 3.14159265358979323846;
     mp.cos_m = (float)cos((double)m);
     mp.sin_m = (float)sin((double)m);
@@ -231,8 +234,8 @@ extern "C" int sib_ce_fwd_bwd(const void* logits, int logits_fp32, const long* l
                               float* loss_rows, float* loss_mean, void* dlogits, float grad_scale,
                               void* stream) {
   SIB_CHECK(labels != nullptr || dense_targets != nullptr, "ce: no targets given");
-  SIB_CHECK(margin_kind == SIB_MARGIN_NONE || labels != nullptr,
-            "ce: angular margins need index labels (reference angular_losses.py:140 scatter_)");
+  SIB_CHECK((margin_kind != SIB_MARGIN_ARC && margin_kind != SIB_MARGIN_ARC_PURE) || labels != nullptr,
+            "ce: ArcFace needs index labels (reference angular_losses.py:140 scatter_)");
   SIB_CHECK(C * sizeof(float) <= 96 * 1024, "ce: too many classes for one CTA (%d)", C);
   const MarginParams mp = make_margin(margin_kind, s, m);
   const size_t smem = sizeof(float) * C;

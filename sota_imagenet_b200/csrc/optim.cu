@@ -28,9 +28,12 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long)gridDim.x * blockDim.x) {
     const long e = i * 4;
-    // segment lookup (few groups: linear scan)
-    int sidx = 0;
-    while (sidx + 1 < nseg && e >= segs[sidx].end) ++sidx;
+    // segment lookup
+    int sidx = 0, hi = nseg - 1;
+    while (sidx < hi) {          // first segment whose end is > e
+      const int mid = (sidx + hi) >> 1;
+      if (e >= segs[mid].end) sidx = mid + 1; else hi = mid;
+    }
     const SgdSeg sg = segs[sidx];
     float4 pv = *reinterpret_cast<float4*>(p + e);
     const float4 gv = *reinterpret_cast<const float4*>(g + e);

@@ -1,0 +1,451 @@
+"""Drop-in nn.Modules whose forward/backward are explicit sequences of libsib200 kernel launches.
+
+Every module implements
+    fwd(x, train) -> (y, saved)      plain tensors in / out, no autograd graph
+    bwd(dy, saved) -> dx             writes parameter gradients into the arena as a side effect
+and `forward()` wraps that pair into ONE autograd node, so a whole ResNet is a single node in
+the autograd graph (no per-op dispatch, no AccumulateGrad kernels).  Activations are bf16
+channels_last ([N,C,H,W] logical, NHWC in memory).
+
+Module / parameter names follow torchvision's ResNet so checkpoints interchange
+(reference train.py:98-101 loads with strict=False).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .arena import ParamArena
+
+
+# --------------------------------------------------------------------------- autograd glue
+class _SibFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dummy, module):
+        y, saved = module.fwd(x, True)
+        ctx.module = module
+        ctx.saved = saved
+        ctx.x_needs_grad = ctx.needs_input_grad[0]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        module = ctx.module
+        module._begin_backward()
+        dx = module.bwd(dy, ctx.saved, need_dx=ctx.x_needs_grad)
+        ctx.saved = None
+        module._end_backward()
+        return dx, None, None
+
+
+class SibModule(nn.Module):
+    """Base class: owns the arena when used as the root of a forward call."""
+
+    def __init__(self):
+        super().__init__()
+        self._arena = None
+        self._bwd_hooks = []   # callables(module) run when backward of this root finishes
+
+    # -- arena management -----------------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._arena = None
+        return out
+
+    def ensure_arena(self):
+        """(Re)build the flat arena for all parameters below this module if needed."""
+        a = self._arena
+        if a is not None and a.intact():
+            return a
+        params = [(n, p) for n, p in self.named_parameters()]
+        if not params:
+            return None
+        dev = params[0][1].device
+        if dev.type != "cuda":
+            raise _lib.SibError("sota_imagenet_b200 modules run on CUDA sm_100a only; call .cuda()")
+        for _, p in params:
+            if p.dtype != torch.float32:
+                raise _lib.SibError("parameters must stay float32 (bf16 shadows are kept internally)")
+        existing = getattr(params[0][1], "_sib_arena", None)
+        if existing is not None and existing.intact() and len(existing.entries) == len(params) and all(
+                getattr(p, "_sib_arena", None) is existing for _, p in params):
+            self._arena = existing
+        else:
+            self._arena = ParamArena(params, dev)
+        for m in self.modules():
+            if isinstance(m, SibModule) and m is not self:
+                m._arena = self._arena
+        return self._arena
+
+    def _begin_backward(self):
+        a = self.ensure_arena()
+        if a is not None:
+            a.prepare_grads()
+
+    def _end_backward(self):
+        for h in self._bwd_hooks:
+            h(self)
+
+    # -- nn.Module API ----------------------------------------------------------------
+    def forward(self, x):
+        _lib.require_device()
+        a = self.ensure_arena()
+        if a is not None:
+            a.refresh_shadow()
+        x = self._prepare_input(x)
+        if torch.is_grad_enabled() and (self.training or x.requires_grad):
+            if not hasattr(self, "_dummy") or self._dummy.device != x.device:
+                self._dummy = torch.zeros((), device=x.device, requires_grad=True)
+            return _SibFn.apply(x, self._dummy, self)
+        y, _ = self.fwd(x, self.training)
+        return y
+
+    def _prepare_input(self, x):
+        if x.dim() == 4 and (x.dtype != torch.bfloat16 or not x.permute(0, 2, 3, 1).is_contiguous()):
+            if x.requires_grad:
+                raise _lib.SibError("inputs that require grad must already be bf16 channels_last")
+            return ops.to_nhwc_bf16(x)
+        return x
+
+    # helpers for parameters living in the arena
+    def _w16(self, p):
+        return self._arena.shadow_view(p)
+
+    def _wd16(self, p):
+        return self._arena.dgrad_view(p)
+
+    def _grad(self, p):
+        return self._arena.grad_view(p)
+
+
+# --------------------------------------------------------------------------- layers
+class Conv2d(SibModule):
+    """bias-free NHWC bf16 convolution on tcgen05 (csrc/conv.cu)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=False,
+                 needs_dgrad=True):
+        super().__init__()
+        assert not bias, "conv bias is not used by the ResNet family (BN follows every conv)"
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = (kernel_size, kernel_size)
+        self.stride, self.padding = stride, padding
+        w = torch.empty(out_channels, in_channels, kernel_size, kernel_size)
+        nn.init.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")
+        self.weight = nn.Parameter(w)
+        self.weight._sib_layout = "krsc"
+        self.weight._sib_needs_dgrad = needs_dgrad
+
+    def extra_repr(self):
+        return "%d, %d, kernel_size=%s, stride=%d, padding=%d" % (
+            self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding)
+
+    def run(self, x, stats=None):
+        return ops.conv2d_fprop(x, self._w16(self.weight), self.stride, self.padding, stats=stats)
+
+    def run_dgrad(self, dy, x_shape, out=None, accumulate=False):
+        k = self.kernel_size[0]
+        return ops.conv2d_dgrad(dy, self._wd16(self.weight), x_shape, k, k, self.stride,
+                                self.padding, out=out, accumulate=accumulate)
+
+    def run_wgrad(self, x, dy):
+        ops.conv2d_wgrad(x, dy, self._grad(self.weight), self.stride, self.padding)
+
+    def fwd(self, x, train):
+        return self.run(x), (x,)
+
+    def bwd(self, dy, saved, need_dx=True):
+        (x,) = saved
+        dy = _as_act(dy)
+        self.run_wgrad(x, dy)
+        return self.run_dgrad(dy, tuple(x.shape)) if need_dx else None
+
+
+class StemConv(SibModule):
+    """KxK stride-2 convolution over the 3-channel image, run as a (K+1)/2 x 1 stride-1
+    tensor-core convolution over a row-pair-packed 64-channel copy (csrc/augment.cu)."""
+
+    def __init__(self, out_channels=64, kernel_size=7, padding=3):
+        super().__init__()
+        assert kernel_size % 2 == 1 and padding == kernel_size // 2
+        self.in_channels, self.out_channels = 3, out_channels
+        self.kernel_size = (kernel_size, kernel_size)
+        self.stride, self.padding = 2, padding
+        # rows 2p + r - pad = 2(p + a - a0) + b  ->  r = 2a + b - off
+        self.off = padding % 2 if padding % 2 == 1 else 0
+        self.a0 = (padding + self.off) // 2
+        self.na = (kernel_size - 1 + self.off) // 2 + 1
+        w = torch.empty(out_channels, 3, kernel_size, kernel_size)
+        nn.init.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")
+        self.weight = nn.Parameter(w)   # plain OIHW layout
+
+    def _packed_weight(self):
+        wq = ops.stem_pack_weight(self.weight.data, self.na, self.off)
+        return wq.permute(0, 3, 1, 2)   # logical [K, 64, NA, 1], KRSC memory
+
+    def _prepare_input(self, x):
+        return x
+
+    def run(self, x, stats=None):
+        n, c, h, w = x.shape
+        xq = ops.stem_pack(x, self.kernel_size[1], self.padding)
+        y = ops.conv2d_fprop(xq, self._packed_weight(), 1, 0, stats=stats, pad_hw=(self.a0, 0),
+                             out_hw=(h // 2, w // 2))
+        return y, xq
+
+    def run_wgrad(self, xq, dy):
+        k = self.out_channels
+        dwq = torch.zeros((k, self.na, 1, 64), dtype=torch.float32, device=dy.device).permute(0, 3, 1, 2)
+        ops.conv2d_wgrad(xq, dy, dwq, 1, 0, pad_hw=(self.a0, 0))
+        ops.stem_unpack_wgrad(dwq, self._grad(self.weight), self.na, self.off, accumulate=True)
+
+    def fwd(self, x, train):
+        y, xq = self.run(x)
+        return y, (xq,)
+
+    def bwd(self, dy, saved, need_dx=False):
+        assert not need_dx, "the stem has no data gradient (image input)"
+        self.run_wgrad(saved[0], _as_act(dy))
+        return None
+
+
+class BatchNorm2d(SibModule):
+    """BatchNorm (+ fused activation), nn.BatchNorm2d-compatible state.  `sync` turns the batch
+    statistics into cross-rank statistics (SyncBN) with one 2C-float all-reduce per pass."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, activation="identity", slope=0.01):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.activation, self.slope = activation, slope
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self.process_group = None
+        self.sync = False
+
+    def extra_repr(self):
+        return "%d, eps=%g, momentum=%g, activation=%s" % (self.num_features, self.eps,
+                                                             self.momentum, self.activation)
+
+    @property
+    def act(self):
+        return ops.ACT_CODES[self.activation]
+
+    def _world(self):
+        if self.sync and torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size(self.process_group)
+        return 1
+
+    def finalize(self, stats, count, train):
+        """stats [2,C] (sum, sumsq of this rank) -> (mean_invstd, scale_shift, total count)."""
+        if not train:
+            return None, ops.bn_eval_scale(self.weight.data, self.bias.data, self.running_mean,
+                                           self.running_var, self.eps), count
+        world = self._world()
+        if world > 1:
+            torch.distributed.all_reduce(stats, group=self.process_group)
+            count = count * world
+        mi, ss = ops.bn_finalize(stats, self.weight.data, self.bias.data, self.running_mean,
+                                 self.running_var, count, self.eps, self.momentum)
+        self.num_batches_tracked += 1
+        return mi, ss, count
+
+    def reduce_sums(self, sums):
+        if self._world() > 1:
+            torch.distributed.all_reduce(sums, group=self.process_group)
+        return sums
+
+    def param_grads(self, sums, second=False):
+        s = sums[2:4] if second else sums[0:2]
+        ops.bn_param_grad(s, self._grad(self.weight), self._grad(self.bias), accumulate=True)
+
+    # standalone use: stats pass + apply
+    def fwd(self, x, train, res=None):
+        n, c, h, w = x.shape
+        stats = ops.bn_stats(x) if train else None
+        mi, ss, count = self.finalize(stats, n * h * w, train)
+        y = ops.bn_apply(x, ss, self.act, self.slope, res=res)
+        return y, (x, y, mi, count)
+
+    def bwd(self, dy, saved, need_dx=True):
+        x, y, mi, count = saved
+        dy = _as_act(dy)
+        sums = self.reduce_sums(ops.bn_bwd_reduce(dy, y, x, mi, self.act, self.slope))
+        self.param_grads(sums)
+        dx, _, _ = ops.bn_bwd_apply(dy, y, x, mi, self.weight.data, sums, count, self.act, self.slope)
+        return dx
+
+
+class MaxPool3x3s2(SibModule):
+    def fwd(self, x, train):
+        y, idx = ops.maxpool3x3s2_fwd(x, want_idx=train)
+        return y, (idx, tuple(x.shape))
+
+    def bwd(self, dy, saved, need_dx=True):
+        idx, shape = saved
+        return ops.maxpool3x3s2_bwd(_as_act(dy), idx, shape)
+
+
+class Linear(SibModule):
+    """Fully connected head run as a 1x1 convolution on the same tcgen05 kernel; bias fused in
+    the epilogue.  weight [out, in] fp32 like nn.Linear."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        assert in_features % 8 == 0 and out_features % 8 == 0
+        w = torch.empty(out_features, in_features)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        self.weight = nn.Parameter(w.view(out_features, in_features, 1, 1))
+        self.weight._sib_layout = "krsc"
+        self.weight._sib_needs_dgrad = True
+        self._register_state_dict_hook(_linear_sd_hook)
+        self._register_load_state_dict_pre_hook(_linear_load_hook)
+        if bias:
+            bound = 1 / math.sqrt(in_features)
+            self.bias = nn.Parameter(torch.empty(out_features).uniform_(-bound, bound))
+        else:
+            self.register_parameter("bias", None)
+
+    def fwd(self, x, train):
+        """x [N, in, 1, 1] bf16 -> logits [N, out] bf16"""
+        x4 = x if x.dim() == 4 else x.view(x.shape[0], x.shape[1], 1, 1)
+        y = ops.conv2d_fprop(x4, self._w16(self.weight), 1, 0,
+                             bias=self.bias.data if self.bias is not None else None)
+        return y.reshape(y.shape[0], y.shape[1]), (x4,)
+
+    def bwd(self, dy, saved, need_dx=True):
+        (x4,) = saved
+        n = x4.shape[0]
+        dy4 = _as_act(dy.reshape(n, self.out_features, 1, 1))
+        ops.conv2d_wgrad(x4, dy4, self._grad(self.weight), 1, 0)
+        if self.bias is not None:
+            col = ops.bn_stats(dy4)       # row 0 = per-column sum of dlogits
+            self._grad(self.bias).add_(col[0])
+        if not need_dx:
+            return None
+        return ops.conv2d_dgrad(dy4, self._wd16(self.weight), tuple(x4.shape), 1, 1, 1, 0)
+
+
+def _linear_sd_hook(module, state_dict, prefix, local_metadata):
+    # expose the nn.Linear shape [out, in] in checkpoints
+    key = prefix + "weight"
+    if key in state_dict:
+        state_dict[key] = state_dict[key].reshape(module.out_features, module.in_features)
+
+
+def _linear_load_hook(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                      error_msgs):
+    key = prefix + "weight"
+    if key in state_dict and state_dict[key].dim() == 2:
+        w = state_dict[key]
+        state_dict[key] = w.reshape(w.shape[0], w.shape[1], 1, 1)
+
+
+def _as_act(t):
+    """Gradient tensors arriving from autograd may be fp32 / NCHW-contiguous: normalise."""
+    if t.dtype == torch.bfloat16 and t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous():
+        return t
+    return ops.to_nhwc_bf16(t)
+
+
+# --------------------------------------------------------------------------- residual block
+class Bottleneck(SibModule):
+    """ResNet v1.5 bottleneck (stride on the 3x3), torchvision naming.  Forward:
+         conv1 -> bn1+act -> conv2 -> bn2+act -> conv3 -> bn3 (+ bn_ds(conv_ds(x)) | + x) -> act
+    BN statistics come out of the conv epilogues; bn3 + shortcut BN + add + act is one kernel.
+    """
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=False, activation="relu", slope=0.01):
+        super().__init__()
+        out = planes * self.expansion
+        self.conv1 = Conv2d(inplanes, planes, 1)
+        self.bn1 = BatchNorm2d(planes, activation=activation, slope=slope)
+        self.conv2 = Conv2d(planes, planes, 3, stride=stride, padding=1)
+        self.bn2 = BatchNorm2d(planes, activation=activation, slope=slope)
+        self.conv3 = Conv2d(planes, out, 1)
+        self.bn3 = BatchNorm2d(out, activation=activation, slope=slope)
+        self.stride = stride
+        if downsample:
+            ds_bn = BatchNorm2d(out, activation="identity")
+            self.downsample = nn.Sequential(Conv2d(inplanes, out, 1, stride=stride), ds_bn)
+        else:
+            self.downsample = None
+
+    @staticmethod
+    def _conv_bn(conv, bn, x, train, **apply_kw):
+        dev = x.device
+        stats = torch.empty((2, conv.out_channels), dtype=torch.float32, device=dev) if train else None
+        c = conv.run(x, stats)
+        n, _, h, w = c.shape
+        mi, ss, count = bn.finalize(stats, n * h * w, train)
+        return c, mi, ss, count
+
+    def fwd(self, x, train):
+        c1, mi1, ss1, cnt1 = self._conv_bn(self.conv1, self.bn1, x, train)
+        a1 = ops.bn_apply(c1, ss1, self.bn1.act, self.bn1.slope)
+        c2, mi2, ss2, cnt2 = self._conv_bn(self.conv2, self.bn2, a1, train)
+        a2 = ops.bn_apply(c2, ss2, self.bn2.act, self.bn2.slope)
+        c3, mi3, ss3, cnt3 = self._conv_bn(self.conv3, self.bn3, a2, train)
+        if self.downsample is not None:
+            cd, mid, ssd, _ = self._conv_bn(self.downsample[0], self.downsample[1], x, train)
+            out = ops.bn_apply(c3, ss3, self.bn3.act, self.bn3.slope, res=cd, scale_shift2=ssd)
+        else:
+            cd = mid = None
+            out = ops.bn_apply(c3, ss3, self.bn3.act, self.bn3.slope, res=x)
+        if not train:
+            return out, None
+        return out, (x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3)
+
+    def bwd(self, dout, saved, need_dx=True):
+        x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3 = saved
+        dout = _as_act(dout)
+        bn1, bn2, bn3 = self.bn1, self.bn2, self.bn3
+        # ---- bn3 (+ shortcut bn) + add + act ----
+        if self.downsample is not None:
+            bnd = self.downsample[1]
+            sums = bn3.reduce_sums(ops.bn_bwd_reduce(dout, out, c3, mi3, bn3.act, bn3.slope, x2=cd,
+                                                     mean_invstd2=mid))
+            bn3.param_grads(sums)
+            bnd.param_grads(sums, second=True)
+            dc3, dcd, _ = ops.bn_bwd_apply(dout, out, c3, mi3, bn3.weight.data, sums, cnt3, bn3.act,
+                                           bn3.slope, x2=cd, mean_invstd2=mid,
+                                           gamma2=bnd.weight.data)
+            g = None
+        else:
+            sums = bn3.reduce_sums(ops.bn_bwd_reduce(dout, out, c3, mi3, bn3.act, bn3.slope))
+            bn3.param_grads(sums)
+            dc3, dcd, g = ops.bn_bwd_apply(dout, out, c3, mi3, bn3.weight.data, sums, cnt3, bn3.act,
+                                           bn3.slope, want_g=need_dx)
+        # ---- conv3 ----
+        self.conv3.run_wgrad(a2, dc3)
+        da2 = self.conv3.run_dgrad(dc3, tuple(a2.shape))
+        # ---- bn2 + act ----
+        sums = bn2.reduce_sums(ops.bn_bwd_reduce(da2, a2, c2, mi2, bn2.act, bn2.slope))
+        bn2.param_grads(sums)
+        dc2, _, _ = ops.bn_bwd_apply(da2, a2, c2, mi2, bn2.weight.data, sums, cnt2, bn2.act,
+                                     bn2.slope)
+        # ---- conv2 ----
+        self.conv2.run_wgrad(a1, dc2)
+        da1 = self.conv2.run_dgrad(dc2, tuple(a1.shape))
+        # ---- bn1 + act ----
+        sums = bn1.reduce_sums(ops.bn_bwd_reduce(da1, a1, c1, mi1, bn1.act, bn1.slope))
+        bn1.param_grads(sums)
+        dc1, _, _ = ops.bn_bwd_apply(da1, a1, c1, mi1, bn1.weight.data, sums, cnt1, bn1.act,
+                                     bn1.slope)
+        # ---- conv1 (+ shortcut) ----
+        self.conv1.run_wgrad(x, dc1)
+        if self.downsample is not None:
+            self.downsample[0].run_wgrad(x, dcd)
+        if not need_dx:
+            return None
+        if self.downsample is not None:
+            dx = self.conv1.run_dgrad(dc1, tuple(x.shape))
+            self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx, accumulate=True)
+        else:
+            # identity shortcut: dx = dgrad(conv1) + g, accumulated in place into g
+            dx = self.conv1.run_dgrad(dc1, tuple(x.shape), out=g, accumulate=True)
+        return dx

@@ -10,7 +10,7 @@ from . import _lib
 from ._lib import c_void_p, call
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
-MARGIN_NONE, MARGIN_ARC, MARGIN_COS = 0, 1, 2
+MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE = 0, 1, 2, 3
 FLAG_FORCE_IM2COL = 1
 ACT_CODES = {None: ACT_NONE, "identity": ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU,
              "leaky_relu": ACT_LEAKY}

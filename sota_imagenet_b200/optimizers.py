@@ -1,0 +1,154 @@
+"""torch.optim.Optimizer drop-ins backed by the multi-tensor kernels.
+
+SGD replaces `torch.optim._multi_tensor.SGD` (reference arg_parser.py:136-138, hyper-parameters
+from configs/hydra_exp/1.r50_baseline.yaml:29-31) with torch/optim/sgd.py arithmetic: coupled
+L2 weight decay, momentum buffer initialised to the first gradient, optional Nesterov.  One
+kernel launch per parameter arena updates every tensor, rewrites the bf16 filter shadows and
+(optionally) an EMA copy of the weights (pt_clb.ModelEma, reference train.py:112).
+"""
+import torch
+
+from . import _lib, ops
+from .arena import ParamArena
+
+
+class SGD(torch.optim.Optimizer):
+    def __init__(self, params, lr=0.0, momentum=0.0, dampening=0.0, weight_decay=0.0,
+                 nesterov=False, ema_decay=0.0, **unused):
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
+                        nesterov=nesterov)
+        super().__init__(params, defaults)
+        self.ema_decay = ema_decay
+        self._arenas = None
+        self._steps = 0
+        self._seg_cache = {}
+
+    # ------------------------------------------------------------------ arenas
+    def _collect_arenas(self):
+        arenas, loose = [], []
+        for group in self.param_groups:
+            for p in group["params"]:
+                a = getattr(p, "_sib_arena", None)
+                if a is not None and a.intact():
+                    if all(a is not b for b in arenas):
+                        arenas.append(a)
+                else:
+                    loose.append(p)
+        if loose:
+            if not loose[0].is_cuda:
+                raise _lib.SibError("fused SGD needs CUDA parameters (no CPU fallback)")
+            grads = [p.grad for p in loose]
+            a = ParamArena([("loose%d" % i, p) for i, p in enumerate(loose)], loose[0].device)
+            for p, g in zip(loose, grads):       # keep autograd-produced grads
+                p.grad = g
+            a._loose = True
+            arenas.append(a)
+        for a in arenas:
+            if a.momentum is None:
+                a.momentum = torch.zeros_like(a.flat)
+            if self.ema_decay and a.ema is None:
+                a.ema = a.flat.clone()
+        self._arenas = arenas
+        # expose momentum buffers in the torch.optim.SGD state format
+        for a in arenas:
+            for _, p, o, n, layout in a.entries:
+                self.state[p]["momentum_buffer"] = ParamArena.view_of(a.momentum, o, p.shape, layout)
+
+    def _segments(self, arena):
+        gmap = {}
+        for gi, group in enumerate(self.param_groups):
+            for p in group["params"]:
+                gmap[id(p)] = gi
+        recs = []
+        for i, (_, p, o, n, _) in enumerate(arena.entries):
+            end = arena.entries[i + 1][2] if i + 1 < len(arena.entries) else arena.total
+            gi = gmap.get(id(p))
+            if gi is None:
+                hp = (0.0, 0.0, 0.0, 0.0, False)
+            else:
+                g = self.param_groups[gi]
+                hp = (float(g["lr"]), float(g["weight_decay"]), float(g["momentum"]),
+                      float(g["dampening"]), bool(g["nesterov"]))
+            if recs and recs[-1][1:] == hp:
+                recs[-1] = (end,) + hp
+            else:
+                recs.append((end,) + hp)
+        return recs
+
+    # ------------------------------------------------------------------ API
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if self._arenas is None or not all(a.intact() for a in self._arenas):
+            self._collect_arenas()
+        first = self._steps == 0
+        for a in self._arenas:
+            for _, p, o, n, layout in a.entries:
+                if p.grad is None:
+                    continue
+                gv = ParamArena.view_of(a.grad, o, p.shape, layout)
+                if p.grad.data_ptr() != gv.data_ptr():
+                    gv.copy_(p.grad)
+            recs = self._segments(a)
+            key = id(a)
+            cached = self._seg_cache.get(key)
+            if cached is None or cached[0] != recs:
+                host = ops.sgd_segments(recs, "cpu").pin_memory()
+                if cached is None or cached[1].numel() != host.numel():
+                    dev = host.to(a.device, non_blocking=True)
+                else:
+                    dev = cached[1]
+                    dev.copy_(host, non_blocking=True)
+                self._seg_cache[key] = (recs, dev, host)
+                cached = self._seg_cache[key]
+            ops.sgd_step(a.flat, a.grad, a.momentum, a.shadow, cached[1], len(recs), first,
+                         ema=a.ema if self.ema_decay else None, ema_decay=self.ema_decay)
+            a.mark_fresh()
+        self._steps += 1
+        return loss
+
+    def zero_grad(self, set_to_none=True):
+        if self._arenas is None:
+            return super().zero_grad(set_to_none)
+        for a in self._arenas:
+            if getattr(a, "_loose", False):
+                for _, p, _, _, _ in a.entries:
+                    p.grad = None if set_to_none else (p.grad.zero_() if p.grad is not None else None)
+            else:
+                a.zero_grad()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._collect_arenas_after_load()
+
+    def _collect_arenas_after_load(self):
+        loaded = {p: dict(s) for p, s in self.state.items()}
+        self._collect_arenas()
+        any_buf = False
+        for p, s in loaded.items():
+            buf = s.get("momentum_buffer")
+            if buf is not None:
+                self.state[p]["momentum_buffer"].copy_(buf)
+                any_buf = True
+        if any_buf:
+            self._steps = max(self._steps, 1)
+
+    def ema_state_dict(self, module):
+        """EMA weights keyed like module.state_dict() (what ModelEma would hold)."""
+        out = {}
+        for a in self._arenas or []:
+            if a.ema is None:
+                continue
+            names = {id(p): n for n, p in module.named_parameters()}
+            for _, p, o, n, layout in a.entries:
+                if id(p) in names:
+                    out[names[id(p)]] = ParamArena.view_of(a.ema, o, p.shape, layout).clone()
+        return out
+
+
+FusedSGD = SGD
