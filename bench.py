@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ResNet-50 224x224 bf16 training step (fwd + bwd + SGD-Nesterov),
+batch 256 per GPU, synthetic data (BASELINE.json configs[1]; data-parallel + SyncBN for N>1).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's sm_100a path
+    python bench.py --impl reference ...                   # CPU oracle port on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM (device-timed,
+max over ranks); `e2e` = the same step driven from pinned HOST uint8 images through the public
+API (H2D copy + GPU augmentation + step + D2H loss read inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 256
+SIZE = 224
+METRIC = "resnet50_224_bf16_train_images_per_sec"
+UNIT = "images/s"
+# conv FLOPs per image fwd 8.174 G, fwd+dgrad(no stem)+wgrad 24.29 G (+0.012 FC)
+TRAIN_GFLOP_PER_IMG = 24.29 + 0.012
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "which": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "which": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_oracle_rate(batch=16, size=SIZE, budget_s=20.0, min_steps=3, warmup=1):
+    """torchvision ResNet-50 fp32 + smooth CE + torch SGD on the host cores (the oracle port of
+    the reference path; pytorch_tools itself is absent).  Returns (img/s, cores, sample text)."""
+    import torch
+    from oracle import torch_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = torch_ref.resnet50(seed=0).train()
+    opt = torch_ref.make_sgd(model.parameters(), lr=0.1, nesterov=True)
+    x, y = torch_ref.synthetic_batch(batch, size, seed=0)
+    for _ in range(warmup):
+        torch_ref.train_step(model, opt, x, y)
+    t0 = time.time()
+    steps = 0
+    while steps < min_steps or (time.time() - t0 < budget_s and steps < 64):
+        torch_ref.train_step(model, opt, x, y)
+        steps += 1
+    dt = time.time() - t0
+    return batch * steps / dt, cores, "%d steps of batch %d at %dx%d fp32, %.1f s" % (steps, batch, size, size, dt)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import torch_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 16
+    model = torch_ref.resnet50(seed=0).train()
+    opt = torch_ref.make_sgd(model.parameters(), lr=0.1, nesterov=True)
+    x, y = torch_ref.synthetic_batch(batch, SIZE, seed=0)
+    for _ in range(max(args.warmup, 1)):
+        torch_ref.train_step(model, opt, x, y)
+    t0 = time.time()
+    for _ in range(args.steps):
+        torch_ref.train_step(model, opt, x, y)
+    dt = time.time() - t0
+    rate = batch * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "ResNet-50 fwd+bwd+SGD-Nesterov, 224x224, synthetic; CPU sample: "
+                               "batch 16 per step (torchvision fp32, smooth CE 0.1, torch SGD)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d steps of batch %d" % (args.steps, batch)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def conv_flops(name, a):
+    """Algorithmic FLOPs of one conv launch from its C-ABI arguments."""
+    if name == "sib_conv2d_fprop":   # x w y N H W C K R S stride ph pw OH OW ...
+        n, c, k, r, s, oh, ow = a[3], a[6], a[7], a[8], a[9], a[13], a[14]
+        return 2.0 * n * oh * ow * k * c * r * s
+    if name in ("sib_conv2d_dgrad",):   # dy w dx N H W C K R S stride pad
+        n, h, w, c, k, r, s, stride, pad = a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]
+        oh, ow = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
+        return 2.0 * n * oh * ow * k * c * r * s
+    if name == "sib_conv2d_dgrad_strided":   # dy w dx ws N H W C K R S stride pad
+        n, h, w, c, k, r, s, stride, pad = a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]
+        oh, ow = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
+        return 2.0 * n * oh * ow * k * c * r * s
+    if name == "sib_conv2d_wgrad":   # x dy dw N H W C K R S stride ph pw OH OW
+        n, c, k, r, s, oh, ow = a[3], a[6], a[7], a[8], a[9], a[13], a[14]
+        return 2.0 * n * oh * ow * k * c * r * s
+    return 0.0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sota_imagenet_b200 import _lib, data, losses, models, optimizers, parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    net = models.resnet50().to(dev).train()
+    crit = losses.CrossEntropyLoss(smoothing=0.1)
+    # lr = 0.1 * global_batch / 256 at its warm-up start (1.r50_baseline.yaml:42: 0.001 -> 1.0)
+    opt = optimizers.SGD(net.parameters(), lr=0.001 * world, momentum=0.9, weight_decay=3e-5,
+                         nesterov=True)
+    model = parallel.DataParallel(net, sync_bn=True) if world > 1 else net
+
+    # ---- device-resident inputs (kernel-path number) -------------------------------------
+    g = torch.Generator(device=dev).manual_seed(rank)
+    x_static = torch.randn(BATCH, 3, SIZE, SIZE, device=dev, generator=g)
+    y_static = torch.randint(0, 1000, (BATCH,), device=dev, generator=g)
+    loss_static = torch.zeros((), device=dev)
+
+    def step(x, y):
+        opt.zero_grad()
+        loss = crit(model(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step(x_static, y_static)
+    torch.cuda.synchronize()
+
+    graph = None
+    calls_per_step = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step(x_static, y_static)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            c0 = _lib.CALLS
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                loss_static.copy_(step(x_static, y_static))
+            calls_per_step = _lib.CALLS - c0
+        except Exception as e:  # capture is an optimisation; eager launches are the same kernels
+            if rank == 0:
+                sys.stderr.write("CUDA graph capture failed (%s); timing eager launches\n" % repr(e)[:300])
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            loss_static.copy_(step(x_static, y_static))
+
+    if calls_per_step is None:
+        c0 = _lib.CALLS
+        run_step()
+        calls_per_step = _lib.CALLS - c0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        run_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss_static)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    ms_per_step = ms / args.steps
+    value = BATCH * world / ms_per_step * 1e3
+
+    # ---- end-to-end through the public API from pinned host memory ------------------------
+    src = data.SyntheticSource(pool=BATCH * 2, height=256, width=256, seed=rank, device=dev,
+                               pinned_host=True)
+    aug = data.GpuAugment(SIZE, 0.08, 1.0, seed=0, output="nhwc4_bf16")
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        imgs, labels = src.batch(i, BATCH)
+        imgs_d = imgs.to(dev, non_blocking=True)
+        labels_d = labels.to(dev, non_blocking=True)
+        xb = aug(imgs_d, first_sample=i * BATCH)
+        loss = step(xb, labels_d)
+        loss_host.copy_(loss.detach(), non_blocking=False)   # D2H read of the step's result
+        return float(loss_host)
+
+    for i in range(max(2, min(args.warmup, 3))):
+        e2e_step(i)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms2], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms2 = float(t)
+    e2e_value = BATCH * world * e2e_steps / ms2 * 1e3
+    h2d = BATCH * 256 * 256 * 3 + BATCH * 8
+    d2h = 4
+
+    # ---- live per-kernel timing of the conv family (roofline of the dominant kernel) --------
+    roofline = None
+    cpu_baseline = None
+    if rank == 0:
+        pk = peaks()
+        _lib.PROFILE = []
+        step(x_static, y_static)
+        torch.cuda.synchronize()
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        groups = {}
+        for name, a, s0, s1 in prof:
+            d = groups.setdefault(name, [0.0, 0.0, 0])
+            d[0] += s0.elapsed_time(s1)
+            d[1] += conv_flops(name, a)
+            d[2] += 1
+        conv_names = [n for n in groups if n.startswith("sib_conv2d")]
+        conv_ms = sum(groups[n][0] for n in conv_names)
+        conv_fl = sum(groups[n][1] for n in conv_names)
+        total_ms = sum(v[0] for v in groups.values())
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roofline = {
+            "bound": "tensor", "kernel": "igemm_kernel / wgrad_kernel (tcgen05 implicit-GEMM conv)",
+            "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["which"],
+            "launches": int(sum(groups[n][2] for n in conv_names)),
+            "conv_ms_per_step_eager_events": conv_ms, "all_kernels_ms_per_step_eager_events": total_ms,
+            "conv_share_of_step": conv_ms / total_ms if total_ms else None,
+            "per_call_ms": {n: round(v[0], 3) for n, v in sorted(groups.items(), key=lambda kv: -kv[1][0])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, cores, sample = cpu_oracle_rate()
+            cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": "ResNet-50 fwd+bwd+SGD-Nesterov(m=.9, wd=3e-5) + smooth-CE(0.1), batch %d/GPU, "
+                            "%dx%d, NHWC bf16, SyncBN + bucketed grad all-reduce for N>1" % (BATCH, SIZE, SIZE),
+                "global_batch": BATCH * world, "parallelism": "dp%d" % world,
+                "cuda_graph": graph is not None,
+                "l2": "activation working set (~12 GB/step) >> 126 MB L2; no flush needed",
+            },
+            "tflops_algorithmic": TRAIN_GFLOP_PER_IMG * value / 1e3,
+            "loss": final_loss,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps,
+                    "path": "pinned host uint8 [256,256,256,3] -> H2D -> GpuAugment -> model -> CE -> backward -> SGD -> loss D2H"},
+            "gpu_launches": int(calls_per_step * args.steps),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 12:
+            args.steps = 12      # bounded CPU sample (about 1 s per batch-16 step on 8 cores)
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

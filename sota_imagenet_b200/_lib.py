@@ -74,8 +74,22 @@ def check(rc):
         raise SibError("libsib200: " + (msg.decode() if msg else "error %d" % rc))
 
 
+CALLS = 0          # number of C-ABI compute calls issued (each launches >= 1 kernel)
+PROFILE = None     # when a list: (name, args, start_event, end_event) per call, for bench.py
+
+
 def call(name, *args):
+    global CALLS
+    CALLS += 1
+    if PROFILE is None:
+        check(getattr(load(), name)(*args))
+        return
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(load(), name)(*args))
+    e1.record()
+    PROFILE.append((name, tuple(a.value if hasattr(a, "value") else a for a in args), e0, e1))
 
 
 _device_ok = False

@@ -1,0 +1,138 @@
+"""Synthetic-input GPU data path standing in for sota_imagenet/dali_dataloader.py.
+
+  SyntheticSource   deterministic pool of uint8 HWC "decoded images" + labels (replaces the
+                    file / TFRecord readers + nvJPEG decode, dali_dataloader.py:47-72; the
+                    north_star scopes real decoding out);
+  GpuAugment        random-resized-crop (area [min_area,1], aspect [0.75,1.25], 100 attempts) ->
+                    triangular resize to SxS -> mirror p=.5 -> (v-127.5)/51 (:65-74,113-122) as one
+                    kernel; crop boxes from a counter-based Philox stream (bit-exact vs the oracle);
+  SyntheticLoader   DaliLoader surface (:163-186): iterable of (data, one-hot label), batch_size,
+                    __len__, drop-last;
+  DataManager       DaliDataManager surface (:189-239): stages with extra_args overrides
+                    (progressive resize / batch change), loaders rebuilt only when data args change.
+"""
+import copy
+import math
+
+import torch
+
+from . import ops
+
+DATA_MEAN, DATA_STD = 127.5, 51.0   # dali_dataloader.py:27-29 (0.5*255, 0.2*255)
+
+
+class GpuAugment:
+    def __init__(self, image_size=224, min_area=0.08, max_area=1.0, seed=0, flip=True,
+                 output="nhwc4_bf16"):
+        assert output in ("nhwc4_bf16", "nchw_f32")
+        self.image_size, self.min_area, self.max_area = image_size, min_area, max_area
+        self.seed, self.flip, self.output = seed, flip, output
+
+    def boxes(self, batch, src_h, src_w, first_sample, device):
+        return ops.rrc_boxes(batch, src_h, src_w, self.min_area, self.max_area, self.seed,
+                             first_sample, self.flip, device)
+
+    def __call__(self, src_u8, first_sample=0):
+        """src_u8: [B, H, W, 3] uint8 CUDA.  Returns the model input (bf16 channels_last
+        [B,4,S,S] with a zero 4th channel, or fp32 NCHW [B,3,S,S] like DALI emits)."""
+        b, h, w, _ = src_u8.shape
+        bx = self.boxes(b, h, w, first_sample, src_u8.device)
+        return ops.augment(src_u8, bx, self.image_size, DATA_MEAN, DATA_STD,
+                           0 if self.output == "nhwc4_bf16" else 1)
+
+
+class SyntheticSource:
+    """Pool of `pool` random images (uint8 HWC) and labels, generated once with a fixed seed."""
+
+    def __init__(self, pool=1024, height=256, width=256, num_classes=1000, seed=0, device="cuda",
+                 pinned_host=False):
+        g = torch.Generator().manual_seed(seed)
+        imgs = torch.randint(0, 256, (pool, height, width, 3), dtype=torch.uint8, generator=g)
+        labels = torch.randint(0, num_classes, (pool,), generator=g)
+        self.pool, self.num_classes = pool, num_classes
+        if pinned_host:
+            self.images, self.labels = imgs.pin_memory(), labels.pin_memory()
+        else:
+            self.images, self.labels = imgs.to(device), labels.to(device)
+
+    def batch(self, index, batch_size):
+        lo = (index * batch_size) % self.pool
+        if lo + batch_size <= self.pool:
+            return self.images[lo:lo + batch_size], self.labels[lo:lo + batch_size]
+        idx = (torch.arange(batch_size) + lo) % self.pool
+        idx = idx.to(self.images.device)
+        return self.images[idx], self.labels[idx]
+
+
+class SyntheticLoader:
+    def __init__(self, cfg, source=None, epoch_size=None, rank=0, world_size=1, train=True,
+                 output="nhwc4_bf16", one_hot=True, device="cuda"):
+        self.cfg = cfg
+        self.batch_size = cfg.batch_size
+        self.num_classes = cfg.num_classes
+        self.rank, self.world_size, self.train, self.one_hot = rank, world_size, train, one_hot
+        self.device = device
+        self.source = source or SyntheticSource(num_classes=cfg.num_classes, device=device)
+        self.epoch_size = epoch_size or self.source.pool
+        min_area = getattr(cfg, "min_area", 0.08) if train else 1.0
+        self.augment = GpuAugment(cfg.image_size, min_area, 1.0, seed=getattr(cfg, "seed", 0),
+                                  flip=train, output=output)
+        self._epoch = 0
+
+    def __len__(self):
+        # drop-last, sharded by rank like the DALI readers (dali_dataloader.py:47,175)
+        return self.epoch_size // (self.batch_size * self.world_size)
+
+    def __iter__(self):
+        n = len(self)
+        for i in range(n):
+            gi = (self._epoch * n + i) * self.world_size + self.rank
+            imgs, labels = self.source.batch(gi, self.batch_size)
+            if not imgs.is_cuda:
+                imgs = imgs.to(self.device, non_blocking=True)
+                labels = labels.to(self.device, non_blocking=True)
+            data = self.augment(imgs, first_sample=gi * self.batch_size)
+            target = ops.one_hot(labels, self.num_classes) if self.one_hot else labels
+            yield data, target
+        self._epoch += 1
+
+
+class DataManager:
+    """Stage list semantics of DaliDataManager (dali_dataloader.py:189-239)."""
+
+    def __init__(self, cfg, source=None, rank=0, world_size=1, **loader_kw):
+        self.cfg = cfg
+        self.stages = cfg.run.stages
+        self.tot_epochs = max(stage.end for stage in self.stages)
+        self._validate_stages()
+        self.source, self.rank, self.world_size, self.loader_kw = source, rank, world_size, loader_kw
+        self.loader = None
+        self.val_loader = None
+        self.start_epoch = None
+        self.end_epoch = None
+
+    def __len__(self):
+        return len(self.stages)
+
+    def _validate_stages(self):
+        end = 0
+        for stage in self.stages:
+            assert stage.start == end, "error in data stages. start != end"
+            assert stage.end > stage.start, "error in data stages, end <= start"
+            end = stage.end
+
+    def set_stage(self, idx):
+        self.start_epoch = self.stages[idx].start
+        self.end_epoch = self.stages[idx].end
+        if self.stages[idx].extra_args is None and self.loader is not None:
+            return   # only the learning rate changed
+        train_cfg = copy.deepcopy(self.cfg.loader)
+        val_cfg = copy.deepcopy(self.cfg.val_loader)
+        if self.stages[idx].extra_args is not None:
+            for key, value in self.stages[idx].extra_args.items():
+                setattr(train_cfg, key, value)
+        val_cfg.image_size = train_cfg.image_size
+        self.loader = SyntheticLoader(train_cfg, self.source, rank=self.rank,
+                                      world_size=self.world_size, train=True, **self.loader_kw)
+        self.val_loader = SyntheticLoader(val_cfg, self.source, rank=self.rank,
+                                          world_size=self.world_size, train=False, **self.loader_kw)

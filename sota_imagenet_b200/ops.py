@@ -7,7 +7,11 @@ channels_last (= KRSC in memory).  PyTorch is only the allocator / stream provid
 import torch
 
 from . import _lib
-from ._lib import c_void_p, call
+from ._lib import c_void_p
+
+
+def call(name, *args):
+    _lib.call(name, *args)
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE = 0, 1, 2, 3

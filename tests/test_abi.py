@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library loads, exports every symbol include/sib200.h declares, and refuses to
+compute without a GPU (no CPU fallback anywhere in the product path)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+import torch
+
+from sota_imagenet_b200 import _lib, ops
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    protos = _lib.header_prototypes()
+    assert len(protos) >= 30
+    for name in protos:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert set(protos) <= exported
+    assert lib.sib_abi_version() == 1
+
+
+def test_library_contains_blackwell_kernels():
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass          # tcgen05.mma
+    assert "UTMALDG" in sass          # TMA loads (tiled + im2col)
+    assert "LDTM" in sass             # tcgen05.ld
+    assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    x = torch.zeros(1, 64, 4, 4)
+    w = torch.zeros(64, 64, 1, 1)
+    with pytest.raises(_lib.SibError):
+        ops.conv2d_fprop(x, w)
+    from sota_imagenet_b200 import models
+    with pytest.raises(_lib.SibError):
+        models.resnet50()(torch.zeros(1, 3, 32, 32))
+
+
+def test_product_never_imports_oracle():
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sota_imagenet_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f

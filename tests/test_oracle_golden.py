@@ -1,0 +1,98 @@
+"""CPU: the oracle restatements against the committed golden vectors, which were produced by
+the REFERENCE's own code (oracle/make_golden.py imports /root/reference/sota_imagenet/
+angular_losses.py and torch.optim._multi_tensor.SGD) in the build container."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import augment_ref, torch_ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name), weights_only=False)
+
+
+def test_heads_restatement_matches_reference_classes():
+    g = _load("heads.pt")
+    x, w, y = g["x"], g["w"], g["y"]
+    for name, (s, m, sm, fn) in {
+        "arc": (10.0, 0.2, 0.1, torch_ref.arcface_logits),
+        "arc_s64": (64.0, 0.5, 0.0, torch_ref.arcface_logits),
+        "adacos_fixed": (10.0, 0.2, 0.1, torch_ref.cosface_logits),
+    }.items():
+        xr = x.clone().requires_grad_(True)
+        wr = w.clone().requires_grad_(True)
+        cos = torch_ref.sphere_linear(xr, wr)
+        loss = torch_ref.smooth_cross_entropy(fn(cos, y, s, m), y, sm)
+        loss.backward()
+        assert torch.allclose(cos, g[name]["cos"], atol=1e-6)
+        assert torch.allclose(loss, g[name]["loss"], atol=1e-5), name
+        assert torch.allclose(xr.grad, g[name]["dx"], atol=1e-5, rtol=1e-4), name
+        assert torch.allclose(wr.grad, g[name]["dw"], atol=1e-5, rtol=1e-4), name
+    # LargeMarginCosineLoss: only W is normalised
+    xn = g["cosface_lm"]["xn"]
+    cos = torch.nn.functional.linear(xn, torch.nn.functional.normalize(w))
+    loss = torch_ref.smooth_cross_entropy(torch_ref.cosface_logits(cos, y, 30.0, 0.4), y, 0.0)
+    assert torch.allclose(loss, g["cosface_lm"]["loss"], atol=1e-5)
+
+
+def test_cross_entropy_restatement():
+    g = _load("cross_entropy.pt")
+    for case in g["cases"]:
+        lr = g["logits"].clone().requires_grad_(True)
+        loss = torch_ref.smooth_cross_entropy(lr, g["y"], case["smoothing"], case["temperature"])
+        loss.backward()
+        assert torch.allclose(loss, case["loss"], atol=1e-6)
+        assert torch.allclose(lr.grad, case["grad"], atol=1e-7)
+        # closed-form gradient of SURVEY App. E.2 (what the CUDA kernel implements)
+        t = torch.zeros_like(g["logits"]).scatter_(1, g["y"][:, None], 1.0)
+        s, T = case["smoothing"], case["temperature"]
+        q = (1 - s) * t + s / t.shape[1]
+        p = torch.softmax(g["logits"] / T, 1)
+        grad = (p * q.sum(1, keepdim=True) - q) / (t.shape[0] * T)
+        assert torch.allclose(grad, case["grad"], atol=1e-6)
+
+
+def test_sgd_arithmetic_restatement():
+    """torch/optim/sgd.py semantics written out == reference optimizer runs."""
+    g = _load("sgd.pt")
+    for nesterov, key in ((False, "plain"), (True, "nesterov")):
+        p = g["p0"].clone()
+        buf = None
+        for grad, lr, want in zip(g["grads"], g["lrs"], g["runs"][key]):
+            d = grad + 3e-5 * p
+            buf = d.clone() if buf is None else 0.9 * buf + d
+            d = d + 0.9 * buf if nesterov else buf
+            p = p - lr * d
+            assert torch.allclose(p, want, atol=1e-6, rtol=1e-6)
+
+
+def test_augment_oracle_vs_golden_and_host_twin():
+    g = _load("augment.pt")
+    boxes = [augment_ref.rrc_box(256, 256, 0.08, 1.0, 42, i) for i in range(256)]
+    assert np.array_equal(np.array(boxes, np.int32), g["boxes_256_seed42"].numpy())
+    from sota_imagenet_b200 import ops
+    host = [ops.rrc_box_host(256, 256, 0.08, 1.0, 42, i) for i in range(256)]
+    assert host == boxes                         # C twin of the CUDA generator, bit-exact
+    wide = [ops.rrc_box_host(100, 400, 0.9, 1.0, 7, i) for i in range(64)]
+    assert np.array_equal(np.array(wide, np.int32), g["boxes_100x400_seed7_minarea09"].numpy())
+    # invariants of dali_dataloader.py:65-72: box inside the image, aspect in [0.75,1.25] (+rounding)
+    for x0, y0, w, h, flip in boxes:
+        assert 0 <= x0 and 0 <= y0 and x0 + w <= 256 and y0 + h <= 256 and flip in (0, 1)
+        assert 0.70 <= w / h <= 1.32
+    out = augment_ref.augment_image(g["img"][0].numpy(), g["boxes"][0].tolist(), 32)
+    assert np.allclose(out, g["out"][0].numpy(), atol=1e-6)
+    assert out.min() >= -2.5001 and out.max() <= 2.5001
+
+
+def test_resnet_oracle_pinned():
+    g = _load("resnet50_step.pt")
+    model = torch_ref.resnet50(seed=0)
+    opt = torch_ref.make_sgd(model.parameters(), lr=0.1)
+    x, y = torch_ref.synthetic_batch(2, 64, seed=0)
+    losses = [torch_ref.train_step(model, opt, x, y) for _ in range(2)]
+    assert np.allclose(losses, g["losses"], rtol=1e-4)
+    assert torch.allclose(model.bn1.running_mean, g["bn1_running_mean"], atol=1e-5)
