@@ -13,7 +13,7 @@ y = torch.randint(0, 1000, (B,), device="cuda")
 
 def fwd():
     with torch.no_grad():
-        return net.fwd(x, True)[0]
+        net.ensure_arena(); return net.fwd(x, True)[0]
 def fwd_loss():
     return crit(net(x), y)
 def fwd_bwd():
