@@ -78,14 +78,17 @@ int sib_bn_eval_scale(const float* gamma, const float* beta, const float* runnin
 int sib_bn_apply(const void* x, const float* scale_shift, const void* res,
                  const float* scale_shift2, void* y, long M, int C, int act, float slope,
                  void* stream);
-/* sums[0..1][C] = (sum g, sum g*xhat), g = dy * act'(out); with x2: sums[2..3] for the 2nd BN */
-int sib_bn_bwd_reduce(const void* dy, const void* out, const void* x, const float* mean_invstd,
-                      const void* x2, const float* mean_invstd2, long M, int C, int act,
-                      float slope, float* sums, void* stream);
-int sib_bn_bwd_apply(const void* dy, const void* out, const void* x, const float* mean_invstd,
-                     const float* gamma, const float* sums, const void* x2,
-                     const float* mean_invstd2, const float* gamma2, void* dx, void* dx2,
-                     void* gout, long M, int C, double count, int act, float slope, void* stream);
+/* sums[0..1][C] = (sum g, sum g*xhat), g = dy * act'(.); with x2: sums[2..3] for the 2nd BN.
+ * The activation mask is taken from `out` (stored forward output) when given, otherwise it is
+ * recomputed bit-exactly from x and the forward's scale/shift (`mask_ss`, [2][C]). */
+int sib_bn_bwd_reduce(const void* dy, const void* out, const float* mask_ss, const void* x,
+                      const float* mean_invstd, const void* x2, const float* mean_invstd2, long M,
+                      int C, int act, float slope, float* sums, void* stream);
+int sib_bn_bwd_apply(const void* dy, const void* out, const float* mask_ss, const void* x,
+                     const float* mean_invstd, const float* gamma, const float* sums,
+                     const void* x2, const float* mean_invstd2, const float* gamma2, void* dx,
+                     void* dx2, void* gout, long M, int C, double count, int act, float slope,
+                     void* stream);
 int sib_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int accumulate,
                       void* stream);
 

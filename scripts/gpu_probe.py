@@ -212,6 +212,14 @@ def run_norm():
         sgx = (g * xhat).sum(dim=(0, 2, 3))
         dxref = (gamma * mi[1]).view(1, -1, 1, 1) * (g - sg.view(1, -1, 1, 1) / m - xhat * sgx.view(1, -1, 1, 1) / m)
         sums = ops.bn_bwd_reduce(dy, y, x, mi, ops.ACT_RELU)
+        # plain BN+ReLU with the mask recomputed from x
+        y0 = ops.bn_apply(x, ss, act=ops.ACT_RELU)
+        s_out = ops.bn_bwd_reduce(dy, y0, x, mi, ops.ACT_RELU)
+        s_re = ops.bn_bwd_reduce(dy, None, x, mi, ops.ACT_RELU, mask_ss=ss)
+        report("bn_bwd_reduce remask == out-mask", rel_err(s_re, s_out), 1e-6)
+        d_out, _, _ = ops.bn_bwd_apply(dy, y0, x, mi, gamma, s_out, m, ops.ACT_RELU)
+        d_re, _, _ = ops.bn_bwd_apply(dy, None, x, mi, gamma, s_out, m, ops.ACT_RELU, mask_ss=ss)
+        report("bn_bwd_apply remask == out-mask", rel_err(d_re, d_out), 0.0)
         report("bn_bwd_reduce", rel_err(sums, torch.stack([sg, sgx])), 1e-4)
         dx, _, gout = ops.bn_bwd_apply(dy, y, x, mi, gamma, sums, m, ops.ACT_RELU, want_g=True)
         report("bn_bwd_apply dx", rel_err(dx, dxref), 1e-2)

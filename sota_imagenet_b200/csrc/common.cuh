@@ -56,7 +56,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // streaming 128-bit global access (read-once / write-once data)
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;

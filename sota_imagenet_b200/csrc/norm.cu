@@ -25,53 +25,79 @@ __device__ __forceinline__ float act_grad(float out, int act, float slope) {
 }
 
 // ---------------------------------------------------------------------------
-// per-channel sum / sum of squares of x[M][C]
+// Thread layout shared by all BatchNorm kernels: a thread OWNS one 8-channel vector column
+// (tx) and walks rows (ty + k * rows-in-flight), so every per-channel coefficient is loaded
+// once into registers and all global traffic is 128-bit and fully coalesced (adjacent tx =
+// adjacent 16 bytes; adjacent ty = adjacent rows = adjacent memory).  U rows are in flight per
+// thread to cover HBM latency.  Requires C % 8 == 0 and C / 8 <= kRedThreads.
 // ---------------------------------------------------------------------------
-// thread layout: tx = vector (8 channels) within the row, ty = row lane.
-// Requires C % 8 == 0 and C/8 <= kRedThreads.
-template <int NACC, class F>
-__device__ __forceinline__ void channel_reduce(long M, int C, float* __restrict__ out, F body) {
-  const int cvec = C >> 3;
-  const int rpb = kRedThreads / cvec;       // rows handled per block iteration
-  const int tx = threadIdx.x % cvec;
-  const int ty = threadIdx.x / cvec;
-  float acc[NACC][8];
-#pragma unroll
-  for (int a = 0; a < NACC; ++a)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
-  if (ty < rpb) {
-    for (long r = (long)blockIdx.x * rpb + ty; r < M; r += (long)gridDim.x * rpb)
-      body(r, tx, acc);
+struct ColOwner {
+  int tx, ty, rpb;
+  long row0, stride;
+  bool active;
+  __device__ __forceinline__ ColOwner(int C) {
+    const int cvec = C >> 3;
+    rpb = kRedThreads / cvec;
+    tx = threadIdx.x % cvec;
+    ty = threadIdx.x / cvec;
+    active = ty < rpb;
+    row0 = (long)blockIdx.x * rpb + ty;
+    stride = (long)gridDim.x * rpb;
   }
-  __shared__ float red[NACC][kRedThreads * 8 / 8][8];   // [acc][thread][8]
+};
+
+__device__ __forceinline__ void load8f(const float* p, float* v) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// cross-thread reduction of per-thread column accumulators -> fp32 atomics on out[NACC][C]
+template <int NACC>
+__device__ __forceinline__ void column_reduce_store(const ColOwner& co, int C,
+                                                    float (&acc)[NACC][8], float* __restrict__ out) {
+  __shared__ float red[NACC][kRedThreads][8];
 #pragma unroll
   for (int a = 0; a < NACC; ++a)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[a][threadIdx.x][j] = acc[a][j];
+    for (int j = 0; j < 8; ++j) red[a][threadIdx.x][j] = co.active ? acc[a][j] : 0.f;
   __syncthreads();
-  // first `cvec*8` threads each own one channel and sum over the row lanes
+  const int cvec = C >> 3;
   for (int idx = threadIdx.x; idx < NACC * C; idx += kRedThreads) {
     const int a = idx / C;
     const int c = idx - a * C;
     const int v = c >> 3, j = c & 7;
     float s = 0.f;
-    for (int y = 0; y < rpb; ++y) s += red[a][y * cvec + v][j];
+    for (int y = 0; y < co.rpb; ++y) s += red[a][y * cvec + v][j];
     atomicAdd(out + (long)a * C + c, s);
   }
 }
 
+constexpr int kU = 4;   // rows in flight per thread
+
 __global__ void __launch_bounds__(kRedThreads)
 bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long M, int C, float* __restrict__ stats) {
-  channel_reduce<2>(M, C, stats, [&](long r, int tx, float (&acc)[2][8]) {
-    float f[8];
-    unpack8(ldg_stream(x + r * C + tx * 8), f);
+  const ColOwner co(C);
+  float acc[2][8] = {};
+  if (co.active) {
+    const __nv_bfloat16* px = x + co.tx * 8;
+    for (long r = co.row0; r < M; r += kU * co.stride) {
+      uint4 v[kU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += f[j];
-      acc[1][j] += f[j] * f[j];
+      for (int u = 0; u < kU; ++u)
+        if (r + u * co.stride < M) v[u] = ldg_stream(px + (r + u * co.stride) * C);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (r + u * co.stride < M) {
+          float f[8];
+          unpack8(v[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[0][j] += f[j]; acc[1][j] += f[j] * f[j]; }
+        }
+      }
     }
-  });
+  }
+  column_reduce_store<2>(co, C, acc, stats);
 }
 
 // ---------------------------------------------------------------------------
@@ -118,144 +144,224 @@ __global__ void bn_eval_scale_kernel(const float* __restrict__ gamma, const floa
 // ---------------------------------------------------------------------------
 // apply: y = act(x*scale + shift [+ res | + res*scale2 + shift2])
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int MODE>   // 0: plain, 1: + res, 2: + res*scale2 + shift2
+__global__ void __launch_bounds__(kRedThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ss,
                 const __nv_bfloat16* __restrict__ res, const float* __restrict__ ss2,
-                __nv_bfloat16* __restrict__ y, long nvec, int C, int act, float slope) {
-  const int cvec = C >> 3;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cvec) * 8;
-    float f[8], o[8];
-    unpack8(ldg_stream(x + i * 8), f);
-    const float4 sa = __ldg(reinterpret_cast<const float4*>(ss + c0));
-    const float4 sb = __ldg(reinterpret_cast<const float4*>(ss + c0 + 4));
-    const float4 ha = __ldg(reinterpret_cast<const float4*>(ss + C + c0));
-    const float4 hb = __ldg(reinterpret_cast<const float4*>(ss + C + c0 + 4));
-    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+                __nv_bfloat16* __restrict__ y, long M, int C, int act, float slope) {
+  const ColOwner co(C);
+  if (!co.active) return;
+  float sc[8], sh[8], sc2[8], sh2[8];
+  load8f(ss + co.tx * 8, sc);
+  load8f(ss + C + co.tx * 8, sh);
+  if (MODE == 2) {
+    load8f(ss2 + co.tx * 8, sc2);
+    load8f(ss2 + C + co.tx * 8, sh2);
+  }
+  const long col = co.tx * 8;
+  for (long r = co.row0; r < M; r += kU * co.stride) {
+    uint4 vx[kU], vr[kU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], sc[j], sh[j]);
-    if (res != nullptr) {
-      float rr[8];
-      unpack8(ldg_stream(res + i * 8), rr);
-      if (ss2 != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] += fmaf(rr[j], __ldg(ss2 + c0 + j), __ldg(ss2 + C + c0 + j));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += rr[j];
+    for (int u = 0; u < kU; ++u) {
+      const long rr = r + u * co.stride;
+      if (rr < M) {
+        vx[u] = ldg_stream(x + rr * C + col);
+        if (MODE != 0) vr[u] = ldg_stream(res + rr * C + col);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = act_fwd(o[j], act, slope);
-    stg_stream(y + i * 8, pack8(o));
+    for (int u = 0; u < kU; ++u) {
+      const long rr = r + u * co.stride;
+      if (rr < M) {
+        float f[8], o[8];
+        unpack8(vx[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], sc[j], sh[j]);
+        if (MODE != 0) {
+          float q[8];
+          unpack8(vr[u], q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += (MODE == 2) ? fmaf(q[j], sc2[j], sh2[j]) : q[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = act_fwd(o[j], act, slope);
+        stg_stream(y + rr * C + col, pack8(o));
+      }
+    }
   }
 }
 
 // ---------------------------------------------------------------------------
-// backward reduce: g = dy * act'(out);  sums[0] = sum g, sums[1] = sum g * xhat
-// optional second BN (downsample branch): sums[2], sums[3] with x2 / mean_invstd2
+// backward.  g = dy * act'(.) where the activation mask comes either from the stored output
+// (`out`, needed when a residual was added) or is recomputed from x with the forward's own
+// scale/shift (`mask_ss`): fmaf(x, scale, shift) > 0 is bit-identical to what the forward
+// evaluated, so no mask tensor and no read of `out` is needed for plain BN+act.
+//   reduce: sums[0] = sum g, sums[1] = sum g*xhat (+ sums[2..3] for a second BN sharing g)
+//   apply : dx = A*g + B*x + Cc with per-channel A = gamma*invstd, B = -gamma*invstd^2*sgx/m,
+//           Cc = -gamma*invstd*sg/m + gamma*invstd^2*mean*sgx/m
 // ---------------------------------------------------------------------------
+template <bool SECOND, bool USE_OUT>
 __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ out,
-                     const __nv_bfloat16* __restrict__ x, const float* __restrict__ mi,
-                     const __nv_bfloat16* __restrict__ x2, const float* __restrict__ mi2, long M,
-                     int C, int act, float slope, float* __restrict__ sums) {
-  if (x2 == nullptr) {
-    channel_reduce<2>(M, C, sums, [&](long r, int tx, float (&acc)[2][8]) {
-      float g[8], o[8], xv[8];
-      const long off = r * C + tx * 8;
-      unpack8(ldg_stream(dy + off), g);
-      unpack8(ldg_stream(x + off), xv);
-      if (act != SIB_ACT_NONE) {
-        unpack8(ldg_stream(out + off), o);
+                     const float* __restrict__ mask_ss, const __nv_bfloat16* __restrict__ x,
+                     const float* __restrict__ mi, const __nv_bfloat16* __restrict__ x2,
+                     const float* __restrict__ mi2, long M, int C, int act, float slope,
+                     float* __restrict__ sums) {
+  const ColOwner co(C);
+  constexpr int NACC = SECOND ? 4 : 2;
+  float acc[NACC][8] = {};
+  if (co.active) {
+    float mean[8], invstd[8], mean2[8], invstd2[8], sc[8], sh[8];
+    load8f(mi + co.tx * 8, mean);
+    load8f(mi + C + co.tx * 8, invstd);
+    if (SECOND) {
+      load8f(mi2 + co.tx * 8, mean2);
+      load8f(mi2 + C + co.tx * 8, invstd2);
+    }
+    const bool remask = !USE_OUT && act != SIB_ACT_NONE;
+    if (remask) {
+      load8f(mask_ss + co.tx * 8, sc);
+      load8f(mask_ss + C + co.tx * 8, sh);
+    }
+    const long col = co.tx * 8;
+    for (long r = co.row0; r < M; r += kU * co.stride) {
+      uint4 vg[kU], vx[kU], vo[kU], vw[kU];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= act_grad(o[j], act, slope);
+      for (int u = 0; u < kU; ++u) {
+        const long rr = r + u * co.stride;
+        if (rr < M) {
+          vg[u] = ldg_stream(dy + rr * C + col);
+          vx[u] = ldg_stream(x + rr * C + col);
+          if (USE_OUT) vo[u] = ldg_stream(out + rr * C + col);
+          if (SECOND) vw[u] = ldg_stream(x2 + rr * C + col);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = tx * 8 + j;
-        const float xh = (xv[j] - __ldg(mi + c)) * __ldg(mi + C + c);
-        acc[0][j] += g[j];
-        acc[1][j] += g[j] * xh;
-      }
-    });
-  } else {
-    channel_reduce<4>(M, C, sums, [&](long r, int tx, float (&acc)[4][8]) {
-      float g[8], o[8], xv[8], xw[8];
-      const long off = r * C + tx * 8;
-      unpack8(ldg_stream(dy + off), g);
-      unpack8(ldg_stream(x + off), xv);
-      unpack8(ldg_stream(x2 + off), xw);
-      if (act != SIB_ACT_NONE) {
-        unpack8(ldg_stream(out + off), o);
+      for (int u = 0; u < kU; ++u) {
+        const long rr = r + u * co.stride;
+        if (rr < M) {
+          float g[8], xv[8];
+          unpack8(vg[u], g);
+          unpack8(vx[u], xv);
+          if (USE_OUT) {
+            float o[8];
+            unpack8(vo[u], o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= act_grad(o[j], act, slope);
-      }
+            for (int j = 0; j < 8; ++j) g[j] *= act_grad(o[j], act, slope);
+          } else if (remask) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = tx * 8 + j;
-        const float xh = (xv[j] - __ldg(mi + c)) * __ldg(mi + C + c);
-        const float xh2 = (xw[j] - __ldg(mi2 + c)) * __ldg(mi2 + C + c);
-        acc[0][j] += g[j];
-        acc[1][j] += g[j] * xh;
-        acc[2][j] += g[j];
-        acc[3][j] += g[j] * xh2;
+            for (int j = 0; j < 8; ++j) g[j] *= act_grad(fmaf(xv[j], sc[j], sh[j]), act, slope);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[0][j] += g[j];
+            acc[1][j] += g[j] * ((xv[j] - mean[j]) * invstd[j]);
+          }
+          if (SECOND) {
+            float xw[8];
+            unpack8(vw[u], xw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[2][j] += g[j];
+              acc[3][j] += g[j] * ((xw[j] - mean2[j]) * invstd2[j]);
+            }
+          }
+        }
       }
-    });
+    }
   }
+  column_reduce_store<NACC>(co, C, acc, sums);
 }
 
-// ---------------------------------------------------------------------------
-// backward apply: dx = gamma*invstd * (g - sum_g/m - xhat * sum_gx/m)
-// writes dx (for x), optionally dx2 (second BN) and g itself (residual-branch grad)
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <bool SECOND, bool USE_OUT, bool WRITE_G>
+__global__ void __launch_bounds__(kRedThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ out,
-                    const __nv_bfloat16* __restrict__ x, const float* __restrict__ mi,
-                    const float* __restrict__ gamma, const float* __restrict__ sums,
-                    const __nv_bfloat16* __restrict__ x2, const float* __restrict__ mi2,
-                    const float* __restrict__ gamma2, __nv_bfloat16* __restrict__ dx,
-                    __nv_bfloat16* __restrict__ dx2, __nv_bfloat16* __restrict__ gout, long nvec,
-                    int C, float inv_count, int act, float slope) {
-  const int cvec = C >> 3;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cvec) * 8;
-    float g[8], o[8], xv[8], d[8];
-    unpack8(ldg_stream(dy + i * 8), g);
-    unpack8(ldg_stream(x + i * 8), xv);
-    if (act != SIB_ACT_NONE) {
-      unpack8(ldg_stream(out + i * 8), o);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= act_grad(o[j], act, slope);
-    }
+                    const float* __restrict__ mask_ss, const __nv_bfloat16* __restrict__ x,
+                    const float* __restrict__ mi, const float* __restrict__ gamma,
+                    const float* __restrict__ sums, const __nv_bfloat16* __restrict__ x2,
+                    const float* __restrict__ mi2, const float* __restrict__ gamma2,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx2,
+                    __nv_bfloat16* __restrict__ gout, long M, int C, float inv_count, int act,
+                    float slope) {
+  const ColOwner co(C);
+  if (!co.active) return;
+  float cA[8], cB[8], cC[8], dA[8], dB[8], dC[8], sc[8], sh[8];
+  {
+    float mean[8], invstd[8], gm[8], sg[8], sgx[8];
+    load8f(mi + co.tx * 8, mean);
+    load8f(mi + C + co.tx * 8, invstd);
+    load8f(sums + co.tx * 8, sg);
+    load8f(sums + C + co.tx * 8, sgx);
+    if (gamma) load8f(gamma + co.tx * 8, gm);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float mean = __ldg(mi + c), invstd = __ldg(mi + C + c);
-      const float xh = (xv[j] - mean) * invstd;
-      const float gm = gamma ? __ldg(gamma + c) : 1.f;
-      d[j] = gm * invstd * (g[j] - __ldg(sums + c) * inv_count - xh * __ldg(sums + C + c) * inv_count);
+      const float a = (gamma ? gm[j] : 1.f) * invstd[j];
+      cA[j] = a;
+      cB[j] = -a * invstd[j] * sgx[j] * inv_count;
+      cC[j] = -a * sg[j] * inv_count - cB[j] * mean[j];
     }
-    stg_stream(dx + i * 8, pack8(d));
-    if (x2 != nullptr) {
-      float xw[8];
-      unpack8(ldg_stream(x2 + i * 8), xw);
+    if (SECOND) {
+      load8f(mi2 + co.tx * 8, mean);
+      load8f(mi2 + C + co.tx * 8, invstd);
+      load8f(sums + 2 * C + co.tx * 8, sg);
+      load8f(sums + 3 * C + co.tx * 8, sgx);
+      if (gamma2) load8f(gamma2 + co.tx * 8, gm);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        const float mean = __ldg(mi2 + c), invstd = __ldg(mi2 + C + c);
-        const float xh = (xw[j] - mean) * invstd;
-        const float gm = gamma2 ? __ldg(gamma2 + c) : 1.f;
-        d[j] = gm * invstd *
-               (g[j] - __ldg(sums + 2 * C + c) * inv_count - xh * __ldg(sums + 3 * C + c) * inv_count);
+        const float a = (gamma2 ? gm[j] : 1.f) * invstd[j];
+        dA[j] = a;
+        dB[j] = -a * invstd[j] * sgx[j] * inv_count;
+        dC[j] = -a * sg[j] * inv_count - dB[j] * mean[j];
       }
-      stg_stream(dx2 + i * 8, pack8(d));
     }
-    if (gout != nullptr) stg_stream(gout + i * 8, pack8(g));
+  }
+  const bool remask = !USE_OUT && act != SIB_ACT_NONE;
+  if (remask) {
+    load8f(mask_ss + co.tx * 8, sc);
+    load8f(mask_ss + C + co.tx * 8, sh);
+  }
+  const long col = co.tx * 8;
+  for (long r = co.row0; r < M; r += kU * co.stride) {
+    uint4 vg[kU], vx[kU], vo[kU], vw[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long rr = r + u * co.stride;
+      if (rr < M) {
+        vg[u] = ldg_stream(dy + rr * C + col);
+        vx[u] = ldg_stream(x + rr * C + col);
+        if (USE_OUT) vo[u] = ldg_stream(out + rr * C + col);
+        if (SECOND) vw[u] = ldg_stream(x2 + rr * C + col);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long rr = r + u * co.stride;
+      if (rr < M) {
+        float g[8], xv[8], d[8];
+        unpack8(vg[u], g);
+        unpack8(vx[u], xv);
+        if (USE_OUT) {
+          float o[8];
+          unpack8(vo[u], o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] *= act_grad(o[j], act, slope);
+        } else if (remask) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] *= act_grad(fmaf(xv[j], sc[j], sh[j]), act, slope);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(cA[j], g[j], fmaf(cB[j], xv[j], cC[j]));
+        stg_stream(dx + rr * C + col, pack8(d));
+        if (SECOND) {
+          float xw[8];
+          unpack8(vw[u], xw);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = fmaf(dA[j], g[j], fmaf(dB[j], xw[j], dC[j]));
+          stg_stream(dx2 + rr * C + col, pack8(d));
+        }
+        if (WRITE_G) stg_stream(gout + rr * C + col, pack8(g));
+      }
+    }
   }
 }
 
@@ -441,14 +547,19 @@ static int check_c(int C) {
   return 0;
 }
 
+static int bn_grid(long M, int C) {
+  const int rpb = kRedThreads / (C / 8);
+  long blocks = (M + (long)rpb * kU - 1) / ((long)rpb * kU);
+  const long cap = (long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
 extern "C" int sib_bn_stats(const void* x, long M, int C, float* stats, void* stream) {
   if (int rc = check_c(C)) return rc;
   SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, ST(stream)));
-  const int rpb = kRedThreads / (C / 8);
-  long blocks = (M + rpb - 1) / rpb;
-  long cap = (long)sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  bn_stats_kernel<<<(int)blocks, kRedThreads, 0, ST(stream)>>>(
+  bn_stats_kernel<<<bn_grid(M, C), kRedThreads, 0, ST(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), M, C, stats);
   SIB_LAUNCH_CHECK();
   return 0;
@@ -477,47 +588,81 @@ extern "C" int sib_bn_eval_scale(const float* gamma, const float* beta, const fl
 extern "C" int sib_bn_apply(const void* x, const float* scale_shift, const void* res,
                             const float* scale_shift2, void* y, long M, int C, int act,
                             float slope, void* stream) {
-  SIB_CHECK(C % 8 == 0, "bn_apply: C %% 8 != 0");
-  const long nvec = M * (C / 8);
-  bn_apply_kernel<<<ew_grid(nvec, 256), 256, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), scale_shift, static_cast<const __nv_bfloat16*>(res),
-      scale_shift2, static_cast<__nv_bfloat16*>(y), nvec, C, act, slope);
+  if (int rc = check_c(C)) return rc;
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(res);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  const int grid = bn_grid(M, C);
+  if (res == nullptr)
+    bn_apply_kernel<0><<<grid, kRedThreads, 0, ST(stream)>>>(xp, scale_shift, rp, scale_shift2, yp,
+                                                            M, C, act, slope);
+  else if (scale_shift2 == nullptr)
+    bn_apply_kernel<1><<<grid, kRedThreads, 0, ST(stream)>>>(xp, scale_shift, rp, scale_shift2, yp,
+                                                            M, C, act, slope);
+  else
+    bn_apply_kernel<2><<<grid, kRedThreads, 0, ST(stream)>>>(xp, scale_shift, rp, scale_shift2, yp,
+                                                            M, C, act, slope);
   SIB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int sib_bn_bwd_reduce(const void* dy, const void* out, const void* x,
-                                 const float* mean_invstd, const void* x2,
+extern "C" int sib_bn_bwd_reduce(const void* dy, const void* out, const float* mask_ss,
+                                 const void* x, const float* mean_invstd, const void* x2,
                                  const float* mean_invstd2, long M, int C, int act, float slope,
                                  float* sums, void* stream) {
   if (int rc = check_c(C)) return rc;
+  SIB_CHECK(act == SIB_ACT_NONE || out != nullptr || mask_ss != nullptr,
+            "bn_bwd_reduce: activation mask needs `out` or `mask_ss`");
   const int nacc = x2 ? 4 : 2;
   SIB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * nacc * C, ST(stream)));
-  const int rpb = kRedThreads / (C / 8);
-  long blocks = (M + rpb - 1) / rpb;
-  long cap = (long)sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  bn_bwd_reduce_kernel<<<(int)blocks, kRedThreads, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(out),
-      static_cast<const __nv_bfloat16*>(x), mean_invstd, static_cast<const __nv_bfloat16*>(x2),
-      mean_invstd2, M, C, act, slope, sums);
+  const int grid = bn_grid(M, C);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(out);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* xq = static_cast<const __nv_bfloat16*>(x2);
+#define SIB_RED(S, O)                                                                         \
+  bn_bwd_reduce_kernel<S, O><<<grid, kRedThreads, 0, ST(stream)>>>(a, o, mask_ss, xp, mean_invstd, \
+                                                                 xq, mean_invstd2, M, C, act,  \
+                                                                 slope, sums)
+  const bool use_out = out != nullptr && act != SIB_ACT_NONE;
+  if (x2) { if (use_out) SIB_RED(true, true); else SIB_RED(true, false); }
+  else    { if (use_out) SIB_RED(false, true); else SIB_RED(false, false); }
+#undef SIB_RED
   SIB_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const void* x,
-                                const float* mean_invstd, const float* gamma, const float* sums,
-                                const void* x2, const float* mean_invstd2, const float* gamma2,
-                                void* dx, void* dx2, void* gout, long M, int C, double count,
-                                int act, float slope, void* stream) {
-  SIB_CHECK(C % 8 == 0, "bn_bwd_apply: C %% 8 != 0");
-  const long nvec = M * (C / 8);
-  bn_bwd_apply_kernel<<<ew_grid(nvec, 256), 256, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(out),
-      static_cast<const __nv_bfloat16*>(x), mean_invstd, gamma, sums,
-      static_cast<const __nv_bfloat16*>(x2), mean_invstd2, gamma2,
-      static_cast<__nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dx2),
-      static_cast<__nv_bfloat16*>(gout), nvec, C, (float)(1.0 / count), act, slope);
+extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* mask_ss,
+                                const void* x, const float* mean_invstd, const float* gamma,
+                                const float* sums, const void* x2, const float* mean_invstd2,
+                                const float* gamma2, void* dx, void* dx2, void* gout, long M,
+                                int C, double count, int act, float slope, void* stream) {
+  if (int rc = check_c(C)) return rc;
+  SIB_CHECK(act == SIB_ACT_NONE || out != nullptr || mask_ss != nullptr,
+            "bn_bwd_apply: activation mask needs `out` or `mask_ss`");
+  const int grid = bn_grid(M, C);
+  const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(dy);
+  const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(out);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* xq = static_cast<const __nv_bfloat16*>(x2);
+  __nv_bfloat16* d1 = static_cast<__nv_bfloat16*>(dx);
+  __nv_bfloat16* d2 = static_cast<__nv_bfloat16*>(dx2);
+  __nv_bfloat16* gg = static_cast<__nv_bfloat16*>(gout);
+  const float ic = (float)(1.0 / count);
+#define SIB_APP(S, O, G)                                                                       \
+  bn_bwd_apply_kernel<S, O, G><<<grid, kRedThreads, 0, ST(stream)>>>(                          \
+      a, o, mask_ss, xp, mean_invstd, gamma, sums, xq, mean_invstd2, gamma2, d1, d2, gg, M, C, ic, \
+      act, slope)
+  const bool use_out = out != nullptr && act != SIB_ACT_NONE;
+  const bool wg = gout != nullptr;
+  if (x2) {
+    if (use_out) { if (wg) SIB_APP(true, true, true); else SIB_APP(true, true, false); }
+    else         { if (wg) SIB_APP(true, false, true); else SIB_APP(true, false, false); }
+  } else {
+    if (use_out) { if (wg) SIB_APP(false, true, true); else SIB_APP(false, true, false); }
+    else         { if (wg) SIB_APP(false, false, true); else SIB_APP(false, false, false); }
+  }
+#undef SIB_APP
   SIB_LAUNCH_CHECK();
   return 0;
 }

@@ -64,10 +64,10 @@ class ResNet(SibModule):
             logits = logits[:, :self._out_features]
         if not train:
             return logits, None
-        return logits, (xq, c0, mi0, cnt0, a0, pool_saved, saved, tuple(y.shape), fc_saved)
+        return logits, (xq, c0, mi0, cnt0, ss0, pool_saved, saved, tuple(y.shape), fc_saved)
 
     def bwd(self, dlogits, saved_all, need_dx=False):
-        xq, c0, mi0, cnt0, a0, pool_saved, saved, y_shape, fc_saved = saved_all
+        xq, c0, mi0, cnt0, ss0, pool_saved, saved, y_shape, fc_saved = saved_all
         n = dlogits.shape[0]
         padded = self.fc.out_features
         if dlogits.shape[1] != padded:
@@ -83,9 +83,10 @@ class ResNet(SibModule):
             self._after_block_backward(i)
         da0 = self.maxpool.bwd(dy, pool_saved)
         bn1 = self.bn1
-        sums = bn1.reduce_sums(ops.bn_bwd_reduce(da0, a0, c0, mi0, bn1.act, bn1.slope))
+        sums = bn1.reduce_sums(ops.bn_bwd_reduce(da0, None, c0, mi0, bn1.act, bn1.slope, mask_ss=ss0))
         bn1.param_grads(sums)
-        dc0, _, _ = ops.bn_bwd_apply(da0, a0, c0, mi0, bn1.weight.data, sums, cnt0, bn1.act, bn1.slope)
+        dc0, _, _ = ops.bn_bwd_apply(da0, None, c0, mi0, bn1.weight.data, sums, cnt0, bn1.act,
+                                     bn1.slope, mask_ss=ss0)
         self.conv1.run_wgrad(xq, dc0)
         return None
 

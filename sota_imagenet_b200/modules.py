@@ -267,14 +267,15 @@ class BatchNorm2d(SibModule):
         stats = ops.bn_stats(x) if train else None
         mi, ss, count = self.finalize(stats, n * h * w, train)
         y = ops.bn_apply(x, ss, self.act, self.slope, res=res)
-        return y, (x, y, mi, count)
+        return y, (x, y if res is not None else None, mi, count, ss)
 
     def bwd(self, dy, saved, need_dx=True):
-        x, y, mi, count = saved
+        x, y, mi, count, ss = saved
         dy = _as_act(dy)
-        sums = self.reduce_sums(ops.bn_bwd_reduce(dy, y, x, mi, self.act, self.slope))
+        sums = self.reduce_sums(ops.bn_bwd_reduce(dy, y, x, mi, self.act, self.slope, mask_ss=ss))
         self.param_grads(sums)
-        dx, _, _ = ops.bn_bwd_apply(dy, y, x, mi, self.weight.data, sums, count, self.act, self.slope)
+        dx, _, _ = ops.bn_bwd_apply(dy, y, x, mi, self.weight.data, sums, count, self.act, self.slope,
+                                    mask_ss=ss)
         return dx
 
 
@@ -398,10 +399,10 @@ class Bottleneck(SibModule):
             out = ops.bn_apply(c3, ss3, self.bn3.act, self.bn3.slope, res=x)
         if not train:
             return out, None
-        return out, (x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3)
+        return out, (x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3, ss1, ss2)
 
     def bwd(self, dout, saved, need_dx=True):
-        x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3 = saved
+        x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3, ss1, ss2 = saved
         dout = _as_act(dout)
         bn1, bn2, bn3 = self.bn1, self.bn2, self.bn3
         # ---- bn3 (+ shortcut bn) + add + act ----
@@ -424,18 +425,19 @@ class Bottleneck(SibModule):
         self.conv3.run_wgrad(a2, dc3)
         da2 = self.conv3.run_dgrad(dc3, tuple(a2.shape))
         # ---- bn2 + act ----
-        sums = bn2.reduce_sums(ops.bn_bwd_reduce(da2, a2, c2, mi2, bn2.act, bn2.slope))
+        # (activation mask recomputed from c2 and the forward scale/shift: a2 is not re-read)
+        sums = bn2.reduce_sums(ops.bn_bwd_reduce(da2, None, c2, mi2, bn2.act, bn2.slope, mask_ss=ss2))
         bn2.param_grads(sums)
-        dc2, _, _ = ops.bn_bwd_apply(da2, a2, c2, mi2, bn2.weight.data, sums, cnt2, bn2.act,
-                                     bn2.slope)
+        dc2, _, _ = ops.bn_bwd_apply(da2, None, c2, mi2, bn2.weight.data, sums, cnt2, bn2.act,
+                                     bn2.slope, mask_ss=ss2)
         # ---- conv2 ----
         self.conv2.run_wgrad(a1, dc2)
         da1 = self.conv2.run_dgrad(dc2, tuple(a1.shape))
         # ---- bn1 + act ----
-        sums = bn1.reduce_sums(ops.bn_bwd_reduce(da1, a1, c1, mi1, bn1.act, bn1.slope))
+        sums = bn1.reduce_sums(ops.bn_bwd_reduce(da1, None, c1, mi1, bn1.act, bn1.slope, mask_ss=ss1))
         bn1.param_grads(sums)
-        dc1, _, _ = ops.bn_bwd_apply(da1, a1, c1, mi1, bn1.weight.data, sums, cnt1, bn1.act,
-                                     bn1.slope)
+        dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, sums, cnt1, bn1.act,
+                                     bn1.slope, mask_ss=ss1)
         # ---- conv1 (+ shortcut) ----
         self.conv1.run_wgrad(x, dc1)
         if self.downsample is not None:

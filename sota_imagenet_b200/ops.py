@@ -164,23 +164,25 @@ def bn_apply(x, scale_shift, act=ACT_NONE, slope=0.01, res=None, scale_shift2=No
     return y
 
 
-def bn_bwd_reduce(dy, out, x, mean_invstd, act, slope=0.01, x2=None, mean_invstd2=None):
+def bn_bwd_reduce(dy, out, x, mean_invstd, act, slope=0.01, x2=None, mean_invstd2=None,
+                  mask_ss=None):
+    """`out` (stored forward output) or `mask_ss` (forward scale/shift, mask recomputed from x)."""
     n, c, h, w = x.shape
     sums = torch.empty((4 if x2 is not None else 2, c), dtype=torch.float32, device=x.device)
-    call("sib_bn_bwd_reduce", _p(dy), _p(out), _p(x), _p(mean_invstd), _p(x2), _p(mean_invstd2),
-         n * h * w, c, act, float(slope), _p(sums), _stream())
+    call("sib_bn_bwd_reduce", _p(dy), _p(out), _p(mask_ss), _p(x), _p(mean_invstd), _p(x2),
+         _p(mean_invstd2), n * h * w, c, act, float(slope), _p(sums), _stream())
     return sums
 
 
 def bn_bwd_apply(dy, out, x, mean_invstd, gamma, sums, count, act, slope=0.01, x2=None,
-                 mean_invstd2=None, gamma2=None, want_g=False, dx_out=None):
+                 mean_invstd2=None, gamma2=None, want_g=False, dx_out=None, mask_ss=None):
     n, c, h, w = x.shape
     dx = dx_out if dx_out is not None else new_act(n, c, h, w, x.device)
     dx2 = new_act(n, c, h, w, x.device) if x2 is not None else None
     g = new_act(n, c, h, w, x.device) if want_g else None
-    call("sib_bn_bwd_apply", _p(dy), _p(out), _p(x), _p(mean_invstd), _p(gamma), _p(sums), _p(x2),
-         _p(mean_invstd2), _p(gamma2), _p(dx), _p(dx2), _p(g), n * h * w, c, float(count), act,
-         float(slope), _stream())
+    call("sib_bn_bwd_apply", _p(dy), _p(out), _p(mask_ss), _p(x), _p(mean_invstd), _p(gamma),
+         _p(sums), _p(x2), _p(mean_invstd2), _p(gamma2), _p(dx), _p(dx2), _p(g), n * h * w, c,
+         float(count), act, float(slope), _stream())
     return dx, dx2, g
 
 
