@@ -35,6 +35,7 @@ extern "C" {
 
 /* conv flags */
 #define SIB_FLAG_FORCE_IM2COL 1 /* use the im2col TMA path even for plain 1x1 (testing) */
+#define SIB_FLAG_TILE_N128 2    /* cap the N tile at 128 columns (tuning / testing)       */
 
 const char* sib_last_error(void);
 int sib_abi_version(void);
@@ -49,16 +50,16 @@ int sib_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W,
                      int R, int S, int stride, int pad_h, int pad_w, int OH, int OW,
                      const float* bias, float* stats, int flags, void* stream);
 
-/* dx[N][H][W][C] (+)= dgrad(dy[N][OH][OW][K]); w_dgrad is the tap-flipped transposed filter
- * [C][R][S][K] produced by sib_pack_dgrad_weights.  stride 1, or stride>1 with a 1x1 filter
- * (accumulate must be 1: only every stride-th pixel is touched). */
-int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int C,
-                     int K, int R, int S, int stride, int pad, int accumulate, int flags,
-                     void* stream);
-/* strided RxS dgrad; workspace holds N*((OH-1)*stride+1)*((OW-1)*stride+1)*K bf16 */
-int sib_conv2d_dgrad_strided(const void* dy, const void* w_dgrad, void* dx, void* workspace, int N,
-                             int H, int W, int C, int K, int R, int S, int stride, int pad,
-                             int accumulate, int flags, void* stream);
+/* dx[N][H][W][C] = dgrad(dy[N][OH][OW][K]) [+ residual]; w_dgrad is the tap-flipped transposed
+ * filter [C][R][S][K] produced by sib_pack_dgrad_weights.  `residual` (optional, geometry of dx,
+ * may alias dx) is added in the epilogue (identity-shortcut gradient).  stride > 1 needs
+ * `workspace`: RxS -> N*((OH-1)s+1)*((OW-1)s+1)*K bf16 (zero-inserted dy); 1x1 -> N*OH*OW*C bf16
+ * (compact result, then ACCUMULATED into dx at every stride-th pixel; residual must be NULL). */
+int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx, const void* residual,
+                     void* workspace, int N, int H, int W, int C, int K, int R, int S, int stride,
+                     int pad, int flags, void* stream);
+int sib_scatter_add_strided(const void* src, void* dst, int N, int OH, int OW, int C, int H, int W,
+                            int stride, void* stream);
 /* dw[K][R][S][C] (fp32) += wgrad(x, dy).  dw must be initialised (zero_grad). */
 int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int K,
                      int R, int S, int stride, int pad_h, int pad_w, int OH, int OW, int flags,

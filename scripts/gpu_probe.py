@@ -64,6 +64,8 @@ def run_conv_fprop(big=False):
     ]
     if big:
         cases = [
+            ("1x1 tiled 64->256 56x56 B64 (persistent, 2 waves)", 64, 56, 56, 64, 256, 1, 1, 0, 0),
+            ("3x3 s1 512->512 7x7 B256 N-tiles", 256, 7, 7, 512, 512, 3, 1, 1, 0),
             ("1x1 tiled 256->64 56x56 B32", 32, 56, 56, 256, 64, 1, 1, 0, 0),
             ("3x3 s1 64->64 56x56 B32", 32, 56, 56, 64, 64, 3, 1, 1, 0),
             ("3x3 s2 256->256 28x28 B32", 32, 28, 28, 256, 256, 3, 2, 1, 0),
@@ -138,10 +140,19 @@ def run_conv_dgrad():
             describe_mismatch(dx, ref)
         if stride == 1:
             base = ops.to_nhwc_bf16(torch.randn(n, c, h, w, device=dev))
-            acc = base.clone()
-            ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=stride, pad=pad, out=acc, accumulate=True)
+            acc = ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=stride, pad=pad, residual=base)
             torch.cuda.synchronize()
-            report("dgrad+acc " + name, rel_err(acc, ref + base.float()), 1e-2)
+            report("dgrad+residual " + name, rel_err(acc, ref + base.float()), 1e-2)
+            inpl = base.clone()
+            ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=stride, pad=pad, out=inpl, residual=inpl)
+            torch.cuda.synchronize()
+            report("dgrad+residual in place " + name, rel_err(inpl, ref + base.float()), 1e-2)
+        elif r == 1:
+            base = ops.to_nhwc_bf16(torch.randn(n, c, h, w, device=dev))
+            acc = base.clone()
+            ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=stride, pad=pad, out=acc)
+            torch.cuda.synchronize()
+            report("dgrad strided scatter-add " + name, rel_err(acc, ref + base.float()), 1e-2)
 
 
 def run_conv_wgrad():
@@ -376,8 +387,7 @@ def run_timing():
         dw = torch.zeros(k, r, r, c, device=dev).permute(0, 3, 1, 2)
         t_f = timeit(lambda: ops.conv2d_fprop(x, w, stride=stride, pad=pad, stats=stats))
         dxbuf = torch.zeros_like(x)
-        t_d = timeit(lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad, out=dxbuf,
-                                              accumulate=(stride > 1 and r == 1)))
+        t_d = timeit(lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad, out=dxbuf))
         t_w = timeit(lambda: ops.conv2d_wgrad(x, dy, dw, stride=stride, pad=pad))
         t_c = timeit(lambda: F.conv2d(x, w, stride=stride, padding=pad))
         flops = 2.0 * B * y.shape[2] * y.shape[3] * k * c * r * r

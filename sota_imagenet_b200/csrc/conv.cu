@@ -18,50 +18,48 @@ namespace sib {
 constexpr int kBM = 128;        // GEMM-M tile (output pixels / wgrad out channels)
 constexpr int kBK = 64;         // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBM * kBK * 2;
-constexpr int kThreads = 192;   // warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int kThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int kIgemmThreads = 256;  // igemm: warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int kSlabBytes = 32 * 128;   // epilogue staging: 32 rows x 64 bf16, 128B-swizzled
 
 struct IgemmParams {
   int M_total;       // GEMM M (pixels of the traversal space)
   int Cout;          // GEMM N
-  int num_kblocks;   // taps * Cin/64
-  int cin_blocks;    // Cin / 64
+  int num_kblocks;   // taps * ceil(Cin/64)
+  int cin_blocks;    // ceil(Cin / 64)
   int S;             // filter width (tap = r * S + s)
   int trav_hw, trav_w;  // traversal space: pixels per image, pixels per row
   int stride, pad_h, pad_w;   // base pixel = (p*stride - pad_h, q*stride - pad_w)
-  int OH, OW, ostride;  // output tensor spatial extent and pixel step (2 = strided scatter)
-  int ldc;           // output row pitch in elements
-  int accumulate;    // out += result
   int tiled_a;       // A is a plain [M][K] matrix (1x1 stride-1)
+  int num_m_tiles, num_n_tiles;
+  int has_residual;  // out = acc + residual (same geometry as out)
   const float* bias; // optional [Cout]
   float* stats;      // optional [2][Cout]: sum, sum of squares of the stored bf16 values
 };
 
-// Column sums across the 32 lanes of a warp: lane l returns sum over lanes of v[l].
-__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32]) {
-  const uint32_t lane = lane_id();
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      float send = upper ? v[i] : v[i + off];
-      float keep = upper ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
+// Persistent, warp-specialised implicit GEMM.
+//   grid  = min(#tiles, #SMs) CTAs, each walking tiles t = blockIdx.x, +gridDim.x, ...
+//           (n-tile fastest so concurrently running CTAs share the A tile through L2)
+//   warp0 : TMA producer            smem ring of STAGES x (A 128x64 + B BNx64), 128B swizzle
+//   warp1 : tcgen05.mma issuer      2 TMEM accumulator stages of BN fp32 columns
+//   warp2 : TMEM alloc / dealloc
+//   warp4-7: epilogue               TMEM -> regs -> (+bias, +residual) -> bf16 -> swizzled smem
+//                                   slab -> TMA store; per-channel sum / sumsq for the next BN
+// The epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             __nv_bfloat16* __restrict__ out, const IgemmParams p) {
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+             const IgemmParams p) {
   constexpr int kBBytes = BN * kBK * 2;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
+  constexpr int kChunks = BN / 64;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
-  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint64_t res_bar[4];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_stats[2][BN];
 
@@ -69,27 +67,32 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * kABytes;
+  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [4 warps][2][kSlabBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * kBM;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+    }
+    for (int s = 0; s < 4; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 2) {
     tmem_alloc(&tmem_base_smem, kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * BN; i += kThreads) (&s_stats[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * BN; i += kIgemmThreads) (&s_stats[0][0])[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -98,29 +101,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) {
     if (lane == 0) {
       // ---- TMA producer ----
-      int n_img = m0 / p.trav_hw;
-      int rem = m0 - n_img * p.trav_hw;
-      int pp = rem / p.trav_w;
-      int qq = rem - pp * p.trav_w;
-      const int w_base = qq * p.stride - p.pad_w;
-      const int h_base = pp * p.stride - p.pad_h;
       int stage = 0;
       uint32_t phase = 0;
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < p.num_kblocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
-        if (p.tiled_a) {
-          tma_load_2d(smem_a + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m0);
-        } else {
-          const int r = tap / p.S;
-          const int s = tap - r * p.S;
-          tma_load_im2col_4d(smem_a + stage * kABytes, &tmA, &full_bar[stage], cb * kBK, w_base,
-                             h_base, n_img, (uint16_t)s, (uint16_t)r);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * kBM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        int n_img = 0, w_base = 0, h_base = 0;
+        if (!p.tiled_a) {
+          n_img = m0 / p.trav_hw;
+          const int rem = m0 - n_img * p.trav_hw;
+          const int pp = rem / p.trav_w;
+          const int qq = rem - pp * p.trav_w;
+          w_base = qq * p.stride - p.pad_w;
+          h_base = pp * p.stride - p.pad_h;
         }
-        tma_load_2d(smem_b + stage * kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
-        if (++cb == p.cin_blocks) { cb = 0; ++tap; }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
+          if (p.tiled_a) {
+            tma_load_2d(smem_a + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m0);
+          } else {
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            tma_load_im2col_4d(smem_a + stage * kABytes, &tmA, &full_bar[stage], cb * kBK,
+                               w_base, h_base, n_img, (uint16_t)s, (uint16_t)r);
+          }
+          tma_load_2d(smem_b + stage * kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
+          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -129,97 +139,147 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kblocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after();
-        const uint64_t a_desc =
-            umma_smem_desc(smem_u32(smem_a + stage * kABytes), 16, 1024, kSwizzle128B);
-        const uint64_t b_desc =
-            umma_smem_desc(smem_u32(smem_b + stage * kBBytes), 16, 1024, kSwizzle128B);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc =
+              umma_smem_desc(smem_u32(smem_a + stage * kABytes), 16, 1024, kSwizzle128B);
+          const uint64_t b_desc =
+              umma_smem_desc(smem_u32(smem_b + stage * kBBytes), 16, 1024, kSwizzle128B);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // +32 bytes along K inside the 128B swizzle row = +2 in 16-byte address units
-          umma_bf16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes along K inside the 128B swizzle row = +2 in 16-byte address units
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      umma_commit(&tmem_full_bar);
     }
-  } else {
-    // ---- epilogue: TMEM -> registers -> (bias, accumulate, stats) -> global ----
+  } else if (warp >= 4) {
+    // ---- epilogue ----
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
-    const int m = m0 + row;
-    const bool valid = m < p.M_total;
-    long pix = m;
-    if (p.ostride != 1 || p.OH * p.OW != p.trav_hw) {
-      int n_img = m / p.trav_hw;
-      int rem = m - n_img * p.trav_hw;
-      int pp = rem / p.trav_w;
-      int qq = rem - pp * p.trav_w;
-      pix = ((long)n_img * p.OH + (long)pp * p.ostride) * p.OW + (long)qq * p.ostride;
-    }
-    __nv_bfloat16* orow = out + pix * (long)p.ldc;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
+    uint8_t* slabs = smem_slab + quarter * 2 * kSlabBytes;
+    const int et = threadIdx.x - 128;         // 0..127 among epilogue threads
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
+    int slab_idx = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * kBM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      const int row0 = m0 + quarter * 32;
+      const bool row_valid = row0 + lane < p.M_total;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-    for (int chunk = 0; chunk < BN / 32; ++chunk) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + chunk * 32, r);
-      tmem_ld_wait();
-      float v[32];
+      for (int chunk = 0; chunk < kChunks; ++chunk) {
+        const int col0 = n0 + chunk * 64;
+        if (col0 >= p.Cout) break;               // ragged N (warp-uniform)
+        uint8_t* slab = slabs + slab_idx * kSlabBytes;
+        // the TMA store that last read this slab must have finished reading it
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        if (p.has_residual) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&res_bar[quarter], kSlabBytes);
+            tma_load_2d(slab, &tmRes, &res_bar[quarter], col0, row0);
+          }
+        }
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 64;
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_32x32b_x32(taddr + 32, r + 32);
+        tmem_ld_wait();
+        if (chunk == kChunks - 1 || col0 + 64 >= p.Cout) {
+          // accumulator fully read by this warp: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        float v[64];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const int col0 = n0 + chunk * 32;
-      if (p.bias != nullptr) {
+        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
-      }
+          for (int j = 0; j < 64; ++j)
+            if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.has_residual) {
+          mbar_wait(&res_bar[quarter], res_phase);
+          res_phase ^= 1;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int c = col0 + g * 8;
-        if (valid && c < p.Cout) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c);
-          if (p.accumulate) {
+          for (int g = 0; g < 8; ++g) {
+            const uint4 q = *reinterpret_cast<const uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4));
             float prev[8];
-            unpack8(*dst, prev);
+            unpack8(q, prev);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
           }
-          *dst = pack8(&v[g * 8]);
+          __syncwarp();
         }
-      }
-      if (p.stats != nullptr) {
-        float s1[32], s2[32];
+        // bf16 pack into the 128B-swizzled slab: row = lane, 16-byte chunk g at (g ^ (row & 7))
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          // statistics of the values as stored (bf16-rounded)
-          float t = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
-          s1[j] = t;
-          s2[j] = t * t;
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(&v[g * 8]);
+        if (p.stats != nullptr) {
+          __syncwarp();
+          // lane owns columns 2*lane, 2*lane+1 (one 32-bit word per row): conflict-free reads
+          float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+          const int g = lane >> 2, wsel = (lane & 3) << 2;
+          const int rows = p.M_total - row0;     // rows of this slab that exist (may exceed 32)
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const uint32_t wv = *reinterpret_cast<const uint32_t*>(slab + rr * 128 + ((g ^ (rr & 7)) << 4) + wsel);
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&wv);
+            float2 f = __bfloat1622float2(h);
+            if (rr >= rows) { f.x = 0.f; f.y = 0.f; }
+            s1a += f.x; s1b += f.y;
+            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+          }
+          const int c = chunk * 64 + 2 * lane;
+          atomicAdd(&s_stats[0][c], s1a);
+          atomicAdd(&s_stats[0][c + 1], s1b);
+          atomicAdd(&s_stats[1][c], s2a);
+          atomicAdd(&s_stats[1][c + 1], s2b);
         }
-        float a = warp_transpose_reduce32(s1);
-        float b = warp_transpose_reduce32(s2);
-        atomicAdd(&s_stats[0][chunk * 32 + lane], a);
-        atomicAdd(&s_stats[1][chunk * 32 + lane], b);
-      }
-    }
-    if (p.stats != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 64;
-      for (int c = t; c < BN; c += 128) {
-        if (n0 + c < p.Cout) {
-          atomicAdd(p.stats + n0 + c, s_stats[0][c]);
-          atomicAdd(p.stats + p.Cout + n0 + c, s_stats[1][c]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, slab, col0, row0);
+          tma_store_commit();
         }
+        slab_idx ^= 1;
       }
+      (void)row_valid;
+      if (p.stats != nullptr) {
+        // CTA-level column sums of this tile -> global, then clear for the next tile
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = et; c < BN; c += 128) {
+          if (n0 + c < p.Cout) {
+            atomicAdd(p.stats + n0 + c, s_stats[0][c]);
+            atomicAdd(p.stats + p.Cout + n0 + c, s_stats[1][c]);
+          }
+          s_stats[0][c] = 0.f;
+          s_stats[1][c] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -379,29 +439,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 // host launchers
 // ----------------------------------------------------------------------------
 template <int BN, int STAGES>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* out,
-                        const IgemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 1024;
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                        const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 8 * kSlabBytes + 1024;
   static bool configured = false;
   if (!configured) {
     SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((p.Cout + BN - 1) / BN, (p.M_total + kBM - 1) / kBM);
-  igemm_kernel<BN, STAGES><<<grid, kThreads, smem, stream>>>(
-      tmA, tmB, static_cast<__nv_bfloat16*>(out), p);
+  int grid = p.num_m_tiles * p.num_n_tiles;
+  if (grid > sm_count()) grid = sm_count();
+  igemm_kernel<BN, STAGES><<<grid, kIgemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
   SIB_LAUNCH_CHECK();
   return 0;
 }
 
 // Shared by fprop and dgrad.  `in` is [N][IH][IW][Cin] NHWC bf16, `w` is [Cout][R][S][Cin].
-// The traversal space (GEMM rows) is [N][TH][TW]; row (n,p,q) reads taps starting at
-// (p*stride - pad, q*stride - pad) and is stored at out[n][p*ostride][q*ostride][:].
-static int run_igemm(const void* in, const void* w, void* out, int N, int IH, int IW, int Cin,
-                     int Cout, int R, int S, int stride, int pad_h, int pad_w, int TH, int TW,
-                     int OH, int OW,
-                     int ostride, int accumulate, const float* bias, float* stats, int flags,
+// The traversal space (GEMM rows) is [N][TH][TW] and equals the output tensor's pixel space;
+// row (n,p,q) reads taps starting at (p*stride - pad_h, q*stride - pad_w).
+// out = conv [+ bias] [+ residual]; residual has the geometry of out (may alias it).
+static int run_igemm(const void* in, const void* w, void* out, const void* residual, int N,
+                     int IH, int IW, int Cin, int Cout, int R, int S, int stride, int pad_h,
+                     int pad_w, int TH, int TW, const float* bias, float* stats, int flags,
                      cudaStream_t stream) {
   // 1x1 filters may have a ragged K: TMA zero-fills both operands past Cin
   SIB_CHECK(Cin % 64 == 0 || (R == 1 && S == 1 && Cin % 8 == 0),
@@ -419,19 +479,21 @@ static int run_igemm(const void* in, const void* w, void* out, int N, int IH, in
   p.stride = stride;
   p.pad_h = pad_h;
   p.pad_w = pad_w;
-  p.OH = OH;
-  p.OW = OW;
-  p.ostride = ostride;
-  p.ldc = Cout;
-  p.accumulate = accumulate;
   p.bias = bias;
   p.stats = stats;
+  p.has_residual = residual != nullptr;
   const bool plain =
       (R == 1 && S == 1 && stride == 1 && pad_h == 0 && pad_w == 0 && TH == IH && TW == IW);
   p.tiled_a = (plain && !(flags & SIB_FLAG_FORCE_IM2COL)) ? 1 : 0;
 
-  const int BN = (Cout <= 64) ? 64 : 128;
-  CUtensorMap tmA, tmB;
+  int BN = 64;
+  if (Cout > 64) BN = 128;
+  if (Cout >= 256 && Cout % 256 == 0) BN = 256;
+  if (flags & SIB_FLAG_TILE_N128 && BN == 256) BN = 128;
+  p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
+  p.num_n_tiles = (Cout + BN - 1) / BN;
+
+  CUtensorMap tmA, tmB, tmOut, tmRes;
   int rc;
   if (p.tiled_a) {
     rc = make_tmap_2d_bf16(&tmA, in, (uint64_t)p.M_total, Cin, Cin, kBM, kBK, true);
@@ -446,9 +508,15 @@ static int run_igemm(const void* in, const void* w, void* out, int N, int IH, in
   rc = make_tmap_2d_bf16(&tmB, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, BN, kBK,
                          true);
   if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmOut, out, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmRes, residual ? residual : out, (uint64_t)p.M_total, Cout, Cout, 32,
+                         64, true);
+  if (rc) return rc;
   if (stats != nullptr) SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, stream));
-  if (BN == 64) return launch_igemm<64, 4>(tmA, tmB, out, p, stream);
-  return launch_igemm<128, 3>(tmA, tmB, out, p, stream);
+  if (BN == 64) return launch_igemm<64, 6>(tmA, tmB, tmOut, tmRes, p, stream);
+  if (BN == 128) return launch_igemm<128, 5>(tmA, tmB, tmOut, tmRes, p, stream);
+  return launch_igemm<256, 3>(tmA, tmB, tmOut, tmRes, p, stream);
 }
 
 template <int BNC, int STAGES>
@@ -476,47 +544,42 @@ extern "C" int sib_conv2d_fprop(const void* x, const void* w, void* y, int N, in
                                 void* stream) {
   SIB_CHECK(OH >= 1 && OW >= 1 && (OH - 1) * stride - pad_h < H && (OW - 1) * stride - pad_w < W,
             "fprop: output extent %dx%d inconsistent with input %dx%d", OH, OW, H, W);
-  return run_igemm(x, w, y, N, H, W, C, K, R, S, stride, pad_h, pad_w, OH, OW, OH, OW, 1, 0, bias,
+  return run_igemm(x, w, y, nullptr, N, H, W, C, K, R, S, stride, pad_h, pad_w, OH, OW, bias,
                    stats, flags, static_cast<cudaStream_t>(stream));
-}
-
-extern "C" int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx, int N, int H,
-                                int W, int C, int K, int R, int S, int stride, int pad,
-                                int accumulate, int flags, void* stream) {
-  const int OH = (H + 2 * pad - R) / stride + 1;
-  const int OW = (W + 2 * pad - S) / stride + 1;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (stride == 1) {
-    // full correlation of dY with the tap-flipped, transposed filter
-    return run_igemm(dy, w_dgrad, dx, N, OH, OW, K, C, R, S, 1, R - 1 - pad, S - 1 - pad, H, W, H,
-                     W, 1, accumulate, nullptr, nullptr, flags, st);
-  }
-  if (R == 1 && S == 1 && pad == 0) {
-    // strided 1x1: only pixels (p*stride, q*stride) receive gradient
-    SIB_CHECK(accumulate, "strided 1x1 dgrad only supports accumulate=1 (dx must be initialised)");
-    return run_igemm(dy, w_dgrad, dx, N, OH, OW, K, C, 1, 1, 1, 0, 0, OH, OW, H, W, stride, 1,
-                     nullptr, nullptr, flags, st);
-  }
-  return fail(1, "dgrad: stride %d with %dx%d filter must go through sib_conv2d_dgrad_strided",
-              stride, R, S);
 }
 
 extern "C" int sib_upsample_zero(const void* dy, void* up, int N, int OH, int OW, int C, int UH,
                                  int UW, int stride, void* stream);
+extern "C" int sib_scatter_add_strided(const void* src, void* dst, int N, int OH, int OW, int C,
+                                       int H, int W, int stride, void* stream);
 
-// Strided RxS dgrad: zero-insert dY into `workspace` ([N][UH][UW][K], UH = (OH-1)*stride+1) and
-// run the stride-1 full correlation over it (TMA zero-fills everything outside the workspace).
-extern "C" int sib_conv2d_dgrad_strided(const void* dy, const void* w_dgrad, void* dx,
-                                        void* workspace, int N, int H, int W, int C, int K, int R,
-                                        int S, int stride, int pad, int accumulate, int flags,
-                                        void* stream) {
+// dx = dgrad(dy) [+ residual].  stride 1: full correlation of dY with the tap-flipped,
+// transposed filter.  stride > 1 needs `workspace`:
+//   1x1 : compact GEMM into workspace [N][OH][OW][C], then dx[n][p*s][q*s][:] += it
+//         (dx must already hold the other gradient contribution; residual must be null)
+//   RxS : zero-insert dY into workspace [N][(OH-1)s+1][(OW-1)s+1][K], stride-1 conv over it
+extern "C" int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx,
+                                const void* residual, void* workspace, int N, int H, int W,
+                                int C, int K, int R, int S, int stride, int pad, int flags,
+                                void* stream) {
   const int OH = (H + 2 * pad - R) / stride + 1;
   const int OW = (W + 2 * pad - S) / stride + 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stride == 1)
+    return run_igemm(dy, w_dgrad, dx, residual, N, OH, OW, K, C, R, S, 1, R - 1 - pad,
+                     S - 1 - pad, H, W, nullptr, nullptr, flags, st);
+  SIB_CHECK(workspace != nullptr, "strided dgrad needs a workspace");
+  if (R == 1 && S == 1 && pad == 0) {
+    SIB_CHECK(residual == nullptr, "strided 1x1 dgrad accumulates into dx; residual must be null");
+    if (int rc = run_igemm(dy, w_dgrad, workspace, nullptr, N, OH, OW, K, C, 1, 1, 1, 0, 0, OH, OW,
+                           nullptr, nullptr, flags, st))
+      return rc;
+    return sib_scatter_add_strided(workspace, dx, N, OH, OW, C, H, W, stride, stream);
+  }
   const int UH = (OH - 1) * stride + 1, UW = (OW - 1) * stride + 1;
   if (int rc = sib_upsample_zero(dy, workspace, N, OH, OW, K, UH, UW, stride, stream)) return rc;
-  return run_igemm(workspace, w_dgrad, dx, N, UH, UW, K, C, R, S, 1, R - 1 - pad, S - 1 - pad, H,
-                   W, H, W, 1, accumulate, nullptr, nullptr, flags,
-                   static_cast<cudaStream_t>(stream));
+  return run_igemm(workspace, w_dgrad, dx, residual, N, UH, UW, K, C, R, S, 1, R - 1 - pad,
+                   S - 1 - pad, H, W, nullptr, nullptr, flags, st);
 }
 
 extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W,

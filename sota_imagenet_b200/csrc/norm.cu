@@ -529,6 +529,29 @@ upsample_zero_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __rest
   }
 }
 
+// dst[n][p*stride][q*stride][:] += src[n][p][q][:]   (strided 1x1 dgrad)
+__global__ void __launch_bounds__(256)
+scatter_add_strided_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                           int N, int OH, int OW, int C, int H, int W, int stride) {
+  const int cvec = C >> 3;
+  const long total = (long)N * OH * OW * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    long t = i / cvec;
+    const int q = (int)(t % OW); t /= OW;
+    const int pp = (int)(t % OH);
+    const int n = (int)(t / OH);
+    float a[8], b[8];
+    unpack8(ldg_stream(src + i * 8), a);
+    __nv_bfloat16* d = dst + ((((long)n * H + (long)pp * stride) * W + (long)q * stride) * cvec + v) * 8;
+    unpack8(*reinterpret_cast<const uint4*>(d), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    *reinterpret_cast<uint4*>(d) = pack8(a);
+  }
+}
+
 static inline int ew_grid(long n, int threads) {
   long b = (n + threads - 1) / threads;
   long cap = (long)sm_count() * 16;
@@ -721,6 +744,17 @@ extern "C" int sib_upsample_zero(const void* dy, void* up, int N, int OH, int OW
   const long total = (long)N * UH * UW * (C / 8);
   upsample_zero_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(up), N, OH, OW, C, UH, UW,
+      stride);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_scatter_add_strided(const void* src, void* dst, int N, int OH, int OW, int C,
+                                       int H, int W, int stride, void* stream) {
+  SIB_CHECK(C % 8 == 0, "scatter_add: C %% 8 != 0");
+  const long total = (long)N * OH * OW * (C / 8);
+  scatter_add_strided_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), N, OH, OW, C, H, W,
       stride);
   SIB_LAUNCH_CHECK();
   return 0;

@@ -143,10 +143,10 @@ class Conv2d(SibModule):
     def run(self, x, stats=None):
         return ops.conv2d_fprop(x, self._w16(self.weight), self.stride, self.padding, stats=stats)
 
-    def run_dgrad(self, dy, x_shape, out=None, accumulate=False):
+    def run_dgrad(self, dy, x_shape, out=None, residual=None):
         k = self.kernel_size[0]
         return ops.conv2d_dgrad(dy, self._wd16(self.weight), x_shape, k, k, self.stride,
-                                self.padding, out=out, accumulate=accumulate)
+                                self.padding, out=out, residual=residual)
 
     def run_wgrad(self, x, dy):
         ops.conv2d_wgrad(x, dy, self._grad(self.weight), self.stride, self.padding)
@@ -444,10 +444,10 @@ class Bottleneck(SibModule):
             self.downsample[0].run_wgrad(x, dcd)
         if not need_dx:
             return None
-        if self.downsample is not None:
-            dx = self.conv1.run_dgrad(dc1, tuple(x.shape))
-            self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx, accumulate=True)
-        else:
-            # identity shortcut: dx = dgrad(conv1) + g, accumulated in place into g
-            dx = self.conv1.run_dgrad(dc1, tuple(x.shape), out=g, accumulate=True)
-        return dx
+        if self.downsample is None:
+            # identity shortcut: dx = dgrad(conv1) + g, the add fused into the conv epilogue
+            return self.conv1.run_dgrad(dc1, tuple(x.shape), residual=g)
+        dx = self.conv1.run_dgrad(dc1, tuple(x.shape))
+        if self.stride == 1:
+            return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx, residual=dx)
+        return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx)   # strided scatter-add

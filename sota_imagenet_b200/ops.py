@@ -16,6 +16,7 @@ def call(name, *args):
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE = 0, 1, 2, 3
 FLAG_FORCE_IM2COL = 1
+FLAG_TILE_N128 = 2
 ACT_CODES = {None: ACT_NONE, "identity": ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU,
              "leaky_relu": ACT_LEAKY}
 
@@ -66,28 +67,28 @@ def conv2d_fprop(x, w, stride=1, pad=0, stats=None, bias=None, flags=0, pad_hw=N
     return y
 
 
-def conv2d_dgrad(dy, w_dgrad, x_shape, r, s, stride=1, pad=0, out=None, accumulate=False, flags=0):
-    """dx for conv(x, w); `w_dgrad` is the [C][R][S][K] flipped pack of w."""
+def conv2d_dgrad(dy, w_dgrad, x_shape, r, s, stride=1, pad=0, out=None, residual=None, flags=0):
+    """dx for conv(x, w); `w_dgrad` is the [C][R][S][K] flipped pack of w.
+    stride 1 (or strided RxS): dx = dgrad [+ residual].  strided 1x1: dx (= `out`, or zeros) +=
+    dgrad at every stride-th pixel."""
     _lib.require_device()
     _check_act(dy, "dy")
     n, c, h, wd = x_shape
     k = dy.shape[1]
-    if out is None:
-        assert not accumulate
-        if stride > 1 and r == 1:
+    oh, ow = dy.shape[2], dy.shape[3]
+    ws = None
+    if stride > 1 and r == 1 and s == 1:
+        assert residual is None
+        if out is None:
             out = torch.zeros((n, h, wd, c), dtype=torch.bfloat16, device=dy.device).permute(0, 3, 1, 2)
-            accumulate = True
-        else:
-            out = new_act(n, c, h, wd, dy.device)
-    if stride == 1 or (r == 1 and s == 1):
-        call("sib_conv2d_dgrad", _p(dy), _p(w_dgrad), _p(out), n, h, wd, c, k, r, s, stride, pad,
-             int(accumulate), flags, _stream())
-    else:
-        oh, ow = dy.shape[2], dy.shape[3]
+        ws = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=dy.device)
+    elif stride > 1:
         uh, uw = (oh - 1) * stride + 1, (ow - 1) * stride + 1
         ws = torch.empty((n, uh, uw, k), dtype=torch.bfloat16, device=dy.device)
-        call("sib_conv2d_dgrad_strided", _p(dy), _p(w_dgrad), _p(out), _p(ws), n, h, wd, c, k, r, s,
-             stride, pad, int(accumulate), flags, _stream())
+    if out is None:
+        out = new_act(n, c, h, wd, dy.device)
+    call("sib_conv2d_dgrad", _p(dy), _p(w_dgrad), _p(out), _p(residual), _p(ws), n, h, wd, c, k, r,
+         s, stride, pad, flags, _stream())
     return out
 
 
