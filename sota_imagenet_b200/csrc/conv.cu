@@ -297,18 +297,25 @@ struct WgradParams {
   int kblocks_per_split;   // 64-pixel blocks handled by one CTA
   int total_kblocks;
   int ldw;           // dW row pitch = R*S*Cin
-  int cin_tiles;     // Cin / BNC
+  int cin_blocks;    // Cin / 64
+  int total_units;   // R*S*Cin/64 : 64-column units of the [Cout][R*S*Cin] gradient matrix
 };
 
-constexpr int kWgPix = 64;  // pixels per k-block
+constexpr int kWgPix = 64;   // pixels per k-block
+constexpr int kWgUnits = 4;  // 64-column units per CTA -> 128 x 256 output tile
 
-template <int BNC, int STAGES>
-__global__ void __launch_bounds__(kThreads)
+// dW tile [128 out channels][4 units x 64 columns]; a unit is one (filter tap, 64 input
+// channels) pair, i.e. 64 consecutive columns of the [Cout][R*S*Cin] matrix.  All units of a
+// CTA share the dY operand; each unit's X operand is its own im2col TMA load.
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
              float* __restrict__ dw, const WgradParams p) {
-  constexpr int kABytesW = kWgPix * kBM * 2;   // dY tile: 64 pixels x 128 out channels
-  constexpr int kBBytesW = kWgPix * BNC * 2;   // X tile : 64 pixels x BNC in channels
-  constexpr uint32_t kTmemCols = BNC < 32 ? 32 : BNC;
+  constexpr int BNC = 64 * kWgUnits;
+  constexpr int kUnitBytes = kWgPix * 128;     // 64 pixels x 64 channels bf16
+  constexpr int kABytesW = 2 * kUnitBytes;     // dY tile: 64 pixels x 128 out channels
+  constexpr int kBBytesW = kWgUnits * kUnitBytes;
+  constexpr uint32_t kTmemCols = BNC;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
@@ -323,8 +330,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * kBM;                 // out-channel tile
-  const int tap = blockIdx.y / p.cin_tiles;        // filter tap
-  const int c0 = (blockIdx.y % p.cin_tiles) * BNC; // in-channel tile
+  const int u0 = blockIdx.y * kWgUnits;            // first 64-column unit
+  int nunits = p.total_units - u0;
+  if (nunits > kWgUnits) nunits = kWgUnits;
   const int kb_begin = blockIdx.z * p.kblocks_per_split;
   int kb_end = kb_begin + p.kblocks_per_split;
   if (kb_end > p.total_kblocks) kb_end = p.total_kblocks;
@@ -353,33 +361,36 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
     // nothing to do for this split (uniform across the CTA); fall through to teardown
   } else if (warp == 0) {
     if (lane == 0) {
-      const int r = tap / p.S;
-      const int s = tap - r * p.S;
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         const int m0 = kb * kWgPix;
-        int n_img = m0 / p.trav_hw;
-        int rem = m0 - n_img * p.trav_hw;
-        int pp = rem / p.trav_w;
-        int qq = rem - pp * p.trav_w;
+        const int n_img = m0 / p.trav_hw;
+        const int rem = m0 - n_img * p.trav_hw;
+        const int pp = rem / p.trav_w;
+        const int qq = rem - pp * p.trav_w;
+        const int wb = qq * p.stride - p.pad_w, hb = pp * p.stride - p.pad_h;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], a_boxes * (kWgPix * 64 * 2) + kBBytesW);
+        mbar_arrive_expect_tx(&full_bar[stage], (a_boxes + nunits) * kUnitBytes);
         uint8_t* a_dst = smem_a + stage * kABytesW;
         for (int h = 0; h < a_boxes; ++h)
-          tma_load_2d(a_dst + h * (kWgPix * 128), &tmDy, &full_bar[stage], k0 + h * 64, m0);
+          tma_load_2d(a_dst + h * kUnitBytes, &tmDy, &full_bar[stage], k0 + h * 64, m0);
         uint8_t* b_dst = smem_b + stage * kBBytesW;
-#pragma unroll
-        for (int h = 0; h < BNC / 64; ++h)
-          tma_load_im2col_4d(b_dst + h * (kWgPix * 128), &tmX, &full_bar[stage], c0 + h * 64,
-                             qq * p.stride - p.pad_w, pp * p.stride - p.pad_h, n_img, (uint16_t)s,
-                             (uint16_t)r);
+        for (int h = 0; h < nunits; ++h) {
+          const int u = u0 + h;
+          const int tap = u / p.cin_blocks;
+          const int c0 = (u - tap * p.cin_blocks) * 64;
+          const int r = tap / p.S;
+          const int s = tap - r * p.S;
+          tma_load_im2col_4d(b_dst + h * kUnitBytes, &tmX, &full_bar[stage], c0, wb, hb, n_img,
+                             (uint16_t)s, (uint16_t)r);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // both operands MN-major: 64-element groups along M/N are kWgPix*128 bytes apart (LBO),
+      // both operands MN-major: 64-element groups along M/N are kUnitBytes apart (LBO),
       // 8-pixel groups along K are 1024 bytes apart (SBO)
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BNC, 1, 1);
       int stage = 0;
@@ -387,10 +398,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a + stage * kABytesW),
-                                               kWgPix * 128, 1024, kSwizzle128B);
-        const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + stage * kBBytesW),
-                                               kWgPix * 128, 1024, kSwizzle128B);
+        const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a + stage * kABytesW), kUnitBytes,
+                                               1024, kSwizzle128B);
+        const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + stage * kBBytesW), kUnitBytes,
+                                               1024, kSwizzle128B);
 #pragma unroll
         for (int k = 0; k < kWgPix / 16; ++k) {
           // 16 pixels along K = two 1024-byte groups = +128 in 16-byte address units
@@ -407,22 +418,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
     const int k = k0 + row;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
-    float* drow = dw + (long)k * p.ldw + (long)tap * p.Cin + c0;
+    float* drow = dw + (long)k * p.ldw + (long)u0 * 64;
+    const int ncols = nunits * 64;
 #pragma unroll 1
     for (int chunk = 0; chunk < BNC / 32; ++chunk) {
+      if (chunk * 32 >= ncols) break;
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + chunk * 32, r);
       tmem_ld_wait();
       if (k < p.Cout) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          if (c0 + chunk * 32 + g * 4 < p.Cin) {
-            float* d = drow + chunk * 32 + g * 4;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d),
-                         "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
-                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
-                         : "memory");
-          }
+          float* d = drow + chunk * 32 + g * 4;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d),
+                       "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
+                       "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                       : "memory");
         }
       }
     }
@@ -519,17 +530,17 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   return launch_igemm<256, 3>(tmA, tmB, tmOut, tmRes, p, stream);
 }
 
-template <int BNC, int STAGES>
+template <int STAGES>
 static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, float* dw,
                         const WgradParams& p, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kWgPix * kBM * 2 + kWgPix * BNC * 2) + 1024;
+  constexpr int smem = STAGES * (2 + kWgUnits) * kWgPix * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(wgrad_kernel<BNC, STAGES>,
+    SIB_CUDA(cudaFuncSetAttribute(wgrad_kernel<STAGES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  wgrad_kernel<BNC, STAGES><<<grid, kThreads, smem, stream>>>(tmDy, tmX, dw, p);
+  wgrad_kernel<STAGES><<<grid, kThreads, smem, stream>>>(tmDy, tmX, dw, p);
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -601,12 +612,13 @@ extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N,
   p.pad_w = pad_w;
   p.total_kblocks = (p.M_total + kWgPix - 1) / kWgPix;
   p.ldw = R * S * C;
-  const int BNC = (C % 128 == 0) ? 128 : 64;
-  p.cin_tiles = C / BNC;
-  const int tiles = ((K + kBM - 1) / kBM) * R * S * p.cin_tiles;
-  // enough splits for ~4 waves, at least 4 k-blocks each
-  int splits = (4 * sm_count() + tiles - 1) / tiles;
-  int max_splits = (p.total_kblocks + 3) / 4;
+  p.cin_blocks = C / 64;
+  p.total_units = R * S * p.cin_blocks;
+  const int groups = (p.total_units + kWgUnits - 1) / kWgUnits;
+  const int tiles = ((K + kBM - 1) / kBM) * groups;
+  // split the pixel reduction so that ~2.5 waves of CTAs exist, at least 8 k-blocks each
+  int splits = (5 * sm_count() / 2 + tiles - 1) / tiles;
+  int max_splits = (p.total_kblocks + 7) / 8;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.kblocks_per_split = (p.total_kblocks + splits - 1) / splits;
@@ -620,7 +632,6 @@ extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N,
   rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, C, -pad_w, -pad_h, up_w, up_h, stride, stride, 64,
                              kWgPix, true);
   if (rc) return rc;
-  dim3 grid((K + kBM - 1) / kBM, R * S * p.cin_tiles, splits);
-  if (BNC == 128) return launch_wgrad<128, 4>(tmDy, tmX, dw, p, grid, st);
-  return launch_wgrad<64, 4>(tmDy, tmX, dw, p, grid, st);
+  dim3 grid((K + kBM - 1) / kBM, groups, splits);
+  return launch_wgrad<4>(tmDy, tmX, dw, p, grid, st);
 }
