@@ -19,7 +19,7 @@ constexpr int kBM = 128;        // GEMM-M tile (output pixels / wgrad out channe
 constexpr int kBK = 64;         // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBM * kBK * 2;
 constexpr int kThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
-constexpr int kIgemmThreads = 256;  // igemm: warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int kIgemmThreads = 384;  // igemm: warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 epilogue
 constexpr int kSlabBytes = 32 * 128;   // epilogue staging: 32 rows x 64 bf16, 128B-swizzled
 
 struct IgemmParams {
@@ -43,10 +43,12 @@ struct IgemmParams {
 //   warp0 : TMA producer            smem ring of STAGES x (A 128x64 + B BNx64), 128B swizzle
 //   warp1 : tcgen05.mma issuer      2 TMEM accumulator stages of BN fp32 columns
 //   warp2 : TMEM alloc / dealloc
-//   warp4-7: epilogue               TMEM -> regs -> (+bias, +residual) -> bf16 -> swizzled smem
-//                                   slab -> TMA store; per-channel sum / sumsq for the next BN
+//   warp4-11: epilogue (8 warps; warp e reads TMEM lane quarter e%4 and the 64-column chunks
+//           with chunk%2 == e/4; BN=64 uses the first four):
+//           TMEM -> regs -> (+bias, +residual) -> bf16 -> swizzled smem slab -> TMA store,
+//           plus per-channel sum / sum-of-squares of the stored values for the following BN.
 // The epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int SLABS>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -54,20 +56,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr int kBBytes = BN * kBK * 2;
   constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
   constexpr int kChunks = BN / 64;
+  constexpr int kHalves = kChunks >= 2 ? 2 : 1;    // epilogue warp groups splitting the columns
+  constexpr int kEpiWarps = 4 * kHalves;
+  constexpr int kChunksPerWarp = kChunks / kHalves;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
-  __shared__ uint64_t res_bar[4];
+  __shared__ uint64_t res_bar[8];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_stats[2][BN];
+  __shared__ float s_part[kEpiWarps][2][kChunksPerWarp * 64];   // per-warp column sums of a tile
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * kABytes;
-  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [4 warps][2][kSlabBytes]
+  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [8 warps][SLABS][kSlabBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,16 +88,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], kEpiWarps);   // one arrival per epilogue warp
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
     tmem_alloc(&tmem_base_smem, kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * BN; i += kIgemmThreads) (&s_stats[0][0])[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -164,11 +168,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ---- epilogue ----
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    uint8_t* slabs = smem_slab + quarter * 2 * kSlabBytes;
-    const int et = threadIdx.x - 128;         // 0..127 among epilogue threads
+    const int e = warp - 4;
+    const int quarter = e & 3;                // TMEM lane quarter (== warp % 4)
+    const int half = e >> 2;                  // which interleaved set of 64-column chunks
+    uint8_t* slabs = smem_slab + e * SLABS * kSlabBytes;
+    const int et = threadIdx.x - 128;         // 0 .. 32*kEpiWarps-1
+    // swizzled 16-byte slots of this lane's row inside a slab (row = lane)
+    uint32_t row_slot[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) row_slot[g] = lane * 128 + ((g ^ (lane & 7)) << 4);
+    // stats pass: lane reads 16 bytes (8 columns, slot lane%8) of rows it*4 + lane/8
+    const int st_row = lane >> 3, st_slot = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
@@ -177,101 +189,125 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int m0 = (tile / p.num_n_tiles) * kBM;
       const int n0 = (tile % p.num_n_tiles) * BN;
       const int row0 = m0 + quarter * 32;
-      const bool row_valid = row0 + lane < p.M_total;
+      const int rows_valid = p.M_total - row0;   // rows of this 32-row slab that exist
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int chunk = 0; chunk < kChunks; ++chunk) {
+      bool released = false;
+#pragma unroll
+      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+        const int chunk = half + ci * kHalves;
         const int col0 = n0 + chunk * 64;
-        if (col0 >= p.Cout) break;               // ragged N (warp-uniform)
-        uint8_t* slab = slabs + slab_idx * kSlabBytes;
-        // the TMA store that last read this slab must have finished reading it
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
-        if (p.has_residual) {
+        const bool live = col0 < p.Cout;           // ragged N (warp-uniform)
+        float cs1[8], cs2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cs1[j] = 0.f; cs2[j] = 0.f; }
+        if (live) {
+          uint8_t* slab = slabs + slab_idx * kSlabBytes;
+          // the TMA store that last read this slab must have finished reading it
+          if (lane == 0) tma_store_wait_read<SLABS - 1>();
+          __syncwarp();
+          if (p.has_residual && lane == 0) {
+            mbar_arrive_expect_tx(&res_bar[e], kSlabBytes);
+            tma_load_2d(slab, &tmRes, &res_bar[e], col0, row0);
+          }
+          uint32_t r[64];
+          const uint32_t taddr =
+              tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 64;
+          tmem_ld_32x32b_x32(taddr, r);
+          tmem_ld_32x32b_x32(taddr + 32, r + 32);
+          tmem_ld_wait();
+          if (ci == kChunksPerWarp - 1 || col0 + 64 * kHalves >= p.Cout) {
+            // accumulator fully read by this warp: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            released = true;
+          }
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.has_residual) {
+            mbar_wait(&res_bar[e], res_phase);
+            res_phase ^= 1;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint4 q = *reinterpret_cast<const uint4*>(slab + row_slot[g]);
+              float prev[8];
+              unpack8(q, prev);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
+            }
+          }
+          // bf16 pack into the 128B-swizzled slab
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(slab + row_slot[g]) = pack8(&v[g * 8]);
+          if (p.stats != nullptr) {
+            __syncwarp();
+            // column sums of the bf16 values as stored: 8 x LDS.128 cover the 32 x 64 slab
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + st_row;
+              uint4 q = *reinterpret_cast<const uint4*>(slab + rr * 128 + ((st_slot ^ (rr & 7)) << 4));
+              if (rr >= rows_valid) q = make_uint4(0, 0, 0, 0);
+              float f[8];
+              unpack8(q, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { cs1[j] += f[j]; cs2[j] = fmaf(f[j], f[j], cs2[j]); }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
           if (lane == 0) {
-            mbar_arrive_expect_tx(&res_bar[quarter], kSlabBytes);
-            tma_load_2d(slab, &tmRes, &res_bar[quarter], col0, row0);
+            tma_store_2d(&tmOut, slab, col0, row0);
+            tma_store_commit();
           }
+          if (SLABS > 1) slab_idx ^= 1;
         }
-        uint32_t r[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 64;
-        tmem_ld_32x32b_x32(taddr, r);
-        tmem_ld_32x32b_x32(taddr + 32, r + 32);
-        tmem_ld_wait();
-        if (chunk == kChunks - 1 || col0 + 64 >= p.Cout) {
-          // accumulator fully read by this warp: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        float v[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
-        }
-        if (p.has_residual) {
-          mbar_wait(&res_bar[quarter], res_phase);
-          res_phase ^= 1;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint4 q = *reinterpret_cast<const uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4));
-            float prev[8];
-            unpack8(q, prev);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
-          }
-          __syncwarp();
-        }
-        // bf16 pack into the 128B-swizzled slab: row = lane, 16-byte chunk g at (g ^ (row & 7))
-#pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(&v[g * 8]);
         if (p.stats != nullptr) {
-          __syncwarp();
-          // lane owns columns 2*lane, 2*lane+1 (one 32-bit word per row): conflict-free reads
-          float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-          const int g = lane >> 2, wsel = (lane & 3) << 2;
-          const int rows = p.M_total - row0;     // rows of this slab that exist (may exceed 32)
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const uint32_t wv = *reinterpret_cast<const uint32_t*>(slab + rr * 128 + ((g ^ (rr & 7)) << 4) + wsel);
-            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&wv);
-            float2 f = __bfloat1622float2(h);
-            if (rr >= rows) { f.x = 0.f; f.y = 0.f; }
-            s1a += f.x; s1b += f.y;
-            s2a = fmaf(f.x, f.x, s2a); s2b = fmaf(f.y, f.y, s2b);
+          // lanes with equal lane%8 hold partial sums of the same 8 columns (different rows)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 8);
+            cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 8);
+            cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 16);
+            cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 16);
           }
-          const int c = chunk * 64 + 2 * lane;
-          atomicAdd(&s_stats[0][c], s1a);
-          atomicAdd(&s_stats[0][c + 1], s1b);
-          atomicAdd(&s_stats[1][c], s2a);
-          atomicAdd(&s_stats[1][c + 1], s2b);
+          if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s_part[e][0][ci * 64 + lane * 8 + j] = cs1[j];
+              s_part[e][1][ci * 64 + lane * 8 + j] = cs2[j];
+            }
+          }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmOut, slab, col0, row0);
-          tma_store_commit();
-        }
-        slab_idx ^= 1;
       }
-      (void)row_valid;
+      if (!released) {     // every chunk of this warp was past Cout: still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (p.stats != nullptr) {
-        // CTA-level column sums of this tile -> global, then clear for the next tile
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int c = et; c < BN; c += 128) {
+        // combine the four row-quarters of each column and publish; s_part is reused next tile
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        for (int c = et; c < BN; c += 32 * kEpiWarps) {
           if (n0 + c < p.Cout) {
-            atomicAdd(p.stats + n0 + c, s_stats[0][c]);
-            atomicAdd(p.stats + p.Cout + n0 + c, s_stats[1][c]);
+            const int chunk = c >> 6;
+            const int h = chunk % kHalves, ci = chunk / kHalves, lc = ci * 64 + (c & 63);
+            const float a = s_part[h * 4 + 0][0][lc] + s_part[h * 4 + 1][0][lc] +
+                            s_part[h * 4 + 2][0][lc] + s_part[h * 4 + 3][0][lc];
+            const float b = s_part[h * 4 + 0][1][lc] + s_part[h * 4 + 1][1][lc] +
+                            s_part[h * 4 + 2][1][lc] + s_part[h * 4 + 3][1][lc];
+            atomicAdd(p.stats + n0 + c, a);
+            atomicAdd(p.stats + p.Cout + n0 + c, b);
           }
-          s_stats[0][c] = 0.f;
-          s_stats[1][c] = 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -308,7 +344,7 @@ constexpr int kWgUnits = 4;  // 64-column units per CTA -> 128 x 256 output tile
 // channels) pair, i.e. 64 consecutive columns of the [Cout][R*S*Cin] matrix.  All units of a
 // CTA share the dY operand; each unit's X operand is its own im2col TMA load.
 template <int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
              float* __restrict__ dw, const WgradParams p) {
   constexpr int BNC = 64 * kWgUnits;
@@ -449,19 +485,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 // ----------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, int SLABS>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                         const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 8 * kSlabBytes + 1024;
+  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 8 * SLABS * kSlabBytes + 1024;
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES>,
+    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   int grid = p.num_m_tiles * p.num_n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  igemm_kernel<BN, STAGES><<<grid, kIgemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
+  igemm_kernel<BN, STAGES, SLABS><<<grid, kIgemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -525,9 +561,9 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
                          64, true);
   if (rc) return rc;
   if (stats != nullptr) SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, stream));
-  if (BN == 64) return launch_igemm<64, 6>(tmA, tmB, tmOut, tmRes, p, stream);
-  if (BN == 128) return launch_igemm<128, 5>(tmA, tmB, tmOut, tmRes, p, stream);
-  return launch_igemm<256, 3>(tmA, tmB, tmOut, tmRes, p, stream);
+  if (BN == 64) return launch_igemm<64, 6, 2>(tmA, tmB, tmOut, tmRes, p, stream);
+  if (BN == 128) return launch_igemm<128, 5, 1>(tmA, tmB, tmOut, tmRes, p, stream);
+  return launch_igemm<256, 3, 2>(tmA, tmB, tmOut, tmRes, p, stream);
 }
 
 template <int STAGES>
@@ -616,8 +652,8 @@ extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N,
   p.total_units = R * S * p.cin_blocks;
   const int groups = (p.total_units + kWgUnits - 1) / kWgUnits;
   const int tiles = ((K + kBM - 1) / kBM) * groups;
-  // split the pixel reduction so that ~2.5 waves of CTAs exist, at least 8 k-blocks each
-  int splits = (5 * sm_count() / 2 + tiles - 1) / tiles;
+  // split the pixel reduction so that ~2 waves of (2 per SM) CTAs exist, >= 8 k-blocks each
+  int splits = (4 * sm_count() + tiles - 1) / tiles;
   int max_splits = (p.total_kblocks + 7) / 8;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -633,5 +669,5 @@ extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N,
                              kWgPix, true);
   if (rc) return rc;
   dim3 grid((K + kBM - 1) / kBM, groups, splits);
-  return launch_wgrad<4>(tmDy, tmX, dw, p, grid, st);
+  return launch_wgrad<2>(tmDy, tmX, dw, p, grid, st);   // 97 KB smem -> two CTAs per SM
 }
