@@ -122,3 +122,22 @@ def resnet26(num_classes=1000, **kwargs):
 
 def resnet101(num_classes=1000, **kwargs):
     return ResNet((3, 4, 23, 3), num_classes=num_classes, **kwargs)
+
+
+class ResNetEmbedding(torch.nn.Module):
+    """ResNet-50 trunk -> `embedding_size`-d embedding -> SphereLinearLayer(embedding, classes):
+    the model side of the angular-margin configs (reference angular_losses.py:202-214 layer in
+    front of AdditiveAngularMarginLoss / AdaCos criteria).  Returns cosine logits [N, classes]."""
+
+    def __init__(self, embedding_size=512, num_classes=1000, **kwargs):
+        super().__init__()
+        from .losses import SphereLinearLayer
+        self.encoder = ResNet((3, 4, 6, 3), num_classes=num_classes, embedding_size=embedding_size, **kwargs)
+        self.head = SphereLinearLayer(embedding_size, num_classes)
+
+    def forward(self, x):
+        return self.head(self.encoder(x))
+
+
+def resnet50_embedding(embedding_size=512, num_classes=1000, **kwargs):
+    return ResNetEmbedding(embedding_size, num_classes, **kwargs)

@@ -451,3 +451,21 @@ class Bottleneck(SibModule):
         if self.stride == 1:
             return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx, residual=dx)
         return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx)   # strided scatter-add
+
+
+class GlobalAvgPool(SibModule):
+    """FastGlobalAvgPool2d(flatten=True) of pytorch_tools: [N,C,H,W] -> [N,C,1,1] bf16."""
+
+    def fwd(self, x, train):
+        return ops.gap_fwd(x), (tuple(x.shape),)
+
+    def bwd(self, dy, saved, need_dx=True):
+        dy = dy.reshape(dy.shape[0], dy.shape[1], 1, 1)
+        return ops.gap_bwd(_as_act(dy), saved[0])
+
+
+class Concat(nn.Module):
+    """channel concatenation of tagged inputs (reference model.py:1109-1111)"""
+
+    def forward(self, *args):
+        return torch.cat(args, dim=1).contiguous(memory_format=torch.channels_last)

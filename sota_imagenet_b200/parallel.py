@@ -16,6 +16,34 @@ import torch.nn as nn
 from .modules import BatchNorm2d, SibModule
 
 
+def plan_buckets(block_starts, total, bucket_elems):
+    """Reverse-order gradient buckets.  `block_starts[i]` = arena offset of residual block i
+    (ascending); backward finishes blocks from the last to the first.  Returns {block_index:
+    (lo, hi)} for the blocks whose completion closes a bucket of >= bucket_elems elements, plus
+    the key -1 for the final bucket (stem and whatever is left) issued when backward ends."""
+    plan, hi = {}, total
+    for i in range(len(block_starts) - 1, -1, -1):
+        lo = block_starts[i]
+        if hi - lo >= bucket_elems:
+            plan[i] = (lo, hi)
+            hi = lo
+    plan[-1] = (0, hi)
+    return plan
+
+
+def allreduce_mean_(flat, lo, hi, group=None, async_op=False):
+    """In-place average of flat[lo:hi] over the ranks (SUM then scale: works on gloo and nccl)."""
+    if hi <= lo:
+        return None
+    buf = flat[lo:hi]
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        return dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+    work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=False)
+    buf.div_(world)
+    return work if async_op else None
+
+
 def convert_sync_batchnorm(module, process_group=None):
     for m in module.modules():
         if isinstance(m, BatchNorm2d):
@@ -35,7 +63,7 @@ class DataParallel(nn.Module):
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.bucket_elems = int(bucket_mb * 1024 * 1024 / 4)
         self._handles = []
-        self._pending_hi = None
+        self._plan = None
         if sync_bn:
             convert_sync_batchnorm(module, process_group)
         arena = module.ensure_arena()
@@ -56,32 +84,27 @@ class DataParallel(nn.Module):
         module._bwd_hooks.append(self._on_backward_done)
 
     def forward(self, *args, **kwargs):
-        self._pending_hi = None
         return self.module(*args, **kwargs)
 
     # ---- bucketed, overlapped gradient averaging --------------------------------------
     def _reduce(self, lo, hi):
         if self.world_size == 1 or hi <= lo:
             return
-        arena = self.module._arena
-        buf = arena.grad[lo:hi]
-        self._handles.append(dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.process_group,
-                                             async_op=True))
+        h = allreduce_mean_(self.module._arena.grad, lo, hi, self.process_group, async_op=True)
+        if h is not None:
+            self._handles.append(h)
 
     def _on_block_done(self, block_index):
-        arena = self.module._arena
-        if self._pending_hi is None:
-            self._pending_hi = arena.total
-        lo = self._block_starts[block_index]
-        if self._pending_hi - lo >= self.bucket_elems:
-            self._reduce(lo, self._pending_hi)
-            self._pending_hi = lo
+        if self._plan is None:
+            self._plan = plan_buckets(self._block_starts, self.module._arena.total, self.bucket_elems)
+        rng = self._plan.get(block_index)
+        if rng is not None:
+            self._reduce(*rng)
 
     def _on_backward_done(self, module):
-        arena = module._arena
-        hi = self._pending_hi if self._pending_hi is not None else arena.total
-        self._reduce(0, hi)
-        self._pending_hi = None
+        if self._plan is None:
+            self._plan = plan_buckets(self._block_starts, module._arena.total, self.bucket_elems)
+        self._reduce(*self._plan[-1])
         for h in self._handles:
             h.wait()
         self._handles = []

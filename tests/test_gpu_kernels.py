@@ -1,0 +1,144 @@
+"""Kernel-level parity through the C ABI against the CPU oracle (torch fp32 on bf16-rounded
+inputs; no TF32 anywhere) at sizes the CPU finishes in seconds, incl. the edge cases: ragged M
+(pixel tail), ragged N / K (1000 classes), strides, asymmetric padding, residual epilogue."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from sota_imagenet_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+CONV_CASES = [
+    # N, H, W, C, K, R, stride, pad, flags
+    (2, 16, 16, 64, 64, 1, 1, 0, 0),
+    (2, 16, 16, 128, 256, 1, 1, 0, 0),
+    (3, 7, 7, 256, 128, 1, 1, 0, ops.FLAG_FORCE_IM2COL),     # ragged M through the im2col path
+    (2, 16, 16, 64, 64, 3, 1, 1, 0),
+    (4, 14, 14, 128, 128, 3, 1, 1, 0),
+    (2, 28, 28, 128, 128, 3, 2, 1, 0),
+    (2, 28, 28, 256, 512, 1, 2, 0, 0),
+    (3, 7, 7, 512, 512, 3, 1, 1, 0),
+    (32, 1, 1, 2048, 1000, 1, 1, 0, 0),                       # FC: ragged N
+    (40, 12, 12, 64, 256, 1, 1, 0, 0),                        # > 1 tile per persistent CTA on small grids
+]
+
+
+@pytest.mark.parametrize("n,h,w,c,k,r,stride,pad,flags", CONV_CASES)
+def test_conv_fprop_dgrad_wgrad(n, h, w, c, k, r, stride, pad, flags):
+    torch.manual_seed(0)
+    x = torch.randn(n, c, h, w).bfloat16().float().requires_grad_(True)
+    wt = (torch.randn(k, c, r, r) / (c * r * r) ** 0.5).bfloat16().float().requires_grad_(True)
+    y_ref = F.conv2d(x, wt, stride=stride, padding=pad)
+    dy = torch.randn_like(y_ref).bfloat16().float()
+    dx_ref, dw_ref = torch.autograd.grad(y_ref, (x, wt), dy)
+
+    xb = ops.to_nhwc_bf16(x.detach().cuda())
+    wb = wt.detach().cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    stats = torch.empty(2, k, device="cuda")
+    y = ops.conv2d_fprop(xb, wb, stride=stride, pad=pad, stats=stats, flags=flags)
+    assert rel(y, y_ref) < 5e-3
+    yf = y.float()
+    sref = torch.stack([yf.sum(dim=(0, 2, 3)), (yf * yf).sum(dim=(0, 2, 3))])
+    assert rel(stats, sref) < 1e-4                      # statistics of the values as stored
+
+    dyb = ops.to_nhwc_bf16(dy.cuda())
+    wd = ops.pack_dgrad_weight(wb)
+    assert torch.equal(wd.float().cpu(), wt.detach().flip(2, 3).permute(1, 2, 3, 0).contiguous())
+    dx = ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=stride, pad=pad)
+    assert rel(dx, dx_ref) < 5e-3
+    if stride == 1:
+        res = ops.to_nhwc_bf16(torch.randn(n, c, h, w, device="cuda"))
+        dxr = ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=1, pad=pad, residual=res)
+        assert rel(dxr, dx_ref + res.float().cpu()) < 5e-3
+    dw = torch.zeros(k, r, r, c, device="cuda").permute(0, 3, 1, 2)
+    ops.conv2d_wgrad(xb, dyb, dw, stride=stride, pad=pad)
+    assert rel(dw, dw_ref) < 1e-4                       # fp32 accumulation end to end
+    ops.conv2d_wgrad(xb, dyb, dw, stride=stride, pad=pad)
+    assert rel(dw, 2 * dw_ref) < 1e-4                   # accumulates into dw (zero_grad contract)
+
+
+def test_stem_7x7_as_packed_4x1_conv():
+    torch.manual_seed(1)
+    x = torch.randn(4, 3, 64, 64)
+    w = (torch.randn(64, 3, 7, 7) / 12).requires_grad_(True)
+    y_ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3)
+    xq = ops.stem_pack(x.cuda(), 7, 3)
+    wq = ops.stem_pack_weight(w.detach().cuda(), 4, 1)
+    y = ops.conv2d_fprop(xq, wq.permute(0, 3, 1, 2), stride=1, pad_hw=(2, 0), out_hw=(32, 32))
+    assert rel(y, y_ref) < 5e-3
+    y2 = F.conv2d(x.bfloat16().float(), w, stride=2, padding=3)
+    dy = torch.randn_like(y2).bfloat16().float()
+    (gref,) = torch.autograd.grad(y2, w, dy)
+    dwq = torch.zeros(64, 4, 1, 64, device="cuda").permute(0, 3, 1, 2)
+    ops.conv2d_wgrad(xq, ops.to_nhwc_bf16(dy.cuda()), dwq, stride=1, pad_hw=(2, 0))
+    dw = torch.zeros(64, 3, 7, 7, device="cuda")
+    ops.stem_unpack_wgrad(dwq, dw, 4, 1, accumulate=False)
+    assert rel(dw, gref) < 1e-4
+    # bf16 4-channel NHWC input (the augmentation kernel's layout) gives the same packing
+    x4 = torch.zeros(4, 4, 64, 64)
+    x4[:, :3] = x
+    xq2 = ops.stem_pack(ops.to_nhwc_bf16(x4.cuda()), 7, 3)
+    assert torch.equal(xq, xq2)
+
+
+@pytest.mark.parametrize("n,c,h,w", [(4, 64, 16, 16), (3, 256, 7, 7), (2, 2048, 7, 7), (5, 24, 9, 9)])
+def test_batchnorm_family(n, c, h, w):
+    torch.manual_seed(2)
+    x = (torch.randn(n, c, h, w) * 2 + 0.5).bfloat16().float()
+    res = torch.randn(n, c, h, w).bfloat16().float()
+    bn = torch.nn.BatchNorm2d(c)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.normal_()
+    xr = x.clone().requires_grad_(True)
+    y_ref = F.relu(bn(xr) + res)
+    dy = torch.randn_like(y_ref).bfloat16().float()
+    y_ref.backward(dy)
+
+    xb, rb = ops.to_nhwc_bf16(x.cuda()), ops.to_nhwc_bf16(res.cuda())
+    gamma, beta = bn.weight.data.cuda(), bn.bias.data.cuda()
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    stats = ops.bn_stats(xb)
+    m = n * h * w
+    mi, ss = ops.bn_finalize(stats, gamma, beta, rm, rv, m, 1e-5, 0.1)
+    assert rel(rm, bn.running_mean) < 1e-4 and rel(rv, bn.running_var) < 1e-4
+    y = ops.bn_apply(xb, ss, ops.ACT_RELU, res=rb)
+    assert rel(y, y_ref) < 5e-3
+    dyb = ops.to_nhwc_bf16(dy.cuda())
+    sums = ops.bn_bwd_reduce(dyb, y, xb, mi, ops.ACT_RELU)
+    dx, _, g = ops.bn_bwd_apply(dyb, y, xb, mi, gamma, sums, m, ops.ACT_RELU, want_g=True)
+    # the ReLU mask of elements whose fp32 output is within bf16 rounding of 0 can differ
+    assert rel(dx, xr.grad) < 2e-2
+    assert rel(sums[1], bn.weight.grad) < 2e-2 and rel(sums[0], bn.bias.grad) < 2e-2
+    # plain BN + ReLU: mask recomputed from x is bit-identical to the mask of the stored output
+    y0 = ops.bn_apply(xb, ss, ops.ACT_RELU)
+    s_out = ops.bn_bwd_reduce(dyb, y0, xb, mi, ops.ACT_RELU)
+    s_re = ops.bn_bwd_reduce(dyb, None, xb, mi, ops.ACT_RELU, mask_ss=ss)
+    assert rel(s_re, s_out) < 1e-6
+    d_out, _, _ = ops.bn_bwd_apply(dyb, y0, xb, mi, gamma, s_out, m, ops.ACT_RELU)
+    d_re, _, _ = ops.bn_bwd_apply(dyb, None, xb, mi, gamma, s_out, m, ops.ACT_RELU, mask_ss=ss)
+    assert torch.equal(d_out, d_re)
+
+
+def test_pooling():
+    torch.manual_seed(3)
+    x = torch.randn(4, 64, 33 - 1, 32).bfloat16().float().requires_grad_(True)
+    y_ref = F.max_pool2d(x, 3, 2, 1)
+    dy = torch.randn_like(y_ref).bfloat16().float()
+    (dx_ref,) = torch.autograd.grad(y_ref, x, dy)
+    xb = ops.to_nhwc_bf16(x.detach().cuda())
+    y, idx = ops.maxpool3x3s2_fwd(xb)
+    assert torch.equal(y.float().cpu(), y_ref.detach())
+    dx = ops.maxpool3x3s2_bwd(ops.to_nhwc_bf16(dy.cuda()), idx, tuple(x.shape))
+    assert rel(dx, dx_ref) < 5e-3
+    f = torch.randn(4, 2048, 7, 7).bfloat16().float()
+    fb = ops.to_nhwc_bf16(f.cuda())
+    assert rel(ops.gap_fwd(fb), f.mean(dim=(2, 3), keepdim=True)) < 5e-3
+    g = torch.randn(4, 2048, 1, 1).bfloat16().float()
+    assert rel(ops.gap_bwd(ops.to_nhwc_bf16(g.cuda()), tuple(f.shape)), g.expand_as(f) / 49) < 5e-3

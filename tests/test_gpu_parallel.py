@@ -1,0 +1,33 @@
+"""Multi-GPU: N-rank data parallel + SyncBN + bucketed gradient averaging == one process on the
+concatenated batch (SURVEY.md 8(e) equivalence oracle).  Needs >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dp2_equals_single_process_on_global_batch(tmp_path):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29517",
+           os.path.join(ROOT, "scripts", "dp_equivalence.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DP_EQUIVALENCE_OK" in r.stdout, r.stdout[-2000:]
+
+
+def test_train_driver_runs_reference_style_config(tmp_path):
+    """train.py on the reference-schema YAML for a few debug steps (1 GPU)."""
+    cmd = [sys.executable, os.path.join(ROOT, "train.py"), os.path.join(ROOT, "configs", "r50_progressive.yaml"),
+           "loader.batch_size=16", "debug=true", "steps_per_epoch=3",
+           "run.stages=[{start: 0, end: 1, lr: [0.001, 0.02], extra_args: {image_size: 64}}, "
+           "{start: 1, end: 2, lr: [0.02, 0], lr_mode: cos, extra_args: {image_size: 96}}]"]
+    env = dict(os.environ, WORLD_SIZE="1", LOCAL_RANK="0")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Epoch 1" in r.stdout and os.path.exists(os.path.join(str(tmp_path), "model_last.chpn"))

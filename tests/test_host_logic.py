@@ -1,0 +1,146 @@
+"""CPU: host-side logic — config schema / `_target_` remap, LR phases, data stages, CModel
+constructor contract, gradient bucket planning, optimizer segment merging, and a world-size-2
+gloo run of the bucketed gradient averaging."""
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sota_imagenet_b200 import cmodel, config, parallel, runner
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_loads_reference_schema_and_remaps_targets():
+    cfg = config.load_config(os.path.join(ROOT, "configs", "r50_baseline.yaml"), ["loader.batch_size=128", "debug=true"])
+    assert cfg.loader.batch_size == 128 and cfg.debug and cfg.loader.image_size == 224
+    assert cfg.optim["momentum"] == 0.9 and cfg.optim["weight_decay"] == 3e-5
+    assert cfg.criterion["smoothing"] == 0.1 and cfg.bn_momentum == 0.1
+    assert [s.lr for s in cfg.run.stages] == [[0.001, 1.0], [1.0, 0]]
+    from sota_imagenet_b200 import losses, models, optimizers
+    assert config.resolve_target("pytorch_tools.models.resnet50") is models.resnet50
+    assert config.resolve_target("torch.optim._multi_tensor.SGD") is optimizers.SGD
+    assert config.resolve_target("sota_imagenet.angular_losses.AdaCos") is losses.AdaCos
+    assert config.resolve_target("src.model.CModel") is cmodel.CModel
+    crit = config.call(cfg.criterion)
+    assert isinstance(crit, losses.CrossEntropyLoss) and crit.smoothing == 0.1
+    arc = config.load_config(os.path.join(ROOT, "configs", "r50_arcface.yaml"))
+    c = config.call(arc.criterion)
+    assert isinstance(c, losses.AdditiveAngularMarginLoss) and c.smoothing == 0.1 and c.s == 10.0
+    with pytest.raises(KeyError):
+        config.load_config(None, ["no_such_key=1"])
+
+
+def test_reference_yaml_runs_unchanged():
+    ref = "/root/reference/configs/hydra_exp/1.r50_baseline.yaml"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not mounted")
+    cfg = config.load_config(ref)
+    assert cfg.model["_target_"] == "pytorch_tools.models.resnet50"
+    assert cfg.run.stages[1].lr_mode == "cos" and cfg.optim["weight_decay"] == 3e-5
+
+
+def test_phases_scheduler():
+    stages = [dict(ep=(0, 8), lr=(0.001, 1.0), mode="linear"), dict(ep=(8, 90), lr=(1.0, 0), mode="cos")]
+    lr = runner.PhasesScheduler.lr_at
+    assert abs(lr(stages, 0.0) - 0.001) < 1e-9
+    assert abs(lr(stages, 4.0) - 0.5005) < 1e-9
+    assert abs(lr(stages, 8.0) - 1.0) < 1e-9
+    assert abs(lr(stages, 49.0) - 0.5) < 1e-9
+    assert abs(lr(stages, 90.0)) < 1e-9
+
+
+def test_data_manager_stage_semantics():
+    from sota_imagenet_b200 import data
+    cfg = config.load_config(os.path.join(ROOT, "configs", "r50_progressive.yaml"))
+    made = []
+
+    class FakeLoader:
+        def __init__(self, c, *a, **k):
+            made.append((c.image_size, k.get("train")))
+    orig, data.SyntheticLoader = data.SyntheticLoader, FakeLoader
+    try:
+        dm = data.DataManager(cfg)
+        assert len(dm) == 3 and dm.tot_epochs == 9
+        dm.set_stage(0)
+        assert (dm.start_epoch, dm.end_epoch) == (0, 3) and made[-2:] == [(128, True), (128, False)]
+        dm.set_stage(1)
+        assert made[-2:] == [(192, True), (192, False)]      # val size follows train size
+        cfg.run.stages[2].extra_args = None
+        n = len(made)
+        dm.set_stage(2)
+        assert len(made) == n and dm.end_epoch == 9           # LR-only stage keeps the loaders
+        cfg.run.stages[1].start = 4
+        with pytest.raises(AssertionError):
+            data.DataManager(cfg)
+    finally:
+        data.SyntheticLoader = orig
+
+
+def test_cmodel_constructor_contract():
+    """Mirror of the reference's inline self-test (model.py:1270-1376) on plain torch modules."""
+    assert cmodel._update_dict({"foo": {"a": 10, "b": 20}}, {"foo": {"a": 12, "c": 30}}) == {"foo": {"a": 12, "b": 20, "c": 30}}
+    layers = [
+        dict(module="nn.Conv2d", args=[3, 8, 3], kwargs=dict(padding=1), tag="c1"),
+        dict(module="nn.Conv2d", args=[8, 8, 3], kwargs=dict(padding="1"), repeat=2),
+        dict(module="Concat", inputs=["_prev_", "c1"]),
+        dict(module="nn.Conv2d", args=[16, 4, 1]),
+    ]
+    m = cmodel.CModel(layers)
+    assert m(torch.zeros(1, 3, 8, 8)).shape == (1, 4, 8, 8)
+    m2 = cmodel.CModel([dict(module="nn.Conv2d", args=[3, 8, 3])], extra_kwargs={"nn.Conv2d": {"bias": False, "padding": 1}})
+    assert m2[0].bias is None and m2[0].padding == (1, 1)
+    r50 = cmodel.CModel([
+        dict(module="StemConv", args=[64, 7, 3]),
+        dict(module="BatchNorm2d", args=[64], kwargs=dict(activation="'relu'")),
+        dict(module="MaxPool3x3s2"),
+        dict(module="Bottleneck", args=[64, 64], kwargs=dict(downsample=True)),
+        dict(module="Bottleneck", args=[256, 64], repeat=2),
+        dict(module="GlobalAvgPool"),
+        dict(module="Linear", args=[256, 1000]),
+    ])
+    assert sum(p.numel() for p in r50.parameters()) > 2e5
+
+
+def test_bucket_plan():
+    starts = [100, 300, 600, 1000]
+    plan = parallel.plan_buckets(starts, 1500, 450)
+    assert plan == {3: (1000, 1500), 1: (300, 1000), -1: (0, 300)}
+    covered = sorted(plan.values())
+    assert covered[0][0] == 0 and covered[-1][1] == 1500
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))      # disjoint, complete
+
+
+def test_sgd_segment_merging():
+    from sota_imagenet_b200 import optimizers
+
+    class FakeArena:
+        total = 512
+    p = [torch.nn.Parameter(torch.zeros(4)) for _ in range(4)]
+    a = FakeArena()
+    a.entries = [("a", p[0], 0, 4, "plain"), ("b", p[1], 128, 4, "plain"), ("c", p[2], 256, 4, "plain"), ("d", p[3], 384, 4, "plain")]
+    opt = optimizers.SGD([{"params": [p[0], p[1]]}, {"params": [p[2]], "weight_decay": 0.0}], lr=0.1, momentum=0.9, weight_decay=1e-4)
+    recs = opt._segments(a)
+    assert recs == [(256, 0.1, 1e-4, 0.9, 0.0, False), (384, 0.1, 0.0, 0.9, 0.0, False), (512, 0.0, 0.0, 0.0, 0.0, False)]
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    flat = torch.arange(1500, dtype=torch.float32) * (rank + 1)
+    plan = parallel.plan_buckets([100, 300, 600, 1000], 1500, 450)
+    for key in (3, 1, -1):                       # reverse order, as backward would issue them
+        parallel.allreduce_mean_(flat, *plan[key])
+    torch.save(flat, os.path.join(out, "r%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_bucketed_mean_allreduce_gloo_world2():
+    with tempfile.TemporaryDirectory() as out:
+        mp.spawn(_gloo_worker, args=(2, 29431, out), nprocs=2, join=True)
+        r0, r1 = torch.load(os.path.join(out, "r0.pt")), torch.load(os.path.join(out, "r1.pt"))
+    want = torch.arange(1500, dtype=torch.float32) * 1.5
+    assert torch.equal(r0, want) and torch.equal(r1, want)
