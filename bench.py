@@ -158,7 +158,8 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     torch.manual_seed(0)
     net = models.resnet50().to(dev).train()
@@ -279,12 +280,13 @@ def run_ours(args):
     # ---- live per-kernel timing of the conv family (roofline of the dominant kernel) --------
     roofline = None
     cpu_baseline = None
+    # (every rank runs the profiled step: with N > 1 it contains collectives)
+    _lib.PROFILE = []
+    step(x_static, y_static)
+    torch.cuda.synchronize()
+    prof, _lib.PROFILE = _lib.PROFILE, None
     if rank == 0:
         pk = peaks()
-        _lib.PROFILE = []
-        step(x_static, y_static)
-        torch.cuda.synchronize()
-        prof, _lib.PROFILE = _lib.PROFILE, None
         groups = {}
         for name, a, s0, s1 in prof:
             d = groups.setdefault(name, [0.0, 0.0, 0])

@@ -8,7 +8,8 @@ from sota_imagenet_b200 import losses, models, parallel
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-dist.init_process_group("nccl")
+import datetime
+dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=120))
 B, S = 8, 64
 x, y = torch_ref.synthetic_batch(B * world, S, seed=5)
 sd = torch_ref.resnet50(seed=0).state_dict()

@@ -159,7 +159,8 @@ def test_fused_sgd_step_matches_oracle():
         loss = crit(net(x.cuda()), y.cuda())
         loss.backward()
         opt.step()
-        assert abs(loss.item() - l_ref) / abs(l_ref) <= 3e-2, (step, loss.item(), l_ref)
+        # step 0 is a pure forward comparison; later steps diverge chaotically (see docstrings)
+        assert abs(loss.item() - l_ref) / abs(l_ref) <= (1e-2 if step == 0 else 0.1), (step, loss.item(), l_ref)
     # the update itself: (new - old) of the head parameters, whose gradients are not yet
     # chaotically decorrelated (early-layer gradients are: see test_one_step docstring)
     ref_params = dict(ref.named_parameters())
