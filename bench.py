@@ -333,6 +333,13 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # tear down: drop the captured graph (it holds NCCL kernels) before the communicator
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        guard = threading.Timer(20.0, lambda: os._exit(0))   # never hang at exit
+        guard.daemon = True
+        guard.start()
         dist.destroy_process_group()
 
 
