@@ -171,7 +171,10 @@ def run_ours(args):
 
     # ---- device-resident inputs (kernel-path number) -------------------------------------
     g = torch.Generator(device=dev).manual_seed(rank)
-    x_static = torch.randn(BATCH, 3, SIZE, SIZE, device=dev, generator=g)
+    # the loader's native layout: bf16 channels_last [N,4,H,W], 4th channel zero (GpuAugment)
+    x_static = torch.zeros(BATCH, SIZE, SIZE, 4, device=dev, dtype=torch.bfloat16)
+    x_static[..., :3] = torch.randn(BATCH, SIZE, SIZE, 3, device=dev, generator=g)
+    x_static = x_static.permute(0, 3, 1, 2)
     y_static = torch.randint(0, 1000, (BATCH,), device=dev, generator=g)
     loss_static = torch.zeros((), device=dev)
 

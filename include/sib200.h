@@ -36,6 +36,7 @@ extern "C" {
 /* conv flags */
 #define SIB_FLAG_FORCE_IM2COL 1 /* use the im2col TMA path even for plain 1x1 (testing) */
 #define SIB_FLAG_TILE_N128 2    /* cap the N tile at 128 columns (tuning / testing)       */
+#define SIB_FLAG_NO_WS 4        /* disable the weight-stationary 1x1 schedule (testing)   */
 
 const char* sib_last_error(void);
 int sib_abi_version(void);
@@ -88,8 +89,9 @@ int sib_bn_bwd_reduce(const void* dy, const void* out, const float* mask_ss, con
 int sib_bn_bwd_apply(const void* dy, const void* out, const float* mask_ss, const void* x,
                      const float* mean_invstd, const float* gamma, const float* sums,
                      const void* x2, const float* mean_invstd2, const float* gamma2, void* dx,
-                     void* dx2, void* gout, long M, int C, double count, int act, float slope,
-                     void* stream);
+                     void* dx2, void* gout, float* dgamma, float* dbeta, float* dgamma2,
+                     float* dbeta2, long M, int C, double count, int act, float slope, void* stream);
+/* (dgamma/dbeta[/2], optional: the affine-parameter gradients are ACCUMULATED into them) */
 int sib_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int accumulate,
                       void* stream);
 

@@ -64,7 +64,12 @@ def run_conv_fprop(big=False):
     ]
     if big:
         cases = [
-            ("1x1 tiled 64->256 56x56 B64 (persistent, 2 waves)", 64, 56, 56, 64, 256, 1, 1, 0, 0),
+            ("1x1 tiled 64->256 56x56 B64 (weight-stationary)", 64, 56, 56, 64, 256, 1, 1, 0, 0),
+            ("1x1 tiled 64->256 56x56 B64 (streaming)", 64, 56, 56, 64, 256, 1, 1, 0, ops.FLAG_NO_WS),
+            ("1x1 256->1024 14x14 B256 (ws, K=256)", 256, 14, 14, 256, 1024, 1, 1, 0, 0),
+            ("1x1 512->128 28x28 B64 (ws, K=512)", 64, 28, 28, 512, 128, 1, 1, 0, 0),
+            ("1x1 s2 256->512 56x56 B32 (ws im2col)", 32, 56, 56, 256, 512, 1, 2, 0, 0),
+            ("1x1 256->64 56x56 B64 (ws 64-wide)", 64, 56, 56, 256, 64, 1, 1, 0, 0),
             ("3x3 s1 512->512 7x7 B256 N-tiles", 256, 7, 7, 512, 512, 3, 1, 1, 0),
             ("1x1 tiled 256->64 56x56 B32", 32, 56, 56, 256, 64, 1, 1, 0, 0),
             ("3x3 s1 64->64 56x56 B32", 32, 56, 56, 64, 64, 3, 1, 1, 0),

@@ -281,10 +281,25 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const float* __restrict__ sums, const __nv_bfloat16* __restrict__ x2,
                     const float* __restrict__ mi2, const float* __restrict__ gamma2,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx2,
-                    __nv_bfloat16* __restrict__ gout, long M, int C, float inv_count, int act,
+                    __nv_bfloat16* __restrict__ gout, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, float* __restrict__ dgamma2,
+                    float* __restrict__ dbeta2, long M, int C, float inv_count, int act,
                     float slope) {
   const ColOwner co(C);
   if (!co.active) return;
+  if (blockIdx.x == 0 && co.ty == 0) {
+    // parameter gradients ride along: dbeta += sum g, dgamma += sum g*xhat (one writer per channel)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = co.tx * 8 + j;
+      if (dbeta) dbeta[c] += sums[c];
+      if (dgamma) dgamma[c] += sums[C + c];
+      if (SECOND) {
+        if (dbeta2) dbeta2[c] += sums[2 * C + c];
+        if (dgamma2) dgamma2[c] += sums[3 * C + c];
+      }
+    }
+  }
   float cA[8], cB[8], cC[8], dA[8], dB[8], dC[8], sc[8], sh[8];
   {
     float mean[8], invstd[8], gm[8], sg[8], sgx[8];
@@ -658,7 +673,8 @@ extern "C" int sib_bn_bwd_reduce(const void* dy, const void* out, const float* m
 extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* mask_ss,
                                 const void* x, const float* mean_invstd, const float* gamma,
                                 const float* sums, const void* x2, const float* mean_invstd2,
-                                const float* gamma2, void* dx, void* dx2, void* gout, long M,
+                                const float* gamma2, void* dx, void* dx2, void* gout,
+                                float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, long M,
                                 int C, double count, int act, float slope, void* stream) {
   if (int rc = check_c(C)) return rc;
   SIB_CHECK(act == SIB_ACT_NONE || out != nullptr || mask_ss != nullptr,
@@ -674,8 +690,8 @@ extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* ma
   const float ic = (float)(1.0 / count);
 #define SIB_APP(S, O, G)                                                                       \
   bn_bwd_apply_kernel<S, O, G><<<grid, kRedThreads, 0, ST(stream)>>>(                          \
-      a, o, mask_ss, xp, mean_invstd, gamma, sums, xq, mean_invstd2, gamma2, d1, d2, gg, M, C, ic, \
-      act, slope)
+      a, o, mask_ss, xp, mean_invstd, gamma, sums, xq, mean_invstd2, gamma2, d1, d2, gg, dgamma,   \
+      dbeta, dgamma2, dbeta2, M, C, ic, act, slope)
   const bool use_out = out != nullptr && act != SIB_ACT_NONE;
   const bool wg = gout != nullptr;
   if (x2) {

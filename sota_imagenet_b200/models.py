@@ -84,9 +84,8 @@ class ResNet(SibModule):
         da0 = self.maxpool.bwd(dy, pool_saved)
         bn1 = self.bn1
         sums = bn1.reduce_sums(ops.bn_bwd_reduce(da0, None, c0, mi0, bn1.act, bn1.slope, mask_ss=ss0))
-        bn1.param_grads(sums)
         dc0, _, _ = ops.bn_bwd_apply(da0, None, c0, mi0, bn1.weight.data, sums, cnt0, bn1.act,
-                                     bn1.slope, mask_ss=ss0)
+                                     bn1.slope, mask_ss=ss0, param_grads=bn1.grad_ptrs())
         self.conv1.run_wgrad(xq, dc0)
         return None
 

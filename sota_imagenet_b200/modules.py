@@ -257,9 +257,9 @@ class BatchNorm2d(SibModule):
             torch.distributed.all_reduce(sums, group=self.process_group)
         return sums
 
-    def param_grads(self, sums, second=False):
-        s = sums[2:4] if second else sums[0:2]
-        ops.bn_param_grad(s, self._grad(self.weight), self._grad(self.bias), accumulate=True)
+    def grad_ptrs(self):
+        """(dgamma, dbeta) arena views: bn_bwd_apply accumulates the parameter gradients itself."""
+        return self._grad(self.weight), self._grad(self.bias)
 
     # standalone use: stats pass + apply
     def fwd(self, x, train, res=None):
@@ -273,9 +273,8 @@ class BatchNorm2d(SibModule):
         x, y, mi, count, ss = saved
         dy = _as_act(dy)
         sums = self.reduce_sums(ops.bn_bwd_reduce(dy, y, x, mi, self.act, self.slope, mask_ss=ss))
-        self.param_grads(sums)
         dx, _, _ = ops.bn_bwd_apply(dy, y, x, mi, self.weight.data, sums, count, self.act, self.slope,
-                                    mask_ss=ss)
+                                    mask_ss=ss, param_grads=self.grad_ptrs())
         return dx
 
 
@@ -410,34 +409,30 @@ class Bottleneck(SibModule):
             bnd = self.downsample[1]
             sums = bn3.reduce_sums(ops.bn_bwd_reduce(dout, out, c3, mi3, bn3.act, bn3.slope, x2=cd,
                                                      mean_invstd2=mid))
-            bn3.param_grads(sums)
-            bnd.param_grads(sums, second=True)
             dc3, dcd, _ = ops.bn_bwd_apply(dout, out, c3, mi3, bn3.weight.data, sums, cnt3, bn3.act,
                                            bn3.slope, x2=cd, mean_invstd2=mid,
-                                           gamma2=bnd.weight.data)
+                                           gamma2=bnd.weight.data, param_grads=bn3.grad_ptrs(),
+                                           param_grads2=bnd.grad_ptrs())
             g = None
         else:
             sums = bn3.reduce_sums(ops.bn_bwd_reduce(dout, out, c3, mi3, bn3.act, bn3.slope))
-            bn3.param_grads(sums)
             dc3, dcd, g = ops.bn_bwd_apply(dout, out, c3, mi3, bn3.weight.data, sums, cnt3, bn3.act,
-                                           bn3.slope, want_g=need_dx)
+                                           bn3.slope, want_g=need_dx, param_grads=bn3.grad_ptrs())
         # ---- conv3 ----
         self.conv3.run_wgrad(a2, dc3)
         da2 = self.conv3.run_dgrad(dc3, tuple(a2.shape))
         # ---- bn2 + act ----
         # (activation mask recomputed from c2 and the forward scale/shift: a2 is not re-read)
         sums = bn2.reduce_sums(ops.bn_bwd_reduce(da2, None, c2, mi2, bn2.act, bn2.slope, mask_ss=ss2))
-        bn2.param_grads(sums)
         dc2, _, _ = ops.bn_bwd_apply(da2, None, c2, mi2, bn2.weight.data, sums, cnt2, bn2.act,
-                                     bn2.slope, mask_ss=ss2)
+                                     bn2.slope, mask_ss=ss2, param_grads=bn2.grad_ptrs())
         # ---- conv2 ----
         self.conv2.run_wgrad(a1, dc2)
         da1 = self.conv2.run_dgrad(dc2, tuple(a1.shape))
         # ---- bn1 + act ----
         sums = bn1.reduce_sums(ops.bn_bwd_reduce(da1, None, c1, mi1, bn1.act, bn1.slope, mask_ss=ss1))
-        bn1.param_grads(sums)
         dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, sums, cnt1, bn1.act,
-                                     bn1.slope, mask_ss=ss1)
+                                     bn1.slope, mask_ss=ss1, param_grads=bn1.grad_ptrs())
         # ---- conv1 (+ shortcut) ----
         self.conv1.run_wgrad(x, dc1)
         if self.downsample is not None:

@@ -17,6 +17,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE = 0, 1, 2, 3
 FLAG_FORCE_IM2COL = 1
 FLAG_TILE_N128 = 2
+FLAG_NO_WS = 4
 ACT_CODES = {None: ACT_NONE, "identity": ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU,
              "leaky_relu": ACT_LEAKY}
 
@@ -176,14 +177,16 @@ def bn_bwd_reduce(dy, out, x, mean_invstd, act, slope=0.01, x2=None, mean_invstd
 
 
 def bn_bwd_apply(dy, out, x, mean_invstd, gamma, sums, count, act, slope=0.01, x2=None,
-                 mean_invstd2=None, gamma2=None, want_g=False, dx_out=None, mask_ss=None):
+                 mean_invstd2=None, gamma2=None, want_g=False, dx_out=None, mask_ss=None,
+                 param_grads=(None, None), param_grads2=(None, None)):
     n, c, h, w = x.shape
     dx = dx_out if dx_out is not None else new_act(n, c, h, w, x.device)
     dx2 = new_act(n, c, h, w, x.device) if x2 is not None else None
     g = new_act(n, c, h, w, x.device) if want_g else None
     call("sib_bn_bwd_apply", _p(dy), _p(out), _p(mask_ss), _p(x), _p(mean_invstd), _p(gamma),
-         _p(sums), _p(x2), _p(mean_invstd2), _p(gamma2), _p(dx), _p(dx2), _p(g), n * h * w, c,
-         float(count), act, float(slope), _stream())
+         _p(sums), _p(x2), _p(mean_invstd2), _p(gamma2), _p(dx), _p(dx2), _p(g),
+         _p(param_grads[0]), _p(param_grads[1]), _p(param_grads2[0]), _p(param_grads2[1]),
+         n * h * w, c, float(count), act, float(slope), _stream())
     return dx, dx2, g
 
 
