@@ -64,8 +64,8 @@ def run_conv_fprop(big=False):
     ]
     if big:
         cases = [
-            ("1x1 tiled 64->256 56x56 B64 (weight-stationary)", 64, 56, 56, 64, 256, 1, 1, 0, 0),
-            ("1x1 tiled 64->256 56x56 B64 (streaming)", 64, 56, 56, 64, 256, 1, 1, 0, ops.FLAG_NO_WS),
+            ("1x1 tiled 64->256 56x56 B64 (persistent)", 64, 56, 56, 64, 256, 1, 1, 0, 0),
+            ("1x1 tiled 64->256 56x56 B64 (streaming)", 64, 56, 56, 64, 256, 1, 1, 0, 0),
             ("1x1 256->1024 14x14 B256 (ws, K=256)", 256, 14, 14, 256, 1024, 1, 1, 0, 0),
             ("1x1 512->128 28x28 B64 (ws, K=512)", 64, 28, 28, 512, 128, 1, 1, 0, 0),
             ("1x1 s2 256->512 56x56 B32 (ws im2col)", 32, 56, 56, 256, 512, 1, 2, 0, 0),

@@ -21,7 +21,6 @@ constexpr int kABytes = kBM * kBK * 2;
 constexpr int kThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
 constexpr int kIgemmThreads = 384;  // igemm: warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 epilogue
 constexpr int kSlabBytes = 32 * 128;   // epilogue staging: 32 rows x 64 bf16, 128B-swizzled
-constexpr int kMaxStages = 12;
 
 struct IgemmParams {
   int M_total;       // GEMM M (pixels of the traversal space)
@@ -34,8 +33,6 @@ struct IgemmParams {
   int tiled_a;       // A is a plain [M][K] matrix (1x1 stride-1)
   int num_m_tiles, num_n_tiles;
   int has_residual;  // out = acc + residual (same geometry as out)
-  int ws;            // weight-stationary: the CTA's B n-tile stays resident in smem (1x1 filters)
-  int stages;        // ring slots in use (<= kMaxStages)
   const float* bias; // optional [Cout]
   float* stats;      // optional [2][Cout]: sum, sum of squares of the stored bf16 values
 };
@@ -51,10 +48,7 @@ struct IgemmParams {
 //           TMEM -> regs -> (+bias, +residual) -> bf16 -> swizzled smem slab -> TMA store,
 //           plus per-channel sum / sum-of-squares of the stored values for the following BN.
 // The epilogue of tile i overlaps the main loop of tile i+1.
-// Weight-stationary variant (p.ws): for 1x1 filters whose [BN x K] weight tile fits in smem the
-// tile is loaded once per CTA and only activations stream through the (deeper) ring; each CTA
-// then owns one n-tile and walks m-tiles.
-template <int BN, int SLABS>
+template <int BN, int STAGES, int SLABS>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -66,35 +60,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr int kEpiWarps = 4 * kHalves;
   constexpr int kChunksPerWarp = kChunks / kHalves;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kMaxStages];
-  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_bar[8];
-  __shared__ uint64_t bres_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_part[kEpiWarps][2][kChunksPerWarp * 64];   // per-warp column sums of a tile
 
-  const int STAGES = p.stages;
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* smem_a = smem;                                     // [STAGES][kABytes]
-  // streaming mode: B ring [STAGES][kBBytes]; weight-stationary: resident [num_kblocks][kBBytes]
+  uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * kABytes;
-  uint8_t* smem_slab = smem_b + (p.ws ? p.num_kblocks : STAGES) * kBBytes;   // [8 warps][SLABS][..]
+  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [8 warps][SLABS][kSlabBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // tile walk: streaming -> tile = blockIdx.x + i*gridDim.x (n fastest);
-  //            weight-stationary -> fixed n-tile, m-tile = blockIdx.x / n_tiles + i*(gridDim.x / n_tiles)
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int t_first = p.ws ? (int)blockIdx.x / p.num_n_tiles : (int)blockIdx.x;
-  const int t_step = p.ws ? (int)gridDim.x / p.num_n_tiles : (int)gridDim.x;
-  const int t_end = p.ws ? p.num_m_tiles : num_tiles;
-  const int ws_n0 = ((int)blockIdx.x % p.num_n_tiles) * BN;
-#define SIB_TILE_COORDS(t, m0, n0)                                         \
-  const int m0 = (p.ws ? (t) : (t) / p.num_n_tiles) * kBM;                 \
-  const int n0 = p.ws ? ws_n0 : ((t) % p.num_n_tiles) * BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -109,7 +91,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&tmem_empty_bar[s], kEpiWarps);   // one arrival per epilogue warp
     }
     for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
-    mbar_init(&bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -126,13 +107,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // ---- TMA producer ----
       int stage = 0;
       uint32_t phase = 0;
-      if (p.ws) {
-        mbar_arrive_expect_tx(&bres_bar, p.num_kblocks * kBBytes);
-        for (int kb = 0; kb < p.num_kblocks; ++kb)
-          tma_load_2d(smem_b + kb * kBBytes, &tmB, &bres_bar, kb * kBK, ws_n0);
-      }
-      for (int tile = t_first; tile < t_end; tile += t_step) {
-        SIB_TILE_COORDS(tile, m0, n0)
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * kBM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
         int n_img = 0, w_base = 0, h_base = 0;
         if (!p.tiled_a) {
           n_img = m0 / p.trav_hw;
@@ -145,7 +122,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int tap = 0, cb = 0;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], p.ws ? kABytes : kABytes + kBBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + kBBytes);
           if (p.tiled_a) {
             tma_load_2d(smem_a + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m0);
           } else {
@@ -154,7 +131,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_im2col_4d(smem_a + stage * kABytes, &tmA, &full_bar[stage], cb * kBK,
                                w_base, h_base, n_img, (uint16_t)s, (uint16_t)r);
           }
-          if (!p.ws) tma_load_2d(smem_b + stage * kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
+          tma_load_2d(smem_b + stage * kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
           if (++cb == p.cin_blocks) { cb = 0; ++tap; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -168,8 +145,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (p.ws) mbar_wait(&bres_bar, 0);
-      for (int tile = t_first; tile < t_end; tile += t_step) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -178,8 +154,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint64_t a_desc =
               umma_smem_desc(smem_u32(smem_a + stage * kABytes), 16, 1024, kSwizzle128B);
-          const uint64_t b_desc = umma_smem_desc(
-              smem_u32(smem_b + (p.ws ? kb : stage) * kBBytes), 16, 1024, kSwizzle128B);
+          const uint64_t b_desc =
+              umma_smem_desc(smem_u32(smem_b + stage * kBBytes), 16, 1024, kSwizzle128B);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // +32 bytes along K inside the 128B swizzle row = +2 in 16-byte address units
@@ -209,8 +185,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
     int slab_idx = 0;
-    for (int tile = t_first; tile < t_end; tile += t_step) {
-      SIB_TILE_COORDS(tile, m0, n0)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * kBM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
       const int row0 = m0 + quarter * 32;
       const int rows_valid = p.M_total - row0;   // rows of this 32-row slab that exist
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -342,7 +319,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-#undef SIB_TILE_COORDS
 }
 
 // ----------------------------------------------------------------------------
@@ -509,34 +485,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 // ----------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------
-constexpr int kSmemBudget = 227 * 1024 - 1024 - 9 * 1024;   // dynamic smem minus alignment pad and static part
-
-template <int BN, int SLABS>
+template <int BN, int STAGES, int SLABS>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                        const CUtensorMap& tmRes, IgemmParams p, cudaStream_t stream) {
-  constexpr int kBBytes = BN * kBK * 2;
-  constexpr int slab_bytes = 8 * SLABS * kSlabBytes;
-  int smem;
-  if (p.ws) {
-    const int bres = p.num_kblocks * kBBytes;
-    p.stages = (kSmemBudget - slab_bytes - bres) / kABytes;
-    if (p.stages > kMaxStages) p.stages = kMaxStages;
-    smem = p.stages * kABytes + bres + slab_bytes + 1024;
-  } else {
-    p.stages = (kSmemBudget - slab_bytes) / (kABytes + kBBytes);
-    if (p.stages > 8) p.stages = 8;
-    smem = p.stages * (kABytes + kBBytes) + slab_bytes + 1024;
-  }
-  static int configured = 0;
-  if (smem > configured) {
-    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, SLABS>,
+                        const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 8 * SLABS * kSlabBytes + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
+    configured = true;
   }
   int grid = p.num_m_tiles * p.num_n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  if (p.ws) grid = (sm_count() / p.num_n_tiles) * p.num_n_tiles;
-  igemm_kernel<BN, SLABS><<<grid, kIgemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
+  igemm_kernel<BN, STAGES, SLABS><<<grid, kIgemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -577,19 +538,6 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   if (Cout >= 256 && Cout % 256 == 0) BN = 256;
   if (flags & SIB_FLAG_TILE_N128 && BN == 256) BN = 128;
   p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
-  // weight-stationary for 1x1 filters: the [BN x K] weight tile (<= 128 KB) stays in smem
-  if (R == 1 && S == 1 && !(flags & SIB_FLAG_NO_WS)) {
-    int bn_ws = BN;
-    while (bn_ws > 64 && p.num_kblocks * bn_ws * kBK * 2 > 128 * 1024) bn_ws >>= 1;
-    const int n_tiles_ws = (Cout + bn_ws - 1) / bn_ws;
-    const bool fits = p.num_kblocks * bn_ws * kBK * 2 <= 128 * 1024 && bn_ws >= 128;
-    const bool small64 = BN == 64;   // 64-wide outputs: tile is tiny, always worth keeping resident
-    if ((fits || (small64 && p.num_kblocks * 64 * kBK * 2 <= 128 * 1024)) &&
-        n_tiles_ws <= sm_count() / 4 && p.num_m_tiles >= 4 * (sm_count() / n_tiles_ws)) {
-      BN = small64 ? 64 : bn_ws;
-      p.ws = 1;
-    }
-  }
   p.num_n_tiles = (Cout + BN - 1) / BN;
 
   CUtensorMap tmA, tmB, tmOut, tmRes;
@@ -613,9 +561,9 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
                          64, true);
   if (rc) return rc;
   if (stats != nullptr) SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, stream));
-  if (BN == 64) return launch_igemm<64, 2>(tmA, tmB, tmOut, tmRes, p, stream);
-  if (BN == 128) return launch_igemm<128, 1>(tmA, tmB, tmOut, tmRes, p, stream);
-  return launch_igemm<256, 1>(tmA, tmB, tmOut, tmRes, p, stream);
+  if (BN == 64) return launch_igemm<64, 6, 2>(tmA, tmB, tmOut, tmRes, p, stream);
+  if (BN == 128) return launch_igemm<128, 5, 1>(tmA, tmB, tmOut, tmRes, p, stream);
+  return launch_igemm<256, 3, 2>(tmA, tmB, tmOut, tmRes, p, stream);
 }
 
 template <int STAGES>
