@@ -66,7 +66,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_bar[8];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_part[kEpiWarps][2][kChunksPerWarp * 64];   // per-warp column sums of a tile
+  __shared__ __align__(16) float s_part[kEpiWarps][2][kChunksPerWarp * 64];   // per-warp column sums of a tile
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -179,8 +179,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t row_slot[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) row_slot[g] = lane * 128 + ((g ^ (lane & 7)) << 4);
-    // stats pass: lane reads 16 bytes (8 columns, slot lane%8) of rows it*4 + lane/8
+    // stats pass: lane reads 16 bytes (8 columns, slot lane%8) of rows it*4 + lane/8; the row's
+    // swizzle phase (row & 7) alternates between st_row and st_row + 4 with the parity of `it`
     const int st_row = lane >> 3, st_slot = lane & 7;
+    const uint32_t st_off0 = st_row * 128 + ((st_slot ^ st_row) << 4);
+    const uint32_t st_off1 = st_row * 128 + ((st_slot ^ (st_row + 4)) << 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
@@ -198,9 +201,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int chunk = half + ci * kHalves;
         const int col0 = n0 + chunk * 64;
         const bool live = col0 < p.Cout;           // ragged N (warp-uniform)
-        float cs1[8], cs2[8];
+        float2 cs1[4], cs2[4];     // packed fp32x2 accumulators (add.f32x2 / fma.f32x2 on sm_100)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { cs1[j] = 0.f; cs2[j] = 0.f; }
+        for (int j = 0; j < 4; ++j) { cs1[j] = make_float2(0.f, 0.f); cs2[j] = make_float2(0.f, 0.f); }
         if (live) {
           uint8_t* slab = slabs + slab_idx * kSlabBytes;
           // the TMA store that last read this slab must have finished reading it
@@ -250,15 +253,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (p.stats != nullptr) {
             __syncwarp();
             // column sums of the bf16 values as stored: 8 x LDS.128 cover the 32 x 64 slab
+            const bool full = rows_valid >= 32;          // warp-uniform
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + st_row;
-              uint4 q = *reinterpret_cast<const uint4*>(slab + rr * 128 + ((st_slot ^ (rr & 7)) << 4));
-              if (rr >= rows_valid) q = make_uint4(0, 0, 0, 0);
-              float f[8];
-              unpack8(q, f);
+              uint4 q = *reinterpret_cast<const uint4*>(slab + it * 512 + ((it & 1) ? st_off1 : st_off0));
+              if (!full && it * 4 + st_row >= rows_valid) q = make_uint4(0, 0, 0, 0);
+              const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { cs1[j] += f[j]; cs2[j] = fmaf(f[j], f[j], cs2[j]); }
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(hq[j]);
+                cs1[j] = __fadd2_rn(cs1[j], f);
+                cs2[j] = __ffma2_rn(f, f, cs2[j]);
+              }
             }
           }
           fence_proxy_async_smem();
@@ -272,18 +278,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.stats != nullptr) {
           // lanes with equal lane%8 hold partial sums of the same 8 columns (different rows)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 8);
-            cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 8);
-            cs1[j] += __shfl_xor_sync(0xffffffffu, cs1[j], 16);
-            cs2[j] += __shfl_xor_sync(0xffffffffu, cs2[j], 16);
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              float2 t1, t2;
+              t1.x = __shfl_xor_sync(0xffffffffu, cs1[j].x, o);
+              t1.y = __shfl_xor_sync(0xffffffffu, cs1[j].y, o);
+              t2.x = __shfl_xor_sync(0xffffffffu, cs2[j].x, o);
+              t2.y = __shfl_xor_sync(0xffffffffu, cs2[j].y, o);
+              cs1[j] = __fadd2_rn(cs1[j], t1);
+              cs2[j] = __fadd2_rn(cs2[j], t2);
+            }
           }
           if (lane < 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              s_part[e][0][ci * 64 + lane * 8 + j] = cs1[j];
-              s_part[e][1][ci * 64 + lane * 8 + j] = cs2[j];
-            }
+            float4* d1 = reinterpret_cast<float4*>(&s_part[e][0][ci * 64 + lane * 8]);
+            float4* d2 = reinterpret_cast<float4*>(&s_part[e][1][ci * 64 + lane * 8]);
+            d1[0] = make_float4(cs1[0].x, cs1[0].y, cs1[1].x, cs1[1].y);
+            d1[1] = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
+            d2[0] = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
+            d2[1] = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
           }
         }
       }
