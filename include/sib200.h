@@ -102,6 +102,28 @@ int sib_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H
 int sib_gap_fwd(const void* x, void* y, int N, int HW, int C, void* stream);
 int sib_gap_bwd(const void* dy, void* dx, int N, int HW, int C, void* stream);
 
+/* ---- BResNet-50 extras (BResNet50_encoder.yaml:44-51): anti-alias BlurPool, AvgPool shortcut,
+ *      ECA attention, per-(sample,channel) scaling (ECA / drop-connect), add+act ---- */
+int sib_blurpool_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int sib_blurpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+int sib_avgpool2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int sib_avgpool2_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+int sib_maxpool3x3s1_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C,
+                         void* stream);
+int sib_maxpool3x3s1_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C,
+                         void* stream);
+/* out[n][c] = scale * sum_hw a[n][hw][c] * (b ? b[n][hw][c] : 1) */
+int sib_chan_reduce(const void* a, const void* b, float* out, int N, int HW, int C, float scale,
+                    void* stream);
+/* y[n][hw][c] = x[n][hw][c] * mul[n][c] (+ add[n][c]) */
+int sib_scale_nc(const void* x, const float* mul, const float* add, void* y, int N, int HW, int C,
+                 void* stream);
+int sib_eca_gate_fwd(const float* p, const float* w, float* s, int N, int C, void* stream);
+int sib_eca_gate_bwd(const float* ds, const float* s, const float* p, const float* w, float* dp,
+                     float* dw, int N, int C, void* stream);
+int sib_add_act(const void* a, const void* b, void* y, long n, int act, float slope, void* stream);
+int sib_act_bwd(const void* dy, const void* y, void* g, long n, int act, float slope, void* stream);
+
 /* ---- heads: pytorch_tools.losses.smooth.CrossEntropyLoss (arg_parser.py:140-142),
  *      angular_losses.py AdditiveAngularMarginLoss / CosFace / SphereLinearLayer ---- */
 int sib_ce_fwd_bwd(const void* logits, int logits_fp32, const long* labels,

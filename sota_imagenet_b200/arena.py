@@ -53,6 +53,10 @@ class ParamArena:
         self.pack_table, self.pack_blocks = ops.pack_table(pack_entries, device)
         self.pack_count = len(pack_entries)
         self._sig = None
+        # weight standardisation (reference train.py:66-67): (param, mean_invstd buffer) pairs whose
+        # bf16 shadow holds (w - mean) / sqrt(var + eps) per output channel instead of w itself
+        self.ws_entries = []
+        self.ws_eps = 1e-7
 
     @staticmethod
     def view_of(buf, off, shape, layout):
@@ -75,6 +79,7 @@ class ParamArena:
         sig = self.signature()
         if force or sig != self._sig:
             ops.cast_bf16(self.flat, self.shadow)
+            self.standardize_shadow()
             self.repack_dgrad()
             self._sig = sig
 
@@ -83,8 +88,29 @@ class ParamArena:
             ops.call("sib_pack_dgrad_weights", ops._p(self.shadow), ops._p(self.wdgrad),
                      ops._p(self.pack_table), self.pack_count, self.pack_blocks, ops._stream())
 
+    def enable_weight_standardization(self, params, eps=1e-7):
+        self.ws_eps = eps
+        self.ws_entries = []
+        for p in params:
+            k = p.shape[0]
+            mi = torch.empty((k, 2), dtype=torch.float32, device=self.device)
+            self.ws_entries.append((p, mi))
+        self._sig = None
+
+    def standardize_shadow(self):
+        for p, mi in self.ws_entries:
+            o, n, k = self.offset_of[id(p)], p.numel(), p.shape[0]
+            ops.weight_standardize(self.flat[o:o + n], self.shadow[o:o + n], mi, k, n // k, self.ws_eps)
+
+    def standardize_grads(self):
+        """dL/dw from dL/d(standardised w), in place in the gradient arena (end of backward)."""
+        for p, mi in self.ws_entries:
+            o, n, k = self.offset_of[id(p)], p.numel(), p.shape[0]
+            ops.weight_standardize_bwd(self.flat[o:o + n], mi, self.grad[o:o + n], k, n // k)
+
     def mark_fresh(self):
         """Called by the fused optimizer after it rewrote params + shadow itself."""
+        self.standardize_shadow()
         self.repack_dgrad()
         self._sig = self.signature()
 

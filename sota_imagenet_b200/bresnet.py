@@ -1,0 +1,442 @@
+"""BResNet-50: `pytorch_tools.models.resnet50(**model_params)` with the kwargs of the reference's
+BResNet configs (configs/_old_configs/_first_attempts/BResNet50_encoder.yaml:44-60, BResNet50.yaml:7-10):
+deep stem, anti-aliased down-sampling (BlurPool, AvgPool shortcut), ECA attention, in-place ABN with
+leaky ReLU, dropout, drop-connect, weight standardisation, EMA (optimizer side).
+
+pytorch_tools is absent and unpinned, so the module graph below is this repo's restatement of those
+switches; oracle/bresnet_ref.py is its fp32 PyTorch twin used for parity.  Convs
+run on the tcgen05 kernels; the extra operators are the memory-bound kernels of csrc/extra.cu.  The
+block is composed from per-operator fwd/bwd pairs (not yet fused like the ResNet-50 bottleneck)."""
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .modules import BatchNorm2d, Conv2d, Linear, SibModule, StemConv, _as_act
+
+
+class PaddedConv2d(SibModule):
+    """3x3 convolution whose logical channel counts (32 in the deep stem) are zero-padded to the 64
+    the implicit-GEMM k-block needs.  Tiny filters: padding / packing / slicing use torch ops."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, phys_in=64, phys_out=64):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = (kernel_size, kernel_size), stride, padding
+        self.phys_in, self.phys_out = phys_in, phys_out
+        w = torch.empty(out_channels, in_channels, kernel_size, kernel_size)
+        nn.init.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")
+        self.weight = nn.Parameter(w)
+        self.ws = False
+        self.ws_eps = 1e-7
+
+    def _effective_weight(self):
+        w = self.weight.data
+        if self.ws:
+            var, mean = torch.var_mean(w, dim=(1, 2, 3), keepdim=True, unbiased=False)
+            self._ws_stats = (mean, torch.rsqrt(var + self.ws_eps))
+            w = (w - mean) * self._ws_stats[1]
+        return w
+
+    def _packed(self):
+        k = self.kernel_size[0]
+        w = self._effective_weight()
+        full = torch.zeros((self.phys_out, k, k, self.phys_in), dtype=torch.bfloat16, device=w.device)
+        full[:self.out_channels, :, :, :self.in_channels] = w.permute(0, 2, 3, 1)
+        return full
+
+    def run(self, x, stats=None):
+        full = self._packed()
+        self._wd = full.flip(1, 2).permute(3, 1, 2, 0).contiguous()
+        return ops.conv2d_fprop(x, full.permute(0, 3, 1, 2), self.stride, self.padding, stats=stats)
+
+    def run_dgrad(self, dy, x_shape):
+        k = self.kernel_size[0]
+        return ops.conv2d_dgrad(dy, self._wd, x_shape, k, k, self.stride, self.padding)
+
+    def run_wgrad(self, x, dy):
+        k = self.kernel_size[0]
+        dw = torch.zeros((self.phys_out, k, k, self.phys_in), dtype=torch.float32, device=dy.device).permute(0, 3, 1, 2)
+        ops.conv2d_wgrad(x, dy, dw, self.stride, self.padding)
+        g = dw[:self.out_channels, :self.in_channels]
+        if self.ws:
+            mean, invstd = self._ws_stats
+            what = (self.weight.data - mean) * invstd
+            g = invstd * (g - g.mean(dim=(1, 2, 3), keepdim=True) - what * (g * what).mean(dim=(1, 2, 3), keepdim=True))
+        self._grad(self.weight).add_(g)
+
+    def fwd(self, x, train):
+        return self.run(x), (x,)
+
+    def bwd(self, dy, saved, need_dx=True):
+        dy = _as_act(dy)
+        self.run_wgrad(saved[0], dy)
+        return self.run_dgrad(dy, tuple(saved[0].shape)) if need_dx else None
+
+
+class DeepStemFirst(StemConv):
+    """3x3/2 conv 3 -> 32 through the row-pair packing; emits 64 physical channels (32 zero)."""
+
+    def __init__(self, out_channels=32, phys_out=64):
+        super().__init__(out_channels, 3, 1)
+        self.phys_out = phys_out
+        self.ws = False
+        self.ws_eps = 1e-7
+
+    def _effective_weight(self):
+        return PaddedConv2d._effective_weight(self)
+
+    def _packed_weight(self):
+        w = self._effective_weight().contiguous()
+        wq = ops.stem_pack_weight(w, self.na, self.off)                      # [K, NA, 1, 64]
+        full = torch.zeros((self.phys_out, self.na, 1, 64), dtype=torch.bfloat16, device=w.device)
+        full[:self.out_channels] = wq
+        return full.permute(0, 3, 1, 2)
+
+    def run_wgrad(self, xq, dy):
+        dwq = torch.zeros((self.phys_out, self.na, 1, 64), dtype=torch.float32, device=dy.device).permute(0, 3, 1, 2)
+        ops.conv2d_wgrad(xq, dy, dwq, 1, 0, pad_hw=(self.a0, 0))
+        g = torch.zeros_like(self.weight.data)
+        ops.stem_unpack_wgrad(dwq[:self.out_channels].contiguous(memory_format=torch.channels_last), g,
+                              self.na, self.off, accumulate=False)
+        if self.ws:
+            mean, invstd = self._ws_stats
+            what = (self.weight.data - mean) * invstd
+            g = invstd * (g - g.mean(dim=(1, 2, 3), keepdim=True) - what * (g * what).mean(dim=(1, 2, 3), keepdim=True))
+        self._grad(self.weight).add_(g)
+
+
+class PaddedBatchNorm2d(BatchNorm2d):
+    """BN over `num_features` logical channels living in a wider physical tensor: the pad channels
+    are all-zero, stay zero (gamma = 1, beta = 0 there) and carry no parameters."""
+
+    def __init__(self, num_features, phys, **kw):
+        super().__init__(num_features, **kw)
+        self.phys = phys
+
+    def _padded(self, t, fill):
+        out = torch.full((self.phys,), fill, dtype=torch.float32, device=t.device)
+        out[:self.num_features] = t
+        return out
+
+    def fwd(self, x, train, stats=None):
+        n, c, h, w = x.shape
+        if train:
+            stats = stats if stats is not None else ops.bn_stats(x)
+            world = self._world()
+            count = n * h * w
+            if world > 1:
+                torch.distributed.all_reduce(stats, group=self.process_group)
+                count *= world
+            rm, rv = self._padded(self.running_mean, 0.0), self._padded(self.running_var, 1.0)
+            mi, ss = ops.bn_finalize(stats, self._padded(self.weight.data, 1.0), self._padded(self.bias.data, 0.0),
+                                     rm, rv, count, self.eps, self.momentum)
+            self.running_mean.copy_(rm[:self.num_features])
+            self.running_var.copy_(rv[:self.num_features])
+            self.num_batches_tracked += 1
+        else:
+            mi, count = None, n * h * w
+            ss = ops.bn_eval_scale(self._padded(self.weight.data, 1.0), self._padded(self.bias.data, 0.0),
+                                   self._padded(self.running_mean, 0.0), self._padded(self.running_var, 1.0), self.eps)
+        y = ops.bn_apply(x, ss, self.act, self.slope)
+        return y, (x, mi, count, ss)
+
+    def bwd(self, dy, saved, need_dx=True):
+        x, mi, count, ss = saved
+        dy = _as_act(dy)
+        sums = self.reduce_sums(ops.bn_bwd_reduce(dy, None, x, mi, self.act, self.slope, mask_ss=ss))
+        gamma = self._padded(self.weight.data, 1.0)
+        dx, _, _ = ops.bn_bwd_apply(dy, None, x, mi, gamma, sums, count, self.act, self.slope, mask_ss=ss)
+        self._grad(self.bias).add_(sums[0, :self.num_features])
+        self._grad(self.weight).add_(sums[1, :self.num_features])
+        return dx
+
+
+class BNAct(BatchNorm2d):
+    """ABN / InplaceABN: BN + activation, statistics from the producing conv's epilogue when given."""
+
+    def fwd(self, x, train, stats=None):
+        n, c, h, w = x.shape
+        if train and stats is None:
+            stats = ops.bn_stats(x)
+        mi, ss, count = self.finalize(stats, n * h * w, train)
+        y = ops.bn_apply(x, ss, self.act, self.slope)
+        return y, (x, mi, count, ss)
+
+    def bwd(self, dy, saved, need_dx=True):
+        x, mi, count, ss = saved
+        dy = _as_act(dy)
+        sums = self.reduce_sums(ops.bn_bwd_reduce(dy, None, x, mi, self.act, self.slope, mask_ss=ss))
+        dx, _, _ = ops.bn_bwd_apply(dy, None, x, mi, self.weight.data, sums, count, self.act, self.slope,
+                                    mask_ss=ss, param_grads=self.grad_ptrs())
+        return dx
+
+
+class BlurPool(SibModule):
+    def __init__(self, channels=0):
+        super().__init__()
+        self.channels = channels
+
+    def fwd(self, x, train):
+        return ops.blurpool_fwd(x), (tuple(x.shape),)
+
+    def bwd(self, dy, saved, need_dx=True):
+        return ops.blurpool_bwd(_as_act(dy), saved[0])
+
+
+class ECA(SibModule):
+    """x * sigmoid(conv1d_k3(GAP(x))) over the channel axis (attn_type: eca)."""
+
+    def __init__(self, channels=None, kernel_size=3):
+        super().__init__()
+        assert kernel_size == 3
+        self.weight = nn.Parameter(torch.empty(1, 1, 3).uniform_(-0.5, 0.5))
+
+    def fwd(self, x, train):
+        n, c, h, w = x.shape
+        p = ops.chan_reduce(x, scale=1.0 / (h * w))
+        s = ops.eca_gate_fwd(p, self.weight.data.view(3).contiguous())
+        return ops.scale_nc(x, s), (x, p, s)
+
+    def bwd(self, dy, saved, need_dx=True):
+        x, p, s = saved
+        dy = _as_act(dy)
+        n, c, h, w = x.shape
+        ds = ops.chan_reduce(dy, x)
+        dw = torch.zeros(3, dtype=torch.float32, device=x.device)
+        dp = ops.eca_gate_bwd(ds, s, p, self.weight.data.view(3).contiguous(), dw)
+        self._grad(self.weight).view(3).add_(dw)
+        return ops.scale_nc(dy, s, add=dp / (h * w))
+
+
+class BBottleneck(SibModule):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=False, norm_act="leaky_relu", antialias=True,
+                 attn=True, keep_prob=1.0):
+        super().__init__()
+        out = planes * self.expansion
+        self.stride, self.antialias, self.keep_prob = stride, antialias, keep_prob
+        conv_stride = 1 if (antialias and stride > 1) else stride
+        self.conv1 = Conv2d(inplanes, planes, 1)
+        self.bn1 = BNAct(planes, activation=norm_act)
+        self.conv2 = Conv2d(planes, planes, 3, stride=conv_stride, padding=1)
+        self.bn2 = BNAct(planes, activation=norm_act)
+        self.blur = BlurPool(planes) if (antialias and stride > 1) else None
+        self.conv3 = Conv2d(planes, out, 1)
+        self.bn3 = BNAct(out, activation="identity")
+        self.eca = ECA(out) if attn else None
+        self.act = ops.ACT_CODES[norm_act]
+        if downsample:
+            ds_stride = 1 if (antialias and stride > 1) else stride
+            self.downsample = nn.Sequential(Conv2d(inplanes, out, 1, stride=ds_stride), BNAct(out, activation="identity"))
+            self.pool_shortcut = antialias and stride > 1
+        else:
+            self.downsample = None
+            self.pool_shortcut = False
+
+    @staticmethod
+    def _conv_bn(conv, bn, x, train):
+        stats = torch.empty((2, conv.out_channels), dtype=torch.float32, device=x.device) if train else None
+        c = conv.run(x, stats)
+        y, s = bn.fwd(c, train, stats=stats)
+        return y, s
+
+    def fwd(self, x, train):
+        a1, s1 = self._conv_bn(self.conv1, self.bn1, x, train)
+        a2, s2 = self._conv_bn(self.conv2, self.bn2, a1, train)
+        sb = None
+        a2b = a2
+        if self.blur is not None:
+            a2b, sb = self.blur.fwd(a2, train)
+        y3, s3 = self._conv_bn(self.conv3, self.bn3, a2b, train)
+        se = None
+        if self.eca is not None:
+            y3, se = self.eca.fwd(y3, train)
+        mask = None
+        if train and self.keep_prob < 1.0:
+            n, c = y3.shape[0], y3.shape[1]
+            keep = (torch.rand(n, 1, device=y3.device) < self.keep_prob).float() / self.keep_prob
+            mask = keep.expand(n, c).contiguous()
+            y3 = ops.scale_nc(y3, mask)
+        xs, sp, sd = x, None, None
+        if self.downsample is not None:
+            if self.pool_shortcut:
+                xs = ops.avgpool2_fwd(x)
+            r, sd = self._conv_bn(self.downsample[0], self.downsample[1], xs, train)
+        else:
+            r = x
+        out = ops.add_act(y3, r, self.act, self.bn1.slope)
+        if not train:
+            return out, None
+        return out, (x, a1, s1, a2, s2, a2b, sb, s3, se, mask, xs, sd, out)
+
+    def bwd(self, dout, saved, need_dx=True):
+        x, a1, s1, a2, s2, a2b, sb, s3, se, mask, xs, sd, out = saved
+        g = ops.act_bwd(_as_act(dout), out, self.act, self.bn1.slope)
+        d = g
+        if mask is not None:
+            d = ops.scale_nc(d, mask)
+        if self.eca is not None:
+            d = self.eca.bwd(d, se)
+        dc3 = self.bn3.bwd(d, s3)
+        self.conv3.run_wgrad(a2b, dc3)
+        d = self.conv3.run_dgrad(dc3, tuple(a2b.shape))
+        if self.blur is not None:
+            d = self.blur.bwd(d, sb)
+        dc2 = self.bn2.bwd(d, s2)
+        self.conv2.run_wgrad(a1, dc2)
+        d = self.conv2.run_dgrad(dc2, tuple(a1.shape))
+        dc1 = self.bn1.bwd(d, s1)
+        self.conv1.run_wgrad(x, dc1)
+        if self.downsample is None:
+            return self.conv1.run_dgrad(dc1, tuple(x.shape), residual=g) if need_dx else None
+        dcd = self.downsample[1].bwd(g, sd)
+        self.downsample[0].run_wgrad(xs, dcd)
+        if not need_dx:
+            return None
+        dx = self.conv1.run_dgrad(dc1, tuple(x.shape))
+        if self.pool_shortcut:
+            dxs = self.downsample[0].run_dgrad(dcd, tuple(xs.shape))
+            return ops.add_act(dx, ops.avgpool2_bwd(dxs, tuple(x.shape)), ops.ACT_NONE)
+        if self.downsample[0].stride == 1:
+            return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx, residual=dx)
+        return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx)
+
+
+class BResNet(SibModule):
+    def __init__(self, layers=(3, 4, 6, 3), num_classes=1000, stem_type="deep", antialias=True, attn_type="eca",
+                 norm_layer="inplaceabn", norm_act="leaky_relu", drop_rate=0.2, drop_connect_rate=0.2,
+                 weight_standardization=False, **unused):
+        super().__init__()
+        if stem_type != "deep":
+            raise _lib.SibError("BResNet: stem_type must be 'deep' (space2depth is not built)")
+        if norm_layer not in ("abn", "inplaceabn"):
+            raise _lib.SibError("BResNet: norm_layer must be abn / inplaceabn")
+        self.drop_rate, self.antialias, self.norm_act = drop_rate, antialias, norm_act
+        self.weight_standardization = weight_standardization
+        # deep stem: conv3x3/2(3->32)-BN-act, conv3x3(32->32)-BN-act, conv3x3(32->64), then bn1-act
+        self.conv1 = nn.Sequential(
+            DeepStemFirst(32, 64), PaddedBatchNorm2d(32, 64, activation=norm_act), nn.Identity(),
+            PaddedConv2d(32, 32, phys_in=64, phys_out=64), PaddedBatchNorm2d(32, 64, activation=norm_act), nn.Identity(),
+            PaddedConv2d(32, 64, phys_in=64, phys_out=64))
+        self.bn1 = BNAct(64, activation=norm_act)
+        self.blurpool = BlurPool(64) if antialias else None
+        inplanes, nblocks, bi = 64, sum(layers), 0
+        for i, (planes, n) in enumerate(zip((64, 128, 256, 512), layers)):
+            blocks = []
+            for j in range(n):
+                keep = 1.0 - drop_connect_rate * bi / nblocks
+                blocks.append(BBottleneck(inplanes, planes, stride=(1 if i == 0 or j > 0 else 2), downsample=(j == 0),
+                                          norm_act=norm_act, antialias=antialias, attn=(attn_type == "eca"),
+                                          keep_prob=keep))
+                inplanes = planes * BBottleneck.expansion
+                bi += 1
+            setattr(self, "layer%d" % (i + 1), nn.Sequential(*blocks))
+        self.fc = Linear(inplanes, (num_classes + 7) // 8 * 8)
+        self._out_features = num_classes
+
+    def _prepare_input(self, x):
+        return x
+
+    def blocks(self):
+        for i in range(1, 5):
+            for blk in getattr(self, "layer%d" % i):
+                yield blk
+
+    def enable_weight_standardization(self, eps=1e-7):
+        self.weight_standardization = True
+        self._ws_eps = eps
+        for m in self.modules():
+            if isinstance(m, (PaddedConv2d, DeepStemFirst)):
+                m.ws, m.ws_eps = True, eps
+        self._arena = None
+        return self
+
+    def ensure_arena(self):
+        fresh = self._arena is None or not self._arena.intact()
+        a = super().ensure_arena()
+        if fresh and self.weight_standardization:
+            convs = [m.weight for m in self.modules() if isinstance(m, Conv2d)]
+            a.enable_weight_standardization(convs, getattr(self, "_ws_eps", 1e-7))
+            for m in self.modules():
+                if isinstance(m, (PaddedConv2d, DeepStemFirst)):
+                    m.ws = True
+        return a
+
+    def _end_backward(self):
+        if self.weight_standardization:
+            self._arena.standardize_grads()
+        super()._end_backward()
+
+    def fwd(self, x, train):
+        c = self.conv1
+        y, xq = c[0].run(x)
+        y, sb0 = c[1].fwd(y, train)
+        y2 = c[3].run(y)
+        a, sb1 = c[4].fwd(y2, train)
+        stats = torch.empty((2, 64), dtype=torch.float32, device=x.device) if train else None
+        y3 = c[6].run(a, stats)
+        a0, sbn = self.bn1.fwd(y3, train, stats=stats)
+        if self.antialias:
+            p, pidx = ops.maxpool3x3s1_fwd(a0)
+            p2, sblur = self.blurpool.fwd(p, train)
+        else:
+            p2, pidx = ops.maxpool3x3s2_fwd(a0)
+            sblur = None
+        h = p2
+        saved = []
+        for blk in self.blocks():
+            h, s = blk.fwd(h, train)
+            saved.append(s)
+        feat = ops.gap_fwd(h)
+        dmask = None
+        if train and self.drop_rate > 0:
+            dmask = ((torch.rand(feat.shape, device=feat.device) >= self.drop_rate).to(torch.bfloat16) / (1 - self.drop_rate))
+            feat = feat * dmask
+        logits, fc_saved = self.fc.fwd(feat, train)
+        logits = logits[:, :self._out_features] if logits.shape[1] != self._out_features else logits
+        if not train:
+            return logits, None
+        return logits, (xq, sb0, y, sb1, a, sbn, tuple(a0.shape), pidx, sblur, saved, tuple(h.shape), dmask, fc_saved)
+
+    def bwd(self, dlogits, saved_all, need_dx=False):
+        xq, sb0, y, sb1, a, sbn, a0_shape, pidx, sblur, saved, h_shape, dmask, fc_saved = saved_all
+        n = dlogits.shape[0]
+        if dlogits.shape[1] != self.fc.out_features:
+            full = torch.zeros((n, self.fc.out_features), dtype=torch.bfloat16, device=dlogits.device)
+            full[:, :dlogits.shape[1]] = dlogits
+            dlogits = full
+        dfeat = self.fc.bwd(dlogits.to(torch.bfloat16).contiguous(), fc_saved)
+        if dmask is not None:
+            dfeat = dfeat * dmask
+        d = ops.gap_bwd(_as_act(dfeat), h_shape)
+        blocks = list(self.blocks())
+        for i in range(len(blocks) - 1, -1, -1):
+            d = blocks[i].bwd(d, saved[i], need_dx=True)
+            saved[i] = None
+            self._after_block_backward(i)
+        if self.antialias:
+            d = self.blurpool.bwd(d, sblur)
+            d = ops.maxpool3x3s1_bwd(d, pidx)
+        else:
+            d = ops.maxpool3x3s2_bwd(d, pidx, a0_shape)
+        c = self.conv1
+        dy3 = self.bn1.bwd(d, sbn)
+        c[6].run_wgrad(a, dy3)
+        d = c[6].run_dgrad(dy3, tuple(a.shape))
+        d = c[4].bwd(d, sb1)
+        c[3].run_wgrad(y, d)
+        d = c[3].run_dgrad(d, tuple(y.shape))
+        d = c[1].bwd(d, sb0)
+        c[0].run_wgrad(xq, d)
+        return None
+
+    def _after_block_backward(self, block_index):
+        cb = getattr(self, "_block_bwd_cb", None)
+        if cb is not None:
+            cb(block_index)
+
+
+def bresnet50(num_classes=1000, **kwargs):
+    """BResNet-50 encoder config (BResNet50_encoder.yaml:44-51)."""
+    return BResNet((3, 4, 6, 3), num_classes=num_classes, **kwargs)

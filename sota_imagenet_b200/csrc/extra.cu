@@ -1,0 +1,441 @@
+// Kernels used only by the BResNet-50 variant (reference configs/_old_configs/_first_attempts/
+// BResNet50_encoder.yaml:44-51 kwargs on pytorch_tools.models.resnet50):
+//   * BlurPool  (antialias: [1,2,1]x[1,2,1]/16 depthwise, stride 2, zero padding 1) fwd / bwd
+//   * AvgPool2d(2,2) of the anti-aliased shortcut                                   fwd / bwd
+//   * ECA attention: per-sample channel means -> conv1d(k=3) over channels -> sigmoid -> scale
+//   * generic per-(sample, channel) scale / shift of an NHWC tensor (ECA scale, drop-connect)
+//   * add + activation and its backward mask
+// All NHWC bf16, 128-bit accesses.  These are memory-bound helpers, not tensor-core work.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/sib200.h"
+
+namespace sib {
+
+static inline int ew_grid(long n, int threads) {
+  long b = (n + threads - 1) / threads;
+  long cap = (long)sm_count() * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+__device__ __forceinline__ float blur_w(int d) { return d == 1 ? 0.5f : 0.25f; }   // [1,2,1]/4
+
+__global__ void __launch_bounds__(256)
+blurpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                    int W, int C, int OH, int OW) {
+  const int cvec = C >> 3;
+  const long total = (long)N * OH * OW * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    long t = i / cvec;
+    const int q = (int)(t % OW); t /= OW;
+    const int p = (int)(t % OH);
+    const int n = (int)(t / OH);
+    float acc[8] = {};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * p - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * q - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long)n * H + h) * W + w) * C + v * 8)), f);
+        const float wt = blur_w(r) * blur_w(s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, f[j], acc[j]);
+      }
+    }
+    stg_stream(y + i * 8, pack8(acc));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+blurpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
+                    int H, int W, int C, int OH, int OW) {
+  const int cvec = C >> 3;
+  const long total = (long)N * H * W * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    long t = i / cvec;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8] = {};
+    for (int p = (h >> 1); p <= ((h + 1) >> 1); ++p) {
+      if (p >= OH) continue;
+      const int r = h - 2 * p + 1;
+      if (r < 0 || r > 2) continue;
+      for (int q = (w >> 1); q <= ((w + 1) >> 1); ++q) {
+        if (q >= OW) continue;
+        const int s = w - 2 * q + 1;
+        if (s < 0 || s > 2) continue;
+        float g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((((long)n * OH + p) * OW + q) * cvec + v) * 8)), g);
+        const float wt = blur_w(r) * blur_w(s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, g[j], acc[j]);
+      }
+    }
+    stg_stream(dx + i * 8, pack8(acc));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                    int W, int C) {
+  const int cvec = C >> 3, OH = H >> 1, OW = W >> 1;
+  const long total = (long)N * OH * OW * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    long t = i / cvec;
+    const int q = (int)(t % OW); t /= OW;
+    const int p = (int)(t % OH);
+    const int n = (int)(t / OH);
+    float acc[8] = {};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        float f[8];
+        unpack8(ldg_stream(x + (((long)n * H + 2 * p + r) * W + 2 * q + s) * C + v * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+    stg_stream(y + i * 8, pack8(acc));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
+                    int H, int W, int C) {
+  const int cvec = C >> 3, OH = H >> 1, OW = W >> 1;
+  const long total = (long)N * H * W * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    long t = i / cvec;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float g[8] = {};
+    if ((h >> 1) < OH && (w >> 1) < OW) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((((long)n * OH + (h >> 1)) * OW + (w >> 1)) * cvec + v) * 8)), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+    }
+    stg_stream(dx + i * 8, pack8(g));
+  }
+}
+
+// out[n][c] = sum_hw a[n][hw][c] * (b ? b[n][hw][c] : 1)       one CTA per (sample, 64-channel group)
+__global__ void __launch_bounds__(256)
+chan_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                   float* __restrict__ out, int HW, int C, float scale) {
+  __shared__ float red[32][8][8];
+  const int n = blockIdx.y;
+  const int v = blockIdx.x * 8 + (threadIdx.x & 7);     // 8-channel vector index
+  const int lane_row = threadIdx.x >> 3;                // 32 row lanes
+  const int cvec = C >> 3;
+  float acc[8] = {};
+  if (v < cvec) {
+    for (int t = lane_row; t < HW; t += 32) {
+      const long off = (((long)n * HW + t) * cvec + v) * 8;
+      float fa[8];
+      unpack8(ldg_stream(a + off), fa);
+      if (b != nullptr) {
+        float fb[8];
+        unpack8(ldg_stream(b + off), fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(fa[j], fb[j], acc[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += fa[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[lane_row][threadIdx.x & 7][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int vv = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float s = 0.f;
+    for (int r = 0; r < 32; ++r) s += red[r][vv][j];
+    const int c = (blockIdx.x * 8 + vv) * 8 + j;
+    if (c < C) out[(long)n * C + c] = s * scale;
+  }
+}
+
+// y[n][hw][c] = x * mul[n][c] (+ add[n][c])
+__global__ void __launch_bounds__(256)
+scale_nc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mul,
+                const float* __restrict__ add, __nv_bfloat16* __restrict__ y, int N, int HW, int C) {
+  const int cvec = C >> 3;
+  const long total = (long)N * HW * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    const long n = i / ((long)HW * cvec);
+    float f[8];
+    unpack8(ldg_stream(x + i * 8), f);
+    const float* m = mul + n * C + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= __ldg(m + j);
+    if (add != nullptr) {
+      const float* ad = add + n * C + v * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += __ldg(ad + j);
+    }
+    stg_stream(y + i * 8, pack8(f));
+  }
+}
+
+// ECA gate: s[n][c] = sigmoid(sum_k w[k] * p[n][c + k - 1])   (conv1d, kernel 3, zero padding 1)
+__global__ void eca_gate_fwd_kernel(const float* __restrict__ p, const float* __restrict__ w,
+                                    float* __restrict__ s, int N, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int c = i % C;
+  float z = w[1] * p[i];
+  if (c > 0) z += w[0] * p[i - 1];
+  if (c + 1 < C) z += w[2] * p[i + 1];
+  s[i] = 1.f / (1.f + __expf(-z));
+}
+
+// ds -> dz = ds*s*(1-s); dp[n][c] = sum_k w[k] * dz[n][c - k + 1]; dw[k] += sum dz[n][c] p[n][c+k-1]
+__global__ void eca_gate_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ s,
+                                    const float* __restrict__ p, const float* __restrict__ w,
+                                    float* __restrict__ dp, float* __restrict__ dw, int N, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  if (i < N * C) {
+    const int c = i % C;
+    auto dz = [&](int idx) { const float sv = s[idx]; return ds[idx] * sv * (1.f - sv); };
+    const float z1 = dz(i);
+    float acc = w[1] * z1;
+    if (c + 1 < C) acc += w[0] * dz(i + 1);
+    if (c > 0) acc += w[2] * dz(i - 1);
+    dp[i] = acc;
+    g1 = z1 * p[i];
+    if (c > 0) g0 = z1 * p[i - 1];
+    if (c + 1 < C) g2 = z1 * p[i + 1];
+  }
+  g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(dw + 0, g0); atomicAdd(dw + 1, g1); atomicAdd(dw + 2, g2);
+  }
+}
+
+// y = act(a + b);   backward: g = dy * act'(y)
+__global__ void __launch_bounds__(256)
+add_act_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+               __nv_bfloat16* __restrict__ y, long nvec, int act, float slope) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long)gridDim.x * blockDim.x) {
+    float fa[8], fb[8];
+    unpack8(ldg_stream(a + i * 8), fa);
+    unpack8(ldg_stream(b + i * 8), fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = fa[j] + fb[j];
+      if (act == SIB_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (act == SIB_ACT_LEAKY) v = v > 0.f ? v : v * slope;
+      fa[j] = v;
+    }
+    stg_stream(y + i * 8, pack8(fa));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+               __nv_bfloat16* __restrict__ g, long nvec, int act, float slope) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long)gridDim.x * blockDim.x) {
+    float fd[8], fy[8];
+    unpack8(ldg_stream(dy + i * 8), fd);
+    unpack8(ldg_stream(y + i * 8), fy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (act == SIB_ACT_RELU) fd[j] = fy[j] > 0.f ? fd[j] : 0.f;
+      else if (act == SIB_ACT_LEAKY) fd[j] = fy[j] > 0.f ? fd[j] : fd[j] * slope;
+    }
+    stg_stream(g + i * 8, pack8(fd));
+  }
+}
+
+// 3x3 stride-1 pad-1 max pool (the anti-aliased stem pools at stride 1, then BlurPool)
+__global__ void __launch_bounds__(256)
+maxpool3x3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                        uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+  const int cvec = C >> 3;
+  const long total = (long)N * H * W * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    long t = i / cvec;
+    const int q = (int)(t % W); t /= W;
+    const int p = (int)(t % H);
+    const int n = (int)(t / H);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = p - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = q - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long)n * H + h) * W + w) * C + v * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > best[j]) { best[j] = f[j]; bi[j] = r * 3 + s; }
+      }
+    }
+    stg_stream(y + i * 8, pack8(best));
+    uint2 pk;
+    pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool3x3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                        __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+  const int cvec = C >> 3;
+  const long total = (long)N * H * W * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    long t = i / cvec;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8] = {};
+    for (int r = 0; r < 3; ++r) {
+      const int p = h + 1 - r;            // window (p,q) with tap (r,s) lands on (h,w)
+      if (p < 0 || p >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int q = w + 1 - s;
+        if (q < 0 || q >= W) continue;
+        const long o = ((((long)n * H + p) * W + q) * cvec + v) * 8;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
+        float g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), g);
+        const int tap = r * 3 + s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int bsel = (j < 4 ? (pk.x >> (8 * j)) : (pk.y >> (8 * (j - 4)))) & 0xff;
+          if (bsel == tap) acc[j] += g[j];
+        }
+      }
+    }
+    stg_stream(dx + i * 8, pack8(acc));
+  }
+}
+
+}  // namespace sib
+
+using namespace sib;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define BF(p) static_cast<__nv_bfloat16*>(p)
+#define CBF(p) static_cast<const __nv_bfloat16*>(p)
+
+extern "C" int sib_blurpool_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  SIB_CHECK(C % 8 == 0, "blurpool: C %% 8 != 0");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  blurpool_fwd_kernel<<<ew_grid((long)N * OH * OW * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), BF(y), N, H, W, C, OH, OW);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_blurpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
+  SIB_CHECK(C % 8 == 0, "blurpool: C %% 8 != 0");
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  blurpool_bwd_kernel<<<ew_grid((long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(dy), BF(dx), N, H, W, C, OH, OW);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_avgpool2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  SIB_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool2: needs C %% 8 == 0 and even H, W");
+  avgpool2_fwd_kernel<<<ew_grid((long)N * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), BF(y), N, H, W, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_avgpool2_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
+  SIB_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool2: needs C %% 8 == 0 and even H, W");
+  avgpool2_bwd_kernel<<<ew_grid((long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(dy), BF(dx), N, H, W, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_chan_reduce(const void* a, const void* b, float* out, int N, int HW, int C,
+                               float scale, void* stream) {
+  SIB_CHECK(C % 8 == 0, "chan_reduce: C %% 8 != 0");
+  dim3 grid((C / 8 + 7) / 8, N);
+  chan_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(a), CBF(b), out, HW, C, scale);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_scale_nc(const void* x, const float* mul, const float* add, void* y, int N,
+                            int HW, int C, void* stream) {
+  SIB_CHECK(C % 8 == 0, "scale_nc: C %% 8 != 0");
+  scale_nc_kernel<<<ew_grid((long)N * HW * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), mul, add,
+                                                                               BF(y), N, HW, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_eca_gate_fwd(const float* p, const float* w, float* s, int N, int C,
+                                void* stream) {
+  eca_gate_fwd_kernel<<<(N * C + 255) / 256, 256, 0, ST(stream)>>>(p, w, s, N, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_eca_gate_bwd(const float* ds, const float* s, const float* p, const float* w,
+                                float* dp, float* dw, int N, int C, void* stream) {
+  eca_gate_bwd_kernel<<<(N * C + 255) / 256, 256, 0, ST(stream)>>>(ds, s, p, w, dp, dw, N, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_add_act(const void* a, const void* b, void* y, long n, int act, float slope,
+                           void* stream) {
+  SIB_CHECK(n % 8 == 0, "add_act: length %% 8 != 0");
+  add_act_kernel<<<ew_grid(n / 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), BF(y), n / 8, act, slope);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_act_bwd(const void* dy, const void* y, void* g, long n, int act, float slope,
+                           void* stream) {
+  SIB_CHECK(n % 8 == 0, "act_bwd: length %% 8 != 0");
+  act_bwd_kernel<<<ew_grid(n / 8, 256), 256, 0, ST(stream)>>>(CBF(dy), CBF(y), BF(g), n / 8, act, slope);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_maxpool3x3s1_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C,
+                                    void* stream) {
+  SIB_CHECK(C % 8 == 0, "maxpool: C %% 8 != 0");
+  maxpool3x3s1_fwd_kernel<<<ew_grid((long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), BF(y), static_cast<uint8_t*>(idx), N, H, W, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_maxpool3x3s1_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W,
+                                    int C, void* stream) {
+  SIB_CHECK(C % 8 == 0, "maxpool: C %% 8 != 0");
+  maxpool3x3s1_bwd_kernel<<<ew_grid((long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(dy), static_cast<const uint8_t*>(idx), BF(dx), N, H, W, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}

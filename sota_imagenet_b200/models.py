@@ -107,10 +107,18 @@ class ResNet(SibModule):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
 
+_BRESNET_KEYS = ("stem_type", "antialias", "attn_type", "norm_layer", "drop_connect_rate", "deep_stem")
+
+
 def resnet50(num_classes=1000, pretrained=None, **kwargs):
-    """`pytorch_tools.models.resnet50` / `torchvision.models.resnet50` replacement."""
+    """`pytorch_tools.models.resnet50` / `torchvision.models.resnet50` replacement.  The BResNet
+    switches of the reference's configs (stem_type, antialias, attn_type, norm_layer, norm_act,
+    drop_rate, drop_connect_rate) select the BResNet-50 graph (bresnet.py)."""
     if pretrained:
         raise _lib.SibError("no pretrained weights are available offline")
+    if any(k in kwargs for k in _BRESNET_KEYS):
+        from .bresnet import bresnet50
+        return bresnet50(num_classes=num_classes, **kwargs)
     return ResNet((3, 4, 6, 3), num_classes=num_classes, **kwargs)
 
 

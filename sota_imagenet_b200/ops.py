@@ -227,6 +227,98 @@ def gap_bwd(dy, x_shape):
     return dx
 
 
+# ------------------------------------------------------------------ BResNet extras
+def blurpool_fwd(x):
+    n, c, h, w = x.shape
+    y = new_act(n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1, x.device)
+    call("sib_blurpool_fwd", _p(x), _p(y), n, h, w, c, _stream())
+    return y
+
+
+def blurpool_bwd(dy, x_shape):
+    n, c, h, w = x_shape
+    dx = new_act(n, c, h, w, dy.device)
+    call("sib_blurpool_bwd", _p(dy), _p(dx), n, h, w, c, _stream())
+    return dx
+
+
+def avgpool2_fwd(x):
+    n, c, h, w = x.shape
+    y = new_act(n, c, h // 2, w // 2, x.device)
+    call("sib_avgpool2_fwd", _p(x), _p(y), n, h, w, c, _stream())
+    return y
+
+
+def avgpool2_bwd(dy, x_shape):
+    n, c, h, w = x_shape
+    dx = new_act(n, c, h, w, dy.device)
+    call("sib_avgpool2_bwd", _p(dy), _p(dx), n, h, w, c, _stream())
+    return dx
+
+
+def maxpool3x3s1_fwd(x):
+    n, c, h, w = x.shape
+    y = new_act(n, c, h, w, x.device)
+    idx = torch.empty((n, h, w, c), dtype=torch.uint8, device=x.device)
+    call("sib_maxpool3x3s1_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
+    return y, idx
+
+
+def maxpool3x3s1_bwd(dy, idx):
+    n, c, h, w = dy.shape
+    dx = new_act(n, c, h, w, dy.device)
+    call("sib_maxpool3x3s1_bwd", _p(dy), _p(idx), _p(dx), n, h, w, c, _stream())
+    return dx
+
+
+def chan_reduce(a, b=None, scale=1.0):
+    n, c, h, w = a.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=a.device)
+    call("sib_chan_reduce", _p(a), _p(b), _p(out), n, h * w, c, float(scale), _stream())
+    return out
+
+
+def scale_nc(x, mul, add=None):
+    n, c, h, w = x.shape
+    y = new_act(n, c, h, w, x.device)
+    call("sib_scale_nc", _p(x), _p(mul), _p(add), _p(y), n, h * w, c, _stream())
+    return y
+
+
+def eca_gate_fwd(p, w):
+    s = torch.empty_like(p)
+    call("sib_eca_gate_fwd", _p(p), _p(w), _p(s), p.shape[0], p.shape[1], _stream())
+    return s
+
+
+def eca_gate_bwd(ds, s, p, w, dw):
+    dp = torch.empty_like(p)
+    call("sib_eca_gate_bwd", _p(ds), _p(s), _p(p), _p(w), _p(dp), _p(dw), p.shape[0], p.shape[1], _stream())
+    return dp
+
+
+def add_act(a, b, act, slope=0.01):
+    y = torch.empty_like(a)
+    call("sib_add_act", _p(a), _p(b), _p(y), a.numel(), act, float(slope), _stream())
+    return y
+
+
+def act_bwd(dy, y, act, slope=0.01):
+    g = torch.empty_like(y)
+    call("sib_act_bwd", _p(dy), _p(y), _p(g), y.numel(), act, float(slope), _stream())
+    return g
+
+
+def weight_standardize(w_flat, out_bf16, mean_invstd, out_channels, fan, eps):
+    call("sib_weight_standardize", _p(w_flat), c_void_p(0), _p(out_bf16), _p(mean_invstd), out_channels, fan,
+         float(eps), _stream())
+
+
+def weight_standardize_bwd(w_flat, mean_invstd, g_flat, out_channels, fan):
+    call("sib_weight_standardize_bwd", _p(w_flat), c_void_p(0), _p(mean_invstd), _p(g_flat), _p(g_flat),
+         out_channels, fan, _stream())
+
+
 # ------------------------------------------------------------------ heads
 def ce_fwd_bwd(logits, target, smoothing=0.0, temperature=1.0, margin_kind=MARGIN_NONE, s=1.0,
                m=0.0, want_grad=True, grad_scale=1.0):

@@ -1,0 +1,111 @@
+"""BResNet-50 (deep stem, anti-alias BlurPool / AvgPool shortcut, ECA, leaky ABN, weight
+standardisation) against its fp32 PyTorch restatement (oracle/bresnet_ref.py; the reference's own
+model class lives in the absent pytorch_tools => parity unpinned).  Drop rates are 0
+here so both sides are deterministic; the stochastic layers are checked separately."""
+import pytest
+import torch
+
+from oracle import bresnet_ref, torch_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float(a @ b / (a.norm() * b.norm() + 1e-30))
+
+
+def _pair(ws):
+    from sota_imagenet_b200 import models
+    kw = dict(antialias=True, attn_type="eca", norm_act="leaky_relu", drop_rate=0.0, drop_connect_rate=0.0)
+    ref = bresnet_ref.bresnet50(seed=0, weight_standardization=ws, **kw)
+    net = models.resnet50(stem_type="deep", norm_layer="inplaceabn", weight_standardization=ws, **kw)
+    missing, unexpected = net.load_state_dict(ref.state_dict(), strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return ref, net.cuda()
+
+
+def test_extra_operators_match_torch():
+    import torch.nn.functional as F
+    from sota_imagenet_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(4, 64, 14, 14, device="cuda").bfloat16()
+    xb = ops.to_nhwc_bf16(x)
+    xr = x.float().requires_grad_(True)
+    blur = bresnet_ref.BlurPool()
+    y_ref = blur(xr)
+    y = ops.blurpool_fwd(xb)
+    assert (y.float() - y_ref).abs().max() < 2e-2
+    dy = torch.randn_like(y_ref).bfloat16()
+    (dx_ref,) = torch.autograd.grad(y_ref, xr, dy.float())
+    assert (ops.blurpool_bwd(ops.to_nhwc_bf16(dy), tuple(x.shape)).float() - dx_ref).abs().max() < 2e-2
+    a_ref = F.avg_pool2d(xr, 2, 2)
+    assert (ops.avgpool2_fwd(xb).float() - a_ref).abs().max() < 2e-2
+    da = torch.randn_like(a_ref).bfloat16()
+    (dxa,) = torch.autograd.grad(a_ref, xr, da.float())
+    assert (ops.avgpool2_bwd(ops.to_nhwc_bf16(da), tuple(x.shape)).float() - dxa).abs().max() < 2e-2
+    m_ref = F.max_pool2d(xr, 3, 1, 1)
+    m, idx = ops.maxpool3x3s1_fwd(xb)
+    assert torch.equal(m.float(), m_ref.detach())
+    dm = torch.randn_like(m_ref).bfloat16()
+    (dxm,) = torch.autograd.grad(m_ref, xr, dm.float())
+    assert (ops.maxpool3x3s1_bwd(ops.to_nhwc_bf16(dm), idx).float() - dxm).abs().max() < 3e-2
+    # ECA module fwd + bwd
+    from sota_imagenet_b200 import bresnet
+    eca_ref = bresnet_ref.ECA().cuda()
+    eca = bresnet.ECA()
+    eca.load_state_dict(eca_ref.state_dict())
+    eca = eca.cuda()
+    xe = xb.clone().requires_grad_(True)
+    xer = x.float().requires_grad_(True)
+    o_ref = eca_ref(xer)
+    o = eca(xe)
+    assert (o.float() - o_ref).abs().max() < 3e-2
+    g = torch.randn_like(o_ref).bfloat16()
+    o_ref.backward(g.float())
+    o.backward(ops.to_nhwc_bf16(g))
+    assert _cos(xe.grad, xer.grad) > 0.999 and _cos(eca.weight.grad, eca_ref.weight.grad) > 0.999
+
+
+@pytest.mark.parametrize("ws", [False, True])
+def test_bresnet50_step_matches_restatement(ws):
+    from sota_imagenet_b200 import losses
+    ref, net = _pair(ws)
+    x, y = torch_ref.synthetic_batch(8, 128, seed=0)
+    ref.train()
+    loss_ref = torch_ref.smooth_cross_entropy(ref(x), y, 0.1)
+    loss_ref.backward()
+    net.train()
+    loss = losses.CrossEntropyLoss(smoothing=0.1)(net(x.cuda()), y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()) <= 1e-2, (loss.item(), loss_ref.item())
+    rp = dict(ref.named_parameters())
+    cos = {n: _cos(p.grad.reshape(rp[n].shape), rp[n].grad) for n, p in net.named_parameters()}
+    print("BResNet ws=%s loss %.4f/%.4f; fc cos %.4f; worst %s" % (ws, loss.item(), loss_ref.item(), cos["fc.weight"],
+                                                                 min(cos.items(), key=lambda kv: kv[1])))
+    assert cos["fc.weight"] >= 0.98 and cos["fc.bias"] >= 0.98
+    late = [v for n, v in cos.items() if n.startswith("layer4.2.")]
+    assert min(late) >= 0.9, sorted((v, n) for n, v in cos.items() if n.startswith("layer4.2."))[:4]
+    # first-layer BN statistics are not yet touched by bf16 chaos
+    rb = dict(ref.named_buffers())
+    for n, b in net.named_buffers():
+        if n.startswith("conv1.1.running"):
+            assert (b.cpu() - rb[n]).norm() / (rb[n].norm() + 1e-12) < 2e-2, n
+
+
+def test_stochastic_layers_and_eval():
+    from sota_imagenet_b200 import models
+    net = models.resnet50(stem_type="deep", antialias=True, attn_type="eca", norm_layer="inplaceabn",
+                          norm_act="leaky_relu", drop_rate=0.2, drop_connect_rate=0.2).cuda()
+    keeps = [b.keep_prob for b in net.blocks()]
+    assert keeps[0] == 1.0 and abs(keeps[-1] - (1 - 0.2 * 15 / 16)) < 1e-9 and keeps == sorted(keeps, reverse=True)
+    x = torch.randn(4, 3, 64, 64, device="cuda")
+    net.train()
+    out = net(x)
+    out.float().sum().backward()
+    assert torch.isfinite(out.float()).all() and all(torch.isfinite(p.grad).all() for p in net.parameters())
+    net.eval()
+    with torch.no_grad():
+        a, b = net(x), net(x)
+    assert torch.equal(a, b)              # no randomness in eval mode
