@@ -36,6 +36,7 @@ extern "C" {
 /* conv flags */
 #define SIB_FLAG_FORCE_IM2COL 1 /* use the im2col TMA path even for plain 1x1 (testing) */
 #define SIB_FLAG_TILE_N128 2    /* cap the N tile at 128 columns (tuning / testing)       */
+#define SIB_FLAG_NO_2CTA 4      /* never use the cta_group::2 kernel (tuning / testing)   */
 
 const char* sib_last_error(void);
 int sib_abi_version(void);

@@ -334,6 +334,317 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+// 2-CTA variant of the persistent implicit GEMM (cta_group::2): a cluster of two CTAs owns a
+// 256 x 256 output tile.  Each CTA loads its own 128 activation rows and HALF of the weight tile
+// (128 of the 256 output channels); the leader CTA (cluster rank 0) issues tcgen05.mma with
+// M = 256, which reads both CTAs' shared memory and writes 128 accumulator rows into each CTA's
+// TMEM.  Per-SM operand traffic per FLOP drops by 1/3 against the 1-CTA 128 x 256 tile.
+// TMA loads of both CTAs complete on the leader's `full` barriers; tcgen05.commit multicasts to
+// both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator on the
+// leader's `tmem_empty` barrier.  Everything else is the 1-CTA kernel:
+// Persistent, warp-specialised implicit GEMM.
+//   grid  = min(#tiles, #SMs) CTAs, each walking tiles t = blockIdx.x, +gridDim.x, ...
+//           (n-tile fastest so concurrently running CTAs share the A tile through L2)
+//   warp0 : TMA producer            smem ring of STAGES x (A 128x64 + B BNx64), 128B swizzle
+//   warp1 : tcgen05.mma issuer      2 TMEM accumulator stages of BN fp32 columns
+//   warp2 : TMEM alloc / dealloc
+//   warp4-11: epilogue (8 warps; warp e reads TMEM lane quarter e%4 and the 64-column chunks
+//           with chunk%2 == e/4; BN=64 uses the first four):
+//           TMEM -> regs -> (+bias, +residual) -> bf16 -> swizzled smem slab -> TMA store,
+//           plus per-channel sum / sum-of-squares of the stored values for the following BN.
+// The epilogue of tile i overlaps the main loop of tile i+1.
+template <int STAGES, int SLABS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1)
+igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+             const IgemmParams p) {
+  constexpr int BN = 256;
+  constexpr int kBBytes = (BN / 2) * kBK * 2;      // this CTA's half of the weight tile
+  constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
+  constexpr int kChunks = BN / 64;
+  constexpr int kHalves = kChunks >= 2 ? 2 : 1;    // epilogue warp groups splitting the columns
+  constexpr int kEpiWarps = 4 * kHalves;
+  constexpr int kChunksPerWarp = kChunks / kHalves;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar[2];
+  __shared__ uint64_t tmem_empty_bar[2];
+  __shared__ uint64_t res_bar[8];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_part[kEpiWarps][2][kChunksPerWarp * 64];   // per-warp column sums of a tile
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * kABytes;
+  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [8 warps][SLABS][kSlabBytes]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_tiles = (p.num_m_tiles >> 1) * p.num_n_tiles;     // 256-row pair tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);   // epilogue warps of BOTH CTAs (leader's copy is used)
+    }
+    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(&tmem_base_smem, kTmemCols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer ----
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / p.num_n_tiles) * 2 * kBM + (int)cta_rank * kBM;
+        const int n0 = (tile % p.num_n_tiles) * BN + (int)cta_rank * (BN / 2);   // this CTA's weight half
+        int n_img = 0, w_base = 0, h_base = 0;
+        if (!p.tiled_a) {
+          n_img = m0 / p.trav_hw;
+          const int rem = m0 - n_img * p.trav_hw;
+          const int pp = rem / p.trav_w;
+          const int qq = rem - pp * p.trav_w;
+          w_base = qq * p.stride - p.pad_w;
+          h_base = pp * p.stride - p.pad_h;
+        }
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of both
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));
+          if (p.tiled_a) {
+            tma2_load_2d(smem_a + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m0);
+          } else {
+            const int r = tap / p.S;
+            const int s = tap - r * p.S;
+            tma2_load_im2col_4d(smem_a + stage * kABytes, &tmA, &full_bar[stage], cb * kBK,
+                                w_base, h_base, n_img, (uint16_t)s, (uint16_t)r);
+          }
+          tma2_load_2d(smem_b + stage * kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
+          if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ---- MMA issuer (leader CTA only) ----
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc =
+              umma_smem_desc(smem_u32(smem_a + stage * kABytes), 16, 1024, kSwizzle128B);
+          const uint64_t b_desc =
+              umma_smem_desc(smem_u32(smem_b + stage * kBBytes), 16, 1024, kSwizzle128B);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // +32 bytes along K inside the 128B swizzle row = +2 in 16-byte address units
+            umma2_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma2_commit_multicast(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_multicast(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+    // ---- epilogue ----
+    const int e = warp - 4;
+    const int quarter = e & 3;                // TMEM lane quarter (== warp % 4)
+    const int half = e >> 2;                  // which interleaved set of 64-column chunks
+    uint8_t* slabs = smem_slab + e * SLABS * kSlabBytes;
+    const int et = threadIdx.x - 128;         // 0 .. 32*kEpiWarps-1
+    // swizzled 16-byte slots of this lane's row inside a slab (row = lane)
+    uint32_t row_slot[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) row_slot[g] = lane * 128 + ((g ^ (lane & 7)) << 4);
+    // stats pass: lane reads 16 bytes (8 columns, slot lane%8) of rows it*4 + lane/8; the row's
+    // swizzle phase (row & 7) alternates between st_row and st_row + 4 with the parity of `it`
+    const int st_row = lane >> 3, st_slot = lane & 7;
+    const uint32_t st_off0 = st_row * 128 + ((st_slot ^ st_row) << 4);
+    const uint32_t st_off1 = st_row * 128 + ((st_slot ^ (st_row + 4)) << 4);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
+    int slab_idx = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / p.num_n_tiles) * 2 * kBM + (int)cta_rank * kBM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      const int row0 = m0 + quarter * 32;
+      const int rows_valid = p.M_total - row0;   // rows of this 32-row slab that exist
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      bool released = false;
+#pragma unroll
+      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+        const int chunk = half + ci * kHalves;
+        const int col0 = n0 + chunk * 64;
+        const bool live = col0 < p.Cout;           // ragged N (warp-uniform)
+        float2 cs1[4], cs2[4];     // packed fp32x2 accumulators (add.f32x2 / fma.f32x2 on sm_100)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { cs1[j] = make_float2(0.f, 0.f); cs2[j] = make_float2(0.f, 0.f); }
+        if (live) {
+          uint8_t* slab = slabs + slab_idx * kSlabBytes;
+          // the TMA store that last read this slab must have finished reading it
+          if (lane == 0) tma_store_wait_read<SLABS - 1>();
+          __syncwarp();
+          if (p.has_residual && lane == 0) {
+            mbar_arrive_expect_tx(&res_bar[e], kSlabBytes);
+            tma_load_2d(slab, &tmRes, &res_bar[e], col0, row0);
+          }
+          uint32_t r[64];
+          const uint32_t taddr =
+              tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 64;
+          tmem_ld_32x32b_x32(taddr, r);
+          tmem_ld_32x32b_x32(taddr + 32, r + 32);
+          tmem_ld_wait();
+          if (ci == kChunksPerWarp - 1 || col0 + 64 * kHalves >= p.Cout) {
+            // accumulator fully read by this warp: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            released = true;
+          }
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
+          }
+          if (p.has_residual) {
+            mbar_wait(&res_bar[e], res_phase);
+            res_phase ^= 1;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint4 q = *reinterpret_cast<const uint4*>(slab + row_slot[g]);
+              float prev[8];
+              unpack8(q, prev);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
+            }
+          }
+          // bf16 pack into the 128B-swizzled slab
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(slab + row_slot[g]) = pack8(&v[g * 8]);
+          if (p.stats != nullptr) {
+            __syncwarp();
+            // column sums of the bf16 values as stored: 8 x LDS.128 cover the 32 x 64 slab
+            const bool full = rows_valid >= 32;          // warp-uniform
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              uint4 q = *reinterpret_cast<const uint4*>(slab + it * 512 + ((it & 1) ? st_off1 : st_off0));
+              if (!full && it * 4 + st_row >= rows_valid) q = make_uint4(0, 0, 0, 0);
+              const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(hq[j]);
+                cs1[j] = __fadd2_rn(cs1[j], f);
+                cs2[j] = __ffma2_rn(f, f, cs2[j]);
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, slab, col0, row0);
+            tma_store_commit();
+          }
+          if (SLABS > 1) slab_idx ^= 1;
+        }
+        if (p.stats != nullptr) {
+          // lanes with equal lane%8 hold partial sums of the same 8 columns (different rows)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              float2 t1, t2;
+              t1.x = __shfl_xor_sync(0xffffffffu, cs1[j].x, o);
+              t1.y = __shfl_xor_sync(0xffffffffu, cs1[j].y, o);
+              t2.x = __shfl_xor_sync(0xffffffffu, cs2[j].x, o);
+              t2.y = __shfl_xor_sync(0xffffffffu, cs2[j].y, o);
+              cs1[j] = __fadd2_rn(cs1[j], t1);
+              cs2[j] = __fadd2_rn(cs2[j], t2);
+            }
+          }
+          if (lane < 8) {
+            float4* d1 = reinterpret_cast<float4*>(&s_part[e][0][ci * 64 + lane * 8]);
+            float4* d2 = reinterpret_cast<float4*>(&s_part[e][1][ci * 64 + lane * 8]);
+            d1[0] = make_float4(cs1[0].x, cs1[0].y, cs1[1].x, cs1[1].y);
+            d1[1] = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
+            d2[0] = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
+            d2[1] = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
+          }
+        }
+      }
+      if (!released) {     // every chunk of this warp was past Cout: still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      }
+      if (p.stats != nullptr) {
+        // combine the four row-quarters of each column and publish; s_part is reused next tile
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+        for (int c = et; c < BN; c += 32 * kEpiWarps) {
+          if (n0 + c < p.Cout) {
+            const int chunk = c >> 6;
+            const int h = chunk % kHalves, ci = chunk / kHalves, lc = ci * 64 + (c & 63);
+            const float a = s_part[h * 4 + 0][0][lc] + s_part[h * 4 + 1][0][lc] +
+                            s_part[h * 4 + 2][0][lc] + s_part[h * 4 + 3][0][lc];
+            const float b = s_part[h * 4 + 0][1][lc] + s_part[h * 4 + 1][1][lc] +
+                            s_part[h * 4 + 2][1][lc] + s_part[h * 4 + 3][1][lc];
+            atomicAdd(p.stats + n0 + c, a);
+            atomicAdd(p.stats + p.Cout + n0 + c, b);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  cluster_sync_all();          // the leader's MMAs read the peer's smem: nobody leaves early
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
 // ----------------------------------------------------------------------------
 // wgrad
 // ----------------------------------------------------------------------------
@@ -515,6 +826,23 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   return 0;
 }
 
+template <int STAGES, int SLABS>
+static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                         const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + 128 * kBK * 2) + 8 * SLABS * kSlabBytes + 1024;
+  static bool configured = false;
+  if (!configured) {
+    SIB_CUDA(cudaFuncSetAttribute(igemm2_kernel<STAGES, SLABS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  int pairs = (p.num_m_tiles / 2) * p.num_n_tiles;
+  if (pairs > sm_count() / 2) pairs = sm_count() / 2;
+  igemm2_kernel<STAGES, SLABS><<<2 * pairs, kIgemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
 // Shared by fprop and dgrad.  `in` is [N][IH][IW][Cin] NHWC bf16, `w` is [Cout][R][S][Cin].
 // The traversal space (GEMM rows) is [N][TH][TW] and equals the output tensor's pixel space;
 // row (n,p,q) reads taps starting at (p*stride - pad_h, q*stride - pad_w).
@@ -565,8 +893,11 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
                                stride, kBK, kBM, true);
   }
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tmB, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, BN, kBK,
-                         true);
+  // 2-CTA pairs (M = 256 per cluster) for the tensor-bound shapes
+  const bool two_cta = BN == 256 && p.num_m_tiles % 2 == 0 && p.num_kblocks >= 4 &&
+                       !(flags & SIB_FLAG_NO_2CTA);
+  rc = make_tmap_2d_bf16(&tmB, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin,
+                         two_cta ? 128 : BN, kBK, true);
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tmOut, out, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
   if (rc) return rc;
@@ -574,6 +905,7 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
                          64, true);
   if (rc) return rc;
   if (stats != nullptr) SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, stream));
+  if (two_cta) return launch_igemm2<5, 1>(tmA, tmB, tmOut, tmRes, p, stream);
   if (BN == 64) return launch_igemm<64, 6, 2>(tmA, tmB, tmOut, tmRes, p, stream);
   if (BN == 128) return launch_igemm<128, 5, 1>(tmA, tmB, tmOut, tmRes, p, stream);
   return launch_igemm<256, 3, 2>(tmA, tmB, tmOut, tmRes, p, stream);

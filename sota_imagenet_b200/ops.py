@@ -17,6 +17,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE = 0, 1, 2, 3
 FLAG_FORCE_IM2COL = 1
 FLAG_TILE_N128 = 2
+FLAG_NO_2CTA = 4
 ACT_CODES = {None: ACT_NONE, "identity": ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU,
              "leaky_relu": ACT_LEAKY}
 
