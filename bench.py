@@ -146,6 +146,20 @@ def conv_flops(name, a):
     return 0.0
 
 
+def bn_bytes(name, a):
+    """Algorithmic HBM bytes of one BatchNorm-family launch (bf16 tensors, E = M*C elements)."""
+    nz = lambda v: 1 if v else 0
+    if name == "sib_bn_finalize_apply":      # x .. res(8) stats2(9) .. y(16) M(17) C(18)
+        return 2.0 * a[17] * a[18] * (2 + nz(a[8]))
+    if name == "sib_bn_apply":               # x ss res ss2 y M C
+        return 2.0 * a[5] * a[6] * (2 + nz(a[2]))
+    if name == "sib_bn_bwd_reduce":          # dy out mask_ss x mi x2 mi2 M C
+        return 2.0 * a[7] * a[8] * (2 + nz(a[1]) + nz(a[5]))
+    if name == "sib_bn_bwd_apply":           # dy out . x . . . x2 . . dx dx2 gout ... M(17) C(18)
+        return 2.0 * a[17] * a[18] * (3 + nz(a[1]) + nz(a[7]) + nz(a[11]) + nz(a[12]))
+    return 0.0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -282,6 +296,7 @@ def run_ours(args):
 
     # ---- live per-kernel timing of the conv family (roofline of the dominant kernel) --------
     roofline = None
+    roofline_bn = None
     cpu_baseline = None
     # (every rank runs the profiled step: with N > 1 it contains collectives)
     _lib.PROFILE = []
@@ -301,6 +316,13 @@ def run_ours(args):
         conv_fl = sum(groups[n][1] for n in conv_names)
         total_ms = sum(v[0] for v in groups.values())
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        bn_names = [n for n in groups if n.startswith("sib_bn_") and bn_bytes(n, prof[0][1]) is not None]
+        bn_b = sum(bn_bytes(n, a) for n, a, _, _ in prof)
+        bn_ms = sum(s0.elapsed_time(s1) for n, a, s0, s1 in prof if bn_bytes(n, a) > 0)
+        roofline_bn = {"bound": "hbm", "kernel": "bn_finalize_apply / bn_bwd_reduce / bn_bwd_apply",
+                       "achieved": bn_b / (bn_ms * 1e-3) / 1e9 if bn_ms else 0.0, "peak": pk["hbm_gbs"],
+                       "unit": "GB/s", "frac": (bn_b / (bn_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if bn_ms else 0.0,
+                       "traffic": None, "bytes_per_step": bn_b, "ms_per_step_eager_events": bn_ms}
         roofline = {
             "bound": "tensor", "kernel": "igemm_kernel / wgrad_kernel (tcgen05 implicit-GEMM conv)",
             "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
@@ -332,7 +354,8 @@ def run_ours(args):
                     "steps": e2e_steps,
                     "path": "pinned host uint8 [256,256,256,3] -> H2D -> GpuAugment -> model -> CE -> backward -> SGD -> loss D2H"},
             "gpu_launches": int(calls_per_step * args.steps),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "roofline": roofline, "roofline_bn": roofline_bn,
+            "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

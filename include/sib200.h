@@ -80,6 +80,15 @@ int sib_bn_eval_scale(const float* gamma, const float* beta, const float* runnin
 int sib_bn_apply(const void* x, const float* scale_shift, const void* res,
                  const float* scale_shift2, void* y, long M, int C, int act, float slope,
                  void* stream);
+/* finalize + apply fused (training): y = act(BN1(x) [+ res | + BN2(res)]); publishes
+ * mean_invstd / scale_shift [2][C] for the backward pass and updates the running statistics */
+int sib_bn_finalize_apply(const void* x, const float* stats, const float* gamma, const float* beta,
+                          float* running_mean, float* running_var, float* mean_invstd,
+                          float* scale_shift, const void* res, const float* stats2,
+                          const float* gamma2, const float* beta2, float* running_mean2,
+                          float* running_var2, float* mean_invstd2, float* scale_shift2, void* y,
+                          long M, int C, double count, float eps, float momentum, int act,
+                          float slope, void* stream);
 /* sums[0..1][C] = (sum g, sum g*xhat), g = dy * act'(.); with x2: sums[2..3] for the 2nd BN.
  * The activation mask is taken from `out` (stored forward output) when given, otherwise it is
  * recomputed bit-exactly from x and the forward's scale/shift (`mask_ss`, [2][C]). */

@@ -155,39 +155,47 @@ __global__ void one_hot_kernel(const long* __restrict__ labels, float* __restric
 // with KW*2*3 real channels padded to 64, i.e. an (NA x 1), stride-1 convolution with 64 input
 // channels that the swizzled implicit-GEMM kernel handles directly.
 // src_mode 0: NHWC bf16 4-channel, 1: NCHW fp32.
+template <int KW>
 __global__ void __launch_bounds__(256)
 stem_pack_kernel(const void* __restrict__ src, __nv_bfloat16* __restrict__ xq, int N, int H,
-                 int W, int KW, int pw, int src_mode) {
+                 int W, int pw, int src_mode) {
+  // one thread per packed pixel (n, j, q): gathers 2 rows x KW source pixels (each read once as
+  // an 8-byte NHWC4 load, or 3 fp32 loads for NCHW input) and writes 64 channels = 8 x 16 bytes
   const int H2 = H >> 1, W2 = W >> 1;
-  const long total = (long)N * H2 * W2 * 8;   // 8 x (8 channels = 16 bytes) per packed pixel
+  const long total = (long)N * H2 * W2;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i & 7);
-    long t = i >> 3;
-    const int q = (int)(t % W2); t /= W2;
-    const int j = (int)(t % H2);
-    const int n = (int)(t / H2);
-    float f[8];
+    const int q = (int)(i % W2);
+    const int j = (int)((i / W2) % H2);
+    const int n = (int)(i / ((long)W2 * H2));
+    __nv_bfloat16 vals[64];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int chn = v * 8 + e;
-      float val = 0.f;
-      if (chn < 2 * KW * 3) {
-        const int b = chn / (KW * 3);
-        const int rem = chn - b * KW * 3;
-        const int s = rem / 3, c = rem - s * 3;
-        const int y = 2 * j + b, x = 2 * q + s - pw;
-        if (x >= 0 && x < W) {
-          if (src_mode == 0)
-            val = __bfloat162float(
-                static_cast<const __nv_bfloat16*>(src)[(((long)n * H + y) * W + x) * 4 + c]);
-          else
-            val = static_cast<const float*>(src)[(((long)n * 3 + c) * H + y) * W + x];
+    for (int e = 0; e < 64; ++e) vals[e] = __float2bfloat16_rn(0.f);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int y = 2 * j + b;
+#pragma unroll
+      for (int s = 0; s < KW; ++s) {
+        const int x = 2 * q + s - pw;
+        if (x < 0 || x >= W) continue;
+        __nv_bfloat16* dst = vals + (b * KW + s) * 3;
+        if (src_mode == 0) {
+          const uint2 px = __ldg(reinterpret_cast<const uint2*>(
+              static_cast<const __nv_bfloat16*>(src) + (((long)n * H + y) * W + x) * 4));
+          const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&px);
+          dst[0] = h[0]; dst[1] = h[1]; dst[2] = h[2];
+        } else {
+          const float* f = static_cast<const float*>(src);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            dst[c] = __float2bfloat16_rn(__ldg(f + (((long)n * 3 + c) * H + y) * W + x));
         }
       }
-      f[e] = val;
     }
-    stg_stream(xq + i * 8, pack8(f));
+    uint4* out = reinterpret_cast<uint4*>(xq + i * 64);
+    const uint4* v4 = reinterpret_cast<const uint4*>(vals);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) stg_stream(out + k, v4[k]);
   }
 }
 
@@ -274,9 +282,15 @@ extern "C" int sib_stem_pack(const void* src, void* xq, int N, int H, int W, int
                              int src_mode, void* stream) {
   SIB_CHECK(H % 2 == 0 && W % 2 == 0, "stem_pack: image extent must be even (got %dx%d)", H, W);
   SIB_CHECK(2 * KW * 3 <= 64, "stem_pack: filter width %d too large", KW);
-  const long total = (long)N * (H / 2) * (W / 2) * 8;
-  stem_pack_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(xq), N, H, W, KW, pad_w, src_mode);
+  const long total = (long)N * (H / 2) * (W / 2);
+  if (KW == 7)
+    stem_pack_kernel<7><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+        src, static_cast<__nv_bfloat16*>(xq), N, H, W, pad_w, src_mode);
+  else if (KW == 3)
+    stem_pack_kernel<3><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+        src, static_cast<__nv_bfloat16*>(xq), N, H, W, pad_w, src_mode);
+  else
+    return fail(1, "stem_pack: filter width %d not instantiated (3 or 7)", KW);
   SIB_LAUNCH_CHECK();
   return 0;
 }

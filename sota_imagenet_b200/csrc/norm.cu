@@ -192,6 +192,101 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ s
 }
 
 // ---------------------------------------------------------------------------
+// finalize + apply in one launch: every thread derives scale/shift of its 8 channels from the
+// raw statistics; the first row-lane of block 0 also publishes mean/invstd, scale/shift (needed
+// by the backward pass) and updates the running statistics.  Saves one tiny launch per BN.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void bn_derive(const float* __restrict__ stats,
+                                          const float* __restrict__ gamma,
+                                          const float* __restrict__ beta,
+                                          float* __restrict__ running_mean,
+                                          float* __restrict__ running_var,
+                                          float* __restrict__ mean_invstd,
+                                          float* __restrict__ scale_shift, int C, int c0,
+                                          float count, float eps, float momentum, bool publish,
+                                          float* sc, float* sh) {
+  float s1[8], s2[8], g[8], b[8];
+  load8f(stats + c0, s1);
+  load8f(stats + C + c0, s2);
+  if (gamma) load8f(gamma + c0, g);
+  if (beta) load8f(beta + c0, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float mean = s1[j] / count;
+    const float var = fmaxf(s2[j] / count - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    const float gm = gamma ? g[j] : 1.f, bt = beta ? b[j] : 0.f;
+    sc[j] = gm * invstd;
+    sh[j] = bt - mean * gm * invstd;
+    if (publish) {
+      const int c = c0 + j;
+      mean_invstd[c] = mean;
+      mean_invstd[C + c] = invstd;
+      scale_shift[c] = sc[j];
+      scale_shift[C + c] = sh[j];
+      if (running_mean) {
+        const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+}
+
+struct BnFinalizeArgs {
+  const float* stats; const float* gamma; const float* beta;
+  float* running_mean; float* running_var; float* mean_invstd; float* scale_shift;
+};
+
+template <int MODE>   // 0: plain, 1: + res, 2: + BN2(res)
+__global__ void __launch_bounds__(kRedThreads)
+bn_finalize_apply_kernel(const __nv_bfloat16* __restrict__ x, BnFinalizeArgs f1,
+                         const __nv_bfloat16* __restrict__ res, BnFinalizeArgs f2,
+                         __nv_bfloat16* __restrict__ y, long M, int C, float count, float eps,
+                         float momentum, int act, float slope) {
+  const ColOwner co(C);
+  if (!co.active) return;
+  const bool publish = blockIdx.x == 0 && co.ty == 0;
+  float sc[8], sh[8], sc2[8], sh2[8];
+  bn_derive(f1.stats, f1.gamma, f1.beta, f1.running_mean, f1.running_var, f1.mean_invstd,
+            f1.scale_shift, C, co.tx * 8, count, eps, momentum, publish, sc, sh);
+  if (MODE == 2)
+    bn_derive(f2.stats, f2.gamma, f2.beta, f2.running_mean, f2.running_var, f2.mean_invstd,
+              f2.scale_shift, C, co.tx * 8, count, eps, momentum, publish, sc2, sh2);
+  const long col = co.tx * 8;
+  for (long r = co.row0; r < M; r += kU * co.stride) {
+    uint4 vx[kU], vr[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long rr = r + u * co.stride;
+      if (rr < M) {
+        vx[u] = ldg_stream(x + rr * C + col);
+        if (MODE != 0) vr[u] = ldg_stream(res + rr * C + col);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long rr = r + u * co.stride;
+      if (rr < M) {
+        float f[8], o[8];
+        unpack8(vx[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], sc[j], sh[j]);
+        if (MODE != 0) {
+          float q[8];
+          unpack8(vr[u], q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += (MODE == 2) ? fmaf(q[j], sc2[j], sh2[j]) : q[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = act_fwd(o[j], act, slope);
+        stg_stream(y + rr * C + col, pack8(o));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // backward.  g = dy * act'(.) where the activation mask comes either from the stored output
 // (`out`, needed when a residual was added) or is recomputed from x with the forward's own
 // scale/shift (`mask_ss`): fmaf(x, scale, shift) > 0 is bit-identical to what the forward
@@ -640,6 +735,36 @@ extern "C" int sib_bn_apply(const void* x, const float* scale_shift, const void*
   else
     bn_apply_kernel<2><<<grid, kRedThreads, 0, ST(stream)>>>(xp, scale_shift, rp, scale_shift2, yp,
                                                             M, C, act, slope);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// y = act(BN1(x) [+ res | + BN2(res)]) with both finalizations fused (training mode).
+extern "C" int sib_bn_finalize_apply(const void* x, const float* stats, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var,
+                                     float* mean_invstd, float* scale_shift, const void* res,
+                                     const float* stats2, const float* gamma2, const float* beta2,
+                                     float* running_mean2, float* running_var2,
+                                     float* mean_invstd2, float* scale_shift2, void* y, long M,
+                                     int C, double count, float eps, float momentum, int act,
+                                     float slope, void* stream) {
+  if (int rc = check_c(C)) return rc;
+  const BnFinalizeArgs f1{stats, gamma, beta, running_mean, running_var, mean_invstd, scale_shift};
+  const BnFinalizeArgs f2{stats2, gamma2, beta2, running_mean2, running_var2, mean_invstd2,
+                          scale_shift2};
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(res);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+  const int grid = bn_grid(M, C);
+  if (res == nullptr)
+    bn_finalize_apply_kernel<0><<<grid, kRedThreads, 0, ST(stream)>>>(
+        xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope);
+  else if (stats2 == nullptr)
+    bn_finalize_apply_kernel<1><<<grid, kRedThreads, 0, ST(stream)>>>(
+        xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope);
+  else
+    bn_finalize_apply_kernel<2><<<grid, kRedThreads, 0, ST(stream)>>>(
+        xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope);
   SIB_LAUNCH_CHECK();
   return 0;
 }

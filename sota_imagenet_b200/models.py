@@ -51,8 +51,7 @@ class ResNet(SibModule):
         stats = torch.empty((2, 64), dtype=torch.float32, device=x.device) if train else None
         c0, xq = self.conv1.run(x, stats)
         n, _, h, w = c0.shape
-        mi0, ss0, cnt0 = self.bn1.finalize(stats, n * h * w, train)
-        a0 = ops.bn_apply(c0, ss0, self.bn1.act, self.bn1.slope)
+        a0, mi0, ss0, cnt0, _ = Bottleneck._bn_act(self.bn1, c0, stats, train)
         p0, pool_saved = self.maxpool.fwd(a0, train)
         y = p0
         for blk in self.blocks():

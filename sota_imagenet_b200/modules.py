@@ -252,6 +252,15 @@ class BatchNorm2d(SibModule):
         self.num_batches_tracked += 1
         return mi, ss, count
 
+    def stats_args(self, stats):
+        """(stats, gamma, beta, running_mean, running_var) for the fused finalize+apply kernel;
+        all-reduces the statistics first under SyncBN.  Returns (args, world)."""
+        world = self._world()
+        if world > 1:
+            torch.distributed.all_reduce(stats, group=self.process_group)
+        self.num_batches_tracked += 1
+        return (stats, self.weight.data, self.bias.data, self.running_mean, self.running_var), world
+
     def reduce_sums(self, sums):
         if self._world() > 1:
             torch.distributed.all_reduce(sums, group=self.process_group)
@@ -376,26 +385,40 @@ class Bottleneck(SibModule):
             self.downsample = None
 
     @staticmethod
-    def _conv_bn(conv, bn, x, train, **apply_kw):
-        dev = x.device
-        stats = torch.empty((2, conv.out_channels), dtype=torch.float32, device=dev) if train else None
-        c = conv.run(x, stats)
+    def _conv(conv, x, train):
+        stats = torch.empty((2, conv.out_channels), dtype=torch.float32, device=x.device) if train else None
+        return conv.run(x, stats), stats
+
+    @staticmethod
+    def _bn_act(bn, c, stats, train, res=None, bn2=None, stats2=None):
+        """act(bn(c) [+ res | + bn2(res)]) -> y, mi, ss, count[, mi2]."""
         n, _, h, w = c.shape
-        mi, ss, count = bn.finalize(stats, n * h * w, train)
-        return c, mi, ss, count
+        count = n * h * w
+        if not train:
+            ss = ops.bn_eval_scale(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps)
+            ss2 = None
+            if bn2 is not None:
+                ss2 = ops.bn_eval_scale(bn2.weight.data, bn2.bias.data, bn2.running_mean, bn2.running_var, bn2.eps)
+            return ops.bn_apply(c, ss, bn.act, bn.slope, res=res, scale_shift2=ss2), None, ss, count, None
+        a1, world = bn.stats_args(stats)
+        a2 = bn2.stats_args(stats2)[0] if bn2 is not None else None
+        y, (mi, ss), (mi2, _) = ops.bn_finalize_apply(c, a1, res=res, bn2=a2, act=bn.act, slope=bn.slope,
+                                                      count=count * world, eps=bn.eps, momentum=bn.momentum)
+        return y, mi, ss, count * world, mi2
 
     def fwd(self, x, train):
-        c1, mi1, ss1, cnt1 = self._conv_bn(self.conv1, self.bn1, x, train)
-        a1 = ops.bn_apply(c1, ss1, self.bn1.act, self.bn1.slope)
-        c2, mi2, ss2, cnt2 = self._conv_bn(self.conv2, self.bn2, a1, train)
-        a2 = ops.bn_apply(c2, ss2, self.bn2.act, self.bn2.slope)
-        c3, mi3, ss3, cnt3 = self._conv_bn(self.conv3, self.bn3, a2, train)
+        c1, st1 = self._conv(self.conv1, x, train)
+        a1, mi1, ss1, cnt1, _ = self._bn_act(self.bn1, c1, st1, train)
+        c2, st2 = self._conv(self.conv2, a1, train)
+        a2, mi2, ss2, cnt2, _ = self._bn_act(self.bn2, c2, st2, train)
+        c3, st3 = self._conv(self.conv3, a2, train)
         if self.downsample is not None:
-            cd, mid, ssd, _ = self._conv_bn(self.downsample[0], self.downsample[1], x, train)
-            out = ops.bn_apply(c3, ss3, self.bn3.act, self.bn3.slope, res=cd, scale_shift2=ssd)
+            cd, std = self._conv(self.downsample[0], x, train)
+            out, mi3, _, cnt3, mid = self._bn_act(self.bn3, c3, st3, train, res=cd, bn2=self.downsample[1],
+                                                  stats2=std)
         else:
             cd = mid = None
-            out = ops.bn_apply(c3, ss3, self.bn3.act, self.bn3.slope, res=x)
+            out, mi3, _, cnt3, _ = self._bn_act(self.bn3, c3, st3, train, res=x)
         if not train:
             return out, None
         return out, (x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3, ss1, ss2)

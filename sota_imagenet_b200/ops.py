@@ -149,6 +149,24 @@ def bn_finalize(stats, gamma, beta, running_mean, running_var, count, eps, momen
     return mean_invstd, scale_shift
 
 
+def bn_finalize_apply(x, bn1, res=None, bn2=None, act=ACT_NONE, slope=0.01, count=None, eps=1e-5,
+                      momentum=0.1):
+    """bn1 / bn2 = (stats, gamma, beta, running_mean, running_var).  Returns y, (mi, ss)[, (mi2, ss2)]."""
+    _check_act(x)
+    n, c, h, w = x.shape
+    y = new_act(n, c, h, w, x.device)
+    mk = lambda: (torch.empty((2, c), dtype=torch.float32, device=x.device),
+                  torch.empty((2, c), dtype=torch.float32, device=x.device))
+    mi, ss = mk()
+    mi2, ss2 = mk() if bn2 is not None else (None, None)
+    b2 = bn2 if bn2 is not None else (None,) * 5
+    call("sib_bn_finalize_apply", _p(x), _p(bn1[0]), _p(bn1[1]), _p(bn1[2]), _p(bn1[3]), _p(bn1[4]),
+         _p(mi), _p(ss), _p(res), _p(b2[0]), _p(b2[1]), _p(b2[2]), _p(b2[3]), _p(b2[4]), _p(mi2),
+         _p(ss2), _p(y), n * h * w, c, float(count if count is not None else n * h * w), float(eps),
+         float(momentum), act, float(slope), _stream())
+    return y, (mi, ss), (mi2, ss2)
+
+
 def bn_eval_scale(gamma, beta, running_mean, running_var, eps):
     c = running_mean.shape[0]
     scale_shift = torch.empty((2, c), dtype=torch.float32, device=running_mean.device)
