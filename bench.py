@@ -316,7 +316,6 @@ def run_ours(args):
         conv_fl = sum(groups[n][1] for n in conv_names)
         total_ms = sum(v[0] for v in groups.values())
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        bn_names = [n for n in groups if n.startswith("sib_bn_") and bn_bytes(n, prof[0][1]) is not None]
         bn_b = sum(bn_bytes(n, a) for n, a, _, _ in prof)
         bn_ms = sum(s0.elapsed_time(s1) for n, a, s0, s1 in prof if bn_bytes(n, a) > 0)
         roofline_bn = {"bound": "hbm", "kernel": "bn_finalize_apply / bn_bwd_reduce / bn_bwd_apply",
