@@ -26,12 +26,12 @@ def test_cmodel_of_fused_modules_trains():
         dict(module="GlobalAvgPool"),
         dict(module="Linear", args=[256, 16]),
     ]).cuda()
-    opt = optimizers.SGD(net.parameters(), lr=0.05, momentum=0.9)
+    opt = optimizers.SGD(net.parameters(), lr=0.005, momentum=0.9)
     crit = losses.CrossEntropyLoss(smoothing=0.1)
     x = torch.randn(8, 3, 64, 64, device="cuda")
     y = torch.randint(0, 16, (8,), device="cuda")
     first = None
-    for _ in range(12):
+    for _ in range(30):
         opt.zero_grad()
         loss = crit(net(x), y)
         loss.backward()
