@@ -9,6 +9,8 @@
 //
 // Replaces what the reference reaches through cuDNN: F.conv2d / autograd conv backward
 // inside pytorch_tools.models.resnet50 (reference train.py:64).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/sib200.h"
@@ -667,10 +669,14 @@ constexpr int kWgUnits = 4;  // 64-column units per CTA -> 128 x 256 output tile
 // dW tile [128 out channels][4 units x 64 columns]; a unit is one (filter tap, 64 input
 // channels) pair, i.e. 64 consecutive columns of the [Cout][R*S*Cin] matrix.  All units of a
 // CTA share the dY operand; each unit's X operand is its own im2col TMA load.
-template <int STAGES>
+// Epilogue (kTmaReduce): TMEM -> registers -> 128B-swizzled fp32 slabs (32 rows x 32 columns, carved
+// out of the drained operand ring) -> TMA add-reduction into dW, so the split-K accumulation is
+// done by the TMA unit / L2 instead of 8192 per-lane RED.v4 per tile.
+template <int STAGES, bool kTmaReduce>
 __global__ void __launch_bounds__(kThreads, 2)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
-             float* __restrict__ dw, const WgradParams p) {
+             const __grid_constant__ CUtensorMap tmDw, float* __restrict__ dw,
+             const WgradParams p) {
   constexpr int BNC = 64 * kWgUnits;
   constexpr int kUnitBytes = kWgPix * 128;     // 64 pixels x 64 channels bf16
   constexpr int kABytesW = 2 * kUnitBytes;     // dY tile: 64 pixels x 128 out channels
@@ -702,6 +708,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDy);
     tma_prefetch_desc(&tmX);
+    if (kTmaReduce) tma_prefetch_desc(&tmDw);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -778,22 +785,52 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
     const int k = k0 + row;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
-    float* drow = dw + (long)k * p.ldw + (long)u0 * 64;
     const int ncols = nunits * 64;
+    if (kTmaReduce) {
+      // all MMAs have completed (tmem_full), hence the operand ring is free: 4 slabs per warp
+      constexpr int kRedSlabs = 4;
+      static_assert(STAGES * (kABytesW + kBBytesW) >= 4 * kRedSlabs * kSlabBytes, "ring too small");
+      uint8_t* slabs = smem + (warp - 2) * kRedSlabs * kSlabBytes;
+      if (k0 + quarter * 32 < p.Cout) {       // warp-uniform: rows past Cout would be clipped anyway
 #pragma unroll 1
-    for (int chunk = 0; chunk < BNC / 32; ++chunk) {
-      if (chunk * 32 >= ncols) break;
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + chunk * 32, r);
-      tmem_ld_wait();
-      if (k < p.Cout) {
+        for (int chunk = 0; chunk < BNC / 32; ++chunk) {
+          if (chunk * 32 >= ncols) break;
+          uint8_t* slab = slabs + (chunk % kRedSlabs) * kSlabBytes;
+          if (lane == 0) tma_store_wait_read<kRedSlabs - 1>();
+          __syncwarp();
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + chunk * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float* d = drow + chunk * 32 + g * 4;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d),
-                       "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
-                       "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
-                       : "memory");
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                make_uint4(r[g * 4], r[g * 4 + 1], r[g * 4 + 2], r[g * 4 + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tmDw, slab, u0 * 64 + chunk * 32, k0 + quarter * 32);
+            tma_store_commit();
+          }
+        }
+        if (lane == 0) tma_store_wait<0>();
+      }
+    } else {
+      float* drow = dw + (long)k * p.ldw + (long)u0 * 64;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BNC / 32; ++chunk) {
+        if (chunk * 32 >= ncols) break;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + chunk * 32, r);
+        tmem_ld_wait();
+        if (k < p.Cout) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float* d = drow + chunk * 32 + g * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d),
+                         "f"(__uint_as_float(r[g * 4])), "f"(__uint_as_float(r[g * 4 + 1])),
+                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                         : "memory");
+          }
         }
       }
     }
@@ -911,17 +948,17 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   return launch_igemm<256, 3, 2>(tmA, tmB, tmOut, tmRes, p, stream);
 }
 
-template <int STAGES>
-static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, float* dw,
-                        const WgradParams& p, dim3 grid, cudaStream_t stream) {
+template <int STAGES, bool kTmaReduce>
+static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const CUtensorMap& tmDw,
+                        float* dw, const WgradParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (2 + kWgUnits) * kWgPix * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(wgrad_kernel<STAGES>,
+    SIB_CUDA(cudaFuncSetAttribute(wgrad_kernel<STAGES, kTmaReduce>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  wgrad_kernel<STAGES><<<grid, kThreads, smem, stream>>>(tmDy, tmX, dw, p);
+  wgrad_kernel<STAGES, kTmaReduce><<<grid, kThreads, smem, stream>>>(tmDy, tmX, tmDw, dw, p);
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -997,8 +1034,10 @@ extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N,
   p.total_units = R * S * p.cin_blocks;
   const int groups = (p.total_units + kWgUnits - 1) / kWgUnits;
   const int tiles = ((K + kBM - 1) / kBM) * groups;
-  // split the pixel reduction so that ~2 waves of (2 per SM) CTAs exist, >= 8 k-blocks each
-  int splits = (4 * sm_count() + tiles - 1) / tiles;
+  // split the pixel reduction so that the CTAs fill `waves` rounds of the 2-per-SM slots without
+  // spilling into a nearly empty extra round (floor, not ceil), >= 8 k-blocks each
+  static const int waves = [] { const char* e = getenv("SIB_WGRAD_WAVES"); return e ? atoi(e) : 1; }();
+  int splits = (waves * 2 * sm_count()) / tiles;
   int max_splits = (p.total_kblocks + 7) / 8;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -1014,5 +1053,11 @@ extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N,
                              kWgPix, true);
   if (rc) return rc;
   dim3 grid((K + kBM - 1) / kBM, groups, splits);
-  return launch_wgrad<2>(tmDy, tmX, dw, p, grid, st);   // 97 KB smem -> two CTAs per SM
+  static const bool lane_red = [] { const char* e = getenv("SIB_WGRAD_LANE_RED"); return e && atoi(e); }();
+  CUtensorMap tmDw;
+  rc = make_tmap_2d_f32(&tmDw, dw, K, p.ldw, p.ldw, 32, 32);
+  if (rc) return rc;
+  // 97 KB smem -> two CTAs per SM
+  if (lane_red) return launch_wgrad<2, false>(tmDy, tmX, tmDw, dw, p, grid, st);
+  return launch_wgrad<2, true>(tmDy, tmX, tmDw, dw, p, grid, st);
 }

@@ -85,6 +85,25 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   return 0;
 }
 
+int make_tmap_2d_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols) {
+  std::call_once(g_once, resolve);
+  SIB_CHECK(g_tiled != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  SIB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  SIB_CHECK((row_stride_elems * 4) % 16 == 0, "TMA row stride must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SIB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d f32) failed: %d rows=%llu cols=%llu",
+            (int)r, (unsigned long long)rows, (unsigned long long)cols);
+  return 0;
+}
+
 int make_tmap_kchunk_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
                           uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_kchunks) {
   std::call_once(g_once, resolve);

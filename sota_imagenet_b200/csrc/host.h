@@ -33,6 +33,11 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
                       uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols,
                       bool swizzle128);
 
+// 2-D row-major fp32 matrix, box = 32 rows x 32 columns (128 bytes), 128B swizzle; used for
+// TMA add-reductions of fp32 accumulator tiles
+int make_tmap_2d_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
+                     uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
+
 // 3-D view used for the no-swizzle K-major "core matrix" layout:
 // dims (inner=8 elems, rows, kchunks) with strides (1, row_stride, 8) elements.
 int make_tmap_kchunk_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
