@@ -136,7 +136,7 @@ def conv_flops(name, a):
     if name == "sib_conv2d_fprop":   # x w y N H W C K R S stride ph pw OH OW ...
         n, c, k, r, s, oh, ow = a[3], a[6], a[7], a[8], a[9], a[13], a[14]
         return 2.0 * n * oh * ow * k * c * r * s
-    if name == "sib_conv2d_dgrad":   # dy w dx residual workspace N H W C K R S stride pad
+    if name in ("sib_conv2d_dgrad", "sib_conv2d_dgrad_bnbwd"):   # dy w dx residual workspace N H W C K R S stride pad
         n, h, w, c, k, r, s, stride, pad = a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13]
         oh, ow = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
         return 2.0 * n * oh * ow * k * c * r * s

@@ -59,6 +59,18 @@ int sib_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W,
 int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx, const void* residual,
                      void* workspace, int N, int H, int W, int C, int K, int R, int S, int stride,
                      int pad, int flags, void* stream);
+/* dgrad with the BatchNorm-backward reduction of the BN this gradient flows into fused in the
+ * epilogue (replaces autograd's separate ReLU-backward + BN-backward reduction passes):
+ *   g  = (dgrad(dy) [+ residual]) * act'(z)   -> dx (bf16, already masked)
+ *   z  = fmaf(mask_src, scale, shift) with mask_ss = [2][C] (the forward's own arithmetic on the
+ *        BN input), or z = mask_src when mask_ss is NULL (mask_src = stored post-activation output)
+ *   sums[0][C] = sum g, sums[1][C] = sum g * xhat, xhat = (xhat_src - mean) * invstd
+ *   (xhat_src NULL -> mask_src).  Not available for strided 1x1 filters. */
+int sib_conv2d_dgrad_bnbwd(const void* dy, const void* w_dgrad, void* dx, const void* residual,
+                           void* workspace, int N, int H, int W, int C, int K, int R, int S,
+                           int stride, int pad, int flags, const void* mask_src,
+                           const float* mask_ss, const void* xhat_src, const float* mean_invstd,
+                           int act, float slope, float* sums, void* stream);
 int sib_scatter_add_strided(const void* src, void* dst, int N, int OH, int OW, int C, int H, int W,
                             int stride, void* stream);
 /* dw[K][R][S][C] (fp32) += wgrad(x, dy).  dw must be initialised (zero_grad). */

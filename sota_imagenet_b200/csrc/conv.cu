@@ -37,7 +37,258 @@ struct IgemmParams {
   int has_residual;  // out = acc + residual (same geometry as out)
   const float* bias; // optional [Cout]
   float* stats;      // optional [2][Cout]: sum, sum of squares of the stored bf16 values
+                     // (fused BN backward: sum g, sum g * xhat)
+  // ---- fused BatchNorm-backward reduction (dgrad epilogue; kernels with AUX >= 1) ----
+  //   g = acc [+ residual], masked by the activation derivative of the BN this gradient flows
+  //   into; the mask comes from tile `aux1`: fmaf(aux1, scale, shift) > 0 when mask_ss is given
+  //   (aux1 = that BN's input, the forward's own arithmetic), else aux1 > 0 (aux1 = the stored
+  //   block output).  xhat is built from aux1 (fuse == 1) or aux2 (fuse == 2).
+  int fuse;          // 0 off, 1 = one auxiliary tile, 2 = two
+  int fuse_act;      // SIB_ACT_* of the BN's activation
+  float fuse_slope;
+  const float* mask_ss;      // [2][Cout] scale, shift (or null)
+  const float* mean_invstd;  // [2][Cout]
 };
+
+// ---- epilogue (shared by the 1-CTA and 2-CTA kernels) ----
+//   warps 4-11 (8 warps; warp e reads TMEM lane quarter e%4 and the 64-column chunks with
+//   chunk%2 == e/4; BN=64 uses the first four):
+//   TMEM -> regs -> (+bias, +residual) -> bf16 -> 128B-swizzled smem slab -> TMA store, plus
+//   per-channel sum / sum-of-squares of the stored values for the following BatchNorm, or (fused
+//   BN backward) activation masking of the gradient and sum g / sum g*xhat.
+template <int BN, int SLABS, int AUX, bool kTwoCta>
+__device__ __forceinline__ void igemm_epilogue(
+    const CUtensorMap* tmOut, const CUtensorMap* tmRes, const CUtensorMap* tmAux1,
+    const CUtensorMap* tmAux2, const IgemmParams& p, uint8_t* smem_slab, uint8_t* smem_aux,
+    uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint64_t* res_bar, float* s_part,
+    uint32_t tmem_base, int first_tile, int tile_step, int num_tiles, int cta_rank) {
+  constexpr int kChunks = BN / 64;
+  constexpr int kHalves = kChunks >= 2 ? 2 : 1;
+  constexpr int kEpiWarps = 4 * kHalves;
+  constexpr int kChunksPerWarp = kChunks / kHalves;
+  constexpr int kPartStride = kChunksPerWarp * 64;       // s_part[e][2][kPartStride]
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int e = warp - 4;
+  const int quarter = e & 3;                // TMEM lane quarter (== warp % 4)
+  const int half = e >> 2;                  // which interleaved set of 64-column chunks
+  uint8_t* slabs = smem_slab + e * SLABS * kSlabBytes;
+  uint8_t* aux = smem_aux + e * (AUX > 0 ? AUX : 1) * kSlabBytes;
+  const int et = threadIdx.x - 128;         // 0 .. 32*kEpiWarps-1
+  // swizzled 16-byte slots of this lane's row inside a slab (row = lane)
+  uint32_t row_slot[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) row_slot[g] = lane * 128 + ((g ^ (lane & 7)) << 4);
+  // stats pass: lane reads 16 bytes (8 columns, slot lane%8) of rows it*4 + lane/8; the row's
+  // swizzle phase (row & 7) alternates between st_row and st_row + 4 with the parity of `it`
+  const int st_row = lane >> 3, st_slot = lane & 7;
+  const uint32_t st_off0 = st_row * 128 + ((st_slot ^ st_row) << 4);
+  const uint32_t st_off1 = st_row * 128 + ((st_slot ^ (st_row + 4)) << 4);
+  const bool fused = AUX > 0 && p.fuse != 0;
+  const int n_loads = (p.has_residual ? 1 : 0) + (fused ? p.fuse : 0);
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  uint32_t res_phase = 0;
+  int slab_idx = 0;
+  for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+    const int m0 = kTwoCta ? (tile / p.num_n_tiles) * 2 * kBM + cta_rank * kBM
+                           : (tile / p.num_n_tiles) * kBM;
+    const int n0 = (tile % p.num_n_tiles) * BN;
+    const int row0 = m0 + quarter * 32;
+    const int rows_valid = p.M_total - row0;   // rows of this 32-row slab that exist
+    mbar_wait(&tmem_full_bar[acc], acc_phase);
+    tc_fence_after();
+    bool released = false;
+#pragma unroll
+    for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+      const int chunk = half + ci * kHalves;
+      const int col0 = n0 + chunk * 64;
+      const bool live = col0 < p.Cout;           // ragged N (warp-uniform)
+      float2 cs1[4], cs2[4];     // packed fp32x2 accumulators (add.f32x2 / fma.f32x2 on sm_100)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { cs1[j] = make_float2(0.f, 0.f); cs2[j] = make_float2(0.f, 0.f); }
+      if (live) {
+        uint8_t* slab = slabs + slab_idx * kSlabBytes;
+        // the TMA store that last read this slab must have finished reading it
+        if (lane == 0) tma_store_wait_read<SLABS - 1>();
+        __syncwarp();
+        if (n_loads != 0 && lane == 0) {
+          mbar_arrive_expect_tx(&res_bar[e], n_loads * kSlabBytes);
+          if (p.has_residual) tma_load_2d(slab, tmRes, &res_bar[e], col0, row0);
+          if (AUX > 0 && fused) {
+            tma_load_2d(aux, tmAux1, &res_bar[e], col0, row0);
+            if (AUX > 1 && p.fuse == 2) tma_load_2d(aux + kSlabBytes, tmAux2, &res_bar[e], col0, row0);
+          }
+        }
+        uint32_t r[64];
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 64;
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_32x32b_x32(taddr + 32, r + 32);
+        tmem_ld_wait();
+        if (ci == kChunksPerWarp - 1 || col0 + 64 * kHalves >= p.Cout) {
+          // accumulator fully read by this warp: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kTwoCta) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          released = true;
+        }
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
+        }
+        if (n_loads != 0) {
+          mbar_wait(&res_bar[e], res_phase);
+          res_phase ^= 1;
+        }
+        if (p.has_residual) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint4 q = *reinterpret_cast<const uint4*>(slab + row_slot[g]);
+            float prev[8];
+            unpack8(q, prev);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
+          }
+        }
+        // bf16 pack into the 128B-swizzled slab
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(slab + row_slot[g]) = pack8(&v[g * 8]);
+        if (AUX > 0 && fused) {
+          __syncwarp();
+          // column-owner pass: this lane owns 8 channels; mask the gradient in place and
+          // accumulate sum g, sum g * xhat
+          const int cbase = col0 + st_slot * 8;
+          float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; mu[j] = 0.f; is[j] = 0.f; }
+          if (cbase < p.Cout) {
+            if (p.mask_ss != nullptr) {
+              load8f(p.mask_ss + cbase, sc);
+              load8f(p.mask_ss + p.Cout + cbase, sh);
+            }
+            load8f(p.mean_invstd + cbase, mu);
+            load8f(p.mean_invstd + p.Cout + cbase, is);
+          }
+          const bool do_mask = p.fuse_act != SIB_ACT_NONE;
+          const float neg = p.fuse_act == SIB_ACT_LEAKY ? p.fuse_slope : 0.f;
+          const uint8_t* xsl = (AUX > 1 && p.fuse == 2) ? aux + kSlabBytes : aux;
+          const bool full = rows_valid >= 32;          // warp-uniform
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const uint32_t off = it * 512 + ((it & 1) ? st_off1 : st_off0);
+            uint4 q = *reinterpret_cast<const uint4*>(slab + off);
+            if (!full && it * 4 + st_row >= rows_valid) q = make_uint4(0, 0, 0, 0);
+            float g[8], mv[8], xv[8];
+            unpack8(q, g);
+            unpack8(*reinterpret_cast<const uint4*>(aux + off), mv);
+            unpack8(*reinterpret_cast<const uint4*>(xsl + off), xv);
+            if (do_mask) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float z = fmaf(mv[j], sc[j], sh[j]);
+                g[j] = z > 0.f ? g[j] : g[j] * neg;
+              }
+              *reinterpret_cast<uint4*>(slab + off) = pack8(g);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 gg = make_float2(g[2 * j], g[2 * j + 1]);
+              const float2 xh = make_float2((xv[2 * j] - mu[2 * j]) * is[2 * j],
+                                            (xv[2 * j + 1] - mu[2 * j + 1]) * is[2 * j + 1]);
+              cs1[j] = __fadd2_rn(cs1[j], gg);
+              cs2[j] = __ffma2_rn(gg, xh, cs2[j]);
+            }
+          }
+        } else if (p.stats != nullptr) {
+          __syncwarp();
+          // column sums of the bf16 values as stored: 8 x LDS.128 cover the 32 x 64 slab
+          const bool full = rows_valid >= 32;          // warp-uniform
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            uint4 q = *reinterpret_cast<const uint4*>(slab + it * 512 + ((it & 1) ? st_off1 : st_off0));
+            if (!full && it * 4 + st_row >= rows_valid) q = make_uint4(0, 0, 0, 0);
+            const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(hq[j]);
+              cs1[j] = __fadd2_rn(cs1[j], f);
+              cs2[j] = __ffma2_rn(f, f, cs2[j]);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmOut, slab, col0, row0);
+          tma_store_commit();
+        }
+        if (SLABS > 1) slab_idx ^= 1;
+      }
+      if (p.stats != nullptr) {
+        // lanes with equal lane%8 hold partial sums of the same 8 columns (different rows)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            float2 t1, t2;
+            t1.x = __shfl_xor_sync(0xffffffffu, cs1[j].x, o);
+            t1.y = __shfl_xor_sync(0xffffffffu, cs1[j].y, o);
+            t2.x = __shfl_xor_sync(0xffffffffu, cs2[j].x, o);
+            t2.y = __shfl_xor_sync(0xffffffffu, cs2[j].y, o);
+            cs1[j] = __fadd2_rn(cs1[j], t1);
+            cs2[j] = __fadd2_rn(cs2[j], t2);
+          }
+        }
+        if (lane < 8) {
+          float4* d1 = reinterpret_cast<float4*>(&s_part[(e * 2 + 0) * kPartStride + ci * 64 + lane * 8]);
+          float4* d2 = reinterpret_cast<float4*>(&s_part[(e * 2 + 1) * kPartStride + ci * 64 + lane * 8]);
+          d1[0] = make_float4(cs1[0].x, cs1[0].y, cs1[1].x, cs1[1].y);
+          d1[1] = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
+          d2[0] = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
+          d2[1] = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
+        }
+      }
+    }
+    if (!released) {     // every chunk of this warp was past Cout: still release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kTwoCta) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
+    }
+    if (p.stats != nullptr) {
+      // combine the four row-quarters of each column and publish; s_part is reused next tile
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      for (int c = et; c < BN; c += 32 * kEpiWarps) {
+        if (n0 + c < p.Cout) {
+          const int chunk = c >> 6;
+          const int h = chunk % kHalves, ci = chunk / kHalves, lc = ci * 64 + (c & 63);
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            a += s_part[((h * 4 + q) * 2 + 0) * kPartStride + lc];
+            b += s_part[((h * 4 + q) * 2 + 1) * kPartStride + lc];
+          }
+          atomicAdd(p.stats + n0 + c, a);
+          atomicAdd(p.stats + p.Cout + n0 + c, b);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+  if (lane == 0) tma_store_wait_read<0>();
+}
 
 // Persistent, warp-specialised implicit GEMM.
 //   grid  = min(#tiles, #SMs) CTAs, each walking tiles t = blockIdx.x, +gridDim.x, ...
@@ -45,15 +296,13 @@ struct IgemmParams {
 //   warp0 : TMA producer            smem ring of STAGES x (A 128x64 + B BNx64), 128B swizzle
 //   warp1 : tcgen05.mma issuer      2 TMEM accumulator stages of BN fp32 columns
 //   warp2 : TMEM alloc / dealloc
-//   warp4-11: epilogue (8 warps; warp e reads TMEM lane quarter e%4 and the 64-column chunks
-//           with chunk%2 == e/4; BN=64 uses the first four):
-//           TMEM -> regs -> (+bias, +residual) -> bf16 -> swizzled smem slab -> TMA store,
-//           plus per-channel sum / sum-of-squares of the stored values for the following BN.
+//   warp4-11: epilogue (igemm_epilogue above)
 // The epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int STAGES, int SLABS>
+template <int BN, int STAGES, int SLABS, int AUX>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+             const __grid_constant__ CUtensorMap tmAux1, const __grid_constant__ CUtensorMap tmAux2,
              const IgemmParams p) {
   constexpr int kBBytes = BN * kBK * 2;
   constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
@@ -68,13 +317,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_bar[8];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_part[kEpiWarps][2][kChunksPerWarp * 64];   // per-warp column sums of a tile
+  __shared__ __align__(16) float s_part[kEpiWarps * 2 * kChunksPerWarp * 64];   // per-warp column sums of a tile
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * kABytes;
-  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [8 warps][SLABS][kSlabBytes]
+  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [epilogue warps][SLABS][kSlabBytes]
+  uint8_t* smem_aux = smem_slab + kEpiWarps * SLABS * kSlabBytes;   // [warps][AUX][kSlabBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,162 +421,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
-    // ---- epilogue ----
-    const int e = warp - 4;
-    const int quarter = e & 3;                // TMEM lane quarter (== warp % 4)
-    const int half = e >> 2;                  // which interleaved set of 64-column chunks
-    uint8_t* slabs = smem_slab + e * SLABS * kSlabBytes;
-    const int et = threadIdx.x - 128;         // 0 .. 32*kEpiWarps-1
-    // swizzled 16-byte slots of this lane's row inside a slab (row = lane)
-    uint32_t row_slot[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) row_slot[g] = lane * 128 + ((g ^ (lane & 7)) << 4);
-    // stats pass: lane reads 16 bytes (8 columns, slot lane%8) of rows it*4 + lane/8; the row's
-    // swizzle phase (row & 7) alternates between st_row and st_row + 4 with the parity of `it`
-    const int st_row = lane >> 3, st_slot = lane & 7;
-    const uint32_t st_off0 = st_row * 128 + ((st_slot ^ st_row) << 4);
-    const uint32_t st_off1 = st_row * 128 + ((st_slot ^ (st_row + 4)) << 4);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t res_phase = 0;
-    int slab_idx = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_tiles) * kBM;
-      const int n0 = (tile % p.num_n_tiles) * BN;
-      const int row0 = m0 + quarter * 32;
-      const int rows_valid = p.M_total - row0;   // rows of this 32-row slab that exist
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      bool released = false;
-#pragma unroll
-      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
-        const int chunk = half + ci * kHalves;
-        const int col0 = n0 + chunk * 64;
-        const bool live = col0 < p.Cout;           // ragged N (warp-uniform)
-        float2 cs1[4], cs2[4];     // packed fp32x2 accumulators (add.f32x2 / fma.f32x2 on sm_100)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { cs1[j] = make_float2(0.f, 0.f); cs2[j] = make_float2(0.f, 0.f); }
-        if (live) {
-          uint8_t* slab = slabs + slab_idx * kSlabBytes;
-          // the TMA store that last read this slab must have finished reading it
-          if (lane == 0) tma_store_wait_read<SLABS - 1>();
-          __syncwarp();
-          if (p.has_residual && lane == 0) {
-            mbar_arrive_expect_tx(&res_bar[e], kSlabBytes);
-            tma_load_2d(slab, &tmRes, &res_bar[e], col0, row0);
-          }
-          uint32_t r[64];
-          const uint32_t taddr =
-              tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 64;
-          tmem_ld_32x32b_x32(taddr, r);
-          tmem_ld_32x32b_x32(taddr + 32, r + 32);
-          tmem_ld_wait();
-          if (ci == kChunksPerWarp - 1 || col0 + 64 * kHalves >= p.Cout) {
-            // accumulator fully read by this warp: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-            released = true;
-          }
-          float v[64];
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
-          }
-          if (p.has_residual) {
-            mbar_wait(&res_bar[e], res_phase);
-            res_phase ^= 1;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const uint4 q = *reinterpret_cast<const uint4*>(slab + row_slot[g]);
-              float prev[8];
-              unpack8(q, prev);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
-            }
-          }
-          // bf16 pack into the 128B-swizzled slab
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(slab + row_slot[g]) = pack8(&v[g * 8]);
-          if (p.stats != nullptr) {
-            __syncwarp();
-            // column sums of the bf16 values as stored: 8 x LDS.128 cover the 32 x 64 slab
-            const bool full = rows_valid >= 32;          // warp-uniform
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              uint4 q = *reinterpret_cast<const uint4*>(slab + it * 512 + ((it & 1) ? st_off1 : st_off0));
-              if (!full && it * 4 + st_row >= rows_valid) q = make_uint4(0, 0, 0, 0);
-              const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(hq[j]);
-                cs1[j] = __fadd2_rn(cs1[j], f);
-                cs2[j] = __ffma2_rn(f, f, cs2[j]);
-              }
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOut, slab, col0, row0);
-            tma_store_commit();
-          }
-          if (SLABS > 1) slab_idx ^= 1;
-        }
-        if (p.stats != nullptr) {
-          // lanes with equal lane%8 hold partial sums of the same 8 columns (different rows)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              float2 t1, t2;
-              t1.x = __shfl_xor_sync(0xffffffffu, cs1[j].x, o);
-              t1.y = __shfl_xor_sync(0xffffffffu, cs1[j].y, o);
-              t2.x = __shfl_xor_sync(0xffffffffu, cs2[j].x, o);
-              t2.y = __shfl_xor_sync(0xffffffffu, cs2[j].y, o);
-              cs1[j] = __fadd2_rn(cs1[j], t1);
-              cs2[j] = __fadd2_rn(cs2[j], t2);
-            }
-          }
-          if (lane < 8) {
-            float4* d1 = reinterpret_cast<float4*>(&s_part[e][0][ci * 64 + lane * 8]);
-            float4* d2 = reinterpret_cast<float4*>(&s_part[e][1][ci * 64 + lane * 8]);
-            d1[0] = make_float4(cs1[0].x, cs1[0].y, cs1[1].x, cs1[1].y);
-            d1[1] = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
-            d2[0] = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
-            d2[1] = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
-          }
-        }
-      }
-      if (!released) {     // every chunk of this warp was past Cout: still release the accumulator
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      }
-      if (p.stats != nullptr) {
-        // combine the four row-quarters of each column and publish; s_part is reused next tile
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        for (int c = et; c < BN; c += 32 * kEpiWarps) {
-          if (n0 + c < p.Cout) {
-            const int chunk = c >> 6;
-            const int h = chunk % kHalves, ci = chunk / kHalves, lc = ci * 64 + (c & 63);
-            const float a = s_part[h * 4 + 0][0][lc] + s_part[h * 4 + 1][0][lc] +
-                            s_part[h * 4 + 2][0][lc] + s_part[h * 4 + 3][0][lc];
-            const float b = s_part[h * 4 + 0][1][lc] + s_part[h * 4 + 1][1][lc] +
-                            s_part[h * 4 + 2][1][lc] + s_part[h * 4 + 3][1][lc];
-            atomicAdd(p.stats + n0 + c, a);
-            atomicAdd(p.stats + p.Cout + n0 + c, b);
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    if (lane == 0) tma_store_wait_read<0>();
+    igemm_epilogue<BN, SLABS, AUX, false>(&tmOut, &tmRes, &tmAux1, &tmAux2, p, smem_slab, smem_aux,
+                                          tmem_full_bar, tmem_empty_bar, res_bar, s_part, tmem_base,
+                                          blockIdx.x, gridDim.x, num_tiles, 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -343,30 +440,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // TMEM.  Per-SM operand traffic per FLOP drops by 1/3 against the 1-CTA 128 x 256 tile.
 // TMA loads of both CTAs complete on the leader's `full` barriers; tcgen05.commit multicasts to
 // both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator on the
-// leader's `tmem_empty` barrier.  Everything else is the 1-CTA kernel:
-// Persistent, warp-specialised implicit GEMM.
-//   grid  = min(#tiles, #SMs) CTAs, each walking tiles t = blockIdx.x, +gridDim.x, ...
-//           (n-tile fastest so concurrently running CTAs share the A tile through L2)
-//   warp0 : TMA producer            smem ring of STAGES x (A 128x64 + B BNx64), 128B swizzle
-//   warp1 : tcgen05.mma issuer      2 TMEM accumulator stages of BN fp32 columns
-//   warp2 : TMEM alloc / dealloc
-//   warp4-11: epilogue (8 warps; warp e reads TMEM lane quarter e%4 and the 64-column chunks
-//           with chunk%2 == e/4; BN=64 uses the first four):
-//           TMEM -> regs -> (+bias, +residual) -> bf16 -> swizzled smem slab -> TMA store,
-//           plus per-channel sum / sum-of-squares of the stored values for the following BN.
-// The epilogue of tile i overlaps the main loop of tile i+1.
-template <int STAGES, int SLABS>
+// leader's `tmem_empty` barrier.  Everything else is the 1-CTA kernel.
+template <int STAGES, int SLABS, int AUX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-             const IgemmParams p) {
+              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+              const __grid_constant__ CUtensorMap tmAux1, const __grid_constant__ CUtensorMap tmAux2,
+              const IgemmParams p) {
   constexpr int BN = 256;
   constexpr int kBBytes = (BN / 2) * kBK * 2;      // this CTA's half of the weight tile
   constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
-  constexpr int kChunks = BN / 64;
-  constexpr int kHalves = kChunks >= 2 ? 2 : 1;    // epilogue warp groups splitting the columns
-  constexpr int kEpiWarps = 4 * kHalves;
-  constexpr int kChunksPerWarp = kChunks / kHalves;
+  constexpr int kEpiWarps = 8;
+  constexpr int kChunksPerWarp = 2;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
@@ -374,13 +459,14 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_bar[8];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float s_part[kEpiWarps][2][kChunksPerWarp * 64];   // per-warp column sums of a tile
+  __shared__ __align__(16) float s_part[kEpiWarps * 2 * kChunksPerWarp * 64];   // per-warp column sums of a tile
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * kABytes;
-  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [8 warps][SLABS][kSlabBytes]
+  uint8_t* smem_slab = smem_b + STAGES * kBBytes;   // [epilogue warps][SLABS][kSlabBytes]
+  uint8_t* smem_aux = smem_slab + kEpiWarps * SLABS * kSlabBytes;   // [warps][AUX][kSlabBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -482,162 +568,9 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
-    // ---- epilogue ----
-    const int e = warp - 4;
-    const int quarter = e & 3;                // TMEM lane quarter (== warp % 4)
-    const int half = e >> 2;                  // which interleaved set of 64-column chunks
-    uint8_t* slabs = smem_slab + e * SLABS * kSlabBytes;
-    const int et = threadIdx.x - 128;         // 0 .. 32*kEpiWarps-1
-    // swizzled 16-byte slots of this lane's row inside a slab (row = lane)
-    uint32_t row_slot[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) row_slot[g] = lane * 128 + ((g ^ (lane & 7)) << 4);
-    // stats pass: lane reads 16 bytes (8 columns, slot lane%8) of rows it*4 + lane/8; the row's
-    // swizzle phase (row & 7) alternates between st_row and st_row + 4 with the parity of `it`
-    const int st_row = lane >> 3, st_slot = lane & 7;
-    const uint32_t st_off0 = st_row * 128 + ((st_slot ^ st_row) << 4);
-    const uint32_t st_off1 = st_row * 128 + ((st_slot ^ (st_row + 4)) << 4);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t res_phase = 0;
-    int slab_idx = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m0 = (tile / p.num_n_tiles) * 2 * kBM + (int)cta_rank * kBM;
-      const int n0 = (tile % p.num_n_tiles) * BN;
-      const int row0 = m0 + quarter * 32;
-      const int rows_valid = p.M_total - row0;   // rows of this 32-row slab that exist
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      bool released = false;
-#pragma unroll
-      for (int ci = 0; ci < kChunksPerWarp; ++ci) {
-        const int chunk = half + ci * kHalves;
-        const int col0 = n0 + chunk * 64;
-        const bool live = col0 < p.Cout;           // ragged N (warp-uniform)
-        float2 cs1[4], cs2[4];     // packed fp32x2 accumulators (add.f32x2 / fma.f32x2 on sm_100)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { cs1[j] = make_float2(0.f, 0.f); cs2[j] = make_float2(0.f, 0.f); }
-        if (live) {
-          uint8_t* slab = slabs + slab_idx * kSlabBytes;
-          // the TMA store that last read this slab must have finished reading it
-          if (lane == 0) tma_store_wait_read<SLABS - 1>();
-          __syncwarp();
-          if (p.has_residual && lane == 0) {
-            mbar_arrive_expect_tx(&res_bar[e], kSlabBytes);
-            tma_load_2d(slab, &tmRes, &res_bar[e], col0, row0);
-          }
-          uint32_t r[64];
-          const uint32_t taddr =
-              tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + chunk * 64;
-          tmem_ld_32x32b_x32(taddr, r);
-          tmem_ld_32x32b_x32(taddr + 32, r + 32);
-          tmem_ld_wait();
-          if (ci == kChunksPerWarp - 1 || col0 + 64 * kHalves >= p.Cout) {
-            // accumulator fully read by this warp: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-            released = true;
-          }
-          float v[64];
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
-          }
-          if (p.has_residual) {
-            mbar_wait(&res_bar[e], res_phase);
-            res_phase ^= 1;
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const uint4 q = *reinterpret_cast<const uint4*>(slab + row_slot[g]);
-              float prev[8];
-              unpack8(q, prev);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
-            }
-          }
-          // bf16 pack into the 128B-swizzled slab
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(slab + row_slot[g]) = pack8(&v[g * 8]);
-          if (p.stats != nullptr) {
-            __syncwarp();
-            // column sums of the bf16 values as stored: 8 x LDS.128 cover the 32 x 64 slab
-            const bool full = rows_valid >= 32;          // warp-uniform
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              uint4 q = *reinterpret_cast<const uint4*>(slab + it * 512 + ((it & 1) ? st_off1 : st_off0));
-              if (!full && it * 4 + st_row >= rows_valid) q = make_uint4(0, 0, 0, 0);
-              const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(hq[j]);
-                cs1[j] = __fadd2_rn(cs1[j], f);
-                cs2[j] = __ffma2_rn(f, f, cs2[j]);
-              }
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOut, slab, col0, row0);
-            tma_store_commit();
-          }
-          if (SLABS > 1) slab_idx ^= 1;
-        }
-        if (p.stats != nullptr) {
-          // lanes with equal lane%8 hold partial sums of the same 8 columns (different rows)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int o = 8; o <= 16; o <<= 1) {
-              float2 t1, t2;
-              t1.x = __shfl_xor_sync(0xffffffffu, cs1[j].x, o);
-              t1.y = __shfl_xor_sync(0xffffffffu, cs1[j].y, o);
-              t2.x = __shfl_xor_sync(0xffffffffu, cs2[j].x, o);
-              t2.y = __shfl_xor_sync(0xffffffffu, cs2[j].y, o);
-              cs1[j] = __fadd2_rn(cs1[j], t1);
-              cs2[j] = __fadd2_rn(cs2[j], t2);
-            }
-          }
-          if (lane < 8) {
-            float4* d1 = reinterpret_cast<float4*>(&s_part[e][0][ci * 64 + lane * 8]);
-            float4* d2 = reinterpret_cast<float4*>(&s_part[e][1][ci * 64 + lane * 8]);
-            d1[0] = make_float4(cs1[0].x, cs1[0].y, cs1[1].x, cs1[1].y);
-            d1[1] = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
-            d2[0] = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
-            d2[1] = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
-          }
-        }
-      }
-      if (!released) {     // every chunk of this warp was past Cout: still release the accumulator
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-      }
-      if (p.stats != nullptr) {
-        // combine the four row-quarters of each column and publish; s_part is reused next tile
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-        for (int c = et; c < BN; c += 32 * kEpiWarps) {
-          if (n0 + c < p.Cout) {
-            const int chunk = c >> 6;
-            const int h = chunk % kHalves, ci = chunk / kHalves, lc = ci * 64 + (c & 63);
-            const float a = s_part[h * 4 + 0][0][lc] + s_part[h * 4 + 1][0][lc] +
-                            s_part[h * 4 + 2][0][lc] + s_part[h * 4 + 3][0][lc];
-            const float b = s_part[h * 4 + 0][1][lc] + s_part[h * 4 + 1][1][lc] +
-                            s_part[h * 4 + 2][1][lc] + s_part[h * 4 + 3][1][lc];
-            atomicAdd(p.stats + n0 + c, a);
-            atomicAdd(p.stats + p.Cout + n0 + c, b);
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    if (lane == 0) tma_store_wait_read<0>();
+    igemm_epilogue<BN, SLABS, AUX, true>(&tmOut, &tmRes, &tmAux1, &tmAux2, p, smem_slab, smem_aux,
+                                         tmem_full_bar, tmem_empty_bar, res_bar, s_part, tmem_base,
+                                         cluster_id, num_clusters, num_tiles, (int)cta_rank);
   }
   tc_fence_before();
   cluster_sync_all();          // the leader's MMAs read the peer's smem: nobody leaves early
@@ -846,39 +779,58 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 // ----------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------
-template <int BN, int STAGES, int SLABS>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                        const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 8 * SLABS * kSlabBytes + 1024;
+struct IgemmMaps {
+  CUtensorMap a, b, out, res, aux1, aux2;
+};
+
+template <int BN, int STAGES, int SLABS, int AUX>
+static int launch_igemm(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t stream) {
+  constexpr int kEpiWarps = BN >= 128 ? 8 : 4;
+  constexpr int smem =
+      STAGES * (kABytes + BN * kBK * 2) + kEpiWarps * (SLABS + AUX) * kSlabBytes + 1024;
+  static_assert(smem + kEpiWarps * 2 * (BN / (kEpiWarps / 4)) * 4 + 512 <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS>,
+    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS, AUX>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   int grid = p.num_m_tiles * p.num_n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  igemm_kernel<BN, STAGES, SLABS><<<grid, kIgemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
+  igemm_kernel<BN, STAGES, SLABS, AUX><<<grid, kIgemmThreads, smem, stream>>>(
+      tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p);
   SIB_LAUNCH_CHECK();
   return 0;
 }
 
-template <int STAGES, int SLABS>
-static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                         const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + 128 * kBK * 2) + 8 * SLABS * kSlabBytes + 1024;
+template <int STAGES, int SLABS, int AUX>
+static int launch_igemm2(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + 128 * kBK * 2) + 8 * (SLABS + AUX) * kSlabBytes + 1024;
+  static_assert(smem + 8192 + 512 <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(igemm2_kernel<STAGES, SLABS>,
+    SIB_CUDA(cudaFuncSetAttribute(igemm2_kernel<STAGES, SLABS, AUX>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   int pairs = (p.num_m_tiles / 2) * p.num_n_tiles;
   if (pairs > sm_count() / 2) pairs = sm_count() / 2;
-  igemm2_kernel<STAGES, SLABS><<<2 * pairs, kIgemmThreads, smem, stream>>>(tmA, tmB, tmOut, tmRes, p);
+  igemm2_kernel<STAGES, SLABS, AUX><<<2 * pairs, kIgemmThreads, smem, stream>>>(
+      tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p);
   SIB_LAUNCH_CHECK();
   return 0;
 }
+
+// Fused BatchNorm-backward reduction riding on a dgrad (see IgemmParams::fuse).
+struct BnBwdFuse {
+  const void* aux1 = nullptr;        // mask source (and xhat source unless aux2 is given)
+  const void* aux2 = nullptr;        // xhat source when the mask comes from a different tensor
+  const float* mask_ss = nullptr;    // [2][C] forward scale/shift: mask = fmaf(aux1, s, t) > 0
+  const float* mean_invstd = nullptr;
+  int act = SIB_ACT_NONE;
+  float slope = 0.f;
+  float* sums = nullptr;             // [2][C]: sum g, sum g * xhat
+};
 
 // Shared by fprop and dgrad.  `in` is [N][IH][IW][Cin] NHWC bf16, `w` is [Cout][R][S][Cin].
 // The traversal space (GEMM rows) is [N][TH][TW] and equals the output tensor's pixel space;
@@ -887,7 +839,7 @@ static int launch_igemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
 static int run_igemm(const void* in, const void* w, void* out, const void* residual, int N,
                      int IH, int IW, int Cin, int Cout, int R, int S, int stride, int pad_h,
                      int pad_w, int TH, int TW, const float* bias, float* stats, int flags,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const BnBwdFuse* fuse = nullptr) {
   // 1x1 filters may have a ragged K: TMA zero-fills both operands past Cin
   SIB_CHECK(Cin % 64 == 0 || (R == 1 && S == 1 && Cin % 8 == 0),
             "igemm: Cin must be a multiple of 64 (or of 8 for 1x1 filters), got %d", Cin);
@@ -907,6 +859,19 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   p.bias = bias;
   p.stats = stats;
   p.has_residual = residual != nullptr;
+  int aux = 0;
+  if (fuse != nullptr) {
+    SIB_CHECK(stats == nullptr && fuse->aux1 != nullptr && fuse->mean_invstd != nullptr &&
+                  fuse->sums != nullptr,
+              "igemm: fused BN backward needs aux1, mean_invstd and sums (and no fprop stats)");
+    aux = fuse->aux2 != nullptr ? 2 : 1;
+    p.fuse = aux;
+    p.fuse_act = fuse->act;
+    p.fuse_slope = fuse->slope;
+    p.mask_ss = fuse->mask_ss;
+    p.mean_invstd = fuse->mean_invstd;
+    p.stats = fuse->sums;
+  }
   const bool plain =
       (R == 1 && S == 1 && stride == 1 && pad_h == 0 && pad_w == 0 && TH == IH && TW == IW);
   p.tiled_a = (plain && !(flags & SIB_FLAG_FORCE_IM2COL)) ? 1 : 0;
@@ -918,34 +883,53 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   p.num_m_tiles = (p.M_total + kBM - 1) / kBM;
   p.num_n_tiles = (Cout + BN - 1) / BN;
 
-  CUtensorMap tmA, tmB, tmOut, tmRes;
+  IgemmMaps tm;
   int rc;
   if (p.tiled_a) {
-    rc = make_tmap_2d_bf16(&tmA, in, (uint64_t)p.M_total, Cin, Cin, kBM, kBK, true);
+    rc = make_tmap_2d_bf16(&tm.a, in, (uint64_t)p.M_total, Cin, Cin, kBM, kBK, true);
   } else {
     // base pixel range: [-pad, -pad + (T-1)*stride]  =>  upper corner = that max - (I-1)
     const int up_w = -pad_w + (TW - 1) * stride - (IW - 1);
     const int up_h = -pad_h + (TH - 1) * stride - (IH - 1);
-    rc = make_tmap_im2col_bf16(&tmA, in, N, IH, IW, Cin, -pad_w, -pad_h, up_w, up_h, stride,
+    rc = make_tmap_im2col_bf16(&tm.a, in, N, IH, IW, Cin, -pad_w, -pad_h, up_w, up_h, stride,
                                stride, kBK, kBM, true);
   }
   if (rc) return rc;
   // 2-CTA pairs (M = 256 per cluster) for the tensor-bound shapes
   const bool two_cta = BN == 256 && p.num_m_tiles % 2 == 0 && p.num_kblocks >= 4 &&
                        !(flags & SIB_FLAG_NO_2CTA);
-  rc = make_tmap_2d_bf16(&tmB, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin,
+  rc = make_tmap_2d_bf16(&tm.b, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin,
                          two_cta ? 128 : BN, kBK, true);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tmOut, out, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
+  rc = make_tmap_2d_bf16(&tm.out, out, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tmRes, residual ? residual : out, (uint64_t)p.M_total, Cout, Cout, 32,
+  rc = make_tmap_2d_bf16(&tm.res, residual ? residual : out, (uint64_t)p.M_total, Cout, Cout, 32,
                          64, true);
   if (rc) return rc;
-  if (stats != nullptr) SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, stream));
-  if (two_cta) return launch_igemm2<5, 1>(tmA, tmB, tmOut, tmRes, p, stream);
-  if (BN == 64) return launch_igemm<64, 6, 2>(tmA, tmB, tmOut, tmRes, p, stream);
-  if (BN == 128) return launch_igemm<128, 5, 1>(tmA, tmB, tmOut, tmRes, p, stream);
-  return launch_igemm<256, 3, 2>(tmA, tmB, tmOut, tmRes, p, stream);
+  rc = make_tmap_2d_bf16(&tm.aux1, aux >= 1 ? fuse->aux1 : out, (uint64_t)p.M_total, Cout, Cout,
+                         32, 64, true);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tm.aux2, aux >= 2 ? fuse->aux2 : out, (uint64_t)p.M_total, Cout, Cout,
+                         32, 64, true);
+  if (rc) return rc;
+  if (p.stats != nullptr) SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * Cout, stream));
+  if (aux == 0) {
+    if (two_cta) return launch_igemm2<5, 1, 0>(tm, p, stream);
+    if (BN == 64) return launch_igemm<64, 6, 2, 0>(tm, p, stream);
+    if (BN == 128) return launch_igemm<128, 5, 1, 0>(tm, p, stream);
+    return launch_igemm<256, 3, 2, 0>(tm, p, stream);
+  }
+  // fused variants trade pipeline stages for the auxiliary slabs (227 KB of smem per CTA)
+  if (aux == 1) {
+    if (two_cta) return launch_igemm2<4, 1, 1>(tm, p, stream);
+    if (BN == 64) return launch_igemm<64, 6, 2, 1>(tm, p, stream);
+    if (BN == 128) return launch_igemm<128, 4, 1, 1>(tm, p, stream);
+    return launch_igemm<256, 3, 1, 1>(tm, p, stream);
+  }
+  if (two_cta) return launch_igemm2<3, 1, 2>(tm, p, stream);
+  if (BN == 64) return launch_igemm<64, 6, 2, 2>(tm, p, stream);
+  if (BN == 128) return launch_igemm<128, 3, 1, 2>(tm, p, stream);
+  return launch_igemm<256, 2, 1, 2>(tm, p, stream);
 }
 
 template <int STAGES, bool kTmaReduce>
@@ -987,19 +971,19 @@ extern "C" int sib_scatter_add_strided(const void* src, void* dst, int N, int OH
 //   1x1 : compact GEMM into workspace [N][OH][OW][C], then dx[n][p*s][q*s][:] += it
 //         (dx must already hold the other gradient contribution; residual must be null)
 //   RxS : zero-insert dY into workspace [N][(OH-1)s+1][(OW-1)s+1][K], stride-1 conv over it
-extern "C" int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx,
-                                const void* residual, void* workspace, int N, int H, int W,
-                                int C, int K, int R, int S, int stride, int pad, int flags,
-                                void* stream) {
+static int dgrad_impl(const void* dy, const void* w_dgrad, void* dx, const void* residual,
+                      void* workspace, int N, int H, int W, int C, int K, int R, int S, int stride,
+                      int pad, int flags, void* stream, const BnBwdFuse* fuse) {
   const int OH = (H + 2 * pad - R) / stride + 1;
   const int OW = (W + 2 * pad - S) / stride + 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (stride == 1)
     return run_igemm(dy, w_dgrad, dx, residual, N, OH, OW, K, C, R, S, 1, R - 1 - pad,
-                     S - 1 - pad, H, W, nullptr, nullptr, flags, st);
+                     S - 1 - pad, H, W, nullptr, nullptr, flags, st, fuse);
   SIB_CHECK(workspace != nullptr, "strided dgrad needs a workspace");
   if (R == 1 && S == 1 && pad == 0) {
     SIB_CHECK(residual == nullptr, "strided 1x1 dgrad accumulates into dx; residual must be null");
+    SIB_CHECK(fuse == nullptr, "strided 1x1 dgrad cannot carry the fused BN backward reduction");
     if (int rc = run_igemm(dy, w_dgrad, workspace, nullptr, N, OH, OW, K, C, 1, 1, 1, 0, 0, OH, OW,
                            nullptr, nullptr, flags, st))
       return rc;
@@ -1008,7 +992,35 @@ extern "C" int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx,
   const int UH = (OH - 1) * stride + 1, UW = (OW - 1) * stride + 1;
   if (int rc = sib_upsample_zero(dy, workspace, N, OH, OW, K, UH, UW, stride, stream)) return rc;
   return run_igemm(workspace, w_dgrad, dx, residual, N, UH, UW, K, C, R, S, 1, R - 1 - pad,
-                   S - 1 - pad, H, W, nullptr, nullptr, flags, st);
+                   S - 1 - pad, H, W, nullptr, nullptr, flags, st, fuse);
+}
+
+extern "C" int sib_conv2d_dgrad(const void* dy, const void* w_dgrad, void* dx,
+                                const void* residual, void* workspace, int N, int H, int W,
+                                int C, int K, int R, int S, int stride, int pad, int flags,
+                                void* stream) {
+  return dgrad_impl(dy, w_dgrad, dx, residual, workspace, N, H, W, C, K, R, S, stride, pad, flags,
+                    stream, nullptr);
+}
+
+extern "C" int sib_conv2d_dgrad_bnbwd(const void* dy, const void* w_dgrad, void* dx,
+                                      const void* residual, void* workspace, int N, int H, int W,
+                                      int C, int K, int R, int S, int stride, int pad, int flags,
+                                      const void* mask_src, const float* mask_ss,
+                                      const void* xhat_src, const float* mean_invstd, int act,
+                                      float slope, float* sums, void* stream) {
+  SIB_CHECK(mask_src != nullptr && mean_invstd != nullptr && sums != nullptr,
+            "dgrad_bnbwd: mask_src, mean_invstd and sums are required");
+  BnBwdFuse f;
+  f.aux1 = mask_src;
+  f.aux2 = (xhat_src != nullptr && xhat_src != mask_src) ? xhat_src : nullptr;
+  f.mask_ss = mask_ss;
+  f.mean_invstd = mean_invstd;
+  f.act = act;
+  f.slope = slope;
+  f.sums = sums;
+  return dgrad_impl(dy, w_dgrad, dx, residual, workspace, N, H, W, C, K, R, S, stride, pad, flags,
+                    stream, &f);
 }
 
 extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W,

@@ -46,12 +46,6 @@ struct ColOwner {
   }
 };
 
-__device__ __forceinline__ void load8f(const float* p, float* v) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-
 // cross-thread reduction of per-thread column accumulators -> fp32 atomics on out[NACC][C]
 template <int NACC>
 __device__ __forceinline__ void column_reduce_store(const ColOwner& co, int C,

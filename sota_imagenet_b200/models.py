@@ -76,8 +76,13 @@ class ResNet(SibModule):
         dfeat = self.fc.bwd(dlogits.to(torch.bfloat16).contiguous(), fc_saved)
         dy = ops.gap_bwd(dfeat, y_shape)
         blocks = list(self.blocks())
+        dy_sums = None
         for i in range(len(blocks) - 1, -1, -1):
-            dy = blocks[i].bwd(dy, saved[i], need_dx=True)
+            # fuse the previous block's bn3 + add + act backward reduction into this block's last
+            # dgrad epilogue when both sides allow it (modules.Bottleneck.fuse_info)
+            prev = blocks[i - 1].fuse_info(saved[i - 1]) if i > 0 and blocks[i].can_fuse_prev() else None
+            r = blocks[i].bwd(dy, saved[i], need_dx=True, dout_sums=dy_sums, prev=prev)
+            dy, dy_sums = r if prev is not None else (r, None)
             saved[i] = None
             self._after_block_backward(i)
         da0 = self.maxpool.bwd(dy, pool_saved)

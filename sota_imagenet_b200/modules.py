@@ -11,12 +11,19 @@ Module / parameter names follow torchvision's ResNet so checkpoints interchange
 (reference train.py:98-101 loads with strict=False).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
 
 from . import _lib, ops
 from .arena import ParamArena
+
+
+# Fuse the BatchNorm-backward reduction (and the activation mask) into the epilogue of the dgrad
+# that produces the gradient (csrc/conv.cu igemm_epilogue); SIB_FUSE_BN_BWD=0 restores the separate
+# bn_bwd_reduce passes (kept for A/B measurements and as the parity cross-check).
+FUSE_BN_BWD = os.environ.get("SIB_FUSE_BN_BWD", "1") != "0"
 
 
 # --------------------------------------------------------------------------- autograd glue
@@ -143,10 +150,10 @@ class Conv2d(SibModule):
     def run(self, x, stats=None):
         return ops.conv2d_fprop(x, self._w16(self.weight), self.stride, self.padding, stats=stats)
 
-    def run_dgrad(self, dy, x_shape, out=None, residual=None):
+    def run_dgrad(self, dy, x_shape, out=None, residual=None, bn_bwd=None):
         k = self.kernel_size[0]
         return ops.conv2d_dgrad(dy, self._wd16(self.weight), x_shape, k, k, self.stride,
-                                self.padding, out=out, residual=residual)
+                                self.padding, out=out, residual=residual, bn_bwd=bn_bwd)
 
     def run_wgrad(self, x, dy):
         ops.conv2d_wgrad(x, dy, self._grad(self.weight), self.stride, self.padding)
@@ -423,12 +430,28 @@ class Bottleneck(SibModule):
             return out, None
         return out, (x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3, ss1, ss2)
 
-    def bwd(self, dout, saved, need_dx=True):
+    def fuse_info(self, saved):
+        """What the NEXT block's final dgrad needs to fuse this block's bn3 + add + act backward
+        reduction into its epilogue (identity-shortcut blocks only): the mask comes from the stored
+        block output, xhat from conv3's output."""
+        if not FUSE_BN_BWD or self.downsample is not None or saved is None:
+            return None
+        c3, mi3, out = saved[7], saved[8], saved[11]
+        return dict(mask_src=out, mask_ss=None, xhat_src=c3, mean_invstd=mi3, act=self.bn3.act,
+                    slope=self.bn3.slope)
+
+    def bwd(self, dout, saved, need_dx=True, dout_sums=None, prev=None):
+        """dout: gradient w.r.t. the block output.  With `dout_sums` it is already masked by this
+        block's final activation and the bn3 reduction (sum g, sum g*xhat) is `dout_sums` (both
+        produced by the next block's dgrad epilogue).  `prev` = fuse_info() of the preceding block:
+        when this block can honour it, returns (dx_masked, sums_for_prev) instead of dx."""
         x, c1, mi1, a1, c2, mi2, a2, c3, mi3, cd, mid, out, cnt1, cnt2, cnt3, ss1, ss2 = saved
         dout = _as_act(dout)
         bn1, bn2, bn3 = self.bn1, self.bn2, self.bn3
+        none = ops.ACT_CODES["identity"]
         # ---- bn3 (+ shortcut bn) + add + act ----
         if self.downsample is not None:
+            assert dout_sums is None
             bnd = self.downsample[1]
             sums = bn3.reduce_sums(ops.bn_bwd_reduce(dout, out, c3, mi3, bn3.act, bn3.slope, x2=cd,
                                                      mean_invstd2=mid))
@@ -437,25 +460,41 @@ class Bottleneck(SibModule):
                                            gamma2=bnd.weight.data, param_grads=bn3.grad_ptrs(),
                                            param_grads2=bnd.grad_ptrs())
             g = None
+        elif dout_sums is not None:
+            # dout is g (masked): it is also the identity-shortcut gradient
+            sums = bn3.reduce_sums(dout_sums)
+            dc3, dcd, _ = ops.bn_bwd_apply(dout, None, c3, mi3, bn3.weight.data, sums, cnt3, none, 0.0,
+                                           param_grads=bn3.grad_ptrs())
+            g = dout
         else:
             sums = bn3.reduce_sums(ops.bn_bwd_reduce(dout, out, c3, mi3, bn3.act, bn3.slope))
             dc3, dcd, g = ops.bn_bwd_apply(dout, out, c3, mi3, bn3.weight.data, sums, cnt3, bn3.act,
                                            bn3.slope, want_g=need_dx, param_grads=bn3.grad_ptrs())
-        # ---- conv3 ----
-        self.conv3.run_wgrad(a2, dc3)
-        da2 = self.conv3.run_dgrad(dc3, tuple(a2.shape))
-        # ---- bn2 + act ----
+        # ---- conv3, bn2 + act ----
         # (activation mask recomputed from c2 and the forward scale/shift: a2 is not re-read)
-        sums = bn2.reduce_sums(ops.bn_bwd_reduce(da2, None, c2, mi2, bn2.act, bn2.slope, mask_ss=ss2))
-        dc2, _, _ = ops.bn_bwd_apply(da2, None, c2, mi2, bn2.weight.data, sums, cnt2, bn2.act,
-                                     bn2.slope, mask_ss=ss2, param_grads=bn2.grad_ptrs())
-        # ---- conv2 ----
+        self.conv3.run_wgrad(a2, dc3)
+        if FUSE_BN_BWD:
+            da2, sums = self.conv3.run_dgrad(dc3, tuple(a2.shape), bn_bwd=dict(
+                mask_src=c2, mask_ss=ss2, mean_invstd=mi2, act=bn2.act, slope=bn2.slope))
+            dc2, _, _ = ops.bn_bwd_apply(da2, None, c2, mi2, bn2.weight.data, bn2.reduce_sums(sums), cnt2,
+                                         none, 0.0, param_grads=bn2.grad_ptrs())
+        else:
+            da2 = self.conv3.run_dgrad(dc3, tuple(a2.shape))
+            sums = bn2.reduce_sums(ops.bn_bwd_reduce(da2, None, c2, mi2, bn2.act, bn2.slope, mask_ss=ss2))
+            dc2, _, _ = ops.bn_bwd_apply(da2, None, c2, mi2, bn2.weight.data, sums, cnt2, bn2.act,
+                                         bn2.slope, mask_ss=ss2, param_grads=bn2.grad_ptrs())
+        # ---- conv2, bn1 + act ----
         self.conv2.run_wgrad(a1, dc2)
-        da1 = self.conv2.run_dgrad(dc2, tuple(a1.shape))
-        # ---- bn1 + act ----
-        sums = bn1.reduce_sums(ops.bn_bwd_reduce(da1, None, c1, mi1, bn1.act, bn1.slope, mask_ss=ss1))
-        dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, sums, cnt1, bn1.act,
-                                     bn1.slope, mask_ss=ss1, param_grads=bn1.grad_ptrs())
+        if FUSE_BN_BWD:
+            da1, sums = self.conv2.run_dgrad(dc2, tuple(a1.shape), bn_bwd=dict(
+                mask_src=c1, mask_ss=ss1, mean_invstd=mi1, act=bn1.act, slope=bn1.slope))
+            dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, bn1.reduce_sums(sums), cnt1,
+                                         none, 0.0, param_grads=bn1.grad_ptrs())
+        else:
+            da1 = self.conv2.run_dgrad(dc2, tuple(a1.shape))
+            sums = bn1.reduce_sums(ops.bn_bwd_reduce(da1, None, c1, mi1, bn1.act, bn1.slope, mask_ss=ss1))
+            dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, sums, cnt1, bn1.act,
+                                         bn1.slope, mask_ss=ss1, param_grads=bn1.grad_ptrs())
         # ---- conv1 (+ shortcut) ----
         self.conv1.run_wgrad(x, dc1)
         if self.downsample is not None:
@@ -464,11 +503,16 @@ class Bottleneck(SibModule):
             return None
         if self.downsample is None:
             # identity shortcut: dx = dgrad(conv1) + g, the add fused into the conv epilogue
-            return self.conv1.run_dgrad(dc1, tuple(x.shape), residual=g)
+            return self.conv1.run_dgrad(dc1, tuple(x.shape), residual=g, bn_bwd=prev)
         dx = self.conv1.run_dgrad(dc1, tuple(x.shape))
         if self.stride == 1:
-            return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx, residual=dx)
+            return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx, residual=dx, bn_bwd=prev)
+        assert prev is None, "a strided shortcut ends in a scatter-add and cannot fuse the reduction"
         return self.downsample[0].run_dgrad(dcd, tuple(x.shape), out=dx)   # strided scatter-add
+
+    def can_fuse_prev(self):
+        """True when this block's input gradient comes out of ONE stride-1 dgrad epilogue."""
+        return FUSE_BN_BWD and (self.downsample is None or self.stride == 1)
 
 
 class GlobalAvgPool(SibModule):

@@ -68,10 +68,13 @@ def conv2d_fprop(x, w, stride=1, pad=0, stats=None, bias=None, flags=0, pad_hw=N
     return y
 
 
-def conv2d_dgrad(dy, w_dgrad, x_shape, r, s, stride=1, pad=0, out=None, residual=None, flags=0):
+def conv2d_dgrad(dy, w_dgrad, x_shape, r, s, stride=1, pad=0, out=None, residual=None, flags=0,
+                 bn_bwd=None):
     """dx for conv(x, w); `w_dgrad` is the [C][R][S][K] flipped pack of w.
     stride 1 (or strided RxS): dx = dgrad [+ residual].  strided 1x1: dx (= `out`, or zeros) +=
-    dgrad at every stride-th pixel."""
+    dgrad at every stride-th pixel.
+    bn_bwd = dict(mask_src, mask_ss, xhat_src, mean_invstd, act, slope): fuse the backward
+    reduction of the BatchNorm (+activation) this gradient flows into; returns (dx_masked, sums)."""
     _lib.require_device()
     _check_act(dy, "dy")
     n, c, h, wd = x_shape
@@ -88,6 +91,13 @@ def conv2d_dgrad(dy, w_dgrad, x_shape, r, s, stride=1, pad=0, out=None, residual
         ws = torch.empty((n, uh, uw, k), dtype=torch.bfloat16, device=dy.device)
     if out is None:
         out = new_act(n, c, h, wd, dy.device)
+    if bn_bwd is not None:
+        sums = torch.empty((2, c), dtype=torch.float32, device=dy.device)
+        call("sib_conv2d_dgrad_bnbwd", _p(dy), _p(w_dgrad), _p(out), _p(residual), _p(ws), n, h, wd,
+             c, k, r, s, stride, pad, flags, _p(bn_bwd["mask_src"]), _p(bn_bwd.get("mask_ss")),
+             _p(bn_bwd.get("xhat_src")), _p(bn_bwd["mean_invstd"]), bn_bwd["act"],
+             float(bn_bwd.get("slope", 0.0)), _p(sums), _stream())
+        return out, sums
     call("sib_conv2d_dgrad", _p(dy), _p(w_dgrad), _p(out), _p(residual), _p(ws), n, h, wd, c, k, r,
          s, stride, pad, flags, _stream())
     return out

@@ -64,6 +64,58 @@ def test_conv_fprop_dgrad_wgrad(n, h, w, c, k, r, stride, pad, flags):
     assert rel(dw, 2 * dw_ref) < 1e-4                   # accumulates into dw (zero_grad contract)
 
 
+FUSED_CASES = [
+    # N, H, W, C(dgrad output channels), K, R, stride, pad, mode
+    (2, 16, 16, 64, 256, 1, 1, 0, "recompute"),     # conv3 dgrad -> bn2 (BN=64 tile)
+    (3, 14, 14, 128, 128, 3, 1, 1, "recompute"),    # conv2 dgrad -> bn1 (BN=128, im2col, ragged M)
+    (2, 28, 28, 128, 128, 3, 2, 1, "recompute"),    # strided 3x3 (zero-inserted dy)
+    (2, 16, 16, 256, 64, 1, 1, 0, "stored"),        # conv1 dgrad + shortcut -> previous block's bn3 (BN=256)
+    (8, 16, 16, 512, 256, 1, 1, 0, "stored"),       # 2-CTA kernel (4 k-blocks, even tiles), leaky
+    (8, 16, 16, 256, 256, 3, 1, 1, "recompute"),    # 2-CTA kernel, one auxiliary tile
+    (3, 7, 7, 1024, 256, 1, 1, 0, "stored"),        # ragged M, several n-tiles
+]
+
+
+@pytest.mark.parametrize("n,h,w,c,k,r,stride,pad,mode", FUSED_CASES)
+def test_dgrad_fused_bn_backward_reduction(n, h, w, c, k, r, stride, pad, mode):
+    """dgrad + activation mask + BN-backward sums in one epilogue == dgrad, then bn_bwd_reduce."""
+    torch.manual_seed(2)
+    oh = (h + 2 * pad - r) // stride + 1
+    act, slope = (ops.ACT_CODES["leaky_relu"], 0.01) if c == 512 else (ops.ACT_CODES["relu"], 0.0)
+    wb = (torch.randn(k, c, r, r, device="cuda") / (c * r * r) ** 0.5).to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last)
+    wd = ops.pack_dgrad_weight(wb)
+    dy = ops.to_nhwc_bf16(torch.randn(n, k, oh, oh, device="cuda"))
+    xin = ops.to_nhwc_bf16(torch.randn(n, c, h, w, device="cuda") * 1.5 + 0.3)   # the BN's input
+    m = n * h * w
+    mean = xin.float().mean(dim=(0, 2, 3))
+    invstd = (xin.float().var(dim=(0, 2, 3), unbiased=False) + 1e-5).rsqrt()
+    mi = torch.stack([mean, invstd]).contiguous()
+    gamma = torch.rand(c, device="cuda") + 0.5
+    ss = torch.stack([gamma * invstd, 0.1 - mean * gamma * invstd]).contiguous()
+    if mode == "recompute":
+        res, out = None, None
+        fuse = dict(mask_src=xin, mask_ss=ss, mean_invstd=mi, act=act, slope=slope)
+    else:
+        res = ops.to_nhwc_bf16(torch.randn(n, c, h, w, device="cuda"))
+        out = ops.to_nhwc_bf16(torch.relu(torch.randn(n, c, h, w, device="cuda")))  # stored block output
+        fuse = dict(mask_src=out, mask_ss=None, xhat_src=xin, mean_invstd=mi, act=act, slope=slope)
+    plain = ops.conv2d_dgrad(dy, wd, (n, c, h, w), r, r, stride=stride, pad=pad, residual=res)
+    sums_ref = ops.bn_bwd_reduce(plain, out, xin, mi, act, slope, mask_ss=None if out is not None else ss)
+    z = out.float() if out is not None else torch.addcmul(ss[1].view(1, -1, 1, 1), xin.float(), ss[0].view(1, -1, 1, 1))
+    g_ref = torch.where(z > 0, plain.float(), plain.float() * slope)
+    fused, sums = ops.conv2d_dgrad(dy, wd, (n, c, h, w), r, r, stride=stride, pad=pad, residual=res,
+                                   bn_bwd=fuse)
+    torch.cuda.synchronize()
+    assert rel(fused, g_ref) < 4e-3 if slope else torch.equal(fused.float(), g_ref)
+    xhat = (xin.float() - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+    gf = fused.float()
+    direct = torch.stack([gf.sum(dim=(0, 2, 3)), (gf * xhat).sum(dim=(0, 2, 3))])
+    scale = direct.abs().max()
+    assert float((sums - direct).abs().max() / scale) < 1e-4         # sums of what was stored
+    assert float((sums - sums_ref).abs().max() / scale) < (2e-3 if slope else 1e-4)   # == separate pass
+
+
 def test_stem_7x7_as_packed_4x1_conv():
     torch.manual_seed(1)
     x = torch.randn(4, 3, 64, 64)
