@@ -37,6 +37,8 @@ extern "C" {
 #define SIB_FLAG_FORCE_IM2COL 1 /* use the im2col TMA path even for plain 1x1 (testing) */
 #define SIB_FLAG_TILE_N128 2    /* cap the N tile at 128 columns (tuning / testing)       */
 #define SIB_FLAG_NO_2CTA 4      /* never use the cta_group::2 kernel (tuning / testing)   */
+#define SIB_FLAG_STATS_ZEROED 8 /* `stats` / `sums` already hold zeros: skip the memset    */
+#define SIB_ACT_FLAG_PREZEROED 0x100 /* or-ed into sib_bn_bwd_reduce's `act`: `sums` already zero */
 
 const char* sib_last_error(void);
 int sib_abi_version(void);
@@ -121,6 +123,14 @@ int sib_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, int H, int W,
                          void* stream);
 int sib_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C,
                          void* stream);
+/* stem: BatchNorm finalize (from the conv epilogue's statistics) + apply + activation + 3x3/s2
+ * max pool in one pass; the normalised activation is never materialised.  y / idx are
+ * bit-identical to sib_bn_finalize_apply followed by sib_maxpool3x3s2_fwd. */
+int sib_bn_act_maxpool3x3s2_fwd(const void* x, const float* stats, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var,
+                                float* mean_invstd, float* scale_shift, void* y, void* idx, int N,
+                                int H, int W, int C, double count, float eps, float momentum,
+                                int act, float slope, void* stream);
 int sib_gap_fwd(const void* x, void* y, int N, int HW, int C, void* stream);
 int sib_gap_bwd(const void* dy, void* dx, int N, int HW, int C, void* stream);
 

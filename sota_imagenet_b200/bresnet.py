@@ -236,7 +236,7 @@ class BBottleneck(SibModule):
 
     @staticmethod
     def _conv_bn(conv, bn, x, train):
-        stats = torch.empty((2, conv.out_channels), dtype=torch.float32, device=x.device) if train else None
+        stats = ops.new_acc(2, conv.out_channels, x.device) if train else None
         c = conv.run(x, stats)
         y, s = bn.fwd(c, train, stats=stats)
         return y, s
@@ -374,7 +374,7 @@ class BResNet(SibModule):
         y, sb0 = c[1].fwd(y, train)
         y2 = c[3].run(y)
         a, sb1 = c[4].fwd(y2, train)
-        stats = torch.empty((2, 64), dtype=torch.float32, device=x.device) if train else None
+        stats = ops.new_acc(2, 64, x.device) if train else None
         y3 = c[6].run(a, stats)
         a0, sbn = self.bn1.fwd(y3, train, stats=stats)
         if self.antialias:

@@ -119,6 +119,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------
+// programmatic dependent launch (see launch_pdl in host.h)
+// ----------------------------------------------------------------------------
+// Let the next kernel of the stream start its prologue as soon as SM resources free up.
+__device__ __forceinline__ void griddep_launch() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// Block until the previous kernel(s) have completed and their writes are visible.
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor)
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {

@@ -353,6 +353,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // everything above touched no global data: overlap it with the previous kernel's tail (PDL)
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -499,6 +502,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -657,6 +662,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // everything above touched no global data: overlap it with the previous kernel's tail (PDL)
+  griddep_launch();
+  griddep_wait();
   if (nkb <= 0) {
     // nothing to do for this split (uniform across the CTA); fall through to teardown
   } else if (warp == 0) {
@@ -797,9 +805,8 @@ static int launch_igemm(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t 
   }
   int grid = p.num_m_tiles * p.num_n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  igemm_kernel<BN, STAGES, SLABS, AUX><<<grid, kIgemmThreads, smem, stream>>>(
-      tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p);
-  SIB_LAUNCH_CHECK();
+  SIB_CUDA(launch_pdl(igemm_kernel<BN, STAGES, SLABS, AUX>, dim3(grid), dim3(kIgemmThreads), smem,
+                      stream, tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p));
   return 0;
 }
 
@@ -815,9 +822,8 @@ static int launch_igemm2(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t
   }
   int pairs = (p.num_m_tiles / 2) * p.num_n_tiles;
   if (pairs > sm_count() / 2) pairs = sm_count() / 2;
-  igemm2_kernel<STAGES, SLABS, AUX><<<2 * pairs, kIgemmThreads, smem, stream>>>(
-      tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p);
-  SIB_LAUNCH_CHECK();
+  SIB_CUDA(launch_pdl(igemm2_kernel<STAGES, SLABS, AUX>, dim3(2 * pairs), dim3(kIgemmThreads), smem,
+                      stream, tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p));
   return 0;
 }
 
@@ -912,7 +918,8 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   rc = make_tmap_2d_bf16(&tm.aux2, aux >= 2 ? fuse->aux2 : out, (uint64_t)p.M_total, Cout, Cout,
                          32, 64, true);
   if (rc) return rc;
-  if (p.stats != nullptr) SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * Cout, stream));
+  if (p.stats != nullptr && !(flags & SIB_FLAG_STATS_ZEROED))
+    SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * Cout, stream));
   if (aux == 0) {
     if (two_cta) return launch_igemm2<5, 1, 0>(tm, p, stream);
     if (BN == 64) return launch_igemm<64, 6, 2, 0>(tm, p, stream);
@@ -942,8 +949,8 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const C
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  wgrad_kernel<STAGES, kTmaReduce><<<grid, kThreads, smem, stream>>>(tmDy, tmX, tmDw, dw, p);
-  SIB_LAUNCH_CHECK();
+  SIB_CUDA(launch_pdl(wgrad_kernel<STAGES, kTmaReduce>, grid, dim3(kThreads), smem, stream, tmDy,
+                      tmX, tmDw, dw, p));
   return 0;
 }
 

@@ -27,6 +27,27 @@ int fail(int code, const char* fmt, ...);
 
 int sm_count();
 
+// Programmatic dependent launch (PDL): the kernel may start (prologue: barrier init, TMEM
+// allocation, descriptor prefetch) while the previous kernel of the stream is still draining.
+// Every kernel launched through here MUST execute griddep_wait() (common.cuh) before it touches
+// global memory.  Opt-in with SIB_PDL=1; otherwise they are ordinary stream-ordered launches.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // 2-D row-major bf16 matrix [rows][cols] (cols contiguous); box = box_rows x box_cols.
 // swizzle128: inner box extent must be 64 elements (128 bytes).
 int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,

@@ -71,6 +71,8 @@ constexpr int kU = 4;   // rows in flight per thread
 
 __global__ void __launch_bounds__(kRedThreads)
 bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long M, int C, float* __restrict__ stats) {
+  griddep_launch();
+  griddep_wait();
   const ColOwner co(C);
   float acc[2][8] = {};
   if (co.active) {
@@ -143,6 +145,8 @@ __global__ void __launch_bounds__(kRedThreads)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ss,
                 const __nv_bfloat16* __restrict__ res, const float* __restrict__ ss2,
                 __nv_bfloat16* __restrict__ y, long M, int C, int act, float slope) {
+  griddep_launch();
+  griddep_wait();
   const ColOwner co(C);
   if (!co.active) return;
   float sc[8], sh[8], sc2[8], sh2[8];
@@ -238,6 +242,8 @@ bn_finalize_apply_kernel(const __nv_bfloat16* __restrict__ x, BnFinalizeArgs f1,
                          const __nv_bfloat16* __restrict__ res, BnFinalizeArgs f2,
                          __nv_bfloat16* __restrict__ y, long M, int C, float count, float eps,
                          float momentum, int act, float slope) {
+  griddep_launch();
+  griddep_wait();
   const ColOwner co(C);
   if (!co.active) return;
   const bool publish = blockIdx.x == 0 && co.ty == 0;
@@ -296,6 +302,8 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ mi, const __nv_bfloat16* __restrict__ x2,
                      const float* __restrict__ mi2, long M, int C, int act, float slope,
                      float* __restrict__ sums) {
+  griddep_launch();
+  griddep_wait();
   const ColOwner co(C);
   constexpr int NACC = SECOND ? 4 : 2;
   float acc[NACC][8] = {};
@@ -374,6 +382,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     float* __restrict__ dbeta, float* __restrict__ dgamma2,
                     float* __restrict__ dbeta2, long M, int C, float inv_count, int act,
                     float slope) {
+  griddep_launch();
+  griddep_wait();
   const ColOwner co(C);
   if (!co.active) return;
   if (blockIdx.x == 0 && co.ty == 0) {
@@ -489,6 +499,8 @@ __global__ void bn_param_grad_kernel(const float* __restrict__ sums, float* __re
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                    uint8_t* __restrict__ idx, int N, int H, int W, int C, int OH, int OW) {
+  griddep_launch();
+  griddep_wait();
   const int cvec = C >> 3;
   const long total = (long)N * OH * OW * cvec;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -530,6 +542,8 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW) {
+  griddep_launch();
+  griddep_wait();
   const int cvec = C >> 3;
   const long total = (long)N * H * W * cvec;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -539,31 +553,108 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
     const int w = (int)(t % W); t /= W;
     const int h = (int)(t % H);
     const int n = (int)(t / H);
+    // windows (p,q) covering (h,w): p*2-1+r = h  =>  r = h - 2p + 1 in [0,3).  h even: p = h/2
+    // (r = 1); h odd: p = (h-1)/2 (r = 2) and p = (h+1)/2 (r = 0).  All (up to four) candidates
+    // are fetched before any is used so the loads overlap.
+    const int pc[2] = {h >> 1, (h + 1) >> 1};
+    const int qc[2] = {w >> 1, (w + 1) >> 1};
+    uint2 pk[4];
+    uint4 gv[4];
+    bool ok[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int k = a * 2 + b;
+        ok[k] = pc[a] < OH && qc[b] < OW && (a == 0 || pc[1] != pc[0]) && (b == 0 || qc[1] != qc[0]);
+        if (ok[k]) {
+          const long o = ((((long)n * OH + pc[a]) * OW + qc[b]) * cvec + v) * 8;
+          pk[k] = __ldg(reinterpret_cast<const uint2*>(idx + o));
+          gv[k] = __ldg(reinterpret_cast<const uint4*>(dy + o));
+        }
+      }
+    }
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // windows (p,q) covering (h,w): p*2-1+r = h  =>  r = h - 2p + 1 in [0,3)
-    for (int p = (h >> 1); p <= ((h + 1) >> 1); ++p) {
-      if (p < 0 || p >= OH) continue;
-      const int r = h - 2 * p + 1;
-      if (r < 0 || r > 2) continue;
-      for (int q = (w >> 1); q <= ((w + 1) >> 1); ++q) {
-        if (q < 0 || q >= OW) continue;
-        const int s = w - 2 * q + 1;
-        if (s < 0 || s > 2) continue;
-        const long o = ((((long)n * OH + p) * OW + q) * cvec + v) * 8;
-        const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
-        float g[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), g);
-        const int tap = r * 3 + s;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int b = (j < 4 ? (pk.x >> (8 * j)) : (pk.y >> (8 * (j - 4)))) & 0xff;
-          if (b == tap) acc[j] += g[j];
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int k = a * 2 + b;
+        if (ok[k]) {
+          const int tap = (h - 2 * pc[a] + 1) * 3 + (w - 2 * qc[b] + 1);
+          float g[8];
+          unpack8(gv[k], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int bsel = (j < 4 ? (pk[k].x >> (8 * j)) : (pk[k].y >> (8 * (j - 4)))) & 0xff;
+            if (bsel == tap) acc[j] += g[j];
+          }
         }
       }
     }
     stg_stream(dx + i * 8, pack8(acc));
+  }
+}
+
+// BatchNorm finalize + apply + activation + 3x3/s2 max pool in one pass (the stem): the
+// normalised activation is never written.  Values are rounded to bf16 before the comparison, so
+// y and idx are bit-identical to bn_finalize_apply followed by maxpool_fwd.
+__global__ void __launch_bounds__(256)
+bn_act_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, BnFinalizeArgs f,
+                          __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx, int N, int H,
+                          int W, int C, int OH, int OW, float count, float eps, float momentum,
+                          int act, float slope) {
+  griddep_launch();
+  griddep_wait();
+  const int cvec = C >> 3;
+  // blockDim and the grid stride are multiples of cvec: a thread keeps its 8 channels
+  const int v = threadIdx.x % cvec;
+  float sc[8], sh[8];
+  bn_derive(f.stats, f.gamma, f.beta, f.running_mean, f.running_var, f.mean_invstd, f.scale_shift,
+            C, v * 8, count, eps, momentum, blockIdx.x == 0 && threadIdx.x < cvec, sc, sh);
+  const long total = (long)N * OH * OW * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    long t = i / cvec;
+    const int q = (int)(t % OW); t /= OW;
+    const int p = (int)(t % OH);
+    const int n = (int)(t / OH);
+    uint4 raw[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int h = p * 2 - 1 + r, w = q * 2 - 1 + s;
+        ok[r * 3 + s] = h >= 0 && h < H && w >= 0 && w < W;
+        if (ok[r * 3 + s])
+          raw[r * 3 + s] = __ldg(reinterpret_cast<const uint4*>(x + (((long)n * H + h) * W + w) * C + v * 8));
+      }
+    }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (!ok[k]) continue;
+      float fv[8];
+      unpack8(raw[k], fv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float o = __bfloat162float(__float2bfloat16(act_fwd(fmaf(fv[j], sc[j], sh[j]), act, slope)));
+        if (o > best[j]) { best[j] = o; bi[j] = k; }
+      }
+    }
+    stg_stream(y + i * 8, pack8(best));
+    if (idx != nullptr) {
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    }
   }
 }
 
@@ -573,6 +664,8 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 __global__ void __launch_bounds__(256)
 gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int HW,
                int C) {
+  griddep_launch();
+  griddep_wait();
   const int cvec = C >> 3;
   const long total = (long)N * cvec;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -598,6 +691,8 @@ gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
 __global__ void __launch_bounds__(256)
 gap_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int HW,
                int C) {
+  griddep_launch();
+  griddep_wait();
   const int cvec = C >> 3;
   const long total = (long)N * HW * cvec;
   const float inv = 1.f / HW;
@@ -617,6 +712,8 @@ gap_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__
 __global__ void __launch_bounds__(256)
 upsample_zero_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ up, int N,
                      int OH, int OW, int C, int UH, int UW, int stride) {
+  griddep_launch();
+  griddep_wait();
   const int cvec = C >> 3;
   const long total = (long)N * UH * UW * cvec;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -637,6 +734,8 @@ upsample_zero_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256)
 scatter_add_strided_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                            int N, int OH, int OW, int C, int H, int W, int stride) {
+  griddep_launch();
+  griddep_wait();
   const int cvec = C >> 3;
   const long total = (long)N * OH * OW * cvec;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -686,8 +785,7 @@ static int bn_grid(long M, int C) {
 extern "C" int sib_bn_stats(const void* x, long M, int C, float* stats, void* stream) {
   if (int rc = check_c(C)) return rc;
   SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, ST(stream)));
-  bn_stats_kernel<<<bn_grid(M, C), kRedThreads, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), M, C, stats);
+  SIB_CUDA(launch_pdl(bn_stats_kernel, dim3(bn_grid(M, C)), dim3(kRedThreads), 0, ST(stream), static_cast<const __nv_bfloat16*>(x), M, C, stats));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -721,14 +819,14 @@ extern "C" int sib_bn_apply(const void* x, const float* scale_shift, const void*
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   const int grid = bn_grid(M, C);
   if (res == nullptr)
-    bn_apply_kernel<0><<<grid, kRedThreads, 0, ST(stream)>>>(xp, scale_shift, rp, scale_shift2, yp,
-                                                            M, C, act, slope);
+    SIB_CUDA(launch_pdl(bn_apply_kernel<0>, dim3(grid), dim3(kRedThreads), 0, ST(stream), xp, scale_shift, rp, scale_shift2, yp,
+                                                            M, C, act, slope));
   else if (scale_shift2 == nullptr)
-    bn_apply_kernel<1><<<grid, kRedThreads, 0, ST(stream)>>>(xp, scale_shift, rp, scale_shift2, yp,
-                                                            M, C, act, slope);
+    SIB_CUDA(launch_pdl(bn_apply_kernel<1>, dim3(grid), dim3(kRedThreads), 0, ST(stream), xp, scale_shift, rp, scale_shift2, yp,
+                                                            M, C, act, slope));
   else
-    bn_apply_kernel<2><<<grid, kRedThreads, 0, ST(stream)>>>(xp, scale_shift, rp, scale_shift2, yp,
-                                                            M, C, act, slope);
+    SIB_CUDA(launch_pdl(bn_apply_kernel<2>, dim3(grid), dim3(kRedThreads), 0, ST(stream), xp, scale_shift, rp, scale_shift2, yp,
+                                                            M, C, act, slope));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -751,14 +849,11 @@ extern "C" int sib_bn_finalize_apply(const void* x, const float* stats, const fl
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
   const int grid = bn_grid(M, C);
   if (res == nullptr)
-    bn_finalize_apply_kernel<0><<<grid, kRedThreads, 0, ST(stream)>>>(
-        xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope);
+    SIB_CUDA(launch_pdl(bn_finalize_apply_kernel<0>, dim3(grid), dim3(kRedThreads), 0, ST(stream), xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope));
   else if (stats2 == nullptr)
-    bn_finalize_apply_kernel<1><<<grid, kRedThreads, 0, ST(stream)>>>(
-        xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope);
+    SIB_CUDA(launch_pdl(bn_finalize_apply_kernel<1>, dim3(grid), dim3(kRedThreads), 0, ST(stream), xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope));
   else
-    bn_finalize_apply_kernel<2><<<grid, kRedThreads, 0, ST(stream)>>>(
-        xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope);
+    SIB_CUDA(launch_pdl(bn_finalize_apply_kernel<2>, dim3(grid), dim3(kRedThreads), 0, ST(stream), xp, f1, rp, f2, yp, M, C, (float)count, eps, momentum, act, slope));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -768,19 +863,21 @@ extern "C" int sib_bn_bwd_reduce(const void* dy, const void* out, const float* m
                                  const float* mean_invstd2, long M, int C, int act, float slope,
                                  float* sums, void* stream) {
   if (int rc = check_c(C)) return rc;
+  const bool prezeroed = (act & SIB_ACT_FLAG_PREZEROED) != 0;
+  act &= ~SIB_ACT_FLAG_PREZEROED;
   SIB_CHECK(act == SIB_ACT_NONE || out != nullptr || mask_ss != nullptr,
             "bn_bwd_reduce: activation mask needs `out` or `mask_ss`");
   const int nacc = x2 ? 4 : 2;
-  SIB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * nacc * C, ST(stream)));
+  if (!prezeroed) SIB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * nacc * C, ST(stream)));
   const int grid = bn_grid(M, C);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(dy);
   const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(out);
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* xq = static_cast<const __nv_bfloat16*>(x2);
 #define SIB_RED(S, O)                                                                         \
-  bn_bwd_reduce_kernel<S, O><<<grid, kRedThreads, 0, ST(stream)>>>(a, o, mask_ss, xp, mean_invstd, \
+  SIB_CUDA(launch_pdl(bn_bwd_reduce_kernel<S, O>, dim3(grid), dim3(kRedThreads), 0, ST(stream), a, o, mask_ss, xp, mean_invstd, \
                                                                  xq, mean_invstd2, M, C, act,  \
-                                                                 slope, sums)
+                                                                 slope, sums))
   const bool use_out = out != nullptr && act != SIB_ACT_NONE;
   if (x2) { if (use_out) SIB_RED(true, true); else SIB_RED(true, false); }
   else    { if (use_out) SIB_RED(false, true); else SIB_RED(false, false); }
@@ -808,9 +905,9 @@ extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* ma
   __nv_bfloat16* gg = static_cast<__nv_bfloat16*>(gout);
   const float ic = (float)(1.0 / count);
 #define SIB_APP(S, O, G)                                                                       \
-  bn_bwd_apply_kernel<S, O, G><<<grid, kRedThreads, 0, ST(stream)>>>(                          \
+  SIB_CUDA(launch_pdl(bn_bwd_apply_kernel<S, O, G>, dim3(grid), dim3(kRedThreads), 0, ST(stream), \
       a, o, mask_ss, xp, mean_invstd, gamma, sums, xq, mean_invstd2, gamma2, d1, d2, gg, dgamma,   \
-      dbeta, dgamma2, dbeta2, M, C, ic, act, slope)
+      dbeta, dgamma2, dbeta2, M, C, ic, act, slope))
   const bool use_out = out != nullptr && act != SIB_ACT_NONE;
   const bool wg = gout != nullptr;
   if (x2) {
@@ -838,9 +935,8 @@ extern "C" int sib_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, in
   SIB_CHECK(C % 8 == 0, "maxpool: C %% 8 != 0");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long total = (long)N * OH * OW * (C / 8);
-  maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
-      static_cast<uint8_t*>(idx), N, H, W, C, OH, OW);
+  SIB_CUDA(launch_pdl(maxpool_fwd_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
+      static_cast<uint8_t*>(idx), N, H, W, C, OH, OW));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -850,25 +946,39 @@ extern "C" int sib_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, i
   SIB_CHECK(C % 8 == 0, "maxpool: C %% 8 != 0");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const long total = (long)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<const uint8_t*>(idx),
-      static_cast<__nv_bfloat16*>(dx), N, H, W, C, OH, OW);
+  SIB_CUDA(launch_pdl(maxpool_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), static_cast<const __nv_bfloat16*>(dy), static_cast<const uint8_t*>(idx),
+      static_cast<__nv_bfloat16*>(dx), N, H, W, C, OH, OW));
   SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_bn_act_maxpool3x3s2_fwd(const void* x, const float* stats, const float* gamma,
+                                           const float* beta, float* running_mean,
+                                           float* running_var, float* mean_invstd,
+                                           float* scale_shift, void* y, void* idx, int N, int H,
+                                           int W, int C, double count, float eps, float momentum,
+                                           int act, float slope, void* stream) {
+  SIB_CHECK(C % 8 == 0 && 256 % (C / 8) == 0, "bn_act_maxpool: C/8 must divide 256 (got C=%d)", C);
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const long total = (long)N * OH * OW * (C / 8);
+  BnFinalizeArgs f{stats, gamma, beta, running_mean, running_var, mean_invstd, scale_shift};
+  SIB_CUDA(launch_pdl(bn_act_maxpool_fwd_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream),
+                      static_cast<const __nv_bfloat16*>(x), f, static_cast<__nv_bfloat16*>(y),
+                      static_cast<uint8_t*>(idx), N, H, W, C, OH, OW, (float)count, eps, momentum,
+                      act, slope));
   return 0;
 }
 
 extern "C" int sib_gap_fwd(const void* x, void* y, int N, int HW, int C, void* stream) {
   SIB_CHECK(C % 8 == 0, "gap: C %% 8 != 0");
-  gap_fwd_kernel<<<ew_grid((long)N * (C / 8), 256), 256, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), N, HW, C);
+  SIB_CUDA(launch_pdl(gap_fwd_kernel, dim3(ew_grid((long)N * (C / 8), 256)), dim3(256), 0, ST(stream), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), N, HW, C));
   SIB_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int sib_gap_bwd(const void* dy, void* dx, int N, int HW, int C, void* stream) {
   SIB_CHECK(C % 8 == 0, "gap: C %% 8 != 0");
-  gap_bwd_kernel<<<ew_grid((long)N * HW * (C / 8), 256), 256, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), N, HW, C);
+  SIB_CUDA(launch_pdl(gap_bwd_kernel, dim3(ew_grid((long)N * HW * (C / 8), 256)), dim3(256), 0, ST(stream), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), N, HW, C));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -877,9 +987,8 @@ extern "C" int sib_upsample_zero(const void* dy, void* up, int N, int OH, int OW
                                  int UW, int stride, void* stream) {
   SIB_CHECK(C % 8 == 0, "upsample_zero: C %% 8 != 0");
   const long total = (long)N * UH * UW * (C / 8);
-  upsample_zero_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(up), N, OH, OW, C, UH, UW,
-      stride);
+  SIB_CUDA(launch_pdl(upsample_zero_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(up), N, OH, OW, C, UH, UW,
+      stride));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -888,9 +997,8 @@ extern "C" int sib_scatter_add_strided(const void* src, void* dst, int N, int OH
                                        int H, int W, int stride, void* stream) {
   SIB_CHECK(C % 8 == 0, "scatter_add: C %% 8 != 0");
   const long total = (long)N * OH * OW * (C / 8);
-  scatter_add_strided_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), N, OH, OW, C, H, W,
-      stride);
+  SIB_CUDA(launch_pdl(scatter_add_strided_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), N, OH, OW, C, H, W,
+      stride));
   SIB_LAUNCH_CHECK();
   return 0;
 }

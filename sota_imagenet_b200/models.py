@@ -4,11 +4,16 @@
 ResNet-50 == torchvision ResNet-50 v1.5 module graph and state_dict keys; the forward and
 backward passes are kernel sequences from libsib200 (see modules.py).
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from . import _lib, ops
 from .modules import (BatchNorm2d, Bottleneck, Linear, MaxPool3x3s2, SibModule, StemConv, _as_act)
+
+
+FUSE_STEM_POOL = os.environ.get("SIB_FUSE_STEM_POOL", "1") != "0"
 
 
 class ResNet(SibModule):
@@ -48,11 +53,21 @@ class ResNet(SibModule):
 
     def fwd(self, x, train):
         saved = []
-        stats = torch.empty((2, 64), dtype=torch.float32, device=x.device) if train else None
+        stats = ops.new_acc(2, 64, x.device) if train else None
         c0, xq = self.conv1.run(x, stats)
         n, _, h, w = c0.shape
-        a0, mi0, ss0, cnt0, _ = Bottleneck._bn_act(self.bn1, c0, stats, train)
-        p0, pool_saved = self.maxpool.fwd(a0, train)
+        if train and FUSE_STEM_POOL:
+            # bn1 + act + max pool in one pass: the 112x112 normalised activation is never written
+            # (its backward mask is recomputed from c0, the pooling backward needs only idx)
+            bn = self.bn1
+            a1, world = bn.stats_args(stats)
+            cnt0 = n * h * w * world
+            p0, idx, mi0, ss0 = ops.bn_act_maxpool3x3s2_fwd(c0, a1, bn.act, bn.slope, cnt0, bn.eps,
+                                                            bn.momentum)
+            pool_saved = (idx, tuple(c0.shape))
+        else:
+            a0, mi0, ss0, cnt0, _ = Bottleneck._bn_act(self.bn1, c0, stats, train)
+            p0, pool_saved = self.maxpool.fwd(a0, train)
         y = p0
         for blk in self.blocks():
             y, s = blk.fwd(y, train)

@@ -89,6 +89,7 @@ class SibModule(nn.Module):
         a = self.ensure_arena()
         if a is not None:
             a.prepare_grads()
+            ops.begin_pass(a.device)
 
     def _end_backward(self):
         for h in self._bwd_hooks:
@@ -100,6 +101,7 @@ class SibModule(nn.Module):
         a = self.ensure_arena()
         if a is not None:
             a.refresh_shadow()
+        ops.begin_pass(x.device)
         x = self._prepare_input(x)
         if torch.is_grad_enabled() and (self.training or x.requires_grad):
             if not hasattr(self, "_dummy") or self._dummy.device != x.device:
@@ -393,7 +395,7 @@ class Bottleneck(SibModule):
 
     @staticmethod
     def _conv(conv, x, train):
-        stats = torch.empty((2, conv.out_channels), dtype=torch.float32, device=x.device) if train else None
+        stats = ops.new_acc(2, conv.out_channels, x.device) if train else None
         return conv.run(x, stats), stats
 
     @staticmethod

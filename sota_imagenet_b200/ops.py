@@ -18,6 +18,8 @@ MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE = 0, 1, 2, 3
 FLAG_FORCE_IM2COL = 1
 FLAG_TILE_N128 = 2
 FLAG_NO_2CTA = 4
+FLAG_STATS_ZEROED = 8
+ACT_FLAG_PREZEROED = 0x100
 ACT_CODES = {None: ACT_NONE, "identity": ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU,
              "leaky_relu": ACT_LEAKY}
 
@@ -49,6 +51,52 @@ def to_nhwc_bf16(x):
     return out
 
 
+class _AccPool:
+    """fp32 accumulators that kernels add into with atomics (BN statistics from the conv epilogues,
+    backward sums) are carved out of ONE buffer that a single fill zeroes at the start of each
+    forward / backward pass, instead of one cudaMemsetAsync node per accumulator (~100 per step)."""
+    SIZE = 1 << 19   # floats (2 MB)
+
+    def __init__(self):
+        self.buf, self.off = None, 0
+
+    def reset(self, device):
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.zeros(self.SIZE, dtype=torch.float32, device=device)
+        else:
+            self.buf.zero_()
+        self.off = 0
+
+    def take(self, rows, c, device):
+        n = rows * c
+        if self.buf is None or self.buf.device != device or self.off + n > self.SIZE:
+            return None
+        t = self.buf[self.off:self.off + n].view(rows, c)
+        self.off += (n + 3) // 4 * 4     # keep 16-byte alignment
+        return t
+
+    def owns(self, t):
+        if t is None or self.buf is None or t.device != self.buf.device:
+            return False
+        base = self.buf.data_ptr()
+        return base <= t.data_ptr() < base + 4 * self.SIZE
+
+
+_ACC_POOL = _AccPool()
+
+
+def begin_pass(device):
+    """Called by the root module at the start of a forward or backward pass."""
+    _ACC_POOL.reset(device)
+
+
+def new_acc(rows, c, device):
+    """[rows, c] fp32 accumulator: a pre-zeroed pool slice when available (the kernels then skip
+    their own memset), else an uninitialised tensor the kernel zeroes itself."""
+    t = _ACC_POOL.take(rows, c, device)
+    return t if t is not None else torch.empty((rows, c), dtype=torch.float32, device=device)
+
+
 def conv_out_hw(h, w, r, s, stride, pad):
     return (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
 
@@ -63,6 +111,8 @@ def conv2d_fprop(x, w, stride=1, pad=0, stats=None, bias=None, flags=0, pad_hw=N
     ph, pw = pad_hw if pad_hw is not None else (pad, pad)
     oh, ow = out_hw if out_hw is not None else conv_out_hw(h, wd, r, s, stride, pad)
     y = new_act(n, k, oh, ow, x.device)
+    if _ACC_POOL.owns(stats):
+        flags |= FLAG_STATS_ZEROED
     call("sib_conv2d_fprop", _p(x), _p(w), _p(y), n, h, wd, c, k, r, s, stride, ph, pw, oh, ow,
          _p(bias), _p(stats), flags, _stream())
     return y
@@ -92,7 +142,9 @@ def conv2d_dgrad(dy, w_dgrad, x_shape, r, s, stride=1, pad=0, out=None, residual
     if out is None:
         out = new_act(n, c, h, wd, dy.device)
     if bn_bwd is not None:
-        sums = torch.empty((2, c), dtype=torch.float32, device=dy.device)
+        sums = new_acc(2, c, dy.device)
+        if _ACC_POOL.owns(sums):
+            flags |= FLAG_STATS_ZEROED
         call("sib_conv2d_dgrad_bnbwd", _p(dy), _p(w_dgrad), _p(out), _p(residual), _p(ws), n, h, wd,
              c, k, r, s, stride, pad, flags, _p(bn_bwd["mask_src"]), _p(bn_bwd.get("mask_ss")),
              _p(bn_bwd.get("xhat_src")), _p(bn_bwd["mean_invstd"]), bn_bwd["act"],
@@ -198,7 +250,9 @@ def bn_bwd_reduce(dy, out, x, mean_invstd, act, slope=0.01, x2=None, mean_invstd
                   mask_ss=None):
     """`out` (stored forward output) or `mask_ss` (forward scale/shift, mask recomputed from x)."""
     n, c, h, w = x.shape
-    sums = torch.empty((4 if x2 is not None else 2, c), dtype=torch.float32, device=x.device)
+    sums = new_acc(4 if x2 is not None else 2, c, x.device)
+    if _ACC_POOL.owns(sums):
+        act |= ACT_FLAG_PREZEROED
     call("sib_bn_bwd_reduce", _p(dy), _p(out), _p(mask_ss), _p(x), _p(mean_invstd), _p(x2),
          _p(mean_invstd2), n * h * w, c, act, float(slope), _p(sums), _stream())
     return sums
@@ -232,6 +286,22 @@ def maxpool3x3s2_fwd(x, want_idx=True):
     idx = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device) if want_idx else None
     call("sib_maxpool3x3s2_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
     return y, idx
+
+
+def bn_act_maxpool3x3s2_fwd(x, bn, act=ACT_RELU, slope=0.01, count=None, eps=1e-5, momentum=0.1):
+    """Stem: y = maxpool3x3s2(act(bn(x))) in one pass.  bn = (stats, gamma, beta, running_mean,
+    running_var).  Returns y, idx, mean_invstd, scale_shift."""
+    _check_act(x)
+    n, c, h, w = x.shape
+    oh, ow = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    y = new_act(n, c, oh, ow, x.device)
+    idx = torch.empty((n, oh, ow, c), dtype=torch.uint8, device=x.device)
+    mi = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    ss = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    call("sib_bn_act_maxpool3x3s2_fwd", _p(x), _p(bn[0]), _p(bn[1]), _p(bn[2]), _p(bn[3]), _p(bn[4]),
+         _p(mi), _p(ss), _p(y), _p(idx), n, h, w, c, float(count if count is not None else n * h * w),
+         float(eps), float(momentum), act, float(slope), _stream())
+    return y, idx, mi, ss
 
 
 def maxpool3x3s2_bwd(dy, idx, x_shape):

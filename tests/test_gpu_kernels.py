@@ -194,3 +194,41 @@ def test_pooling():
     assert rel(ops.gap_fwd(fb), f.mean(dim=(2, 3), keepdim=True)) < 5e-3
     g = torch.randn(4, 2048, 1, 1).bfloat16().float()
     assert rel(ops.gap_bwd(ops.to_nhwc_bf16(g.cuda()), tuple(f.shape)), g.expand_as(f) / 49) < 5e-3
+
+
+def test_stem_bn_act_maxpool_fused_is_bit_identical():
+    """bn finalize + apply + relu + maxpool in one pass == the two separate kernels, bit for bit
+    (values, winning taps, published coefficients, running statistics)."""
+    torch.manual_seed(3)
+    n, c, h, w = 3, 64, 30, 26
+    x = ops.to_nhwc_bf16(torch.randn(n, c, h, w, device="cuda") * 2 + 0.5)
+    gamma, beta = torch.rand(c, device="cuda") - 0.3, torch.randn(c, device="cuda")   # some gammas < 0
+    act = ops.ACT_CODES["relu"]
+    outs = []
+    stats0 = ops.bn_stats(x)      # (fp32 atomics: compute once so both paths see the same sums)
+    for fused in (False, True):
+        stats = stats0.clone()
+        rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        bn = (stats, gamma, beta, rm, rv)
+        if fused:
+            y, idx, mi, ss = ops.bn_act_maxpool3x3s2_fwd(x, bn, act, 0.0, n * h * w, 1e-5, 0.1)
+        else:
+            a, (mi, ss), _ = ops.bn_finalize_apply(x, bn, act=act, slope=0.0, count=n * h * w, eps=1e-5, momentum=0.1)
+            y, idx = ops.maxpool3x3s2_fwd(a)
+        outs.append((y, idx, mi, ss, rm, rv))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    # and the pooling backward (rewritten with up-front loads) against autograd on the same values
+    y, idx = outs[0][0], outs[0][1]
+    a = ops.bn_finalize_apply(x, (ops.bn_stats(x), gamma, beta, torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")),
+                              act=act, slope=0.0, count=n * h * w)[0]
+    af = a.float().requires_grad_(True)
+    ref = F.max_pool2d(af, 3, 2, 1)
+    dy = torch.randn_like(ref).bfloat16()
+    dy_nhwc = ops.to_nhwc_bf16(dy)
+    dx = ops.maxpool3x3s2_bwd(dy_nhwc, idx, (n, c, h, w))
+    ref.backward(dy.float())
+    # total gradient mass is conserved per (n, c) plane regardless of tie-breaking among zeros
+    assert rel(dx.float().sum(dim=(2, 3)), dy.float().sum(dim=(2, 3))) < 2e-2
+    pos = af.detach() > 0
+    assert rel(dx.float()[pos], af.grad[pos]) < 1e-2
