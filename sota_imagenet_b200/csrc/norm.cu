@@ -539,62 +539,65 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   }
 }
 
+// One block per input row (n, h): 32-bit index math only (the 64-bit divisions of a flat
+// grid-stride loop made this kernel instruction-bound: 340 us against an 87 us HBM time).
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
-                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW) {
+                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
+                   int cshift) {
   griddep_launch();
   griddep_wait();
-  const int cvec = C >> 3;
-  const long total = (long)N * H * W * cvec;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cvec);
-    long t = i / cvec;
-    const int w = (int)(t % W); t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
+  const int cvec = 1 << cshift;
+  for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
+    const int n = row / H;
+    const int h = row - n * H;
     // windows (p,q) covering (h,w): p*2-1+r = h  =>  r = h - 2p + 1 in [0,3).  h even: p = h/2
     // (r = 1); h odd: p = (h-1)/2 (r = 2) and p = (h+1)/2 (r = 0).  All (up to four) candidates
     // are fetched before any is used so the loads overlap.
     const int pc[2] = {h >> 1, (h + 1) >> 1};
-    const int qc[2] = {w >> 1, (w + 1) >> 1};
-    uint2 pk[4];
-    uint4 gv[4];
-    bool ok[4];
+    const bool pok[2] = {pc[0] < OH, pc[1] != pc[0] && pc[1] < OH};
+    const size_t prow[2] = {((size_t)n * OH + pc[0]) * OW, ((size_t)n * OH + pc[1]) * OW};
+    __nv_bfloat16* drow = dx + (size_t)row * W * C;
+    for (int item = threadIdx.x; item < (W << cshift); item += blockDim.x) {
+      const int w = item >> cshift;
+      const int v = item & (cvec - 1);
+      const int qc[2] = {w >> 1, (w + 1) >> 1};
+      const bool qok[2] = {qc[0] < OW, qc[1] != qc[0] && qc[1] < OW};
+      uint2 pk[4];
+      uint4 gv[4];
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < 2; ++a) {
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int k = a * 2 + b;
-        ok[k] = pc[a] < OH && qc[b] < OW && (a == 0 || pc[1] != pc[0]) && (b == 0 || qc[1] != qc[0]);
-        if (ok[k]) {
-          const long o = ((((long)n * OH + pc[a]) * OW + qc[b]) * cvec + v) * 8;
-          pk[k] = __ldg(reinterpret_cast<const uint2*>(idx + o));
-          gv[k] = __ldg(reinterpret_cast<const uint4*>(dy + o));
-        }
-      }
-    }
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int k = a * 2 + b;
-        if (ok[k]) {
-          const int tap = (h - 2 * pc[a] + 1) * 3 + (w - 2 * qc[b] + 1);
-          float g[8];
-          unpack8(gv[k], g);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int bsel = (j < 4 ? (pk[k].x >> (8 * j)) : (pk[k].y >> (8 * (j - 4)))) & 0xff;
-            if (bsel == tap) acc[j] += g[j];
+        for (int b = 0; b < 2; ++b) {
+          if (pok[a] && qok[b]) {
+            const size_t o = (((prow[a] + qc[b]) << cshift) + v) * 8;
+            pk[a * 2 + b] = __ldg(reinterpret_cast<const uint2*>(idx + o));
+            gv[a * 2 + b] = __ldg(reinterpret_cast<const uint4*>(dy + o));
           }
         }
       }
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (pok[a] && qok[b]) {
+            const int k = a * 2 + b;
+            const uint32_t tap = (h - 2 * pc[a] + 1) * 3 + (w - 2 * qc[b] + 1);
+            float g[8];
+            unpack8(gv[k], g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t bsel = ((j < 4 ? (pk[k].x >> (8 * j)) : (pk[k].y >> (8 * (j - 4)))) & 0xffu);
+              if (bsel == tap) acc[j] += g[j];
+            }
+          }
+        }
+      }
+      stg_stream(drow + (size_t)item * 8, pack8(acc));
     }
-    stg_stream(dx + i * 8, pack8(acc));
   }
 }
 
@@ -604,56 +607,64 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
 __global__ void __launch_bounds__(256)
 bn_act_maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, BnFinalizeArgs f,
                           __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx, int N, int H,
-                          int W, int C, int OH, int OW, float count, float eps, float momentum,
-                          int act, float slope) {
+                          int W, int C, int OH, int OW, int cshift, float count, float eps,
+                          float momentum, int act, float slope) {
   griddep_launch();
   griddep_wait();
-  const int cvec = C >> 3;
-  // blockDim and the grid stride are multiples of cvec: a thread keeps its 8 channels
-  const int v = threadIdx.x % cvec;
+  const int cvec = 1 << cshift;
+  // blockDim is a multiple of cvec: a thread keeps its 8 channels across items
+  const int v = threadIdx.x & (cvec - 1);
   float sc[8], sh[8];
   bn_derive(f.stats, f.gamma, f.beta, f.running_mean, f.running_var, f.mean_invstd, f.scale_shift,
             C, v * 8, count, eps, momentum, blockIdx.x == 0 && threadIdx.x < cvec, sc, sh);
-  const long total = (long)N * OH * OW * cvec;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    long t = i / cvec;
-    const int q = (int)(t % OW); t /= OW;
-    const int p = (int)(t % OH);
-    const int n = (int)(t / OH);
-    uint4 raw[9];
-    bool ok[9];
+  // one block per output row (n, p): 32-bit index math only
+  for (int row = blockIdx.x; row < N * OH; row += gridDim.x) {
+    const int n = row / OH;
+    const int p = row - n * OH;
+    const __nv_bfloat16* xin[3];
+    bool hok[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int h = p * 2 - 1 + r, w = q * 2 - 1 + s;
-        ok[r * 3 + s] = h >= 0 && h < H && w >= 0 && w < W;
-        if (ok[r * 3 + s])
-          raw[r * 3 + s] = __ldg(reinterpret_cast<const uint4*>(x + (((long)n * H + h) * W + w) * C + v * 8));
-      }
+      const int h = p * 2 - 1 + r;
+      hok[r] = h >= 0 && h < H;
+      xin[r] = x + ((size_t)n * H + (hok[r] ? h : 0)) * W * C + v * 8;
     }
-    float best[8];
-    int bi[8];
+    for (int item = threadIdx.x; item < (OW << cshift); item += blockDim.x) {
+      const int q = item >> cshift;
+      uint4 raw[9];
+      bool ok[9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+      for (int r = 0; r < 3; ++r) {
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      if (!ok[k]) continue;
-      float fv[8];
-      unpack8(raw[k], fv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float o = __bfloat162float(__float2bfloat16(act_fwd(fmaf(fv[j], sc[j], sh[j]), act, slope)));
-        if (o > best[j]) { best[j] = o; bi[j] = k; }
+        for (int s = 0; s < 3; ++s) {
+          const int w = q * 2 - 1 + s;
+          ok[r * 3 + s] = hok[r] && w >= 0 && w < W;
+          if (ok[r * 3 + s]) raw[r * 3 + s] = __ldg(reinterpret_cast<const uint4*>(xin[r] + (size_t)w * C));
+        }
       }
-    }
-    stg_stream(y + i * 8, pack8(best));
-    if (idx != nullptr) {
-      uint2 pk;
-      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+      float best[8];
+      int bi[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        if (!ok[k]) continue;
+        float fv[8];
+        unpack8(raw[k], fv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float o = __bfloat162float(__float2bfloat16(act_fwd(fmaf(fv[j], sc[j], sh[j]), act, slope)));
+          if (o > best[j]) { best[j] = o; bi[j] = k; }
+        }
+      }
+      const size_t o8 = ((size_t)row * OW << cshift) * 8 + (size_t)item * 8;
+      stg_stream(y + o8, pack8(best));
+      if (idx != nullptr) {
+        uint2 pk;
+        pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+        *reinterpret_cast<uint2*>(idx + o8) = pk;
+      }
     }
   }
 }
@@ -941,14 +952,22 @@ extern "C" int sib_maxpool3x3s2_fwd(const void* x, void* y, void* idx, int N, in
   return 0;
 }
 
+static int log2_exact(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return (1 << s) == v ? s : -1;
+}
+
 extern "C" int sib_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W,
                                     int C, void* stream) {
-  SIB_CHECK(C % 8 == 0, "maxpool: C %% 8 != 0");
+  const int cshift = C % 8 == 0 ? log2_exact(C / 8) : -1;
+  SIB_CHECK(cshift >= 0, "maxpool_bwd: C/8 must be a power of two (got C=%d)", C);
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-  const long total = (long)N * H * W * (C / 8);
-  SIB_CUDA(launch_pdl(maxpool_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream), static_cast<const __nv_bfloat16*>(dy), static_cast<const uint8_t*>(idx),
-      static_cast<__nv_bfloat16*>(dx), N, H, W, C, OH, OW));
-  SIB_LAUNCH_CHECK();
+  int grid = N * H;
+  if (grid > sm_count() * 64) grid = sm_count() * 64;
+  SIB_CUDA(launch_pdl(maxpool_bwd_kernel, dim3(grid), dim3(256), 0, ST(stream),
+                      static_cast<const __nv_bfloat16*>(dy), static_cast<const uint8_t*>(idx),
+                      static_cast<__nv_bfloat16*>(dx), N, H, W, C, OH, OW, cshift));
   return 0;
 }
 
@@ -958,14 +977,16 @@ extern "C" int sib_bn_act_maxpool3x3s2_fwd(const void* x, const float* stats, co
                                            float* scale_shift, void* y, void* idx, int N, int H,
                                            int W, int C, double count, float eps, float momentum,
                                            int act, float slope, void* stream) {
-  SIB_CHECK(C % 8 == 0 && 256 % (C / 8) == 0, "bn_act_maxpool: C/8 must divide 256 (got C=%d)", C);
+  const int cshift = C % 8 == 0 ? log2_exact(C / 8) : -1;
+  SIB_CHECK(cshift >= 0 && cshift <= 8, "bn_act_maxpool: C/8 must be a power of two <= 256 (got C=%d)", C);
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-  const long total = (long)N * OH * OW * (C / 8);
+  int grid = N * OH;
+  if (grid > sm_count() * 64) grid = sm_count() * 64;
   BnFinalizeArgs f{stats, gamma, beta, running_mean, running_var, mean_invstd, scale_shift};
-  SIB_CUDA(launch_pdl(bn_act_maxpool_fwd_kernel, dim3(ew_grid(total, 256)), dim3(256), 0, ST(stream),
+  SIB_CUDA(launch_pdl(bn_act_maxpool_fwd_kernel, dim3(grid), dim3(256), 0, ST(stream),
                       static_cast<const __nv_bfloat16*>(x), f, static_cast<__nv_bfloat16*>(y),
-                      static_cast<uint8_t*>(idx), N, H, W, C, OH, OW, (float)count, eps, momentum,
-                      act, slope));
+                      static_cast<uint8_t*>(idx), N, H, W, C, OH, OW, cshift, (float)count, eps,
+                      momentum, act, slope));
   return 0;
 }
 

@@ -4,6 +4,8 @@ Activations are torch tensors of logical shape [N, C, H, W], dtype bfloat16, in
 torch.channels_last memory format (= NHWC in memory).  Conv filters are [K, C, R, S]
 channels_last (= KRSC in memory).  PyTorch is only the allocator / stream provider here.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -83,6 +85,21 @@ class _AccPool:
 
 
 _ACC_POOL = _AccPool()
+_DEBUG_POOL = os.environ.get("SIB_DEBUG_POOL", "0") == "1"
+_DIRTY = []
+
+
+def _report_dirty():
+    bad = [(int(n), off, rows, c, tb) for n, off, rows, c, tb in _DIRTY if int(n) != 0]
+    print("ACC POOL: %d slices checked, %d dirty" % (len(_DIRTY), len(bad)))
+    for n, off, rows, c, tb in bad[:5]:
+        print("dirty slice: %d non-zeros, end offset %d, shape [%d,%d]\n%s" % (n, off, rows, c, tb))
+
+
+if _DEBUG_POOL:
+    import atexit
+    atexit.register(_report_dirty)
+_USE_POOL = os.environ.get("SIB_ACC_POOL", "1") != "0"
 
 
 def begin_pass(device):
@@ -93,7 +110,11 @@ def begin_pass(device):
 def new_acc(rows, c, device):
     """[rows, c] fp32 accumulator: a pre-zeroed pool slice when available (the kernels then skip
     their own memset), else an uninitialised tensor the kernel zeroes itself."""
-    t = _ACC_POOL.take(rows, c, device)
+    t = _ACC_POOL.take(rows, c, device) if _USE_POOL else None
+    if t is not None and _DEBUG_POOL and not torch.cuda.is_current_stream_capturing():
+        # asynchronous check (keeps the GPU timeline dense): count non-zeros now, report at exit
+        import traceback
+        _DIRTY.append(((t != 0).sum(), _ACC_POOL.off, rows, c, "".join(traceback.format_stack(limit=4)[:-1])))
     return t if t is not None else torch.empty((rows, c), dtype=torch.float32, device=device)
 
 
