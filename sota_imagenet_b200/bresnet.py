@@ -434,6 +434,7 @@ class BResNet(SibModule):
     def _after_block_backward(self, block_index):
         cb = getattr(self, "_block_bwd_cb", None)
         if cb is not None:
+            ops.side_join()      # the block's weight gradients (side stream) must be complete
             cb(block_index)
 
 

@@ -112,6 +112,7 @@ class ResNet(SibModule):
         """Hook point for the data-parallel wrapper (bucketed gradient all-reduce)."""
         cb = getattr(self, "_block_bwd_cb", None)
         if cb is not None:
+            ops.side_join()      # the block's weight gradients (side stream) must be complete
             cb(block_index)
 
     # checkpoints written by torchvision have fc.weight [1000, 2048]; ours may be padded

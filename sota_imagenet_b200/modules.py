@@ -92,6 +92,7 @@ class SibModule(nn.Module):
             ops.begin_pass(a.device)
 
     def _end_backward(self):
+        ops.side_join()
         for h in self._bwd_hooks:
             h(self)
 
@@ -158,7 +159,8 @@ class Conv2d(SibModule):
                                 self.padding, out=out, residual=residual, bn_bwd=bn_bwd)
 
     def run_wgrad(self, x, dy):
-        ops.conv2d_wgrad(x, dy, self._grad(self.weight), self.stride, self.padding)
+        dw = self._grad(self.weight)
+        ops.side_launch(lambda: ops.conv2d_wgrad(x, dy, dw, self.stride, self.padding), x, dy)
 
     def fwd(self, x, train):
         return self.run(x), (x,)

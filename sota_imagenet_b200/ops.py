@@ -118,6 +118,46 @@ def new_acc(rows, c, device):
     return t if t is not None else torch.empty((rows, c), dtype=torch.float32, device=device)
 
 
+class _SideStream:
+    """Weight-gradient kernels have no consumer until the optimizer (or the gradient all-reduce of
+    their block), so they run on a second stream: the tensor-core-bound wgrad then overlaps the
+    HBM-bound BatchNorm-backward kernels and the head / tail of the dgrad that follow on the main
+    stream.  Inputs are kept alive until the join (no allocator stream bookkeeping, graph-capture
+    safe: the fork / join become parallel branches of the captured graph)."""
+    enabled = os.environ.get("SIB_WGRAD_STREAM", "1") != "0"
+    streams = {}
+    keep = []
+    forked = False
+
+
+def side_launch(fn, *tensors):
+    """Run fn() (kernel launches reading `tensors`) on the side stream, ordered after everything
+    enqueued so far on the current stream."""
+    if not _SideStream.enabled:
+        fn()
+        return
+    main = torch.cuda.current_stream()
+    side = _SideStream.streams.get(main.device)
+    if side is None:
+        side = _SideStream.streams[main.device] = torch.cuda.Stream(device=main.device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        fn()
+    _SideStream.keep.extend(tensors)
+    _SideStream.forked = True
+
+
+def side_join():
+    """Make the current stream wait for the side stream; drops the keep-alive references."""
+    if _SideStream.forked:
+        main = torch.cuda.current_stream()
+        side = _SideStream.streams.get(main.device)
+        if side is not None:
+            main.wait_stream(side)
+        _SideStream.forked = False
+    _SideStream.keep.clear()
+
+
 def conv_out_hw(h, w, r, s, stride, pad):
     return (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
 
