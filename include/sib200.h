@@ -38,6 +38,8 @@ extern "C" {
 #define SIB_FLAG_TILE_N128 2    /* cap the N tile at 128 columns (tuning / testing)       */
 #define SIB_FLAG_NO_2CTA 4      /* never use the cta_group::2 kernel (tuning / testing)   */
 #define SIB_FLAG_STATS_ZEROED 8 /* `stats` / `sums` already hold zeros: skip the memset    */
+#define SIB_FLAG_FORCE_HALO 16  /* 3x3/s1/p1: use the halo-reuse kernel whenever it applies */
+#define SIB_FLAG_NO_HALO 32     /* never use the halo-reuse kernel (tuning / testing)       */
 #define SIB_ACT_FLAG_PREZEROED 0x100 /* or-ed into sib_bn_bwd_reduce's `act`: `sums` already zero */
 
 const char* sib_last_error(void);

@@ -118,6 +118,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Warp-converged wait: every lane polls, the loop condition is a warp vote and therefore
+// provably uniform, so code after the wait stays on the uniform datapath (used by the
+// MMA-issuing warps together with the *_w instruction wrappers below).
+__device__ __forceinline__ void mbar_wait_w(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!__any_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
 // ----------------------------------------------------------------------------
 // programmatic dependent launch (see launch_pdl in host.h)
 // ----------------------------------------------------------------------------
@@ -150,6 +160,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 // im2col-mode load of an NHWC tensor: (c, w, h, n) is the base pixel, (off_w, off_h)
@@ -231,6 +249,29 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
+// Warp-converged variants: ALL 32 lanes of the issuing warp execute these with identical
+// operands and one elected lane issues the instruction.  Keeping the issue loop converged lets
+// ptxas keep descriptors in uniform registers; issuing from inside `if (lane == 0)` instead makes
+// it wrap every tcgen05.mma in an ELECT / BRA.U.ANY serialisation loop plus R2UR moves, which
+// made the single issuing thread the bottleneck of the N = 64 kernels (~115 clk per MMA).
+__device__ __forceinline__ void umma_bf16_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -302,6 +343,26 @@ __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
       "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// warp-converged variants (see umma_bf16_ss_w)
+__device__ __forceinline__ void umma2_bf16_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n\t}" ::"r"(smem_u32(bar)),
       "h"((uint16_t)3)
       : "memory");
 }

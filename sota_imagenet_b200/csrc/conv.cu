@@ -86,6 +86,14 @@ __device__ __forceinline__ void igemm_epilogue(
   const uint32_t st_off1 = st_row * 128 + ((st_slot ^ (st_row + 4)) << 4);
   const bool fused = AUX > 0 && p.fuse != 0;
   const int n_loads = (p.has_residual ? 1 : 0) + (fused ? p.fuse : 0);
+  // One n-tile per launch (Cout <= BN, all the 56x56 layers): every tile of this CTA covers the
+  // same columns, so the per-channel sums are accumulated in this warp's s_part slots for the
+  // whole kernel and published once at the end -- no named barrier and no 2*BN atomics per tile.
+  const bool cta_sums = p.stats != nullptr && p.num_n_tiles == 1;
+  if (cta_sums) {
+    for (int i = lane; i < 2 * kPartStride; i += 32) s_part[e * 2 * kPartStride + i] = 0.f;
+    __syncwarp();
+  }
   int acc = 0;
   uint32_t acc_phase = 0;
   uint32_t res_phase = 0;
@@ -251,10 +259,18 @@ __device__ __forceinline__ void igemm_epilogue(
         if (lane < 8) {
           float4* d1 = reinterpret_cast<float4*>(&s_part[(e * 2 + 0) * kPartStride + ci * 64 + lane * 8]);
           float4* d2 = reinterpret_cast<float4*>(&s_part[(e * 2 + 1) * kPartStride + ci * 64 + lane * 8]);
-          d1[0] = make_float4(cs1[0].x, cs1[0].y, cs1[1].x, cs1[1].y);
-          d1[1] = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
-          d2[0] = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
-          d2[1] = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
+          float4 a0 = make_float4(cs1[0].x, cs1[0].y, cs1[1].x, cs1[1].y);
+          float4 a1 = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
+          float4 b0 = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
+          float4 b1 = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
+          if (cta_sums) {     // running totals of this warp (its own slots: no other writer)
+            const float4 p0 = d1[0], p1 = d1[1], q0 = d2[0], q1 = d2[1];
+            a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
+            a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
+            b0.x += q0.x; b0.y += q0.y; b0.z += q0.z; b0.w += q0.w;
+            b1.x += q1.x; b1.y += q1.y; b1.z += q1.z; b1.w += q1.w;
+          }
+          d1[0] = a0; d1[1] = a1; d2[0] = b0; d2[1] = b1;
         }
       }
     }
@@ -266,7 +282,7 @@ __device__ __forceinline__ void igemm_epilogue(
         else mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
-    if (p.stats != nullptr) {
+    if (p.stats != nullptr && !cta_sums) {
       // combine the four row-quarters of each column and publish; s_part is reused next tile
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       for (int c = et; c < BN; c += 32 * kEpiWarps) {
@@ -286,6 +302,23 @@ __device__ __forceinline__ void igemm_epilogue(
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     }
     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+  if (cta_sums) {
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    for (int c = et; c < BN; c += 32 * kEpiWarps) {
+      if (c < p.Cout) {
+        const int chunk = c >> 6;
+        const int h = chunk % kHalves, ci = chunk / kHalves, lc = ci * 64 + (c & 63);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a += s_part[((h * 4 + q) * 2 + 0) * kPartStride + lc];
+          b += s_part[((h * 4 + q) * 2 + 1) * kPartStride + lc];
+        }
+        atomicAdd(p.stats + c, a);
+        atomicAdd(p.stats + p.Cout + c, b);
+      }
+    }
   }
   if (lane == 0) tma_store_wait_read<0>();
 }
@@ -393,35 +426,33 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---- MMA issuer ----
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+    // ---- MMA issuer: the whole warp runs the loop converged, one elected lane issues ----
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), 16, 1024, kSwizzle128B);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), 16, 1024, kSwizzle128B);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait_w(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        mbar_wait_w(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint64_t a_desc =
-              umma_smem_desc(smem_u32(smem_a + stage * kABytes), 16, 1024, kSwizzle128B);
-          const uint64_t b_desc =
-              umma_smem_desc(smem_u32(smem_b + stage * kBBytes), 16, 1024, kSwizzle128B);
+        const uint64_t a_desc = a_desc0 + (uint32_t)(stage * (kABytes >> 4));
+        const uint64_t b_desc = b_desc0 + (uint32_t)(stage * (kBBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes along K inside the 128B swizzle row = +2 in 16-byte address units
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int k = 0; k < kBK / 16; ++k) {
+          // +32 bytes along K inside the 128B swizzle row = +2 in 16-byte address units
+          umma_bf16_ss_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit(&tmem_full_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        umma_commit_w(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      umma_commit_w(&tmem_full_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     igemm_epilogue<BN, SLABS, AUX, false>(&tmOut, &tmRes, &tmAux1, &tmAux2, p, smem_slab, smem_aux,
@@ -542,33 +573,33 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---- MMA issuer (leader CTA only) ----
+    if (leader) {
+      // ---- MMA issuer (leader CTA only): whole warp converged, one elected lane issues ----
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kBM, BN, 0, 0);
+      const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), 16, 1024, kSwizzle128B);
+      const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), 16, 1024, kSwizzle128B);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
+        mbar_wait_w(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_w(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t a_desc =
-              umma_smem_desc(smem_u32(smem_a + stage * kABytes), 16, 1024, kSwizzle128B);
-          const uint64_t b_desc =
-              umma_smem_desc(smem_u32(smem_b + stage * kBBytes), 16, 1024, kSwizzle128B);
+          const uint64_t a_desc = a_desc0 + (uint32_t)(stage * (kABytes >> 4));
+          const uint64_t b_desc = b_desc0 + (uint32_t)(stage * (kBBytes >> 4));
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // +32 bytes along K inside the 128B swizzle row = +2 in 16-byte address units
-            umma2_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma2_bf16_ss_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma2_commit_multicast(&empty_bar[stage]);
+          umma2_commit_multicast_w(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma2_commit_multicast(&tmem_full_bar[acc]);
+        umma2_commit_multicast_w(&tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -582,6 +613,357 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 with shared-memory halo reuse
+// ----------------------------------------------------------------------------
+// The im2col kernel above fetches every input pixel nine times from L2 (once per filter tap), and
+// the 64- and 128-channel 3x3 layers at 56x56 / 28x28 are bound by exactly that L2 -> SM traffic
+// (profiles/r01_ncu_conv_layers_metrics.txt: 8-10 TB/s against a ~10.5 TB/s fabric ceiling, tensor
+// pipe 17-32 %).  Here a CTA loads, per 64 input channels, ONE zero-padded pixel region
+// [TH+2 rows][W+2 columns] (two im2col TMA loads over a bounding box one pixel larger than the
+// image on every side; the border is zero-filled), and every tap is the same region shifted by (r * (W+2) + s) rows of 128 bytes: the 128B swizzle
+// is a function of the absolute shared-memory address, so a K-major UMMA descriptor may start at
+// any 128-byte row (scripts/probes/umma_shift_probe.cu, measured exact for arbitrary shifts).
+// GEMM row j of a tile is the padded position (j / (W+2), j % (W+2)); positions with column >= W
+// are junk rows that the epilogue drops (W = 56: 112 of 128 rows useful).  With 64 -> 64 channels
+// the nine weight k-blocks (72 KB) stay resident in shared memory for the whole kernel.
+struct HaloParams {
+  int N, H, W, Cin, Cout;
+  int pitch;          // W + 2
+  int tile_h;         // output rows per tile: floor(128 / pitch)
+  int num_h_tiles;    // ceil(H / tile_h)
+  int num_n_tiles;
+  int cin_blocks;
+  int a_bytes;        // bytes of one region load: pitch * (tile_h + 2) * 128
+  int b_stationary;   // all weight k-blocks fit the ring: load them once
+  float* stats;       // [2][Cout] (fprop: sum, sumsq; fused BN backward: sum g, sum g*xhat) or null
+  int fuse;           // 1: fused BN-backward reduction (see IgemmParams)
+  int fuse_act;
+  float fuse_slope;
+  const __nv_bfloat16* aux;    // [N][H][W][Cout] mask / xhat source
+  const float* mask_ss;
+  const float* mean_invstd;
+};
+
+constexpr int kHaloAStage = 32768;   // region of up to 256 rows x 128 bytes
+
+template <int BN, int BSTAGES, int kHaloAStages>
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+halo3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               __nv_bfloat16* __restrict__ out, const HaloParams p) {
+  constexpr int kBBytes = BN * kBK * 2;
+  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr int kGroups = BN == 64 ? 2 : 1;     // epilogue warp groups working on alternate tiles
+  constexpr int kEpiWarps = 8;
+  constexpr int kWarpsPerAcc = 8 / kGroups;     // warps that drain one accumulator stage
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t a_full[kHaloAStages], a_empty[kHaloAStages];
+  __shared__ uint64_t b_full[BSTAGES], b_empty[BSTAGES];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kHaloAStages * kHaloAStage;
+  uint8_t* smem_slab = smem_b + BSTAGES * kBBytes;    // [epilogue warps][kSlabBytes]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.N * p.num_h_tiles * p.num_n_tiles;
+  const int num_kblocks = 9 * p.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kHaloAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kWarpsPerAcc); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&tmem_base_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  griddep_launch();
+  griddep_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- TMA producer: one region per (tile, 64 input channels), one weight k-block per tap ----
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles;
+        const int n0 = (tile - mt * p.num_n_tiles) * BN;
+        const int n_img = mt / p.num_h_tiles;
+        const int h0 = (mt - n_img * p.num_h_tiles) * p.tile_h;
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          mbar_wait(&a_empty[a_stage], a_phase ^ 1);
+          // The padded region is fetched as two im2col loads of 128 consecutive padded positions
+          // (bounding box = image + 1 pixel of zero-filled border on every side, so the
+          // traversal pitch is W + 2).  The second load may run past the region; those rows only
+          // feed junk outputs.  (A tiled 4-D box of the same region measured 7x slower per row.)
+          int h1 = h0 - 1 + 128 / p.pitch, w1 = -1 + 128 % p.pitch, n1 = n_img;
+          if (h1 > p.H) { h1 -= p.H + 2; ++n1; }
+          const bool second = n1 < p.N;
+          mbar_arrive_expect_tx(&a_full[a_stage], second ? 2 * kABytes : kABytes);
+          uint8_t* dst = smem_a + a_stage * kHaloAStage;
+          tma_load_im2col_4d(dst, &tmA, &a_full[a_stage], cb * kBK, -1, h0 - 1, n_img, 0, 0);
+          if (second)
+            tma_load_im2col_4d(dst + kABytes, &tmA, &a_full[a_stage], cb * kBK, w1, h1, n1, 0, 0);
+          if (++a_stage == kHaloAStages) { a_stage = 0; a_phase ^= 1; }
+          if (!p.b_stationary || first) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[b_stage], b_phase ^ 1);
+              mbar_arrive_expect_tx(&b_full[b_stage], kBBytes);
+              tma_load_2d(smem_b + b_stage * kBBytes, &tmB, &b_full[b_stage],
+                          tap * p.Cin + cb * kBK, n0);
+              if (++b_stage == BSTAGES) { b_stage = 0; b_phase ^= 1; }
+            }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: the whole warp runs the loop converged, one elected lane issues ----
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    // tap (r, s) = the region shifted by r * pitch + s pixel rows of 128 bytes (16-byte units)
+    uint32_t tap_off[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((tap / 3) * p.pitch + (tap % 3)) * 8;
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), 16, 1024, kSwizzle128B);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), 16, 1024, kSwizzle128B);
+    int a_stage = 0, b_stage = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if (p.b_stationary) {
+      // the weight k-blocks are loaded once and never released
+      for (int kb = 0; kb < num_kblocks; ++kb) mbar_wait_w(&b_full[kb], 0);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait_w(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        mbar_wait_w(&a_full[a_stage], a_phase);
+        tc_fence_after();
+        const uint64_t a_desc = a_desc0 + (uint32_t)(a_stage * (kHaloAStage >> 4));
+        if (p.b_stationary) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t ad = a_desc + tap_off[tap];
+            const uint64_t bd = b_desc0 + (uint32_t)((cb * 9 + tap) * (kBBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ss_w(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (cb | tap | k) != 0);
+          }
+        } else {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait_w(&b_full[b_stage], b_phase);
+            tc_fence_after();
+            const uint64_t ad = a_desc + tap_off[tap];
+            const uint64_t bd = b_desc0 + (uint32_t)(b_stage * (kBBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ss_w(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (cb | tap | k) != 0);
+            umma_commit_w(&b_empty[b_stage]);
+            if (++b_stage == BSTAGES) { b_stage = 0; b_phase ^= 1; }
+          }
+        }
+        umma_commit_w(&a_empty[a_stage]);
+        if (++a_stage == kHaloAStages) { a_stage = 0; a_phase ^= 1; }
+      }
+      umma_commit_w(&tmem_full_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+    // ---- epilogue: TMEM -> bf16 slab -> column-owner pass (statistics / fused BN backward,
+    //      junk-row removal) -> coalesced 128-bit global stores.
+    // BN = 64: two groups of four warps take alternate tiles (group g owns accumulator stage g),
+    // so two epilogues are in flight and their latency no longer bounds the tile rate.
+    // BN = 128: one group of eight warps, warp e handles 64-column chunk e / 4.
+    // The per-channel sums stay in registers across all tiles of the CTA (one n-tile per launch)
+    // and are published once at the end.
+    const int e = warp - 4;
+    const int quarter = e & 3;
+    const int group = kGroups == 2 ? (e >> 2) : 0;
+    const int chunk = kGroups == 2 ? 0 : (e >> 2);
+    uint8_t* slab = smem_slab + e * kSlabBytes;
+    uint32_t row_slot[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) row_slot[g] = lane * 128 + ((g ^ (lane & 7)) << 4);
+    const int st_row = lane >> 3, st_slot = lane & 7;
+    const uint32_t st_off0 = st_row * 128 + ((st_slot ^ st_row) << 4);
+    const uint32_t st_off1 = st_row * 128 + ((st_slot ^ (st_row + 4)) << 4);
+    // padded position of the 8 rows this lane handles in the column-owner pass
+    int rel_m[8], rel_h[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int j = quarter * 32 + it * 4 + st_row;
+      const int hh = j / p.pitch;
+      const int ww = j - hh * p.pitch;
+      rel_h[it] = hh;
+      rel_m[it] = (ww < p.W && hh < p.tile_h) ? hh * p.W + ww : -1;
+    }
+    const bool fused = p.fuse != 0;
+    const int cbase = chunk * 64 + st_slot * 8;       // (num_n_tiles == 1: n0 = 0)
+    const bool col_ok = cbase < p.Cout;
+    float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; mu[j] = 0.f; is[j] = 0.f; }
+    if (fused && col_ok) {
+      if (p.mask_ss != nullptr) {
+        load8f(p.mask_ss + cbase, sc);
+        load8f(p.mask_ss + p.Cout + cbase, sh);
+      }
+      load8f(p.mean_invstd + cbase, mu);
+      load8f(p.mean_invstd + p.Cout + cbase, is);
+    }
+    const bool do_mask = p.fuse_act != SIB_ACT_NONE;
+    const float neg = p.fuse_act == SIB_ACT_LEAKY ? p.fuse_slope : 0.f;
+    float2 cs1[4], cs2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cs1[j] = make_float2(0.f, 0.f); cs2[j] = make_float2(0.f, 0.f); }
+    const int acc = group;                    // kGroups == 1: alternates below
+    int acc1 = 0;
+    uint32_t acc_phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      if (kGroups == 2 && (local & 1) != group) continue;
+      const int a = kGroups == 2 ? acc : acc1;
+      const int mt = tile / p.num_n_tiles;
+      const int n_img = mt / p.num_h_tiles;
+      const int h0 = (mt - n_img * p.num_h_tiles) * p.tile_h;
+      const int rows_here = p.H - h0;                   // rows of this tile that exist
+      const size_t m_base = ((size_t)n_img * p.H + h0) * p.W;
+      mbar_wait(&tmem_full_bar[a], acc_phase);
+      tc_fence_after();
+      uint32_t r[64];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + a * BN + chunk * 64;
+      tmem_ld_32x32b_x32(taddr, r);
+      tmem_ld_32x32b_x32(taddr + 32, r + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[a]);
+      {
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j]);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(slab + row_slot[g]) = pack8(&v[g * 8]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const bool ok = rel_m[it] >= 0 && rel_h[it] < rows_here && col_ok;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (ok) q = *reinterpret_cast<const uint4*>(slab + it * 512 + ((it & 1) ? st_off1 : st_off0));
+        const size_t o = (m_base + (ok ? rel_m[it] : 0)) * p.Cout + cbase;
+        if (fused) {
+          float g[8], xv[8];
+          unpack8(q, g);
+          uint4 xa = make_uint4(0, 0, 0, 0);
+          if (ok) xa = __ldg(reinterpret_cast<const uint4*>(p.aux + o));
+          unpack8(xa, xv);
+          if (do_mask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float z = fmaf(xv[j], sc[j], sh[j]);
+              g[j] = z > 0.f ? g[j] : g[j] * neg;
+            }
+            q = pack8(g);
+          }
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 gg = make_float2(g[2 * j], g[2 * j + 1]);
+              const float2 xh = make_float2((xv[2 * j] - mu[2 * j]) * is[2 * j],
+                                            (xv[2 * j + 1] - mu[2 * j + 1]) * is[2 * j + 1]);
+              cs1[j] = __fadd2_rn(cs1[j], gg);
+              cs2[j] = __ffma2_rn(gg, xh, cs2[j]);
+            }
+          }
+        } else if (p.stats != nullptr) {
+          const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(hq[j]);
+            cs1[j] = __fadd2_rn(cs1[j], f);
+            cs2[j] = __ffma2_rn(f, f, cs2[j]);
+          }
+        }
+        if (ok) *reinterpret_cast<uint4*>(out + o) = q;
+      }
+      __syncwarp();     // the slab is rewritten by this warp's next tile
+      if (kGroups == 2) {
+        acc_phase ^= 1;
+      } else if (++acc1 == 2) {
+        acc1 = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (p.stats != nullptr) {
+      // lanes with equal lane%8 hold partial sums of the same 8 columns (different rows)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          float2 t1, t2;
+          t1.x = __shfl_xor_sync(0xffffffffu, cs1[j].x, o);
+          t1.y = __shfl_xor_sync(0xffffffffu, cs1[j].y, o);
+          t2.x = __shfl_xor_sync(0xffffffffu, cs2[j].x, o);
+          t2.y = __shfl_xor_sync(0xffffffffu, cs2[j].y, o);
+          cs1[j] = __fadd2_rn(cs1[j], t1);
+          cs2[j] = __fadd2_rn(cs2[j], t2);
+        }
+      }
+      // combine the eight warps in shared memory (the drained slabs), then ONE atomic per column
+      // and CTA: same-address atomics from all CTAs at once otherwise pile up at the kernel's end
+      float* part = reinterpret_cast<float*>(slab);     // this warp's own (drained) slab: [2][64]
+      if (lane < 8) {
+        float4* d1 = reinterpret_cast<float4*>(&part[lane * 8]);
+        float4* d2 = reinterpret_cast<float4*>(&part[64 + lane * 8]);
+        d1[0] = make_float4(cs1[0].x, cs1[0].y, cs1[1].x, cs1[1].y);
+        d1[1] = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
+        d2[0] = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
+        d2[1] = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int et = threadIdx.x - 128;
+      for (int idx = et; idx < 2 * BN; idx += 256) {
+        const int kind = idx / BN, c = idx - kind * BN;
+        const int ch = c >> 6, lc = c & 63;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+          if (kGroups == 2 || (w >> 2) == ch)
+            t += reinterpret_cast<const float*>(smem_slab + w * kSlabBytes)[kind * 64 + lc];
+        if (c < p.Cout) atomicAdd(p.stats + kind * p.Cout + c, t);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -697,29 +1079,28 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // both operands MN-major: 64-element groups along M/N are kUnitBytes apart (LBO),
-      // 8-pixel groups along K are 1024 bytes apart (SBO)
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BNC, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint64_t a_desc = umma_smem_desc(smem_u32(smem_a + stage * kABytesW), kUnitBytes,
-                                               1024, kSwizzle128B);
-        const uint64_t b_desc = umma_smem_desc(smem_u32(smem_b + stage * kBBytesW), kUnitBytes,
-                                               1024, kSwizzle128B);
+    // both operands MN-major: 64-element groups along M/N are kUnitBytes apart (LBO),
+    // 8-pixel groups along K are 1024 bytes apart (SBO).  Whole warp converged, one elected
+    // lane issues.
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BNC, 1, 1);
+    const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), kUnitBytes, 1024, kSwizzle128B);
+    const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), kUnitBytes, 1024, kSwizzle128B);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait_w(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint64_t a_desc = a_desc0 + (uint32_t)(stage * (kABytesW >> 4));
+      const uint64_t b_desc = b_desc0 + (uint32_t)(stage * (kBBytesW >> 4));
 #pragma unroll
-        for (int k = 0; k < kWgPix / 16; ++k) {
-          // 16 pixels along K = two 1024-byte groups = +128 in 16-byte address units
-          umma_bf16_ss(tmem_base, a_desc + 128 * k, b_desc + 128 * k, idesc, (i | k) != 0);
-        }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int k = 0; k < kWgPix / 16; ++k) {
+        // 16 pixels along K = two 1024-byte groups = +128 in 16-byte address units
+        umma_bf16_ss_w(tmem_base, a_desc + 128 * k, b_desc + 128 * k, idesc, (i | k) != 0);
       }
-      umma_commit(&tmem_full_bar);
+      umma_commit_w(&empty_bar[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    umma_commit_w(&tmem_full_bar);
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;   // out channel within the tile
@@ -827,6 +1208,24 @@ static int launch_igemm2(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t
   return 0;
 }
 
+template <int BN, int BSTAGES, int kHaloAStages>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, void* out, const HaloParams& p,
+                       cudaStream_t stream) {
+  constexpr int smem = kHaloAStages * kHaloAStage + BSTAGES * BN * kBK * 2 + 8 * kSlabBytes + 1024;
+  static_assert(smem + 512 <= 232448, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    SIB_CUDA(cudaFuncSetAttribute(halo3x3_kernel<BN, BSTAGES, kHaloAStages>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  int grid = p.N * p.num_h_tiles * p.num_n_tiles;
+  if (grid > sm_count()) grid = sm_count();
+  SIB_CUDA(launch_pdl(halo3x3_kernel<BN, BSTAGES, kHaloAStages>, dim3(grid), dim3(kIgemmThreads), smem, stream, tmA,
+                      tmB, static_cast<__nv_bfloat16*>(out), p));
+  return 0;
+}
+
 // Fused BatchNorm-backward reduction riding on a dgrad (see IgemmParams::fuse).
 struct BnBwdFuse {
   const void* aux1 = nullptr;        // mask source (and xhat source unless aux2 is given)
@@ -851,6 +1250,53 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
             "igemm: Cin must be a multiple of 64 (or of 8 for 1x1 filters), got %d", Cin);
   SIB_CHECK(Cout % 8 == 0, "igemm: Cout must be a multiple of 8 (got %d)", Cout);
   SIB_CHECK((long)N * TH * TW < (1l << 31), "igemm: too many pixels");
+  // 3x3 / stride 1 / pad 1 on 64 or 128 output channels at >= 28 pixel rows: halo-reuse kernel
+  {
+    const bool geometry = R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && TH == IH &&
+                          TW == IW && Cin % 64 == 0 && IW + 2 <= 63 && residual == nullptr &&
+                          bias == nullptr && (Cout == 64 || Cout == 128) &&
+                          (fuse == nullptr || fuse->aux2 == nullptr);
+    // measured (B200, batch 256): 64 -> 64 @ 56x56 0.166 -> 0.12 ms; 128 -> 128 @ 28x28 is slower
+    // than the im2col kernel (0.104 vs 0.092 ms: the streamed weight k-blocks dominate), so only
+    // the weight-stationary shape is picked automatically
+    const bool wanted = (flags & SIB_FLAG_FORCE_HALO) ||
+                        (IW >= 28 && Cin == 64 && Cout == 64 && !(flags & SIB_FLAG_NO_HALO));
+    if (geometry && wanted) {
+      HaloParams h{};
+      h.N = N; h.H = IH; h.W = IW; h.Cin = Cin; h.Cout = Cout;
+      h.pitch = IW + 2;
+      h.tile_h = 128 / h.pitch;
+      if (h.tile_h > IH) h.tile_h = IH;
+      h.num_h_tiles = (IH + h.tile_h - 1) / h.tile_h;
+      h.num_n_tiles = 1;
+      h.cin_blocks = Cin / 64;
+      h.a_bytes = h.pitch * (h.tile_h + 2) * 128;
+      h.stats = stats;
+      if (fuse != nullptr) {
+        SIB_CHECK(stats == nullptr && fuse->aux1 && fuse->mean_invstd && fuse->sums,
+                  "halo: fused BN backward needs aux1, mean_invstd and sums");
+        h.fuse = 1;
+        h.fuse_act = fuse->act;
+        h.fuse_slope = fuse->slope;
+        h.aux = static_cast<const __nv_bfloat16*>(fuse->aux1);
+        h.mask_ss = fuse->mask_ss;
+        h.mean_invstd = fuse->mean_invstd;
+        h.stats = fuse->sums;
+      }
+      CUtensorMap tmA, tmB;
+      if (int rc = make_tmap_im2col_bf16(&tmA, in, N, IH, IW, Cin, -1, -1, 1, 1, 1, 1, kBK, kBM, true)) return rc;
+      if (int rc = make_tmap_2d_bf16(&tmB, w, Cout, (uint64_t)9 * Cin, (uint64_t)9 * Cin, Cout, kBK, true))
+        return rc;
+      if (h.stats != nullptr && !(flags & SIB_FLAG_STATS_ZEROED))
+        SIB_CUDA(cudaMemsetAsync(h.stats, 0, sizeof(float) * 2 * Cout, stream));
+      if (Cout == 64) {
+        h.b_stationary = 9 * h.cin_blocks <= 9;
+        return launch_halo<64, 9, 3>(tmA, tmB, out, h, stream);
+      }
+      h.b_stationary = 0;
+      return launch_halo<128, 6, 2>(tmA, tmB, out, h, stream);
+    }
+  }
   IgemmParams p{};
   p.M_total = N * TH * TW;
   p.Cout = Cout;

@@ -115,6 +115,26 @@ int make_tmap_2d_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
   return 0;
 }
 
+int make_tmap_nhwc_tile_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, int C,
+                             uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+  std::call_once(g_once, resolve);
+  SIB_CHECK(g_tiled != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  SIB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  SIB_CHECK((C * 2) % 16 == 0, "NHWC channel count must be a multiple of 8 for TMA");
+  SIB_CHECK(box_c == 64 && box_w <= 256 && box_h <= 256, "nhwc tile box %ux%ux%u unsupported", box_c,
+            box_w, box_h);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SIB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc tile) failed: %d", (int)r);
+  return 0;
+}
+
 int make_tmap_kchunk_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
                           uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_kchunks) {
   std::call_once(g_once, resolve);

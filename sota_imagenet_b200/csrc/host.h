@@ -59,6 +59,11 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
 int make_tmap_2d_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
                      uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
 
+// Tiled 4-D map over an NHWC bf16 tensor, dims (C, W, H, N); box = box_c channels x box_w x box_h
+// pixels of one image, 128B swizzle, out-of-bounds pixels (halo) read as zeros.
+int make_tmap_nhwc_tile_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, int C,
+                             uint32_t box_c, uint32_t box_w, uint32_t box_h);
+
 // 3-D view used for the no-swizzle K-major "core matrix" layout:
 // dims (inner=8 elems, rows, kchunks) with strides (1, row_stride, 8) elements.
 int make_tmap_kchunk_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,

@@ -21,6 +21,8 @@ FLAG_FORCE_IM2COL = 1
 FLAG_TILE_N128 = 2
 FLAG_NO_2CTA = 4
 FLAG_STATS_ZEROED = 8
+FLAG_FORCE_HALO = 16
+FLAG_NO_HALO = 32
 ACT_FLAG_PREZEROED = 0x100
 ACT_CODES = {None: ACT_NONE, "identity": ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU,
              "leaky_relu": ACT_LEAKY}
