@@ -15,6 +15,7 @@ SHAPES = [(64,64,56,1,1,0,1),(64,64,56,3,1,1,3),(64,256,56,1,1,0,4),(256,64,56,1
           (512,256,28,1,1,0,1),(256,256,28,3,2,1,1),(256,1024,14,1,1,0,6),(512,1024,28,1,2,0,1),(1024,256,14,1,1,0,5),
           (256,256,14,3,1,1,5),(1024,512,14,1,1,0,1),(512,512,14,3,2,1,1),(512,2048,7,1,1,0,3),(1024,2048,14,1,2,0,1),
           (2048,512,7,1,1,0,2),(512,512,7,3,1,1,2)]
+FLAGS = int(os.environ.get("SIB_FLAGS", "0"))      # e.g. 2 = N tile capped at 128, 4 = no 2-CTA kernel
 profile = "--profile" in sys.argv
 only = [a for a in sys.argv[1:] if not a.startswith("--")]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
@@ -44,8 +45,8 @@ for (c, k, h, r, stride, pad, cnt) in SHAPES:
     y = ops.conv2d_fprop(x, w, stride=stride, pad=pad, stats=stats)
     dy = torch.randn_like(y)
     dw = torch.zeros(k, r, r, c, device="cuda").permute(0, 3, 1, 2)
-    fns = {"fprop": lambda: ops.conv2d_fprop(x, w, stride=stride, pad=pad, stats=stats),
-           "dgrad": lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad),
+    fns = {"fprop": lambda: ops.conv2d_fprop(x, w, stride=stride, pad=pad, stats=stats, flags=FLAGS),
+           "dgrad": lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad, flags=FLAGS),
            "wgrad": lambda: ops.conv2d_wgrad(x, dy, dw, stride=stride, pad=pad)}
     flops = 2.0 * B * oh * oh * k * c * r * r
     byt = 2.0 * B * (h * h * c + oh * oh * k) + 2.0 * k * c * r * r
