@@ -75,6 +75,16 @@ int sib_conv2d_dgrad_bnbwd(const void* dy, const void* w_dgrad, void* dx, const 
                            int stride, int pad, int flags, const void* mask_src,
                            const float* mask_ss, const void* xhat_src, const float* mean_invstd,
                            int act, float slope, float* sums, void* stream);
+/* 3x3 / stride 2 / pad 1 dgrad by row parity (no zero insertion): two stride-1 GEMMs over dy with
+ * the sub-filters of sib_pack_dgrad_s2, each storing one row parity of dx[N][H][W][C] in place.
+ * H, W even, W/2 <= 32.  mask_src non-NULL fuses the BatchNorm-backward reduction of the BN whose
+ * INPUT is mask_src (geometry of dx), as in sib_conv2d_dgrad_bnbwd with mask_ss. */
+int sib_conv2d_dgrad_s2(const void* dy, const void* w_sub0, const void* w_sub1, void* dx, int N,
+                        int H, int W, int C, int K, int flags, const void* mask_src,
+                        const float* mask_ss, const float* mean_invstd, int act, float slope,
+                        float* sums, void* stream);
+/* w_dgrad [C][3][3][K] (sib_pack_dgrad_weights) -> w_sub0 [2C][1][2][K], w_sub1 [2C][2][2][K] */
+int sib_pack_dgrad_s2(const void* w_dgrad, void* w_sub0, void* w_sub1, int C, int K, void* stream);
 int sib_scatter_add_strided(const void* src, void* dst, int N, int OH, int OW, int C, int H, int W,
                             int stride, void* stream);
 /* dw[K][R][S][C] (fp32) += wgrad(x, dy).  dw must be initialised (zero_grad). */

@@ -41,12 +41,14 @@ for (c, k, h, r, stride, pad, cnt) in SHAPES:
     x = ops.to_nhwc_bf16(torch.randn(B, c, h, h, device="cuda"))
     w = (torch.randn(k, c, r, r, device="cuda") / (c * r * r) ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     wd = ops.pack_dgrad_weight(w)
+    ws2 = ops.pack_dgrad_s2(wd) if ops.dgrad_s2_ok((B, c, h, h), r, r, stride, pad) and not os.environ.get("NO_S2") else None
+    dx_buf = ops.new_act(B, c, h, h, "cuda") if stride > 1 and r == 1 else None
     stats = torch.empty(2, k, device="cuda")
     y = ops.conv2d_fprop(x, w, stride=stride, pad=pad, stats=stats)
     dy = torch.randn_like(y)
     dw = torch.zeros(k, r, r, c, device="cuda").permute(0, 3, 1, 2)
     fns = {"fprop": lambda: ops.conv2d_fprop(x, w, stride=stride, pad=pad, stats=stats, flags=FLAGS),
-           "dgrad": lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad, flags=FLAGS),
+           "dgrad": lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad, flags=FLAGS, w_s2=ws2, out=dx_buf),
            "wgrad": lambda: ops.conv2d_wgrad(x, dy, dw, stride=stride, pad=pad)}
     flops = 2.0 * B * oh * oh * k * c * r * r
     byt = 2.0 * B * (h * h * c + oh * oh * k) + 2.0 * k * c * r * r

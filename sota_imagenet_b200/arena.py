@@ -50,6 +50,14 @@ class ParamArena:
                 self.dgrad_offset[id(p)] = doff
                 doff += _round_up(n)
         self.wdgrad = torch.zeros(max(doff, ALIGN), dtype=torch.bfloat16, device=device)
+        # row-parity sub-filters for the 3x3 / stride-2 dgrads (ops.pack_dgrad_s2)
+        self.s2 = {}
+        for name, p, o, n, layout in self.entries:
+            if id(p) in self.dgrad_offset and getattr(p, "_sib_stride", 1) == 2 and tuple(p.shape[2:]) == (3, 3) \
+                    and p.shape[0] % 8 == 0:
+                k, c = p.shape[0], p.shape[1]
+                self.s2[id(p)] = (p, torch.zeros((2 * c, 1, 2, k), dtype=torch.bfloat16, device=device),
+                                  torch.zeros((2 * c, 2, 2, k), dtype=torch.bfloat16, device=device))
         self.pack_table, self.pack_blocks = ops.pack_table(pack_entries, device)
         self.pack_count = len(pack_entries)
         self._sig = None
@@ -87,6 +95,12 @@ class ParamArena:
         if self.pack_count:
             ops.call("sib_pack_dgrad_weights", ops._p(self.shadow), ops._p(self.wdgrad),
                      ops._p(self.pack_table), self.pack_count, self.pack_blocks, ops._stream())
+        for p, sub0, sub1 in self.s2.values():
+            ops.pack_dgrad_s2(self.dgrad_view(p), sub0, sub1)
+
+    def dgrad_s2_view(self, p):
+        e = self.s2.get(id(p))
+        return (e[1], e[2]) if e is not None else None
 
     def enable_weight_standardization(self, params, eps=1e-7):
         self.ws_eps = eps

@@ -189,6 +189,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0,
+                                             int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // fp32 add-reduction of a shared-memory tile into global memory, performed by the TMA unit
 // (the element type comes from the tensor map)
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* src, int c0,

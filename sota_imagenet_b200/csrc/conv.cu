@@ -48,6 +48,13 @@ struct IgemmParams {
   float fuse_slope;
   const float* mask_ss;      // [2][Cout] scale, shift (or null)
   const float* mean_invstd;  // [2][Cout]
+  // ---- strided output view (stride-2 dgrad by row parity, see dgrad_s2_impl) ----
+  //   GEMM row m = (image row, q) with q in [0, out_q): out / residual / aux tiles are addressed
+  //   through 3-D tensor maps (channel, q, image row); out_q in {8, 16, 32} divides the 32-row
+  //   slab, columns q >= the real width are clipped by the TMA unit.  0 = plain [M][Cout].
+  int out_q;
+  int stat_c;        // real channel count behind the GEMM columns: column j is channel j % stat_c
+                     // for `stats`, `mask_ss` and `mean_invstd` (== Cout except for the parity GEMMs)
 };
 
 // ---- epilogue (shared by the 1-CTA and 2-CTA kernels) ----
@@ -122,10 +129,19 @@ __device__ __forceinline__ void igemm_epilogue(
         __syncwarp();
         if (n_loads != 0 && lane == 0) {
           mbar_arrive_expect_tx(&res_bar[e], n_loads * kSlabBytes);
-          if (p.has_residual) tma_load_2d(slab, tmRes, &res_bar[e], col0, row0);
-          if (AUX > 0 && fused) {
-            tma_load_2d(aux, tmAux1, &res_bar[e], col0, row0);
-            if (AUX > 1 && p.fuse == 2) tma_load_2d(aux + kSlabBytes, tmAux2, &res_bar[e], col0, row0);
+          if (p.out_q == 0) {
+            if (p.has_residual) tma_load_2d(slab, tmRes, &res_bar[e], col0, row0);
+            if (AUX > 0 && fused) {
+              tma_load_2d(aux, tmAux1, &res_bar[e], col0, row0);
+              if (AUX > 1 && p.fuse == 2) tma_load_2d(aux + kSlabBytes, tmAux2, &res_bar[e], col0, row0);
+            }
+          } else {
+            const int r3 = row0 / p.out_q;
+            if (p.has_residual) tma_load_3d(slab, tmRes, &res_bar[e], col0, 0, r3);
+            if (AUX > 0 && fused) {
+              tma_load_3d(aux, tmAux1, &res_bar[e], col0, 0, r3);
+              if (AUX > 1 && p.fuse == 2) tma_load_3d(aux + kSlabBytes, tmAux2, &res_bar[e], col0, 0, r3);
+            }
           }
         }
         uint32_t r[64];
@@ -179,12 +195,13 @@ __device__ __forceinline__ void igemm_epilogue(
 #pragma unroll
           for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; mu[j] = 0.f; is[j] = 0.f; }
           if (cbase < p.Cout) {
+            const int ch = cbase % p.stat_c;
             if (p.mask_ss != nullptr) {
-              load8f(p.mask_ss + cbase, sc);
-              load8f(p.mask_ss + p.Cout + cbase, sh);
+              load8f(p.mask_ss + ch, sc);
+              load8f(p.mask_ss + p.stat_c + ch, sh);
             }
-            load8f(p.mean_invstd + cbase, mu);
-            load8f(p.mean_invstd + p.Cout + cbase, is);
+            load8f(p.mean_invstd + ch, mu);
+            load8f(p.mean_invstd + p.stat_c + ch, is);
           }
           const bool do_mask = p.fuse_act != SIB_ACT_NONE;
           const float neg = p.fuse_act == SIB_ACT_LEAKY ? p.fuse_slope : 0.f;
@@ -236,7 +253,8 @@ __device__ __forceinline__ void igemm_epilogue(
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(tmOut, slab, col0, row0);
+          if (p.out_q == 0) tma_store_2d(tmOut, slab, col0, row0);
+          else tma_store_3d(tmOut, slab, col0, 0, row0 / p.out_q);
           tma_store_commit();
         }
         if (SLABS > 1) slab_idx ^= 1;
@@ -295,8 +313,9 @@ __device__ __forceinline__ void igemm_epilogue(
             a += s_part[((h * 4 + q) * 2 + 0) * kPartStride + lc];
             b += s_part[((h * 4 + q) * 2 + 1) * kPartStride + lc];
           }
-          atomicAdd(p.stats + n0 + c, a);
-          atomicAdd(p.stats + p.Cout + n0 + c, b);
+          const int ch = (n0 + c) % p.stat_c;
+          atomicAdd(p.stats + ch, a);
+          atomicAdd(p.stats + p.stat_c + ch, b);
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -315,8 +334,8 @@ __device__ __forceinline__ void igemm_epilogue(
           a += s_part[((h * 4 + q) * 2 + 0) * kPartStride + lc];
           b += s_part[((h * 4 + q) * 2 + 1) * kPartStride + lc];
         }
-        atomicAdd(p.stats + c, a);
-        atomicAdd(p.stats + p.Cout + c, b);
+        atomicAdd(p.stats + c % p.stat_c, a);
+        atomicAdd(p.stats + p.stat_c + c % p.stat_c, b);
       }
     }
   }
@@ -1237,6 +1256,17 @@ struct BnBwdFuse {
   float* sums = nullptr;             // [2][C]: sum g, sum g * xhat
 };
 
+// Output addressed as (channel, q, image row) with independent strides: the stride-2 dgrad writes
+// one row parity of dx per launch (dgrad_s2_impl).
+struct StridedOut {
+  int q_pad;             // traversal width of the GEMM (8, 16 or 32; >= q_valid)
+  int q_valid;           // real pixels per image row
+  long rows;             // image rows
+  long stride_q;         // elements between consecutive q
+  long stride_row;       // elements between consecutive image rows
+  int stat_c;            // real channels behind the GEMM columns (column j = channel j % stat_c)
+};
+
 // Shared by fprop and dgrad.  `in` is [N][IH][IW][Cin] NHWC bf16, `w` is [Cout][R][S][Cin].
 // The traversal space (GEMM rows) is [N][TH][TW] and equals the output tensor's pixel space;
 // row (n,p,q) reads taps starting at (p*stride - pad_h, q*stride - pad_w).
@@ -1244,7 +1274,8 @@ struct BnBwdFuse {
 static int run_igemm(const void* in, const void* w, void* out, const void* residual, int N,
                      int IH, int IW, int Cin, int Cout, int R, int S, int stride, int pad_h,
                      int pad_w, int TH, int TW, const float* bias, float* stats, int flags,
-                     cudaStream_t stream, const BnBwdFuse* fuse = nullptr) {
+                     cudaStream_t stream, const BnBwdFuse* fuse = nullptr,
+                     const StridedOut* so = nullptr) {
   // 1x1 filters may have a ragged K: TMA zero-fills both operands past Cin
   SIB_CHECK(Cin % 64 == 0 || (R == 1 && S == 1 && Cin % 8 == 0),
             "igemm: Cin must be a multiple of 64 (or of 8 for 1x1 filters), got %d", Cin);
@@ -1252,7 +1283,7 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   SIB_CHECK((long)N * TH * TW < (1l << 31), "igemm: too many pixels");
   // 3x3 / stride 1 / pad 1 on 64 or 128 output channels at >= 28 pixel rows: halo-reuse kernel
   {
-    const bool geometry = R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && TH == IH &&
+    const bool geometry = so == nullptr && R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && TH == IH &&
                           TW == IW && Cin % 64 == 0 && IW + 2 <= 63 && residual == nullptr &&
                           bias == nullptr && (Cout == 64 || Cout == 128) &&
                           (fuse == nullptr || fuse->aux2 == nullptr);
@@ -1310,6 +1341,7 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   p.pad_w = pad_w;
   p.bias = bias;
   p.stats = stats;
+  p.stat_c = so != nullptr ? so->stat_c : Cout;
   p.has_residual = residual != nullptr;
   int aux = 0;
   if (fuse != nullptr) {
@@ -1353,19 +1385,34 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   rc = make_tmap_2d_bf16(&tm.b, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin,
                          two_cta ? 128 : BN, kBK, true);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tm.out, out, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
-  if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tm.res, residual ? residual : out, (uint64_t)p.M_total, Cout, Cout, 32,
-                         64, true);
-  if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tm.aux1, aux >= 1 ? fuse->aux1 : out, (uint64_t)p.M_total, Cout, Cout,
-                         32, 64, true);
-  if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tm.aux2, aux >= 2 ? fuse->aux2 : out, (uint64_t)p.M_total, Cout, Cout,
-                         32, 64, true);
-  if (rc) return rc;
+  const void* res_p = residual ? residual : out;
+  const void* aux1_p = aux >= 1 ? fuse->aux1 : out;
+  const void* aux2_p = aux >= 2 ? fuse->aux2 : out;
+  if (so == nullptr) {
+    rc = make_tmap_2d_bf16(&tm.out, out, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tm.res, res_p, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tm.aux1, aux1_p, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tm.aux2, aux2_p, (uint64_t)p.M_total, Cout, Cout, 32, 64, true);
+    if (rc) return rc;
+  } else {
+    SIB_CHECK((so->q_pad == 8 || so->q_pad == 16 || so->q_pad == 32) && so->q_valid <= so->q_pad &&
+                  TW == so->q_pad && (long)N * TH == so->rows,
+              "igemm: bad strided output view (q_pad %d, q_valid %d)", so->q_pad, so->q_valid);
+    p.out_q = so->q_pad;
+    const uint32_t bq = so->q_pad, br = 32 / so->q_pad;
+    const void* ptrs[4] = {out, res_p, aux1_p, aux2_p};
+    CUtensorMap* maps[4] = {&tm.out, &tm.res, &tm.aux1, &tm.aux2};
+    for (int i = 0; i < 4; ++i) {
+      rc = make_tmap_3d_bf16(maps[i], ptrs[i], Cout, so->q_valid, so->rows, so->stride_q,
+                             so->stride_row, 64, bq, br);
+      if (rc) return rc;
+    }
+  }
   if (p.stats != nullptr && !(flags & SIB_FLAG_STATS_ZEROED))
-    SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * Cout, stream));
+    SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * p.stat_c, stream));
   if (aux == 0) {
     if (two_cta) return launch_igemm2<5, 1, 0>(tm, p, stream);
     if (BN == 64) return launch_igemm<64, 6, 2, 0>(tm, p, stream);
@@ -1474,6 +1521,66 @@ extern "C" int sib_conv2d_dgrad_bnbwd(const void* dy, const void* w_dgrad, void*
   f.sums = sums;
   return dgrad_impl(dy, w_dgrad, dx, residual, workspace, N, H, W, C, K, R, S, stride, pad, flags,
                     stream, &f);
+}
+
+// 3x3 / stride 2 / pad 1 dgrad without zero insertion.  dx row 2p+a only receives filter rows
+// r with (2p + a + 1 - r) even, so each row parity a is a small stride-1 convolution over dy:
+//   a = 0 : r = 1            -> 1 x 2 taps
+//   a = 1 : r in {2, 0}      -> 2 x 2 taps           (tap (dp, dq) reads dy[p + dp][q + dq])
+// with 2C output columns (b, c): column parity b = 1 uses s = 2 - 2 dq, b = 0 uses s = 1 at dq = 0
+// (zero weights elsewhere; packed by sib_pack_dgrad_s2).  The output row (n, p) of parity a IS the
+// dx row (n, 2p + a) verbatim ((q, b, c) = (2q + b) C + c), so the GEMM stores straight into dx
+// through a 3-D tensor map (channel pair block, q, image row).  The traversal width is padded to
+// 8 / 16 / 32 so that a 32-row epilogue slab is a whole number of image rows; the padding columns
+// read zeros (im2col bounding box widened to the right) and are clipped on store.
+// 12 C K MACs per output pixel pair instead of 36 for the zero-inserted form.
+static int dgrad_s2_impl(const void* dy, const void* sub0, const void* sub1, void* dx, int N, int H,
+                         int W, int C, int K, int flags, void* stream, const BnBwdFuse* fuse) {
+  SIB_CHECK(H % 2 == 0 && W % 2 == 0 && W / 2 <= 32, "dgrad_s2: needs even H, W and W/2 <= 32 (got %dx%d)", H, W);
+  SIB_CHECK((2 * C) % 64 == 0 && K % 64 == 0, "dgrad_s2: needs 2C and K multiples of 64");
+  const int OH = H / 2, OW = W / 2;
+  StridedOut so{};
+  so.q_pad = OW <= 8 ? 8 : (OW <= 16 ? 16 : 32);
+  so.q_valid = OW;
+  so.rows = (long)N * OH;
+  so.stride_q = 2 * C;
+  so.stride_row = 2l * W * C;
+  so.stat_c = C;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int a = 0; a < 2; ++a) {
+    const long off = (long)a * W * C;
+    BnBwdFuse f;
+    if (fuse != nullptr) {
+      f = *fuse;
+      f.aux1 = static_cast<const __nv_bfloat16*>(fuse->aux1) + off;
+      if (fuse->aux2 != nullptr) f.aux2 = static_cast<const __nv_bfloat16*>(fuse->aux2) + off;
+    }
+    int fl = flags;
+    if (a == 1 && fuse != nullptr) fl |= SIB_FLAG_STATS_ZEROED;   // both parities add into one buffer
+    if (int rc = run_igemm(dy, a == 0 ? sub0 : sub1, static_cast<__nv_bfloat16*>(dx) + off, nullptr,
+                           N, OH, OW, K, 2 * C, a == 0 ? 1 : 2, 2, 1, 0, 0, OH, so.q_pad, nullptr,
+                           nullptr, fl, st, fuse != nullptr ? &f : nullptr, &so))
+      return rc;
+  }
+  return 0;
+}
+
+extern "C" int sib_conv2d_dgrad_s2(const void* dy, const void* w_sub0, const void* w_sub1, void* dx,
+                                   int N, int H, int W, int C, int K, int flags,
+                                   const void* mask_src, const float* mask_ss,
+                                   const float* mean_invstd, int act, float slope, float* sums,
+                                   void* stream) {
+  if (mask_src == nullptr)
+    return dgrad_s2_impl(dy, w_sub0, w_sub1, dx, N, H, W, C, K, flags, stream, nullptr);
+  SIB_CHECK(mean_invstd != nullptr && sums != nullptr, "dgrad_s2: mean_invstd and sums are required with mask_src");
+  BnBwdFuse f;
+  f.aux1 = mask_src;
+  f.mask_ss = mask_ss;
+  f.mean_invstd = mean_invstd;
+  f.act = act;
+  f.slope = slope;
+  f.sums = sums;
+  return dgrad_s2_impl(dy, w_sub0, w_sub1, dx, N, H, W, C, K, flags, stream, &f);
 }
 
 extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W,

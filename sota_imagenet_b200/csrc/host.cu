@@ -115,6 +115,28 @@ int make_tmap_2d_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t 
   return 0;
 }
 
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1,
+                      uint32_t box2) {
+  std::call_once(g_once, resolve);
+  SIB_CHECK(g_tiled != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  SIB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  SIB_CHECK((stride1_elems * 2) % 16 == 0 && (stride2_elems * 2) % 16 == 0,
+            "TMA strides must be multiples of 16 bytes");
+  SIB_CHECK(box0 == 64 && box1 <= 256 && box2 <= 256, "3d box %ux%ux%u unsupported", box0, box1, box2);
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
+                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SIB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed: %d dims=%llu,%llu,%llu", (int)r,
+            (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2);
+  return 0;
+}
+
 int make_tmap_nhwc_tile_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, int C,
                              uint32_t box_c, uint32_t box_w, uint32_t box_h) {
   std::call_once(g_once, resolve);

@@ -59,6 +59,12 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
 int make_tmap_2d_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols,
                      uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
 
+// 3-D bf16 tensor (d0 contiguous, strides in elements for d1 and d2), box = box0 x box1 x box2,
+// 128B swizzle (box0 must be 64).  Out-of-bounds elements are dropped on stores, zero on loads.
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1,
+                      uint32_t box2);
+
 // Tiled 4-D map over an NHWC bf16 tensor, dims (C, W, H, N); box = box_c channels x box_w x box_h
 // pixels of one image, 128B swizzle, out-of-bounds pixels (halo) read as zeros.
 int make_tmap_nhwc_tile_bf16(CUtensorMap* tm, const void* base, int N, int H, int W, int C,

@@ -125,6 +125,34 @@ pack_dgrad_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restri
   }
 }
 
+// Row-parity sub-filters of a 3x3 / stride-2 dgrad (conv.cu dgrad_s2_impl) from the flipped
+// pack wd[c][fr][fs][k] (= w[k][2-fr][2-fs][c]):
+//   sub1[(b,c)][dp][dq][k] = b ? wd[c][2dp][2dq][k] : (dq == 0 ? wd[c][2dp][1][k] : 0)
+//   sub0[(b,c)][0 ][dq][k] = b ? wd[c][1  ][2dq][k] : (dq == 0 ? wd[c][1  ][1][k] : 0)
+// one block per (a, b, c, dp, dq) row of K elements.
+__global__ void __launch_bounds__(128)
+pack_dgrad_s2_kernel(const __nv_bfloat16* __restrict__ wd, __nv_bfloat16* __restrict__ sub0,
+                     __nv_bfloat16* __restrict__ sub1, int C, int K) {
+  int row = blockIdx.x;                      // [0, 2C*2) -> sub0 rows, then [.., + 2C*4) -> sub1 rows
+  const int n0 = 2 * C * 2;
+  const int a = row >= n0 ? 1 : 0;
+  if (a) row -= n0;
+  const int taps = a ? 4 : 2;
+  const int bc = row / taps, tap = row - bc * taps;
+  const int b = bc / C, c = bc - b * C;
+  const int dp = a ? (tap >> 1) : 0, dq = tap & 1;
+  const int fr = a ? 2 * dp : 1;
+  const bool zero = (b == 0 && dq == 1);
+  const int fs = b ? 2 * dq : 1;
+  const __nv_bfloat16* src = wd + (((long)c * 3 + fr) * 3 + fs) * K;
+  __nv_bfloat16* dst = (a ? sub1 : sub0) + (long)row * K;
+  for (int k = threadIdx.x * 8; k < K; k += blockDim.x * 8) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!zero) v = *reinterpret_cast<const uint4*>(src + k);
+    *reinterpret_cast<uint4*>(dst + k) = v;
+  }
+}
+
 // one CTA per output channel: w_std = (w - mean) / sqrt(var_biased + eps) * gain
 __global__ void __launch_bounds__(256)
 weight_std_kernel(const float* __restrict__ w, const float* __restrict__ gain,
@@ -221,6 +249,16 @@ extern "C" int sib_pack_dgrad_weights(const void* w_bf16, void* w_dgrad, const v
   pack_dgrad_kernel<<<total_blocks, 256, 0, ST(stream)>>>(
       static_cast<const __nv_bfloat16*>(w_bf16), static_cast<__nv_bfloat16*>(w_dgrad),
       static_cast<const PackEntry*>(table_dev), nent);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_pack_dgrad_s2(const void* w_dgrad, void* w_sub0, void* w_sub1, int C, int K,
+                                 void* stream) {
+  SIB_CHECK(K % 8 == 0, "pack_dgrad_s2: K must be a multiple of 8");
+  pack_dgrad_s2_kernel<<<2 * C * 6, 128, 0, ST(stream)>>>(
+      static_cast<const __nv_bfloat16*>(w_dgrad), static_cast<__nv_bfloat16*>(w_sub0),
+      static_cast<__nv_bfloat16*>(w_sub1), C, K);
   SIB_LAUNCH_CHECK();
   return 0;
 }

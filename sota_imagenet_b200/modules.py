@@ -145,6 +145,7 @@ class Conv2d(SibModule):
         self.weight = nn.Parameter(w)
         self.weight._sib_layout = "krsc"
         self.weight._sib_needs_dgrad = needs_dgrad
+        self.weight._sib_stride = stride
 
     def extra_repr(self):
         return "%d, %d, kernel_size=%s, stride=%d, padding=%d" % (
@@ -155,8 +156,9 @@ class Conv2d(SibModule):
 
     def run_dgrad(self, dy, x_shape, out=None, residual=None, bn_bwd=None):
         k = self.kernel_size[0]
+        w_s2 = self._arena.dgrad_s2_view(self.weight) if self.stride == 2 and k == 3 else None
         return ops.conv2d_dgrad(dy, self._wd16(self.weight), x_shape, k, k, self.stride,
-                                self.padding, out=out, residual=residual, bn_bwd=bn_bwd)
+                                self.padding, out=out, residual=residual, bn_bwd=bn_bwd, w_s2=w_s2)
 
     def run_wgrad(self, x, dy):
         dw = self._grad(self.weight)

@@ -23,6 +23,8 @@ CONV_CASES = [
     (2, 16, 16, 64, 64, 3, 1, 1, 0),
     (4, 14, 14, 128, 128, 3, 1, 1, 0),
     (2, 28, 28, 128, 128, 3, 2, 1, 0),
+    (3, 56, 56, 128, 128, 3, 2, 1, 0),                        # parity dgrad: q padded 28 -> 32
+    (5, 14, 14, 64, 128, 3, 2, 1, 0),                         # parity dgrad: q padded 7 -> 8, 1-CTA tiles
     (2, 28, 28, 256, 512, 1, 2, 0, 0),
     (3, 7, 7, 512, 512, 3, 1, 1, 0),
     (32, 1, 1, 2048, 1000, 1, 1, 0, 0),                       # FC: ragged N
@@ -60,6 +62,20 @@ def test_conv_fprop_dgrad_wgrad(n, h, w, c, k, r, stride, pad, flags):
     assert torch.equal(wd.float().cpu(), wt.detach().flip(2, 3).permute(1, 2, 3, 0).contiguous())
     dx = ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=stride, pad=pad, flags=flags)
     assert rel(dx, dx_ref) < 5e-3
+    if ops.dgrad_s2_ok((n, c, h, w), r, r, stride, pad):
+        # row-parity decomposition of the strided 3x3 dgrad (no zero insertion)
+        sub = ops.pack_dgrad_s2(wd)
+        ref0 = torch.zeros(2, c, 1, 2, k)
+        ref1 = torch.zeros(2, c, 2, 2, k)
+        wdf = wd.float().cpu()
+        ref1[1] = wdf[:, 0::2, 0::2, :]
+        ref1[0][:, :, 0, :] = wdf[:, 0::2, 1, :]
+        ref0[1][:, 0] = wdf[:, 1, 0::2, :]
+        ref0[0][:, 0, 0, :] = wdf[:, 1, 1, :]
+        assert torch.equal(sub[0].float().cpu(), ref0.view(2 * c, 1, 2, k))
+        assert torch.equal(sub[1].float().cpu(), ref1.view(2 * c, 2, 2, k))
+        dx2 = ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=stride, pad=pad, flags=flags, w_s2=sub)
+        assert rel(dx2, dx_ref) < 5e-3
     if stride == 1:
         res = ops.to_nhwc_bf16(torch.randn(n, c, h, w, device="cuda"))
         dxr = ops.conv2d_dgrad(dyb, wd, (n, c, h, w), r, r, stride=1, pad=pad, residual=res)
@@ -83,14 +99,19 @@ FUSED_CASES = [
     (2, 56, 56, 64, 64, 3, 1, 1, "recompute"),      # halo-reuse kernel, resident weights
     (3, 28, 28, 128, 128, 3, 1, 1, "recompute"),    # halo-reuse kernel, streamed weights
     (2, 18, 18, 64, 128, 3, 1, 1, "halo"),          # halo-reuse kernel forced on a small image
+    (2, 28, 28, 128, 128, 3, 2, 1, "s2"),           # strided 3x3 by row parity, fused reduction
+    (4, 56, 56, 128, 192, 3, 2, 1, "s2"),           # q padded 28 -> 32, 2-CTA tiles
 ]
 
 
 @pytest.mark.parametrize("n,h,w,c,k,r,stride,pad,mode", FUSED_CASES)
 def test_dgrad_fused_bn_backward_reduction(n, h, w, c, k, r, stride, pad, mode):
     flags = 0
+    s2 = mode == "s2"
     if mode == "halo":
         mode, flags = "recompute", ops.FLAG_FORCE_HALO
+    if s2:
+        mode = "recompute"
     """dgrad + activation mask + BN-backward sums in one epilogue == dgrad, then bn_bwd_reduce."""
     torch.manual_seed(2)
     oh = (h + 2 * pad - r) // stride + 1
@@ -119,11 +140,11 @@ def test_dgrad_fused_bn_backward_reduction(n, h, w, c, k, r, stride, pad, mode):
     z = out.float() if out is not None else torch.addcmul(ss[1].view(1, -1, 1, 1), xin.float(), ss[0].view(1, -1, 1, 1))
     g_ref = torch.where(z > 0, plain.float(), plain.float() * slope)
     fused, sums = ops.conv2d_dgrad(dy, wd, (n, c, h, w), r, r, stride=stride, pad=pad, residual=res,
-                                   bn_bwd=fuse, flags=flags)
+                                   bn_bwd=fuse, flags=flags, w_s2=ops.pack_dgrad_s2(wd) if s2 else None)
     torch.cuda.synchronize()
     # same kernel family => same accumulation order => bit-identical; the halo kernel walks the
     # k-blocks channel-block-major, so its bf16 roundings may differ from the im2col kernel's
-    halo = r == 3 and stride == 1 and (w >= 28 or flags)
+    halo = (r == 3 and stride == 1 and (w >= 28 or flags)) or s2
     assert rel(fused, g_ref) < 4e-3 if (slope or halo) else torch.equal(fused.float(), g_ref)
     xhat = (xin.float() - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
     gf = fused.float()
