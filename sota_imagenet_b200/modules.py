@@ -24,6 +24,8 @@ from .arena import ParamArena
 # that produces the gradient (csrc/conv.cu igemm_epilogue); SIB_FUSE_BN_BWD=0 restores the separate
 # bn_bwd_reduce passes (kept for A/B measurements and as the parity cross-check).
 FUSE_BN_BWD = os.environ.get("SIB_FUSE_BN_BWD", "1") != "0"
+# 3x3 / stride-2 dgrad by row parity (csrc/conv.cu dgrad_s2_impl); 0 = zero-inserted dy
+DGRAD_S2 = os.environ.get("SIB_DGRAD_S2", "1") != "0"
 
 
 # --------------------------------------------------------------------------- autograd glue
@@ -156,7 +158,7 @@ class Conv2d(SibModule):
 
     def run_dgrad(self, dy, x_shape, out=None, residual=None, bn_bwd=None):
         k = self.kernel_size[0]
-        w_s2 = self._arena.dgrad_s2_view(self.weight) if self.stride == 2 and k == 3 else None
+        w_s2 = self._arena.dgrad_s2_view(self.weight) if self.stride == 2 and k == 3 and DGRAD_S2 else None
         return ops.conv2d_dgrad(dy, self._wd16(self.weight), x_shape, k, k, self.stride,
                                 self.padding, out=out, residual=residual, bn_bwd=bn_bwd, w_s2=w_s2)
 
