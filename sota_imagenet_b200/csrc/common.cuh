@@ -373,6 +373,34 @@ __device__ __forceinline__ void umma2_commit_multicast_w(uint64_t* bar) {
       "h"((uint16_t)3)
       : "memory");
 }
+// ---- cluster multicast (1-CTA MMAs, operand tiles shared by the CTAs of a cluster) ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// im2col load delivered to the same smem offset (and mbarrier offset) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_im2col_4d_mc(void* dst, const CUtensorMap* tm,
+                                                      uint64_t* bar, int c, int w, int h, int n,
+                                                      uint16_t off_w, uint16_t off_h,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h),
+      "h"(cta_mask)
+      : "memory");
+}
+// commit of a 1-CTA MMA group arriving on the same-offset mbarrier of every CTA in cta_mask
+__device__ __forceinline__ void umma_commit_mc_w(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
 // arrive on the mbarrier at the same offset in CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(

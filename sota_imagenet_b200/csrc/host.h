@@ -33,19 +33,31 @@ int sm_count();
 // global memory.  Opt-in with SIB_PDL=1; otherwise they are ordinary stream-ordered launches.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                              cudaStream_t stream, Args... args) {
+inline cudaError_t launch_cluster_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                      cudaStream_t stream, unsigned cluster_x, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster_x > 1) {      // thread-block cluster along x (runtime cluster dimension)
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  return launch_cluster_pdl(kernel, grid, block, smem, stream, 1u, args...);
 }
 
 // 2-D row-major bf16 matrix [rows][cols] (cols contiguous); box = box_rows x box_cols.

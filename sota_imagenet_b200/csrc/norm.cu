@@ -57,13 +57,21 @@ __device__ __forceinline__ void column_reduce_store(const ColOwner& co, int C,
     for (int j = 0; j < 8; ++j) red[a][threadIdx.x][j] = co.active ? acc[a][j] : 0.f;
   __syncthreads();
   const int cvec = C >> 3;
-  for (int idx = threadIdx.x; idx < NACC * C; idx += kRedThreads) {
-    const int a = idx / C;
-    const int c = idx - a * C;
+  // one 4-channel vector atomic per thread and accumulator (C % 8 == 0): the grids of the
+  // reduction kernels are capped at two blocks per SM (bn_reduce_grid) because same-address
+  // atomics from ~1200 blocks finishing together cost ~50 us at the end of the kernel
+  for (int idx = threadIdx.x; idx < NACC * (C >> 2); idx += kRedThreads) {
+    const int a = idx / (C >> 2);
+    const int c = (idx - a * (C >> 2)) * 4;
     const int v = c >> 3, j = c & 7;
-    float s = 0.f;
-    for (int y = 0; y < co.rpb; ++y) s += red[a][y * cvec + v][j];
-    atomicAdd(out + (long)a * C + c, s);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int y = 0; y < co.rpb; ++y) {
+      const float* r4 = &red[a][y * cvec + v][j];
+      s0 += r4[0]; s1 += r4[1]; s2 += r4[2]; s3 += r4[3];
+    }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + (long)a * C + c),
+                 "f"(s0), "f"(s1), "f"(s2), "f"(s3)
+                 : "memory");
   }
 }
 
@@ -306,6 +314,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   griddep_wait();
   const ColOwner co(C);
   constexpr int NACC = SECOND ? 4 : 2;
+  constexpr int U = kU;
   float acc[NACC][8] = {};
   if (co.active) {
     float mean[8], invstd[8], mean2[8], invstd2[8], sc[8], sh[8];
@@ -321,10 +330,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       load8f(mask_ss + C + co.tx * 8, sh);
     }
     const long col = co.tx * 8;
-    for (long r = co.row0; r < M; r += kU * co.stride) {
-      uint4 vg[kU], vx[kU], vo[kU], vw[kU];
+    for (long r = co.row0; r < M; r += U * co.stride) {
+      uint4 vg[U], vx[U], vo[U], vw[U];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long rr = r + u * co.stride;
         if (rr < M) {
           vg[u] = ldg_stream(dy + rr * C + col);
@@ -334,7 +343,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         }
       }
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long rr = r + u * co.stride;
         if (rr < M) {
           float g[8], xv[8];
@@ -793,10 +802,17 @@ static int bn_grid(long M, int C) {
   return (int)blocks;
 }
 
+// statistics / backward-sum kernels: every block ends in 2C..4C atomics on the same addresses
+static int bn_reduce_grid(long M, int C) {
+  const int g = bn_grid(M, C);
+  const int cap = sm_count() * 2;
+  return g < cap ? g : cap;
+}
+
 extern "C" int sib_bn_stats(const void* x, long M, int C, float* stats, void* stream) {
   if (int rc = check_c(C)) return rc;
   SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, ST(stream)));
-  SIB_CUDA(launch_pdl(bn_stats_kernel, dim3(bn_grid(M, C)), dim3(kRedThreads), 0, ST(stream), static_cast<const __nv_bfloat16*>(x), M, C, stats));
+  SIB_CUDA(launch_pdl(bn_stats_kernel, dim3(bn_reduce_grid(M, C)), dim3(kRedThreads), 0, ST(stream), static_cast<const __nv_bfloat16*>(x), M, C, stats));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -880,7 +896,7 @@ extern "C" int sib_bn_bwd_reduce(const void* dy, const void* out, const float* m
             "bn_bwd_reduce: activation mask needs `out` or `mask_ss`");
   const int nacc = x2 ? 4 : 2;
   if (!prezeroed) SIB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * nacc * C, ST(stream)));
-  const int grid = bn_grid(M, C);
+  const int grid = bn_reduce_grid(M, C);
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(dy);
   const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(out);
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
