@@ -327,10 +327,18 @@ def run_ours(args):
                        "achieved": bn_b / (bn_ms * 1e-3) / 1e9 if bn_ms else 0.0, "peak": pk["hbm_gbs"],
                        "unit": "GB/s", "frac": (bn_b / (bn_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if bn_ms else 0.0,
                        "traffic": None, "bytes_per_step": bn_b, "ms_per_step_eager_events": bn_ms}
+        # DRAM bytes of the same conv launches from the committed ncu capture (profiles/): compare
+        # with the algorithmic minimum (read x + write y + read w per pass)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_dram_traffic.json")
+        if os.path.exists(tpath) and BATCH == 256 and SIZE == 224:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["dram_bytes_per_step"], "profiles/r01_conv_dram_traffic.json (ncu, %d conv launches of one step)" % tj["conv_launches_per_step"]
         roofline = {
-            "bound": "tensor", "kernel": "igemm_kernel / wgrad_kernel (tcgen05 implicit-GEMM conv)",
+            "bound": "tensor", "kernel": "igemm / igemm2 / halo3x3 / wgrad kernels (tcgen05 implicit-GEMM conv)",
             "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["which"],
+            "frac": achieved / pk["tflops"], "traffic": traffic, "traffic_unit": "bytes per step (all conv launches)",
+            "traffic_source": traffic_src, "algorithmic_bytes_per_step": 3 * 11.2e9, "peak_source": pk["which"],
             "launches": int(sum(groups[n][2] for n in conv_names)),
             "conv_ms_per_step_eager_events": conv_ms, "all_kernels_ms_per_step_eager_events": total_ms,
             "conv_share_of_step": conv_ms / total_ms if total_ms else None,

@@ -132,7 +132,7 @@ class PaddedBatchNorm2d(BatchNorm2d):
                                      rm, rv, count, self.eps, self.momentum)
             self.running_mean.copy_(rm[:self.num_features])
             self.running_var.copy_(rv[:self.num_features])
-            self.num_batches_tracked += 1
+            self._count_batch()
         else:
             mi, count = None, n * h * w
             ss = ops.bn_eval_scale(self._padded(self.weight.data, 1.0), self._padded(self.bias.data, 0.0),

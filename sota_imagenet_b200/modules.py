@@ -85,6 +85,15 @@ class SibModule(nn.Module):
         for m in self.modules():
             if isinstance(m, SibModule) and m is not self:
                 m._arena = self._arena
+        # one counter tensor for every BatchNorm below this root: `num_batches_tracked += 1` was 53
+        # tiny launches per step; the buffers become views and the root bumps them all at once
+        bns = [m for m in self.modules() if isinstance(m, BatchNorm2d)]
+        self._nbt = None
+        if bns:
+            self._nbt = torch.stack([m.num_batches_tracked.to(dev) for m in bns]).contiguous()
+            for i, m in enumerate(bns):
+                m._buffers["num_batches_tracked"] = self._nbt[i]
+                m._nbt_batched = True
         return self._arena
 
     def _begin_backward(self):
@@ -106,6 +115,8 @@ class SibModule(nn.Module):
             a.refresh_shadow()
         ops.begin_pass(x.device)
         x = self._prepare_input(x)
+        if self.training and getattr(self, "_nbt", None) is not None:
+            self._nbt += 1
         if torch.is_grad_enabled() and (self.training or x.requires_grad):
             if not hasattr(self, "_dummy") or self._dummy.device != x.device:
                 self._dummy = torch.zeros((), device=x.device, requires_grad=True)
@@ -264,7 +275,7 @@ class BatchNorm2d(SibModule):
             count = count * world
         mi, ss = ops.bn_finalize(stats, self.weight.data, self.bias.data, self.running_mean,
                                  self.running_var, count, self.eps, self.momentum)
-        self.num_batches_tracked += 1
+        self._count_batch()
         return mi, ss, count
 
     def stats_args(self, stats):
@@ -273,8 +284,12 @@ class BatchNorm2d(SibModule):
         world = self._world()
         if world > 1:
             torch.distributed.all_reduce(stats, group=self.process_group)
-        self.num_batches_tracked += 1
+        self._count_batch()
         return (stats, self.weight.data, self.bias.data, self.running_mean, self.running_var), world
+
+    def _count_batch(self):
+        if not getattr(self, "_nbt_batched", False):     # else the root module counts for everyone
+            self.num_batches_tracked += 1
 
     def reduce_sums(self, sums):
         if self._world() > 1:
