@@ -760,8 +760,11 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         first = false;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || (warp == 3 && p.b_stationary && p.cin_blocks == 1)) {
     // ---- MMA issuer: the whole warp runs the loop converged, one elected lane issues ----
+    // With resident weights and one channel block per tile the issue loop itself bounds the tile
+    // rate (36 MMAs of 32 clk each), so TWO warps (1 and 3) issue alternate tiles, each into its
+    // own TMEM accumulator stage.
     constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
     // tap (r, s) = the region shifted by r * pitch + s pixel rows of 128 bytes (16-byte units)
     uint32_t tap_off[9];
@@ -769,51 +772,74 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tap = 0; tap < 9; ++tap) tap_off[tap] = ((tap / 3) * p.pitch + (tap % 3)) * 8;
     const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), 16, 1024, kSwizzle128B);
     const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), 16, 1024, kSwizzle128B);
-    int a_stage = 0, b_stage = 0;
-    uint32_t a_phase = 0, b_phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    if (p.b_stationary) {
+    if (p.b_stationary && p.cin_blocks == 1) {
+      const int g = warp == 3 ? 1 : 0;
       // the weight k-blocks are loaded once and never released
-      for (int kb = 0; kb < num_kblocks; ++kb) mbar_wait_w(&b_full[kb], 0);
+      for (int kb = 0; kb < 9; ++kb) mbar_wait_w(&b_full[kb], 0);
       tc_fence_after();
-    }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait_w(&tmem_empty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int cb = 0; cb < p.cin_blocks; ++cb) {
-        mbar_wait_w(&a_full[a_stage], a_phase);
+      int i = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
+        if ((i & 1) != g) continue;
+        const int st = i % kHaloAStages;
+        const uint32_t ph = (uint32_t)(i / kHaloAStages) & 1u;
+        const uint32_t acc_ph = (uint32_t)(i >> 1) & 1u;
+        mbar_wait_w(&tmem_empty_bar[g], acc_ph ^ 1);
         tc_fence_after();
-        const uint64_t a_desc = a_desc0 + (uint32_t)(a_stage * (kHaloAStage >> 4));
-        if (p.b_stationary) {
+        mbar_wait_w(&a_full[st], ph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + g * BN;
+        const uint64_t a_desc = a_desc0 + (uint32_t)(st * (kHaloAStage >> 4));
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t ad = a_desc + tap_off[tap];
-            const uint64_t bd = b_desc0 + (uint32_t)((cb * 9 + tap) * (kBBytes >> 4));
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint64_t ad = a_desc + tap_off[tap];
+          const uint64_t bd = b_desc0 + (uint32_t)(tap * (kBBytes >> 4));
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16_ss_w(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (cb | tap | k) != 0);
-          }
-        } else {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait_w(&b_full[b_stage], b_phase);
-            tc_fence_after();
-            const uint64_t ad = a_desc + tap_off[tap];
-            const uint64_t bd = b_desc0 + (uint32_t)(b_stage * (kBBytes >> 4));
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16_ss_w(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (cb | tap | k) != 0);
-            umma_commit_w(&b_empty[b_stage]);
-            if (++b_stage == BSTAGES) { b_stage = 0; b_phase ^= 1; }
-          }
+          for (int k = 0; k < kBK / 16; ++k)
+            umma_bf16_ss_w(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (tap | k) != 0);
         }
-        umma_commit_w(&a_empty[a_stage]);
-        if (++a_stage == kHaloAStages) { a_stage = 0; a_phase ^= 1; }
+        umma_commit_w(&a_empty[st]);
+        umma_commit_w(&tmem_full_bar[g]);
       }
-      umma_commit_w(&tmem_full_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    } else {
+      int a_stage = 0, b_stage = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      if (p.b_stationary) {
+        for (int kb = 0; kb < num_kblocks; ++kb) mbar_wait_w(&b_full[kb], 0);
+        tc_fence_after();
+      }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait_w(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          mbar_wait_w(&a_full[a_stage], a_phase);
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + (uint32_t)(a_stage * (kHaloAStage >> 4));
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            if (!p.b_stationary) {
+              mbar_wait_w(&b_full[b_stage], b_phase);
+              tc_fence_after();
+            }
+            const uint64_t ad = a_desc + tap_off[tap];
+            const uint64_t bd =
+                b_desc0 + (uint32_t)((p.b_stationary ? cb * 9 + tap : b_stage) * (kBBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_ss_w(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (cb | tap | k) != 0);
+            if (!p.b_stationary) {
+              umma_commit_w(&b_empty[b_stage]);
+              if (++b_stage == BSTAGES) { b_stage = 0; b_phase ^= 1; }
+            }
+          }
+          umma_commit_w(&a_empty[a_stage]);
+          if (++a_stage == kHaloAStages) { a_stage = 0; a_phase ^= 1; }
+        }
+        umma_commit_w(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ---- epilogue: TMEM -> bf16 slab -> column-owner pass (statistics / fused BN backward,
