@@ -6,6 +6,8 @@
   GpuAugment        random-resized-crop (area [min_area,1], aspect [0.75,1.25], 100 attempts) ->
                     triangular resize to SxS -> mirror p=.5 -> (v-127.5)/51 (:65-74,113-122) as one
                     kernel; crop boxes from a counter-based Philox stream (bit-exact vs the oracle);
+  HostPrefetcher    double-buffered pinned-host -> device staging on a copy stream (DALI's prefetch
+                    queue), used by bench.py's end-to-end measurement;
   SyntheticLoader   DaliLoader surface (:163-186): iterable of (data, one-hot label), batch_size,
                     __len__, drop-last;
   DataManager       DaliDataManager surface (:189-239): stages with extra_args overrides
@@ -62,6 +64,41 @@ class SyntheticSource:
         idx = (torch.arange(batch_size) + lo) % self.pool
         idx = idx.to(self.images.device)
         return self.images[idx], self.labels[idx]
+
+
+class HostPrefetcher:
+    """Double-buffered host -> device staging of (uint8 images, labels) batches, the role DALI's
+    prefetch queue plays in the reference (dali_dataloader.py:163-186 `prefetch_queue_depth`): the
+    copy of batch i+1 runs on its own stream while step i computes.  Every batch is still copied
+    from pinned host memory exactly once; slots are reused only after the step that read them has
+    been waited for by the caller (the per-step loss read-back in a training loop)."""
+
+    def __init__(self, source, batch_size, device="cuda", first_index=0):
+        self.source, self.batch_size, self.device = source, batch_size, torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        imgs, labels = source.batch(first_index, batch_size)
+        self.slots = [(torch.empty_like(imgs, device=self.device), torch.empty_like(labels, device=self.device),
+                       torch.cuda.Event()) for _ in range(2)]
+        self.next_index = first_index
+        self._issue()
+
+    def _issue(self):
+        imgs, labels = self.source.batch(self.next_index, self.batch_size)
+        d_imgs, d_labels, ev = self.slots[self.next_index % 2]
+        with torch.cuda.stream(self.stream):
+            d_imgs.copy_(imgs, non_blocking=True)
+            d_labels.copy_(labels, non_blocking=True)
+            ev.record(self.stream)
+
+    def next(self):
+        """(images, labels, index) of the next batch on the device; starts the copy of the one after.
+        The caller must have finished (synchronised on) the step before the previous one."""
+        i = self.next_index
+        d_imgs, d_labels, ev = self.slots[i % 2]
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        self.next_index = i + 1
+        self._issue()
+        return d_imgs, d_labels, i
 
 
 class SyntheticLoader:
