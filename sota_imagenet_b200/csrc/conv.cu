@@ -501,17 +501,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // TMA loads of both CTAs complete on the leader's `full` barriers; tcgen05.commit multicasts to
 // both CTAs' `empty` / `tmem_full` barriers; both epilogues release the accumulator on the
 // leader's `tmem_empty` barrier.  Everything else is the 1-CTA kernel.
-template <int STAGES, int SLABS, int AUX>
+template <int BN, int STAGES, int SLABS, int AUX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kIgemmThreads, 1)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
               const __grid_constant__ CUtensorMap tmAux1, const __grid_constant__ CUtensorMap tmAux2,
               const IgemmParams p) {
-  constexpr int BN = 256;
   constexpr int kBBytes = (BN / 2) * kBK * 2;      // this CTA's half of the weight tile
   constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
   constexpr int kEpiWarps = 8;
-  constexpr int kChunksPerWarp = 2;
+  constexpr int kChunksPerWarp = BN / 128;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
@@ -1258,19 +1257,19 @@ static int launch_igemm(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t 
   return 0;
 }
 
-template <int STAGES, int SLABS, int AUX>
+template <int BN, int STAGES, int SLABS, int AUX>
 static int launch_igemm2(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t stream) {
-  constexpr int smem = STAGES * (kABytes + 128 * kBK * 2) + 8 * (SLABS + AUX) * kSlabBytes + 1024;
+  constexpr int smem = STAGES * (kABytes + (BN / 2) * kBK * 2) + 8 * (SLABS + AUX) * kSlabBytes + 1024;
   static_assert(smem + 8192 + 512 <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(igemm2_kernel<STAGES, SLABS, AUX>,
+    SIB_CUDA(cudaFuncSetAttribute(igemm2_kernel<BN, STAGES, SLABS, AUX>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   int pairs = (p.num_m_tiles / 2) * p.num_n_tiles;
   if (pairs > sm_count() / 2) pairs = sm_count() / 2;
-  SIB_CUDA(launch_pdl(igemm2_kernel<STAGES, SLABS, AUX>, dim3(2 * pairs), dim3(kIgemmThreads), smem,
+  SIB_CUDA(launch_pdl(igemm2_kernel<BN, STAGES, SLABS, AUX>, dim3(2 * pairs), dim3(kIgemmThreads), smem,
                       stream, tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p));
   return 0;
 }
@@ -1428,10 +1427,12 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   }
   if (rc) return rc;
   // 2-CTA pairs (M = 256 per cluster) for the tensor-bound shapes
+  // (a 2-CTA variant with a 128-column tile measured no faster than the 1-CTA kernel:
+  //  128 -> 128 3x3 at 28x28 0.094 vs 0.092 ms)
   const bool two_cta = BN == 256 && p.num_m_tiles % 2 == 0 && p.num_kblocks >= 4 &&
                        !(flags & SIB_FLAG_NO_2CTA);
   rc = make_tmap_2d_bf16(&tm.b, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin,
-                         two_cta ? 128 : BN, kBK, true);
+                         two_cta ? BN / 2 : BN, kBK, true);
   if (rc) return rc;
   const void* res_p = residual ? residual : out;
   const void* aux1_p = aux >= 1 ? fuse->aux1 : out;
@@ -1462,19 +1463,19 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   if (p.stats != nullptr && !(flags & SIB_FLAG_STATS_ZEROED))
     SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * p.stat_c, stream));
   if (aux == 0) {
-    if (two_cta) return launch_igemm2<5, 1, 0>(tm, p, stream);
+    if (two_cta) return launch_igemm2<256, 5, 1, 0>(tm, p, stream);
     if (BN == 64) return launch_igemm<64, 6, 2, 0>(tm, p, stream);
     if (BN == 128) return launch_igemm<128, 5, 1, 0>(tm, p, stream);
     return launch_igemm<256, 3, 2, 0>(tm, p, stream);
   }
   // fused variants trade pipeline stages for the auxiliary slabs (227 KB of smem per CTA)
   if (aux == 1) {
-    if (two_cta) return launch_igemm2<4, 1, 1>(tm, p, stream);
+    if (two_cta) return launch_igemm2<256, 4, 1, 1>(tm, p, stream);
     if (BN == 64) return launch_igemm<64, 6, 2, 1>(tm, p, stream);
     if (BN == 128) return launch_igemm<128, 4, 1, 1>(tm, p, stream);
     return launch_igemm<256, 3, 1, 1>(tm, p, stream);
   }
-  if (two_cta) return launch_igemm2<3, 1, 2>(tm, p, stream);
+  if (two_cta) return launch_igemm2<256, 3, 1, 2>(tm, p, stream);
   if (BN == 64) return launch_igemm<64, 6, 2, 2>(tm, p, stream);
   if (BN == 128) return launch_igemm<128, 3, 1, 2>(tm, p, stream);
   return launch_igemm<256, 2, 1, 2>(tm, p, stream);

@@ -29,6 +29,8 @@ CONV_CASES = [
     (3, 7, 7, 512, 512, 3, 1, 1, 0),
     (32, 1, 1, 2048, 1000, 1, 1, 0, 0),                       # FC: ragged N
     (40, 12, 12, 64, 256, 1, 1, 0, 0),                        # > 1 tile per persistent CTA on small grids
+    (8, 16, 16, 128, 128, 3, 1, 1, ops.FLAG_NO_HALO),         # 128-column tiles, even tile count
+    (8, 16, 16, 256, 128, 1, 1, 0, 0),                        # N = 128, 4 k-blocks
     # halo-reuse 3x3 kernel (one padded region per tile, taps = row-shifted UMMA descriptors)
     (2, 16, 16, 64, 64, 3, 1, 1, ops.FLAG_FORCE_HALO),        # resident weights, partial last h-tile
     (4, 14, 14, 128, 128, 3, 1, 1, ops.FLAG_FORCE_HALO),      # 2 channel blocks, streamed weights
@@ -95,6 +97,7 @@ FUSED_CASES = [
     (2, 16, 16, 256, 64, 1, 1, 0, "stored"),        # conv1 dgrad + shortcut -> previous block's bn3 (BN=256)
     (8, 16, 16, 512, 256, 1, 1, 0, "stored"),       # 2-CTA kernel (4 k-blocks, even tiles), leaky
     (8, 16, 16, 256, 256, 3, 1, 1, "recompute"),    # 2-CTA kernel, one auxiliary tile
+    (8, 16, 16, 128, 128, 3, 1, 1, "recompute"),    # 128-column tile, one auxiliary tile
     (3, 7, 7, 1024, 256, 1, 1, 0, "stored"),        # ragged M, several n-tiles
     (2, 56, 56, 64, 64, 3, 1, 1, "recompute"),      # halo-reuse kernel, resident weights
     (3, 28, 28, 128, 128, 3, 1, 1, "recompute"),    # halo-reuse kernel, streamed weights
