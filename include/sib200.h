@@ -181,6 +181,22 @@ int sib_sphere_linear_bwd(const float* dcos, const float* x_or_xn, const float* 
                           const float* xnorm, const float* wnorm, float* dx, float* dw,
                           float* scratch, int B, int C, int D, int normalize_x, void* stream);
 
+/* ---- data-parallel: one-shot all-reduce of small fp32 vectors over NVLink peer memory (SyncBN
+ *      statistics; replaces the per-layer NCCL all-reduce of SyncBatchNorm under DDP, reference
+ *      train.py:113-114).  Every rank allocates a mailbox + flag buffer with sib_ipc_alloc, the
+ *      64-byte handles are exchanged by the host, peers map them with sib_ipc_open.
+ *      table_dev: device struct { u64* mailbox[8]; void* unused[8]; } indexed by rank.
+ *      Mailbox layout [2 parities][parity_stride 8-byte words] ({value, epoch} per float); call
+ *      `slot` uses words [slot_off, slot_off + world*n); epochs_dev [num_slots] u32 (local).
+ *      All ranks must issue the same sequence of calls.  data is summed in place, bitwise
+ *      identical on every rank. ---- */
+int sib_ipc_alloc(unsigned long long bytes, void** ptr, unsigned char* handle64);
+int sib_ipc_open(const unsigned char* handle64, void** ptr);
+int sib_ipc_close(void* ptr);
+int sib_ipc_free(void* ptr);
+int sib_peer_allreduce(float* data, int n, const void* table_dev, long slot_off, long parity_stride,
+                       int slot, int num_slots, void* epochs_dev, int rank, int world, void* stream);
+
 /* ---- optimizer: torch.optim._multi_tensor.SGD (arg_parser.py:136-138), ModelEma
  *      (train.py:112), weight standardisation (train.py:66-67, model.py:91-100) ---- */
 /* segs_dev: nseg x {long end; float lr, weight_decay, momentum, dampening; int nesterov, pad} */

@@ -44,6 +44,45 @@ if rank == 0:
     # chaos described in DESIGN.md (the two runs differ only in fp32 summation order, which is
     # enough to flip bf16 roundings), so they get loose gates.
     ok = abs(ltot.item() - lb.item()) / lb.item() < 1e-2 and early < 2e-3 and late < 0.15 and fc > 0.95
+# ---- the peer-memory one-shot all-reduce itself: == NCCL, bitwise identical across ranks, eager and
+#      replayed from a CUDA graph (epochs / parity buffers keep working across replays)
+from sota_imagenet_b200 import ops
+if ops.PEER is not None:
+    torch.cuda.synchronize(); ops.PEER.reset_layout(); dist.barrier()
+    g = torch.Generator(device="cuda").manual_seed(100 + rank)
+    sizes = [128, 4096, 8192, 512, 16]
+    vecs = [torch.randn(n, device="cuda", generator=g) for n in sizes]
+    def run_all(out):
+        ops.PEER.begin_forward()
+        for v, o in zip(vecs, out):
+            o.copy_(v); ops.PEER.allreduce_(o)
+    outs = [torch.empty_like(v) for v in vecs]
+    for it in range(5):
+        run_all(outs)
+    refs = [v.clone() for v in vecs]
+    for r_ in refs: dist.all_reduce(r_)
+    torch.cuda.synchronize()
+    peer_ok = all(float((o - r_).abs().max()) <= 1e-5 * float(r_.abs().max()) for o, r_ in zip(outs, refs))
+    s_ = torch.cuda.Stream(); s_.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_):
+        run_all(outs)
+    torch.cuda.current_stream().wait_stream(s_)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        run_all(outs)
+    for it in range(7):
+        graph.replay()
+    torch.cuda.synchronize()
+    peer_ok = peer_ok and all(float((o - r_).abs().max()) <= 1e-5 * float(r_.abs().max()) for o, r_ in zip(outs, refs))
+    same = torch.stack([o.double().sum() for o in outs])
+    lo_, hi_ = same.clone(), same.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    peer_ok = peer_ok and bool((lo_ == hi_).all())
+    if rank == 0:
+        print("peer all-reduce: %s (%d calls eager + graph)" % ("OK" if peer_ok else "MISMATCH", 13 * len(sizes)))
+    ok = ok and peer_ok
+elif rank == 0:
+    print("peer all-reduce: not active (NCCL path)")
 # every rank holds identical averaged gradients
 chk = torch.stack([g.sum() for g in g_dp.values()]).sum()
 lo, hi = chk.clone(), chk.clone()

@@ -125,7 +125,7 @@ class PaddedBatchNorm2d(BatchNorm2d):
             world = self._world()
             count = n * h * w
             if world > 1:
-                torch.distributed.all_reduce(stats, group=self.process_group)
+                ops.small_allreduce_(stats, self.process_group)
                 count *= world
             rm, rv = self._padded(self.running_mean, 0.0), self._padded(self.running_var, 1.0)
             mi, ss = ops.bn_finalize(stats, self._padded(self.weight.data, 1.0), self._padded(self.bias.data, 0.0),

@@ -113,7 +113,7 @@ class SibModule(nn.Module):
         a = self.ensure_arena()
         if a is not None:
             a.refresh_shadow()
-        ops.begin_pass(x.device)
+        ops.begin_pass(x.device, forward=True)
         x = self._prepare_input(x)
         if self.training and getattr(self, "_nbt", None) is not None:
             self._nbt += 1
@@ -271,7 +271,7 @@ class BatchNorm2d(SibModule):
                                            self.running_var, self.eps), count
         world = self._world()
         if world > 1:
-            torch.distributed.all_reduce(stats, group=self.process_group)
+            ops.small_allreduce_(stats, self.process_group)
             count = count * world
         mi, ss = ops.bn_finalize(stats, self.weight.data, self.bias.data, self.running_mean,
                                  self.running_var, count, self.eps, self.momentum)
@@ -283,7 +283,7 @@ class BatchNorm2d(SibModule):
         all-reduces the statistics first under SyncBN.  Returns (args, world)."""
         world = self._world()
         if world > 1:
-            torch.distributed.all_reduce(stats, group=self.process_group)
+            ops.small_allreduce_(stats, self.process_group)
         self._count_batch()
         return (stats, self.weight.data, self.bias.data, self.running_mean, self.running_var), world
 
@@ -293,7 +293,7 @@ class BatchNorm2d(SibModule):
 
     def reduce_sums(self, sums):
         if self._world() > 1:
-            torch.distributed.all_reduce(sums, group=self.process_group)
+            ops.small_allreduce_(sums, self.process_group)
         return sums
 
     def grad_ptrs(self):

@@ -104,9 +104,23 @@ if _DEBUG_POOL:
 _USE_POOL = os.environ.get("SIB_ACC_POOL", "1") != "0"
 
 
-def begin_pass(device):
+PEER = None      # parallel.PeerAllReduce once a SyncBN data-parallel wrapper has set it up
+
+
+def begin_pass(device, forward=False):
     """Called by the root module at the start of a forward or backward pass."""
     _ACC_POOL.reset(device)
+    if forward and PEER is not None:
+        PEER.begin_forward()
+
+
+def small_allreduce_(t, group=None):
+    """Sum a small fp32 statistics tensor over the ranks: peer-memory one-shot kernel when
+    available (same group), else torch.distributed."""
+    if PEER is not None and PEER.group is group and t.is_cuda:
+        return PEER.allreduce_(t)
+    torch.distributed.all_reduce(t, group=group)
+    return t
 
 
 def new_acc(rows, c, device):

@@ -44,6 +44,104 @@ def allreduce_mean_(flat, lo, hi, group=None, async_op=False):
     return work if async_op else None
 
 
+class PeerAllReduce:
+    """One-shot all-reduce of small fp32 vectors over NVLink peer memory (csrc/peer.cu): the 106
+    sequentially dependent SyncBN reductions of a ResNet-50 step no longer pay a collective-library
+    latency each.  Single node, one process per GPU, <= 8 ranks; every rank must issue the same
+    sequence of calls per step (it does: same model).  Call slots restart at every forward pass."""
+    SLOTS = 512
+    CAPACITY = 1 << 21            # 8-byte words per parity (16 MB): sum over calls of world * n
+
+    def __init__(self, group=None):
+        import ctypes
+        from . import _lib, ops
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        assert 1 <= self.world <= 8
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        lib = _lib.load()
+        self._lib, self._check = lib, _lib.check
+        flag_bytes = 2 * self.SLOTS * self.world * 4
+        mine, err = [], None
+        try:
+            for nbytes in (2 * self.CAPACITY * 8, flag_bytes):
+                ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+                _lib.check(lib.sib_ipc_alloc(nbytes, ctypes.byref(ptr), handle))
+                mine.append((ptr.value, bytes(handle)))
+            torch.cuda.synchronize()
+        except Exception as e:
+            err = e
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, None if err else [h for _, h in mine], group=group)
+        self._local = [p for p, _ in mine]
+        self._opened = []
+        table = []
+        try:
+            if err or any(g is None for g in gathered):
+                raise RuntimeError("IPC allocation failed on some rank: %s" % err)
+            for kind in range(2):
+                for r in range(self.world):
+                    if r == self.rank:
+                        table.append(mine[kind][0])
+                    else:
+                        ptr = ctypes.c_void_p()
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(gathered[r][kind])
+                        _lib.check(lib.sib_ipc_open(buf, ctypes.byref(ptr)))
+                        self._opened.append(ptr.value)
+                        table.append(ptr.value)
+                table += [0] * (8 - self.world)
+        except Exception as e:
+            err = e
+        ok = torch.tensor([0.0 if err else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)     # also: all mailboxes mapped
+        if ok.item() != 1.0:
+            raise RuntimeError("peer mailboxes could not be mapped on every rank (%s)" % err)
+        self.table = torch.tensor(table, dtype=torch.int64).to(self.device)     # PeerTable
+        self.epochs = torch.zeros(self.SLOTS, dtype=torch.int32, device=self.device)
+        self.slot = 0
+        self.offset = 0
+        self._layout = {}          # slot -> (offset, n): fixed after the first step
+
+    def begin_forward(self):
+        self.slot, self.offset = 0, 0
+
+    def reset_layout(self):
+        """Forget the per-slot sizes (a different model is about to use the mailboxes).  Collective:
+        call on every rank, followed by a barrier, before the next reduction."""
+        self._layout = {}
+        self.slot, self.offset = 0, 0
+
+    def allreduce_(self, t):
+        """In-place sum of a contiguous fp32 tensor (numel % 4 == 0) over the ranks."""
+        from . import ops
+        n = t.numel()
+        s = self.slot
+        lay = self._layout.get(s)
+        if lay is None:
+            lay = self._layout[s] = (self.offset, n)
+        off, n0 = lay
+        if n0 != n or s >= self.SLOTS or off + self.world * n > self.CAPACITY or not t.is_contiguous():
+            raise RuntimeError("PeerAllReduce: call sequence changed (slot %d: %d vs %d floats)" % (s, n0, n))
+        self.slot += 1
+        self.offset = off + self.world * n
+        ops.call("sib_peer_allreduce", ops._p(t), n, ops._p(self.table), off, self.CAPACITY, s, self.SLOTS,
+                 ops._p(self.epochs), self.rank, self.world, ops._stream())
+        return t
+
+    def close(self):
+        for p in self._opened:
+            self._lib.sib_ipc_close(ctypes_void(p))
+        for p in self._local:
+            self._lib.sib_ipc_free(ctypes_void(p))
+        self._opened, self._local = [], []
+
+
+def ctypes_void(v):
+    import ctypes
+    return ctypes.c_void_p(v)
+
+
 def convert_sync_batchnorm(module, process_group=None):
     for m in module.modules():
         if isinstance(m, BatchNorm2d):
@@ -66,6 +164,21 @@ class DataParallel(nn.Module):
         self._plan = None
         if sync_bn:
             convert_sync_batchnorm(module, process_group)
+            # SyncBN statistics over NVLink peer memory instead of one NCCL all-reduce per layer
+            import os
+            from . import ops
+            if (self.world_size > 1 and self.world_size <= 8 and dist.get_backend(process_group) == "nccl"
+                    and os.environ.get("SIB_PEER_ALLREDUCE", "1") != "0"):
+                if ops.PEER is None:
+                    # every rank must take the same path: agree on success before using it
+                    try:      # (the constructor agrees on success across ranks before raising)
+                        ops.PEER = PeerAllReduce(process_group)
+                    except RuntimeError as e:    # no peer access / IPC unavailable: NCCL path
+                        print("sota_imagenet_b200: peer-memory all-reduce unavailable (%s); using NCCL" % e)
+                else:
+                    torch.cuda.synchronize()
+                    ops.PEER.reset_layout()
+                    dist.barrier(group=process_group)
         arena = module.ensure_arena()
         if self.world_size > 1:
             dist.broadcast(arena.flat, 0, group=process_group)
