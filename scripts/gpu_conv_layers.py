@@ -50,6 +50,13 @@ for (c, k, h, r, stride, pad, cnt) in SHAPES:
     fns = {"fprop": lambda: ops.conv2d_fprop(x, w, stride=stride, pad=pad, stats=stats, flags=FLAGS),
            "dgrad": lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad, flags=FLAGS, w_s2=ws2, out=dx_buf),
            "wgrad": lambda: ops.conv2d_wgrad(x, dy, dw, stride=stride, pad=pad)}
+    if "--fused" in sys.argv:
+        # dgrad with the fused BN-backward reduction (mask recomputed from the BN input)
+        mi = torch.stack([x.float().mean(dim=(0, 2, 3)), torch.ones(c, device="cuda")]).contiguous()
+        ss = torch.stack([torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")]).contiguous()
+        fuse = dict(mask_src=x, mask_ss=ss, mean_invstd=mi, act=ops.ACT_RELU, slope=0.0)
+        fns["dgrad+bn"] = lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad, flags=FLAGS, w_s2=ws2, bn_bwd=fuse)
+        fns["reduce"] = lambda: ops.bn_bwd_reduce(x, None, x, mi, ops.ACT_RELU, 0.0, mask_ss=ss)
     flops = 2.0 * B * oh * oh * k * c * r * r
     byt = 2.0 * B * (h * h * c + oh * oh * k) + 2.0 * k * c * r * r
     ideal = max(flops / TF, byt / BW) * 1e3
@@ -63,8 +70,11 @@ for (c, k, h, r, stride, pad, cnt) in SHAPES:
         torch.cuda.profiler.stop()
         continue
     t = {n: timeit(f) for n, f in fns.items()}
-    for n in t: tot[n] += t[n] * cnt
+    for n in t: tot[n] = tot.get(n, 0.0) + t[n] * cnt
     ideal_tot += ideal * cnt
+    if "--fused" in sys.argv:
+        print("%-24s dgrad %.3f  dgrad+bn %.3f  separate reduce %.3f ms" % (str((c, k, h, r, stride)), t["dgrad"], t["dgrad+bn"], t["reduce"]))
+        continue
     print("%-24s %5d | %8.3f %8.3f %8.3f | %8.3f   %4.0f %4.0f %4.0f" % (
         str((c, k, h, r, stride)), cnt, t["fprop"], t["dgrad"], t["wgrad"], ideal,
         flops / t["fprop"] / 1e9, flops / t["dgrad"] / 1e9, flops / t["wgrad"] / 1e9))

@@ -25,6 +25,7 @@ from .arena import ParamArena
 # bn_bwd_reduce passes (kept for A/B measurements and as the parity cross-check).
 FUSE_BN_BWD = os.environ.get("SIB_FUSE_BN_BWD", "1") != "0"
 # 3x3 / stride-2 dgrad by row parity (csrc/conv.cu dgrad_s2_impl); 0 = zero-inserted dy
+FUSE_BN_BWD_ALL = os.environ.get("SIB_FUSE_BN_BWD_ALL", "0") == "1"   # A/B: fuse even where it loses
 DGRAD_S2 = os.environ.get("SIB_DGRAD_S2", "1") != "0"
 
 
@@ -508,7 +509,13 @@ class Bottleneck(SibModule):
                                          bn2.slope, mask_ss=ss2, param_grads=bn2.grad_ptrs())
         # ---- conv2, bn1 + act ----
         self.conv2.run_wgrad(a1, dc2)
-        if FUSE_BN_BWD:
+        # Measured (B200, batch 256): the fused reduction LOSES where conv2's dgrad runs on the
+        # halo-reuse kernel (64 -> 64 at 56x56: 0.172 ms fused vs 0.062 + 0.045 ms separate; its
+        # epilogue reads the BN input with exposed global loads) and on the row-parity stride-2
+        # path (0.195 vs 0.097 + 0.078 ms); everywhere else it wins or is neutral.
+        fuse1 = FUSE_BN_BWD and (FUSE_BN_BWD_ALL or self.stride == 1) and not (not FUSE_BN_BWD_ALL and ops.halo_applies(a1.shape[1], dc2.shape[1], 3, 1,
+                                                                                                    a1.shape[3]))
+        if fuse1:
             da1, sums = self.conv2.run_dgrad(dc2, tuple(a1.shape), bn_bwd=dict(
                 mask_src=c1, mask_ss=ss1, mean_invstd=mi1, act=bn1.act, slope=bn1.slope))
             dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, bn1.reduce_sums(sums), cnt1,

@@ -207,6 +207,12 @@ def pack_dgrad_s2(w_dgrad, sub0=None, sub1=None):
     return sub0, sub1
 
 
+def halo_applies(c_out, c_in, r, stride, width):
+    """Mirror of the automatic dispatch in csrc/conv.cu run_igemm: the halo-reuse kernel takes the
+    3x3 / stride-1 / pad-1 convolutions with 64 -> 64 channels at >= 28 columns."""
+    return r == 3 and stride == 1 and c_out == 64 and c_in == 64 and 28 <= width <= 61
+
+
 def dgrad_s2_ok(x_shape, r, s, stride, pad):
     n, c, h, w = x_shape
     return r == 3 and s == 3 and stride == 2 and pad == 1 and h % 2 == 0 and w % 2 == 0 and w // 2 <= 32 \
