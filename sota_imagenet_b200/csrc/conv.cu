@@ -78,14 +78,19 @@ __device__ __forceinline__ void igemm_epilogue(
     uint32_t tmem_base, int first_tile, int tile_step, int num_tiles, int cta_rank) {
   constexpr int kChunks = BN / 64;
   constexpr int kHalves = kChunks >= 2 ? 2 : 1;
-  constexpr int kEpiWarps = 4 * kHalves;
+  // BN = 64 has a single 64-column chunk: its eight epilogue warps form TWO groups that take
+  // alternate tiles (group g drains accumulator stage g), so two epilogues are in flight and
+  // their latency no longer bounds the tile rate of the N = 64 kernels (stem, 64-channel 1x1).
+  constexpr int kGroups = (BN == 64 && !kTwoCta) ? 2 : 1;
+  constexpr int kEpiWarps = 4 * kHalves * kGroups;
   constexpr int kChunksPerWarp = kChunks / kHalves;
   constexpr int kPartStride = kChunksPerWarp * 64;       // s_part[e][2][kPartStride]
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int e = warp - 4;
   const int quarter = e & 3;                // TMEM lane quarter (== warp % 4)
-  const int half = e >> 2;                  // which interleaved set of 64-column chunks
+  const int group = kGroups == 2 ? (e >> 2) : 0;
+  const int half = kGroups == 2 ? 0 : (e >> 2);   // which interleaved set of 64-column chunks
   uint8_t* slabs = smem_slab + e * SLABS * kSlabBytes;
   uint8_t* aux = smem_aux + e * (AUX > 0 ? AUX : 1) * kSlabBytes;
   const int et = threadIdx.x - 128;         // 0 .. 32*kEpiWarps-1
@@ -103,16 +108,18 @@ __device__ __forceinline__ void igemm_epilogue(
   // One n-tile per launch (Cout <= BN, all the 56x56 layers): every tile of this CTA covers the
   // same columns, so the per-channel sums are accumulated in this warp's s_part slots for the
   // whole kernel and published once at the end -- no named barrier and no 2*BN atomics per tile.
-  const bool cta_sums = p.stats != nullptr && p.num_n_tiles == 1;
+  const bool cta_sums = p.stats != nullptr && (p.num_n_tiles == 1 || kGroups == 2);
   if (cta_sums) {
     for (int i = lane; i < 2 * kPartStride; i += 32) s_part[e * 2 * kPartStride + i] = 0.f;
     __syncwarp();
   }
-  int acc = 0;
+  int acc = group;
   uint32_t acc_phase = 0;
   uint32_t res_phase = 0;
   int slab_idx = 0;
-  for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+  int local = 0;
+  for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local) {
+    if (kGroups == 2 && (local & 1) != group) continue;
     const int m0 = kTwoCta ? (tile / p.num_n_tiles) * 2 * kBM + cta_rank * kBM
                            : (tile / p.num_n_tiles) * kBM;
     const int n0 = (tile % p.num_n_tiles) * BN;
@@ -327,7 +334,12 @@ __device__ __forceinline__ void igemm_epilogue(
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     }
-    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    if (kGroups == 2) {
+      acc_phase ^= 1;            // this group always drains accumulator stage `group`
+    } else if (++acc == 2) {
+      acc = 0;
+      acc_phase ^= 1;
+    }
   }
   if (cta_sums) {
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -338,7 +350,7 @@ __device__ __forceinline__ void igemm_epilogue(
         const int h = chunk % kHalves, ci = chunk / kHalves, lc = ci * 64 + (c & 63);
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 4 * kGroups; ++q) {
           const float4 v = *reinterpret_cast<const float4*>(&s_part[((h * 4 + q) * 2 + kind) * kPartStride + lc]);
           t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
@@ -367,7 +379,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
   constexpr int kChunks = BN / 64;
   constexpr int kHalves = kChunks >= 2 ? 2 : 1;    // epilogue warp groups splitting the columns
-  constexpr int kEpiWarps = 4 * kHalves;
+  constexpr int kWarpsPerAcc = 4 * kHalves;        // warps that drain one accumulator stage
+  constexpr int kEpiWarps = BN == 64 ? 8 : kWarpsPerAcc;   // BN = 64: two groups on alternate tiles
   constexpr int kChunksPerWarp = kChunks / kHalves;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
@@ -399,7 +412,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kEpiWarps);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], kWarpsPerAcc);   // one arrival per epilogue warp of the stage
     }
     for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
@@ -1240,10 +1253,10 @@ struct IgemmMaps {
 
 template <int BN, int STAGES, int SLABS, int AUX>
 static int launch_igemm(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t stream) {
-  constexpr int kEpiWarps = BN >= 128 ? 8 : 4;
+  constexpr int kEpiWarps = 8;
   constexpr int smem =
       STAGES * (kABytes + BN * kBK * 2) + kEpiWarps * (SLABS + AUX) * kSlabBytes + 1024;
-  static_assert(smem + kEpiWarps * 2 * (BN / (kEpiWarps / 4)) * 4 + 512 <= 232448, "shared memory budget");
+  static_assert(smem + 8192 + 512 <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS, AUX>,
@@ -1464,19 +1477,19 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
     SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * p.stat_c, stream));
   if (aux == 0) {
     if (two_cta) return launch_igemm2<256, 5, 1, 0>(tm, p, stream);
-    if (BN == 64) return launch_igemm<64, 6, 2, 0>(tm, p, stream);
+    if (BN == 64) return launch_igemm<64, 6, 1, 0>(tm, p, stream);
     if (BN == 128) return launch_igemm<128, 5, 1, 0>(tm, p, stream);
     return launch_igemm<256, 3, 2, 0>(tm, p, stream);
   }
   // fused variants trade pipeline stages for the auxiliary slabs (227 KB of smem per CTA)
   if (aux == 1) {
     if (two_cta) return launch_igemm2<256, 4, 1, 1>(tm, p, stream);
-    if (BN == 64) return launch_igemm<64, 6, 2, 1>(tm, p, stream);
+    if (BN == 64) return launch_igemm<64, 6, 1, 1>(tm, p, stream);
     if (BN == 128) return launch_igemm<128, 4, 1, 1>(tm, p, stream);
     return launch_igemm<256, 3, 1, 1>(tm, p, stream);
   }
   if (two_cta) return launch_igemm2<256, 3, 1, 2>(tm, p, stream);
-  if (BN == 64) return launch_igemm<64, 6, 2, 2>(tm, p, stream);
+  if (BN == 64) return launch_igemm<64, 5, 1, 2>(tm, p, stream);
   if (BN == 128) return launch_igemm<128, 3, 1, 2>(tm, p, stream);
   return launch_igemm<256, 2, 1, 2>(tm, p, stream);
 }
