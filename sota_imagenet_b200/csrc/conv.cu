@@ -466,6 +466,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ---- MMA issuer: the whole warp runs the loop converged, one elected lane issues ----
+    // (Two issuing warps on alternate tiles, as in the halo kernel, were tried for BN = 64 and
+    //  REMOVED: with a shared k-block ring a warp can wait on lap L of a stage whose lap L-1 --
+    //  owned by the other warp -- has not completed yet; the parity test then passes at once and
+    //  the MMAs read data still in flight (launch failure at full size).  The halo kernel's ring
+    //  holds one whole tile per stage and both of its issuing warps observe every tile's barrier.)
     constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
     const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), 16, 1024, kSwizzle128B);
     const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), 16, 1024, kSwizzle128B);
@@ -791,9 +796,15 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       int i = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++i) {
-        if ((i & 1) != g) continue;
         const int st = i % kHaloAStages;
         const uint32_t ph = (uint32_t)(i / kHaloAStages) & 1u;
+        if ((i & 1) != g) {
+          // not this warp's tile, but OBSERVE its barrier: a parity wait can only be trusted by
+          // a waiter that has seen every earlier lap of the stage complete (otherwise "previous
+          // lap still in flight" looks like "this lap done")
+          mbar_wait_w(&a_full[st], ph);
+          continue;
+        }
         const uint32_t acc_ph = (uint32_t)(i >> 1) & 1u;
         mbar_wait_w(&tmem_empty_bar[g], acc_ph ^ 1);
         tc_fence_after();
