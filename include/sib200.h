@@ -32,6 +32,7 @@ extern "C" {
 #define SIB_MARGIN_ARC 1 /* AdditiveAngularMarginLoss, angular_losses.py:128-146 */
 #define SIB_MARGIN_COS 2 /* CosFace, angular_losses.py:186-198 and :332-333      */
 #define SIB_MARGIN_ARC_PURE 3 /* cos(theta + m) without fallback, angular_losses.py:78-83 */
+#define SIB_MARGIN_ARCCOS 4 /* z = -(acos(clamp(cos)) + m[target]) * s: ArcCosSoftmax :572-576, AdaCos arc_logits :323-330 */
 
 /* conv flags */
 #define SIB_FLAG_FORCE_IM2COL 1 /* use the im2col TMA path even for plain 1x1 (testing) */
@@ -203,6 +204,15 @@ int sib_peer_allreduce(float* data, int n, const void* table_dev, long slot_off,
 int sib_sgd_step(float* params, const float* grads, float* momentum_buf, void* params_bf16,
                  float* ema, float ema_decay, const void* segs_dev, int nseg, long n,
                  int first_step, void* stream);
+/* MyNovograd (reference sota_imagenet/optimizers.py:35-161): per-tensor (or per-output-unit,
+ * unitwise_norm=True) running norm of the WEIGHTS (:133-140), first moment of the gradient
+ * (:143-147), p = (p - lr*ema_grad/(sqrt(ema_norm)+eps)) * (1 - lr*wd) (:155-158).
+ * table_dev: ntensors x {long begin, end; int unit_len, ngroups, norm_base; float lr, decay,
+ * beta1, one_minus_beta1, beta2, one_minus_beta2; int pad}; group_* are [total groups] fp32. */
+int sib_novograd_step(float* params, const float* grads, float* ema_grad, void* params_bf16,
+                      float* ema, float ema_decay, const void* table_dev, int ntensors,
+                      float* group_sumsq, float* group_ema_norm, float* group_denom, long n,
+                      float eps, int unitwise, void* stream);
 int sib_cast_bf16(const float* src, void* dst, long n, void* stream);
 /* table_dev: nent x {long src_off, dst_off; int K, RS, C, block_begin} */
 int sib_pack_dgrad_weights(const void* w_bf16, void* w_dgrad, const void* table_dev, int nent,

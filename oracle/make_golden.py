@@ -128,6 +128,80 @@ def augment():
                os.path.join(OUT, "augment.pt"))
 
 
+def heads_arccos():
+    """ArcCosSoftmax and AdaCos(arc_logits) of the reference (angular_losses.py:572-576,
+    :323-330), index and soft targets; includes cosines at and beyond the clamp range."""
+    ang, _, RefCE = load_reference_modules()
+    torch.manual_seed(3)
+    b, c = 16, 40
+    cos = torch.rand(b, c) * 2 - 1
+    cos[0, 0], cos[0, 1], cos[1, 2], cos[2, 3] = 1.0, -1.0, 1.0 - 1e-7, 0.99999
+    y = torch.randint(0, c, (b,))
+    y[0], y[1] = 0, 2
+    soft = torch.zeros(b, c).scatter_(1, y[:, None], 0.7)
+    soft.scatter_(1, ((y + 5) % c)[:, None], 0.3)
+    out = {"cos": cos, "y": y, "soft": soft}
+    for name, crit, tgt in (
+        ("arccos", ang.ArcCosSoftmax(smoothing=0.1), y),
+        ("arccos_t015", ang.ArcCosSoftmax(smoothing=0.1, temperature=0.15), y),
+        ("arccos_soft", ang.ArcCosSoftmax(smoothing=0.1), soft),
+        ("adacos_arc", ang.AdaCos(final_criterion=RefCE(smoothing=0.1), margin=0.2, fixed_s=10,
+                                  arc_logits=True, arc_margin=True), y),
+        ("adacos_arc_soft", ang.AdaCos(final_criterion=RefCE(smoothing=0.1), margin=0.2, fixed_s=10,
+                                       arc_logits=True, arc_margin=True), soft),
+    ):
+        cr = cos.clone().requires_grad_(True)
+        loss = crit(cr, tgt)
+        loss.backward()
+        out[name] = {"loss": loss.detach(), "dcos": cr.grad.clone()}
+    l = torch_ref.smooth_cross_entropy(torch_ref.arccos_logits(cos), y, 0.1)
+    assert torch.allclose(l, out["arccos"]["loss"], atol=1e-6)
+    l = torch_ref.smooth_cross_entropy(torch_ref.arccos_logits(cos, soft, 10.0, 0.2), soft, 0.1)
+    assert torch.allclose(l, out["adacos_arc_soft"]["loss"], atol=1e-5)
+    torch.save(out, os.path.join(OUT, "heads_arccos.pt"))
+
+
+def novograd():
+    """The reference's own MyNovograd (sota_imagenet/optimizers.py:35-161) on a small mixed bag
+    of tensors (conv with odd fan 7*7*3, 3x3 conv, linear, 1-D, a gradient-less tensor), five
+    steps with a changing learning rate, whole-tensor and unitwise norms."""
+    _, ropt, _ = load_reference_modules()
+    torch.manual_seed(4)
+    shapes = [(8, 3, 7, 7), (16, 8, 3, 3), (10, 12), (24,), (6, 4, 1, 1), (5,)]
+    p0 = [torch.randn(s) * 0.5 for s in shapes]
+    steps = 5
+    grads = [[torch.randn(s) for s in shapes] for _ in range(steps)]
+    lrs = [1e-2, 2e-2, 5e-3, 4e-2, 1e-3]
+    nograd_index = 4            # this tensor never receives a gradient (reference :104-110 skips it)
+    out = {"shapes": shapes, "p0": p0, "grads": grads, "lrs": lrs, "nograd_index": nograd_index,
+           "runs": {}}
+    for unitwise in (False, True):
+        ps = [p.clone().requires_grad_(True) for p in p0]
+        opt = ropt.MyNovograd(ps, lr=0.0, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2,
+                              unitwise_norm=unitwise)
+        traj = []
+        for gs, lr in zip(grads, lrs):
+            opt.param_groups[0]["lr"] = lr
+            for i, (p, g) in enumerate(zip(ps, gs)):
+                p.grad = None if i == nograd_index else g.clone()
+            opt.step()
+            traj.append([p.detach().clone() for p in ps])
+        out["runs"]["unitwise" if unitwise else "tensor"] = {
+            "traj": traj,
+            "ema_grad": [opt.state[p]["ema_grad"].clone() if p in opt.state else None for p in ps],
+            "ema_norm": [opt.state[p]["ema_norm"].clone() if p in opt.state else None for p in ps]}
+        # the written-out restatement must reproduce the reference class
+        qs = [p.clone() for p in p0]
+        state = [{} for _ in qs]
+        for gs, lr, want in zip(grads, lrs, traj):
+            idx = [i for i in range(len(qs)) if i != nograd_index]
+            torch_ref.novograd_step([qs[i] for i in idx], [gs[i] for i in idx],
+                                    [state[i] for i in idx], lr, unitwise=unitwise)
+            for q, w in zip(qs, want):
+                assert torch.allclose(q, w, atol=1e-6, rtol=1e-5)
+    torch.save(out, os.path.join(OUT, "novograd.pt"))
+
+
 def resnet_step():
     """Tiny pin of the whole-step oracle: torchvision ResNet-50, B=2, 64x64, seed 0."""
     model = torch_ref.resnet50(seed=0)
@@ -146,4 +220,6 @@ if __name__ == "__main__":
     sgd()
     augment()
     resnet_step()
+    heads_arccos()
+    novograd()
     print("golden vectors written to", os.path.abspath(OUT))

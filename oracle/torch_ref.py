@@ -51,6 +51,38 @@ def cosface_logits(cosine, y_true, s=30.0, m=0.4):
     return ((one_hot * (cosine - m)) + ((1.0 - one_hot) * cosine)) * s
 
 
+def arccos_logits(cosine, y_true=None, s=1.0, m=0.0):
+    """reference angular_losses.py:572-576 (ArcCosSoftmax: s=1, m=0) and :323-330 (AdaCos
+    arc_logits): -(acos(clamp(cos, -1+1e-7, 1-1e-7)) + m on columns with target mass) * s."""
+    eps = 1e-7
+    theta = torch.acos(cosine.clamp(-1 + eps, 1 - eps))
+    if m:
+        onehot = y_true if y_true.dim() == 2 else torch.zeros_like(cosine).scatter_(1, y_true[:, None], 1.0)
+        theta = theta.where(onehot.eq(0), theta + m)
+    return theta.neg() * s
+
+
+def novograd_step(params, grads, state, lr, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2,
+                  ema_norm_init=1e-3, unitwise=False):
+    """One step of the reference's MyNovograd written out (sota_imagenet/optimizers.py:85-160).
+    `state` is a list of dicts (ema_grad tensor, ema_norm tensor of the norm-group shape)."""
+    b1, b2 = betas
+    for p, g, st in zip(params, grads, state):
+        if not st:
+            st["ema_grad"] = torch.zeros_like(p)
+            st["ema_norm"] = None
+        if unitwise:                                             # :18-22, :133-134
+            nrm = p.norm(2) if p.ndim <= 1 else p.norm(2, dim=tuple(range(1, p.ndim)), keepdim=True)
+        else:
+            nrm = p.pow(2).sum()                                 # :136 (weights, not gradients)
+        if st["ema_norm"] is None:
+            st["ema_norm"] = torch.full_like(nrm, ema_norm_init)
+        st["ema_norm"] = st["ema_norm"] * b2 + (1 - b2) * nrm    # :139-140
+        st["ema_grad"] = st["ema_grad"] * b1 + (1 - b1) * g      # :143,147
+        denom = st["ema_norm"].sqrt() + eps                      # :144-145
+        p.copy_((p - lr * st["ema_grad"] / denom) * (1 - lr * weight_decay))   # :155,158
+
+
 def resnet50(num_classes=1000, seed=0):
     import torchvision
     torch.manual_seed(seed)

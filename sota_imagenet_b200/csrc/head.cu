@@ -23,6 +23,10 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
   return __float2bfloat16_rn(v);
 }
 
+// clamp range of the arccos heads: EPS = 1e-7 (angular_losses.py:324,574) in fp32
+#define ARCCOS_HI (1.f - 1e-7f)
+#define ARCCOS_LO (-1.f + 1e-7f)
+
 struct MarginParams {
   int kind;        // SIB_MARGIN_*
   float s;         // logit scale
@@ -57,7 +61,13 @@ ce_kernel(const T* __restrict__ logits, const long* __restrict__ labels,
   float lmax = -INFINITY;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float v = to_f<T>(x[c]);
-    if (mp.kind != SIB_MARGIN_NONE) {
+    if (mp.kind == SIB_MARGIN_ARCCOS) {
+      // z = -(acos(clamp(x)) + m [target]) * s   (ArcCosSoftmax :572-576; AdaCos arc_logits :326-329)
+      float th = acosf(fminf(fmaxf(v, ARCCOS_LO), ARCCOS_HI));
+      const bool tgt = labels ? (c == y) : (dense_t[(long)row * C + c] != 0.f);
+      if (tgt) th += mp.m;
+      v = -th * mp.s;
+    } else if (mp.kind != SIB_MARGIN_NONE) {
       if (c == y) {
         if (mp.kind == SIB_MARGIN_ARC || mp.kind == SIB_MARGIN_ARC_PURE) {
           const float sine = sqrtf(fmaxf(1.f - v * v, 0.f));
@@ -120,7 +130,11 @@ ce_kernel(const T* __restrict__ logits, const long* __restrict__ labels,
       const float t = dense_t ? dense_t[(long)row * C + c] : (c == y ? 1.f : 0.f);
       float g = pr * wsum - ((1.f - smoothing) * t + smoothing / C);
       g *= grad_scale * inv_temp;
-      if (mp.kind != SIB_MARGIN_NONE) {
+      if (mp.kind == SIB_MARGIN_ARCCOS) {
+        // d(-acos(clamp(v)))/dv = 1/sqrt(1-v^2) inside the clamp range, 0 outside (torch clamp)
+        const float v0 = to_f<T>(x[c]);
+        g *= (v0 >= ARCCOS_LO && v0 <= ARCCOS_HI) ? mp.s * rsqrtf(1.f - v0 * v0) : 0.f;
+      } else if (mp.kind != SIB_MARGIN_NONE) {
         g *= mp.s;
         if (c == y) g *= dphi_t;
       }

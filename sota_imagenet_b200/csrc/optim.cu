@@ -74,6 +74,158 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// MyNovograd (reference sota_imagenet/optimizers.py:35-161) over one flat arena.
+//   norm_t   = sum(p_t^2)                 (whole tensor; the reference squares the WEIGHTS,
+//                                          optimizers.py:136, not the gradients: kept as is)
+//            | ||p_unit||_2               (unitwise_norm=True: per output unit, :18-22,133-134)
+//   ema_norm = beta2*ema_norm + (1-beta2)*norm_t                     (:139-140)
+//   ema_grad = beta1*ema_grad + (1-beta1)*g                          (:143,147)
+//   p        = (p - lr * ema_grad / (sqrt(ema_norm) + eps)) * (1 - lr*wd)   (:144-145,155,158)
+// ema_norm is one scalar per norm group here (the reference stores it expanded to the
+// parameter's shape, :120-121; the host side exposes an expanded view).
+// Three launches per arena: segmented sum of squares, per-group norm update, elementwise update.
+struct NovoTensor {
+  long begin;      // first element of the tensor in the arena
+  long end;        // first element of the next tensor (alignment padding included, zeros)
+  int unit_len;    // elements per norm group
+  int ngroups;     // norm groups of this tensor
+  int norm_base;   // index of its first group
+  float lr, decay, beta1, one_minus_beta1, beta2, one_minus_beta2;
+  int pad;
+};
+
+__device__ __forceinline__ int novo_find(const NovoTensor* __restrict__ tab, int nt, long e) {
+  int lo = 0, hi = nt - 1;
+  while (lo < hi) {            // first tensor whose end is > e
+    const int mid = (lo + hi) >> 1;
+    if (e >= tab[mid].end) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int novo_group(const NovoTensor& t, long e) {
+  const long g = (e - t.begin) / t.unit_len;
+  return t.norm_base + (int)(g < t.ngroups ? g : t.ngroups - 1);   // padding joins the last group (zeros)
+}
+
+constexpr int NOVO_ROUNDS = 8;   // float4 rounds a warp walks before its segmented reduction
+
+__global__ void __launch_bounds__(256)
+novograd_sumsq_kernel(const float* __restrict__ p, const NovoTensor* __restrict__ tab, int nt,
+                      long n4, float* __restrict__ sumsq) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long base4 = warp * (32 * NOVO_ROUNDS);
+  int cur = INT_MAX;             // group this lane is accumulating
+  float acc = 0.f;
+  for (int r = 0; r < NOVO_ROUNDS; ++r) {
+    const long i = base4 + r * 32 + lane;
+    if (i >= n4) {               // ragged tail: flush, then sort after every live lane
+      if (cur != INT_MAX && acc != 0.f) atomicAdd(sumsq + cur, acc);
+      cur = INT_MAX;
+      acc = 0.f;
+      break;
+    }
+    const long e = i * 4;
+    const NovoTensor t = tab[novo_find(tab, nt, e)];
+    const float4 v = *reinterpret_cast<const float4*>(p + e);
+    const int g0 = novo_group(t, e), g3 = novo_group(t, e + 3);
+    if (g0 == g3) {
+      const float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      if (g0 != cur) {
+        if (cur != INT_MAX && acc != 0.f) atomicAdd(sumsq + cur, acc);
+        cur = g0;
+        acc = 0.f;
+      }
+      acc += s;
+    } else {                     // a float4 straddling units (odd fan, e.g. 7*7*3)
+      // keep the LAST element's group in the lane (lanes stay sorted by group for the reduction
+      // below), push the others straight to memory
+      if (cur != INT_MAX && acc != 0.f) atomicAdd(sumsq + cur, acc);
+      cur = g3;
+      acc = 0.f;
+      const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gj = novo_group(t, e + j);
+        if (gj == g3) acc += a[j] * a[j];
+        else atomicAdd(sumsq + gj, a[j] * a[j]);
+      }
+    }
+  }
+  // lanes hold non-decreasing groups after the last round: segmented shuffle reduction
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float ov = __shfl_down_sync(full, acc, off);
+    const int og = __shfl_down_sync(full, cur, off);
+    if (lane + off < 32 && og == cur) acc += ov;
+  }
+  const int pg = __shfl_up_sync(full, cur, 1);
+  if ((lane == 0 || pg != cur) && cur != INT_MAX && acc != 0.f) atomicAdd(sumsq + cur, acc);
+}
+
+// one CTA per tensor: fold this step's norms into the running ones, publish the denominators
+__global__ void __launch_bounds__(128)
+novograd_norm_kernel(const NovoTensor* __restrict__ tab, float* __restrict__ sumsq,
+                     float* __restrict__ ema_norm, float* __restrict__ denom, float eps,
+                     int unitwise) {
+  const NovoTensor t = tab[blockIdx.x];
+  for (int g = threadIdx.x; g < t.ngroups; g += blockDim.x) {
+    const int i = t.norm_base + g;
+    const float s = sumsq[i];
+    const float nrm = unitwise ? sqrtf(s) : s;
+    const float en = __fmaf_rn(t.one_minus_beta2, nrm, __fmul_rn(ema_norm[i], t.beta2));
+    ema_norm[i] = en;
+    denom[i] = sqrtf(en) + eps;
+    sumsq[i] = 0.f;              // ready for the next step
+  }
+}
+
+__global__ void __launch_bounds__(256)
+novograd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ ema_grad,
+                __nv_bfloat16* __restrict__ p_bf16, float* __restrict__ ema, float ema_decay,
+                const NovoTensor* __restrict__ tab, int nt, const float* __restrict__ denom,
+                long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long)gridDim.x * blockDim.x) {
+    const long e = i * 4;
+    const NovoTensor t = tab[novo_find(tab, nt, e)];
+    const float4 pv = *reinterpret_cast<const float4*>(p + e);
+    const float4 gv = *reinterpret_cast<const float4*>(g + e);
+    const float4 mv = *reinterpret_cast<const float4*>(ema_grad + e);
+    float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+    const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+    float ma[4] = {mv.x, mv.y, mv.z, mv.w};
+    const int g0 = novo_group(t, e), g3 = novo_group(t, e + 3);
+    const float d0 = denom[g0];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = (g0 == g3) ? d0 : denom[novo_group(t, e + j)];
+      ma[j] = __fmaf_rn(t.one_minus_beta1, ga[j], __fmul_rn(ma[j], t.beta1));
+      pa[j] = __fmaf_rn(-t.lr, __fdiv_rn(ma[j], d), pa[j]);
+      pa[j] = __fmul_rn(pa[j], t.decay);
+    }
+    *reinterpret_cast<float4*>(p + e) = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    *reinterpret_cast<float4*>(ema_grad + e) = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    if (p_bf16 != nullptr) {
+      uint2 o;
+      o.x = pack2(pa[0], pa[1]);
+      o.y = pack2(pa[2], pa[3]);
+      *reinterpret_cast<uint2*>(p_bf16 + e) = o;
+    }
+    if (ema != nullptr) {
+      float4 ev = *reinterpret_cast<float4*>(ema + e);
+      ev.x = ema_decay * ev.x + (1.f - ema_decay) * pa[0];
+      ev.y = ema_decay * ev.y + (1.f - ema_decay) * pa[1];
+      ev.z = ema_decay * ev.z + (1.f - ema_decay) * pa[2];
+      ev.w = ema_decay * ev.w + (1.f - ema_decay) * pa[3];
+      *reinterpret_cast<float4*>(ema + e) = ev;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n4) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
@@ -230,6 +382,32 @@ extern "C" int sib_sgd_step(float* params, const float* grads, float* momentum_b
   sgd_kernel<<<ew_grid(n4, 256), 256, 0, ST(stream)>>>(
       params, grads, momentum_buf, static_cast<__nv_bfloat16*>(params_bf16), ema, ema_decay,
       static_cast<const SgdSeg*>(segs_dev), nseg, n4, first_step);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// table_dev: ntensors x {long begin, end; int unit_len, ngroups, norm_base; float lr, decay,
+// beta1, 1-beta1, beta2, 1-beta2; int pad}.  group_sumsq must be zero on the first call (the
+// norm kernel re-zeroes it); group_ema_norm holds ema_norm_init before the first step.
+extern "C" int sib_novograd_step(float* params, const float* grads, float* ema_grad,
+                                 void* params_bf16, float* ema, float ema_decay,
+                                 const void* table_dev, int ntensors, float* group_sumsq,
+                                 float* group_ema_norm, float* group_denom, long n, float eps,
+                                 int unitwise, void* stream) {
+  SIB_CHECK(n % 4 == 0, "novograd: arena length must be a multiple of 4 (pad the arena)");
+  SIB_CHECK(ntensors >= 1, "novograd: need at least one tensor record");
+  const long n4 = n / 4;
+  const NovoTensor* tab = static_cast<const NovoTensor*>(table_dev);
+  const long per_block = 8L * 32 * NOVO_ROUNDS;      // float4s one 256-thread block walks
+  novograd_sumsq_kernel<<<(unsigned)((n4 + per_block - 1) / per_block), 256, 0, ST(stream)>>>(
+      params, tab, ntensors, n4, group_sumsq);
+  SIB_LAUNCH_CHECK();
+  novograd_norm_kernel<<<ntensors, 128, 0, ST(stream)>>>(tab, group_sumsq, group_ema_norm,
+                                                         group_denom, eps, unitwise);
+  SIB_LAUNCH_CHECK();
+  novograd_kernel<<<ew_grid(n4, 256), 256, 0, ST(stream)>>>(
+      params, grads, ema_grad, static_cast<__nv_bfloat16*>(params_bf16), ema, ema_decay, tab,
+      ntensors, group_denom, n4);
   SIB_LAUNCH_CHECK();
   return 0;
 }

@@ -8,6 +8,7 @@
   AdaCos                     reference angular_losses.py:248-334 (fixed_s = CosFace on cosines;
                              adaptive scale statistics kept with the reference's update rule)
   AngularPenaltySMLoss       reference angular_losses.py:13-95 (arcface / cosface variants)
+  ArcCosSoftmax              reference angular_losses.py:572-576 (CE over -acos(cos))
 """
 import math
 
@@ -173,15 +174,15 @@ class AngularPenaltySMLoss(nn.Module):
 
 class AdaCos(nn.Module):
     """AdaCos on cosine logits.  With `fixed_s` this is CosFace (margin on the target column,
-    constant scale).  The adaptive scale follows reference :301-314 (running B, running median
+    constant scale); `arc_logits` feeds -(theta + margin) * s instead.  The adaptive scale follows reference :301-314 (running B, running median
     cosine, s = log B / (max(med, 0.7) - margin) capped at max_s); those no-grad statistics are
     a handful of tiny tensor ops, the margin + scale + CE forward/backward is the fused kernel."""
 
     def __init__(self, final_criterion=None, margin=0, max_s=20, fixed_s=None, momentum=0.95,
                  arc_logits=False, arc_margin=False):
         super().__init__()
-        if arc_logits or arc_margin:
-            raise _lib.SibError("AdaCos: arc_logits / arc_margin variants are not fused")
+        assert (not arc_logits) or arc_margin, "arc_logits=True and arc_margin=False are not supported!"
+        self.arc_logits, self.arc_margin = arc_logits, arc_margin
         self.final_criterion = final_criterion
         self.smoothing, self.temperature = _smoothing_of(final_criterion)
         self.margin, self.momentum, self.max_s, self.fixed_s = margin, momentum, max_s, fixed_s
@@ -209,8 +210,19 @@ class AdaCos(nn.Module):
                 self.prev_s = min(float(s), self.max_s)
         self.idx += 1
         scale = self.fixed_s if self.fixed_s is not None else self.prev_s
-        return _fused_ce(cosine, y_true, self.smoothing, self.temperature, ops.MARGIN_COS, scale,
-                         self.margin)
+        # arc_logits (:323-327): logits = -(acos(clamp(cos)) + margin[target]) * s; otherwise the
+        # margin is subtracted from the target cosine (:329) whatever `arc_margin` says
+        kind = ops.MARGIN_ARCCOS if self.arc_logits else ops.MARGIN_COS
+        return _fused_ce(cosine, y_true, self.smoothing, self.temperature, kind, scale, self.margin)
+
+
+class ArcCosSoftmax(CrossEntropyLoss):
+    """Smooth CE over -acos(clamp(cos, -1+1e-7, 1-1e-7)) (reference angular_losses.py:572-576)."""
+
+    def forward(self, y_pred, y_true):
+        loss = _fused_ce(y_pred.float(), y_true, self.smoothing, self.temperature,
+                         ops.MARGIN_ARCCOS, 1.0, 0.0)
+        return loss * self.loss_weight if self.loss_weight != 1.0 else loss
 
 
 LOSS_FROM_NAME = {"arcface": AdditiveAngularMarginLoss, "cross_entropy": CrossEntropyLoss}

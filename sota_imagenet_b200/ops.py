@@ -16,7 +16,7 @@ def call(name, *args):
     _lib.call(name, *args)
 
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
-MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE = 0, 1, 2, 3
+MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE, MARGIN_ARCCOS = 0, 1, 2, 3, 4
 FLAG_FORCE_IM2COL = 1
 FLAG_TILE_N128 = 2
 FLAG_NO_2CTA = 4
@@ -600,6 +600,26 @@ def sgd_segments(records, device):
 def sgd_step(params, grads, buf, params_bf16, segs, nseg, first_step, ema=None, ema_decay=0.0):
     call("sib_sgd_step", _p(params), _p(grads), _p(buf), _p(params_bf16), _p(ema), float(ema_decay),
          _p(segs), nseg, params.numel(), int(first_step), _stream())
+
+
+def novograd_table(records):
+    """records: (begin, end, unit_len, ngroups, norm_base, lr, decay, beta1, 1-beta1, beta2,
+    1-beta2) per tensor -> host byte tensor laid out like csrc/optim.cu NovoTensor."""
+    import numpy as np
+    rec = np.zeros(len(records), dtype=np.dtype([
+        ("begin", "<i8"), ("end", "<i8"), ("unit", "<i4"), ("ngroups", "<i4"), ("base", "<i4"),
+        ("lr", "<f4"), ("decay", "<f4"), ("b1", "<f4"), ("omb1", "<f4"), ("b2", "<f4"),
+        ("omb2", "<f4"), ("pad", "<i4")]))
+    for i, r in enumerate(records):
+        rec[i] = tuple(r) + (0,)
+    return torch.from_numpy(rec.view(np.uint8).copy())
+
+
+def novograd_step(params, grads, ema_grad, params_bf16, table, ntensors, sumsq, ema_norm, denom,
+                  eps, unitwise, ema=None, ema_decay=0.0):
+    call("sib_novograd_step", _p(params), _p(grads), _p(ema_grad), _p(params_bf16), _p(ema),
+         float(ema_decay), _p(table), ntensors, _p(sumsq), _p(ema_norm), _p(denom), params.numel(),
+         float(eps), int(bool(unitwise)), _stream())
 
 
 def cast_bf16(src, dst):

@@ -144,3 +144,26 @@ def test_bucketed_mean_allreduce_gloo_world2():
         r0, r1 = torch.load(os.path.join(out, "r0.pt")), torch.load(os.path.join(out, "r1.pt"))
     want = torch.arange(1500, dtype=torch.float32) * 1.5
     assert torch.equal(r0, want) and torch.equal(r1, want)
+
+
+def test_novograd_norm_groups_and_table_layout():
+    """Host side of MyNovograd: norm groups per tensor / per output unit (reference
+    optimizers.py:18-22) and the 56-byte records csrc/optim.cu NovoTensor expects."""
+    import numpy as np
+    from sota_imagenet_b200 import ops, optimizers
+    ng = optimizers.MyNovograd.norm_groups
+    assert ng((64, 3, 7, 7), False) == (64 * 147, 1)
+    assert ng((64, 3, 7, 7), True) == (147, 64)
+    assert ng((1000, 2048), True) == (2048, 1000)
+    assert ng((256,), True) == (256, 1) and ng((), False) == (1, 1)
+    recs = [(0, 128, 147, 8, 0, 0.01, 1 - 1e-4, 0.9, 0.1, 0.99, 0.01),
+            (128, 1280, 1152, 1, 8, 0.0, 1.0, 1.0, 0.0, 1.0, 0.0)]
+    raw = ops.novograd_table(recs)
+    assert raw.dtype == torch.uint8 and raw.numel() == 2 * 56
+    b = raw.numpy().tobytes()
+    assert np.frombuffer(b[:16], "<i8").tolist() == [0, 128]
+    assert np.frombuffer(b[16:28], "<i4").tolist() == [147, 8, 0]
+    assert np.allclose(np.frombuffer(b[28:52], "<f4"), [0.01, 1 - 1e-4, 0.9, 0.1, 0.99, 0.01])
+    assert np.frombuffer(b[56:72], "<i8").tolist() == [128, 1280]
+    with pytest.raises(ValueError):
+        optimizers.MyNovograd([torch.nn.Parameter(torch.zeros(4))], betas=(1.0, 0.99))

@@ -96,3 +96,41 @@ def test_resnet_oracle_pinned():
     losses = [torch_ref.train_step(model, opt, x, y) for _ in range(2)]
     assert np.allclose(losses, g["losses"], rtol=1e-4)
     assert torch.allclose(model.bn1.running_mean, g["bn1_running_mean"], atol=1e-5)
+
+
+def test_arccos_restatement_matches_reference_classes():
+    """oracle arccos_logits + smooth CE == the reference's ArcCosSoftmax / AdaCos(arc_logits)
+    (angular_losses.py:572-576, :323-330), losses and gradients, index and soft targets."""
+    g = _load("heads_arccos.pt")
+    cos, y, soft = g["cos"], g["y"], g["soft"]
+    for name, tgt, s, m, temp in (("arccos", y, 1.0, 0.0, 1.0), ("arccos_t015", y, 1.0, 0.0, 0.15),
+                                  ("arccos_soft", soft, 1.0, 0.0, 1.0), ("adacos_arc", y, 10.0, 0.2, 1.0),
+                                  ("adacos_arc_soft", soft, 10.0, 0.2, 1.0)):
+        cr = cos.clone().requires_grad_(True)
+        loss = torch_ref.smooth_cross_entropy(torch_ref.arccos_logits(cr, tgt, s, m), tgt, 0.1, temp)
+        loss.backward()
+        assert torch.allclose(loss, g[name]["loss"], atol=1e-5, rtol=1e-5), name
+        assert torch.allclose(cr.grad, g[name]["dcos"], atol=1e-5, rtol=1e-4), name
+    # the clamp kills the gradient at exactly +-1 and keeps it finite next to it
+    assert float(g["arccos"]["dcos"][0, 0]) == 0.0 and float(g["arccos"]["dcos"][0, 1]) == 0.0
+    assert torch.isfinite(g["arccos"]["dcos"]).all()
+
+
+def test_novograd_restatement_matches_reference_optimizer():
+    """oracle novograd_step == the reference's own MyNovograd class (optimizers.py:35-161)."""
+    g = _load("novograd.pt")
+    skip = g["nograd_index"]
+    for unitwise, key in ((False, "tensor"), (True, "unitwise")):
+        run = g["runs"][key]
+        ps = [p.clone() for p in g["p0"]]
+        state = [{} for _ in ps]
+        idx = [i for i in range(len(ps)) if i != skip]
+        for grads, lr, want in zip(g["grads"], g["lrs"], run["traj"]):
+            torch_ref.novograd_step([ps[i] for i in idx], [grads[i] for i in idx],
+                                    [state[i] for i in idx], lr, unitwise=unitwise)
+            for p, w in zip(ps, want):
+                assert torch.allclose(p, w, atol=1e-6, rtol=1e-5)
+        assert torch.equal(ps[skip], g["p0"][skip])                 # gradient-less tensor untouched
+        for i in idx:
+            assert torch.allclose(state[i]["ema_grad"], run["ema_grad"][i], atol=1e-6)
+            assert torch.allclose(state[i]["ema_norm"].expand_as(ps[i]), run["ema_norm"][i], rtol=1e-5)
