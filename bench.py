@@ -39,40 +39,65 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML every 20 ms (the timed
+    region of the default run is ~1 s), `nvidia-smi` polling as the fallback."""
+    _BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+             0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.source = "nvml"
+        self.ready = threading.Event()      # set once the first sample is in (NVML initialised)
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop_evt.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            mask = int(get_reasons(h))
+            self.rows.append((int(sm), int(mx), [n for b, n in self._BITS.items() if mask & b]))
+            self.ready.set()
+            self._stop_evt.wait(0.02)
+
+    def _smi_loop(self):
+        self.source = "nvidia-smi"
+        self.ready.set()
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True,
                                      text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")]
+                if len(r) >= 6 and r[0].isdigit() and r[1].isdigit():
+                    self.rows.append((int(r[0]), int(r[1]), [n for n, v in zip(names, r[2:6])
+                                                             if v.lower().startswith("active")]))
             except Exception:
                 pass
             self._stop_evt.wait(0.2)
 
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
+
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({n for r in self.rows for n in r[2]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(r[1] for r in self.rows) if self.rows else None,
+                "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 # --------------------------------------------------------------------------------------------
@@ -239,12 +264,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        run_step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                 # NVML initialises while the warm-up runs
+    for _ in range(args.warmup):
+        run_step()
+    if rank == 0:
+        sampler.ready.wait(3.0)
+    barrier()
+    sampler.rows.clear()                # keep only samples taken inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -410,7 +438,7 @@ def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
