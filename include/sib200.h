@@ -232,6 +232,16 @@ void sib_rrc_box_host(int H, int W, double min_area, double max_area, unsigned l
 int sib_augment(const void* src_u8, const int* boxes_dev, void* out, int B, int SH, int SW, int S,
                 float mean, float std, int out_mode, void* stream);
 int sib_one_hot(const long* labels, float* out, int B, int C, void* stream);
+/* batch-level mixing on the resident batch: pt_clb.Mixup / pt_clb.Cutmix as combined by
+ * CutmixMixup (sota_imagenet/callbacks.py:232-247).  layout 0: NHWC bf16 [N][H][W][C], 1: NCHW
+ * fp32; mode 0: out = lam*x + one_minus_lam*prev[perm[n]]; mode 1: out = prev[perm[n]] inside
+ * rows [h1,h2) x columns [w1,w2), x elsewhere.  prev is [N][PH][PW][C] / [N][C][PH][PW]. */
+int sib_mix_batch(const void* x, const void* prev, const int* perm_dev, void* out, int N, int H,
+                  int W, int C, int PH, int PW, int layout, int mode, float lam,
+                  float one_minus_lam, int h1, int w1, int h2, int w2, void* stream);
+/* out[n][c] = w_self*t[n][c] + w_prev*prev_t[perm[n]][c] (soft targets of the mixed batch) */
+int sib_mix_targets(const float* t, const float* prev_t, const int* perm_dev, float* out, int N,
+                    int C, float w_self, float w_prev, void* stream);
 /* stem packing (see csrc/augment.cu): src_mode 0 = NHWC4 bf16, 1 = NCHW fp32 */
 int sib_stem_pack(const void* src, void* xq, int N, int H, int W, int KW, int pad_w, int src_mode,
                   void* stream);

@@ -105,3 +105,36 @@ def one_hot(labels, num_classes):
     out = np.zeros((len(labels), num_classes), np.float32)
     out[np.arange(len(labels)), labels] = 1.0
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Batch-level mixing.  pt_clb.Mixup / pt_clb.Cutmix live in the absent
+# pytorch_tools package (unpinned); the reference combines them in sota_imagenet/callbacks.py:
+# 232-247.  Restated in NCHW, fp32 arithmetic with one rounding at the end:
+#   mixup : out = c * x + (1 - c) * prev[perm]      targets likewise
+#   cutmix: out[:, :, h1:h2, w1:w2] = prev[perm][:, :, h1:h2, w1:w2];  t = (1-lam) t + lam prev_t[perm]
+def mixup_batch(x, prev, perm, c):
+    c = np.float32(c)
+    omc = np.float32(1.0) - c
+    return (c * x.astype(np.float32) + omc * prev[perm].astype(np.float32)).astype(np.float32)
+
+
+def cutmix_batch(x, prev, perm, box):
+    h1, w1, h2, w2 = box
+    out = x.copy()
+    out[:, :, h1:h2, w1:w2] = prev[perm][:, :, h1:h2, w1:w2]
+    return out
+
+
+def mix_targets(t, prev_t, perm, w_self, w_prev):
+    return (np.float32(w_self) * t.astype(np.float32) + np.float32(w_prev) * prev_t[perm].astype(np.float32))
+
+
+def cutmix_bbox(H, W, lam, ch, cw):
+    """box of area ~ lam*H*W centred on (ch, cw), clipped to the image; returns the box and the
+    clipped box's true share of the image (the lambda the targets are mixed with)."""
+    cut_rat = np.sqrt(lam)
+    cut_h, cut_w = int(H * cut_rat), int(W * cut_rat)
+    box = (int(np.clip(ch - cut_h // 2, 0, H)), int(np.clip(cw - cut_w // 2, 0, W)),
+           int(np.clip(ch + cut_h // 2, 0, H)), int(np.clip(cw + cut_w // 2, 0, W)))
+    return box, (box[2] - box[0]) * (box[3] - box[1]) / (H * W)

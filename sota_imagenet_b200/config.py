@@ -27,6 +27,11 @@ PREFIX_REMAP = {
     "sota_imagenet.model.CModel": "sota_imagenet_b200.cmodel.CModel",
     "src.model.CModel": "sota_imagenet_b200.cmodel.CModel",
     "sota_imagenet.optimizers.": "sota_imagenet_b200.optimizers.",
+    "src.optimizers.": "sota_imagenet_b200.optimizers.",
+    "sota_imagenet.callbacks.CutmixMixup": "sota_imagenet_b200.runner.CutmixMixup",
+    "src.callbacks.CutmixMixup": "sota_imagenet_b200.runner.CutmixMixup",
+    "pytorch_tools.fit_wrapper.callbacks.Cutmix": "sota_imagenet_b200.runner.Cutmix",
+    "pytorch_tools.fit_wrapper.callbacks.Mixup": "sota_imagenet_b200.runner.Mixup",
 }
 
 

@@ -148,6 +148,95 @@ __global__ void one_hot_kernel(const long* __restrict__ labels, float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batch-level mixing on the resident batch: pt_clb.Mixup / pt_clb.Cutmix as combined by the
+// reference's CutmixMixup (sota_imagenet/callbacks.py:232-247; the two parents live in the absent
+// pytorch_tools package: restated, unpinned).
+//   mode 0 (mixup):  out = lam * x + (1 - lam) * prev[perm[n]]          (fp32 math, one rounding)
+//   mode 1 (cutmix): out = (h1 <= h < h2 && w1 <= w < w2) ? prev[perm[n]] : x
+// LAYOUT 0: NHWC bf16, 8-element vectors along the (w, c) row; LAYOUT 1: NCHW fp32, float4 along w.
+// `prev` may have another spatial extent (progressive resizing): [N][PH][PW][C] / [N][C][PH][PW].
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+mix_batch_kernel(const void* __restrict__ xv, const void* __restrict__ prevv,
+                 const int* __restrict__ perm, void* __restrict__ outv, int N, int H, int W, int C,
+                 int PH, int PW, int mode, float lam, float one_minus_lam, int h1, int w1, int h2,
+                 int w2) {
+  constexpr int V = LAYOUT == 0 ? 8 : 4;
+  const int rowlen = LAYOUT == 0 ? W * C : W;            // elements of one vectorised row
+  const int rowvecs = rowlen / V;
+  const long rows = LAYOUT == 0 ? (long)N * H : (long)N * C * H;
+  const long total = rows * rowvecs;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (long)gridDim.x * blockDim.x) {
+    const long row = v / rowvecs;
+    const int col = (int)(v - row * rowvecs) * V;
+    const int h = (int)(row % H);
+    const long nc = row / H;                             // n (NHWC) or n*C + c (NCHW)
+    const int n = LAYOUT == 0 ? (int)nc : (int)(nc / C);
+    const int pn = perm[n];
+    const long prow = LAYOUT == 0 ? ((long)pn * PH + h) * ((long)PW * C)
+                                  : (((long)pn * C + (nc - (long)n * C)) * PH + h) * (long)PW;
+    bool in[V];
+    bool any = mode == 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int w = LAYOUT == 0 ? (col + j) / C : col + j;
+      in[j] = mode == 1 && h >= h1 && h < h2 && w >= w1 && w < w2;
+      any |= in[j];
+    }
+    if (LAYOUT == 0) {
+      const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(xv) + row * rowlen + col;
+      uint4 a = *reinterpret_cast<const uint4*>(x);
+      if (any) {
+        const uint4 b = *reinterpret_cast<const uint4*>(
+            static_cast<const __nv_bfloat16*>(prevv) + prow + col);
+        __nv_bfloat16* ae = reinterpret_cast<__nv_bfloat16*>(&a);
+        const __nv_bfloat16* be = reinterpret_cast<const __nv_bfloat16*>(&b);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          if (mode == 0)
+            ae[j] = __float2bfloat16_rn(__fadd_rn(__fmul_rn(lam, __bfloat162float(ae[j])),
+                                                  __fmul_rn(one_minus_lam, __bfloat162float(be[j]))));
+          else if (in[j])
+            ae[j] = be[j];
+        }
+      }
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(outv) + row * rowlen + col) = a;
+    } else {
+      const float* x = static_cast<const float*>(xv) + row * rowlen + col;
+      float4 a = *reinterpret_cast<const float4*>(x);
+      if (any) {
+        const float4 b = *reinterpret_cast<const float4*>(static_cast<const float*>(prevv) + prow + col);
+        float* ae = reinterpret_cast<float*>(&a);
+        const float* be = reinterpret_cast<const float*>(&b);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          if (mode == 0)
+            ae[j] = __fadd_rn(__fmul_rn(lam, ae[j]), __fmul_rn(one_minus_lam, be[j]));
+          else if (in[j])
+            ae[j] = be[j];
+        }
+      }
+      *reinterpret_cast<float4*>(static_cast<float*>(outv) + row * rowlen + col) = a;
+    }
+  }
+}
+
+// out[n][c] = w_self * t[n][c] + w_prev * prev_t[perm[n]][c]   (soft targets of mixup / cutmix)
+__global__ void __launch_bounds__(256)
+mix_targets_kernel(const float* __restrict__ t, const float* __restrict__ prev_t,
+                   const int* __restrict__ perm, float* __restrict__ out, int N, int C,
+                   float w_self, float w_prev) {
+  const long total = (long)N * C;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / C);
+    const int c = (int)(i - (long)n * C);
+    out[i] = __fadd_rn(__fmul_rn(w_self, t[i]), __fmul_rn(w_prev, prev_t[(long)perm[n] * C + c]));
+  }
+}
+
 // Stem packer.  For a KHxKW stride-2 convolution with padding (ph, pw) over a 3-channel
 // image, output row p reads image rows 2p + r - ph.  Writing that row as 2*(p + a) + b with
 // b in {0,1} turns the filter into NA row-pair taps over a packed tensor
@@ -274,6 +363,38 @@ extern "C" int sib_augment(const void* src_u8, const int* boxes_dev, void* out, 
 
 extern "C" int sib_one_hot(const long* labels, float* out, int B, int C, void* stream) {
   one_hot_kernel<<<ew_grid((long)B * C, 256), 256, 0, ST(stream)>>>(labels, out, B, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_mix_batch(const void* x, const void* prev, const int* perm_dev, void* out, int N,
+                             int H, int W, int C, int PH, int PW, int layout, int mode, float lam,
+                             float one_minus_lam, int h1, int w1, int h2, int w2, void* stream) {
+  SIB_CHECK(layout == 0 || layout == 1, "mix_batch: layout must be 0 (NHWC bf16) or 1 (NCHW f32)");
+  SIB_CHECK(mode == 0 || mode == 1, "mix_batch: mode must be 0 (mixup) or 1 (cutmix)");
+  SIB_CHECK(mode == 1 || (PH == H && PW == W),
+            "mix_batch: mixup needs the previous batch at the same size (%dx%d vs %dx%d)", PH, PW, H, W);
+  SIB_CHECK(mode == 0 || (h1 >= 0 && w1 >= 0 && h2 <= (H < PH ? H : PH) && w2 <= (W < PW ? W : PW)),
+            "mix_batch: box outside the common extent of the two batches");
+  if (layout == 0) {
+    SIB_CHECK((W * C) % 8 == 0 && (PW * C) % 8 == 0, "mix_batch: W*C must be a multiple of 8");
+    const long total = (long)N * H * (W * C / 8);
+    mix_batch_kernel<0><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+        x, prev, perm_dev, out, N, H, W, C, PH, PW, mode, lam, one_minus_lam, h1, w1, h2, w2);
+  } else {
+    SIB_CHECK(W % 4 == 0 && PW % 4 == 0, "mix_batch: W must be a multiple of 4");
+    const long total = (long)N * C * H * (W / 4);
+    mix_batch_kernel<1><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+        x, prev, perm_dev, out, N, H, W, C, PH, PW, mode, lam, one_minus_lam, h1, w1, h2, w2);
+  }
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_mix_targets(const float* t, const float* prev_t, const int* perm_dev, float* out,
+                               int N, int C, float w_self, float w_prev, void* stream) {
+  mix_targets_kernel<<<ew_grid((long)N * C, 256), 256, 0, ST(stream)>>>(t, prev_t, perm_dev, out, N,
+                                                                         C, w_self, w_prev);
   SIB_LAUNCH_CHECK();
   return 0;
 }

@@ -659,6 +659,42 @@ def one_hot(labels, num_classes):
     return out
 
 
+def mix_batch(x, prev, perm, mode, lam=1.0, one_minus_lam=0.0, box=(0, 0, 0, 0)):
+    """Mixup (mode 0) / CutMix (mode 1) of a resident batch with a permuted previous batch.
+    x, prev: bf16 channels_last [N,C,H,W] or fp32 NCHW; perm int32 [N] on the device;
+    box = (h1, w1, h2, w2).  Out of place (prev may be x itself)."""
+    _lib.require_device()
+    n, c, h, w = x.shape
+    ph, pw = prev.shape[2], prev.shape[3]
+    if prev.shape[0] != n or prev.shape[1] != c or prev.dtype != x.dtype:
+        raise _lib.SibError("mix_batch: previous batch must have the same batch size, channels and dtype")
+    if x.dtype == torch.bfloat16 and x.permute(0, 2, 3, 1).is_contiguous() and \
+            prev.permute(0, 2, 3, 1).is_contiguous():
+        layout = 0
+    elif x.dtype == torch.float32 and x.is_contiguous() and prev.is_contiguous():
+        layout = 1
+    else:
+        raise _lib.SibError("mix_batch: batches must be bf16 channels_last or fp32 NCHW contiguous")
+    if perm.dtype != torch.int32 or not perm.is_cuda or perm.numel() != n:
+        raise _lib.SibError("mix_batch: perm must be an int32 device tensor of the batch size")
+    out = torch.empty_like(x)
+    h1, w1, h2, w2 = (int(v) for v in box)
+    call("sib_mix_batch", _p(x), _p(prev), _p(perm), _p(out), n, h, w, c, ph, pw, layout, int(mode),
+         float(lam), float(one_minus_lam), h1, w1, h2, w2, _stream())
+    return out
+
+
+def mix_targets(t, prev_t, perm, w_self, w_prev):
+    _lib.require_device()
+    if t.dtype != torch.float32 or prev_t.dtype != torch.float32 or t.shape != prev_t.shape:
+        raise _lib.SibError("mix_targets: dense fp32 targets of equal shape expected")
+    t, prev_t = t.contiguous(), prev_t.contiguous()
+    out = torch.empty_like(t)
+    call("sib_mix_targets", _p(t), _p(prev_t), _p(perm), _p(out), t.shape[0], t.shape[1],
+         float(w_self), float(w_prev), _stream())
+    return out
+
+
 def stem_pack(x, kw, pad_w):
     """[N,3,H,W] fp32 NCHW or [N,4,H,W] bf16 channels_last -> [N,64,H/2,W/2] packed rows."""
     n, c, h, w = x.shape

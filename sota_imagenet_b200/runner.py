@@ -6,7 +6,10 @@ back every `log_every` steps only."""
 import math
 import os
 
+import numpy as np
 import torch
+
+from . import ops
 
 
 class Callback:
@@ -111,8 +114,8 @@ class Runner:
             if steps is not None and i >= steps:
                 break
             st.step, st.input = i, batch
-            data, target = batch
             self._cb("on_batch_begin")
+            data, target = st.input          # callbacks (CutmixMixup) may replace the batch
             if train:
                 out = st.model(data)
                 loss = st.criterion(out, target)
@@ -163,6 +166,111 @@ class Runner:
         vl, vm = self._run_loader(loader, steps, train=False)
         self.state.val_loss, self.state.val_metrics = vl, vm
         return vl, vm
+
+
+class _BatchMix(Callback):
+    """Shared state of pt_clb.Mixup / pt_clb.Cutmix (pytorch_tools, absent: restated; the
+    reference combines them in sota_imagenet/callbacks.py:232-247).  Random draws use the same
+    host generators in the same order as the originals (np.random for the gates and the box
+    centre, torch CPU RNG for the permutation and the Beta sample); the data path is two
+    kernels on the resident batch (ops.mix_batch, ops.mix_targets)."""
+
+    def __init__(self, alpha, num_classes, prob=0.5):
+        self.tb = torch.distributions.Beta(alpha, alpha)
+        self.num_classes = num_classes
+        self.prob = prob
+        self.prev_input = None
+
+    def _one_hot(self, data, target):
+        if target.dim() == 1:
+            return ops.one_hot(target.to(torch.int64), self.num_classes)
+        return target
+
+    def _gate(self):
+        is_train = self.state.is_train if getattr(self, "state", None) is not None else True
+        return is_train and not (np.random.rand() > self.prob)
+
+    def _previous(self, data, target_one_hot):
+        prev = (data, target_one_hot) if self.prev_input is None else self.prev_input
+        self.prev_input = data.clone(), target_one_hot.clone()
+        return prev
+
+    @staticmethod
+    def _perm(n, device):
+        return torch.randperm(n).to(device=device, dtype=torch.int32)
+
+
+class Mixup(_BatchMix):
+    """out = c*data + (1-c)*prev[perm], targets likewise, c ~ Beta(alpha, alpha)."""
+
+    def on_batch_begin(self):
+        self.state.input = self.mixup(*self.state.input)
+
+    @torch.no_grad()
+    def mixup(self, data, target):
+        target_one_hot = self._one_hot(data, target)
+        if not self._gate():
+            return data, target_one_hot
+        prev_data, prev_target = self._previous(data, target_one_hot)
+        perm = self._perm(data.size(0), data.device)
+        c = np.float32(self.tb.sample().item())
+        omc = np.float32(1.0) - c
+        md = ops.mix_batch(data, prev_data, perm, 0, c, omc)
+        mt = ops.mix_targets(target_one_hot, prev_target, perm, c, omc)
+        return md, mt
+
+
+class Cutmix(_BatchMix):
+    """A random box of the permuted previous batch is pasted into the batch; the targets mix
+    with the box's true area fraction."""
+
+    def on_batch_begin(self):
+        self.state.input = self.cutmix(*self.state.input)
+
+    @torch.no_grad()
+    def cutmix(self, data, target):
+        target_one_hot = self._one_hot(data, target)
+        if not self._gate():
+            return data, target_one_hot
+        prev_data, prev_target = self._previous(data, target_one_hot)
+        # the previous batch can have another size (progressive resizing): use the common extent
+        H, W = min(data.size(2), prev_data.size(2)), min(data.size(3), prev_data.size(3))
+        perm = self._perm(data.size(0), data.device)
+        lam = float(self.tb.sample())
+        lam = min(lam, 1 - lam)
+        bbh1, bbw1, bbh2, bbw2 = self.rand_bbox(H, W, lam)
+        lam = (bbh2 - bbh1) * (bbw2 - bbw1) / (H * W)      # the clipped box's real share
+        md = ops.mix_batch(data, prev_data, perm, 1, box=(bbh1, bbw1, bbh2, bbw2))
+        mt = ops.mix_targets(target_one_hot, prev_target, perm, np.float32(1 - lam), np.float32(lam))
+        return md, mt
+
+    @staticmethod
+    def rand_bbox(H, W, lam):
+        """box with area close to lam*H*W around a uniform centre, clipped to the image"""
+        cut_rat = np.sqrt(lam)
+        cut_h, cut_w = int(H * cut_rat), int(W * cut_rat)
+        ch, cw = np.random.randint(H), np.random.randint(W)
+        return (int(np.clip(ch - cut_h // 2, 0, H)), int(np.clip(cw - cut_w // 2, 0, W)),
+                int(np.clip(ch + cut_h // 2, 0, H)), int(np.clip(cw + cut_w // 2, 0, W)))
+
+
+class CutmixMixup(Cutmix, Mixup):
+    """Reference sota_imagenet/callbacks.py:232-247: CutMix or Mixup, a coin flip per batch."""
+
+    def __init__(self, cutmix_alpha, mixup_alpha, prob=0.5, num_classes=1000):
+        self.cutmix_tb = torch.distributions.Beta(cutmix_alpha, cutmix_alpha)
+        self.mixup_tb = torch.distributions.Beta(mixup_alpha, mixup_alpha)
+        self.prob = prob
+        self.prev_input = None
+        self.num_classes = num_classes    # the reference leaves it unset (DALI targets are one-hot)
+
+    def on_batch_begin(self):
+        if np.random.rand() > 0.5:
+            self.tb = self.cutmix_tb
+            self.state.input = self.cutmix(*self.state.input)
+        else:
+            self.tb = self.mixup_tb
+            self.state.input = self.mixup(*self.state.input)
 
 
 class CheckpointSaver(Callback):

@@ -167,3 +167,53 @@ def test_novograd_norm_groups_and_table_layout():
     assert np.frombuffer(b[56:72], "<i8").tolist() == [128, 1280]
     with pytest.raises(ValueError):
         optimizers.MyNovograd([torch.nn.Parameter(torch.zeros(4))], betas=(1.0, 0.99))
+
+
+def test_cutmix_mixup_host_logic_with_oracle_kernels(monkeypatch):
+    """Host side of CutmixMixup (reference callbacks.py:232-247): coin flips, previous-batch
+    memory, box arithmetic and target weights, with the two kernels replaced by the numpy oracle
+    (the GPU test runs the same replay against the CUDA kernels)."""
+    import numpy as np
+    from oracle import augment_ref
+    from sota_imagenet_b200 import ops
+
+    def mix_batch(x, prev, perm, mode, lam=1.0, one_minus_lam=0.0, box=(0, 0, 0, 0)):
+        xr, pr, pm = x.numpy(), prev.numpy(), perm.numpy()
+        out = augment_ref.mixup_batch(xr, pr, pm, lam) if mode == 0 else augment_ref.cutmix_batch(xr, pr, pm, box)
+        return torch.from_numpy(out)
+
+    monkeypatch.setattr(ops, "mix_batch", mix_batch)
+    monkeypatch.setattr(ops, "mix_targets", lambda t, p, perm, a, b: torch.from_numpy(
+        augment_ref.mix_targets(t.numpy(), p.numpy(), perm.numpy(), a, b)))
+    monkeypatch.setattr(ops, "one_hot", lambda l, n: torch.eye(n)[l])
+
+    class State:
+        is_train, input = True, None
+
+    np.random.seed(3)
+    torch.manual_seed(3)
+    cb = runner.CutmixMixup(cutmix_alpha=1.0, mixup_alpha=0.2, prob=1.0, num_classes=10)
+    cb.set_state(State())
+    first = None
+    for i in range(8):
+        x = torch.randn(4, 3, 12, 12)
+        y = torch.randint(0, 10, (4,))
+        if first is None:
+            first = x.clone()
+        cb.state.input = (x, y)
+        cb.on_batch_begin()
+        md, mt = cb.state.input
+        assert md.shape == x.shape and tuple(mt.shape) == (4, 10)
+        assert torch.allclose(mt.sum(1), torch.ones(4), atol=1e-6)        # soft targets stay normalised
+        assert torch.equal(cb.prev_input[0], x)                           # memory = the UNMIXED batch
+        # every output pixel comes from this batch, the previous one, or a blend of the two
+        assert float(md.abs().max()) <= max(float(x.abs().max()), float(cb_prev_max if i else x.abs().max())) + 1e-6
+        cb_prev_max = float(x.abs().max())
+    box, lam = augment_ref.cutmix_bbox(224, 224, 0.25, 0, 223)            # clipped at two borders
+    assert box == (0, 167, 56, 224) and abs(lam - 56 * 57 / 224 ** 2) < 1e-12
+    assert runner.Cutmix.rand_bbox.__doc__
+    cb.state.is_train = False
+    x = torch.randn(4, 3, 12, 12)
+    cb.state.input = (x, torch.randint(0, 10, (4,)))
+    cb.on_batch_begin()
+    assert cb.state.input[0] is x
