@@ -231,6 +231,12 @@ void sib_rrc_box_host(int H, int W, double min_area, double max_area, unsigned l
 /* out_mode 0: NHWC bf16, 4 channels (4th zero); 1: NCHW fp32 (the reference layout) */
 int sib_augment(const void* src_u8, const int* boxes_dev, void* out, int B, int SH, int SW, int S,
                 float mean, float std, int out_mode, void* stream);
+/* validation pipeline (dali_dataloader.py:146-160): resize the shorter side to `resize_shorter`
+ * (triangular), centre crop S x S, normalise; out_mode as sib_augment.  g4_host receives
+ * {resized H, resized W, crop origin y, crop origin x}. */
+int sib_val_transform(const void* src_u8, void* out, int B, int SH, int SW, int S,
+                      int resize_shorter, float mean, float std, int out_mode, void* stream);
+void sib_val_geometry_host(int SH, int SW, int S, int resize_shorter, int* g4_host);
 int sib_one_hot(const long* labels, float* out, int B, int C, void* stream);
 /* batch-level mixing on the resident batch: pt_clb.Mixup / pt_clb.Cutmix as combined by
  * CutmixMixup (sota_imagenet/callbacks.py:232-247).  layout 0: NHWC bf16 [N][H][W][C], 1: NCHW

@@ -138,3 +138,56 @@ def cutmix_bbox(H, W, lam, ch, cw):
     box = (int(np.clip(ch - cut_h // 2, 0, H)), int(np.clip(cw - cut_w // 2, 0, W)),
            int(np.clip(ch + cut_h // 2, 0, H)), int(np.clip(cw + cut_w // 2, 0, W)))
     return box, (box[2] - box[0]) * (box[3] - box[1]) / (H * W)
+
+
+# ---------------------------------------------------------------------------------------------
+# Validation transform (reference dali_dataloader.py:146-160): fn.resize(resize_shorter=crop_size,
+# INTERP_TRIANGULAR) then crop_mirror_normalize(crop=(S, S)) (centre crop, no mirror).  DALI is
+# absent: restated, unpinned.  Rounding conventions fixed here: the longer side is
+# floor(long * RS / short + 0.5), the crop origin floor(0.5 * (R - S) + 0.5).
+def val_geometry(sh, sw, size, resize_shorter):
+    if sh <= sw:
+        rh, rw = resize_shorter, int(math.floor(sw * resize_shorter / sh + 0.5))
+    else:
+        rw, rh = resize_shorter, int(math.floor(sh * resize_shorter / sw + 0.5))
+    return [rh, rw, int(math.floor(0.5 * (rh - size) + 0.5)), int(math.floor(0.5 * (rw - size) + 0.5))]
+
+
+def _tri_weights_window(out_size, origin, in_size, resized):
+    """taps of output index o = pixel (o + origin) of the virtual `resized`-long axis, over an
+    `in_size`-long source axis; taps clamp at the image border."""
+    f32 = np.float32
+    scale = f32(in_size) / f32(resized)
+    sup = max(scale, f32(1.0))
+    taps = []
+    for o in range(out_size):
+        c = (f32(o + origin) + f32(0.5)) * scale
+        lo, hi = int(math.floor(c - sup)), int(math.ceil(c + sup))
+        row = []
+        for i in range(lo, hi):
+            w = max(f32(0.0), f32(1.0) - abs((f32(i) + f32(0.5) - c) / sup))
+            if w > 0:
+                row.append((min(max(i, 0), in_size - 1), f32(w)))
+        taps.append(row)
+    return taps
+
+
+def val_transform_image(img, size, resize_shorter, mean=127.5, std=51.0):
+    """img uint8 [H,W,3] -> float32 [size,size,3]"""
+    sh, sw = img.shape[:2]
+    rh, rw, oy0, ox0 = val_geometry(sh, sw, size, resize_shorter)
+    ty = _tri_weights_window(size, oy0, sh, rh)
+    tx = _tri_weights_window(size, ox0, sw, rw)
+    src = img.astype(np.float32)
+    out = np.zeros((size, size, 3), np.float32)
+    for oy in range(size):
+        for ox in range(size):
+            acc = np.zeros(3, np.float64)
+            ws = 0.0
+            for (sy, wy) in ty[oy]:
+                for (sx, wx) in tx[ox]:
+                    w = float(wx) * float(wy)
+                    acc += w * src[sy, sx]
+                    ws += w
+            out[oy, ox] = (acc / ws - mean) / std
+    return out

@@ -138,6 +138,64 @@ augment_kernel(const uint8_t* __restrict__ src, const int* __restrict__ boxes, v
   }
 }
 
+// Validation transform (reference dali_dataloader.py:146-160): resize so that the SHORTER side
+// becomes `RS` (INTERP_TRIANGULAR, the other side scaled by the same ratio and rounded), centre
+// crop S x S, normalise.  Resize and crop are fused: output pixel (oy, ox) is pixel
+// (oy + oy0, ox + ox0) of the virtual RH x RW resized image; filter taps clamp at the IMAGE
+// border (not at the crop window, unlike the train kernel whose crop happens before the resize).
+__global__ void __launch_bounds__(256)
+val_transform_kernel(const uint8_t* __restrict__ src, void* __restrict__ out, int B, int SH, int SW,
+                     int S, int RH, int RW, int oy0, int ox0, float mean, float inv_std,
+                     int out_mode) {
+  const long total = (long)B * S * S;
+  const float scx = (float)SW / (float)RW, scy = (float)SH / (float)RH;
+  const float supx = fmaxf(scx, 1.f), supy = fmaxf(scy, 1.f);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % S);
+    const int oy = (int)((i / S) % S);
+    const int n = (int)(i / ((long)S * S));
+    const float cx = ((float)(ox + ox0) + 0.5f) * scx, cy = ((float)(oy + oy0) + 0.5f) * scy;
+    const int xlo = (int)floorf(cx - supx), xhi = (int)ceilf(cx + supx);
+    const int ylo = (int)floorf(cy - supy), yhi = (int)ceilf(cy + supy);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, wsum = 0.f;
+    const uint8_t* img = src + (long)n * SH * SW * 3;
+    for (int yy = ylo; yy < yhi; ++yy) {
+      const float wy = fmaxf(0.f, 1.f - fabsf(((float)yy + 0.5f - cy) / supy));
+      if (wy <= 0.f) continue;
+      const int sy = min(max(yy, 0), SH - 1);
+      for (int xx = xlo; xx < xhi; ++xx) {
+        const float wx = fmaxf(0.f, 1.f - fabsf(((float)xx + 0.5f - cx) / supx));
+        if (wx <= 0.f) continue;
+        const int sx = min(max(xx, 0), SW - 1);
+        const uint8_t* px = img + ((long)sy * SW + sx) * 3;
+        const float w = wx * wy;
+        acc0 = fmaf(w, (float)px[0], acc0);
+        acc1 = fmaf(w, (float)px[1], acc1);
+        acc2 = fmaf(w, (float)px[2], acc2);
+        wsum += w;
+      }
+    }
+    const float inv = 1.f / wsum;
+    const float v0 = (acc0 * inv - mean) * inv_std;
+    const float v1 = (acc1 * inv - mean) * inv_std;
+    const float v2 = (acc2 * inv - mean) * inv_std;
+    if (out_mode == 0) {
+      uint2 o;
+      o.x = pack2(v0, v1);
+      o.y = pack2(v2, 0.f);
+      reinterpret_cast<uint2*>(out)[i] = o;
+    } else {
+      float* o = static_cast<float*>(out);
+      const long plane = (long)S * S;
+      const long base = (long)n * 3 * plane + (long)oy * S + ox;
+      o[base] = v0;
+      o[base + plane] = v1;
+      o[base + 2 * plane] = v2;
+    }
+  }
+}
+
 __global__ void one_hot_kernel(const long* __restrict__ labels, float* __restrict__ out, int B,
                                int C) {
   const long total = (long)B * C;
@@ -357,6 +415,36 @@ extern "C" int sib_augment(const void* src_u8, const int* boxes_dev, void* out, 
   const long total = (long)B * S * S;
   augment_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
       static_cast<const uint8_t*>(src_u8), boxes_dev, out, B, SH, SW, S, mean, 1.f / std, out_mode);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// resized extent of the resize-shorter step and the centre-crop origin (host twin exported for
+// the tests: sib_val_geometry_host)
+static void val_geometry(int SH, int SW, int S, int RS, int* g4) {
+  int RH, RW;
+  if (SH <= SW) { RH = RS; RW = (int)floor((double)SW * RS / SH + 0.5); }
+  else          { RW = RS; RH = (int)floor((double)SH * RS / SW + 0.5); }
+  g4[0] = RH; g4[1] = RW;
+  g4[2] = (int)floor(0.5 * (RH - S) + 0.5);   // oy0
+  g4[3] = (int)floor(0.5 * (RW - S) + 0.5);   // ox0
+}
+
+extern "C" void sib_val_geometry_host(int SH, int SW, int S, int resize_shorter, int* g4_host) {
+  val_geometry(SH, SW, S, resize_shorter, g4_host);
+}
+
+extern "C" int sib_val_transform(const void* src_u8, void* out, int B, int SH, int SW, int S,
+                                 int resize_shorter, float mean, float std, int out_mode,
+                                 void* stream) {
+  SIB_CHECK(out_mode == 0 || out_mode == 1, "val_transform: out_mode must be 0 (NHWC4 bf16) or 1 (NCHW f32)");
+  SIB_CHECK(resize_shorter >= S, "val_transform: resize_shorter %d smaller than the crop %d", resize_shorter, S);
+  int g[4];
+  val_geometry(SH, SW, S, resize_shorter, g);
+  const long total = (long)B * S * S;
+  val_transform_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
+      static_cast<const uint8_t*>(src_u8), out, B, SH, SW, S, g[0], g[1], g[2], g[3], mean, 1.f / std,
+      out_mode);
   SIB_LAUNCH_CHECK();
   return 0;
 }

@@ -43,6 +43,21 @@ class GpuAugment:
                            0 if self.output == "nhwc4_bf16" else 1)
 
 
+class GpuValTransform:
+    """Validation transform of the reference (dali_dataloader.py:146-160): resize the shorter side
+    to `crop_size` (= image_size when full_crop, else ceil((1.14*image_size + 8) // 16 * 16)),
+    centre crop image_size, normalise."""
+
+    def __init__(self, image_size=224, full_crop=False, output="nhwc4_bf16"):
+        assert output in ("nhwc4_bf16", "nchw_f32")
+        self.image_size, self.output = image_size, output
+        self.crop_size = image_size if full_crop else math.ceil((image_size * 1.14 + 8) // 16 * 16)
+
+    def __call__(self, src_u8, first_sample=0):
+        return ops.val_transform(src_u8, self.image_size, self.crop_size, DATA_MEAN, DATA_STD,
+                                 0 if self.output == "nhwc4_bf16" else 1)
+
+
 class SyntheticSource:
     """Pool of `pool` random images (uint8 HWC) and labels, generated once with a fixed seed."""
 
@@ -111,9 +126,11 @@ class SyntheticLoader:
         self.device = device
         self.source = source or SyntheticSource(num_classes=cfg.num_classes, device=device)
         self.epoch_size = epoch_size or self.source.pool
-        min_area = getattr(cfg, "min_area", 0.08) if train else 1.0
-        self.augment = GpuAugment(cfg.image_size, min_area, 1.0, seed=getattr(cfg, "seed", 0),
-                                  flip=train, output=output)
+        if train:
+            self.augment = GpuAugment(cfg.image_size, getattr(cfg, "min_area", 0.08), 1.0,
+                                      seed=getattr(cfg, "seed", 0), flip=True, output=output)
+        else:
+            self.augment = GpuValTransform(cfg.image_size, getattr(cfg, "full_crop", False), output)
         self._epoch = 0
 
     def __len__(self):

@@ -653,6 +653,26 @@ def augment(src_u8, boxes, size, mean=127.5, std=51.0, out_mode=0):
     return out
 
 
+def val_transform(src_u8, size, resize_shorter, mean=127.5, std=51.0, out_mode=0):
+    """resize-shorter + centre crop + normalise (reference val_pipeline, dali_dataloader.py:146-160)"""
+    b, sh, sw, ch = src_u8.shape
+    assert ch == 3 and src_u8.dtype == torch.uint8 and src_u8.is_contiguous()
+    if out_mode == 0:
+        out = new_act(b, 4, size, size, src_u8.device)
+    else:
+        out = torch.empty((b, 3, size, size), dtype=torch.float32, device=src_u8.device)
+    call("sib_val_transform", _p(src_u8), _p(out), b, sh, sw, size, int(resize_shorter), float(mean),
+         float(std), out_mode, _stream())
+    return out
+
+
+def val_geometry_host(sh, sw, size, resize_shorter):
+    import ctypes
+    g = (ctypes.c_int * 4)()
+    _lib.load().sib_val_geometry_host(sh, sw, size, int(resize_shorter), g)
+    return list(g)
+
+
 def one_hot(labels, num_classes):
     out = torch.empty((labels.shape[0], num_classes), dtype=torch.float32, device=labels.device)
     call("sib_one_hot", _p(labels), _p(out), labels.shape[0], num_classes, _stream())

@@ -134,3 +134,28 @@ def test_novograd_restatement_matches_reference_optimizer():
         for i in idx:
             assert torch.allclose(state[i]["ema_grad"], run["ema_grad"][i], atol=1e-6)
             assert torch.allclose(state[i]["ema_norm"].expand_as(ps[i]), run["ema_norm"][i], rtol=1e-5)
+
+
+def test_val_transform_oracle_properties_and_host_twin():
+    """Validation transform (dali_dataloader.py:146-160) restatement: geometry == the C host twin
+    of the kernel's, constant images stay constant, identity when nothing is resized, and the
+    centre of a down-scaled gradient image keeps the gradient."""
+    from sota_imagenet_b200 import ops
+    for sh, sw, s, rs in ((256, 256, 224, 256), (320, 427, 224, 256), (500, 375, 128, 144),
+                          (64, 48, 32, 32), (333, 500, 224, 224)):
+        assert augment_ref.val_geometry(sh, sw, s, rs) == ops.val_geometry_host(sh, sw, s, rs)
+    rh, rw, oy0, ox0 = augment_ref.val_geometry(320, 427, 224, 256)
+    assert (rh, rw) == (256, 342) and (oy0, ox0) == (16, 59)
+    const = np.full((40, 56, 3), 200, np.uint8)
+    out = augment_ref.val_transform_image(const, 16, 20)
+    assert np.allclose(out, (200 - 127.5) / 51.0, atol=1e-5)
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, size=(24, 24, 3), dtype=np.uint8)
+    same = augment_ref.val_transform_image(img, 24, 24)          # no resize, no crop
+    assert np.allclose(same, (img.astype(np.float32) - 127.5) / 51.0, atol=1e-5)
+    crop = augment_ref.val_transform_image(img, 16, 24)          # no resize, centre crop
+    assert np.allclose(crop, (img[4:20, 4:20].astype(np.float32) - 127.5) / 51.0, atol=1e-5)
+    ramp = np.tile(np.arange(64, dtype=np.uint8)[None, :, None] * 4, (64, 1, 3))
+    out = augment_ref.val_transform_image(ramp, 16, 32)          # 2x down-scale, centre 16 of 32
+    d = np.diff(out[8, :, 0])
+    assert np.allclose(d, 8.0 / 51.0, atol=1e-4)                 # 2 source pixels (x4) per output pixel
