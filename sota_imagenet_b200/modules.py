@@ -119,9 +119,13 @@ class SibModule(nn.Module):
         if self.training and getattr(self, "_nbt", None) is not None:
             self._nbt += 1
         if torch.is_grad_enabled() and (self.training or x.requires_grad):
-            if not hasattr(self, "_dummy") or self._dummy.device != x.device:
-                self._dummy = torch.zeros((), device=x.device, requires_grad=True)
-            return _SibFn.apply(x, self._dummy, self)
+            # A fresh leaf per call (no kernel: torch.empty): it only makes the node's output require
+            # grad.  A cached leaf keeps ONE AccumulateGrad node, bound to the stream of its first
+            # use, alive for as long as any earlier loss is still referenced; a later CUDA-graph
+            # capture then fails with "dependency created on uncaptured work in another stream"
+            # (scripts/probes/graph_capture_probe.py, variant 64).
+            dummy = torch.empty((), device=x.device, requires_grad=True)
+            return _SibFn.apply(x, dummy, self)
         y, _ = self.fwd(x, self.training)
         return y
 

@@ -112,3 +112,40 @@ def test_ema_accumulation_checkpoint_resume(tmp_path):
     err = (net.fc.weight - net2.fc.weight).abs().max().item()
     assert err < 5e-3, err          # same weights + same momentum -> same next step (up to bf16 chaos)
     assert not torch.equal(p1, net.fc.weight.detach())
+
+
+def test_cuda_graph_capture_while_previous_loss_is_alive():
+    """A training loop that keeps `loss` around (logging) must still capture: the autograd glue may
+    not cache a leaf whose AccumulateGrad node stays bound to the eager steps' stream
+    (scripts/probes/graph_capture_probe.py)."""
+    from sota_imagenet_b200 import losses, models, optimizers
+    torch.manual_seed(0)
+    net = models.resnet26(num_classes=16).cuda().train()
+    opt = optimizers.SGD(net.parameters(), lr=0.01, momentum=0.9, nesterov=True)
+    crit = losses.CrossEntropyLoss(smoothing=0.1)
+    x = torch.randn(8, 3, 64, 64, device="cuda")
+    y = torch.randint(0, 16, (8,), device="cuda")
+
+    def step():
+        opt.zero_grad()
+        loss = crit(net(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    held = [step() for _ in range(2)]          # losses (and their autograd nodes) stay referenced
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    out = torch.zeros((), device="cuda")
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        out.copy_(step())
+    before = float(out)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out) and float(out) != before and len(held) == 2
