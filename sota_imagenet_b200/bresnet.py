@@ -7,6 +7,8 @@ pytorch_tools is absent and unpinned, so the module graph below is this repo's r
 switches; oracle/bresnet_ref.py is its fp32 PyTorch twin used for parity.  Convs
 run on the tcgen05 kernels; the extra operators are the memory-bound kernels of csrc/extra.cu.  The
 block is composed from per-operator fwd/bwd pairs (not yet fused like the ResNet-50 bottleneck)."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -183,6 +185,11 @@ class BlurPool(SibModule):
         return ops.blurpool_bwd(_as_act(dy), saved[0])
 
 
+# Fold the drop-connect keep mask into the ECA gate (one scale pass instead of two, forward and
+# backward); SIB_FUSE_DROP_CONNECT=0 keeps the two-pass sequence (A/B and parity cross-check).
+FUSE_DROP_CONNECT = os.environ.get("SIB_FUSE_DROP_CONNECT", "1") != "0"
+
+
 class ECA(SibModule):
     """x * sigmoid(conv1d_k3(GAP(x))) over the channel axis (attn_type: eca)."""
 
@@ -191,21 +198,29 @@ class ECA(SibModule):
         assert kernel_size == 3
         self.weight = nn.Parameter(torch.empty(1, 1, 3).uniform_(-0.5, 0.5))
 
-    def fwd(self, x, train):
+    def fwd(self, x, train, extra=None):
+        """`extra` [N,C]: a further per-(sample, channel) factor applied in the same pass (the
+        drop-connect keep mask of the block: y = x * gate * extra), saving one full read + write of
+        the activation in forward and one in backward."""
         n, c, h, w = x.shape
         p = ops.chan_reduce(x, scale=1.0 / (h * w))
         s = ops.eca_gate_fwd(p, self.weight.data.view(3).contiguous())
-        return ops.scale_nc(x, s), (x, p, s)
+        if extra is None:
+            return ops.scale_nc(x, s), (x, p, s)
+        return ops.scale_nc(x, s * extra), (x, p, s, extra)
 
     def bwd(self, dy, saved, need_dx=True):
-        x, p, s = saved
+        x, p, s = saved[:3]
+        extra = saved[3] if len(saved) > 3 else None
         dy = _as_act(dy)
         n, c, h, w = x.shape
         ds = ops.chan_reduce(dy, x)
+        if extra is not None:            # d/d(gate) of x*gate*extra; extra is constant over (h, w)
+            ds = ds * extra
         dw = torch.zeros(3, dtype=torch.float32, device=x.device)
         dp = ops.eca_gate_bwd(ds, s, p, self.weight.data.view(3).contiguous(), dw)
         self._grad(self.weight).view(3).add_(dw)
-        return ops.scale_nc(dy, s, add=dp / (h * w))
+        return ops.scale_nc(dy, s if extra is None else s * extra, add=dp / (h * w))
 
 
 class BBottleneck(SibModule):
@@ -250,13 +265,15 @@ class BBottleneck(SibModule):
             a2b, sb = self.blur.fwd(a2, train)
         y3, s3 = self._conv_bn(self.conv3, self.bn3, a2b, train)
         se = None
-        if self.eca is not None:
-            y3, se = self.eca.fwd(y3, train)
         mask = None
         if train and self.keep_prob < 1.0:
             n, c = y3.shape[0], y3.shape[1]
             keep = (torch.rand(n, 1, device=y3.device) < self.keep_prob).float() / self.keep_prob
             mask = keep.expand(n, c).contiguous()
+        fused = mask is not None and self.eca is not None and FUSE_DROP_CONNECT
+        if self.eca is not None:
+            y3, se = self.eca.fwd(y3, train, extra=mask if fused else None)
+        if mask is not None and not fused:
             y3 = ops.scale_nc(y3, mask)
         xs, sp, sd = x, None, None
         if self.downsample is not None:
@@ -274,7 +291,7 @@ class BBottleneck(SibModule):
         x, a1, s1, a2, s2, a2b, sb, s3, se, mask, xs, sd, out = saved
         g = ops.act_bwd(_as_act(dout), out, self.act, self.bn1.slope)
         d = g
-        if mask is not None:
+        if mask is not None and not (se is not None and len(se) > 3):   # else folded into the ECA gate
             d = ops.scale_nc(d, mask)
         if self.eca is not None:
             d = self.eca.bwd(d, se)

@@ -110,3 +110,35 @@ def test_stochastic_layers_and_eval():
     with torch.no_grad():
         a, b = net(x), net(x)
     assert torch.equal(a, b)              # no randomness in eval mode
+
+
+def test_drop_connect_folded_into_eca_gate_matches_two_pass():
+    """y = x * gate * keep in one scale pass (forward and backward) == the two-pass sequence on the
+    same keep mask: block output, input gradient and every parameter gradient."""
+    from sota_imagenet_b200 import bresnet, ops
+    torch.manual_seed(1)
+    blk = bresnet.BBottleneck(256, 64, keep_prob=0.6).cuda().train()
+    x0 = ops.to_nhwc_bf16(torch.randn(16, 256, 14, 14, device="cuda"))
+    g0 = ops.to_nhwc_bf16(torch.randn(16, 256, 14, 14, device="cuda"))
+    runs = {}
+    for fused in (False, True):
+        bresnet.FUSE_DROP_CONNECT = fused
+        for p in blk.parameters():
+            p.grad = None
+        torch.manual_seed(7)                     # same keep mask in both runs
+        x = x0.clone().requires_grad_(True)
+        out = blk(x)
+        out.backward(g0)
+        torch.cuda.synchronize()
+        runs[fused] = (out.detach().float(), x.grad.float(),
+                       {n: p.grad.detach().clone() for n, p in blk.named_parameters()})
+    bresnet.FUSE_DROP_CONNECT = True
+    (o0, dx0, gr0), (o1, dx1, gr1) = runs[False], runs[True]
+    assert (o0 - o1).abs().max() <= 0.13 and _cos(o0, o1) > 0.99999   # one bf16 rounding instead of two
+    skip = torch.nn.functional.leaky_relu(x0.float(), 0.01)            # a dropped branch leaves act(x)
+    dropped = (o1.flatten(1) - skip.flatten(1)).abs().amax(1) < 2e-2
+    assert 0 < int(dropped.sum()) < 16                                 # some samples skipped the branch
+    assert torch.equal(dropped, (o0.flatten(1) - skip.flatten(1)).abs().amax(1) < 2e-2)
+    assert _cos(dx0, dx1) > 0.9999
+    for n in gr0:
+        assert _cos(gr0[n], gr1[n]) > 0.999, n
