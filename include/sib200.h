@@ -163,6 +163,9 @@ int sib_chan_reduce(const void* a, const void* b, float* out, int N, int HW, int
 /* y[n][hw][c] = x[n][hw][c] * mul[n][c] (+ add[n][c]) */
 int sib_scale_nc(const void* x, const float* mul, const float* add, void* y, int N, int HW, int C,
                  void* stream);
+/* y = act(x * mul[n][c] + res): BResNet block tail (ECA gate, drop-connect, shortcut, activation) */
+int sib_scale_add_act(const void* x, const float* mul, const void* res, void* y, int N, int HW,
+                      int C, int act, float slope, void* stream);
 int sib_eca_gate_fwd(const float* p, const float* w, float* s, int N, int C, void* stream);
 int sib_eca_gate_bwd(const float* ds, const float* s, const float* p, const float* w, float* dp,
                      float* dw, int N, int C, void* stream);

@@ -188,6 +188,9 @@ class BlurPool(SibModule):
 # Fold the drop-connect keep mask into the ECA gate (one scale pass instead of two, forward and
 # backward); SIB_FUSE_DROP_CONNECT=0 keeps the two-pass sequence (A/B and parity cross-check).
 FUSE_DROP_CONNECT = os.environ.get("SIB_FUSE_DROP_CONNECT", "1") != "0"
+# Apply the ECA gate inside the shortcut-add + activation pass (act(x*gate + r) in one kernel: the
+# gated tensor is never written); SIB_FUSE_ECA_TAIL=0 keeps scale_nc + add_act.
+FUSE_ECA_TAIL = os.environ.get("SIB_FUSE_ECA_TAIL", "1") != "0"
 
 
 class ECA(SibModule):
@@ -198,16 +201,18 @@ class ECA(SibModule):
         assert kernel_size == 3
         self.weight = nn.Parameter(torch.empty(1, 1, 3).uniform_(-0.5, 0.5))
 
-    def fwd(self, x, train, extra=None):
+    def fwd(self, x, train, extra=None, defer=False):
         """`extra` [N,C]: a further per-(sample, channel) factor applied in the same pass (the
         drop-connect keep mask of the block: y = x * gate * extra), saving one full read + write of
         the activation in forward and one in backward."""
         n, c, h, w = x.shape
         p = ops.chan_reduce(x, scale=1.0 / (h * w))
         s = ops.eca_gate_fwd(p, self.weight.data.view(3).contiguous())
-        if extra is None:
-            return ops.scale_nc(x, s), (x, p, s)
-        return ops.scale_nc(x, s * extra), (x, p, s, extra)
+        saved = (x, p, s) if extra is None else (x, p, s, extra)
+        se = s if extra is None else s * extra
+        if defer:                        # the caller applies the scale inside its own fused pass
+            return se, saved
+        return ops.scale_nc(x, se), saved
 
     def bwd(self, dy, saved, need_dx=True):
         x, p, s = saved[:3]
@@ -271,8 +276,12 @@ class BBottleneck(SibModule):
             keep = (torch.rand(n, 1, device=y3.device) < self.keep_prob).float() / self.keep_prob
             mask = keep.expand(n, c).contiguous()
         fused = mask is not None and self.eca is not None and FUSE_DROP_CONNECT
+        tail_scale = None                # ECA gate (* keep mask) applied inside the add + act pass
         if self.eca is not None:
-            y3, se = self.eca.fwd(y3, train, extra=mask if fused else None)
+            if FUSE_ECA_TAIL and (mask is None or fused):
+                tail_scale, se = self.eca.fwd(y3, train, extra=mask if fused else None, defer=True)
+            else:
+                y3, se = self.eca.fwd(y3, train, extra=mask if fused else None)
         if mask is not None and not fused:
             y3 = ops.scale_nc(y3, mask)
         xs, sp, sd = x, None, None
@@ -282,7 +291,10 @@ class BBottleneck(SibModule):
             r, sd = self._conv_bn(self.downsample[0], self.downsample[1], xs, train)
         else:
             r = x
-        out = ops.add_act(y3, r, self.act, self.bn1.slope)
+        if tail_scale is not None:
+            out = ops.scale_add_act(y3, tail_scale, r, self.act, self.bn1.slope)
+        else:
+            out = ops.add_act(y3, r, self.act, self.bn1.slope)
         if not train:
             return out, None
         return out, (x, a1, s1, a2, s2, a2b, sb, s3, se, mask, xs, sd, out)

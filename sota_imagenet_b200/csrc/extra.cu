@@ -196,6 +196,33 @@ scale_nc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ m
   }
 }
 
+// y[n][hw][c] = act(x[n][hw][c] * mul[n][c] + res[n][hw][c]): the BResNet block tail
+// (ECA gate * drop-connect keep, shortcut add, activation) in one pass
+__global__ void __launch_bounds__(256)
+scale_add_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mul,
+                     const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, int N,
+                     int HW, int C, int act, float slope) {
+  const int cvec = C >> 3;
+  const long total = (long)N * HW * cvec;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    const long n = i / ((long)HW * cvec);
+    float f[8], r[8];
+    unpack8(ldg_stream(x + i * 8), f);
+    unpack8(ldg_stream(res + i * 8), r);
+    const float* m = mul + n * C + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(f[j], __ldg(m + j), r[j]);
+      if (act == SIB_ACT_RELU) t = fmaxf(t, 0.f);
+      else if (act == SIB_ACT_LEAKY) t = t > 0.f ? t : t * slope;
+      f[j] = t;
+    }
+    stg_stream(y + i * 8, pack8(f));
+  }
+}
+
 // ECA gate: s[n][c] = sigmoid(sum_k w[k] * p[n][c + k - 1])   (conv1d, kernel 3, zero padding 1)
 __global__ void eca_gate_fwd_kernel(const float* __restrict__ p, const float* __restrict__ w,
                                     float* __restrict__ s, int N, int C) {
@@ -394,6 +421,14 @@ extern "C" int sib_scale_nc(const void* x, const float* mul, const float* add, v
   SIB_CHECK(C % 8 == 0, "scale_nc: C %% 8 != 0");
   scale_nc_kernel<<<ew_grid((long)N * HW * (C / 8), 256), 256, 0, ST(stream)>>>(CBF(x), mul, add,
                                                                                BF(y), N, HW, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_scale_add_act(const void* x, const float* mul, const void* res, void* y, int N,
+                                 int HW, int C, int act, float slope, void* stream) {
+  SIB_CHECK(C % 8 == 0, "scale_add_act: C %% 8 != 0");
+  scale_add_act_kernel<<<ew_grid((long)N * HW * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), mul, CBF(res), BF(y), N, HW, C, act, slope);
   SIB_LAUNCH_CHECK();
   return 0;
 }

@@ -513,6 +513,15 @@ def eca_gate_bwd(ds, s, p, w, dw):
     return dp
 
 
+def scale_add_act(x, mul, res, act, slope=0.01):
+    """act(x * mul[n, c] + res) in one pass (x, res: bf16 channels_last of equal shape)."""
+    n, c, h, w = x.shape
+    assert res.shape == x.shape
+    y = new_act(n, c, h, w, x.device)
+    call("sib_scale_add_act", _p(x), _p(mul), _p(res), _p(y), n, h * w, c, act, float(slope), _stream())
+    return y
+
+
 def add_act(a, b, act, slope=0.01):
     y = torch.empty_like(a)
     call("sib_add_act", _p(a), _p(b), _p(y), a.numel(), act, float(slope), _stream())
