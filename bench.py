@@ -100,6 +100,18 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
+def merge_profiles(runs):
+    """runs: lists of (name, args, start_event, end_event), one list per profiled step, same call
+    sequence -> [(name, args, ms)] with the per-call minimum over the steps.  Falls back to the
+    first step alone if the sequences differ."""
+    timed = [[(n, a, s0.elapsed_time(s1)) for n, a, s0, s1 in r] for r in runs]
+    first = timed[0]
+    same = all(len(r) == len(first) and all(x[0] == y[0] for x, y in zip(r, first)) for r in timed[1:])
+    if not same:
+        return first
+    return [(first[i][0], first[i][1], min(r[i][2] for r in timed)) for i in range(len(first))]
+
+
 # --------------------------------------------------------------------------------------------
 def cpu_oracle_rate(batch=16, size=SIZE, budget_s=20.0, min_steps=3, warmup=1):
     """torchvision ResNet-50 fp32 + smooth CE + torch SGD on the host cores (the oracle port of
@@ -334,17 +346,21 @@ def run_ours(args):
     #  for per-kernel durations the profiled step serialises them on one stream)
     from sota_imagenet_b200 import ops as _ops
     side_was, _ops._SideStream.enabled = _ops._SideStream.enabled, False
-    _lib.PROFILE = []
-    step(x_static, y_static)
-    torch.cuda.synchronize()
-    prof, _lib.PROFILE = _lib.PROFILE, None
+    runs = []
+    for _ in range(3):                  # three profiled steps; per call the fastest of the three
+        _lib.PROFILE = []               # (an eager step can catch a host hiccup inside one call)
+        step(x_static, y_static)
+        torch.cuda.synchronize()
+        runs.append(_lib.PROFILE)
+    _lib.PROFILE = None
+    prof = merge_profiles(runs)
     _ops._SideStream.enabled = side_was
     if rank == 0:
         pk = peaks()
         groups = {}
-        for name, a, s0, s1 in prof:
+        for name, a, ms_call in prof:
             d = groups.setdefault(name, [0.0, 0.0, 0])
-            d[0] += s0.elapsed_time(s1)
+            d[0] += ms_call
             d[1] += conv_flops(name, a)
             d[2] += 1
         conv_names = [n for n in groups if n.startswith("sib_conv2d")]
@@ -352,8 +368,8 @@ def run_ours(args):
         conv_fl = sum(groups[n][1] for n in conv_names)
         total_ms = sum(v[0] for v in groups.values())
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        bn_b = sum(bn_bytes(n, a) for n, a, _, _ in prof)
-        bn_ms = sum(s0.elapsed_time(s1) for n, a, s0, s1 in prof if bn_bytes(n, a) > 0)
+        bn_b = sum(bn_bytes(n, a) for n, a, _ in prof)
+        bn_ms = sum(t for n, a, t in prof if bn_bytes(n, a) > 0)
         roofline_bn = {"bound": "hbm", "kernel": "bn_finalize_apply / bn_bwd_reduce / bn_bwd_apply",
                        "achieved": bn_b / (bn_ms * 1e-3) / 1e9 if bn_ms else 0.0, "peak": pk["hbm_gbs"],
                        "unit": "GB/s", "frac": (bn_b / (bn_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if bn_ms else 0.0,

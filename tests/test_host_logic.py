@@ -217,3 +217,26 @@ def test_cutmix_mixup_host_logic_with_oracle_kernels(monkeypatch):
     cb.state.input = (x, torch.randint(0, 10, (4,)))
     cb.on_batch_begin()
     assert cb.state.input[0] is x
+
+
+def test_bench_profile_merge_takes_per_call_minimum():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+
+    def run(ts):
+        return [(n, (i,), Ev(0.0), Ev(t)) for i, (n, t) in enumerate(zip(("a", "b", "a"), ts))]
+
+    merged = bench.merge_profiles([run((1.0, 5.0, 2.0)), run((1.5, 2.0, 2.5)), run((0.9, 2.2, 9.0))])
+    assert merged == [("a", (0,), 0.9), ("b", (1,), 2.0), ("a", (2,), 2.0)]
+    odd = [run((1.0, 5.0, 2.0)), run((1.0, 5.0, 2.0))[:2]]
+    assert bench.merge_profiles(odd) == [("a", (0,), 1.0), ("b", (1,), 5.0), ("a", (2,), 2.0)]
+    assert bench.merge_profiles([run((3.0, 1.0, 2.0))])[0][2] == 3.0
