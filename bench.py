@@ -293,7 +293,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    final_loss = float(loss_static)
+    final_loss = float(loss_static.detach())
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -49,7 +49,7 @@ def test_one_step_loss_and_late_grads(batch, size):
     """Whole network, one step, against the pure-fp32 CPU oracle: loss within 1e-2 relative.
 
     Gradients: ResNet-50 at random init is a chaotic map - a 1e-3 perturbation of layer1 grows
-    ~1.8x per residual block (measured, scripts/gpu_debug_grads.py; stock torch.autocast(bf16)
+    ~1.8x per residual block (measured, tests/tools/gpu_debug_grads.py; stock torch.autocast(bf16)
     vs fp32 gives per-parameter cosines around 0.0-0.1 at batch 16, DESIGN.md "Parity"), so
     per-parameter cosine >= 0.999 over the WHOLE network is not attainable by any bf16 pipeline.
     The strict gradient gate therefore lives per block (tests/test_gpu_blocks.py); here the

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_dp2_equals_single_process_on_global_batch(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29517",
-           os.path.join(ROOT, "scripts", "dp_equivalence.py"), str(tmp_path)]
+           os.path.join(ROOT, "tests", "tools", "dp_equivalence.py"), str(tmp_path)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DP_EQUIVALENCE_OK" in r.stdout, r.stdout[-2000:]

@@ -1,7 +1,7 @@
 """Run under torchrun with 2 ranks: DP(2 x B) with SyncBN + bucketed all-reduce must equal one
 process on the concatenated 2B batch (gradients after one step, BN running statistics)."""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch, torch.distributed as dist
 from oracle import torch_ref
 from sota_imagenet_b200 import losses, models, parallel

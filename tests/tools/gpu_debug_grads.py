@@ -1,7 +1,7 @@
 """Layer-by-layer comparison of block outputs and block-output gradients: ours vs the
 bf16-faithful oracle (and vs pure fp32)."""
 import os, sys
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch, torch.nn.functional as F
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
