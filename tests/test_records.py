@@ -1,0 +1,148 @@
+"""CPU: host side of the real-data ingest (sota_imagenet_b200/records.py) — TFRecord framing and
+`tf.train.Example` wire format as the reference's create_records.py:84-106 writes them, DALI index
+files, reader sharding / shuffling semantics (dali_dataloader.py:47-65), decode + ragged packing."""
+import io
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from sota_imagenet_b200 import records
+
+
+def _jpeg(rng, h, w, mode="RGB", fmt="JPEG"):
+    from PIL import Image
+    ch = {"RGB": 3, "L": 1, "CMYK": 4}[mode]
+    arr = rng.randint(0, 256, size=(h, w, ch) if ch > 1 else (h, w), dtype=np.uint8)
+    buf = io.BytesIO()
+    Image.fromarray(arr, mode=mode).save(buf, format=fmt, quality=95)
+    return buf.getvalue(), arr
+
+
+def test_crc32c_and_example_known_answers():
+    assert records.crc32c(b"123456789") == 0xE3069283            # CRC-32C check value
+    assert records.crc32c(b"") == 0
+    # masked CRC as TFRecord defines it: rotr15(crc) + 0xa282ead8
+    c = 0xE3069283
+    assert records.masked_crc(b"123456789") == (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+    # Example{features{feature{"a": int64_list{value: [1]}}}} written out by hand from the
+    # protobuf wire format (Int64List is packed)
+    want = bytes.fromhex("0a0c0a0a0a01611205" "1a030a0101")
+    assert records.encode_example({"a": 1}) == want
+    assert records.parse_example(want) == {"a": [1]}
+    # unpacked (repeated varint) Int64List, as older writers emit it
+    unpacked = bytes.fromhex("0a0b0a090a01611204" "1a020801")
+    assert records.parse_example(unpacked) == {"a": [1]}
+    ex = records.encode_example({"image/encoded": b"\xff\xd8jpeg", "image/class/label": 999,
+                                 "image/filename": b"n01440764_1.JPEG", "neg": -1, "f": [0.5, 2.0]})
+    got = records.parse_example(ex)
+    assert got["image/encoded"] == b"\xff\xd8jpeg" and got["image/class/label"] == [999]
+    assert got["image/filename"] == b"n01440764_1.JPEG" and got["neg"] == [-1] and got["f"] == [0.5, 2.0]
+
+
+def test_tfrecord_roundtrip_index_and_corruption(tmp_path):
+    recs = [records.encode_example({"image/encoded": bytes([i]) * (10 + 7 * i), "image/class/label": i})
+            for i in range(9)]
+    path = str(tmp_path / "train-0-1.tfrecord")
+    index = records.write_tfrecord(path, recs)
+    assert index[0] == (0, 16 + len(recs[0])) and index[1][0] == index[0][1]
+    assert records.build_index(path) == index                    # what tfrecord2idx would emit
+    idx_path = str(tmp_path / "train-0-1.idx")
+    records.write_index(index, idx_path)
+    assert open(idx_path).readline() == "0 %d\n" % (16 + len(recs[0]))
+    assert records.read_index(idx_path) == index
+    # framing: little-endian u64 length first
+    raw = open(path, "rb").read()
+    assert struct.unpack("<Q", raw[:8])[0] == len(recs[0])
+    rd = records.TFRecordReader([path], [idx_path], verify=True)
+    out = list(rd)
+    assert [l for _, l in out] == list(range(9)) and out[3][0] == bytes([3]) * 31
+    assert len(rd) == 9 and rd.epoch == 1
+    rd.close()
+    # corrupt one payload byte: the CRC check catches it, the unchecked reader does not care
+    bad = bytearray(raw)
+    bad[index[2][0] + 20] ^= 0xFF
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(ValueError, match="CRC"):
+        list(records.TFRecordReader([path], [idx_path], verify=True))
+    # truncated file
+    open(path, "wb").write(raw[:-3])
+    with pytest.raises(ValueError, match="truncated"):
+        records.build_index(path)
+    with pytest.raises(ValueError):
+        records.TFRecordReader([path], [idx_path, idx_path])
+
+
+def test_reader_sharding_and_shuffle(tmp_path):
+    paths, idxs, n = [], [], 0
+    for s in range(3):
+        recs = [records.encode_example({"image/encoded": b"x%d" % (n + i), "image/class/label": n + i})
+                for i in range(5 + s)]
+        n += len(recs)
+        p = str(tmp_path / ("val-%d-3.tfrecord" % s))
+        records.write_index(records.write_tfrecord(p, recs), p + ".idx")
+        paths.append(p)
+        idxs.append(p + ".idx")
+    assert n == 18
+    # shards partition the sample space contiguously (no overlap, nothing dropped)
+    seen = []
+    for rank in range(4):
+        rd = records.TFRecordReader(paths, idxs, shard_id=rank, num_shards=4)
+        labels = [l for _, l in rd]
+        assert labels == list(range(*records.shard_range(18, rank, 4)))
+        seen += labels
+    assert seen == list(range(18))
+    assert [records.shard_range(10, i, 3) for i in range(3)] == [(0, 3), (3, 6), (6, 10)]
+    with pytest.raises(ValueError):
+        records.shard_range(10, 3, 3)
+    # shuffle: a permutation of the shard, new every epoch, reproducible from the seed
+    a = records.TFRecordReader(paths, idxs, shard_id=1, num_shards=2, random_shuffle=True, seed=7)
+    e0 = [l for _, l in a]
+    e1 = [l for _, l in a]
+    b = records.TFRecordReader(paths, None, shard_id=1, num_shards=2, random_shuffle=True, seed=7)   # index rebuilt by scanning
+    assert sorted(e0) == list(range(9, 18)) == sorted(e1) and e0 != e1 and e0 != sorted(e0)
+    assert [l for _, l in b] == e0
+
+
+def test_file_reader_and_decode_pack(tmp_path):
+    rng = np.random.RandomState(0)
+    root = tmp_path / "train"
+    want = {}
+    for ci, cname in enumerate(["n02", "n01", "n03"]):           # labels follow SORTED directory names
+        (root / cname).mkdir(parents=True)
+        for k in range(2):
+            data, arr = _jpeg(rng, 20 + 4 * ci, 30 + k, fmt="PNG")
+            (root / cname / ("img%d.png" % k)).write_bytes(data)
+            want[(cname, k)] = arr
+    (root / "n01" / "notes.txt").write_text("ignored")
+    rd = records.FileReader(str(root))
+    assert rd.classes == ["n01", "n02", "n03"] and len(rd) == 6
+    samples = list(rd)
+    assert [l for _, l in samples] == [0, 0, 1, 1, 2, 2]
+    assert np.array_equal(records.decode_image(samples[2][0]), want[("n02", 0)])      # lossless PNG
+    # ragged pack: one buffer, 16-byte aligned offsets, exact bytes back
+    buf, offsets, dims, labels = records.decode_batch(samples, workers=2)
+    assert labels.tolist() == [0, 0, 1, 1, 2, 2] and dims.dtype == torch.int32 and offsets.dtype == torch.int64
+    assert all(int(o) % 16 == 0 for o in offsets)
+    for i, (cname, k) in enumerate([("n01", 0), ("n01", 1), ("n02", 0), ("n02", 1), ("n03", 0), ("n03", 1)]):
+        h, w = dims[i].tolist()
+        got = buf[int(offsets[i]):int(offsets[i]) + h * w * 3].numpy().reshape(h, w, 3)
+        assert np.array_equal(got, want[(cname, k)])
+    # fixed canvas for the uniform kernels: centred, cropped / zero padded
+    imgs, labels = records.decode_batch(samples, canvas=(24, 28))
+    assert tuple(imgs.shape) == (6, 24, 28, 3) and imgs.dtype == torch.uint8
+    src = want[("n01", 0)]                                       # 24 x 30 -> all rows, cols 1..28
+    assert src.shape == (24, 30, 3) and np.array_equal(imgs[0].numpy(), src[:, 1:29])
+    tall = want[("n03", 1)]                                      # 28 x 31 -> rows 2..25, cols 1..28
+    assert tall.shape == (28, 31, 3) and np.array_equal(imgs[5].numpy(), tall[2:26, 1:29])
+    small = records.letterbox(np.full((4, 6, 3), 9, np.uint8), 8, 8)
+    assert small.sum() == 9 * 4 * 6 * 3 and small[2:6, 1:7].min() == 9 and small[0].max() == 0
+    # JPEG, grey and CMYK sources all come out as RGB (create_records.py:71-83 re-encodes the CMYK ones)
+    for mode in ("RGB", "L", "CMYK"):
+        data, arr = _jpeg(rng, 16, 24, mode=mode)
+        im = records.decode_image(data)
+        assert im.shape == (16, 24, 3) and im.dtype == np.uint8
+    with pytest.raises(ValueError):
+        records.FileReader(str(tmp_path))                        # one level too high: no images found
