@@ -240,6 +240,19 @@ int sib_augment(const void* src_u8, const int* boxes_dev, void* out, int B, int 
 int sib_val_transform(const void* src_u8, void* out, int B, int SH, int SW, int S,
                       int resize_shorter, float mean, float std, int out_mode, void* stream);
 void sib_val_geometry_host(int SH, int SW, int S, int resize_shorter, int* g4_host);
+/* ragged batches of real images (records.pack_batch): packed uint8 buffer + per-image byte offsets
+ * [B] + {H, W} [B][2]; same arithmetic as sib_rrc_boxes / sib_augment / sib_val_transform with the
+ * image base and extent looked up per sample (fn.decoders.image_random_crop + fn.resize on images of
+ * different sizes, dali_dataloader.py:65-74, :144-148). */
+int sib_rrc_boxes_ragged(int* boxes_dev, const int* dims_dev, int B, double min_area, double max_area,
+                         unsigned long long seed, unsigned long long first_sample, int do_flip,
+                         void* stream);
+int sib_augment_ragged(const void* packed_u8, const long* offsets_dev, const int* dims_dev,
+                       const int* boxes_dev, void* out, int B, int S, float mean, float std,
+                       int out_mode, void* stream);
+int sib_val_transform_ragged(const void* packed_u8, const long* offsets_dev, const int* dims_dev,
+                             void* out, int B, int S, int resize_shorter, float mean, float std,
+                             int out_mode, void* stream);
 int sib_one_hot(const long* labels, float* out, int B, int C, void* stream);
 /* batch-level mixing on the resident batch: pt_clb.Mixup / pt_clb.Cutmix as combined by
  * CutmixMixup (sota_imagenet/callbacks.py:232-247).  layout 0: NHWC bf16 [N][H][W][C], 1: NCHW

@@ -421,7 +421,7 @@ extern "C" int sib_augment(const void* src_u8, const int* boxes_dev, void* out, 
 
 // resized extent of the resize-shorter step and the centre-crop origin (host twin exported for
 // the tests: sib_val_geometry_host)
-static void val_geometry(int SH, int SW, int S, int RS, int* g4) {
+__host__ __device__ static inline void val_geometry(int SH, int SW, int S, int RS, int* g4) {
   int RH, RW;
   if (SH <= SW) { RH = RS; RW = (int)floor((double)SW * RS / SH + 0.5); }
   else          { RW = RS; RH = (int)floor((double)SH * RS / SW + 0.5); }
@@ -445,6 +445,129 @@ extern "C" int sib_val_transform(const void* src_u8, void* out, int B, int SH, i
   val_transform_kernel<<<ew_grid(total, 256), 256, 0, ST(stream)>>>(
       static_cast<const uint8_t*>(src_u8), out, B, SH, SW, S, g[0], g[1], g[2], g[3], mean, 1.f / std,
       out_mode);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ragged batches (real images of different sizes, records.pack_batch): one packed uint8 buffer,
+// per-image byte offsets and {H, W}.  Same arithmetic as the uniform kernels above, with the
+// image base pointer and extent looked up per sample.  mode 0: train (crop box, flip);
+// mode 1: validation (resize shorter side to RS, centre crop).
+namespace sib {
+
+__global__ void rrc_boxes_ragged_kernel(int* __restrict__ boxes, const int* __restrict__ dims, int B,
+                                        double min_area, double max_area, uint64_t seed,
+                                        uint64_t first_sample, int do_flip) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  int b[5];
+  rrc_box(dims[2 * i], dims[2 * i + 1], min_area, max_area, seed, first_sample + (uint64_t)i, b);
+  if (!do_flip) b[4] = 0;
+  for (int j = 0; j < 5; ++j) boxes[i * 5 + j] = b[j];
+}
+
+__global__ void __launch_bounds__(256)
+resample_ragged_kernel(const uint8_t* __restrict__ packed, const long* __restrict__ offsets,
+                       const int* __restrict__ dims, const int* __restrict__ boxes,
+                       void* __restrict__ out, int B, int S, int RS, int mode, float mean,
+                       float inv_std, int out_mode) {
+  const long total = (long)B * S * S;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % S);
+    const int oy = (int)((i / S) % S);
+    const int n = (int)(i / ((long)S * S));
+    const int SH = dims[2 * n], SW = dims[2 * n + 1];
+    const uint8_t* img = packed + offsets[n];
+    // source window [x0, x0 + cw) x [y0, y0 + ch) that taps clamp to, sample scale and centre
+    int x0, y0, cw, ch;
+    float scx, scy, cx, cy;
+    if (mode == 0) {
+      const int* bx = boxes + n * 5;
+      x0 = bx[0]; y0 = bx[1]; cw = bx[2]; ch = bx[3];
+      const int sx_out = bx[4] ? (S - 1 - ox) : ox;
+      scx = (float)cw / (float)S; scy = (float)ch / (float)S;
+      cx = ((float)sx_out + 0.5f) * scx; cy = ((float)oy + 0.5f) * scy;
+    } else {
+      int g[4];
+      val_geometry(SH, SW, S, RS, g);
+      x0 = 0; y0 = 0; cw = SW; ch = SH;
+      scx = (float)SW / (float)g[1]; scy = (float)SH / (float)g[0];
+      cx = ((float)(ox + g[3]) + 0.5f) * scx; cy = ((float)(oy + g[2]) + 0.5f) * scy;
+    }
+    const float supx = fmaxf(scx, 1.f), supy = fmaxf(scy, 1.f);
+    const int xlo = (int)floorf(cx - supx), xhi = (int)ceilf(cx + supx);
+    const int ylo = (int)floorf(cy - supy), yhi = (int)ceilf(cy + supy);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, wsum = 0.f;
+    for (int yy = ylo; yy < yhi; ++yy) {
+      const float wy = fmaxf(0.f, 1.f - fabsf(((float)yy + 0.5f - cy) / supy));
+      if (wy <= 0.f) continue;
+      const int sy = min(max(yy, 0), ch - 1) + y0;
+      for (int xx = xlo; xx < xhi; ++xx) {
+        const float wx = fmaxf(0.f, 1.f - fabsf(((float)xx + 0.5f - cx) / supx));
+        if (wx <= 0.f) continue;
+        const int sx = min(max(xx, 0), cw - 1) + x0;
+        const uint8_t* px = img + ((long)sy * SW + sx) * 3;
+        const float w = wx * wy;
+        acc0 = fmaf(w, (float)px[0], acc0);
+        acc1 = fmaf(w, (float)px[1], acc1);
+        acc2 = fmaf(w, (float)px[2], acc2);
+        wsum += w;
+      }
+    }
+    const float inv = 1.f / wsum;
+    const float v0 = (acc0 * inv - mean) * inv_std;
+    const float v1 = (acc1 * inv - mean) * inv_std;
+    const float v2 = (acc2 * inv - mean) * inv_std;
+    if (out_mode == 0) {
+      uint2 o;
+      o.x = pack2(v0, v1);
+      o.y = pack2(v2, 0.f);
+      reinterpret_cast<uint2*>(out)[i] = o;
+    } else {
+      float* o = static_cast<float*>(out);
+      const long plane = (long)S * S;
+      const long base = (long)n * 3 * plane + (long)oy * S + ox;
+      o[base] = v0;
+      o[base + plane] = v1;
+      o[base + 2 * plane] = v2;
+    }
+  }
+}
+
+}  // namespace sib
+
+extern "C" int sib_rrc_boxes_ragged(int* boxes_dev, const int* dims_dev, int B, double min_area,
+                                    double max_area, unsigned long long seed,
+                                    unsigned long long first_sample, int do_flip, void* stream) {
+  rrc_boxes_ragged_kernel<<<(B + 127) / 128, 128, 0, ST(stream)>>>(boxes_dev, dims_dev, B, min_area,
+                                                                  max_area, seed, first_sample, do_flip);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_augment_ragged(const void* packed_u8, const long* offsets_dev, const int* dims_dev,
+                                  const int* boxes_dev, void* out, int B, int S, float mean, float std,
+                                  int out_mode, void* stream) {
+  SIB_CHECK(out_mode == 0 || out_mode == 1, "augment_ragged: out_mode must be 0 (NHWC4 bf16) or 1 (NCHW f32)");
+  resample_ragged_kernel<<<ew_grid((long)B * S * S, 256), 256, 0, ST(stream)>>>(
+      static_cast<const uint8_t*>(packed_u8), offsets_dev, dims_dev, boxes_dev, out, B, S, 0, 0, mean,
+      1.f / std, out_mode);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sib_val_transform_ragged(const void* packed_u8, const long* offsets_dev,
+                                        const int* dims_dev, void* out, int B, int S,
+                                        int resize_shorter, float mean, float std, int out_mode,
+                                        void* stream) {
+  SIB_CHECK(out_mode == 0 || out_mode == 1, "val_transform_ragged: out_mode must be 0 or 1");
+  SIB_CHECK(resize_shorter >= S, "val_transform_ragged: resize_shorter %d smaller than the crop %d",
+            resize_shorter, S);
+  resample_ragged_kernel<<<ew_grid((long)B * S * S, 256), 256, 0, ST(stream)>>>(
+      static_cast<const uint8_t*>(packed_u8), offsets_dev, dims_dev, nullptr, out, B, S, resize_shorter,
+      1, mean, 1.f / std, out_mode);
   SIB_LAUNCH_CHECK();
   return 0;
 }

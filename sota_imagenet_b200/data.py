@@ -15,6 +15,7 @@
 """
 import copy
 import math
+import os
 
 import torch
 
@@ -151,6 +152,81 @@ class SyntheticLoader:
         self._epoch += 1
 
 
+class RecordLoader:
+    """(data, target) batches from real images: a `records.TFRecordReader` / `records.FileReader`
+    (sharded by rank like the DALI readers, dali_dataloader.py:47) -> host decode -> ONE pinned
+    ragged buffer -> H2D -> crop boxes / resample on the device (`sib_*_ragged`) -> one-hot targets.
+    Same interface as `SyntheticLoader` (`batch_size`, `__len__`, iteration; drop-last)."""
+
+    def __init__(self, cfg, reader, train=True, output="nhwc4_bf16", one_hot=True, device="cuda",
+                 decode_workers=8):
+        from . import records
+        self._records = records
+        self.cfg, self.reader, self.train, self.one_hot = cfg, reader, train, one_hot
+        self.batch_size, self.num_classes, self.device = cfg.batch_size, cfg.num_classes, device
+        self.image_size = cfg.image_size
+        self.out_mode = 0 if output == "nhwc4_bf16" else 1
+        self.min_area, self.seed = getattr(cfg, "min_area", 0.08), getattr(cfg, "seed", 0)
+        full_crop = getattr(cfg, "full_crop", False)
+        self.crop_size = self.image_size if full_crop else math.ceil((self.image_size * 1.14 + 8) // 16 * 16)
+        self.decode_workers = decode_workers
+        self._seen = 0
+
+    def __len__(self):
+        return len(self.reader) // self.batch_size
+
+    def _emit(self, samples):
+        buf, offsets, dims, labels = self._records.decode_batch(samples, workers=self.decode_workers,
+                                                                pinned=torch.cuda.is_available())
+        dev = self.device
+        buf, offsets, dims = (t.to(dev, non_blocking=True) for t in (buf, offsets, dims))
+        labels = labels.to(dev, non_blocking=True)
+        if self.train:
+            boxes = ops.rrc_boxes_ragged(dims, self.min_area, 1.0, self.seed, self._seen, True)
+            data = ops.augment_ragged(buf, offsets, dims, boxes, self.image_size, DATA_MEAN, DATA_STD,
+                                      self.out_mode)
+        else:
+            data = ops.val_transform_ragged(buf, offsets, dims, self.image_size, self.crop_size,
+                                            DATA_MEAN, DATA_STD, self.out_mode)
+        self._seen += len(samples)
+        target = ops.one_hot(labels, self.num_classes) if self.one_hot else labels
+        return data, target
+
+    def __iter__(self):
+        batch = []
+        for sample in self.reader:
+            batch.append(sample)
+            if len(batch) == self.batch_size:
+                yield self._emit(batch)
+                batch = []
+        # the ragged tail is dropped (LastBatchPolicy.DROP, dali_dataloader.py:175)
+
+
+def real_data_root(cfg):
+    """cfg.root_data_dir (default "${env:IMAGENET_DIR}", arg_parser.py:25) if it names a directory
+    that holds the reference's layout, else None (-> synthetic data)."""
+    root = getattr(cfg, "root_data_dir", None)
+    if not root:
+        return None
+    if root.startswith("${env:") and root.endswith("}"):
+        root = os.environ.get(root[6:-1], "")
+    if not root or not os.path.isdir(root):
+        return None
+    sub = "train_records" if getattr(cfg, "use_tfrecords", False) else "train"
+    return root if os.path.isdir(os.path.join(root, sub)) else None
+
+
+def make_reader(cfg, root, split, rank=0, world_size=1):
+    """TFRecord shards + DALI indexes (`use_tfrecords`) or class folders, sharded by rank; the
+    train split is shuffled every epoch (dali_dataloader.py:47), validation is read in order (:130)."""
+    from . import records
+    kw = dict(shard_id=rank, num_shards=world_size, random_shuffle=(split == "train"),
+              seed=getattr(cfg, "seed", 0))
+    if getattr(cfg, "use_tfrecords", False):
+        return records.TFRecordReader.from_root(root, split, **kw)
+    return records.FileReader(os.path.join(root, split), **kw)
+
+
 class DataManager:
     """Stage list semantics of DaliDataManager (dali_dataloader.py:189-239)."""
 
@@ -186,6 +262,14 @@ class DataManager:
             for key, value in self.stages[idx].extra_args.items():
                 setattr(train_cfg, key, value)
         val_cfg.image_size = train_cfg.image_size
+        root = real_data_root(train_cfg) if self.source is None else None
+        if root is not None:
+            # real images on disk, laid out like the reference expects (dali_dataloader.py:46-65)
+            self.loader = RecordLoader(train_cfg, make_reader(train_cfg, root, "train", self.rank, self.world_size),
+                                       train=True, **self.loader_kw)
+            self.val_loader = RecordLoader(val_cfg, make_reader(val_cfg, root, "val", self.rank, self.world_size),
+                                           train=False, **self.loader_kw)
+            return
         self.loader = SyntheticLoader(train_cfg, self.source, rank=self.rank,
                                       world_size=self.world_size, train=True, **self.loader_kw)
         self.val_loader = SyntheticLoader(val_cfg, self.source, rank=self.rank,

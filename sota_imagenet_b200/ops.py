@@ -682,6 +682,46 @@ def val_geometry_host(sh, sw, size, resize_shorter):
     return list(g)
 
 
+def _check_ragged(packed, offsets, dims):
+    if packed.dtype != torch.uint8 or not packed.is_cuda or not packed.is_contiguous():
+        raise _lib.SibError("ragged batch: packed buffer must be a contiguous uint8 CUDA tensor")
+    if offsets.dtype != torch.int64 or dims.dtype != torch.int32 or dims.dim() != 2 or dims.shape[1] != 2 \
+            or offsets.numel() != dims.shape[0] or not offsets.is_cuda or not dims.is_cuda:
+        raise _lib.SibError("ragged batch: offsets int64 [B] and dims int32 [B, 2] on the device expected")
+    return dims.shape[0]
+
+
+def rrc_boxes_ragged(dims, min_area, max_area, seed, first_sample, do_flip):
+    """Crop boxes for images of different sizes (dims int32 [B, 2] = {H, W} on the device)."""
+    b = dims.shape[0]
+    boxes = torch.empty((b, 5), dtype=torch.int32, device=dims.device)
+    call("sib_rrc_boxes_ragged", _p(boxes), _p(dims.contiguous()), b, float(min_area), float(max_area),
+         int(seed), int(first_sample), int(do_flip), _stream())
+    return boxes
+
+
+def augment_ragged(packed, offsets, dims, boxes, size, mean=127.5, std=51.0, out_mode=0):
+    b = _check_ragged(packed, offsets, dims)
+    if out_mode == 0:
+        out = new_act(b, 4, size, size, packed.device)
+    else:
+        out = torch.empty((b, 3, size, size), dtype=torch.float32, device=packed.device)
+    call("sib_augment_ragged", _p(packed), _p(offsets.contiguous()), _p(dims.contiguous()), _p(boxes), _p(out),
+         b, size, float(mean), float(std), out_mode, _stream())
+    return out
+
+
+def val_transform_ragged(packed, offsets, dims, size, resize_shorter, mean=127.5, std=51.0, out_mode=0):
+    b = _check_ragged(packed, offsets, dims)
+    if out_mode == 0:
+        out = new_act(b, 4, size, size, packed.device)
+    else:
+        out = torch.empty((b, 3, size, size), dtype=torch.float32, device=packed.device)
+    call("sib_val_transform_ragged", _p(packed), _p(offsets.contiguous()), _p(dims.contiguous()), _p(out), b,
+         size, int(resize_shorter), float(mean), float(std), out_mode, _stream())
+    return out
+
+
 def one_hot(labels, num_classes):
     out = torch.empty((labels.shape[0], num_classes), dtype=torch.float32, device=labels.device)
     call("sib_one_hot", _p(labels), _p(out), labels.shape[0], num_classes, _stream())

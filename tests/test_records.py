@@ -146,3 +146,80 @@ def test_file_reader_and_decode_pack(tmp_path):
         assert im.shape == (16, 24, 3) and im.dtype == np.uint8
     with pytest.raises(ValueError):
         records.FileReader(str(tmp_path))                        # one level too high: no images found
+
+
+def test_record_loader_host_flow_with_oracle_kernels(tmp_path, monkeypatch):
+    """RecordLoader + make_reader + real_data_root on a tiny class-folder data set of images of
+    different sizes; the three ragged kernels are replaced by the numpy oracle (the GPU test
+    tests/test_gpu_ragged.py runs the same comparison against the CUDA kernels)."""
+    from types import SimpleNamespace
+    from oracle import augment_ref
+    from sota_imagenet_b200 import data, ops
+    rng = np.random.RandomState(1)
+    root = tmp_path / "imagenet"
+    imgs = {}
+    for split, per_class in (("train", 3), ("val", 2)):
+        for ci, cname in enumerate(["n01", "n02"]):
+            (root / split / cname).mkdir(parents=True)
+            for k in range(per_class):
+                d, arr = _jpeg(rng, 24 + 5 * k + ci, 40 - 3 * k, fmt="PNG")
+                (root / split / cname / ("%d.png" % k)).write_bytes(d)
+                imgs[(split, ci, k)] = arr
+
+    def unpack(packed, offsets, dims):
+        out = []
+        for o, (h, w) in zip(offsets.tolist(), dims.tolist()):
+            out.append(packed[o:o + h * w * 3].numpy().reshape(h, w, 3))
+        return out
+
+    def boxes_ragged(dims, min_area, max_area, seed, first, flip):
+        return torch.tensor([augment_ref.rrc_box(h, w, min_area, max_area, seed, first + i)
+                             for i, (h, w) in enumerate(dims.tolist())], dtype=torch.int32)
+
+    def aug_ragged(packed, offsets, dims, boxes, size, mean, std, out_mode):
+        ims = unpack(packed, offsets, dims)
+        return torch.from_numpy(np.stack([augment_ref.augment_image(im, b, size, mean, std)
+                                          for im, b in zip(ims, boxes.tolist())]))
+
+    def val_ragged(packed, offsets, dims, size, rs, mean, std, out_mode):
+        return torch.from_numpy(np.stack([augment_ref.val_transform_image(im, size, rs, mean, std)
+                                          for im in unpack(packed, offsets, dims)]))
+
+    monkeypatch.setattr(ops, "rrc_boxes_ragged", boxes_ragged)
+    monkeypatch.setattr(ops, "augment_ragged", aug_ragged)
+    monkeypatch.setattr(ops, "val_transform_ragged", val_ragged)
+    monkeypatch.setattr(ops, "one_hot", lambda l, n: torch.eye(n)[l])
+    cfg = SimpleNamespace(image_size=16, batch_size=2, num_classes=2, min_area=0.3, seed=5,
+                          root_data_dir=str(root), use_tfrecords=False)
+    assert data.real_data_root(cfg) == str(root)
+    monkeypatch.setenv("SIB_TEST_ROOT", str(root))
+    assert data.real_data_root(SimpleNamespace(root_data_dir="${env:SIB_TEST_ROOT}")) == str(root)
+    assert data.real_data_root(SimpleNamespace(root_data_dir="${env:SIB_NOT_SET_ANYWHERE}")) is None
+    assert data.real_data_root(SimpleNamespace(root_data_dir=str(root), use_tfrecords=True)) is None
+    # validation: in order, resize-shorter (crop_size ceil((16*1.14+8)//16*16) = 16) + centre crop
+    vl = data.RecordLoader(cfg, data.make_reader(cfg, str(root), "val"), train=False, device="cpu")
+    assert vl.crop_size == 16 and len(vl) == 2 and vl.batch_size == 2
+    batches = list(vl)
+    assert len(batches) == 2
+    x, t = batches[0]
+    assert tuple(x.shape) == (2, 16, 16, 3) and t.tolist() == [[1.0, 0.0], [1.0, 0.0]]
+    want = augment_ref.val_transform_image(imgs[("val", 0, 1)], 16, 16)
+    assert np.allclose(x[1].numpy(), want)
+    # training: sharded by rank, shuffled per epoch, crop RNG keyed by the running sample index
+    seen = []
+    for rank in range(2):
+        tl = data.RecordLoader(cfg, data.make_reader(cfg, str(root), "train", rank, 2), train=True, device="cpu")
+        assert len(tl) == 1                                   # 3 samples per shard, batch 2, drop last
+        for x, t in tl:
+            assert tuple(x.shape) == (2, 16, 16, 3) and t.sum().item() == 2.0
+            seen.append(t.argmax(1).tolist())
+        assert tl._seen == 2
+    assert seen[0] == [0, 0] or seen[0] == [0, 0][::-1]      # shard 0 holds class n01 only
+    assert set(seen[1]) == {1}
+    # the stage manager picks the real-data loaders when the data set is there
+    run = SimpleNamespace(stages=[SimpleNamespace(start=0, end=1, extra_args=None)])
+    full = SimpleNamespace(loader=cfg, val_loader=SimpleNamespace(**dict(vars(cfg), batch_size=2, full_crop=True)), run=run)
+    dm = data.DataManager(full, device="cpu")
+    dm.set_stage(0)
+    assert isinstance(dm.loader, data.RecordLoader) and isinstance(dm.val_loader, data.RecordLoader)
+    assert dm.val_loader.crop_size == 16 and len(dm.loader) == 3
