@@ -12,9 +12,9 @@ augmentation kernels.
 
 Pure Python + numpy (no tensorflow, no protobuf package): the wire formats are small enough to state
 here.  JPEG decoding uses PIL (or OpenCV) on host threads and packs a batch into ONE pinned uint8
-buffer with per-image offsets / sizes, ready for a single H2D copy.  The device side that consumes
-ragged batches (per-image base pointers in `sib_augment`) is the next step; until then
-`decode_batch(..., canvas=(H, W))` letterboxes onto a fixed canvas for the existing uniform kernels.
+buffer with per-image offsets / sizes, ready for a single H2D copy; `data.RecordLoader` hands it
+to the ragged kernels (`sib_rrc_boxes_ragged`, `sib_augment_ragged`, `sib_val_transform_ragged`).
+`decode_batch(..., canvas=(H, W))` letterboxes onto a fixed canvas for the uniform-shape kernels.
 """
 import io
 import os
