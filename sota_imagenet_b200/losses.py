@@ -10,8 +10,6 @@
   AngularPenaltySMLoss       reference angular_losses.py:13-95 (arcface / cosface variants)
   ArcCosSoftmax              reference angular_losses.py:572-576 (CE over -acos(cos))
 """
-import math
-
 import torch
 import torch.nn as nn
 

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .modules import (BatchNorm2d, Bottleneck, Linear, MaxPool3x3s2, SibModule, StemConv, _as_act)
+from .modules import BatchNorm2d, Bottleneck, Linear, MaxPool3x3s2, SibModule, StemConv
 
 
 FUSE_STEM_POOL = os.environ.get("SIB_FUSE_STEM_POOL", "1") != "0"

@@ -1,6 +1,5 @@
 """CPU: the C-ABI library loads, exports every symbol include/sib200.h declares, and refuses to
 compute without a GPU (no CPU fallback anywhere in the product path)."""
-import ctypes
 import os
 import subprocess
 

@@ -2,7 +2,6 @@
 `tf.train.Example` wire format as the reference's create_records.py:84-106 writes them, DALI index
 files, reader sharding / shuffling semantics (dali_dataloader.py:47-65), decode + ragged packing."""
 import io
-import os
 import struct
 
 import numpy as np
