@@ -240,3 +240,20 @@ def test_bench_profile_merge_takes_per_call_minimum():
     odd = [run((1.0, 5.0, 2.0)), run((1.0, 5.0, 2.0))[:2]]
     assert bench.merge_profiles(odd) == [("a", (0,), 1.0), ("b", (1,), 5.0), ("a", (2,), 2.0)]
     assert bench.merge_profiles([run((3.0, 1.0, 2.0))])[0][2] == 3.0
+
+
+def test_reference_targets_of_the_widened_rows_resolve():
+    """`_target_` strings of the reference's configs for MyNovograd / CutmixMixup / ArcCosSoftmax
+    (e.g. configs/hydra_exp/67.vgg-cmodel_s2d4_frn1.yaml:126) resolve to this package's classes."""
+    from sota_imagenet_b200 import losses, optimizers
+    opt = config.call({"_target_": "sota_imagenet.optimizers.MyNovograd", "weight_decay": 1e-3,
+                       "unitwise_norm": True}, [torch.nn.Parameter(torch.zeros(4))])
+    assert isinstance(opt, optimizers.MyNovograd) and opt.unitwise_norm and opt.defaults["betas"] == (0.9, 0.99)
+    cb = config.call({"_target_": "sota_imagenet.callbacks.CutmixMixup", "cutmix_alpha": 1.0, "mixup_alpha": 0.2})
+    assert isinstance(cb, runner.CutmixMixup) and cb.prob == 0.5
+    assert isinstance(config.call({"_target_": "src.callbacks.CutmixMixup", "cutmix_alpha": 1.0, "mixup_alpha": 1.0}),
+                      runner.CutmixMixup)
+    crit = config.call({"_target_": "src.angular_losses.ArcCosSoftmax", "smoothing": 0.1})
+    assert isinstance(crit, losses.ArcCosSoftmax) and crit.smoothing == 0.1
+    with pytest.raises(AssertionError):
+        losses.AdaCos(final_criterion=None, arc_logits=True)      # reference angular_losses.py:277
