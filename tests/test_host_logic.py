@@ -257,3 +257,32 @@ def test_reference_targets_of_the_widened_rows_resolve():
     assert isinstance(crit, losses.ArcCosSoftmax) and crit.smoothing == 0.1
     with pytest.raises(AssertionError):
         losses.AdaCos(final_criterion=None, arc_logits=True)      # reference angular_losses.py:277
+
+
+def test_cmodel_graph_executor_matches_manual_wiring_and_releases_outputs():
+    """Tagged multi-input graph (the reference's U-Net / FPN style self-test, model.py:1304-1356):
+    same numbers as wiring the layers by hand; retained outputs are dropped after their last reader."""
+    torch.manual_seed(0)
+    layers = [
+        dict(module="nn.Conv2d", args=[3, 4, 3], kwargs=dict(padding=1), tag="a"),
+        dict(module="nn.ReLU"),
+        dict(module="nn.Conv2d", args=[4, 4, 3], kwargs=dict(padding=1), tag="b"),
+        dict(module="Concat", inputs=["a", "b"], tag="ab"),
+        dict(module="nn.Conv2d", args=[8, 2, 1]),
+        dict(module="Concat", inputs=["_prev_", "ab", "a"]),
+    ]
+    m = cmodel.CModel(layers)
+    assert m.saved_layers_idx == [0, 2, 3, 0] and m._last_reader == {0: 5, 2: 3, 3: 5}
+    assert [l.input_indexes for l in m] == [[-1], [-1], [-1], [0, 2], [-1], [-1, 3, 0]]
+    x = torch.randn(2, 3, 5, 5)
+    a = m[0](x)
+    b = m[2](torch.relu(a))
+    ab = torch.cat([a, b], 1)
+    want = torch.cat([m[4](ab), ab, a], 1)
+    assert torch.allclose(m(x), want, atol=1e-6) and want.shape == (2, 14, 5, 5)   # Concat emits channels_last
+    with pytest.raises(KeyError):
+        cmodel.CModel([dict(module="nn.ReLU", inputs=["nope"])])
+    # ModuleStructure instances are accepted as well as dicts; a chain keeps nn.Sequential.forward
+    chain = cmodel.CModel([cmodel.ModuleStructure(module="nn.ReLU"), dict(module="nn.Identity", repeat=3)])
+    assert chain.saved_layers_idx == [] and isinstance(chain[1], torch.nn.Sequential) and len(chain[1]) == 3
+    assert "forward" not in chain.__dict__
