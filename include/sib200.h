@@ -56,6 +56,22 @@ int sib_conv2d_fprop(const void* x, const void* w, void* y, int N, int H, int W,
                      int R, int S, int stride, int pad_h, int pad_w, int OH, int OW,
                      const float* bias, float* stats, int flags, void* stream);
 
+/* y = conv(act(BN(x)), w): BatchNorm (+ activation) of the PRODUCER layer fused into the conv's
+ * operand prologue -- x is the raw (pre-BN) output of the previous conv and the normalised
+ * activation is never written to memory (north_star (2); replaces the cuDNN BatchNorm forward +
+ * ReLU that pytorch_tools' ABN runs between two convs, reference train.py:64,76).
+ * Training (bn_stats != NULL: [2][C] sum / sum of squares of x, already all-reduced under SyncBN):
+ * the kernel also finalises that BatchNorm -- mean_invstd [2][C], scale_shift [2][C] are written,
+ * running_mean / running_var updated with `momentum` (nn.BatchNorm2d semantics, `count` = elements
+ * per channel).  Eval (bn_stats == NULL): scale_shift is an input.  Zero padding applies to the
+ * ACTIVATED tensor (padding taps contribute 0).  C % 64 == 0, C <= 512. */
+int sib_conv2d_fprop_bnact(const void* x, const void* w, void* y, int N, int H, int W, int C, int K,
+                           int R, int S, int stride, int pad_h, int pad_w, int OH, int OW,
+                           float* stats, int flags, const float* bn_stats, const float* gamma,
+                           const float* beta, float* running_mean, float* running_var,
+                           float* mean_invstd, float* scale_shift, double count, float eps,
+                           float momentum, int act, float slope, void* stream);
+
 /* dx[N][H][W][C] = dgrad(dy[N][OH][OW][K]) [+ residual]; w_dgrad is the tap-flipped transposed
  * filter [C][R][S][K] produced by sib_pack_dgrad_weights.  `residual` (optional, geometry of dx,
  * may alias dx) is added in the epilogue (identity-shortcut gradient).  stride > 1 needs

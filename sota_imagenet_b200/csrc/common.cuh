@@ -73,6 +73,30 @@ __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
                : "memory");
 }
 
+// BatchNorm coefficients of one channel from its raw batch sums.  Every kernel that derives
+// them (bn_finalize, the fused finalize+apply kernels, the conv prologue) goes through this one
+// function with explicit roundings, so scale/shift are bit-identical wherever they are computed
+// and a ReLU mask recomputed in backward matches the forward exactly.
+struct BnCoeffs {
+  float mean, var, invstd, scale, shift;
+};
+__device__ __forceinline__ BnCoeffs bn_coeffs(float sum, float sumsq, float gamma, float beta,
+                                              float count, float eps) {
+  BnCoeffs k;
+  k.mean = __fdiv_rn(sum, count);
+  k.var = fmaxf(__fmaf_rn(-k.mean, k.mean, __fdiv_rn(sumsq, count)), 0.f);
+  k.invstd = rsqrtf(__fadd_rn(k.var, eps));
+  k.scale = __fmul_rn(gamma, k.invstd);
+  k.shift = __fmaf_rn(-k.mean, k.scale, beta);
+  return k;
+}
+__device__ __forceinline__ float bn_unbiased(float var, float count) {
+  return count > 1.f ? __fdiv_rn(__fmul_rn(var, count), __fsub_rn(count, 1.f)) : var;
+}
+__device__ __forceinline__ float bn_running(float running, float value, float momentum) {
+  return __fmaf_rn(momentum, value, __fmul_rn(__fsub_rn(1.f, momentum), running));
+}
+
 // ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------

@@ -22,6 +22,8 @@ constexpr int kBK = 64;         // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int kABytes = kBM * kBK * 2;
 constexpr int kThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA + TMEM alloc, warps 2-5 epilogue
 constexpr int kIgemmThreads = 384;  // igemm: warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 epilogue
+constexpr int kIgemmThreadsPro = 512;   // + warps 12-15: BatchNorm/activation transform of the A operand
+constexpr int kProMaxC = 512;           // input channels the fused prologue's scale/shift table holds
 constexpr int kSlabBytes = 32 * 128;   // epilogue staging: 32 rows x 64 bf16, 128B-swizzled
 
 // 4 consecutive fp32 sums in one L2 operation (16-byte aligned address)
@@ -63,6 +65,40 @@ struct IgemmParams {
   int stat_c;        // real channel count behind the GEMM columns: column j is channel j % stat_c
                      // for `stats`, `mask_ss` and `mean_invstd` (== Cout except for the parity GEMMs)
 };
+
+// ---- fused BatchNorm (+ activation) prologue on the A operand (fprop; kernels with PRO) ----
+//   The conv consumes a = act(fmaf(c, scale, shift)) where c is the raw output of the previous
+//   conv: TMA lands the raw tile in shared memory, four transform warps rewrite it in place
+//   (zero-padding taps stay zero), fence.proxy.async, and only then the MMA warp may read it.
+//   The normalised activation is never written to HBM.  scale/shift come from the raw batch
+//   statistics of the producer conv's epilogue (training: every CTA derives the table, CTA 0
+//   publishes mean/invstd, scale/shift and the running statistics, i.e. bn_finalize folded in)
+//   or from `scale_shift` itself (eval: stats == nullptr).
+struct BnPrologue {
+  const float* stats;        // [2][Cin] sum, sum of squares (already all-reduced under SyncBN) or null
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* mean_invstd;        // out [2][Cin] (training)
+  float* scale_shift;        // out [2][Cin] (training) / in (eval)
+  float count, eps, momentum;
+  int act;
+  float slope;
+  int IH, IW, Cin;           // input extent: taps outside it are padding and stay zero
+};
+
+// setmaxnreg: the PRO kernels run 512 threads (128 registers each at launch); the producer /
+// MMA warpgroup and the transform warpgroup give registers back so the two epilogue
+// warpgroups keep the 168 they need ((64 + 168 + 168 + 104) * 128 <= 64 Ki registers).
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 // ---- epilogue (shared by the 1-CTA and 2-CTA kernels) ----
 //   warps 4-11 (8 warps; warp e reads TMEM lane quarter e%4 and the 64-column chunks with
@@ -369,12 +405,14 @@ __device__ __forceinline__ void igemm_epilogue(
 //   warp2 : TMEM alloc / dealloc
 //   warp4-11: epilogue (igemm_epilogue above)
 // The epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int STAGES, int SLABS, int AUX>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+//   PRO: warps 12-15 apply the producer BatchNorm (+ activation) to every A stage in place
+//        between the TMA load and the MMA (BnPrologue above).
+template <int BN, int STAGES, int SLABS, int AUX, bool PRO>
+__global__ void __launch_bounds__(PRO ? kIgemmThreadsPro : kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
              const __grid_constant__ CUtensorMap tmAux1, const __grid_constant__ CUtensorMap tmAux2,
-             const IgemmParams p) {
+             const IgemmParams p, const BnPrologue pro) {
   constexpr int kBBytes = BN * kBK * 2;
   constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
   constexpr int kChunks = BN / 64;
@@ -388,8 +426,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
   __shared__ uint64_t res_bar[8];
+  __shared__ uint64_t ready_bar[PRO ? STAGES : 1];   // PRO: A stage transformed (4 warp arrivals)
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_part[kEpiWarps * 2 * kChunksPerWarp * 64];   // per-warp column sums of a tile
+  __shared__ __align__(16) float s_ss[PRO ? 2 * kProMaxC : 4];   // PRO: scale | shift per input channel
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -409,6 +449,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      if (PRO) mbar_init(&ready_bar[s], 4);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -429,7 +470,105 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   griddep_launch();
   griddep_wait();
 
-  if (warp == 0) {
+  if (PRO) {
+    // BatchNorm finalize folded in: every CTA derives the scale/shift table of the producer BN
+    // from its raw batch sums; CTA 0 publishes what backward needs and the running statistics
+    const int C = pro.Cin;
+    for (int c = threadIdx.x; c < C; c += kIgemmThreadsPro) {
+      float sc, sh;
+      if (pro.stats != nullptr) {
+        const BnCoeffs k = bn_coeffs(pro.stats[c], pro.stats[C + c], pro.gamma ? pro.gamma[c] : 1.f,
+                                     pro.beta ? pro.beta[c] : 0.f, pro.count, pro.eps);
+        sc = k.scale;
+        sh = k.shift;
+        if (blockIdx.x == 0) {
+          pro.mean_invstd[c] = k.mean;
+          pro.mean_invstd[C + c] = k.invstd;
+          pro.scale_shift[c] = sc;
+          pro.scale_shift[C + c] = sh;
+          if (pro.running_mean != nullptr) {
+            pro.running_mean[c] = bn_running(pro.running_mean[c], k.mean, pro.momentum);
+            pro.running_var[c] = bn_running(pro.running_var[c], bn_unbiased(k.var, pro.count), pro.momentum);
+          }
+        }
+      } else {
+        sc = pro.scale_shift[c];
+        sh = pro.scale_shift[C + c];
+      }
+      s_ss[c] = sc;
+      s_ss[kProMaxC + c] = sh;
+    }
+    __syncthreads();
+  }
+
+  // (setmaxnreg sits at the top of each role branch so that it dominates the role's code)
+  if (PRO && warp >= 12) {
+    reg_dec<104>();
+    // ---- A-operand transform: a = act(fmaf(c, scale, shift)), padding taps stay zero ----
+    // thread t owns the logical 16-byte chunk (8 channels) t % 8 of rows t / 8 + 16 i: its
+    // coefficients stay in registers for a whole k-block and a warp touches four whole
+    // 128-byte rows per access (conflict-free under the 128B swizzle)
+    const int tt = threadIdx.x - 384;
+    const int lc = tt & 7, r0 = tt >> 3;
+    const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((lc ^ (r0 & 7)) << 4);
+    const int act = pro.act;
+    const float slope = pro.slope;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * kBM;
+      int bh[8], bw[8];         // base pixel (tap 0) of the thread's eight rows
+      if (!p.tiled_a) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + r0 + 16 * i;
+          const int n_img = m / p.trav_hw;
+          const int rem = m - n_img * p.trav_hw;
+          const int pp = rem / p.trav_w;
+          bh[i] = pp * p.stride - p.pad_h;
+          bw[i] = (rem - pp * p.trav_w) * p.stride - p.pad_w;
+        }
+      }
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        float sc[8], sh[8];
+        {
+          const float4* t4 = reinterpret_cast<const float4*>(&s_ss[cb * kBK + lc * 8]);
+          const float4* u4 = reinterpret_cast<const float4*>(&s_ss[kProMaxC + cb * kBK + lc * 8]);
+          const float4 a0 = t4[0], a1 = t4[1], b0 = u4[0], b1 = u4[1];
+          sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+          sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+        }
+        const int tr = tap / p.S;
+        const int ts = tap - tr * p.S;
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* base = smem_a + stage * kABytes + off0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4* q = reinterpret_cast<uint4*>(base + i * 2048);
+          bool inside = true;
+          if (!p.tiled_a)
+            inside = (unsigned)(bh[i] + tr) < (unsigned)pro.IH && (unsigned)(bw[i] + ts) < (unsigned)pro.IW;
+          float f[8];
+          unpack8(*q, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float v = fmaf(f[j], sc[j], sh[j]);
+            if (act == SIB_ACT_RELU) v = fmaxf(v, 0.f);
+            else if (act == SIB_ACT_LEAKY) v = v > 0.f ? v : v * slope;
+            f[j] = inside ? v : 0.f;
+          }
+          *q = pack8(f);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_bar[stage]);
+        if (++cb == p.cin_blocks) { cb = 0; ++tap; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
+    if (PRO) reg_dec<64>();
     if (lane == 0) {
       // ---- TMA producer ----
       int stage = 0;
@@ -471,6 +610,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     //  owned by the other warp -- has not completed yet; the parity test then passes at once and
     //  the MMAs read data still in flight (launch failure at full size).  The halo kernel's ring
     //  holds one whole tile per stage and both of its issuing warps observe every tile's barrier.)
+    if (PRO) reg_dec<64>();
     constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
     const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), 16, 1024, kSwizzle128B);
     const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), 16, 1024, kSwizzle128B);
@@ -484,6 +624,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < p.num_kblocks; ++kb) {
         mbar_wait_w(&full_bar[stage], phase);
+        if (PRO) mbar_wait_w(&ready_bar[stage], phase);   // A stage rewritten by the transform warps
         tc_fence_after();
         const uint64_t a_desc = a_desc0 + (uint32_t)(stage * (kABytes >> 4));
         const uint64_t b_desc = b_desc0 + (uint32_t)(stage * (kBBytes >> 4));
@@ -499,9 +640,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+    if (PRO) reg_inc<168>();
     igemm_epilogue<BN, SLABS, AUX, false>(&tmOut, &tmRes, &tmAux1, &tmAux2, p, smem_slab, smem_aux,
                                           tmem_full_bar, tmem_empty_bar, res_bar, s_part, tmem_base,
                                           blockIdx.x, gridDim.x, num_tiles, 0);
+  } else if (PRO) {
+    reg_dec<64>();      // warps 2 and 3: the rest of warpgroup 0 must execute the same setmaxnreg
   }
   tc_fence_before();
   __syncthreads();
@@ -1262,22 +1406,24 @@ struct IgemmMaps {
   CUtensorMap a, b, out, res, aux1, aux2;
 };
 
-template <int BN, int STAGES, int SLABS, int AUX>
-static int launch_igemm(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t stream) {
+template <int BN, int STAGES, int SLABS, int AUX, bool PRO = false>
+static int launch_igemm(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t stream,
+                        const BnPrologue* pro = nullptr) {
   constexpr int kEpiWarps = 8;
   constexpr int smem =
       STAGES * (kABytes + BN * kBK * 2) + kEpiWarps * (SLABS + AUX) * kSlabBytes + 1024;
-  static_assert(smem + 8192 + 512 <= 232448, "shared memory budget");
+  static_assert(smem + 8192 + 512 + (PRO ? 8 * kProMaxC + 64 : 0) <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS, AUX>,
+    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS, AUX, PRO>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   int grid = p.num_m_tiles * p.num_n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  SIB_CUDA(launch_pdl(igemm_kernel<BN, STAGES, SLABS, AUX>, dim3(grid), dim3(kIgemmThreads), smem,
-                      stream, tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p));
+  SIB_CUDA(launch_pdl(igemm_kernel<BN, STAGES, SLABS, AUX, PRO>, dim3(grid),
+                      dim3(PRO ? kIgemmThreadsPro : kIgemmThreads), smem, stream, tm.a, tm.b, tm.out,
+                      tm.res, tm.aux1, tm.aux2, p, pro != nullptr ? *pro : BnPrologue{}));
   return 0;
 }
 
@@ -1346,7 +1492,7 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
                      int IH, int IW, int Cin, int Cout, int R, int S, int stride, int pad_h,
                      int pad_w, int TH, int TW, const float* bias, float* stats, int flags,
                      cudaStream_t stream, const BnBwdFuse* fuse = nullptr,
-                     const StridedOut* so = nullptr) {
+                     const StridedOut* so = nullptr, const BnPrologue* pro = nullptr) {
   // 1x1 filters may have a ragged K: TMA zero-fills both operands past Cin
   SIB_CHECK(Cin % 64 == 0 || (R == 1 && S == 1 && Cin % 8 == 0),
             "igemm: Cin must be a multiple of 64 (or of 8 for 1x1 filters), got %d", Cin);
@@ -1354,7 +1500,7 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   SIB_CHECK((long)N * TH * TW < (1l << 31), "igemm: too many pixels");
   // 3x3 / stride 1 / pad 1 on 64 or 128 output channels at >= 28 pixel rows: halo-reuse kernel
   {
-    const bool geometry = so == nullptr && R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && TH == IH &&
+    const bool geometry = pro == nullptr && so == nullptr && R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && TH == IH &&
                           TW == IW && Cin % 64 == 0 && IW + 2 <= 63 && residual == nullptr &&
                           bias == nullptr && (Cout == 64 || Cout == 128) &&
                           (fuse == nullptr || fuse->aux2 == nullptr);
@@ -1454,7 +1600,11 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   // (a 2-CTA variant with a 128-column tile measured no faster than the 1-CTA kernel:
   //  128 -> 128 3x3 at 28x28 0.094 vs 0.092 ms)
   const bool two_cta = BN == 256 && p.num_m_tiles % 2 == 0 && p.num_kblocks >= 4 &&
-                       !(flags & SIB_FLAG_NO_2CTA);
+                       !(flags & SIB_FLAG_NO_2CTA) && pro == nullptr;
+  if (pro != nullptr)
+    SIB_CHECK(Cin % 64 == 0 && Cin <= kProMaxC && aux == 0 && so == nullptr && residual == nullptr,
+              "igemm: the fused BatchNorm prologue needs Cin %% 64 == 0, Cin <= %d (got %d) and a plain fprop",
+              kProMaxC, Cin);
   rc = make_tmap_2d_bf16(&tm.b, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin,
                          two_cta ? BN / 2 : BN, kBK, true);
   if (rc) return rc;
@@ -1486,6 +1636,11 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   }
   if (p.stats != nullptr && !(flags & SIB_FLAG_STATS_ZEROED))
     SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * p.stat_c, stream));
+  if (pro != nullptr) {
+    if (BN == 64) return launch_igemm<64, 6, 1, 0, true>(tm, p, stream, pro);
+    if (BN == 128) return launch_igemm<128, 5, 1, 0, true>(tm, p, stream, pro);
+    return launch_igemm<256, 3, 2, 0, true>(tm, p, stream, pro);
+  }
   if (aux == 0) {
     if (two_cta) return launch_igemm2<256, 5, 1, 0>(tm, p, stream);
     if (BN == 64) return launch_igemm<64, 6, 1, 0>(tm, p, stream);
@@ -1532,6 +1687,31 @@ extern "C" int sib_conv2d_fprop(const void* x, const void* w, void* y, int N, in
             "fprop: output extent %dx%d inconsistent with input %dx%d", OH, OW, H, W);
   return run_igemm(x, w, y, nullptr, N, H, W, C, K, R, S, stride, pad_h, pad_w, OH, OW, bias,
                    stats, flags, static_cast<cudaStream_t>(stream));
+}
+
+// y = conv(act(BN(x)), w): the BatchNorm (+ activation) of the producer layer is applied to the
+// A operand inside the kernel (BnPrologue); training mode (bn_stats != null) also finalises that
+// BatchNorm (mean/invstd, scale/shift, running statistics).
+extern "C" int sib_conv2d_fprop_bnact(const void* x, const void* w, void* y, int N, int H, int W,
+                                      int C, int K, int R, int S, int stride, int pad_h, int pad_w,
+                                      int OH, int OW, float* stats, int flags, const float* bn_stats,
+                                      const float* gamma, const float* beta, float* running_mean,
+                                      float* running_var, float* mean_invstd, float* scale_shift,
+                                      double count, float eps, float momentum, int act, float slope,
+                                      void* stream) {
+  SIB_CHECK(OH >= 1 && OW >= 1 && (OH - 1) * stride - pad_h < H && (OW - 1) * stride - pad_w < W,
+            "fprop_bnact: output extent %dx%d inconsistent with input %dx%d", OH, OW, H, W);
+  SIB_CHECK(scale_shift != nullptr && (bn_stats == nullptr || mean_invstd != nullptr),
+            "fprop_bnact: scale_shift (and mean_invstd in training mode) are required");
+  BnPrologue pro{};
+  pro.stats = bn_stats; pro.gamma = gamma; pro.beta = beta;
+  pro.running_mean = running_mean; pro.running_var = running_var;
+  pro.mean_invstd = mean_invstd; pro.scale_shift = scale_shift;
+  pro.count = (float)count; pro.eps = eps; pro.momentum = momentum;
+  pro.act = act; pro.slope = slope;
+  pro.IH = H; pro.IW = W; pro.Cin = C;
+  return run_igemm(x, w, y, nullptr, N, H, W, C, K, R, S, stride, pad_h, pad_w, OH, OW, nullptr,
+                   stats, flags, static_cast<cudaStream_t>(stream), nullptr, nullptr, &pro);
 }
 
 extern "C" int sib_upsample_zero(const void* dy, void* up, int N, int OH, int OW, int C, int UH,

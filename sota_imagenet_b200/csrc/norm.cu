@@ -114,20 +114,15 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
                                    float eps, float momentum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float mean = stats[c] / count;
-  float var = stats[C + c] / count - mean * mean;
-  var = fmaxf(var, 0.f);
-  const float invstd = rsqrtf(var + eps);
-  mean_invstd[c] = mean;
-  mean_invstd[C + c] = invstd;
-  const float g = gamma ? gamma[c] : 1.f;
-  const float b = beta ? beta[c] : 0.f;
-  scale_shift[c] = g * invstd;
-  scale_shift[C + c] = b - mean * g * invstd;
+  const BnCoeffs k = bn_coeffs(stats[c], stats[C + c], gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f,
+                               count, eps);
+  mean_invstd[c] = k.mean;
+  mean_invstd[C + c] = k.invstd;
+  scale_shift[c] = k.scale;
+  scale_shift[C + c] = k.shift;
   if (running_mean) {
-    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    running_mean[c] = bn_running(running_mean[c], k.mean, momentum);
+    running_var[c] = bn_running(running_var[c], bn_unbiased(k.var, count), momentum);
   }
 }
 
@@ -218,22 +213,18 @@ __device__ __forceinline__ void bn_derive(const float* __restrict__ stats,
   if (beta) load8f(beta + c0, b);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float mean = s1[j] / count;
-    const float var = fmaxf(s2[j] / count - mean * mean, 0.f);
-    const float invstd = rsqrtf(var + eps);
-    const float gm = gamma ? g[j] : 1.f, bt = beta ? b[j] : 0.f;
-    sc[j] = gm * invstd;
-    sh[j] = bt - mean * gm * invstd;
+    const BnCoeffs k = bn_coeffs(s1[j], s2[j], gamma ? g[j] : 1.f, beta ? b[j] : 0.f, count, eps);
+    sc[j] = k.scale;
+    sh[j] = k.shift;
     if (publish) {
       const int c = c0 + j;
-      mean_invstd[c] = mean;
-      mean_invstd[C + c] = invstd;
+      mean_invstd[c] = k.mean;
+      mean_invstd[C + c] = k.invstd;
       scale_shift[c] = sc[j];
       scale_shift[C + c] = sh[j];
       if (running_mean) {
-        const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+        running_mean[c] = bn_running(running_mean[c], k.mean, momentum);
+        running_var[c] = bn_running(running_var[c], bn_unbiased(k.var, count), momentum);
       }
     }
   }

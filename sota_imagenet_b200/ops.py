@@ -195,6 +195,39 @@ def conv2d_fprop(x, w, stride=1, pad=0, stats=None, bias=None, flags=0, pad_hw=N
     return y
 
 
+def conv2d_fprop_bnact(x, w, bn, stride=1, pad=0, stats=None, act=ACT_RELU, slope=0.01, count=None,
+                       eps=1e-5, momentum=0.1, scale_shift=None, flags=0):
+    """y = conv(act(BN(x)), w) with the BatchNorm (+ activation) of the producer layer applied to
+    the conv's A operand inside the kernel: `x` is the RAW output of the previous conv, the
+    normalised activation never reaches HBM (csrc/conv.cu BnPrologue).
+    Training: bn = (stats, gamma, beta, running_mean, running_var); returns y, mean_invstd,
+    scale_shift (the finalize step is folded into the conv).  Eval: bn = None, `scale_shift` given."""
+    _lib.require_device()
+    _check_act(x, "x")
+    n, c, h, wd = x.shape
+    k, c2, r, s = w.shape
+    assert c2 == c, "filter/input channel mismatch"
+    oh, ow = conv_out_hw(h, wd, r, s, stride, pad)
+    y = new_act(n, k, oh, ow, x.device)
+    if _ACC_POOL.owns(stats):
+        flags |= FLAG_STATS_ZEROED
+    mi = None
+    if bn is not None:
+        mi = torch.empty((2, c), dtype=torch.float32, device=x.device)
+        scale_shift = torch.empty((2, c), dtype=torch.float32, device=x.device)
+    b = bn if bn is not None else (None,) * 5
+    call("sib_conv2d_fprop_bnact", _p(x), _p(w), _p(y), n, h, wd, c, k, r, s, stride, pad, pad, oh, ow,
+         _p(stats), flags, _p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]), _p(b[4]), _p(mi), _p(scale_shift),
+         float(count if count is not None else n * h * wd), float(eps), float(momentum), act,
+         float(slope), _stream())
+    return y, mi, scale_shift
+
+
+def fprop_bnact_ok(c_in):
+    """Mirror of the C-side limits of the fused prologue (csrc/conv.cu kProMaxC)."""
+    return c_in % 64 == 0 and c_in <= 512
+
+
 def pack_dgrad_s2(w_dgrad, sub0=None, sub1=None):
     """[C][3][3][K] flipped pack -> row-parity sub-filters ([2C][1][2][K], [2C][2][2][K]) of the
     3x3 / stride-2 dgrad."""

@@ -89,6 +89,70 @@ def test_conv_fprop_dgrad_wgrad(n, h, w, c, k, r, stride, pad, flags):
     assert rel(dw, 2 * dw_ref) < 1e-4                   # accumulates into dw (zero_grad contract)
 
 
+PROLOGUE_CASES = [
+    # N, H, W, C, K, R, stride, act
+    (2, 16, 16, 64, 256, 1, 1, "relu"),        # conv3 <- bn2: tiled A, one k-block, BN = 256
+    (3, 14, 14, 128, 512, 1, 1, "relu"),       # two k-blocks, two n-tiles, ragged M
+    (8, 16, 16, 256, 1024, 1, 1, "leaky_relu"),  # four k-blocks, several tiles per CTA
+    (3, 7, 7, 512, 2048, 1, 1, "relu"),        # eight k-blocks (ring wraps), ragged M
+    (2, 16, 16, 64, 64, 3, 1, "relu"),         # conv2 <- bn1: im2col, padding taps must stay zero
+    (4, 14, 14, 128, 128, 3, 1, "relu"),       # BN = 128, 18 k-blocks
+    (2, 28, 28, 128, 128, 3, 2, "relu"),       # strided 3x3
+    (3, 15, 15, 256, 256, 3, 2, "leaky_relu"),   # odd extent, stride 2, BN = 256
+    (40, 12, 12, 64, 64, 1, 1, "identity"),    # BN = 64 (two epilogue groups), no activation
+    (2, 56, 56, 64, 64, 3, 1, "relu"),         # the layer1 shape
+]
+
+
+@pytest.mark.parametrize("n,h,w,c,k,r,stride,act", PROLOGUE_CASES)
+def test_conv_fprop_fused_bn_prologue(n, h, w, c, k, r, stride, act):
+    """conv(act(BN(x))) with the BatchNorm applied inside the conv's operand prologue ==
+    bn_finalize_apply followed by the plain conv: BIT-identical output, statistics within atomics
+    order, identical mean/invstd/scale/shift and running statistics."""
+    torch.manual_seed(5)
+    pad = r // 2
+    x = ops.to_nhwc_bf16((torch.randn(n, c, h, w) * 1.7 + 0.4).cuda())
+    wt = (torch.randn(k, c, r, r) / (c * r * r) ** 0.5).cuda().to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last)
+    gamma = (torch.rand(c, device="cuda") + 0.5)
+    beta = torch.randn(c, device="cuda") * 0.3
+    code = ops.ACT_CODES[act]
+    count = n * h * w
+
+    def fresh():
+        return torch.zeros(c, device="cuda") + 0.25, torch.ones(c, device="cuda") * 1.5
+
+    # reference: separate finalize + apply, then the plain conv
+    rm0, rv0 = fresh()
+    st = ops.bn_stats(x)
+    a, (mi0, ss0), _ = ops.bn_finalize_apply(x, (st, gamma, beta, rm0, rv0), act=code, slope=0.02,
+                                             count=count, eps=1e-5, momentum=0.1)
+    stats0 = torch.empty(2, k, device="cuda")
+    y0 = ops.conv2d_fprop(a, wt, stride=stride, pad=pad, stats=stats0, flags=ops.FLAG_NO_HALO | ops.FLAG_NO_2CTA)
+    # fused
+    rm1, rv1 = fresh()
+    stats1 = torch.empty(2, k, device="cuda")
+    y1, mi1, ss1 = ops.conv2d_fprop_bnact(x, wt, (st, gamma, beta, rm1, rv1), stride=stride, pad=pad,
+                                          stats=stats1, act=code, slope=0.02, count=count)
+    torch.cuda.synchronize()
+    assert torch.equal(mi0, mi1) and torch.equal(ss0, ss1)
+    assert torch.equal(rm0, rm1) and torch.equal(rv0, rv1)
+    assert torch.equal(y0, y1), "fused prologue differs: max |d| = %g" % float((y0.float() - y1.float()).abs().max())
+    assert rel(stats1, stats0) < 1e-5
+    # eval mode: scale/shift supplied, nothing finalised
+    y2, _, _ = ops.conv2d_fprop_bnact(x, wt, None, stride=stride, pad=pad, act=code, slope=0.02, scale_shift=ss0)
+    assert torch.equal(y0, y2)
+    # against fp32 torch
+    xf = x.float().cpu()
+    mean = xf.mean(dim=(0, 2, 3))
+    var = xf.var(dim=(0, 2, 3), unbiased=False)
+    z = (xf - mean[None, :, None, None]) / (var[None, :, None, None] + 1e-5).sqrt() * gamma.cpu()[None, :, None, None] \
+        + beta.cpu()[None, :, None, None]
+    z = {"relu": F.relu, "leaky_relu": lambda t: F.leaky_relu(t, 0.02), "identity": lambda t: t}[act](z)
+    y_ref = F.conv2d(z.bfloat16().float(), wt.float().cpu(), stride=stride, padding=pad)
+    assert rel(y1, y_ref) < 8e-3
+
+
 FUSED_CASES = [
     # N, H, W, C(dgrad output channels), K, R, stride, pad, mode
     (2, 16, 16, 64, 256, 1, 1, 0, "recompute"),     # conv3 dgrad -> bn2 (BN=64 tile)
