@@ -170,13 +170,16 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 def conv_flops(name, a):
     """Algorithmic FLOPs of one conv launch from its C-ABI arguments."""
-    if name == "sib_conv2d_fprop":   # x w y N H W C K R S stride ph pw OH OW ...
+    if name in ("sib_conv2d_fprop", "sib_conv2d_fprop_bnact"):   # x w y N H W C K R S stride ph pw OH OW ...
         n, c, k, r, s, oh, ow = a[3], a[6], a[7], a[8], a[9], a[13], a[14]
         return 2.0 * n * oh * ow * k * c * r * s
     if name in ("sib_conv2d_dgrad", "sib_conv2d_dgrad_bnbwd"):   # dy w dx residual workspace N H W C K R S stride pad
         n, h, w, c, k, r, s, stride, pad = a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13]
         oh, ow = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
         return 2.0 * n * oh * ow * k * c * r * s
+    if name == "sib_conv2d_dgrad_s2":   # dy w_sub0 w_sub1 dx N H W C K : 3x3 / stride-2 dgrad by row parity
+        n, h, w, c, k = a[4], a[5], a[6], a[7], a[8]
+        return 2.0 * n * (h // 2) * (w // 2) * k * c * 9
     if name == "sib_conv2d_wgrad":   # x dy dw N H W C K R S stride ph pw OH OW
         n, c, k, r, s, oh, ow = a[3], a[6], a[7], a[8], a[9], a[13], a[14]
         return 2.0 * n * oh * ow * k * c * r * s
@@ -192,6 +195,8 @@ def bn_bytes(name, a):
         return 2.0 * a[5] * a[6] * (2 + nz(a[2]))
     if name == "sib_bn_bwd_reduce":          # dy out mask_ss x mi x2 mi2 M C
         return 2.0 * a[7] * a[8] * (2 + nz(a[1]) + nz(a[5]))
+    if name == "sib_bn_bwd_apply_remat":     # dy mask_ss x mi gamma sums dx dgamma dbeta act_ss act slope a_out M(13) C(14)
+        return 2.0 * a[13] * a[14] * 4
     if name == "sib_bn_bwd_apply":           # dy out . x . . . x2 . . dx dx2 gout ... M(17) C(18)
         return 2.0 * a[17] * a[18] * (3 + nz(a[1]) + nz(a[7]) + nz(a[11]) + nz(a[12]))
     return 0.0
@@ -370,7 +375,7 @@ def run_ours(args):
         achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         bn_b = sum(bn_bytes(n, a) for n, a, _ in prof)
         bn_ms = sum(t for n, a, t in prof if bn_bytes(n, a) > 0)
-        roofline_bn = {"bound": "hbm", "kernel": "bn_finalize_apply / bn_bwd_reduce / bn_bwd_apply",
+        roofline_bn = {"bound": "hbm", "kernel": "bn_finalize_apply / bn_bwd_reduce / bn_bwd_apply(_remat)",
                        "achieved": bn_b / (bn_ms * 1e-3) / 1e9 if bn_ms else 0.0, "peak": pk["hbm_gbs"],
                        "unit": "GB/s", "frac": (bn_b / (bn_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if bn_ms else 0.0,
                        "traffic": None, "bytes_per_step": bn_b, "ms_per_step_eager_events": bn_ms}

@@ -143,6 +143,16 @@ int sib_bn_bwd_apply(const void* dy, const void* out, const float* mask_ss, cons
                      const void* x2, const float* mean_invstd2, const float* gamma2, void* dx,
                      void* dx2, void* gout, float* dgamma, float* dbeta, float* dgamma2,
                      float* dbeta2, long M, int C, double count, int act, float slope, void* stream);
+/* sib_bn_bwd_apply for a plain BatchNorm (+ activation) that ALSO re-materialises the forward
+ * activation a_out = fwd_act(x * act_ss.scale + act_ss.shift): with the fused conv prologue
+ * (sib_conv2d_fprop_bnact) the activation is never stored in forward, and the weight gradient of
+ * the consumer conv needs it in backward.  x is in registers anyway: +2 B/element written. */
+int sib_bn_bwd_apply_remat(const void* dy, const float* mask_ss, const void* x,
+                           const float* mean_invstd, const float* gamma, const float* sums, void* dx,
+                           float* dgamma, float* dbeta, const float* act_ss, int fwd_act,
+                           float fwd_slope, void* a_out, long M, int C, double count, int act,
+                           float slope, void* stream);
+
 /* (dgamma/dbeta[/2], optional: the affine-parameter gradients are ACCUMULATED into them) */
 int sib_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int accumulate,
                       void* stream);

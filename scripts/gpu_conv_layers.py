@@ -57,6 +57,24 @@ for (c, k, h, r, stride, pad, cnt) in SHAPES:
         fuse = dict(mask_src=x, mask_ss=ss, mean_invstd=mi, act=ops.ACT_RELU, slope=0.0)
         fns["dgrad+bn"] = lambda: ops.conv2d_dgrad(dy, wd, tuple(x.shape), r, r, stride=stride, pad=pad, flags=FLAGS, w_s2=ws2, bn_bwd=fuse)
         fns["reduce"] = lambda: ops.bn_bwd_reduce(x, None, x, mi, ops.ACT_RELU, 0.0, mask_ss=ss)
+    if "--prologue" in sys.argv:
+        # fprop with the producer BatchNorm + ReLU fused into the A-operand prologue vs the separate
+        # bn_finalize_apply pass followed by the plain conv (conv2 <- bn1, conv3 <- bn2 shapes)
+        if not (ops.fprop_bnact_ok(c) and ((r == 3) or (r == 1 and k == 4 * c and stride == 1))):
+            continue
+        g1, b1 = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+        rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        st = ops.bn_stats(x)
+        bn = (st, g1, b1, rm, rv)
+        fns = {"fprop": fns["fprop"],
+               "bn_apply": lambda: ops.bn_finalize_apply(x, bn, act=ops.ACT_RELU, count=B * h * h),
+               "fused": lambda: ops.conv2d_fprop_bnact(x, w, bn, stride=stride, pad=pad, stats=stats, count=B * h * h)}
+        t = {n: timeit(f) for n, f in fns.items()}
+        for n in t: tot[n] = tot.get(n, 0.0) + t[n] * cnt
+        print("%-24s %3d | fprop %.3f + bn_apply %.3f = %.3f | fused %.3f ms  (%+.3f)" % (
+            str((c, k, h, r, stride)), cnt, t["fprop"], t["bn_apply"], t["fprop"] + t["bn_apply"], t["fused"],
+            t["fused"] - t["fprop"] - t["bn_apply"]))
+        continue
     flops = 2.0 * B * oh * oh * k * c * r * r
     byt = 2.0 * B * (h * h * c + oh * oh * k) + 2.0 * k * c * r * r
     ideal = max(flops / TF, byt / BW) * 1e3
@@ -79,6 +97,9 @@ for (c, k, h, r, stride, pad, cnt) in SHAPES:
         str((c, k, h, r, stride)), cnt, t["fprop"], t["dgrad"], t["wgrad"], ideal,
         flops / t["fprop"] / 1e9, flops / t["dgrad"] / 1e9, flops / t["wgrad"] / 1e9))
     del x, w, wd, y, dy, dw
-if not profile:
+if "--prologue" in sys.argv:
+    print("weighted: fprop %.3f + bn_apply %.3f = %.3f | fused %.3f ms" % (
+        tot["fprop"], tot["bn_apply"], tot["fprop"] + tot["bn_apply"], tot["fused"]))
+elif not profile:
     print("weighted totals (no stem): fprop %.3f dgrad %.3f wgrad %.3f | ideal per pass %.3f ms" % (
         tot["fprop"], tot["dgrad"], tot["wgrad"], ideal_tot))

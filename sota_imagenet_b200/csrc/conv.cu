@@ -145,9 +145,11 @@ __device__ __forceinline__ void igemm_epilogue(
   // same columns, so the per-channel sums are accumulated in this warp's s_part slots for the
   // whole kernel and published once at the end -- no named barrier and no 2*BN atomics per tile.
   const bool cta_sums = p.stats != nullptr && (p.num_n_tiles == 1 || kGroups == 2);
-  if (cta_sums) {
-    for (int i = lane; i < 2 * kPartStride; i += 32) s_part[e * 2 * kPartStride + i] = 0.f;
-    __syncwarp();
+  float2 acc1[kChunksPerWarp][4], acc2[kChunksPerWarp][4];
+#pragma unroll
+  for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc1[ci][j] = make_float2(0.f, 0.f); acc2[ci][j] = make_float2(0.f, 0.f); }
   }
   int acc = group;
   uint32_t acc_phase = 0;
@@ -169,9 +171,14 @@ __device__ __forceinline__ void igemm_epilogue(
       const int chunk = half + ci * kHalves;
       const int col0 = n0 + chunk * 64;
       const bool live = col0 < p.Cout;           // ragged N (warp-uniform)
-      float2 cs1[4], cs2[4];     // packed fp32x2 accumulators (add.f32x2 / fma.f32x2 on sm_100)
+      // packed fp32x2 accumulators (add.f32x2 / fma.f32x2 on sm_100); with cta_sums they run on
+      // across all tiles of the CTA and are reduced across lanes only once, after the tile loop
+      float2 (&cs1)[4] = acc1[ci];
+      float2 (&cs2)[4] = acc2[ci];
+      if (!cta_sums) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { cs1[j] = make_float2(0.f, 0.f); cs2[j] = make_float2(0.f, 0.f); }
+        for (int j = 0; j < 4; ++j) { cs1[j] = make_float2(0.f, 0.f); cs2[j] = make_float2(0.f, 0.f); }
+      }
       if (live) {
         uint8_t* slab = slabs + slab_idx * kSlabBytes;
         // the TMA store that last read this slab must have finished reading it
@@ -232,7 +239,12 @@ __device__ __forceinline__ void igemm_epilogue(
             for (int j = 0; j < 8; ++j) v[g * 8 + j] += prev[j];
           }
         }
-        // bf16 pack into the 128B-swizzled slab
+        // bf16 pack into the 128B-swizzled slab.  Rows past M_total (last m-tile only; the TMA
+        // store clips them) are written as zeros so that the statistics pass needs no row mask.
+        if (rows_valid < 32 && lane >= rows_valid) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = 0.f;
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           *reinterpret_cast<uint4*>(slab + row_slot[g]) = pack8(&v[g * 8]);
@@ -256,12 +268,10 @@ __device__ __forceinline__ void igemm_epilogue(
           const bool do_mask = p.fuse_act != SIB_ACT_NONE;
           const float neg = p.fuse_act == SIB_ACT_LEAKY ? p.fuse_slope : 0.f;
           const uint8_t* xsl = (AUX > 1 && p.fuse == 2) ? aux + kSlabBytes : aux;
-          const bool full = rows_valid >= 32;          // warp-uniform
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const uint32_t off = it * 512 + ((it & 1) ? st_off1 : st_off0);
-            uint4 q = *reinterpret_cast<const uint4*>(slab + off);
-            if (!full && it * 4 + st_row >= rows_valid) q = make_uint4(0, 0, 0, 0);
+            const uint4 q = *reinterpret_cast<const uint4*>(slab + off);   // (rows past M_total hold zeros)
             float g[8], mv[8], xv[8];
             unpack8(q, g);
             unpack8(*reinterpret_cast<const uint4*>(aux + off), mv);
@@ -286,11 +296,9 @@ __device__ __forceinline__ void igemm_epilogue(
         } else if (p.stats != nullptr) {
           __syncwarp();
           // column sums of the bf16 values as stored: 8 x LDS.128 cover the 32 x 64 slab
-          const bool full = rows_valid >= 32;          // warp-uniform
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            uint4 q = *reinterpret_cast<const uint4*>(slab + it * 512 + ((it & 1) ? st_off1 : st_off0));
-            if (!full && it * 4 + st_row >= rows_valid) q = make_uint4(0, 0, 0, 0);
+            const uint4 q = *reinterpret_cast<const uint4*>(slab + it * 512 + ((it & 1) ? st_off1 : st_off0));
             const __nv_bfloat162* hq = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -309,7 +317,7 @@ __device__ __forceinline__ void igemm_epilogue(
         }
         if (SLABS > 1) slab_idx ^= 1;
       }
-      if (p.stats != nullptr) {
+      if (p.stats != nullptr && !cta_sums) {
         // lanes with equal lane%8 hold partial sums of the same 8 columns (different rows)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -331,13 +339,6 @@ __device__ __forceinline__ void igemm_epilogue(
           float4 a1 = make_float4(cs1[2].x, cs1[2].y, cs1[3].x, cs1[3].y);
           float4 b0 = make_float4(cs2[0].x, cs2[0].y, cs2[1].x, cs2[1].y);
           float4 b1 = make_float4(cs2[2].x, cs2[2].y, cs2[3].x, cs2[3].y);
-          if (cta_sums) {     // running totals of this warp (its own slots: no other writer)
-            const float4 p0 = d1[0], p1 = d1[1], q0 = d2[0], q1 = d2[1];
-            a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
-            a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
-            b0.x += q0.x; b0.y += q0.y; b0.z += q0.z; b0.w += q0.w;
-            b1.x += q1.x; b1.y += q1.y; b1.z += q1.z; b1.w += q1.w;
-          }
           d1[0] = a0; d1[1] = a1; d2[0] = b0; d2[1] = b1;
         }
       }
@@ -378,6 +379,31 @@ __device__ __forceinline__ void igemm_epilogue(
     }
   }
   if (cta_sums) {
+    // one cross-lane reduction per CTA: this warp's totals -> its s_part slots
+#pragma unroll
+    for (int ci = 0; ci < kChunksPerWarp; ++ci) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          float2 t1, t2;
+          t1.x = __shfl_xor_sync(0xffffffffu, acc1[ci][j].x, o);
+          t1.y = __shfl_xor_sync(0xffffffffu, acc1[ci][j].y, o);
+          t2.x = __shfl_xor_sync(0xffffffffu, acc2[ci][j].x, o);
+          t2.y = __shfl_xor_sync(0xffffffffu, acc2[ci][j].y, o);
+          acc1[ci][j] = __fadd2_rn(acc1[ci][j], t1);
+          acc2[ci][j] = __fadd2_rn(acc2[ci][j], t2);
+        }
+      }
+      if (lane < 8) {
+        float4* d1 = reinterpret_cast<float4*>(&s_part[(e * 2 + 0) * kPartStride + ci * 64 + lane * 8]);
+        float4* d2 = reinterpret_cast<float4*>(&s_part[(e * 2 + 1) * kPartStride + ci * 64 + lane * 8]);
+        d1[0] = make_float4(acc1[ci][0].x, acc1[ci][0].y, acc1[ci][1].x, acc1[ci][1].y);
+        d1[1] = make_float4(acc1[ci][2].x, acc1[ci][2].y, acc1[ci][3].x, acc1[ci][3].y);
+        d2[0] = make_float4(acc2[ci][0].x, acc2[ci][0].y, acc2[ci][1].x, acc2[ci][1].y);
+        d2[1] = make_float4(acc2[ci][2].x, acc2[ci][2].y, acc2[ci][3].x, acc2[ci][3].y);
+      }
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     for (int idx = et; idx < BN / 2; idx += 32 * kEpiWarps) {
       const int kind = idx / (BN / 4), c = (idx - kind * (BN / 4)) * 4;
@@ -541,24 +567,53 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         const int tr = tap / p.S;
         const int ts = tap - tr * p.S;
+        uint32_t inside = 0xffu;      // bit i: row i of this thread is a real pixel for this tap
+        if (!p.tiled_a) {
+          inside = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            inside |= ((unsigned)(bh[i] + tr) < (unsigned)pro.IH && (unsigned)(bw[i] + ts) < (unsigned)pro.IW)
+                          ? (1u << i) : 0u;
+        }
         mbar_wait(&full_bar[stage], phase);
         uint8_t* base = smem_a + stage * kABytes + off0;
+        // all eight loads first (independent), then the arithmetic: one exposed LDS latency
+        uint4 raw[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4* q = reinterpret_cast<uint4*>(base + i * 2048);
-          bool inside = true;
-          if (!p.tiled_a)
-            inside = (unsigned)(bh[i] + tr) < (unsigned)pro.IH && (unsigned)(bw[i] + ts) < (unsigned)pro.IW;
-          float f[8];
-          unpack8(*q, f);
+        for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint4*>(base + i * 2048);
+        if (act == SIB_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v = fmaf(f[j], sc[j], sh[j]);
-            if (act == SIB_ACT_RELU) v = fmaxf(v, 0.f);
-            else if (act == SIB_ACT_LEAKY) v = v > 0.f ? v : v * slope;
-            f[j] = inside ? v : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw[i]);
+            uint4 o;
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x2 = make_float2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xffff0000u));
+              const float2 v = __ffma2_rn(x2, make_float2(sc[2 * j], sc[2 * j + 1]),
+                                          make_float2(sh[2 * j], sh[2 * j + 1]));
+              ow[j] = pack2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+            }
+            if (!((inside >> i) & 1u)) o = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(base + i * 2048) = o;
           }
-          *q = pack8(f);
+        } else {
+          const float neg = act == SIB_ACT_LEAKY ? slope : 1.f;     // identity: v * 1
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(&raw[i]);
+            uint4 o;
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x2 = make_float2(__uint_as_float(rw[j] << 16), __uint_as_float(rw[j] & 0xffff0000u));
+              const float2 v = __ffma2_rn(x2, make_float2(sc[2 * j], sc[2 * j + 1]),
+                                          make_float2(sh[2 * j], sh[2 * j + 1]));
+              ow[j] = pack2(v.x > 0.f ? v.x : v.x * neg, v.y > 0.f ? v.y : v.y * neg);
+            }
+            if (!((inside >> i) & 1u)) o = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(base + i * 2048) = o;
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();

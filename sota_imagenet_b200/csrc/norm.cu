@@ -370,7 +370,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   column_reduce_store<NACC>(co, C, acc, sums);
 }
 
-template <bool SECOND, bool USE_OUT, bool WRITE_G>
+//   EMIT_A: also rewrite the forward activation a = fwd_act(fmaf(x, scale, shift)) of this BatchNorm
+//   (x is in registers anyway): the fused conv prologue never stored it and the weight gradient
+//   of the consumer conv needs it.  +2 B/element written, no extra read.
+template <bool SECOND, bool USE_OUT, bool WRITE_G, bool EMIT_A = false>
 __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ out,
                     const float* __restrict__ mask_ss, const __nv_bfloat16* __restrict__ x,
@@ -381,7 +384,8 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     __nv_bfloat16* __restrict__ gout, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ dgamma2,
                     float* __restrict__ dbeta2, long M, int C, float inv_count, int act,
-                    float slope) {
+                    float slope, const float* __restrict__ emit_ss = nullptr, int emit_act = 0,
+                    float emit_slope = 0.f, __nv_bfloat16* __restrict__ a_out = nullptr) {
   griddep_launch();
   griddep_wait();
   const ColOwner co(C);
@@ -434,6 +438,11 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     load8f(mask_ss + co.tx * 8, sc);
     load8f(mask_ss + C + co.tx * 8, sh);
   }
+  float esc[8], esh[8];
+  if (EMIT_A) {
+    load8f(emit_ss + co.tx * 8, esc);
+    load8f(emit_ss + C + co.tx * 8, esh);
+  }
   const long col = co.tx * 8;
   for (long r = co.row0; r < M; r += kU * co.stride) {
     uint4 vg[kU], vx[kU], vo[kU], vw[kU];
@@ -474,6 +483,12 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
           stg_stream(dx2 + rr * C + col, pack8(d));
         }
         if (WRITE_G) stg_stream(gout + rr * C + col, pack8(g));
+        if (EMIT_A) {
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = act_fwd(fmaf(xv[j], esc[j], esh[j]), emit_act, emit_slope);
+          stg_stream(a_out + rr * C + col, pack8(a));
+        }
       }
     }
   }
@@ -925,7 +940,8 @@ extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* ma
 #define SIB_APP(S, O, G)                                                                       \
   SIB_CUDA(launch_pdl(bn_bwd_apply_kernel<S, O, G>, dim3(grid), dim3(kRedThreads), 0, ST(stream), \
       a, o, mask_ss, xp, mean_invstd, gamma, sums, xq, mean_invstd2, gamma2, d1, d2, gg, dgamma,   \
-      dbeta, dgamma2, dbeta2, M, C, ic, act, slope))
+      dbeta, dgamma2, dbeta2, M, C, ic, act, slope, static_cast<const float*>(nullptr), 0, 0.f,     \
+      static_cast<__nv_bfloat16*>(nullptr)))
   const bool use_out = out != nullptr && act != SIB_ACT_NONE;
   const bool wg = gout != nullptr;
   if (x2) {
@@ -936,6 +952,32 @@ extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* ma
     else         { if (wg) SIB_APP(false, false, true); else SIB_APP(false, false, false); }
   }
 #undef SIB_APP
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// bn_bwd_apply of a plain BatchNorm (+ activation) that also re-materialises the forward
+// activation a = fwd_act(fmaf(x, act_ss)) for the consumer conv's weight gradient.
+extern "C" int sib_bn_bwd_apply_remat(const void* dy, const float* mask_ss, const void* x,
+                                      const float* mean_invstd, const float* gamma,
+                                      const float* sums, void* dx, float* dgamma, float* dbeta,
+                                      const float* act_ss, int fwd_act, float fwd_slope, void* a_out,
+                                      long M, int C, double count, int act, float slope,
+                                      void* stream) {
+  if (int rc = check_c(C)) return rc;
+  SIB_CHECK(act == SIB_ACT_NONE || mask_ss != nullptr, "bn_bwd_apply_remat: activation mask needs `mask_ss`");
+  SIB_CHECK(act_ss != nullptr && a_out != nullptr, "bn_bwd_apply_remat: act_ss and a_out are required");
+  const int grid = bn_grid(M, C);
+  SIB_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false, false, true>, dim3(grid), dim3(kRedThreads), 0,
+                      ST(stream), static_cast<const __nv_bfloat16*>(dy),
+                      static_cast<const __nv_bfloat16*>(nullptr), mask_ss,
+                      static_cast<const __nv_bfloat16*>(x), mean_invstd, gamma, sums,
+                      static_cast<const __nv_bfloat16*>(nullptr), static_cast<const float*>(nullptr),
+                      static_cast<const float*>(nullptr), static_cast<__nv_bfloat16*>(dx),
+                      static_cast<__nv_bfloat16*>(nullptr), static_cast<__nv_bfloat16*>(nullptr), dgamma,
+                      dbeta, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, C,
+                      (float)(1.0 / count), act, slope, act_ss, fwd_act, fwd_slope,
+                      static_cast<__nv_bfloat16*>(a_out)));
   SIB_LAUNCH_CHECK();
   return 0;
 }

@@ -27,6 +27,24 @@ FUSE_BN_BWD = os.environ.get("SIB_FUSE_BN_BWD", "1") != "0"
 # 3x3 / stride-2 dgrad by row parity (csrc/conv.cu dgrad_s2_impl); 0 = zero-inserted dy
 FUSE_BN_BWD_ALL = os.environ.get("SIB_FUSE_BN_BWD_ALL", "0") == "1"   # A/B: fuse even where it loses
 DGRAD_S2 = os.environ.get("SIB_DGRAD_S2", "1") != "0"
+# BatchNorm + activation applied inside the CONSUMER conv's operand prologue (csrc/conv.cu
+# BnPrologue): the normalised activation is not stored in forward; backward re-materialises it
+# inside bn_bwd_apply for the weight gradient.  0 = off (separate bn_finalize_apply pass),
+# 1 = where it wins (measured per layer on B200, profiles/r02_prologue_fusion_layers.log):
+# conv3 <- bn2 (1x1) up to 256 input channels and the stride-2 conv2 <- bn1 (the separate pass
+# would run over the 4x larger input) up to 256; 2 = 1 + every conv3, 3 = everything that fits
+# (3x3 stride-1 loses: its transform runs once per filter tap on the im2col kernel).
+FUSE_BN_FWD = int(os.environ.get("SIB_FUSE_BN_FWD", "1"))
+
+
+def _fuse_fwd(kind, planes, stride):
+    if FUSE_BN_FWD <= 0 or not ops.fprop_bnact_ok(planes):
+        return False
+    if FUSE_BN_FWD >= 3:
+        return True
+    if kind == "conv3":
+        return planes <= 256 or FUSE_BN_FWD >= 2
+    return stride == 2 and planes <= 256
 
 
 # --------------------------------------------------------------------------- autograd glue
@@ -441,12 +459,40 @@ class Bottleneck(SibModule):
                                                       count=count * world, eps=bn.eps, momentum=bn.momentum)
         return y, mi, ss, count * world, mi2
 
+    @staticmethod
+    def _conv_bnact(conv, bn, c, stats_c, train):
+        """conv(act(bn(c))) with the BatchNorm applied in the conv's operand prologue.
+        -> y, stats(y), mean_invstd, scale_shift, count (of bn)."""
+        n, _, h, w = c.shape
+        count = n * h * w
+        w16 = conv._w16(conv.weight)
+        if not train:
+            ss = ops.bn_eval_scale(bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps)
+            y, _, _ = ops.conv2d_fprop_bnact(c, w16, None, conv.stride, conv.padding, act=bn.act,
+                                             slope=bn.slope, scale_shift=ss)
+            return y, None, None, ss, count
+        args, world = bn.stats_args(stats_c)
+        st = ops.new_acc(2, conv.out_channels, c.device)
+        y, mi, ss = ops.conv2d_fprop_bnact(c, w16, args, conv.stride, conv.padding, stats=st, act=bn.act,
+                                           slope=bn.slope, count=count * world, eps=bn.eps,
+                                           momentum=bn.momentum)
+        return y, st, mi, ss, count * world
+
     def fwd(self, x, train):
         c1, st1 = self._conv(self.conv1, x, train)
-        a1, mi1, ss1, cnt1, _ = self._bn_act(self.bn1, c1, st1, train)
-        c2, st2 = self._conv(self.conv2, a1, train)
-        a2, mi2, ss2, cnt2, _ = self._bn_act(self.bn2, c2, st2, train)
-        c3, st3 = self._conv(self.conv3, a2, train)
+        planes = self.conv2.in_channels
+        if _fuse_fwd("conv2", planes, self.stride):
+            a1 = None
+            c2, st2, mi1, ss1, cnt1 = self._conv_bnact(self.conv2, self.bn1, c1, st1, train)
+        else:
+            a1, mi1, ss1, cnt1, _ = self._bn_act(self.bn1, c1, st1, train)
+            c2, st2 = self._conv(self.conv2, a1, train)
+        if _fuse_fwd("conv3", planes, self.stride):
+            a2 = None
+            c3, st3, mi2, ss2, cnt2 = self._conv_bnact(self.conv3, self.bn2, c2, st2, train)
+        else:
+            a2, mi2, ss2, cnt2, _ = self._bn_act(self.bn2, c2, st2, train)
+            c3, st3 = self._conv(self.conv3, a2, train)
         if self.downsample is not None:
             cd, std = self._conv(self.downsample[0], x, train)
             out, mi3, _, cnt3, mid = self._bn_act(self.bn3, c3, st3, train, res=cd, bn2=self.downsample[1],
@@ -500,35 +546,51 @@ class Bottleneck(SibModule):
                                            bn3.slope, want_g=need_dx, param_grads=bn3.grad_ptrs())
         # ---- conv3, bn2 + act ----
         # (activation mask recomputed from c2 and the forward scale/shift: a2 is not re-read)
-        self.conv3.run_wgrad(a2, dc3)
+        # a2 / a1 are None when the forward applied the BatchNorm inside the consumer conv's
+        # prologue: bn_bwd_apply then re-materialises them and the weight gradient follows it
+        if a2 is not None:
+            self.conv3.run_wgrad(a2, dc3)
         if FUSE_BN_BWD:
-            da2, sums = self.conv3.run_dgrad(dc3, tuple(a2.shape), bn_bwd=dict(
+            da2, sums = self.conv3.run_dgrad(dc3, tuple(c2.shape), bn_bwd=dict(
                 mask_src=c2, mask_ss=ss2, mean_invstd=mi2, act=bn2.act, slope=bn2.slope))
-            dc2, _, _ = ops.bn_bwd_apply(da2, None, c2, mi2, bn2.weight.data, bn2.reduce_sums(sums), cnt2,
-                                         none, 0.0, param_grads=bn2.grad_ptrs())
+            sums, mask = bn2.reduce_sums(sums), (none, 0.0, None)
         else:
-            da2 = self.conv3.run_dgrad(dc3, tuple(a2.shape))
+            da2 = self.conv3.run_dgrad(dc3, tuple(c2.shape))
             sums = bn2.reduce_sums(ops.bn_bwd_reduce(da2, None, c2, mi2, bn2.act, bn2.slope, mask_ss=ss2))
-            dc2, _, _ = ops.bn_bwd_apply(da2, None, c2, mi2, bn2.weight.data, sums, cnt2, bn2.act,
-                                         bn2.slope, mask_ss=ss2, param_grads=bn2.grad_ptrs())
+            mask = (bn2.act, bn2.slope, ss2)
+        if a2 is not None:
+            dc2, _, _ = ops.bn_bwd_apply(da2, None, c2, mi2, bn2.weight.data, sums, cnt2, mask[0], mask[1],
+                                         mask_ss=mask[2], param_grads=bn2.grad_ptrs())
+        else:
+            dc2, a2 = ops.bn_bwd_apply_remat(da2, c2, mi2, bn2.weight.data, sums, cnt2, ss2, bn2.act, bn2.slope,
+                                             act=mask[0], slope=mask[1], mask_ss=mask[2],
+                                             param_grads=bn2.grad_ptrs())
+            self.conv3.run_wgrad(a2, dc3)
         # ---- conv2, bn1 + act ----
-        self.conv2.run_wgrad(a1, dc2)
+        if a1 is not None:
+            self.conv2.run_wgrad(a1, dc2)
         # Measured (B200, batch 256): the fused reduction LOSES where conv2's dgrad runs on the
         # halo-reuse kernel (64 -> 64 at 56x56: 0.172 ms fused vs 0.062 + 0.045 ms separate; its
         # epilogue reads the BN input with exposed global loads) and on the row-parity stride-2
         # path (0.195 vs 0.097 + 0.078 ms); everywhere else it wins or is neutral.
-        fuse1 = FUSE_BN_BWD and (FUSE_BN_BWD_ALL or self.stride == 1) and not (not FUSE_BN_BWD_ALL and ops.halo_applies(a1.shape[1], dc2.shape[1], 3, 1,
-                                                                                                    a1.shape[3]))
+        fuse1 = FUSE_BN_BWD and (FUSE_BN_BWD_ALL or self.stride == 1) and not (not FUSE_BN_BWD_ALL and ops.halo_applies(c1.shape[1], dc2.shape[1], 3, 1,
+                                                                                                    c1.shape[3]))
         if fuse1:
-            da1, sums = self.conv2.run_dgrad(dc2, tuple(a1.shape), bn_bwd=dict(
+            da1, sums = self.conv2.run_dgrad(dc2, tuple(c1.shape), bn_bwd=dict(
                 mask_src=c1, mask_ss=ss1, mean_invstd=mi1, act=bn1.act, slope=bn1.slope))
-            dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, bn1.reduce_sums(sums), cnt1,
-                                         none, 0.0, param_grads=bn1.grad_ptrs())
+            sums, mask = bn1.reduce_sums(sums), (none, 0.0, None)
         else:
-            da1 = self.conv2.run_dgrad(dc2, tuple(a1.shape))
+            da1 = self.conv2.run_dgrad(dc2, tuple(c1.shape))
             sums = bn1.reduce_sums(ops.bn_bwd_reduce(da1, None, c1, mi1, bn1.act, bn1.slope, mask_ss=ss1))
-            dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, sums, cnt1, bn1.act,
-                                         bn1.slope, mask_ss=ss1, param_grads=bn1.grad_ptrs())
+            mask = (bn1.act, bn1.slope, ss1)
+        if a1 is not None:
+            dc1, _, _ = ops.bn_bwd_apply(da1, None, c1, mi1, bn1.weight.data, sums, cnt1, mask[0], mask[1],
+                                         mask_ss=mask[2], param_grads=bn1.grad_ptrs())
+        else:
+            dc1, a1 = ops.bn_bwd_apply_remat(da1, c1, mi1, bn1.weight.data, sums, cnt1, ss1, bn1.act, bn1.slope,
+                                             act=mask[0], slope=mask[1], mask_ss=mask[2],
+                                             param_grads=bn1.grad_ptrs())
+            self.conv2.run_wgrad(a1, dc2)
         # ---- conv1 (+ shortcut) ----
         self.conv1.run_wgrad(x, dc1)
         if self.downsample is not None:

@@ -422,6 +422,20 @@ def bn_bwd_apply(dy, out, x, mean_invstd, gamma, sums, count, act, slope=0.01, x
     return dx, dx2, g
 
 
+def bn_bwd_apply_remat(dy, x, mean_invstd, gamma, sums, count, act_ss, fwd_act, fwd_slope=0.01,
+                       act=ACT_NONE, slope=0.01, mask_ss=None, param_grads=(None, None)):
+    """bn_bwd_apply of a plain BatchNorm (+ activation) that also re-materialises the forward
+    activation a = fwd_act(fmaf(x, scale, shift)) (the fused conv prologue never stored it; the
+    consumer conv's weight gradient reads it).  Returns dx, a."""
+    n, c, h, w = x.shape
+    dx = new_act(n, c, h, w, x.device)
+    a = new_act(n, c, h, w, x.device)
+    call("sib_bn_bwd_apply_remat", _p(dy), _p(mask_ss), _p(x), _p(mean_invstd), _p(gamma), _p(sums),
+         _p(dx), _p(param_grads[0]), _p(param_grads[1]), _p(act_ss), fwd_act, float(fwd_slope), _p(a),
+         n * h * w, c, float(count), act, float(slope), _stream())
+    return dx, a
+
+
 def bn_param_grad(sums, dgamma, dbeta, accumulate=True):
     c = sums.shape[1]
     call("sib_bn_param_grad", _p(sums), _p(dgamma), _p(dbeta), c, int(accumulate), _stream())
