@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SIB_ABI_VERSION 1
+#define SIB_ABI_VERSION 2
 
 /* activation codes (pytorch_tools ABN `activation=`; BResNet50_encoder.yaml:49 leaky_relu) */
 #define SIB_ACT_NONE 0
@@ -138,11 +138,16 @@ int sib_bn_finalize_apply(const void* x, const float* stats, const float* gamma,
 int sib_bn_bwd_reduce(const void* dy, const void* out, const float* mask_ss, const void* x,
                       const float* mean_invstd, const void* x2, const float* mean_invstd2, long M,
                       int C, int act, float slope, float* sums, void* stream);
+/* dx = BN backward (dx2 for a second BN sharing g); dgamma / dbeta (optional) += sums * pgrad_scale.
+ * pgrad_scale = 1 normally; 1 / world under SyncBN, where `sums` hold totals over ALL ranks and the
+ * data-parallel wrapper averages parameter gradients over the ranks afterwards (torch's SyncBatchNorm
+ * uses the rank-local sums for the same reason, torch/nn/modules/_functions.py:150-160). */
 int sib_bn_bwd_apply(const void* dy, const void* out, const float* mask_ss, const void* x,
                      const float* mean_invstd, const float* gamma, const float* sums,
                      const void* x2, const float* mean_invstd2, const float* gamma2, void* dx,
                      void* dx2, void* gout, float* dgamma, float* dbeta, float* dgamma2,
-                     float* dbeta2, long M, int C, double count, int act, float slope, void* stream);
+                     float* dbeta2, long M, int C, double count, int act, float slope,
+                     float pgrad_scale, void* stream);
 /* sib_bn_bwd_apply for a plain BatchNorm (+ activation) that ALSO re-materialises the forward
  * activation a_out = fwd_act(x * act_ss.scale + act_ss.shift): with the fused conv prologue
  * (sib_conv2d_fprop_bnact) the activation is never stored in forward, and the weight gradient of
@@ -151,7 +156,7 @@ int sib_bn_bwd_apply_remat(const void* dy, const float* mask_ss, const void* x,
                            const float* mean_invstd, const float* gamma, const float* sums, void* dx,
                            float* dgamma, float* dbeta, const float* act_ss, int fwd_act,
                            float fwd_slope, void* a_out, long M, int C, double count, int act,
-                           float slope, void* stream);
+                           float slope, float pgrad_scale, void* stream);
 
 /* (dgamma/dbeta[/2], optional: the affine-parameter gradients are ACCUMULATED into them) */
 int sib_bn_param_grad(const float* sums, float* dgamma, float* dbeta, int C, int accumulate,

@@ -58,7 +58,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sib_abi_version() != 1:
+    if lib.sib_abi_version() != 2:
         raise RuntimeError("libsib200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -148,8 +148,9 @@ class PaddedBatchNorm2d(BatchNorm2d):
         sums = self.reduce_sums(ops.bn_bwd_reduce(dy, None, x, mi, self.act, self.slope, mask_ss=ss))
         gamma = self._padded(self.weight.data, 1.0)
         dx, _, _ = ops.bn_bwd_apply(dy, None, x, mi, gamma, sums, count, self.act, self.slope, mask_ss=ss)
-        self._grad(self.bias).add_(sums[0, :self.num_features])
-        self._grad(self.weight).add_(sums[1, :self.num_features])
+        pg = 1.0 / self._world()          # sums are totals over all ranks under SyncBN (see grad_ptrs)
+        self._grad(self.bias).add_(sums[0, :self.num_features], alpha=pg)
+        self._grad(self.weight).add_(sums[1, :self.num_features], alpha=pg)
         return dx
 
 

@@ -384,22 +384,25 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     __nv_bfloat16* __restrict__ gout, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ dgamma2,
                     float* __restrict__ dbeta2, long M, int C, float inv_count, int act,
-                    float slope, const float* __restrict__ emit_ss = nullptr, int emit_act = 0,
-                    float emit_slope = 0.f, __nv_bfloat16* __restrict__ a_out = nullptr) {
+                    float slope, float pg_scale, const float* __restrict__ emit_ss = nullptr,
+                    int emit_act = 0, float emit_slope = 0.f,
+                    __nv_bfloat16* __restrict__ a_out = nullptr) {
   griddep_launch();
   griddep_wait();
   const ColOwner co(C);
   if (!co.active) return;
   if (blockIdx.x == 0 && co.ty == 0) {
-    // parameter gradients ride along: dbeta += sum g, dgamma += sum g*xhat (one writer per channel)
+    // parameter gradients ride along: dbeta += sum g, dgamma += sum g*xhat (one writer per channel).
+    // pg_scale = 1 / world under SyncBN: `sums` are then totals over ALL ranks, while the
+    // data-parallel wrapper averages parameter gradients over the ranks afterwards.
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = co.tx * 8 + j;
-      if (dbeta) dbeta[c] += sums[c];
-      if (dgamma) dgamma[c] += sums[C + c];
+      if (dbeta) dbeta[c] += sums[c] * pg_scale;
+      if (dgamma) dgamma[c] += sums[C + c] * pg_scale;
       if (SECOND) {
-        if (dbeta2) dbeta2[c] += sums[2 * C + c];
-        if (dgamma2) dgamma2[c] += sums[3 * C + c];
+        if (dbeta2) dbeta2[c] += sums[2 * C + c] * pg_scale;
+        if (dgamma2) dgamma2[c] += sums[3 * C + c] * pg_scale;
       }
     }
   }
@@ -924,7 +927,8 @@ extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* ma
                                 const float* sums, const void* x2, const float* mean_invstd2,
                                 const float* gamma2, void* dx, void* dx2, void* gout,
                                 float* dgamma, float* dbeta, float* dgamma2, float* dbeta2, long M,
-                                int C, double count, int act, float slope, void* stream) {
+                                int C, double count, int act, float slope, float pgrad_scale,
+                                void* stream) {
   if (int rc = check_c(C)) return rc;
   SIB_CHECK(act == SIB_ACT_NONE || out != nullptr || mask_ss != nullptr,
             "bn_bwd_apply: activation mask needs `out` or `mask_ss`");
@@ -940,7 +944,7 @@ extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* ma
 #define SIB_APP(S, O, G)                                                                       \
   SIB_CUDA(launch_pdl(bn_bwd_apply_kernel<S, O, G>, dim3(grid), dim3(kRedThreads), 0, ST(stream), \
       a, o, mask_ss, xp, mean_invstd, gamma, sums, xq, mean_invstd2, gamma2, d1, d2, gg, dgamma,   \
-      dbeta, dgamma2, dbeta2, M, C, ic, act, slope, static_cast<const float*>(nullptr), 0, 0.f,     \
+      dbeta, dgamma2, dbeta2, M, C, ic, act, slope, pgrad_scale, static_cast<const float*>(nullptr), 0, 0.f, \
       static_cast<__nv_bfloat16*>(nullptr)))
   const bool use_out = out != nullptr && act != SIB_ACT_NONE;
   const bool wg = gout != nullptr;
@@ -963,7 +967,7 @@ extern "C" int sib_bn_bwd_apply_remat(const void* dy, const float* mask_ss, cons
                                       const float* sums, void* dx, float* dgamma, float* dbeta,
                                       const float* act_ss, int fwd_act, float fwd_slope, void* a_out,
                                       long M, int C, double count, int act, float slope,
-                                      void* stream) {
+                                      float pgrad_scale, void* stream) {
   if (int rc = check_c(C)) return rc;
   SIB_CHECK(act == SIB_ACT_NONE || mask_ss != nullptr, "bn_bwd_apply_remat: activation mask needs `mask_ss`");
   SIB_CHECK(act_ss != nullptr && a_out != nullptr, "bn_bwd_apply_remat: act_ss and a_out are required");
@@ -976,7 +980,7 @@ extern "C" int sib_bn_bwd_apply_remat(const void* dy, const float* mask_ss, cons
                       static_cast<const float*>(nullptr), static_cast<__nv_bfloat16*>(dx),
                       static_cast<__nv_bfloat16*>(nullptr), static_cast<__nv_bfloat16*>(nullptr), dgamma,
                       dbeta, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, C,
-                      (float)(1.0 / count), act, slope, act_ss, fwd_act, fwd_slope,
+                      (float)(1.0 / count), act, slope, pgrad_scale, act_ss, fwd_act, fwd_slope,
                       static_cast<__nv_bfloat16*>(a_out)));
   SIB_LAUNCH_CHECK();
   return 0;

@@ -320,8 +320,11 @@ class BatchNorm2d(SibModule):
         return sums
 
     def grad_ptrs(self):
-        """(dgamma, dbeta) arena views: bn_bwd_apply accumulates the parameter gradients itself."""
-        return self._grad(self.weight), self._grad(self.bias)
+        """(dgamma, dbeta, scale) for bn_bwd_apply, which accumulates the parameter gradients itself.
+        Under SyncBN the backward sums are totals over ALL ranks while DataParallel averages the
+        parameter gradients over the ranks afterwards, hence scale = 1 / world (torch's SyncBatchNorm
+        takes the rank-local sums for the same reason)."""
+        return self._grad(self.weight), self._grad(self.bias), 1.0 / self._world()
 
     # standalone use: stats pass + apply
     def fwd(self, x, train, res=None):

@@ -410,29 +410,33 @@ def bn_bwd_reduce(dy, out, x, mean_invstd, act, slope=0.01, x2=None, mean_invstd
 
 def bn_bwd_apply(dy, out, x, mean_invstd, gamma, sums, count, act, slope=0.01, x2=None,
                  mean_invstd2=None, gamma2=None, want_g=False, dx_out=None, mask_ss=None,
-                 param_grads=(None, None), param_grads2=(None, None)):
+                 param_grads=(None, None), param_grads2=(None, None), pgrad_scale=1.0):
     n, c, h, w = x.shape
+    if len(param_grads) > 2:          # (dgamma, dbeta, scale) from BatchNorm2d.grad_ptrs()
+        pgrad_scale = param_grads[2]
     dx = dx_out if dx_out is not None else new_act(n, c, h, w, x.device)
     dx2 = new_act(n, c, h, w, x.device) if x2 is not None else None
     g = new_act(n, c, h, w, x.device) if want_g else None
     call("sib_bn_bwd_apply", _p(dy), _p(out), _p(mask_ss), _p(x), _p(mean_invstd), _p(gamma),
          _p(sums), _p(x2), _p(mean_invstd2), _p(gamma2), _p(dx), _p(dx2), _p(g),
          _p(param_grads[0]), _p(param_grads[1]), _p(param_grads2[0]), _p(param_grads2[1]),
-         n * h * w, c, float(count), act, float(slope), _stream())
+         n * h * w, c, float(count), act, float(slope), float(pgrad_scale), _stream())
     return dx, dx2, g
 
 
 def bn_bwd_apply_remat(dy, x, mean_invstd, gamma, sums, count, act_ss, fwd_act, fwd_slope=0.01,
-                       act=ACT_NONE, slope=0.01, mask_ss=None, param_grads=(None, None)):
+                       act=ACT_NONE, slope=0.01, mask_ss=None, param_grads=(None, None), pgrad_scale=1.0):
     """bn_bwd_apply of a plain BatchNorm (+ activation) that also re-materialises the forward
     activation a = fwd_act(fmaf(x, scale, shift)) (the fused conv prologue never stored it; the
     consumer conv's weight gradient reads it).  Returns dx, a."""
     n, c, h, w = x.shape
+    if len(param_grads) > 2:
+        pgrad_scale = param_grads[2]
     dx = new_act(n, c, h, w, x.device)
     a = new_act(n, c, h, w, x.device)
     call("sib_bn_bwd_apply_remat", _p(dy), _p(mask_ss), _p(x), _p(mean_invstd), _p(gamma), _p(sums),
          _p(dx), _p(param_grads[0]), _p(param_grads[1]), _p(act_ss), fwd_act, float(fwd_slope), _p(a),
-         n * h * w, c, float(count), act, float(slope), _stream())
+         n * h * w, c, float(count), act, float(slope), float(pgrad_scale), _stream())
     return dx, a
 
 

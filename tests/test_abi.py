@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     assert set(protos) <= exported
-    assert lib.sib_abi_version() == 1
+    assert lib.sib_abi_version() == 2
 
 
 def test_library_contains_blackwell_kernels():

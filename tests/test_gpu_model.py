@@ -84,6 +84,59 @@ def test_one_step_loss_and_late_grads(batch, size):
             assert err < 2e-2, (name, float(err))
 
 
+def test_every_parameter_gradient_in_a_damped_regime():
+    """In-situ wiring of ALL 161 parameter gradients.  At random init the network is chaotic (see
+    above), which hides a mis-wired gradient behind "bf16 noise".  With every residual branch
+    scaled down (bn3.weight = 0.1: the common small-gamma / zero-init-residual regime) a
+    perturbation no longer grows from block to block, so every parameter can be held to a strict
+    gate: cosine >= 0.999 and gradient-norm ratio within 1% against the bf16-faithful oracle of
+    the whole network, and cosine >= 0.99 / norm within 3% against PURE fp32 torchvision (bf16
+    storage flips ~0.15% of the ReLU masks per layer, which alone costs 0.997 on a single
+    block, tests/test_gpu_blocks.py)."""
+    import copy
+    from sota_imagenet_b200 import losses
+    ref, net = _build_pair()
+    with torch.no_grad():
+        for name, p in ref.named_parameters():
+            if name.endswith("bn3.weight"):
+                p.fill_(0.1)
+            elif name.endswith(".weight") and p.dim() == 1:
+                p.uniform_(0.7, 1.3)           # non-trivial BN scales elsewhere
+            elif name.endswith(".bias") and "bn" in name:
+                p.normal_(0, 0.1)
+    net.load_state_dict(ref.state_dict())
+    x, y = torch_ref.synthetic_batch(16, 128, seed=4)
+    ref = ref.cuda().train()
+    faith = copy.deepcopy(ref)
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        loss_ref = torch_ref.smooth_cross_entropy(ref(x.cuda()), y.cuda(), 0.1)
+        loss_ref.backward()
+        loss_f = torch_ref.smooth_cross_entropy(torch_ref.bf16_faithful_forward(faith, x.cuda()), y.cuda(), 0.1)
+        loss_f.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    net.train()
+    loss = losses.CrossEntropyLoss(smoothing=0.1)(net(x.cuda()), y.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) / loss_ref.item() < 5e-3
+    rp, fp = dict(ref.named_parameters()), dict(faith.named_parameters())
+    rows = []
+    for name, p in net.named_parameters():
+        g = p.grad.detach().float().reshape(rp[name].shape)
+        gf, gr = fp[name].grad, rp[name].grad
+        rows.append((name, _cos(g, gf), float(g.norm() / gf.norm()), _cos(g, gr), float(g.norm() / gr.norm())))
+    assert len(rows) == 161
+    print("worst vs bf16-faithful:", sorted(rows, key=lambda r: r[1])[:3])
+    print("worst norm ratio vs bf16-faithful:", sorted(rows, key=lambda r: -abs(r[2] - 1))[:3])
+    print("worst vs fp32:", [(r[0], r[3], r[4]) for r in sorted(rows, key=lambda r: r[3])[:3]])
+    for name, cf, nf, cr, nr in rows:
+        assert cf >= 0.999 and abs(nf - 1) < 1e-2, (name, cf, nf)
+        assert cr >= 0.99 and abs(nr - 1) < 3e-2, (name, cr, nr)
+
+
 def test_200_step_loss_curve_tracks_oracle():
     """north_star: a 200-step synthetic loss curve that tracks the reference (fixed pool of 64
     images at 64x64, batch 16, SGD-Nesterov lr 0.01, smoothing 0.1).  Trajectories of a chaotic

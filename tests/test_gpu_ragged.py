@@ -1,10 +1,8 @@
 """Ragged-batch kernels (sib_rrc_boxes_ragged / sib_augment_ragged / sib_val_transform_ragged) against
 the numpy oracle and against the uniform kernels.
 
-NOT YET RUN ON HARDWARE: these kernels were written after the round's GPU budget was spent (they
-compile for sm_100a; the host flow around them is covered on CPU by tests/test_records.py).  The
-module is therefore opt-in: SIB_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_ragged.py -m gpu.
-Remove the gate once it has passed on a B200."""
+First run on a B200 in round 2 (profiles/r02_pytest_gpu_ragged.log): both tests pass, the opt-in gate
+is gone."""
 import os
 
 import numpy as np
@@ -14,9 +12,7 @@ import torch
 from oracle import augment_ref
 from sota_imagenet_b200 import ops, records
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SIB_RUN_UNVERIFIED") != "1",
-                                 reason="ragged kernels not yet validated on hardware (opt-in)")]
+pytestmark = pytest.mark.gpu
 
 
 def _batch(shapes, seed=0):

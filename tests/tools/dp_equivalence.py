@@ -1,10 +1,15 @@
-"""Run under torchrun with 2 ranks: DP(2 x B) with SyncBN + bucketed all-reduce must equal one
-process on the concatenated 2B batch (gradients after one step, BN running statistics)."""
+"""Run under torchrun with N ranks (2, 4 or 8): DP(N x B) with SyncBN + bucketed all-reduce must equal
+one process on the concatenated N*B batch -- per parameter: gradient cosine >= 0.999 AND gradient-norm
+ratio within 1 % (a SUM-instead-of-AVG reduction, a missed bucket or unsynchronised statistics all
+fail it), BN running statistics, the loss; plus one Bottleneck under SyncBN against the same block on
+the global batch.  The network runs in the damped regime of tests/test_gpu_model.py
+(bn3.weight = 0.1) so that bf16 summation-order noise is not chaotically amplified and the gates can
+be strict."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch, torch.distributed as dist
 from oracle import torch_ref
-from sota_imagenet_b200 import losses, models, parallel
+from sota_imagenet_b200 import losses, models, modules, ops, parallel
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -13,8 +18,62 @@ dist.init_process_group("nccl", timeout=datetime.timedelta(seconds=120))
 B, S = 8, 128
 x, y = torch_ref.synthetic_batch(B * world, S, seed=5)
 sd = torch_ref.resnet50(seed=0).state_dict()
+g0 = torch.Generator().manual_seed(9)
+for k, v in sd.items():
+    if k.endswith("bn3.weight"):
+        v.fill_(0.1)
+    elif k.endswith(".weight") and v.dim() == 1:
+        v.copy_(torch.rand(v.shape, generator=g0) * 0.6 + 0.7)
 crit = losses.CrossEntropyLoss(smoothing=0.1)
 
+
+def compare(g_dp, named_big):
+    """-> (worst cosine, worst |norm ratio - 1|, name of the worst) over all parameters."""
+    worst_c, worst_n, who = 1.0, 0.0, ""
+    for n, p in named_big:
+        a, b = g_dp[n].double().flatten(), p.grad.double().flatten()
+        c = float(a @ b / (a.norm() * b.norm() + 1e-30))
+        r = abs(float(a.norm() / (b.norm() + 1e-30)) - 1.0)
+        if c < worst_c or r > worst_n:
+            who = n
+        worst_c, worst_n = min(worst_c, c), max(worst_n, r)
+    return worst_c, worst_n, who
+
+
+ok = True
+# ---- one Bottleneck: SyncBN over N ranks == BatchNorm over the global batch -------------------
+torch.manual_seed(3)
+blk_sd = modules.Bottleneck(256, 64).state_dict()
+xb_all = torch.relu(torch.randn(4 * world, 256, 28, 28)).bfloat16()
+dy_all = torch.randn(4 * world, 256, 28, 28).bfloat16()
+blk = modules.Bottleneck(256, 64); blk.load_state_dict(blk_sd); blk = blk.cuda().train()
+dpb = parallel.DataParallel(blk, sync_bn=True)
+xl = ops.to_nhwc_bf16(xb_all[rank * 4:(rank + 1) * 4].cuda()).requires_grad_(True)
+out = dpb(xl)
+# DataParallel averages parameter gradients over ranks: feed dy * world so that the average equals the
+# global-batch gradient of sum(out * dy)
+out.backward(ops.to_nhwc_bf16((dy_all[rank * 4:(rank + 1) * 4].float() * world).cuda()))
+torch.cuda.synchronize()
+gb = {n: p.grad.detach().float().clone() for n, p in blk.named_parameters()}
+rb = {n: b.clone() for n, b in blk.named_buffers() if "running" in n}
+if rank == 0:
+    big = modules.Bottleneck(256, 64); big.load_state_dict(blk_sd); big = big.cuda().train()
+    xa = ops.to_nhwc_bf16(xb_all.cuda()).requires_grad_(True)
+    oa = big(xa)
+    oa.backward(ops.to_nhwc_bf16(dy_all.cuda()))
+    torch.cuda.synchronize()
+    c, r, who = compare(gb, list(big.named_parameters()))
+    o_err = float((out.float() - oa[:4].float()).norm() / oa[:4].float().norm())
+    dx_err = float((xl.grad.float() / world - xa.grad[:4].float()).norm() / xa.grad[:4].float().norm())
+    s_err = max(float((rb[n] - b).norm() / (b.norm() + 1e-12)) for n, b in big.named_buffers() if "running" in n)
+    print("bottleneck SyncBN x%d vs global batch: out err %.2e dx err %.2e | worst grad cosine %.6f, norm dev %.2e (%s) | "
+          "running-stat err %.2e" % (world, o_err, dx_err, c, r, who, s_err))
+    ok = ok and o_err < 5e-3 and dx_err < 1e-2 and c >= 0.999 and r < 1e-2 and s_err < 1e-4
+if ops.PEER is not None:
+    torch.cuda.synchronize(); ops.PEER.reset_layout()
+dist.barrier()
+
+# ---- whole ResNet-50 ---------------------------------------------------------------------------
 net = models.resnet50(); net.load_state_dict(sd); net = net.cuda().train()
 dp = parallel.DataParallel(net, sync_bn=True, bucket_mb=8.0)
 xs, ys = x[rank * B:(rank + 1) * B].cuda(), y[rank * B:(rank + 1) * B].cuda()
@@ -23,30 +82,21 @@ g_dp = {n: p.grad.detach().float().clone() for n, p in net.named_parameters()}
 bufs_dp = {n: b.clone() for n, b in net.named_buffers() if "running" in n}
 ltot = loss.detach().clone(); dist.all_reduce(ltot); ltot /= world
 
-ok = True
 if rank == 0:
     big = models.resnet50(); big.load_state_dict(sd); big = big.cuda().train()
     lb = crit(big(x.cuda()), y.cuda()); lb.backward(); torch.cuda.synchronize()
-    worst = 1.0
-    for n, p in big.named_parameters():
-        a, b = g_dp[n].double().flatten(), p.grad.double().flatten()
-        c = float(a @ b / (a.norm() * b.norm() + 1e-30))
-        worst = min(worst, c)
+    worst_c, worst_n, who = compare(g_dp, list(big.named_parameters()))
     def buf_err(prefixes):
         return max(float((bufs_dp[n] - b).norm() / (b.norm() + 1e-12)) for n, b in big.named_buffers()
                    if "running" in n and n.startswith(prefixes))
     early, late = buf_err(("bn1.", "layer1.0.")), buf_err(("layer4.",))
-    fc = float((g_dp["fc.weight"].flatten() @ big.fc.weight.grad.float().flatten()) /
-               (g_dp["fc.weight"].norm() * big.fc.weight.grad.float().norm()))
-    print("loss dp %.5f big %.5f | worst grad cosine %.4f fc.weight cosine %.5f | running-stat err early %.2e late %.2e"
-          % (ltot.item(), lb.item(), worst, fc, early, late))
-    # SyncBN statistics of the first layers match tightly; deeper quantities inherit the bf16
-    # chaos described in DESIGN.md (the two runs differ only in fp32 summation order, which is
-    # enough to flip bf16 roundings), so they get loose gates.
-    ok = abs(ltot.item() - lb.item()) / lb.item() < 1e-2 and early < 2e-3 and late < 0.15 and fc > 0.95
+    print("resnet50 DP x%d vs global batch (161 parameters): loss dp %.5f big %.5f | worst grad cosine %.6f, worst norm "
+          "deviation %.2e (%s) | running-stat err early %.2e late %.2e"
+          % (world, ltot.item(), lb.item(), worst_c, worst_n, who, early, late))
+    ok = ok and abs(ltot.item() - lb.item()) / lb.item() < 2e-3 and early < 2e-3 and late < 2e-2 \
+        and worst_c >= 0.999 and worst_n < 1e-2
 # ---- the peer-memory one-shot all-reduce itself: == NCCL, bitwise identical across ranks, eager and
 #      replayed from a CUDA graph (epochs / parity buffers keep working across replays)
-from sota_imagenet_b200 import ops
 if ops.PEER is not None:
     torch.cuda.synchronize(); ops.PEER.reset_layout(); dist.barrier()
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
