@@ -140,3 +140,37 @@ class BResNet(nn.Module):
 def bresnet50(seed=0, **kw):
     torch.manual_seed(seed)
     return BResNet(**kw)
+
+
+def bbottleneck_bf16_faithful(blk, x):
+    """BBottleneck.forward with values rounded to bfloat16 exactly where the B200 pipeline stores
+    bf16 tensors (conv outputs, BN+activation outputs, blur / avg-pool outputs, the block output;
+    the ECA gate and the pooled means stay fp32, the gate is applied inside the final add +
+    activation pass): the per-block strict oracle of tests/test_gpu_bresnet.py."""
+    from .torch_ref import _RoundFwd, _q
+
+    def conv(m, t):
+        w = m.weight
+        if m.ws:
+            var, mean = torch.var_mean(w, dim=(1, 2, 3), keepdim=True, unbiased=False)
+            w = (w - mean) * torch.rsqrt(var + m.eps)
+        return _q(F.conv2d(t, _RoundFwd.apply(w), None, m.stride, m.padding))
+
+    def bn(m, t):
+        return _q(m(t))
+
+    o = bn(blk.bn1, conv(blk.conv1, x))
+    o = bn(blk.bn2, conv(blk.conv2, o))
+    if blk.blur is not None:
+        o = _q(blk.blur(o))
+    o = bn(blk.bn3, conv(blk.conv3, o))
+    if blk.eca is not None:
+        p = o.mean(dim=(2, 3))
+        s = torch.sigmoid(F.conv1d(p[:, None, :], blk.eca.weight, padding=1))[:, 0]
+        o = o * s[:, :, None, None]
+    r = x
+    if blk.downsample is not None:
+        if blk.pool_shortcut:
+            r = _q(F.avg_pool2d(r, 2, 2))
+        r = bn(blk.downsample[1], conv(blk.downsample[0], r))
+    return _q(blk.act_fn(o + r))

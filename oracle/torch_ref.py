@@ -154,19 +154,20 @@ def _bn(m, x):
                         m.momentum, m.eps)
 
 
-def bf16_faithful_forward(model, x):
-    """torchvision ResNet forward with bf16 storage rounding (see comment above)."""
+def bf16_faithful_forward(model, x, act=F.relu):
+    """torchvision ResNet forward with bf16 storage rounding (see comment above); `act` replaces
+    every ReLU (the leaky-ReLU regime of tests/test_gpu_model.py)."""
     x = _RoundFwd.apply(x)
-    y = _q(F.relu(_bn(model.bn1, _conv_q(model.conv1, x))))
+    y = _q(act(_bn(model.bn1, _conv_q(model.conv1, x))))
     y = F.max_pool2d(y, 3, 2, 1)
     for layer in (model.layer1, model.layer2, model.layer3, model.layer4):
         for blk in layer:
             idt = y
-            o = _q(F.relu(_bn(blk.bn1, _conv_q(blk.conv1, y))))
-            o = _q(F.relu(_bn(blk.bn2, _conv_q(blk.conv2, o))))
+            o = _q(act(_bn(blk.bn1, _conv_q(blk.conv1, y))))
+            o = _q(act(_bn(blk.bn2, _conv_q(blk.conv2, o))))
             o = _bn(blk.bn3, _conv_q(blk.conv3, o))
             if blk.downsample is not None:
                 idt = _bn(blk.downsample[1], _conv_q(blk.downsample[0], y))
-            y = _q(F.relu(o + idt))
+            y = _q(act(o + idt))
     feat = _q(y.mean(dim=(2, 3)))
     return _q(F.linear(feat, _RoundFwd.apply(model.fc.weight), model.fc.bias))

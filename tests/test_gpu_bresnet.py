@@ -67,6 +67,62 @@ def test_extra_operators_match_torch():
     assert _cos(xe.grad, xer.grad) > 0.999 and _cos(eca.weight.grad, eca_ref.weight.grad) > 0.999
 
 
+@pytest.mark.parametrize("inplanes,planes,stride,down,hw,batch", [
+    (256, 64, 1, False, 56, 4),     # identity block (ECA + leaky ABN)
+    (64, 64, 1, True, 56, 4),       # layer1.0: projection shortcut, no anti-aliasing
+    (256, 128, 2, True, 56, 4),     # layer2.0: 3x3 stride 1 + BlurPool, AvgPool + 1x1 shortcut
+    (1024, 512, 2, True, 14, 16),   # layer4.0
+    (2048, 512, 1, False, 7, 16),   # layer4 identity
+])
+def test_bbottleneck_forward_backward(inplanes, planes, stride, down, hw, batch):
+    """One BBottleneck against (i) its bf16-faithful restatement (oracle/bresnet_ref.py
+    bbottleneck_bf16_faithful: fp32 arithmetic, bf16 rounding where the kernels store bf16) --
+    every parameter gradient and dx: cosine >= 0.999, output within bf16 rounding -- and (ii) the
+    pure fp32 block: cosine >= 0.995 (same gates as tests/test_gpu_blocks.py for ResNet's
+    Bottleneck)."""
+    import copy
+    from sota_imagenet_b200 import bresnet, ops
+    torch.manual_seed(0)
+    ref = bresnet_ref.BBottleneck(inplanes, planes, stride, down).cuda().train()
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if p.dim() == 1:
+                p.uniform_(0.5, 1.5) if n.endswith("weight") else p.normal_(0, 0.2)
+            elif p.dim() == 4:
+                p.copy_(p.bfloat16().float())
+    blk = bresnet.BBottleneck(inplanes, planes, stride, downsample=down)
+    missing, unexpected = blk.load_state_dict(ref.state_dict(), strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    blk = blk.cuda().train()
+    faith = copy.deepcopy(ref)
+    x = torch.nn.functional.leaky_relu(torch.randn(batch, inplanes, hw, hw, device="cuda"), 0.01).bfloat16()
+    xr = x.float().requires_grad_(True)
+    out_ref = ref(xr)
+    dy = torch.randn_like(out_ref).bfloat16()
+    out_ref.backward(dy.float())
+    xf = x.float().requires_grad_(True)
+    out_f = bresnet_ref.bbottleneck_bf16_faithful(faith, xf)
+    out_f.backward(dy.float())
+    xb = ops.to_nhwc_bf16(x).requires_grad_(True)
+    out = blk(xb)
+    out.backward(ops.to_nhwc_bf16(dy))
+    torch.cuda.synchronize()
+    assert (out.float() - out_f).norm() / out_f.norm() < 2e-3
+    assert (out.float() - out_ref).norm() / out_ref.norm() < 1e-2
+    fp, rp = dict(faith.named_parameters()), dict(ref.named_parameters())
+    report = {"dx": (_cos(xb.grad, xf.grad), _cos(xb.grad, xr.grad))}
+    for name, p in blk.named_parameters():
+        report[name] = (_cos(p.grad.reshape(fp[name].shape), fp[name].grad), _cos(p.grad.reshape(rp[name].shape), rp[name].grad))
+    print(report)
+    for name, (c_faithful, c_fp32) in report.items():
+        assert c_faithful >= 0.999, (name, c_faithful, c_fp32)
+        assert c_fp32 >= 0.995, (name, c_faithful, c_fp32)
+    rb = dict(ref.named_buffers())
+    for name, b in blk.named_buffers():
+        if "running" in name:
+            assert (b - rb[name]).norm() / (rb[name].norm() + 1e-12) < 1e-2, name
+
+
 @pytest.mark.parametrize("ws", [False, True])
 def test_bresnet50_step_matches_restatement(ws):
     from sota_imagenet_b200 import losses
