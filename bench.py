@@ -25,6 +25,87 @@ BATCH = 256
 SIZE = 224
 METRIC = "resnet50_224_bf16_train_images_per_sec"
 UNIT = "images/s"
+# --config: every BASELINE.json configuration through the same timed loop (the default, r50, is the
+# headline; the others are configs[2..4]: the progressive-resize stages, BResNet-50, the angular heads)
+CONFIGS = {
+    "r50": dict(size=224, metric=METRIC, desc="ResNet-50"),
+    "r50_192": dict(size=192, metric="resnet50_192_bf16_train_images_per_sec", desc="ResNet-50 (progressive stage)"),
+    "r50_128": dict(size=128, metric="resnet50_128_bf16_train_images_per_sec", desc="ResNet-50 (progressive stage)"),
+    "bresnet50": dict(size=224, metric="bresnet50_224_bf16_train_images_per_sec",
+                      desc="BResNet-50 encoder (deep stem, blur-pool, ECA, leaky in-place ABN, weight standardisation, "
+                           "drop 0.2 / drop-connect 0.2: reference configs/_old_configs/_first_attempts/BResNet50_encoder.yaml:41-51)"),
+    "r50_arcface": dict(size=224, metric="resnet50_arcface_224_bf16_train_images_per_sec",
+                        desc="ResNet-50 -> 512-d -> SphereLinearLayer(512, 1000) + ArcFace(s=10, m=0.2)"),
+    "r50_cosface": dict(size=224, metric="resnet50_cosface_224_bf16_train_images_per_sec",
+                        desc="ResNet-50 -> 512-d -> SphereLinearLayer(512, 1000) + CosFace (AdaCos fixed_s=10, margin 0.2)"),
+}
+
+
+def build_workload(config):
+    """-> (net, criterion) of a BASELINE.json configuration (random init, on the CPU)."""
+    from sota_imagenet_b200 import losses, models
+    ce = losses.CrossEntropyLoss(smoothing=0.1)
+    if config == "bresnet50":
+        net = models.resnet50(stem_type="deep", antialias=True, attn_type="eca", norm_layer="inplaceabn",
+                              norm_act="leaky_relu", drop_rate=0.2, drop_connect_rate=0.2,
+                              weight_standardization=True)
+        return net, ce
+    if config == "r50_arcface":
+        return models.resnet50_embedding(512, 1000), losses.AdditiveAngularMarginLoss(final_criterion=ce, s=10.0, m=0.2)
+    if config == "r50_cosface":
+        return models.resnet50_embedding(512, 1000), losses.AdaCos(final_criterion=ce, margin=0.2, fixed_s=10)
+    return models.resnet50(), ce
+
+
+def gpu_baseline_rate(dev, world, rank, size, steps=12, warmup=4):
+    """The practical comparator SURVEY 8(d) asks for: stock PyTorch on the same GPU(s) -- torchvision
+    ResNet-50, channels_last, torch.autocast(bfloat16), cuDNN / cuBLAS kernels, torch.optim.SGD
+    (Nesterov, foreach), SyncBatchNorm + DistributedDataParallel for N > 1 -- same batch, same
+    synthetic data, device-timed.  This is what the reference's train.py runs minus DALI."""
+    import torch
+    import torch.distributed as dist
+    import torchvision
+    torch.manual_seed(0)
+    net = torchvision.models.resnet50(weights=None).to(dev).to(memory_format=torch.channels_last).train()
+    if world > 1:
+        net = torch.nn.SyncBatchNorm.convert_sync_batchnorm(net)
+        net = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index])
+    opt = torch.optim.SGD(net.parameters(), lr=0.001 * world, momentum=0.9, weight_decay=3e-5, nesterov=True)
+    x = torch.randn(BATCH, 3, size, size, device=dev).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 1000, (BATCH,), device=dev)
+    crit = torch.nn.CrossEntropyLoss(label_smoothing=0.1)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = crit(net(x), y)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    del net, opt, x
+    torch.cuda.empty_cache()
+    return {"value": BATCH * world * steps / ms * 1e3, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "kind": "stock PyTorch %s: torchvision ResNet-50 channels_last + autocast(bf16) (cuDNN/cuBLAS) + "
+                    "torch SGD-Nesterov%s" % (torch.__version__, ", SyncBatchNorm + DDP" if world > 1 else ""),
+            "note": "same GPU(s), batch %d/GPU at %dx%d, synthetic, device-timed; a reported comparator" % (BATCH, size, size)}
 # SURVEY.md 8(d): conv FLOPs per image fwd 8.174 G, fwd+dgrad(no stem)+wgrad 24.29 G (+0.012 FC)
 TRAIN_GFLOP_PER_IMG = 24.29 + 0.012
 
@@ -217,13 +298,26 @@ def run_ours(args):
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
+    global SIZE
+    cfg = CONFIGS[args.config]
+    SIZE = cfg["size"]
     torch.manual_seed(0)
-    net = models.resnet50().to(dev).train()
-    crit = losses.CrossEntropyLoss(smoothing=0.1)
+    net, crit = build_workload(args.config)
+    net = net.to(dev).train()
     # lr = 0.1 * global_batch / 256 at its warm-up start (1.r50_baseline.yaml:42: 0.001 -> 1.0)
     opt = optimizers.SGD(net.parameters(), lr=0.001 * world, momentum=0.9, weight_decay=3e-5,
                          nesterov=True)
-    model = parallel.DataParallel(net, sync_bn=True) if world > 1 else net
+    root = net.encoder if hasattr(net, "encoder") else net     # (embedding models wrap the trunk)
+    if world > 1:
+        dp = parallel.DataParallel(root, sync_bn=True)
+        if root is net:
+            model = dp
+        else:
+            net.encoder_dp = dp      # keeps the hooks alive; the head's few parameters are averaged below
+            model = net
+    else:
+        model = net
+    head_params = [p for n, p in net.named_parameters() if not n.startswith("encoder.")] if root is not net else []
 
     # ---- device-resident inputs (kernel-path number) -------------------------------------
     g = torch.Generator(device=dev).manual_seed(rank)
@@ -238,6 +332,9 @@ def run_ours(args):
         opt.zero_grad()
         loss = crit(model(x), y)
         loss.backward()
+        if world > 1:
+            for p in head_params:        # sphere-linear head (plain nn.Parameter): average like DDP
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
         opt.step()
         return loss
 
@@ -396,30 +493,45 @@ def run_ours(args):
             "conv_share_of_step": conv_ms / total_ms if total_ms else None,
             "per_call_ms": {n: round(v[0], 3) for n, v in sorted(groups.items(), key=lambda kv: -kv[1][0])},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            rate, cores, sample = cpu_oracle_rate()
+        if world == 1 and not args.no_cpu_baseline and args.config.startswith("r50") and "face" not in args.config:
+            rate, cores, sample = cpu_oracle_rate(size=SIZE)
             cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    # ---- stock PyTorch on the same GPU(s): cuDNN channels_last + autocast(bf16) (+ DDP / SyncBN) ----
+    gpu_baseline = None
+    used_graph = graph is not None
+    if not args.no_gpu_baseline:
+        torch.cuda.synchronize()
+        net = model = opt = graph = dp = root = None     # free our model first (the comparator needs ~22 GB)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            gpu_baseline = gpu_baseline_rate(dev, world, rank, SIZE)
+        except Exception as e:     # a comparator failure must not lose the measurement
+            gpu_baseline = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
-                "workload": "ResNet-50 fwd+bwd+SGD-Nesterov(m=.9, wd=3e-5) + smooth-CE(0.1), batch %d/GPU, "
-                            "%dx%d, NHWC bf16, SyncBN + bucketed grad all-reduce for N>1" % (BATCH, SIZE, SIZE),
+                "workload": "%s fwd+bwd+SGD-Nesterov(m=.9, wd=3e-5) + smooth-CE(0.1), batch %d/GPU, "
+                            "%dx%d, NHWC bf16, SyncBN + bucketed grad all-reduce for N>1" % (cfg["desc"], BATCH, SIZE, SIZE),
+                "name": args.config,
                 "global_batch": BATCH * world, "parallelism": "dp%d" % world,
-                "cuda_graph": graph is not None,
+                "cuda_graph": used_graph,
                 "l2": "activation working set (~12 GB/step) >> 126 MB L2; no flush needed",
             },
-            "tflops_algorithmic": TRAIN_GFLOP_PER_IMG * value / 1e3,
+            "tflops_algorithmic": (TRAIN_GFLOP_PER_IMG * (SIZE / 224.0) ** 2 * value / 1e3) if args.config.startswith("r50") else None,
             "loss": final_loss,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
                     "path": "pinned host uint8 [256,256,256,3] -> H2D (copy stream, double-buffered) -> GpuAugment -> model -> CE -> backward -> SGD -> loss D2H"},
             "gpu_launches": int(calls_per_step * args.steps),
             "clocks": clocks, "roofline": roofline, "roofline_bn": roofline_bn,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
         }
         emit(line)
     if world > 1:
@@ -464,6 +576,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--config", default="r50", choices=sorted(CONFIGS))
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 12:

@@ -50,9 +50,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    # build.build() is a no-op when the source digest matches the stamp of the built library: a stale
+    # .so (missing newer symbols) is rebuilt instead of failing later with AttributeError.  On a box
+    # without nvcc the shipped library is used as is.
+    try:
         from . import build as _build
         _build.build()
+    except Exception:
+        if not os.path.exists(LIB_PATH):
+            raise
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in header_prototypes().items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

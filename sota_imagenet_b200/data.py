@@ -170,7 +170,12 @@ class RecordLoader:
         full_crop = getattr(cfg, "full_crop", False)
         self.crop_size = self.image_size if full_crop else math.ceil((self.image_size * 1.14 + 8) // 16 * 16)
         self.decode_workers = decode_workers
+        # global sample counter of the crop / flip Philox stream: epoch * dataset + position, offset by
+        # the shard so that ranks draw different randoms; carried across loader rebuilds by DataManager
+        self.rank = getattr(reader, "shard_id", 0)
+        self.world = max(getattr(reader, "num_shards", 1), 1)
         self._seen = 0
+        self._epoch = 0
 
     def __len__(self):
         return len(self.reader) // self.batch_size
@@ -182,7 +187,8 @@ class RecordLoader:
         buf, offsets, dims = (t.to(dev, non_blocking=True) for t in (buf, offsets, dims))
         labels = labels.to(dev, non_blocking=True)
         if self.train:
-            boxes = ops.rrc_boxes_ragged(dims, self.min_area, 1.0, self.seed, self._seen, True)
+            first = (self._epoch * len(self.reader) + self._seen) * self.world + self.rank * len(samples)
+            boxes = ops.rrc_boxes_ragged(dims, self.min_area, 1.0, self.seed, first, True)
             data = ops.augment_ragged(buf, offsets, dims, boxes, self.image_size, DATA_MEAN, DATA_STD,
                                       self.out_mode)
         else:
@@ -194,12 +200,18 @@ class RecordLoader:
 
     def __iter__(self):
         batch = []
-        for sample in self.reader:
-            batch.append(sample)
-            if len(batch) == self.batch_size:
-                yield self._emit(batch)
-                batch = []
-        # the ragged tail is dropped (LastBatchPolicy.DROP, dali_dataloader.py:175)
+        self._seen = 0
+        if hasattr(self.reader, "epoch"):
+            self.reader.epoch = self._epoch      # a steps_per_epoch / debug break must not replay the order
+        try:
+            for sample in self.reader:
+                batch.append(sample)
+                if len(batch) == self.batch_size:
+                    yield self._emit(batch)
+                    batch = []
+            # the ragged tail is dropped (LastBatchPolicy.DROP, dali_dataloader.py:175)
+        finally:
+            self._epoch += 1
 
 
 def real_data_root(cfg):
@@ -262,15 +274,24 @@ class DataManager:
             for key, value in self.stages[idx].extra_args.items():
                 setattr(train_cfg, key, value)
         val_cfg.image_size = train_cfg.image_size
+        unsupported = [k for k in ("blur_prob", "random_interpolation")
+                       if getattr(train_cfg, k, 0)]
+        if unsupported:
+            import warnings
+            warnings.warn("sota_imagenet_b200.data: augmentation fields %s of the reference train_pipeline "
+                          "(dali_dataloader.py:75-83) are not implemented and are ignored" % unsupported)
         root = real_data_root(train_cfg) if self.source is None else None
+        prev_epoch = getattr(self.loader, "_epoch", 0) if self.loader is not None else 0
         if root is not None:
             # real images on disk, laid out like the reference expects (dali_dataloader.py:46-65)
             self.loader = RecordLoader(train_cfg, make_reader(train_cfg, root, "train", self.rank, self.world_size),
                                        train=True, **self.loader_kw)
             self.val_loader = RecordLoader(val_cfg, make_reader(val_cfg, root, "val", self.rank, self.world_size),
                                            train=False, **self.loader_kw)
+            self.loader._epoch = prev_epoch          # progressive resizing must not replay epoch 0
             return
         self.loader = SyntheticLoader(train_cfg, self.source, rank=self.rank,
                                       world_size=self.world_size, train=True, **self.loader_kw)
         self.val_loader = SyntheticLoader(val_cfg, self.source, rank=self.rank,
                                           world_size=self.world_size, train=False, **self.loader_kw)
+        self.loader._epoch = prev_epoch

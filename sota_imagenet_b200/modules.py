@@ -96,8 +96,12 @@ class SibModule(nn.Module):
             if p.dtype != torch.float32:
                 raise _lib.SibError("parameters must stay float32 (bf16 shadows are kept internally)")
         existing = getattr(params[0][1], "_sib_arena", None)
+        # reuse only an arena laid out in REGISTRATION order: the data-parallel bucket plan
+        # (parallel.plan_buckets) assumes arena order == registration order; an arena built by an
+        # optimizer in param-group order (step()/load_state_dict() before the first forward) is
+        # rebuilt here and the optimizer migrates its state (optimizers._collect_arenas)
         if existing is not None and existing.intact() and len(existing.entries) == len(params) and all(
-                getattr(p, "_sib_arena", None) is existing for _, p in params):
+                e[1] is p for e, (_, p) in zip(existing.entries, params)):
             self._arena = existing
         else:
             self._arena = ParamArena(params, dev)

@@ -54,10 +54,16 @@ class SGD(torch.optim.Optimizer):
             if self.ema_decay and a.ema is None:
                 a.ema = a.flat.clone()
         self._arenas = arenas
-        # expose momentum buffers in the torch.optim.SGD state format
+        # expose momentum buffers in the torch.optim.SGD state format.  When the arenas were
+        # re-collected (a .cuda()/.to() or an arena rebuilt in registration order) the state
+        # accumulated so far MIGRATES into the new buffers instead of being silently zeroed.
         for a in arenas:
             for _, p, o, n, layout in a.entries:
-                self.state[p]["momentum_buffer"] = ParamArena.view_of(a.momentum, o, p.shape, layout)
+                view = ParamArena.view_of(a.momentum, o, p.shape, layout)
+                old = self.state[p].get("momentum_buffer") if p in self.state else None
+                if old is not None and old.data_ptr() != view.data_ptr() and old.shape == view.shape:
+                    view.copy_(old)
+                self.state[p]["momentum_buffer"] = view
 
     def _segments(self, arena):
         gmap = {}
@@ -240,8 +246,16 @@ class MyNovograd(torch.optim.Optimizer):
             for (_, p, o, n, lay), (unit, ng, nb) in zip(a.entries, a.novo_layout):
                 st = self.state[p]
                 st.setdefault("step", 0)
-                st["ema_grad"] = ParamArena.view_of(a.novo_ema_grad, o, p.shape, lay)
+                view = ParamArena.view_of(a.novo_ema_grad, o, p.shape, lay)
                 norms = a.novo_ema_norm[nb:nb + ng]
+                # re-collection (arena rebuilt / moved): accumulated state migrates, it is not reset
+                old_g, old_n = st.get("ema_grad"), st.get("ema_norm")
+                if old_g is not None and old_g.data_ptr() != view.data_ptr() and old_g.shape == view.shape:
+                    view.copy_(old_g)
+                if old_n is not None and old_n.numel() == p.numel() and p.numel() > 0 and \
+                        old_n.data_ptr() != norms.data_ptr():
+                    norms.copy_(old_n.reshape(ng, -1)[:, 0])
+                st["ema_grad"] = view
                 if ng == 1:
                     st["ema_norm"] = norms.expand(p.numel()).view(p.shape) if p.dim() == 0 else \
                         norms.view((1,) * p.dim()).expand(p.shape)

@@ -248,6 +248,7 @@ class _ShardedReader:
 
     def __init__(self, n, shard_id=0, num_shards=1, random_shuffle=False, seed=0):
         self.n_total = n
+        self.shard_id, self.num_shards = shard_id, num_shards
         self.lo, self.hi = shard_range(n, shard_id, num_shards)
         self.random_shuffle, self.seed, self.epoch = random_shuffle, seed, 0
 

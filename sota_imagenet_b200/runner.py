@@ -20,6 +20,8 @@ class Callback:
 
     def on_begin(self): pass
     def on_epoch_begin(self): pass
+    def on_loader_begin(self): pass
+    def on_loader_end(self): pass
     def on_batch_begin(self): pass
     def on_after_backward(self): pass
     def on_batch_end(self): pass
@@ -109,6 +111,7 @@ class Runner:
         st.loss_meter = AverageMeter()
         st.metric_meters = {"Acc@1": AverageMeter(), "Acc@5": AverageMeter()}
         st.epoch_size = steps or len(loader)
+        self._cb("on_loader_begin")
         pending = []
         for i, batch in enumerate(loader):
             if steps is not None and i >= steps:
@@ -135,7 +138,23 @@ class Runner:
                 self._drain(pending)
             self._cb("on_batch_end")
         self._drain(pending)
+        self._cb("on_loader_end")
+        self._reduce_meters()
         return st.loss_meter.avg, {k: m.avg for k, m in st.metric_meters.items()}
+
+    def _reduce_meters(self):
+        """Sum the loss / metric meters over the ranks (each rank sees 1 / world of the data; the
+        reference Runner reduces them too), so that rank 0 logs whole-dataset numbers."""
+        if not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+                torch.distributed.get_world_size() == 1:
+            return
+        st = self.state
+        meters = [st.loss_meter] + [st.metric_meters[k] for k in sorted(st.metric_meters)]
+        dev = "cuda" if torch.distributed.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([v for m in meters for v in (m.sum, float(m.n))], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t)
+        for i, m in enumerate(meters):
+            m.sum, m.n = float(t[2 * i]), int(t[2 * i + 1])
 
     def _drain(self, pending):
         """One device->host sync for a window of steps (the reference reads every step)."""
@@ -271,6 +290,89 @@ class CutmixMixup(Cutmix, Mixup):
         else:
             self.tb = self.mixup_tb
             self.state.input = self.mixup(*self.state.input)
+
+
+class ModelEma(Callback):
+    """pt_clb.ModelEma(model, decay) as the reference wires it (train.py:112,138: created after
+    .cuda(), placed AFTER CheckpointSaver): an exponential moving average of the weights that is
+    swapped into the model when validation starts, so validation and the epoch's checkpoint
+    (CheckpointSaver.on_epoch_end runs first) see the EMA weights, and swapped back out at epoch
+    end before training continues.  With a fused optimizer (`optimizer` given: SGD / MyNovograd
+    keep `arena.ema` up to date inside their update kernel) this callback only swaps; otherwise it
+    also maintains the average itself after every batch.  The average covers the parameters
+    (BatchNorm running statistics stay the live ones)."""
+
+    def __init__(self, model, decay=0.9999, optimizer=None):
+        self.model = model.module if hasattr(model, "module") else model
+        self.decay, self.optimizer = decay, optimizer
+        self.swapped = False
+        self._own = None
+
+    def _arena(self):
+        return self.model.ensure_arena()
+
+    def on_batch_end(self):
+        if self.optimizer is not None or not self.state.is_train:
+            return
+        a = self._arena()
+        if self._own is None:
+            self._own = a.flat.clone()
+        self._own.lerp_(a.flat, 1.0 - self.decay)
+
+    def _ema_buffer(self):
+        a = self._arena()
+        return a.ema if self.optimizer is not None else self._own
+
+    def _swap(self):
+        a, ema = self._arena(), self._ema_buffer()
+        if ema is None:
+            return False
+        tmp = a.flat.clone()
+        a.flat.copy_(ema)
+        ema.copy_(tmp)
+        a.refresh_shadow(force=True)
+        return True
+
+    def on_loader_begin(self):
+        if not self.state.is_train and not self.swapped:
+            self.swapped = self._swap()
+
+    def on_epoch_end(self):
+        if self.swapped:
+            self._swap()
+            self.swapped = False
+
+    def state_dict(self):
+        """EMA weights keyed like model.state_dict()."""
+        from .arena import ParamArena
+        a, ema = self._arena(), self._ema_buffer()
+        if ema is None:
+            return {}
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        return {names[id(p)]: ParamArena.view_of(ema, o, p.shape, layout).clone()
+                for _, p, o, n, layout in a.entries if id(p) in names}
+
+
+def initialize(model, gamma=1.72):
+    """pt.utils.misc.initialize(model, gamma) (reference train.py:70-71, absent package; SURVEY
+    App. C): variance-preserving init with gain `gamma` -- conv / linear weights ~ N(0, gamma^2 /
+    fan_in)  (gamma = 1.72 compensates the variance a (leaky-)ReLU removes), BatchNorm weight 1 /
+    bias 0, linear bias 0.  Parity unpinned (the reference's source is absent)."""
+    from .modules import BatchNorm2d, Conv2d, Linear, StemConv
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, (Conv2d, StemConv, Linear, torch.nn.Conv2d, torch.nn.Linear)):
+                w = m.weight
+                fan_in = w[0].numel()
+                w.normal_(0.0, gamma / math.sqrt(fan_in))
+                if getattr(m, "bias", None) is not None:
+                    m.bias.zero_()
+            elif isinstance(m, (BatchNorm2d, torch.nn.modules.batchnorm._BatchNorm)):
+                # (a zero-initialised last BN of a residual block is kept)
+                if m.weight is not None and float(m.weight.abs().sum()) != 0.0:
+                    m.weight.fill_(1.0)
+                if m.bias is not None:
+                    m.bias.zero_()
 
 
 class CheckpointSaver(Callback):

@@ -114,6 +114,77 @@ def test_ema_accumulation_checkpoint_resume(tmp_path):
     assert not torch.equal(p1, net.fc.weight.detach())
 
 
+def test_model_ema_callback_swaps_weights_for_validation_and_checkpoint(tmp_path):
+    """Reference train.py:112,138: ModelEma placed after CheckpointSaver -- validation and the
+    epoch's checkpoint see the EMA weights, training continues on the raw ones.  Both the fused
+    (optimizer-maintained) and the stand-alone average are exercised."""
+    from sota_imagenet_b200 import losses, models, optimizers, runner
+
+    class Loader:
+        batch_size = 8
+
+        def __init__(self, n):
+            g = torch.Generator(device="cuda").manual_seed(0)
+            self.b = [(torch.randn(8, 3, 64, 64, device="cuda", generator=g),
+                       torch.randint(0, 16, (8,), device="cuda", generator=g)) for _ in range(n)]
+
+        def __len__(self):
+            return len(self.b)
+
+        def __iter__(self):
+            return iter(self.b)
+
+    for fused in (True, False):
+        torch.manual_seed(0)
+        net = models.resnet26(num_classes=16).cuda().train()
+        net.ensure_arena()
+        w0 = net.fc.weight.detach().clone()
+        opt = optimizers.SGD(net.parameters(), lr=0.05, momentum=0.9, ema_decay=0.5 if fused else 0.0)
+        seen = {}
+
+        class Spy(runner.Callback):
+            def on_loader_end(self):
+                seen["val" if not self.state.is_train else "train"] = net.fc.weight.detach().clone()
+
+        ema = runner.ModelEma(net, 0.5, opt if fused else None)
+        saver = runner.CheckpointSaver(str(tmp_path), "m%d.chpn" % fused)
+        run = runner.Runner(net, opt, losses.CrossEntropyLoss(), callbacks=[saver, ema, Spy()])
+        run.fit(Loader(3), val_loader=Loader(1), epochs=1)
+        raw_after = net.fc.weight.detach().clone()
+        assert torch.equal(raw_after, seen["train"])                 # swapped back after the epoch
+        assert not torch.equal(seen["val"], seen["train"])           # validation ran on other weights
+        # the EMA after 3 steps with decay 0.5 lies strictly between the initial and the final weights
+        d_total = (raw_after - w0).norm()
+        assert 0 < (seen["val"] - w0).norm() < d_total
+        ck = torch.load(os.path.join(str(tmp_path), "m%d.chpn" % fused), map_location="cuda", weights_only=False)
+        assert torch.equal(ck["state_dict"]["fc.weight"].reshape(seen["val"].shape[:2]),
+                           seen["val"].reshape(seen["val"].shape[:2]))    # the checkpoint holds the EMA weights
+
+
+def test_optimizer_state_survives_an_arena_rebuild():
+    """An optimizer stepped (or loaded) BEFORE the model's first forward builds a loose arena in
+    param-group order; the model's first forward rebuilds it in registration order (what the
+    data-parallel bucket plan needs) and the momentum accumulated so far must migrate, not vanish."""
+    from sota_imagenet_b200 import models, optimizers, runner
+    torch.manual_seed(0)
+    net = models.resnet26(num_classes=16).cuda().train()
+    groups = runner.filter_from_weight_decay(net, skip_list=("bn", "bias"))   # two groups: order != registration
+    opt = optimizers.SGD(groups, lr=0.0, momentum=0.9)
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()                                   # momentum buffers = 1 everywhere, loose arena
+    loose = opt._arenas[0]
+    assert getattr(loose, "_loose", False)
+    net(torch.randn(2, 3, 64, 64, device="cuda"))   # first forward: arena rebuilt in registration order
+    arena = net._arena
+    assert arena is not loose and [e[1] for e in arena.entries] == [p for _, p in net.named_parameters()]
+    for p in net.parameters():
+        p.grad.zero_()
+    opt.step()                                   # re-collects: buf = 0.9 * 1 + 0
+    for p in net.parameters():
+        assert torch.allclose(opt.state[p]["momentum_buffer"], torch.full_like(p, 0.9)), p.shape
+
+
 def test_cuda_graph_capture_while_previous_loss_is_alive():
     """A training loop that keeps `loss` around (logging) must still capture: the autograd glue may
     not cache a leaf whose AccumulateGrad node stays bound to the eager steps' stream

@@ -146,6 +146,45 @@ def test_bucketed_mean_allreduce_gloo_world2():
     assert torch.equal(r0, want) and torch.equal(r1, want)
 
 
+def _meter_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sota_imagenet_b200 import runner
+    run = runner.Runner(torch.nn.Linear(2, 2), None, None)
+    run.state.loss_meter.update(1.0 + rank, 10 * (rank + 1))           # rank 0: 10 samples of 1, rank 1: 20 of 2
+    run.state.metric_meters["Acc@1"].update(50.0 * rank, 10 * (rank + 1))
+    run._reduce_meters()
+    torch.save((run.state.loss_meter.avg, run.state.loss_meter.n, run.state.metric_meters["Acc@1"].avg),
+               os.path.join(out, "m%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_runner_meters_are_reduced_over_ranks_gloo_world2():
+    """Each rank sees 1 / world of the data; rank 0 must log whole-dataset numbers."""
+    with tempfile.TemporaryDirectory() as out:
+        mp.spawn(_meter_worker, args=(2, 29433, out), nprocs=2, join=True)
+        m0, m1 = torch.load(os.path.join(out, "m0.pt")), torch.load(os.path.join(out, "m1.pt"))
+    assert m0 == m1
+    assert abs(m0[0] - (10 * 1.0 + 20 * 2.0) / 30) < 1e-12 and m0[1] == 30 and abs(m0[2] - 20 * 50.0 / 30) < 1e-9
+
+
+def test_initialize_gain_and_ema_only_for_accepting_optimizers():
+    """pt.utils.misc.initialize(model, gamma) stand-in (reference train.py:70-71) and the ema_decay
+    plumbing of train.py: only optimizers that accept the keyword receive it."""
+    import inspect
+    from sota_imagenet_b200 import models, optimizers, runner
+    torch.manual_seed(0)
+    net = models.resnet26(num_classes=16)
+    runner.initialize(net, 1.72)
+    w = net.layer2[0].conv2.weight
+    fan_in = w[0].numel()
+    assert abs(float(w.std()) * fan_in ** 0.5 / 1.72 - 1) < 0.05
+    assert float(net.layer1[0].bn1.weight.min()) == 1.0 and float(net.layer1[0].bn1.bias.abs().max()) == 0.0
+    assert "ema_decay" in inspect.signature(optimizers.SGD.__init__).parameters
+    assert "ema_decay" in inspect.signature(optimizers.MyNovograd.__init__).parameters
+    assert "ema_decay" not in inspect.signature(torch.optim.AdamW.__init__).parameters
+
+
 def test_novograd_norm_groups_and_table_layout():
     """Host side of MyNovograd: norm groups per tensor / per output unit (reference
     optimizers.py:18-22) and the 56-byte records csrc/optim.cu NovoTensor expects."""

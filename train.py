@@ -3,7 +3,8 @@
     torchrun --nproc-per-node N train.py configs/r50_baseline.yaml [key=value ...]
 Config files use the reference's live YAML schema; its `_target_` entries resolve to the fused
 sm_100a model / criterion / optimizer (sota_imagenet_b200.config.TARGET_REMAP).  Data is the
-synthetic GPU pipeline (sota_imagenet_b200.data) — real-image ingest is out of scope."""
+synthetic GPU pipeline (sota_imagenet_b200.data) unless cfg.loader.root_data_dir / $IMAGENET_DIR holds the
+reference's layout (class folders or TFRecord shards + DALI indexes): then data.RecordLoader reads it."""
 import os
 import sys
 import time
@@ -33,7 +34,13 @@ def main(argv=None):
     model = cfglib.call(cfg.model)                                    # train.py:64
     if cfg.weight_standardization and hasattr(model, "enable_weight_standardization"):
         model.enable_weight_standardization()                         # train.py:66-67
+    if cfg.init_gamma is not None:                                    # train.py:70-71
+        rt.initialize(model, cfg.init_gamma)
     model = model.cuda()                                              # train.py:73
+    if hasattr(model, "ensure_arena"):
+        # build the parameter arena in registration order BEFORE the optimizer exists (or loads a
+        # checkpoint): the data-parallel bucket plan relies on that order
+        model.ensure_arena()
     rt.patch_bn_mom(model, cfg.bn_momentum)                           # train.py:76
     criterion = cfglib.call(cfg.criterion).cuda()                     # train.py:81
     if cfg.filter_from_wd is not None:                                # train.py:83-86
@@ -41,7 +48,11 @@ def main(argv=None):
     else:
         opt_params = [{"params": list(model.parameters())}]
     opt_params[0]["params"].extend(list(criterion.parameters()))      # train.py:89
-    optimizer = cfglib.call(cfg.optim, opt_params, ema_decay=cfg.run.ema_decay)   # train.py:92, :112
+    # the fused optimizers keep the EMA copy of the weights themselves (one extra stream of the update
+    # kernel); any other optimizer target gets the reference's stand-alone ModelEma callback below
+    opt_cls = cfglib.resolve_target(cfg.optim["_target_"])
+    fused_ema = cfg.run.ema_decay > 0 and "ema_decay" in __import__("inspect").signature(opt_cls.__init__).parameters
+    optimizer = cfglib.call(cfg.optim, opt_params, **({"ema_decay": cfg.run.ema_decay} if fused_ema else {}))   # train.py:92
     log("Model params: %.2fM" % (sum(p.numel() for p in model.parameters()) / 1e6))
 
     if cfg.run.resume:                                                # train.py:98-109
@@ -61,6 +72,8 @@ def main(argv=None):
     log("Learning rate stages: %s" % lr_stages)
     callbacks = [rt.PhasesScheduler(lr_stages),
                  rt.CheckpointSaver(os.getcwd(), "model.chpn", cfg.log.save_optim) if cfg.is_master else None]
+    if cfg.run.ema_decay > 0:                                         # train.py:112,138: after CheckpointSaver
+        callbacks.append(rt.ModelEma(model, cfg.run.ema_decay, optimizer if fused_ema else None))
     callbacks += [cfglib.call(c) for c in cfg.run.extra_callbacks]
     run = rt.Runner(model, optimizer, criterion, callbacks=callbacks,
                     accumulate_steps=cfg.run.accumulate_steps, logger=log)
