@@ -414,14 +414,25 @@ def run_ours(args):
     # region, and every step ends with the D2H read of its loss
     pre = data.HostPrefetcher(src, BATCH, device=dev)
 
+    # the step itself goes through the package's public training-step API (runner.GraphStep, what
+    # runner.Runner / train.py use): eager for the first two calls, then captured once and replayed
+    from sota_imagenet_b200 import runner as _runner
+
+    def _avg_head():
+        for p in head_params:
+            dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
+
+    gstep = _runner.GraphStep(model, crit, opt, enabled=not args.no_graph,
+                              after_backward=_avg_head if (world > 1 and head_params) else None)
+
     def e2e_step(_):
         imgs_d, labels_d, i = pre.next()
         xb = aug(imgs_d, first_sample=i * BATCH)
-        loss = step(xb, labels_d)
-        loss_host.copy_(loss.detach(), non_blocking=False)   # D2H read of the step's result
+        loss = gstep(xb, labels_d)[0]
+        loss_host.copy_(loss, non_blocking=False)   # D2H read of the step's result
         return float(loss_host)
 
-    for i in range(max(2, min(args.warmup, 3))):
+    for i in range(max(4, min(args.warmup, 6))):
         e2e_step(i)
     barrier()
     e2e_steps = max(3, min(args.steps, 20))
@@ -436,6 +447,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms2 = float(t)
     e2e_value = BATCH * world * e2e_steps / ms2 * 1e3
+    e2e_replays = gstep.replays
     h2d = BATCH * 256 * 256 * 3 + BATCH * 8
     d2h = 4
 
@@ -502,7 +514,7 @@ def run_ours(args):
     used_graph = graph is not None
     if not args.no_gpu_baseline:
         torch.cuda.synchronize()
-        net = model = opt = graph = dp = root = None     # free our model first (the comparator needs ~22 GB)
+        net = model = opt = graph = dp = root = gstep = None     # free our model first (the comparator needs ~22 GB)
         import gc
         gc.collect()
         torch.cuda.empty_cache()
@@ -528,15 +540,17 @@ def run_ours(args):
             "loss": final_loss,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps,
-                    "path": "pinned host uint8 [256,256,256,3] -> H2D (copy stream, double-buffered) -> GpuAugment -> model -> CE -> backward -> SGD -> loss D2H"},
+                    "cuda_graph_replays": e2e_replays,
+                    "path": "pinned host uint8 [256,256,256,3] -> H2D (copy stream, double-buffered) -> GpuAugment -> runner.GraphStep "
+                            "(model -> CE -> backward -> SGD, one CUDA-graph launch per step) -> loss D2H"},
             "gpu_launches": int(calls_per_step * args.steps),
             "clocks": clocks, "roofline": roofline, "roofline_bn": roofline_bn,
             "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
         }
         emit(line)
     if world > 1:
-        # tear down: drop the captured graph (it holds NCCL kernels) before the communicator
-        graph = None
+        # tear down: drop the captured graphs (they hold NCCL kernels) before the communicator
+        graph = gstep = None
         torch.cuda.synchronize()
         dist.barrier()
         guard = threading.Timer(20.0, lambda: os._exit(0))   # never hang at exit

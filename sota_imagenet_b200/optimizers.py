@@ -103,23 +103,40 @@ class SGD(torch.optim.Optimizer):
                 gv = ParamArena.view_of(a.grad, o, p.shape, layout)
                 if p.grad.data_ptr() != gv.data_ptr():
                     gv.copy_(p.grad)
-            recs = self._segments(a)
-            key = id(a)
-            cached = self._seg_cache.get(key)
-            if cached is None or cached[0] != recs:
-                host = ops.sgd_segments(recs, "cpu").pin_memory()
-                if cached is None or cached[1].numel() != host.numel():
-                    dev = host.to(a.device, non_blocking=True)
-                else:
-                    dev = cached[1]
-                    dev.copy_(host, non_blocking=True)
-                self._seg_cache[key] = (recs, dev, host)
-                cached = self._seg_cache[key]
+            cached = self._upload_segments(a)
+            recs = cached[0]
             ops.sgd_step(a.flat, a.grad, a.momentum, a.shadow, cached[1], len(recs), first,
                          ema=a.ema if self.ema_decay else None, ema_decay=self.ema_decay)
             a.mark_fresh()
         self._steps += 1
         return loss
+
+    def _upload_segments(self, a):
+        """Per-arena hyper-parameter table (lr, weight decay, momentum, ... per segment) in a
+        PERSISTENT device buffer: when a value changes, only its contents are rewritten (async copy
+        from a pinned host table), the address stays -- so a captured CUDA graph of step() keeps
+        reading live values (sync_hyperparams)."""
+        recs = self._segments(a)
+        key = id(a)
+        cached = self._seg_cache.get(key)
+        if cached is None or cached[0] != recs:
+            host = ops.sgd_segments(recs, "cpu").pin_memory()
+            if cached is None or cached[1].numel() != host.numel():
+                if cached is not None and torch.cuda.is_current_stream_capturing():
+                    raise _lib.SibError("optimizer param-group structure changed inside a CUDA graph capture")
+                dev = host.to(a.device, non_blocking=True)
+            else:
+                dev = cached[1]
+                dev.copy_(host, non_blocking=True)
+            self._seg_cache[key] = (recs, dev, host)
+            cached = self._seg_cache[key]
+        return cached
+
+    def sync_hyperparams(self):
+        """Push the current param_group values (a per-batch LR schedule) to the device tables WITHOUT
+        running step(): call before replaying a CUDA graph that captured step()."""
+        for a in self._arenas or []:
+            self._upload_segments(a)
 
     def zero_grad(self, set_to_none=True):
         if self._arenas is None:
@@ -296,22 +313,32 @@ class MyNovograd(torch.optim.Optimizer):
                 if p.grad.data_ptr() != gv.data_ptr():
                     gv.copy_(p.grad)
                 self.state[p]["step"] += 1
-            recs = self._records(a)
-            cached = self._tab_cache.get(id(a))
-            if cached is None or cached[0] != recs:
-                host = ops.novograd_table(recs).pin_memory()
-                if cached is None or cached[1].numel() != host.numel():
-                    dev = host.to(a.device, non_blocking=True)
-                else:
-                    dev = cached[1]
-                    dev.copy_(host, non_blocking=True)
-                cached = self._tab_cache[id(a)] = (recs, dev, host)
+            cached = self._upload_table(a)
+            recs = cached[0]
             ops.novograd_step(a.flat, a.grad, a.novo_ema_grad, a.shadow, cached[1], len(recs),
                               a.novo_sumsq, a.novo_ema_norm, a.novo_denom, self.eps,
                               self.unitwise_norm, ema=a.ema if self.ema_decay else None,
                               ema_decay=self.ema_decay)
             a.mark_fresh()
         return loss
+
+    def _upload_table(self, a):
+        """Persistent device table, contents refreshed in place (see SGD._upload_segments)."""
+        recs = self._records(a)
+        cached = self._tab_cache.get(id(a))
+        if cached is None or cached[0] != recs:
+            host = ops.novograd_table(recs).pin_memory()
+            if cached is None or cached[1].numel() != host.numel():
+                dev = host.to(a.device, non_blocking=True)
+            else:
+                dev = cached[1]
+                dev.copy_(host, non_blocking=True)
+            cached = self._tab_cache[id(a)] = (recs, dev, host)
+        return cached
+
+    def sync_hyperparams(self):
+        for a in self._arenas or []:
+            self._upload_table(a)
 
     def zero_grad(self, set_to_none=False):
         if self._arenas is None:

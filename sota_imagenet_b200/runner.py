@@ -77,6 +77,86 @@ def accuracy(output, target, topk=(1, 5)):
     return [correct[:, :k].any(1).float().mean() * 100 for k in topk]
 
 
+class GraphStep:
+    """One training step (forward, loss, backward, optimizer step, zero_grad, Acc@1/5) captured in a
+    CUDA graph per input signature (shapes / dtypes of the batch: a progressive-resize stage or a
+    switch between index and soft targets captures a new graph) and replayed afterwards: ~300 kernel
+    launches become one graph launch, which is what keeps small-image stages (128 px: 7 ms of GPU
+    work per step) from being bound by the host.  Replaces the eager body of the reference's
+    training loop (pytorch_tools Runner._run_one_epoch, wired at train.py:121-131).
+
+    * inputs are copied into static buffers (one D2D copy of the batch), outputs (loss, logits,
+      Acc@1, Acc@5) live in static tensors that the next replay overwrites;
+    * optimizer hyper-parameters are read by the update kernel from a persistent device table;
+      `optimizer.sync_hyperparams()` refreshes it before every replay, so a per-batch LR schedule
+      (PhasesScheduler) takes effect across replays;
+    * anything that cannot be captured (an optimizer without sync_hyperparams, a capture error)
+      falls back to the same step launched eagerly -- same kernels, same results."""
+
+    WARMUP = 2
+
+    def __init__(self, model, criterion, optimizer, enabled=True, loss_scale=1.0, after_backward=None):
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        self.after_backward = after_backward     # e.g. gradient averaging of parameters outside DataParallel
+        self.enabled = enabled and hasattr(optimizer, "sync_hyperparams") and torch.cuda.is_available()
+        self.loss_scale = loss_scale
+        self.graphs = {}         # signature -> (graph, static_x, static_y, outputs) or None (eager)
+        self.replays = 0
+
+    def _eager(self, x, y):
+        out = self.model(x)
+        loss = self.criterion(out, y)
+        (loss * self.loss_scale if self.loss_scale != 1.0 else loss).backward()
+        if self.after_backward is not None:
+            self.after_backward()
+        self.optimizer.step()
+        self.optimizer.zero_grad()
+        a1, a5 = accuracy(out.detach(), y)
+        return loss.detach(), out.detach(), a1, a5
+
+    @staticmethod
+    def _sig(x, y):
+        return (tuple(x.shape), x.dtype, tuple(x.stride()), tuple(y.shape), y.dtype)
+
+    def _capture(self, x, y):
+        sx, sy = x.clone(), y.clone()
+        self.optimizer.sync_hyperparams()        # no table upload may be captured (it would be replayed)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            outs = self._eager(sx, sy)           # recorded, not executed: the replay below is the step
+        return graph, sx, sy, outs
+
+    def __call__(self, x, y):
+        """-> (loss, logits, acc1, acc5): device tensors, valid until the next call."""
+        if not self.enabled:
+            return self._eager(x, y)
+        sig = self._sig(x, y)
+        entry = self.graphs.get(sig, 0)
+        if isinstance(entry, int):
+            if entry < self.WARMUP:              # the first steps of a signature run eagerly (lazy
+                self.graphs[sig] = entry + 1     # initialisation, arena build, allocator warm-up)
+                return self._eager(x, y)
+            try:
+                entry = self._capture(x, y)
+            except Exception as e:               # capture is an optimisation
+                import warnings
+                warnings.warn("sota_imagenet_b200: CUDA graph capture of the training step failed (%s); "
+                              "running eagerly" % repr(e)[:200])
+                torch.cuda.synchronize()
+                entry = None
+            self.graphs[sig] = entry
+        if entry is None:
+            return self._eager(x, y)
+        graph, sx, sy, outs = entry
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(y, non_blocking=True)
+        self.optimizer.sync_hyperparams()
+        graph.replay()
+        self.replays += 1
+        return outs
+
+
 class RunnerState:
     def __init__(self, model, optimizer, criterion):
         self.model, self.optimizer, self.criterion = model, optimizer, criterion
@@ -91,8 +171,17 @@ class RunnerState:
 
 class Runner:
     def __init__(self, model, optimizer, criterion, callbacks=(), use_fp16=True, accumulate_steps=1,
-                 log_every=50, logger=None):
+                 log_every=50, logger=None, use_graph=None):
         self.state = RunnerState(model, optimizer, criterion)
+        # CUDA-graph replay of the whole training step (GraphStep); off with gradient accumulation
+        # (the optimizer step is then not part of every batch) and for callbacks that hook between
+        # backward and the optimizer step; SIB_GRAPH=0 forces eager launches
+        if use_graph is None:
+            use_graph = os.environ.get("SIB_GRAPH", "1") != "0"
+        hooks_backward = any(type(c).on_after_backward is not Callback.on_after_backward
+                             for c in callbacks if c is not None)
+        self.graph_step = GraphStep(model, criterion, optimizer,
+                                    enabled=use_graph and accumulate_steps == 1 and not hooks_backward)
         self.callbacks = [c for c in callbacks if c is not None]
         for c in self.callbacks:
             c.set_state(self.state)
@@ -119,7 +208,12 @@ class Runner:
             st.step, st.input = i, batch
             self._cb("on_batch_begin")
             data, target = st.input          # callbacks (CutmixMixup) may replace the batch
-            if train:
+            accs = None
+            if train and self.graph_step.enabled:
+                loss, out, a1, a5 = self.graph_step(data, target)
+                # static tensors, overwritten by the next replay: keep three scalars, not the logits
+                accs = torch.stack([loss.float(), a1, a5])
+            elif train:
                 out = st.model(data)
                 loss = st.criterion(out, target)
                 (loss / self.accumulate_steps).backward()
@@ -133,7 +227,10 @@ class Runner:
                     loss = st.criterion(out, target)
             st.output, st.loss = out, loss
             st.global_sample_step += data.shape[0]
-            pending.append((loss.detach(), out.detach(), target, data.shape[0]))
+            if accs is not None:
+                pending.append((accs, None, None, data.shape[0]))
+            else:
+                pending.append((loss.detach(), out.detach(), target, data.shape[0]))
             if len(pending) >= self.log_every:
                 self._drain(pending)
             self._cb("on_batch_end")
@@ -160,10 +257,14 @@ class Runner:
         """One device->host sync for a window of steps (the reference reads every step)."""
         st = self.state
         for loss, out, target, n in pending:
-            a1, a5 = accuracy(out, target)
-            st.loss_meter.update(loss.item(), n)
-            st.metric_meters["Acc@1"].update(a1.item(), n)
-            st.metric_meters["Acc@5"].update(a5.item(), n)
+            if out is None:                     # graph-replayed step: (loss, Acc@1, Acc@5) already reduced
+                lv, a1, a5 = loss.tolist()
+            else:
+                a1, a5 = (v.item() for v in accuracy(out, target))
+                lv = loss.item()
+            st.loss_meter.update(lv, n)
+            st.metric_meters["Acc@1"].update(a1, n)
+            st.metric_meters["Acc@5"].update(a5, n)
         pending.clear()
 
     def fit(self, loader, steps_per_epoch=None, val_loader=None, val_steps=None, epochs=1, start_epoch=0):

@@ -185,6 +185,48 @@ def test_optimizer_state_survives_an_arena_rebuild():
         assert torch.allclose(opt.state[p]["momentum_buffer"], torch.full_like(p, 0.9)), p.shape
 
 
+def test_graph_step_replays_match_eager_and_follow_the_lr_schedule():
+    """runner.GraphStep: the whole training step captured once per input signature and replayed;
+    a per-batch LR change (PhasesScheduler) must take effect across replays (the optimizer reads
+    its hyper-parameters from a persistent device table, optimizers.SGD.sync_hyperparams)."""
+    from sota_imagenet_b200 import losses, models, optimizers, runner
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(8, 3, 64, 64, device="cuda", generator=g)
+    y = torch.randint(0, 16, (8,), device="cuda", generator=g)
+    crit = losses.CrossEntropyLoss(smoothing=0.1)
+    nets, opts = [], []
+    for _ in range(2):
+        torch.manual_seed(0)
+        net = models.resnet26(num_classes=16).cuda().train()
+        nets.append(net)
+        opts.append(optimizers.SGD(net.parameters(), lr=0.02, momentum=0.9, weight_decay=1e-4, nesterov=True))
+    gs = runner.GraphStep(nets[0], crit, opts[0])
+    eager = runner.GraphStep(nets[1], crit, opts[1], enabled=False)
+    lrs = [0.02, 0.02, 0.02, 0.01, 0.0, 0.03]
+    for i, lr in enumerate(lrs):
+        before = nets[0].fc.weight.detach().clone()
+        for o in opts:
+            o.param_groups[0]["lr"] = lr
+        l0 = gs(x, y)[0].item()
+        l1 = eager(x, y)[0].item()
+        assert abs(l0 - l1) / abs(l1) < 3e-2, (i, l0, l1)
+        changed = not torch.equal(before, nets[0].fc.weight.detach())
+        assert changed == (lr != 0.0), (i, lr)          # lr = 0 inside a replay: weights stay put
+    assert gs.replays == len(lrs) - runner.GraphStep.WARMUP and eager.replays == 0
+    a, b = nets[0].fc.weight.detach().float(), nets[1].fc.weight.detach().float()
+    assert float((a - b).norm() / b.norm()) < 2e-2
+    # a new input signature (progressive resize) captures its own graph
+    x2 = torch.randn(8, 3, 96, 96, device="cuda", generator=g)
+    for _ in range(4):
+        gs(x2, y)
+    assert len(gs.graphs) == 2 and gs.replays == len(lrs) - 2 + 2
+    # Runner drives it and the meters get loss / accuracy from the replayed step
+    run = runner.Runner(nets[0], opts[0], crit, callbacks=[runner.PhasesScheduler([dict(ep=(0, 1), lr=(0.02, 0.0), mode="cos")])])
+    loader = [(x, y)] * 6
+    loss, metrics = run._run_loader(loader, train=True)
+    assert run.graph_step.replays >= 4 and 0 < loss < 10 and 0 <= metrics["Acc@1"] <= 100
+
+
 def test_cuda_graph_capture_while_previous_loss_is_alive():
     """A training loop that keeps `loss` around (logging) must still capture: the autograd glue may
     not cache a leaf whose AccumulateGrad node stays bound to the eager steps' stream
