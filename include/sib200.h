@@ -285,6 +285,22 @@ int sib_val_transform_ragged(const void* packed_u8, const long* offsets_dev, con
                              void* out, int B, int S, int resize_shorter, float mean, float std,
                              int out_mode, void* stream);
 int sib_one_hot(const long* labels, float* out, int B, int C, void* stream);
+/* Per-sample photometric augmentations of the resident batch (the output of sib_augment): replaces
+ * fn.color_twist / fn.hsv(saturation=0) / fn.erase of the reference's train_pipeline
+ * (dali_dataloader.py:86-111).  In place.  params[N][16 + 4 * nboxes] fp32 per sample:
+ *   [0..8] 3x3 colour matrix, [9..11] offset (both already expressed in NORMALISED space),
+ *   [12] lower / [13] upper clamp (the normalised images of 0 and 255), [14] grayscale flag,
+ *   [15] erase fill value, then nboxes x (h1, w1, h2, w2) erase boxes in UN-mirrored pixel
+ *   coordinates (an empty box erases nothing).  crop_boxes (optional): the int32 [N][5] boxes of
+ *   sib_rrc_boxes; samples with the flip flag get their erase boxes mirrored.
+ * layout 0: bf16 NHWC, 4 channels (4th stays 0); layout 1: fp32 NCHW, 3 channels. */
+int sib_pixel_ops(void* x, const float* params, const int* crop_boxes, int N, int H, int W, int layout,
+                  int nboxes, void* stream);
+/* fn.gaussian_blur(window_size=11, sigma) of dali_dataloader.py:81-83 on the resident batch, out of
+ * place; sigma[N] fp32 per sample, sigma <= 0 copies the sample through.  Border: reflect-101. */
+int sib_gaussian_blur(const void* x, void* y, const float* sigma, int N, int H, int W, int layout,
+                      void* stream);
+
 /* batch-level mixing on the resident batch: pt_clb.Mixup / pt_clb.Cutmix as combined by
  * CutmixMixup (sota_imagenet/callbacks.py:232-247).  layout 0: NHWC bf16 [N][H][W][C], 1: NCHW
  * fp32; mode 0: out = lam*x + one_minus_lam*prev[perm[n]]; mode 1: out = prev[perm[n]] inside

@@ -191,3 +191,67 @@ def val_transform_image(img, size, resize_shorter, mean=127.5, std=51.0):
                     ws += w
             out[oy, ox] = (acc / ws - mean) / std
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Photometric augmentations of the resident batch (reference dali_dataloader.py:81-111:
+# fn.gaussian_blur / fn.color_twist / fn.hsv(saturation=0) / fn.erase).  DALI itself is absent
+# (parity unpinned); these restate the operators as the affine maps their documentation gives,
+# evaluated on the NORMALISED values like the CUDA kernels (csrc/batchaug.cu).
+# ---------------------------------------------------------------------------------------------
+def pixel_ops(x, params, flips, nboxes):
+    """x: float array [N, H, W, 3] (normalised values); params: [N, 16 + 4 * nboxes] as produced
+    by data.BatchPixelAug.draw; flips: [N] bool (crop was mirrored).  Returns the transformed
+    array (float32 arithmetic in the kernel's operation order)."""
+    x = np.asarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    n, h, w, _ = x.shape
+    for i in range(n):
+        p = params[i].astype(np.float32)
+        m, o = p[0:9].reshape(3, 3), p[9:12]
+        v = x[i]
+        y = np.empty_like(v)
+        for c in range(3):
+            t = np.float32(m[c, 0]) * v[..., 0] + o[c]
+            t = np.float32(m[c, 1]) * v[..., 1] + t
+            t = np.float32(m[c, 2]) * v[..., 2] + t
+            y[..., c] = np.minimum(np.maximum(t, p[12]), p[13])
+        if p[14] != 0:
+            g = np.float32(0.299) * y[..., 0]
+            g = np.float32(0.587) * y[..., 1] + g
+            g = np.float32(0.114) * y[..., 2] + g
+            y[...] = g[..., None]
+        for b in range(nboxes):
+            h1, w1, h2, w2 = (int(q) for q in p[16 + 4 * b:20 + 4 * b])
+            if flips[i]:
+                w1, w2 = w - w2, w - w1
+            y[h1:h2, w1:w2, :] = p[15]
+        out[i] = y
+    return out
+
+
+def _reflect101(i, n):
+    if n == 1:
+        return 0
+    while i < 0 or i >= n:
+        i = -i if i < 0 else 2 * (n - 1) - i
+    return i
+
+
+def gaussian_blur11(x, sigma):
+    """Separable 11-tap Gaussian with reflect-101 borders per sample; sigma <= 0 copies through.
+    x: [N, H, W, 3] float."""
+    x = np.asarray(x, dtype=np.float64)
+    out = x.copy()
+    n, h, w, _ = x.shape
+    for i in range(n):
+        if sigma[i] <= 0:
+            continue
+        k = np.arange(-5, 6)
+        wt = np.exp(-(k.astype(np.float64) ** 2) / (2.0 * float(sigma[i]) ** 2))
+        wt /= wt.sum()
+        rows = np.array([[_reflect101(r + d, h) for d in k] for r in range(h)])
+        cols = np.array([[_reflect101(c + d, w) for d in k] for c in range(w)])
+        hor = np.einsum("hwkc,k->hwc", x[i][:, cols, :], wt)
+        out[i] = np.einsum("hkwc,k->hwc", hor[rows, :, :], wt)
+    return out

@@ -70,6 +70,38 @@ def heads():
     torch.save(out, os.path.join(OUT, "heads.pt"))
 
 
+def sphere_mlp():
+    """Reference SphereMLPLayer (angular_losses.py:217-245): train-mode forward / backward and the
+    validation forward of the class itself, bf16-representable inputs and FC weights."""
+    ang, _, RefCE = load_reference_modules()
+    torch.manual_seed(3)
+    b, d, c, hid = 32, 64, 40, 128
+    out = {}
+    for act in ("relu", "hswish"):
+        layer = ang.SphereMLPLayer(d, c, hidden_size=hid, act=act)
+        with torch.no_grad():
+            for p in layer.projector.parameters():
+                if p.dim() == 2:
+                    p.copy_(p.bfloat16().float())
+            layer.projector[1].weight.uniform_(0.5, 1.5)
+            layer.projector[1].bias.normal_(0, 0.2)
+        x = torch.randn(b, d).bfloat16().float()
+        g = torch.randn(b, c)
+        sd = {k: v.clone() for k, v in layer.state_dict().items()}
+        layer.train()
+        xr = x.clone().requires_grad_(True)
+        cos = layer(xr)
+        cos.backward(g)
+        rec = {"state_dict": sd, "x": x, "g": g, "cos_train": cos.detach(), "dx": xr.grad.clone(),
+               "grads": {n: p.grad.clone() for n, p in layer.named_parameters()},
+               "running_mean": layer.projector[1].running_mean.clone(),
+               "running_var": layer.projector[1].running_var.clone()}
+        layer.eval()
+        rec["cos_eval"] = layer(x).detach()
+        out[act] = rec
+    torch.save(out, os.path.join(OUT, "sphere_mlp.pt"))
+
+
 def cross_entropy():
     torch.manual_seed(1)
     b, c = 12, 50
@@ -222,4 +254,5 @@ if __name__ == "__main__":
     resnet_step()
     heads_arccos()
     novograd()
+    sphere_mlp()
     print("golden vectors written to", os.path.abspath(OUT))

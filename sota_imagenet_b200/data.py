@@ -35,13 +35,97 @@ class GpuAugment:
         return ops.rrc_boxes(batch, src_h, src_w, self.min_area, self.max_area, self.seed,
                              first_sample, self.flip, device)
 
-    def __call__(self, src_u8, first_sample=0):
+    def __call__(self, src_u8, first_sample=0, return_boxes=False):
         """src_u8: [B, H, W, 3] uint8 CUDA.  Returns the model input (bf16 channels_last
         [B,4,S,S] with a zero 4th channel, or fp32 NCHW [B,3,S,S] like DALI emits)."""
         b, h, w, _ = src_u8.shape
         bx = self.boxes(b, h, w, first_sample, src_u8.device)
-        return ops.augment(src_u8, bx, self.image_size, DATA_MEAN, DATA_STD,
-                           0 if self.output == "nhwc4_bf16" else 1)
+        out = ops.augment(src_u8, bx, self.image_size, DATA_MEAN, DATA_STD,
+                          0 if self.output == "nhwc4_bf16" else 1)
+        return (out, bx) if return_boxes else out
+
+
+_RGB2YIQ = ((0.299, 0.587, 0.114), (0.596, -0.274, -0.321), (0.211, -0.523, 0.311))
+
+
+def color_twist_matrix(contrast=1.0, brightness=1.0, hue_deg=0.0, saturation=1.0):
+    """fn.color_twist as ONE affine map of the uint8 pixel: hue / saturation = a rotation + scaling
+    of the chroma plane in YIQ, then out = brightness * (128 + contrast * (. - 128)).
+    -> (A [3,3], t [3]) float64 with out = A @ rgb + t (before the [0, 255] clamp)."""
+    import numpy as np
+    m = np.array(_RGB2YIQ, dtype=np.float64)
+    h = math.radians(hue_deg)
+    rot = np.array([[1.0, 0.0, 0.0], [0.0, saturation * math.cos(h), -saturation * math.sin(h)],
+                    [0.0, saturation * math.sin(h), saturation * math.cos(h)]])
+    a = brightness * contrast * (np.linalg.inv(m) @ rot @ m)
+    t = np.full(3, brightness * 128.0 * (1.0 - contrast))
+    return a, t
+
+
+class BatchPixelAug:
+    """The photometric part of the reference's train_pipeline (dali_dataloader.py:81-111) on the
+    resident, already normalised batch: gaussian blur (prob blur_prob, sigma ~ U(0.5, 1.1), window
+    11), colour twist (prob color_twist_prob; contrast / brightness from their ranges, hue ~ U(-20,
+    20) degrees, saturation ~ U(0.7, 1.3)), grayscale (prob gray_prob), random erasing (prob re_prob,
+    re_count boxes, anchor ~ U(0, 1), extent ~ U(0.05, 0.25) of the image, fill = DATA_MEAN).
+    Per-sample parameters come from a host numpy stream seeded by (seed, batch index) -- the numpy
+    oracle (oracle/augment_ref.py) consumes the same table -- and travel as one small H2D copy; the
+    pixels never leave the device.  DALI keeps uint8 between the operators; here the chain is
+    evaluated in fp32 on the normalised values and rounded once (restated, unpinned: DALI is absent)."""
+
+    def __init__(self, cfg, seed=0):
+        self.blur_prob = float(getattr(cfg, "blur_prob", 0) or 0)
+        self.twist_prob = float(getattr(cfg, "color_twist_prob", 0) or 0)
+        self.gray_prob = float(getattr(cfg, "gray_prob", 0) or 0)
+        self.re_prob = float(getattr(cfg, "re_prob", 0) or 0)
+        self.re_count = int(getattr(cfg, "re_count", 3) or 0) if self.re_prob > 0 else 0
+        self.contrast_range = tuple(getattr(cfg, "contrast_range", (0.7, 1.3)))
+        self.brightness_range = tuple(getattr(cfg, "brightness_range", (0.7, 1.3)))
+        self.seed = seed
+
+    @property
+    def active(self):
+        return self.blur_prob > 0 or self.twist_prob > 0 or self.gray_prob > 0 or self.re_prob > 0
+
+    def draw(self, batch, size, batch_index):
+        """-> (sigma [B] float32, params [B, 16 + 4 * re_count] float32) numpy arrays."""
+        import numpy as np
+        rng = np.random.RandomState((self.seed * 1000003 + batch_index * 7919 + 17) & 0x7FFFFFFF)
+        sigma = np.zeros(batch, dtype=np.float32)
+        params = np.zeros((batch, 16 + 4 * self.re_count), dtype=np.float32)
+        lo, hi = (0.0 - DATA_MEAN) / DATA_STD, (255.0 - DATA_MEAN) / DATA_STD
+        for i in range(batch):
+            if self.blur_prob > 0 and rng.rand() < self.blur_prob:
+                sigma[i] = rng.uniform(0.5, 1.1)
+            a, t = np.eye(3), np.zeros(3)
+            if self.twist_prob > 0 and rng.rand() < self.twist_prob:
+                a, t = color_twist_matrix(rng.uniform(*self.contrast_range), rng.uniform(*self.brightness_range),
+                                          rng.uniform(-20.0, 20.0), rng.uniform(0.7, 1.3))
+            # the same map on normalised values x = (v - mean) / std
+            params[i, 0:9] = a.reshape(-1)
+            params[i, 9:12] = (a @ np.full(3, DATA_MEAN) + t - DATA_MEAN) / DATA_STD
+            params[i, 12], params[i, 13] = lo, hi
+            params[i, 14] = 1.0 if (self.gray_prob > 0 and rng.rand() < self.gray_prob) else 0.0
+            params[i, 15] = 0.0                               # erase fill = DATA_MEAN -> 0 after normalisation
+            if self.re_count and rng.rand() < self.re_prob:
+                anchor = rng.uniform(0.0, 1.0, size=2 * self.re_count)
+                shape = rng.uniform(0.05, 0.25, size=2 * self.re_count)
+                for b in range(self.re_count):
+                    h1, w1 = int(anchor[2 * b] * size), int(anchor[2 * b + 1] * size)
+                    h2 = min(size, int((anchor[2 * b] + shape[2 * b]) * size))
+                    w2 = min(size, int((anchor[2 * b + 1] + shape[2 * b + 1]) * size))
+                    params[i, 16 + 4 * b:20 + 4 * b] = (h1, w1, h2, w2)
+        return sigma, params
+
+    def __call__(self, x, crop_boxes, batch_index):
+        if not self.active:
+            return x
+        sigma, params = self.draw(x.shape[0], x.shape[2], batch_index)
+        if self.blur_prob > 0 and float(sigma.max()) > 0:
+            x = ops.gaussian_blur(x, torch.from_numpy(sigma).to(x.device, non_blocking=True))
+        if self.twist_prob > 0 or self.gray_prob > 0 or self.re_count:
+            ops.pixel_ops_(x, torch.from_numpy(params).to(x.device, non_blocking=True), crop_boxes, self.re_count)
+        return x
 
 
 class GpuValTransform:
@@ -132,6 +216,7 @@ class SyntheticLoader:
                                       seed=getattr(cfg, "seed", 0), flip=True, output=output)
         else:
             self.augment = GpuValTransform(cfg.image_size, getattr(cfg, "full_crop", False), output)
+        self.pixel_aug = BatchPixelAug(cfg, seed=getattr(cfg, "seed", 0)) if train else None
         self._epoch = 0
 
     def __len__(self):
@@ -146,7 +231,11 @@ class SyntheticLoader:
             if not imgs.is_cuda:
                 imgs = imgs.to(self.device, non_blocking=True)
                 labels = labels.to(self.device, non_blocking=True)
-            data = self.augment(imgs, first_sample=gi * self.batch_size)
+            if self.pixel_aug is not None and self.pixel_aug.active:
+                data, bx = self.augment(imgs, first_sample=gi * self.batch_size, return_boxes=True)
+                data = self.pixel_aug(data, bx, gi)
+            else:
+                data = self.augment(imgs, first_sample=gi * self.batch_size)
             target = ops.one_hot(labels, self.num_classes) if self.one_hot else labels
             yield data, target
         self._epoch += 1
@@ -170,6 +259,8 @@ class RecordLoader:
         full_crop = getattr(cfg, "full_crop", False)
         self.crop_size = self.image_size if full_crop else math.ceil((self.image_size * 1.14 + 8) // 16 * 16)
         self.decode_workers = decode_workers
+        self.pixel_aug = BatchPixelAug(cfg, seed=self.seed) if train else None
+        self._batches = 0
         # global sample counter of the crop / flip Philox stream: epoch * dataset + position, offset by
         # the shard so that ranks draw different randoms; carried across loader rebuilds by DataManager
         self.rank = getattr(reader, "shard_id", 0)
@@ -191,6 +282,9 @@ class RecordLoader:
             boxes = ops.rrc_boxes_ragged(dims, self.min_area, 1.0, self.seed, first, True)
             data = ops.augment_ragged(buf, offsets, dims, boxes, self.image_size, DATA_MEAN, DATA_STD,
                                       self.out_mode)
+            if self.pixel_aug is not None and self.pixel_aug.active:
+                data = self.pixel_aug(data, boxes, self._batches * self.world + self.rank)
+            self._batches += 1
         else:
             data = ops.val_transform_ragged(buf, offsets, dims, self.image_size, self.crop_size,
                                             DATA_MEAN, DATA_STD, self.out_mode)
@@ -274,12 +368,12 @@ class DataManager:
             for key, value in self.stages[idx].extra_args.items():
                 setattr(train_cfg, key, value)
         val_cfg.image_size = train_cfg.image_size
-        unsupported = [k for k in ("blur_prob", "random_interpolation")
-                       if getattr(train_cfg, k, 0)]
+        unsupported = [k for k in ("random_interpolation",) if getattr(train_cfg, k, 0)]
         if unsupported:
             import warnings
             warnings.warn("sota_imagenet_b200.data: augmentation fields %s of the reference train_pipeline "
-                          "(dali_dataloader.py:75-83) are not implemented and are ignored" % unsupported)
+                          "(dali_dataloader.py:75-79: a coin flip between cubic and triangular resampling) are not implemented "
+                          "and are ignored" % unsupported)
         root = real_data_root(train_cfg) if self.source is None else None
         prev_epoch = getattr(self.loader, "_epoch", 0) if self.loader is not None else 0
         if root is not None:

@@ -100,6 +100,41 @@ class SphereLinearLayer(nn.Module):
         return sphere_linear(x, self.weight)
 
 
+class SphereMLPLayer(nn.Module):
+    """Reference angular_losses.py:217-245: in training mode (or with `val_projector`) the
+    embedding first goes through a projector FC(no bias) - BatchNorm1d - act - FC, then
+    cos = normalize(.) . normalize(W)^T; in validation only the cosine layer.  Same parameter names
+    (`weight`, `projector.{0,1,3}.*`), so checkpoints interchange.  The two FCs run on the tcgen05
+    1x1-conv kernel, BatchNorm + ReLU on the fused NHWC kernels (statistics over the batch dimension
+    = BatchNorm1d), the cosine layer on the sphere-linear kernels; `hswish` runs the activation as
+    a torch op between two fused modules."""
+
+    def __init__(self, embedding_size, num_classes, hidden_size=4096, act="relu", val_projector=False):
+        super().__init__()
+        from .modules import BatchNorm2d, Linear
+        if act not in ("relu", "hswish"):
+            raise _lib.SibError("SphereMLPLayer: act must be 'relu' or 'hswish'")
+        self.register_parameter("weight", nn.Parameter(torch.zeros(num_classes, embedding_size)))
+        nn.init.xavier_uniform_(self.weight)
+        self.projector = nn.Sequential(
+            Linear(embedding_size, hidden_size, bias=False),
+            BatchNorm2d(hidden_size, activation="relu" if act == "relu" else "identity"),
+            nn.Identity() if act == "relu" else nn.Hardswish(),
+            Linear(hidden_size, embedding_size),
+        )
+        self.val_projector = val_projector
+
+    def forward(self, x):
+        if self.training or self.val_projector:
+            fc1, bn, act, fc2 = self.projector
+            h = fc1(x.to(torch.bfloat16).reshape(x.shape[0], x.shape[1], 1, 1))
+            h = bn(h.reshape(h.shape[0], h.shape[1], 1, 1))
+            if not isinstance(act, nn.Identity):
+                h = act(h.float()).to(torch.bfloat16)
+            x = fc2(h.reshape(h.shape[0], h.shape[1], 1, 1))
+        return sphere_linear(x, self.weight)
+
+
 def _smoothing_of(criterion):
     """Extract (smoothing, temperature) from a `final_criterion` the reference would pass."""
     if criterion is None:

@@ -804,6 +804,36 @@ def mix_batch(x, prev, perm, mode, lam=1.0, one_minus_lam=0.0, box=(0, 0, 0, 0))
     return out
 
 
+def _aug_layout(x):
+    if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] == 4 and x.permute(0, 2, 3, 1).is_contiguous():
+        return 0
+    if x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and x.is_contiguous():
+        return 1
+    raise _lib.SibError("batch augmentation: bf16 channels_last [N,4,H,W] or fp32 NCHW [N,3,H,W] expected")
+
+
+def pixel_ops_(x, params, crop_boxes=None, nboxes=0):
+    """Colour twist / grayscale / random erasing of the resident batch, in place (csrc/batchaug.cu).
+    params: fp32 [N, 16 + 4 * nboxes] on the device; crop_boxes: the int32 [N, 5] boxes of rrc_boxes."""
+    _lib.require_device()
+    n, _, h, w = x.shape
+    if params.dtype != torch.float32 or not params.is_cuda or tuple(params.shape) != (n, 16 + 4 * nboxes):
+        raise _lib.SibError("pixel_ops: params must be a CUDA fp32 tensor [N, 16 + 4 * nboxes]")
+    call("sib_pixel_ops", _p(x), _p(params.contiguous()), _p(crop_boxes), n, h, w, _aug_layout(x), nboxes, _stream())
+    return x
+
+
+def gaussian_blur(x, sigma):
+    """11-tap Gaussian blur per sample (sigma fp32 [N] on the device, <= 0: copied through)."""
+    _lib.require_device()
+    n, _, h, w = x.shape
+    out = torch.empty_like(x)
+    if x.dtype == torch.bfloat16:
+        out.zero_()                  # the zero 4th channel
+    call("sib_gaussian_blur", _p(x), _p(out), _p(sigma.contiguous()), n, h, w, _aug_layout(x), _stream())
+    return out
+
+
 def mix_targets(t, prev_t, perm, w_self, w_prev):
     _lib.require_device()
     if t.dtype != torch.float32 or prev_t.dtype != torch.float32 or t.shape != prev_t.shape:
