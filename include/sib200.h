@@ -194,9 +194,22 @@ int sib_chan_reduce(const void* a, const void* b, float* out, int N, int HW, int
 /* y[n][hw][c] = x[n][hw][c] * mul[n][c] (+ add[n][c]) */
 int sib_scale_nc(const void* x, const float* mul, const float* add, void* y, int N, int HW, int C,
                  void* stream);
-/* y = act(x * mul[n][c] + res): BResNet block tail (ECA gate, drop-connect, shortcut, activation) */
-int sib_scale_add_act(const void* x, const float* mul, const void* res, void* y, int N, int HW,
-                      int C, int act, float slope, void* stream);
+/* y = act(x * mul[n][c] (+ add[n][c]) + res): BResNet block tail (ECA gate, drop-connect, shortcut,
+ * activation).  With `add` (optional) x may be the RAW output of the block's last conv: mul / add
+ * then carry its BatchNorm scale / shift times the gate, and the normalised tensor is never written. */
+int sib_scale_add_act(const void* x, const float* mul, const float* add, const void* res, void* y,
+                      int N, int HW, int C, int act, float slope, void* stream);
+/* Block-tail backward in one pass: g = dy * act'(y) (written; also the shortcut gradient) and per
+ * (sample, channel) s1[N][C] = sum_hw g, s2[N][C] = sum_hw g * x.  Replaces act_bwd + chan_reduce(g, x)
+ * (the ECA gate's backward input, reference model graph: pytorch_tools ECA inside Bottleneck). */
+int sib_act_bwd_reduce(const void* dy, const void* y, const void* x, void* g, float* s1, float* s2,
+                       int N, int HW, int C, int act, float slope, void* stream);
+/* sib_bn_bwd_apply for an activation-free BatchNorm whose incoming gradient is
+ * dy * dy_mul[n][c] + dy_add[n][c]: the gate scale of the block tail folded into the BN backward. */
+int sib_bn_bwd_apply_scaled(const void* dy, const float* dy_mul, const float* dy_add, const void* x,
+                            const float* mean_invstd, const float* gamma, const float* sums, void* dx,
+                            float* dgamma, float* dbeta, int N, int HW, int C, double count,
+                            float pgrad_scale, void* stream);
 int sib_eca_gate_fwd(const float* p, const float* w, float* s, int N, int C, void* stream);
 int sib_eca_gate_bwd(const float* ds, const float* s, const float* p, const float* w, float* dp,
                      float* dw, int N, int C, void* stream);

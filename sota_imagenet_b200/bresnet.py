@@ -159,15 +159,33 @@ class BNAct(BatchNorm2d):
 
     def fwd(self, x, train, stats=None):
         n, c, h, w = x.shape
-        if train and stats is None:
+        if not train:
+            mi, ss, count = self.finalize(None, n * h * w, False)
+            return ops.bn_apply(x, ss, self.act, self.slope), (x, mi, count, ss)
+        if stats is None:
             stats = ops.bn_stats(x)
-        mi, ss, count = self.finalize(stats, n * h * w, train)
-        y = ops.bn_apply(x, ss, self.act, self.slope)
+        # finalize (+ running statistics) and apply in ONE launch (was bn_finalize + bn_apply)
+        args, world = self.stats_args(stats)
+        count = n * h * w * world
+        y, (mi, ss), _ = ops.bn_finalize_apply(x, args, act=self.act, slope=self.slope, count=count,
+                                               eps=self.eps, momentum=self.momentum)
         return y, (x, mi, count, ss)
 
-    def bwd(self, dy, saved, need_dx=True):
+    def fuse_info(self, saved):
+        """What a dgrad needs to fuse this BatchNorm's backward reduction (and activation mask) into
+        its epilogue (ops.conv2d_dgrad bn_bwd=...)."""
+        x, mi, count, ss = saved
+        return dict(mask_src=x, mask_ss=ss, mean_invstd=mi, act=self.act, slope=self.slope)
+
+    def bwd(self, dy, saved, need_dx=True, sums=None):
+        """`sums` given: dy is already masked by this BN's activation and (sum g, sum g*xhat) come
+        from the producing dgrad's epilogue -- the separate reduction pass is skipped."""
         x, mi, count, ss = saved
         dy = _as_act(dy)
+        if sums is not None:
+            dx, _, _ = ops.bn_bwd_apply(dy, None, x, mi, self.weight.data, self.reduce_sums(sums), count,
+                                        ops.ACT_NONE, 0.0, param_grads=self.grad_ptrs())
+            return dx
         sums = self.reduce_sums(ops.bn_bwd_reduce(dy, None, x, mi, self.act, self.slope, mask_ss=ss))
         dx, _, _ = ops.bn_bwd_apply(dy, None, x, mi, self.weight.data, sums, count, self.act, self.slope,
                                     mask_ss=ss, param_grads=self.grad_ptrs())
@@ -192,6 +210,14 @@ FUSE_DROP_CONNECT = os.environ.get("SIB_FUSE_DROP_CONNECT", "1") != "0"
 # Apply the ECA gate inside the shortcut-add + activation pass (act(x*gate + r) in one kernel: the
 # gated tensor is never written); SIB_FUSE_ECA_TAIL=0 keeps scale_nc + add_act.
 FUSE_ECA_TAIL = os.environ.get("SIB_FUSE_ECA_TAIL", "1") != "0"
+FUSE_BN_BWD = os.environ.get("SIB_FUSE_BN_BWD", "1") != "0"
+# Block tail without the normalised bn3 output: the ECA gate pools the RAW conv3 output (BatchNorm is
+# affine per channel, so mean_hw(bn3(c3)) = scale * mean_hw(c3) + shift), the output pass computes
+# act(c3 * (scale * gate) + shift * gate + shortcut) straight from c3, and in backward ONE pass yields
+# the masked gradient plus the per-(sample, channel) sums from which both the gate's gradient and the
+# BatchNorm-backward sums follow algebraically; the gate scale rides inside bn_bwd_apply.  12 passes
+# over the widest tensor of the block become 7.  SIB_FUSE_BN3_TAIL=0 restores the operator sequence.
+FUSE_BN3_TAIL = os.environ.get("SIB_FUSE_BN3_TAIL", "1") != "0"
 
 
 class ECA(SibModule):
@@ -269,6 +295,9 @@ class BBottleneck(SibModule):
         a2b = a2
         if self.blur is not None:
             a2b, sb = self.blur.fwd(a2, train)
+        fused_tail = train and self.eca is not None and FUSE_BN3_TAIL
+        if fused_tail:
+            return self._fwd_fused_tail(x, a1, s1, a2, s2, a2b, sb)
         y3, s3 = self._conv_bn(self.conv3, self.bn3, a2b, train)
         se = None
         mask = None
@@ -300,23 +329,95 @@ class BBottleneck(SibModule):
             return out, None
         return out, (x, a1, s1, a2, s2, a2b, sb, s3, se, mask, xs, sd, out)
 
+    def _shortcut(self, x, train):
+        xs, sd = x, None
+        if self.downsample is not None:
+            if self.pool_shortcut:
+                xs = ops.avgpool2_fwd(x)
+            r, sd = self._conv_bn(self.downsample[0], self.downsample[1], xs, train)
+        else:
+            r = x
+        return r, xs, sd
+
+    def _fwd_fused_tail(self, x, a1, s1, a2, s2, a2b, sb):
+        """Training forward of conv3 .. block output without materialising bn3's output (see
+        FUSE_BN3_TAIL)."""
+        bn3 = self.bn3
+        st3 = ops.new_acc(2, self.conv3.out_channels, x.device)
+        c3 = self.conv3.run(a2b, st3)
+        n, c, h, w = c3.shape
+        args, world = bn3.stats_args(st3)
+        cnt3 = n * h * w * world
+        mi3, ss3 = ops.bn_finalize(*args, cnt3, bn3.eps, bn3.momentum)
+        pc = ops.chan_reduce(c3, scale=1.0 / (h * w))              # mean_hw of the raw conv output
+        p = torch.addcmul(ss3[1], pc, ss3[0])                       # = mean_hw(bn3(c3)): what ECA pools
+        gate = ops.eca_gate_fwd(p, self.eca.weight.data.view(3).contiguous())
+        if self.keep_prob < 1.0:
+            keep = (torch.rand(n, 1, device=c3.device) < self.keep_prob).float() / self.keep_prob
+            gate_k = gate * keep
+        else:
+            keep, gate_k = None, gate
+        r, xs, sd = self._shortcut(x, True)
+        out = ops.scale_add_act(c3, gate_k * ss3[0], r, self.act, self.bn1.slope, add=gate_k * ss3[1])
+        tail = (c3, mi3, ss3, cnt3, pc, p, gate, gate_k, keep)
+        return out, (x, a1, s1, a2, s2, a2b, sb, ("fused", tail), None, None, xs, sd, out)
+
+    def _bwd_fused_tail(self, dout, out, tail):
+        """-> g (masked block-output gradient = shortcut gradient), dc3."""
+        c3, mi3, ss3, cnt3, pc, p, gate, gate_k, keep = tail
+        bn3 = self.bn3
+        n, c, h, w = c3.shape
+        hw = float(h * w)
+        g, s1, s2 = ops.act_bwd_reduce(_as_act(dout), out, c3, self.act, self.bn1.slope)
+        mean, invstd = mi3[0], mi3[1]
+        # ECA: gated = y3 * gate * keep, y3 = c3 * scale + shift  =>  d/d(gate) = keep * sum_hw g * y3
+        ds = torch.addcmul(ss3[1] * s1, s2, ss3[0])
+        if keep is not None:
+            ds = ds * keep
+        dw = torch.zeros(3, dtype=torch.float32, device=c3.device)
+        dp = ops.eca_gate_bwd(ds.contiguous(), gate, p, self.eca.weight.data.view(3).contiguous(), dw)
+        self.eca._grad(self.eca.weight).view(3).add_(dw)
+        add_nc = dp / hw                                         # pooled path, broadcast over (h, w)
+        # BatchNorm-backward sums of d = g * gate_k + add_nc, from the per-(sample, channel) sums
+        gx = invstd * (s2 - mean * s1)                           # sum_hw g * xhat
+        xh = invstd * hw * (pc - mean)                           # sum_hw xhat
+        sums = torch.stack([(gate_k * s1 + add_nc * hw).sum(0), (gate_k * gx + add_nc * xh).sum(0)]).contiguous()
+        sums = bn3.reduce_sums(sums)
+        dc3 = ops.bn_bwd_apply_scaled(g, gate_k.contiguous(), add_nc.contiguous(), c3, mi3, bn3.weight.data, sums,
+                                      cnt3, param_grads=bn3.grad_ptrs())
+        return g, dc3
+
     def bwd(self, dout, saved, need_dx=True):
         x, a1, s1, a2, s2, a2b, sb, s3, se, mask, xs, sd, out = saved
-        g = ops.act_bwd(_as_act(dout), out, self.act, self.bn1.slope)
-        d = g
-        if mask is not None and not (se is not None and len(se) > 3):   # else folded into the ECA gate
-            d = ops.scale_nc(d, mask)
-        if self.eca is not None:
-            d = self.eca.bwd(d, se)
-        dc3 = self.bn3.bwd(d, s3)
+        if isinstance(s3, tuple) and len(s3) == 2 and s3[0] == "fused":
+            g, dc3 = self._bwd_fused_tail(dout, out, s3[1])
+        else:
+            g = ops.act_bwd(_as_act(dout), out, self.act, self.bn1.slope)
+            d = g
+            if mask is not None and not (se is not None and len(se) > 3):   # else folded into the ECA gate
+                d = ops.scale_nc(d, mask)
+            if self.eca is not None:
+                d = self.eca.bwd(d, se)
+            dc3 = self.bn3.bwd(d, s3)
         self.conv3.run_wgrad(a2b, dc3)
-        d = self.conv3.run_dgrad(dc3, tuple(a2b.shape))
-        if self.blur is not None:
-            d = self.blur.bwd(d, sb)
-        dc2 = self.bn2.bwd(d, s2)
+        # BN-backward reduction + leaky mask fused into the dgrad epilogue that produces the gradient
+        # (same machinery as modules.Bottleneck; not across the blur-pool, not where it loses: the
+        # halo-reuse 3x3 kernel)
+        if FUSE_BN_BWD and self.blur is None:
+            d, sums = self.conv3.run_dgrad(dc3, tuple(a2b.shape), bn_bwd=self.bn2.fuse_info(s2))
+            dc2 = self.bn2.bwd(d, s2, sums=sums)
+        else:
+            d = self.conv3.run_dgrad(dc3, tuple(a2b.shape))
+            if self.blur is not None:
+                d = self.blur.bwd(d, sb)
+            dc2 = self.bn2.bwd(d, s2)
         self.conv2.run_wgrad(a1, dc2)
-        d = self.conv2.run_dgrad(dc2, tuple(a1.shape))
-        dc1 = self.bn1.bwd(d, s1)
+        if FUSE_BN_BWD and not ops.halo_applies(a1.shape[1], dc2.shape[1], 3, self.conv2.stride, a1.shape[3]):
+            d, sums = self.conv2.run_dgrad(dc2, tuple(a1.shape), bn_bwd=self.bn1.fuse_info(s1))
+            dc1 = self.bn1.bwd(d, s1, sums=sums)
+        else:
+            d = self.conv2.run_dgrad(dc2, tuple(a1.shape))
+            dc1 = self.bn1.bwd(d, s1)
         self.conv1.run_wgrad(x, dc1)
         if self.downsample is None:
             return self.conv1.run_dgrad(dc1, tuple(x.shape), residual=g) if need_dx else None

@@ -172,6 +172,74 @@ chan_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __r
   }
 }
 
+// Block-tail backward in one pass: g = dy * act'(y) is written out (it is also the shortcut
+// gradient) and, per (sample, channel), s1 = sum_hw g and s2 = sum_hw g * x are reduced -- what the
+// ECA gate's backward and (through them) the BatchNorm-backward sums of the block's last BN need.
+// Same CTA layout as chan_reduce_kernel; two rows in flight per thread.
+__global__ void __launch_bounds__(256)
+act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                      const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ g,
+                      float* __restrict__ s1, float* __restrict__ s2, int HW, int C, int act,
+                      float slope) {
+  __shared__ float red[2][32][8][8];
+  const int n = blockIdx.y;
+  const int v = blockIdx.x * 8 + (threadIdx.x & 7);
+  const int lane_row = threadIdx.x >> 3;
+  const int cvec = C >> 3;
+  float a1[8] = {}, a2[8] = {};
+  if (v < cvec) {
+    for (int t = lane_row; t < HW; t += 64) {
+      uint4 qd[2], qy[2], qx[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int tt = t + 32 * u;
+        if (tt < HW) {
+          const long off = (((long)n * HW + tt) * cvec + v) * 8;
+          qd[u] = ldg_stream(dy + off);
+          qy[u] = ldg_stream(y + off);
+          qx[u] = ldg_stream(x + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int tt = t + 32 * u;
+        if (tt < HW) {
+          const long off = (((long)n * HW + tt) * cvec + v) * 8;
+          float fd[8], fy[8], fx[8];
+          unpack8(qd[u], fd);
+          unpack8(qy[u], fy);
+          unpack8(qx[u], fx);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float gg = fd[j];
+            if (act == SIB_ACT_RELU) gg = fy[j] > 0.f ? gg : 0.f;
+            else if (act == SIB_ACT_LEAKY) gg = fy[j] > 0.f ? gg : gg * slope;
+            // sums of the values AS STORED (bf16), like every other statistic of the pipeline
+            gg = __bfloat162float(__float2bfloat16_rn(gg));
+            fd[j] = gg;
+            a1[j] += gg;
+            a2[j] = fmaf(gg, fx[j], a2[j]);
+          }
+          stg_stream(g + off, pack8(fd));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][lane_row][threadIdx.x & 7][j] = a1[j];
+    red[1][lane_row][threadIdx.x & 7][j] = a2[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int k = threadIdx.x >> 6, vv = (threadIdx.x >> 3) & 7, j = threadIdx.x & 7;
+    float s = 0.f;
+    for (int r = 0; r < 32; ++r) s += red[k][r][vv][j];
+    const int c = (blockIdx.x * 8 + vv) * 8 + j;
+    if (c < C) (k == 0 ? s1 : s2)[(long)n * C + c] = s;
+  }
+}
+
 // y[n][hw][c] = x * mul[n][c] (+ add[n][c])
 __global__ void __launch_bounds__(256)
 scale_nc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mul,
@@ -200,8 +268,8 @@ scale_nc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ m
 // (ECA gate * drop-connect keep, shortcut add, activation) in one pass
 __global__ void __launch_bounds__(256)
 scale_add_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mul,
-                     const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y, int N,
-                     int HW, int C, int act, float slope) {
+                     const float* __restrict__ add, const __nv_bfloat16* __restrict__ res,
+                     __nv_bfloat16* __restrict__ y, int N, int HW, int C, int act, float slope) {
   const int cvec = C >> 3;
   const long total = (long)N * HW * cvec;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -212,9 +280,12 @@ scale_add_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     unpack8(ldg_stream(x + i * 8), f);
     unpack8(ldg_stream(res + i * 8), r);
     const float* m = mul + n * C + v * 8;
+    const float* ad = add != nullptr ? add + n * C + v * 8 : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = fmaf(f[j], __ldg(m + j), r[j]);
+      // (x * mul + add) is the gated BatchNorm output when x is the RAW conv output and mul / add
+      // carry the BN scale / shift times the gate; then the shortcut is added
+      float t = ad != nullptr ? fmaf(f[j], __ldg(m + j), __ldg(ad + j)) + r[j] : fmaf(f[j], __ldg(m + j), r[j]);
       if (act == SIB_ACT_RELU) t = fmaxf(t, 0.f);
       else if (act == SIB_ACT_LEAKY) t = t > 0.f ? t : t * slope;
       f[j] = t;
@@ -416,6 +487,14 @@ extern "C" int sib_chan_reduce(const void* a, const void* b, float* out, int N, 
   SIB_LAUNCH_CHECK();
   return 0;
 }
+extern "C" int sib_act_bwd_reduce(const void* dy, const void* y, const void* x, void* g, float* s1,
+                                  float* s2, int N, int HW, int C, int act, float slope, void* stream) {
+  SIB_CHECK(C % 8 == 0, "act_bwd_reduce: C %% 8 != 0");
+  dim3 grid((C / 8 + 7) / 8, N);
+  act_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dy), CBF(y), CBF(x), BF(g), s1, s2, HW, C, act, slope);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
 extern "C" int sib_scale_nc(const void* x, const float* mul, const float* add, void* y, int N,
                             int HW, int C, void* stream) {
   SIB_CHECK(C % 8 == 0, "scale_nc: C %% 8 != 0");
@@ -424,11 +503,11 @@ extern "C" int sib_scale_nc(const void* x, const float* mul, const float* add, v
   SIB_LAUNCH_CHECK();
   return 0;
 }
-extern "C" int sib_scale_add_act(const void* x, const float* mul, const void* res, void* y, int N,
-                                 int HW, int C, int act, float slope, void* stream) {
+extern "C" int sib_scale_add_act(const void* x, const float* mul, const float* add, const void* res,
+                                 void* y, int N, int HW, int C, int act, float slope, void* stream) {
   SIB_CHECK(C % 8 == 0, "scale_add_act: C %% 8 != 0");
   scale_add_act_kernel<<<ew_grid((long)N * HW * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(x), mul, CBF(res), BF(y), N, HW, C, act, slope);
+      CBF(x), mul, add, CBF(res), BF(y), N, HW, C, act, slope);
   SIB_LAUNCH_CHECK();
   return 0;
 }

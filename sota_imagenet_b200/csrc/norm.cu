@@ -373,7 +373,10 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 //   EMIT_A: also rewrite the forward activation a = fwd_act(fmaf(x, scale, shift)) of this BatchNorm
 //   (x is in registers anyway): the fused conv prologue never stored it and the weight gradient
 //   of the consumer conv needs it.  +2 B/element written, no extra read.
-template <bool SECOND, bool USE_OUT, bool WRITE_G, bool EMIT_A = false>
+//   DYT: the incoming gradient is dy * dy_mul[n][c] + dy_add[n][c] (n = row / HW): the ECA gate
+//   (* drop-connect keep) and the gate's pooled-path gradient of the BResNet block tail, folded
+//   into this pass instead of a separate scale pass over the widest tensor of the block.
+template <bool SECOND, bool USE_OUT, bool WRITE_G, bool EMIT_A = false, bool DYT = false>
 __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ out,
                     const float* __restrict__ mask_ss, const __nv_bfloat16* __restrict__ x,
@@ -386,7 +389,9 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     float* __restrict__ dbeta2, long M, int C, float inv_count, int act,
                     float slope, float pg_scale, const float* __restrict__ emit_ss = nullptr,
                     int emit_act = 0, float emit_slope = 0.f,
-                    __nv_bfloat16* __restrict__ a_out = nullptr) {
+                    __nv_bfloat16* __restrict__ a_out = nullptr,
+                    const float* __restrict__ dy_mul = nullptr,
+                    const float* __restrict__ dy_add = nullptr, int HW = 1) {
   griddep_launch();
   griddep_wait();
   const ColOwner co(C);
@@ -466,6 +471,14 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
         float g[8], xv[8], d[8];
         unpack8(vg[u], g);
         unpack8(vx[u], xv);
+        if (DYT) {
+          const long nn = rr / HW;
+          float m[8], ad[8];
+          load8f(dy_mul + nn * C + col, m);
+          load8f(dy_add + nn * C + col, ad);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = fmaf(g[j], m[j], ad[j]);
+        }
         if (USE_OUT) {
           float o[8];
           unpack8(vo[u], o);
@@ -945,7 +958,8 @@ extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* ma
   SIB_CUDA(launch_pdl(bn_bwd_apply_kernel<S, O, G>, dim3(grid), dim3(kRedThreads), 0, ST(stream), \
       a, o, mask_ss, xp, mean_invstd, gamma, sums, xq, mean_invstd2, gamma2, d1, d2, gg, dgamma,   \
       dbeta, dgamma2, dbeta2, M, C, ic, act, slope, pgrad_scale, static_cast<const float*>(nullptr), 0, 0.f, \
-      static_cast<__nv_bfloat16*>(nullptr)))
+      static_cast<__nv_bfloat16*>(nullptr), static_cast<const float*>(nullptr),                     \
+      static_cast<const float*>(nullptr), 1))
   const bool use_out = out != nullptr && act != SIB_ACT_NONE;
   const bool wg = gout != nullptr;
   if (x2) {
@@ -956,6 +970,32 @@ extern "C" int sib_bn_bwd_apply(const void* dy, const void* out, const float* ma
     else         { if (wg) SIB_APP(false, false, true); else SIB_APP(false, false, false); }
   }
 #undef SIB_APP
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// bn_bwd_apply of an activation-free BatchNorm whose incoming gradient is dy * dy_mul[n][c] +
+// dy_add[n][c] (BResNet block tail: ECA gate x keep mask and the gate's pooled-path gradient).
+extern "C" int sib_bn_bwd_apply_scaled(const void* dy, const float* dy_mul, const float* dy_add,
+                                       const void* x, const float* mean_invstd, const float* gamma,
+                                       const float* sums, void* dx, float* dgamma, float* dbeta,
+                                       int N, int HW, int C, double count, float pgrad_scale,
+                                       void* stream) {
+  if (int rc = check_c(C)) return rc;
+  SIB_CHECK(dy_mul != nullptr && dy_add != nullptr, "bn_bwd_apply_scaled: dy_mul and dy_add are required");
+  const long M = (long)N * HW;
+  const int grid = bn_grid(M, C);
+  SIB_CUDA(launch_pdl(bn_bwd_apply_kernel<false, false, false, false, true>, dim3(grid), dim3(kRedThreads), 0,
+                      ST(stream), static_cast<const __nv_bfloat16*>(dy),
+                      static_cast<const __nv_bfloat16*>(nullptr), static_cast<const float*>(nullptr),
+                      static_cast<const __nv_bfloat16*>(x), mean_invstd, gamma, sums,
+                      static_cast<const __nv_bfloat16*>(nullptr), static_cast<const float*>(nullptr),
+                      static_cast<const float*>(nullptr), static_cast<__nv_bfloat16*>(dx),
+                      static_cast<__nv_bfloat16*>(nullptr), static_cast<__nv_bfloat16*>(nullptr), dgamma,
+                      dbeta, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, C,
+                      (float)(1.0 / count), (int)SIB_ACT_NONE, 0.f, pgrad_scale,
+                      static_cast<const float*>(nullptr), 0, 0.f, static_cast<__nv_bfloat16*>(nullptr),
+                      dy_mul, dy_add, HW));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -981,7 +1021,8 @@ extern "C" int sib_bn_bwd_apply_remat(const void* dy, const float* mask_ss, cons
                       static_cast<__nv_bfloat16*>(nullptr), static_cast<__nv_bfloat16*>(nullptr), dgamma,
                       dbeta, static_cast<float*>(nullptr), static_cast<float*>(nullptr), M, C,
                       (float)(1.0 / count), act, slope, pgrad_scale, act_ss, fwd_act, fwd_slope,
-                      static_cast<__nv_bfloat16*>(a_out)));
+                      static_cast<__nv_bfloat16*>(a_out), static_cast<const float*>(nullptr),
+                      static_cast<const float*>(nullptr), 1));
   SIB_LAUNCH_CHECK();
   return 0;
 }

@@ -564,13 +564,35 @@ def eca_gate_bwd(ds, s, p, w, dw):
     return dp
 
 
-def scale_add_act(x, mul, res, act, slope=0.01):
-    """act(x * mul[n, c] + res) in one pass (x, res: bf16 channels_last of equal shape)."""
+def scale_add_act(x, mul, res, act, slope=0.01, add=None):
+    """act(x * mul[n, c] (+ add[n, c]) + res) in one pass (x, res: bf16 channels_last of equal shape)."""
     n, c, h, w = x.shape
     assert res.shape == x.shape
     y = new_act(n, c, h, w, x.device)
-    call("sib_scale_add_act", _p(x), _p(mul), _p(res), _p(y), n, h * w, c, act, float(slope), _stream())
+    call("sib_scale_add_act", _p(x), _p(mul), _p(add), _p(res), _p(y), n, h * w, c, act, float(slope), _stream())
     return y
+
+
+def act_bwd_reduce(dy, y, x, act, slope=0.01):
+    """g = dy * act'(y); s1[n, c] = sum_hw g, s2[n, c] = sum_hw g * x  -> g, s1, s2."""
+    n, c, h, w = y.shape
+    g = torch.empty_like(y)
+    s1 = torch.empty((n, c), dtype=torch.float32, device=y.device)
+    s2 = torch.empty((n, c), dtype=torch.float32, device=y.device)
+    call("sib_act_bwd_reduce", _p(dy), _p(y), _p(x), _p(g), _p(s1), _p(s2), n, h * w, c, act, float(slope), _stream())
+    return g, s1, s2
+
+
+def bn_bwd_apply_scaled(dy, dy_mul, dy_add, x, mean_invstd, gamma, sums, count, param_grads=(None, None),
+                        pgrad_scale=1.0):
+    """BN backward (no activation) of the gradient dy * dy_mul[n, c] + dy_add[n, c] -> dx."""
+    n, c, h, w = x.shape
+    if len(param_grads) > 2:
+        pgrad_scale = param_grads[2]
+    dx = new_act(n, c, h, w, x.device)
+    call("sib_bn_bwd_apply_scaled", _p(dy), _p(dy_mul), _p(dy_add), _p(x), _p(mean_invstd), _p(gamma), _p(sums),
+         _p(dx), _p(param_grads[0]), _p(param_grads[1]), n, h * w, c, float(count), float(pgrad_scale), _stream())
+    return dx
 
 
 def add_act(a, b, act, slope=0.01):

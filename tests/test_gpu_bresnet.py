@@ -177,6 +177,8 @@ def test_drop_connect_folded_into_eca_gate_matches_two_pass():
     x0 = ops.to_nhwc_bf16(torch.randn(16, 256, 14, 14, device="cuda"))
     g0 = ops.to_nhwc_bf16(torch.randn(16, 256, 14, 14, device="cuda"))
     runs = {}
+    tail_was = bresnet.FUSE_BN3_TAIL
+    bresnet.FUSE_BN3_TAIL = False          # this test is about the operator-sequence tail
     for fused in (False, True):
         bresnet.FUSE_DROP_CONNECT = fused
         for p in blk.parameters():
@@ -189,6 +191,7 @@ def test_drop_connect_folded_into_eca_gate_matches_two_pass():
         runs[fused] = (out.detach().float(), x.grad.float(),
                        {n: p.grad.detach().clone() for n, p in blk.named_parameters()})
     bresnet.FUSE_DROP_CONNECT = True
+    bresnet.FUSE_BN3_TAIL = tail_was
     (o0, dx0, gr0), (o1, dx1, gr1) = runs[False], runs[True]
     assert (o0 - o1).abs().max() <= 0.13 and _cos(o0, o1) > 0.99999   # one bf16 rounding instead of two
     skip = torch.nn.functional.leaky_relu(x0.float(), 0.01)            # a dropped branch leaves act(x)
@@ -201,3 +204,43 @@ def test_drop_connect_folded_into_eca_gate_matches_two_pass():
     assert _cos(dx0, dx1) > 0.999
     for n in gr0:
         assert _cos(gr0[n], gr1[n]) > 0.995, n
+
+
+@pytest.mark.parametrize("inplanes,planes,stride,down,keep", [(256, 64, 1, False, 0.7), (256, 128, 2, True, 1.0)])
+def test_fused_block_tail_matches_operator_sequence(inplanes, planes, stride, down, keep):
+    """FUSE_BN3_TAIL: bn3's output never materialised, one backward pass for mask + per-(sample,
+    channel) sums, BatchNorm-backward sums derived algebraically, gate scale inside bn_bwd_apply ==
+    the operator sequence (bn_apply, chan_reduce, scale, act_bwd, chan_reduce, scale_nc, bn_bwd_reduce,
+    bn_bwd_apply) on the same drop-connect mask: output, dx and every parameter gradient."""
+    from sota_imagenet_b200 import bresnet, ops
+    torch.manual_seed(2)
+    blk = bresnet.BBottleneck(inplanes, planes, stride, downsample=down, keep_prob=keep).cuda().train()
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            if p.dim() == 1:
+                p.uniform_(0.5, 1.5) if n.endswith("weight") else p.normal_(0, 0.2)
+    x0 = ops.to_nhwc_bf16(torch.randn(16, inplanes, 28, 28, device="cuda"))
+    shape = (16, planes * 4, 28 // stride, 28 // stride)
+    g0 = ops.to_nhwc_bf16(torch.randn(*shape, device="cuda"))
+    runs = {}
+    was = bresnet.FUSE_BN3_TAIL
+    for fused in (False, True):
+        bresnet.FUSE_BN3_TAIL = fused
+        for p in blk.parameters():
+            p.grad = None
+        torch.manual_seed(7)                     # same keep mask in both runs
+        x = x0.clone().requires_grad_(True)
+        out = blk(x)
+        out.backward(g0)
+        torch.cuda.synchronize()
+        runs[fused] = (out.detach().float(), x.grad.float(), {n: p.grad.detach().clone() for n, p in blk.named_parameters()},
+                       {n: b.clone() for n, b in blk.named_buffers() if "running" in n})
+    bresnet.FUSE_BN3_TAIL = was
+    (o0, dx0, gr0, b0), (o1, dx1, gr1, b1) = runs[False], runs[True]
+    assert _cos(o0, o1) > 0.99999 and (o0 - o1).abs().max() <= 0.13      # one bf16 rounding instead of two
+    assert _cos(dx0, dx1) > 0.999
+    for n in gr0:
+        assert _cos(gr0[n], gr1[n]) > 0.999, (n, _cos(gr0[n], gr1[n]))
+        assert abs(float(gr1[n].norm() / gr0[n].norm()) - 1) < 2e-2, n
+    for n in b0:                                                          # same statistics, same updates
+        assert torch.allclose(b0[n], b1[n], rtol=1e-5, atol=1e-6), n

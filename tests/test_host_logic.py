@@ -185,6 +185,45 @@ def test_initialize_gain_and_ema_only_for_accepting_optimizers():
     assert "ema_decay" not in inspect.signature(torch.optim.AdamW.__init__).parameters
 
 
+def test_batch_pixel_aug_parameter_table():
+    """Host side of the photometric augmentations (reference dali_dataloader.py:81-111): the colour
+    twist as one affine map, its transport into normalised space, probabilities, box geometry."""
+    import numpy as np
+    from sota_imagenet_b200 import data
+    a, t = data.color_twist_matrix()
+    assert np.allclose(a, np.eye(3), atol=1e-12) and np.allclose(t, 0)
+    a, t = data.color_twist_matrix(saturation=0.0)                 # saturation 0 = luma in every channel
+    assert np.allclose(a, np.tile([0.299, 0.587, 0.114], (3, 1)), atol=2e-3)
+    a, t = data.color_twist_matrix(contrast=0.5, brightness=2.0)
+    assert np.allclose(a, np.eye(3)) and np.allclose(t, 128.0)     # 2 * (128 + 0.5 * (v - 128)) = v + 128
+    a, _ = data.color_twist_matrix(hue_deg=120.0)
+    assert np.allclose(a @ a @ a, np.eye(3), atol=1e-9)            # three 120-degree hue turns = identity
+
+    class Cfg:
+        blur_prob, color_twist_prob, gray_prob, re_prob, re_count = 0.5, 1.0, 0.25, 1.0, 2
+        contrast_range, brightness_range = (0.7, 1.3), (0.7, 1.3)
+
+    aug = data.BatchPixelAug(Cfg(), seed=1)
+    assert aug.active
+    sigma, p = aug.draw(4000, 64, batch_index=3)
+    assert p.shape == (4000, 16 + 8) and 0.45 < (sigma > 0).mean() < 0.55
+    assert sigma[sigma > 0].min() >= 0.5 and sigma.max() <= 1.1 and 0.2 < p[:, 14].mean() < 0.3
+    assert np.all(p[:, 12] == -2.5) and np.all(p[:, 13] == 2.5)
+    boxes = p[:, 16:].reshape(-1, 2, 4)
+    ext_h, ext_w = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
+    assert boxes.min() >= 0 and boxes.max() <= 64 and ext_h.max() <= 17 and ext_w.max() <= 17 and ext_h.mean() > 6
+    # the affine map in normalised space reproduces the 255-space map
+    rng = np.random.RandomState(0)
+    v = rng.uniform(0, 255, size=3)
+    a, t = data.color_twist_matrix(1.2, 0.9, 15.0, 1.1)
+    xn = (v - data.DATA_MEAN) / data.DATA_STD
+    o = (a @ np.full(3, data.DATA_MEAN) + t - data.DATA_MEAN) / data.DATA_STD
+    assert np.allclose(a @ xn + o, (a @ v + t - data.DATA_MEAN) / data.DATA_STD)
+    sigma2, p2 = aug.draw(16, 64, batch_index=3)
+    s3, p3 = data.BatchPixelAug(Cfg(), seed=1).draw(16, 64, batch_index=3)
+    assert np.array_equal(p3, p2) and np.array_equal(s3, sigma2)   # deterministic
+
+
 def test_novograd_norm_groups_and_table_layout():
     """Host side of MyNovograd: norm groups per tensor / per output unit (reference
     optimizers.py:18-22) and the 56-byte records csrc/optim.cu NovoTensor expects."""
