@@ -142,11 +142,11 @@ def bresnet50(seed=0, **kw):
     return BResNet(**kw)
 
 
-def bbottleneck_bf16_faithful(blk, x):
+def bbottleneck_bf16_faithful(blk, x, round_bn3=False):
     """BBottleneck.forward with values rounded to bfloat16 exactly where the B200 pipeline stores
-    bf16 tensors (conv outputs, BN+activation outputs, blur / avg-pool outputs, the block output;
-    the ECA gate and the pooled means stay fp32, the gate is applied inside the final add +
-    activation pass): the per-block strict oracle of tests/test_gpu_bresnet.py."""
+    bf16 tensors (conv outputs, bn1 / bn2 + activation outputs, blur / avg-pool outputs, the block
+    output; the ECA gate and the pooled means stay fp32, the gate is applied inside the final add +
+    activation pass; `round_bn3` = the operator-sequence tail that also stores bn3's output): the per-block strict oracle of tests/test_gpu_bresnet.py."""
     from .torch_ref import _RoundFwd, _q
 
     def conv(m, t):
@@ -163,7 +163,11 @@ def bbottleneck_bf16_faithful(blk, x):
     o = bn(blk.bn2, conv(blk.conv2, o))
     if blk.blur is not None:
         o = _q(blk.blur(o))
-    o = bn(blk.bn3, conv(blk.conv3, o))
+    # the fused block tail (bresnet.FUSE_BN3_TAIL, the default) never stores bn3's output: the gate
+    # and the shortcut add are applied to fp32 values and the block output is rounded once
+    o = blk.bn3(conv(blk.conv3, o))
+    if round_bn3:
+        o = _q(o)
     if blk.eca is not None:
         p = o.mean(dim=(2, 3))
         s = torch.sigmoid(F.conv1d(p[:, None, :], blk.eca.weight, padding=1))[:, 0]

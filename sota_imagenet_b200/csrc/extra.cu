@@ -279,13 +279,14 @@ scale_add_act_kernel(const __nv_bfloat16* __restrict__ x, const float* __restric
     float f[8], r[8];
     unpack8(ldg_stream(x + i * 8), f);
     unpack8(ldg_stream(res + i * 8), r);
-    const float* m = mul + n * C + v * 8;
-    const float* ad = add != nullptr ? add + n * C + v * 8 : nullptr;
+    float m[8], ad[8];
+    load8f(mul + n * C + v * 8, m);
+    if (add != nullptr) load8f(add + n * C + v * 8, ad);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       // (x * mul + add) is the gated BatchNorm output when x is the RAW conv output and mul / add
       // carry the BN scale / shift times the gate; then the shortcut is added
-      float t = ad != nullptr ? fmaf(f[j], __ldg(m + j), __ldg(ad + j)) + r[j] : fmaf(f[j], __ldg(m + j), r[j]);
+      float t = add != nullptr ? fmaf(f[j], m[j], ad[j]) + r[j] : fmaf(f[j], m[j], r[j]);
       if (act == SIB_ACT_RELU) t = fmaxf(t, 0.f);
       else if (act == SIB_ACT_LEAKY) t = t > 0.f ? t : t * slope;
       f[j] = t;

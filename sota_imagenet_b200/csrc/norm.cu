@@ -472,7 +472,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
         unpack8(vg[u], g);
         unpack8(vx[u], xv);
         if (DYT) {
-          const long nn = rr / HW;
+          const long nn = (long)((unsigned)rr / (unsigned)HW);     // (M < 2^31: 32-bit division)
           float m[8], ad[8];
           load8f(dy_mul + nn * C + col, m);
           load8f(dy_add + nn * C + col, ad);

@@ -224,8 +224,11 @@ def test_fused_block_tail_matches_operator_sequence(inplanes, planes, stride, do
     g0 = ops.to_nhwc_bf16(torch.randn(*shape, device="cuda"))
     runs = {}
     was = bresnet.FUSE_BN3_TAIL
+    buf0 = {n: b.clone() for n, b in blk.named_buffers()}
     for fused in (False, True):
         bresnet.FUSE_BN3_TAIL = fused
+        for n, b in blk.named_buffers():
+            b.copy_(buf0[n])                     # both runs start from the same running statistics
         for p in blk.parameters():
             p.grad = None
         torch.manual_seed(7)                     # same keep mask in both runs
@@ -240,7 +243,10 @@ def test_fused_block_tail_matches_operator_sequence(inplanes, planes, stride, do
     assert _cos(o0, o1) > 0.99999 and (o0 - o1).abs().max() <= 0.13      # one bf16 rounding instead of two
     assert _cos(dx0, dx1) > 0.999
     for n in gr0:
-        assert _cos(gr0[n], gr1[n]) > 0.999, (n, _cos(gr0[n], gr1[n]))
-        assert abs(float(gr1[n].norm() / gr0[n].norm()) - 1) < 2e-2, n
+        # (the 3-tap ECA filter gradient is a heavily cancelling sum over (sample, channel): the
+        #  operator sequence feeds it the bf16-rounded bn3 output, the fused tail the fp32 one)
+        lim = (0.99, 1e-1) if n == "eca.weight" else (0.999, 2e-2)
+        assert _cos(gr0[n], gr1[n]) > lim[0], (n, _cos(gr0[n], gr1[n]))
+        assert abs(float(gr1[n].norm() / gr0[n].norm()) - 1) < lim[1], n
     for n in b0:                                                          # same statistics, same updates
         assert torch.allclose(b0[n], b1[n], rtol=1e-5, atol=1e-6), n
