@@ -309,7 +309,11 @@ def run_ours(args):
                          nesterov=True)
     root = net.encoder if hasattr(net, "encoder") else net     # (embedding models wrap the trunk)
     if world > 1:
-        dp = parallel.DataParallel(root, sync_bn=True)
+        # (attribution switches for the scaling analysis, profiles/r02_scaling_attribution.md)
+        dp = parallel.DataParallel(root, sync_bn=not args.no_sync_bn,
+                                   bucket_mb=1e9 if args.no_overlap else 25.0)
+        if args.no_grad_allreduce:
+            dp._reduce = lambda lo, hi: None
         if root is net:
             model = dp
         else:
@@ -532,6 +536,7 @@ def run_ours(args):
                 "workload": "%s fwd+bwd+SGD-Nesterov(m=.9, wd=3e-5) + smooth-CE(0.1), batch %d/GPU, "
                             "%dx%d, NHWC bf16, SyncBN + bucketed grad all-reduce for N>1" % (cfg["desc"], BATCH, SIZE, SIZE),
                 "name": args.config,
+                "attribution_switches": [k for k in ("no_sync_bn", "no_grad_allreduce", "no_overlap") if getattr(args, k)] or None,
                 "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                 "cuda_graph": used_graph,
                 "l2": "activation working set (~12 GB/step) >> 126 MB L2; no flush needed",
@@ -591,6 +596,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-sync-bn", action="store_true", help="attribution only: per-rank BatchNorm statistics")
+    ap.add_argument("--no-grad-allreduce", action="store_true", help="attribution only: skip the gradient all-reduce")
+    ap.add_argument("--no-overlap", action="store_true", help="attribution only: one gradient bucket after backward")
     ap.add_argument("--config", default="r50", choices=sorted(CONFIGS))
     args = ap.parse_args()
     if args.impl == "reference":
