@@ -452,6 +452,26 @@ def run_ours(args):
         ms2 = float(t)
     e2e_value = BATCH * world * e2e_steps / ms2 * 1e3
     e2e_replays = gstep.replays
+    # the augmentation kernel alone (crop boxes + resample + mirror + normalise): HBM-bound, reads at
+    # most the source batch, writes the bf16 NHWC4 model input
+    roofline_aug = None
+    if rank == 0:
+        imgs_d, _, _ = pre.next()
+        for _ in range(3):
+            aug(imgs_d, first_sample=0)
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for k in range(10):
+            aug(imgs_d, first_sample=k * BATCH)
+        eb.record()
+        torch.cuda.synchronize()
+        aug_ms = ea.elapsed_time(eb) / 10
+        aug_bytes = BATCH * (256 * 256 * 3 * 0.54 + SIZE * SIZE * 4 * 2)   # mean crop area 0.54 of the source
+        roofline_aug = {"bound": "hbm", "kernel": "rrc_boxes + augment_kernel (crop, triangular resize, mirror, normalise, uint8 -> bf16 NHWC4)",
+                        "ms_per_batch": aug_ms, "achieved": aug_bytes / (aug_ms * 1e-3) / 1e9, "peak": peaks()["hbm_gbs"],
+                        "unit": "GB/s", "frac": aug_bytes / (aug_ms * 1e-3) / 1e9 / peaks()["hbm_gbs"],
+                        "bytes_per_batch": aug_bytes, "note": "source reads estimated from the mean crop area (0.54); two launches"}
     h2d = BATCH * 256 * 256 * 3 + BATCH * 8
     d2h = 4
 
@@ -494,11 +514,16 @@ def run_ours(args):
                        "traffic": None, "bytes_per_step": bn_b, "ms_per_step_eager_events": bn_ms}
         # DRAM bytes of the same conv launches from the committed ncu capture (profiles/): compare
         # with the algorithmic minimum (read x + write y + read w per pass)
+        # (a committed capture of the SAME command under ncu, not measured in this run: refresh it
+        #  with scripts/ncu_step_traffic.py whenever a kernel changes)
         traffic, traffic_src = None, None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_dram_traffic.json")
-        if os.path.exists(tpath) and BATCH == 256 and SIZE == 224:
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_step_dram_traffic.json")
+        if os.path.exists(tpath) and BATCH == 256 and SIZE == 224 and args.config == "r50":
             tj = json.load(open(tpath))
-            traffic, traffic_src = tj["dram_bytes_per_step"], "profiles/r01_conv_dram_traffic.json (ncu, %d conv launches of one step)" % tj["conv_launches_per_step"]
+            traffic = tj["conv"]["dram_bytes_per_step"]
+            traffic_src = "profiles/r02_step_dram_traffic.json (ncu dram__bytes_read+write, %d conv launches of one step)" % tj["conv"]["launches"]
+            roofline_bn["traffic"] = tj["bn"]["dram_bytes_per_step"]
+            roofline_bn["traffic_source"] = "profiles/r02_step_dram_traffic.json (ncu, %d BatchNorm-family launches of one step)" % tj["bn"]["launches"]
         roofline = {
             "bound": "tensor", "kernel": "igemm / igemm2 / halo3x3 / wgrad kernels (tcgen05 implicit-GEMM conv)",
             "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
@@ -549,7 +574,7 @@ def run_ours(args):
                     "path": "pinned host uint8 [256,256,256,3] -> H2D (copy stream, double-buffered) -> GpuAugment -> runner.GraphStep "
                             "(model -> CE -> backward -> SGD, one CUDA-graph launch per step) -> loss D2H"},
             "gpu_launches": int(calls_per_step * args.steps),
-            "clocks": clocks, "roofline": roofline, "roofline_bn": roofline_bn,
+            "clocks": clocks, "roofline": roofline, "roofline_bn": roofline_bn, "roofline_augment": roofline_aug,
             "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
         }
         emit(line)
