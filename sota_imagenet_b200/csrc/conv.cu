@@ -1917,7 +1917,10 @@ extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N,
   // split the pixel reduction so that the CTAs fill `waves` rounds of the 2-per-SM slots without
   // spilling into a nearly empty extra round (floor, not ceil), >= 8 k-blocks each
   static const int waves = [] { const char* e = getenv("SIB_WGRAD_WAVES"); return e ? atoi(e) : 1; }();
-  int splits = (waves * 2 * sm_count()) / tiles;
+  // SIB_DETERMINISTIC=1: no split over the pixel reduction (the TMA add-reduction of several splits
+  // into one gradient tile lands in a varying order); one CTA per gradient tile, much slower
+  static const bool det = [] { const char* e = getenv("SIB_DETERMINISTIC"); return e && e[0] == '1'; }();
+  int splits = det ? 1 : (waves * 2 * sm_count()) / tiles;
   int max_splits = (p.total_kblocks + 7) / 8;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

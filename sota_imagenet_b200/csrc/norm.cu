@@ -5,6 +5,8 @@
 //
 // Arithmetic follows nn.BatchNorm2d in training mode, which is what
 // pytorch_tools' ABN / the reference's `patch_bn_mom` path run (reference train.py:76).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host.h"
 #include "../../include/sib200.h"
@@ -46,11 +48,22 @@ struct ColOwner {
   }
 };
 
+// SIB_DETERMINISTIC=1: the cross-block combination of the reduction kernels does not use
+// floating-point atomics (whose arrival order changes the last bits from run to run); every block
+// stores its partial sums to a scratch buffer and the LAST block to finish (ticket counter) adds
+// them up in block order.  One scratch buffer per process: all reductions run on one stream.
+struct DetScratch {
+  float* partials;          // [max blocks][4][kRedThreads * 8]
+  unsigned* counter;
+};
+
 // cross-thread reduction of per-thread column accumulators -> fp32 atomics on out[NACC][C]
 template <int NACC>
 __device__ __forceinline__ void column_reduce_store(const ColOwner& co, int C,
-                                                    float (&acc)[NACC][8], float* __restrict__ out) {
+                                                    float (&acc)[NACC][8], float* __restrict__ out,
+                                                    const DetScratch det = DetScratch{nullptr, nullptr}) {
   __shared__ float red[NACC][kRedThreads][8];
+  __shared__ unsigned s_ticket;
 #pragma unroll
   for (int a = 0; a < NACC; ++a)
 #pragma unroll
@@ -69,16 +82,37 @@ __device__ __forceinline__ void column_reduce_store(const ColOwner& co, int C,
       const float* r4 = &red[a][y * cvec + v][j];
       s0 += r4[0]; s1 += r4[1]; s2 += r4[2]; s3 += r4[3];
     }
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + (long)a * C + c),
-                 "f"(s0), "f"(s1), "f"(s2), "f"(s3)
-                 : "memory");
+    if (det.partials != nullptr) {
+      *reinterpret_cast<float4*>(det.partials + ((long)blockIdx.x * NACC + a) * C + c) = make_float4(s0, s1, s2, s3);
+    } else {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + (long)a * C + c),
+                   "f"(s0), "f"(s1), "f"(s2), "f"(s3)
+                   : "memory");
+    }
+  }
+  if (det.partials != nullptr) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(det.counter, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) {           // last block: fixed-order sum over the blocks
+      __threadfence();
+      for (int idx = threadIdx.x; idx < NACC * C; idx += kRedThreads) {
+        float t = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b)
+          t += __ldcg(det.partials + (long)b * NACC * C + idx);
+        out[idx] = t;
+      }
+      if (threadIdx.x == 0) *det.counter = 0u;  // ready for the next launch (same stream)
+    }
   }
 }
 
 constexpr int kU = 4;   // rows in flight per thread
 
 __global__ void __launch_bounds__(kRedThreads)
-bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long M, int C, float* __restrict__ stats) {
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long M, int C, float* __restrict__ stats,
+                const DetScratch det) {
   griddep_launch();
   griddep_wait();
   const ColOwner co(C);
@@ -101,7 +135,7 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long M, int C, float* __res
       }
     }
   }
-  column_reduce_store<2>(co, C, acc, stats);
+  column_reduce_store<2>(co, C, acc, stats, det);
 }
 
 // ---------------------------------------------------------------------------
@@ -300,7 +334,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      const float* __restrict__ mask_ss, const __nv_bfloat16* __restrict__ x,
                      const float* __restrict__ mi, const __nv_bfloat16* __restrict__ x2,
                      const float* __restrict__ mi2, long M, int C, int act, float slope,
-                     float* __restrict__ sums) {
+                     float* __restrict__ sums, const DetScratch det) {
   griddep_launch();
   griddep_wait();
   const ColOwner co(C);
@@ -367,7 +401,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
       }
     }
   }
-  column_reduce_store<NACC>(co, C, acc, sums);
+  column_reduce_store<NACC>(co, C, acc, sums, det);
 }
 
 //   EMIT_A: also rewrite the forward activation a = fwd_act(fmaf(x, scale, shift)) of this BatchNorm
@@ -824,6 +858,25 @@ static int bn_grid(long M, int C) {
   return (int)blocks;
 }
 
+// SIB_DETERMINISTIC=1 (read once): scratch for the fixed-order cross-block sums
+static DetScratch det_scratch() {
+  static DetScratch d{nullptr, nullptr};
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char* e = getenv("SIB_DETERMINISTIC");
+    if (e != nullptr && e[0] == '1') {
+      void* p = nullptr;
+      const size_t bytes = (size_t)2 * sm_count() * 4 * kRedThreads * 8 * sizeof(float) + 256;
+      if (cudaMalloc(&p, bytes) == cudaSuccess && cudaMemset(p, 0, bytes) == cudaSuccess) {
+        d.counter = static_cast<unsigned*>(p);
+        d.partials = reinterpret_cast<float*>(static_cast<char*>(p) + 256);
+      }
+    }
+  }
+  return d;
+}
+
 // statistics / backward-sum kernels: every block ends in 2C..4C atomics on the same addresses
 static int bn_reduce_grid(long M, int C) {
   const int g = bn_grid(M, C);
@@ -834,7 +887,7 @@ static int bn_reduce_grid(long M, int C) {
 extern "C" int sib_bn_stats(const void* x, long M, int C, float* stats, void* stream) {
   if (int rc = check_c(C)) return rc;
   SIB_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, ST(stream)));
-  SIB_CUDA(launch_pdl(bn_stats_kernel, dim3(bn_reduce_grid(M, C)), dim3(kRedThreads), 0, ST(stream), static_cast<const __nv_bfloat16*>(x), M, C, stats));
+  SIB_CUDA(launch_pdl(bn_stats_kernel, dim3(bn_reduce_grid(M, C)), dim3(kRedThreads), 0, ST(stream), static_cast<const __nv_bfloat16*>(x), M, C, stats, det_scratch()));
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -926,7 +979,7 @@ extern "C" int sib_bn_bwd_reduce(const void* dy, const void* out, const float* m
 #define SIB_RED(S, O)                                                                         \
   SIB_CUDA(launch_pdl(bn_bwd_reduce_kernel<S, O>, dim3(grid), dim3(kRedThreads), 0, ST(stream), a, o, mask_ss, xp, mean_invstd, \
                                                                  xq, mean_invstd2, M, C, act,  \
-                                                                 slope, sums))
+                                                                 slope, sums, det_scratch()))
   const bool use_out = out != nullptr && act != SIB_ACT_NONE;
   if (x2) { if (use_out) SIB_RED(true, true); else SIB_RED(true, false); }
   else    { if (use_out) SIB_RED(false, true); else SIB_RED(false, false); }

@@ -53,8 +53,10 @@ class ResNet(SibModule):
 
     def fwd(self, x, train):
         saved = []
-        stats = ops.new_acc(2, 64, x.device) if train else None
+        stats = ops.new_acc(2, 64, x.device) if train and not ops.DETERMINISTIC else None
         c0, xq = self.conv1.run(x, stats)
+        if train and ops.DETERMINISTIC:
+            stats = ops.bn_stats(c0)
         n, _, h, w = c0.shape
         if train and FUSE_STEM_POOL:
             # bn1 + act + max pool in one pass: the 112x112 normalised activation is never written

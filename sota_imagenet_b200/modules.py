@@ -23,7 +23,7 @@ from .arena import ParamArena
 # Fuse the BatchNorm-backward reduction (and the activation mask) into the epilogue of the dgrad
 # that produces the gradient (csrc/conv.cu igemm_epilogue); SIB_FUSE_BN_BWD=0 restores the separate
 # bn_bwd_reduce passes (kept for A/B measurements and as the parity cross-check).
-FUSE_BN_BWD = os.environ.get("SIB_FUSE_BN_BWD", "1") != "0"
+FUSE_BN_BWD = os.environ.get("SIB_FUSE_BN_BWD", "1") != "0" and not ops.DETERMINISTIC
 # 3x3 / stride-2 dgrad by row parity (csrc/conv.cu dgrad_s2_impl); 0 = zero-inserted dy
 FUSE_BN_BWD_ALL = os.environ.get("SIB_FUSE_BN_BWD_ALL", "0") == "1"   # A/B: fuse even where it loses
 DGRAD_S2 = os.environ.get("SIB_DGRAD_S2", "1") != "0"
@@ -34,7 +34,7 @@ DGRAD_S2 = os.environ.get("SIB_DGRAD_S2", "1") != "0"
 # conv3 <- bn2 (1x1) up to 256 input channels and the stride-2 conv2 <- bn1 (the separate pass
 # would run over the 4x larger input) up to 256; 2 = 1 + every conv3, 3 = everything that fits
 # (3x3 stride-1 loses: its transform runs once per filter tap on the im2col kernel).
-FUSE_BN_FWD = int(os.environ.get("SIB_FUSE_BN_FWD", "1"))
+FUSE_BN_FWD = 0 if ops.DETERMINISTIC else int(os.environ.get("SIB_FUSE_BN_FWD", "1"))
 
 
 def _fuse_fwd(kind, planes, stride):
@@ -446,6 +446,9 @@ class Bottleneck(SibModule):
 
     @staticmethod
     def _conv(conv, x, train):
+        if train and ops.DETERMINISTIC:       # statistics by the fixed-order reduction, not the epilogue atomics
+            y = conv.run(x, None)
+            return y, ops.bn_stats(y)
         stats = ops.new_acc(2, conv.out_channels, x.device) if train else None
         return conv.run(x, stats), stats
 

@@ -15,6 +15,14 @@ from ._lib import c_void_p
 def call(name, *args):
     _lib.call(name, *args)
 
+# SIB_DETERMINISTIC=1: bitwise run-to-run reproducibility (goldens, debugging) at the price of speed.
+# No floating-point atomics anywhere on the step: BatchNorm statistics come from a stand-alone
+# fixed-order reduction instead of the conv epilogues, the BN-backward sums from bn_bwd_reduce
+# (fixed order) instead of the dgrad epilogues, the weight gradient is not split over pixels, and
+# the conv-prologue fusion (which consumes epilogue statistics) is off.  Read at import time; the
+# C side reads the same variable (csrc/norm.cu det_scratch, csrc/conv.cu sib_conv2d_wgrad).
+DETERMINISTIC = os.environ.get("SIB_DETERMINISTIC", "0") == "1"
+
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 MARGIN_NONE, MARGIN_ARC, MARGIN_COS, MARGIN_ARC_PURE, MARGIN_ARCCOS = 0, 1, 2, 3, 4
 FLAG_FORCE_IM2COL = 1

@@ -281,3 +281,24 @@ def test_eval_mode_uses_running_stats():
         out = net(x.cuda()).float().cpu()
     err = (out - out_ref).norm() / out_ref.norm()
     assert err < 3e-2, float(err)
+
+
+def test_deterministic_mode_is_bitwise_reproducible():
+    """SIB_DETERMINISTIC=1 (ops.DETERMINISTIC): no floating-point atomics on the step -- statistics and
+    backward sums by fixed-order reductions, unsplit weight gradient -- so two runs from the same
+    state agree BITWISE in loss, all gradients, running statistics and updated weights (the default
+    mode differs in the last bits: fp32 atomics arrive in a different order on every run)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "tools", "determinism_probe.py")
+    out = {}
+    for mode in ("1", "0"):
+        env = dict(os.environ, SIB_DETERMINISTIC=mode)
+        r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        out[mode] = [l.split()[2] for l in r.stdout.splitlines() if l.startswith("DIGEST")]
+        assert len(out[mode]) == 2
+    print("deterministic digests:", out["1"], "default-mode digests:", out["0"])
+    assert out["1"][0] == out["1"][1]
