@@ -24,6 +24,9 @@ constexpr int kThreads = 192;   // wgrad kernel: warp0 TMA, warp1 MMA + TMEM all
 constexpr int kIgemmThreads = 384;  // igemm: warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 epilogue
 constexpr int kIgemmThreadsPro = 512;   // + warps 12-15: BatchNorm/activation transform of the A operand
 constexpr int kProMaxC = 512;           // input channels the fused prologue's scale/shift table holds
+// threads of an igemm CTA: 4 control warps + epilogue warps (8, or 16 with CG = 4) + 4 transform warps (PRO)
+constexpr int igemm_epi_warps(int BN, int CG) { return BN == 64 ? 8 : 4 * (CG ? CG : 2); }
+constexpr int igemm_threads(int BN, bool PRO, int CG) { return 128 + 32 * igemm_epi_warps(BN, CG) + (PRO ? 128 : 0); }
 constexpr int kSlabBytes = 32 * 128;   // epilogue staging: 32 rows x 64 bf16, 128B-swizzled
 
 // 4 consecutive fp32 sums in one L2 operation (16-byte aligned address)
@@ -106,14 +109,18 @@ __device__ __forceinline__ void reg_inc() {
 //   TMEM -> regs -> (+bias, +residual) -> bf16 -> 128B-swizzled smem slab -> TMA store, plus
 //   per-channel sum / sum-of-squares of the stored values for the following BatchNorm, or (fused
 //   BN backward) activation masking of the gradient and sum g / sum g*xhat.
-template <int BN, int SLABS, int AUX, bool kTwoCta>
+//   CG (column groups, default 2): warps e / 4 == g take the 64-column chunks with chunk % CG == g.
+//   CG = 4 with BN = 256 ("16-warp epilogue"): every warp drains ONE chunk per tile and four warps
+//   share a scheduler instead of two -- the BN = 256 kernels with short K (all 1x1 layers) are bound
+//   by the latency of this epilogue, not by the tensor pipe or HBM.
+template <int BN, int SLABS, int AUX, bool kTwoCta, int CG = 0>
 __device__ __forceinline__ void igemm_epilogue(
     const CUtensorMap* tmOut, const CUtensorMap* tmRes, const CUtensorMap* tmAux1,
     const CUtensorMap* tmAux2, const IgemmParams& p, uint8_t* smem_slab, uint8_t* smem_aux,
     uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint64_t* res_bar, float* s_part,
     uint32_t tmem_base, int first_tile, int tile_step, int num_tiles, int cta_rank) {
   constexpr int kChunks = BN / 64;
-  constexpr int kHalves = kChunks >= 2 ? 2 : 1;
+  constexpr int kHalves = CG ? CG : (kChunks >= 2 ? 2 : 1);
   // BN = 64 has a single 64-column chunk: its eight epilogue warps form TWO groups that take
   // alternate tiles (group g drains accumulator stage g), so two epilogues are in flight and
   // their latency no longer bounds the tile rate of the N = 64 kernels (stem, 64-channel 1x1).
@@ -433,8 +440,8 @@ __device__ __forceinline__ void igemm_epilogue(
 // The epilogue of tile i overlaps the main loop of tile i+1.
 //   PRO: warps 12-15 apply the producer BatchNorm (+ activation) to every A stage in place
 //        between the TMA load and the MMA (BnPrologue above).
-template <int BN, int STAGES, int SLABS, int AUX, bool PRO>
-__global__ void __launch_bounds__(PRO ? kIgemmThreadsPro : kIgemmThreads, 1)
+template <int BN, int STAGES, int SLABS, int AUX, bool PRO, int CG = 0>
+__global__ void __launch_bounds__(igemm_threads(BN, PRO, CG), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
              const __grid_constant__ CUtensorMap tmAux1, const __grid_constant__ CUtensorMap tmAux2,
@@ -442,16 +449,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr int kBBytes = BN * kBK * 2;
   constexpr uint32_t kTmemCols = 2 * BN;           // two accumulator stages (power of two)
   constexpr int kChunks = BN / 64;
-  constexpr int kHalves = kChunks >= 2 ? 2 : 1;    // epilogue warp groups splitting the columns
+  constexpr int kHalves = CG ? CG : (kChunks >= 2 ? 2 : 1);    // epilogue warp groups splitting the columns
   constexpr int kWarpsPerAcc = 4 * kHalves;        // warps that drain one accumulator stage
   constexpr int kEpiWarps = BN == 64 ? 8 : kWarpsPerAcc;   // BN = 64: two groups on alternate tiles
   constexpr int kChunksPerWarp = kChunks / kHalves;
+  constexpr int kThreads_ = igemm_threads(BN, PRO, CG);
+  // setmaxnreg rebalancing.  setmaxnreg.inc can only draw what setmaxnreg.dec released inside the
+  // SAME CTA (the pool is the launch allocation, registers/thread x threads): the sum of the
+  // increments must not exceed the sum of the decrements or the last warpgroup blocks forever.
+  constexpr bool kRebalance = PRO || CG == 4;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
   __shared__ uint64_t tmem_full_bar[2];
   __shared__ uint64_t tmem_empty_bar[2];
-  __shared__ uint64_t res_bar[8];
+  __shared__ uint64_t res_bar[16];
   __shared__ uint64_t ready_bar[PRO ? STAGES : 1];   // PRO: A stage transformed (4 warp arrivals)
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_part[kEpiWarps * 2 * kChunksPerWarp * 64];   // per-warp column sums of a tile
@@ -481,7 +493,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], kWarpsPerAcc);   // one arrival per epilogue warp of the stage
     }
-    for (int s = 0; s < 8; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 16; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -500,7 +512,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // BatchNorm finalize folded in: every CTA derives the scale/shift table of the producer BN
     // from its raw batch sums; CTA 0 publishes what backward needs and the running statistics
     const int C = pro.Cin;
-    for (int c = threadIdx.x; c < C; c += kIgemmThreadsPro) {
+    for (int c = threadIdx.x; c < C; c += kThreads_) {
       float sc, sh;
       if (pro.stats != nullptr) {
         const BnCoeffs k = bn_coeffs(pro.stats[c], pro.stats[C + c], pro.gamma ? pro.gamma[c] : 1.f,
@@ -528,13 +540,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 
   // (setmaxnreg sits at the top of each role branch so that it dominates the role's code)
-  if (PRO && warp >= 12) {
-    reg_dec<104>();
+  // register budgets (x 128 threads per warpgroup, <= 64 Ki):
+  //   PRO, 8 epilogue warps  (512 thr, 128 at launch): control 64, epilogue 2 x 168, transform 104
+  //                           released 8192 + 3072 >= drawn 2 x 5120
+  //   16 epilogue warps      (640 thr,  96 at launch): control 32, epilogue 4 x 112
+  //                           released 8192 >= drawn 4 x 2048
+  //   (PRO + 16 epilogue warps would need 768 threads at 80 registers: not instantiated)
+  if (PRO && warp >= 4 + kEpiWarps) {
+    if (CG != 4) reg_dec<104>();
     // ---- A-operand transform: a = act(fmaf(c, scale, shift)), padding taps stay zero ----
     // thread t owns the logical 16-byte chunk (8 channels) t % 8 of rows t / 8 + 16 i: its
     // coefficients stay in registers for a whole k-block and a warp touches four whole
     // 128-byte rows per access (conflict-free under the 128B swizzle)
-    const int tt = threadIdx.x - 384;
+    const int tt = threadIdx.x - (128 + 32 * kEpiWarps);
     const int lc = tt & 7, r0 = tt >> 3;
     const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((lc ^ (r0 & 7)) << 4);
     const int act = pro.act;
@@ -623,7 +641,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 0) {
-    if (PRO) reg_dec<64>();
+    if (kRebalance) { if (CG == 4) reg_dec<32>(); else reg_dec<64>(); }
     if (lane == 0) {
       // ---- TMA producer ----
       int stage = 0;
@@ -665,7 +683,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     //  owned by the other warp -- has not completed yet; the parity test then passes at once and
     //  the MMAs read data still in flight (launch failure at full size).  The halo kernel's ring
     //  holds one whole tile per stage and both of its issuing warps observe every tile's barrier.)
-    if (PRO) reg_dec<64>();
+    if (kRebalance) { if (CG == 4) reg_dec<32>(); else reg_dec<64>(); }
     constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
     const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem_a), 16, 1024, kSwizzle128B);
     const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem_b), 16, 1024, kSwizzle128B);
@@ -695,12 +713,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 4 + kEpiWarps) {
-    if (PRO) reg_inc<168>();
-    igemm_epilogue<BN, SLABS, AUX, false>(&tmOut, &tmRes, &tmAux1, &tmAux2, p, smem_slab, smem_aux,
-                                          tmem_full_bar, tmem_empty_bar, res_bar, s_part, tmem_base,
-                                          blockIdx.x, gridDim.x, num_tiles, 0);
-  } else if (PRO) {
-    reg_dec<64>();      // warps 2 and 3: the rest of warpgroup 0 must execute the same setmaxnreg
+    static_assert(!(PRO && CG == 4), "PRO + 16-warp epilogue is not instantiated (register budget)");
+    if (kRebalance) { if (CG == 4) reg_inc<112>(); else reg_inc<168>(); }
+    igemm_epilogue<BN, SLABS, AUX, false, CG>(&tmOut, &tmRes, &tmAux1, &tmAux2, p, smem_slab, smem_aux,
+                                              tmem_full_bar, tmem_empty_bar, res_bar, s_part, tmem_base,
+                                              blockIdx.x, gridDim.x, num_tiles, 0);
+  } else if (kRebalance) {
+    // warps 2 and 3: the rest of warpgroup 0 must execute the same setmaxnreg
+    if (CG == 4) reg_dec<32>(); else reg_dec<64>();
   }
   tc_fence_before();
   __syncthreads();
@@ -1461,23 +1481,23 @@ struct IgemmMaps {
   CUtensorMap a, b, out, res, aux1, aux2;
 };
 
-template <int BN, int STAGES, int SLABS, int AUX, bool PRO = false>
+template <int BN, int STAGES, int SLABS, int AUX, bool PRO = false, int CG = 0>
 static int launch_igemm(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t stream,
                         const BnPrologue* pro = nullptr) {
-  constexpr int kEpiWarps = 8;
+  constexpr int kEpiWarps = igemm_epi_warps(BN, CG);
   constexpr int smem =
       STAGES * (kABytes + BN * kBK * 2) + kEpiWarps * (SLABS + AUX) * kSlabBytes + 1024;
   static_assert(smem + 8192 + 512 + (PRO ? 8 * kProMaxC + 64 : 0) <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS, AUX, PRO>,
+    SIB_CUDA(cudaFuncSetAttribute(igemm_kernel<BN, STAGES, SLABS, AUX, PRO, CG>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   int grid = p.num_m_tiles * p.num_n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  SIB_CUDA(launch_pdl(igemm_kernel<BN, STAGES, SLABS, AUX, PRO>, dim3(grid),
-                      dim3(PRO ? kIgemmThreadsPro : kIgemmThreads), smem, stream, tm.a, tm.b, tm.out,
+  SIB_CUDA(launch_pdl(igemm_kernel<BN, STAGES, SLABS, AUX, PRO, CG>, dim3(grid),
+                      dim3(igemm_threads(BN, PRO, CG)), smem, stream, tm.a, tm.b, tm.out,
                       tm.res, tm.aux1, tm.aux2, p, pro != nullptr ? *pro : BnPrologue{}));
   return 0;
 }
@@ -1691,6 +1711,8 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   }
   if (p.stats != nullptr && !(flags & SIB_FLAG_STATS_ZEROED))
     SIB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * p.stat_c, stream));
+  // 16-warp epilogue for the 256-column 1-CTA tiles: opt-in (SIB_EPI16=1) until measured faster
+  static const bool epi16 = [] { const char* e = getenv("SIB_EPI16"); return e && e[0] == '1'; }();
   if (pro != nullptr) {
     if (BN == 64) return launch_igemm<64, 6, 1, 0, true>(tm, p, stream, pro);
     if (BN == 128) return launch_igemm<128, 5, 1, 0, true>(tm, p, stream, pro);
@@ -1700,6 +1722,7 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
     if (two_cta) return launch_igemm2<256, 5, 1, 0>(tm, p, stream);
     if (BN == 64) return launch_igemm<64, 6, 1, 0>(tm, p, stream);
     if (BN == 128) return launch_igemm<128, 5, 1, 0>(tm, p, stream);
+    if (epi16) return launch_igemm<256, 3, 1, 0, false, 4>(tm, p, stream);
     return launch_igemm<256, 3, 2, 0>(tm, p, stream);
   }
   // fused variants trade pipeline stages for the auxiliary slabs (227 KB of smem per CTA)
