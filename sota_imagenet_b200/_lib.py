@@ -59,7 +59,9 @@ def load():
     except Exception:
         if not os.path.exists(LIB_PATH):
             raise
-    lib = ctypes.CDLL(LIB_PATH)
+    variant = os.environ.get("SIB_LIB_VARIANT")       # experimental A/B builds (build.build_variant)
+    path = os.path.join(_HERE, "libsib200_%s.so" % variant) if variant else LIB_PATH
+    lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in header_prototypes().items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = restype

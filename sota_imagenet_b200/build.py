@@ -36,6 +36,20 @@ def _digest(paths):
     return h.hexdigest()
 
 
+def build_variant(name, extra_flags):
+    """Experimental second library (libsib200_<name>.so) with extra nvcc flags, selected at run time
+    with SIB_LIB_VARIANT=<name> (A/B measurements on the same box)."""
+    global OUT_DIR, LIB, NVCC_FLAGS
+    saved = OUT_DIR, LIB, list(NVCC_FLAGS)
+    try:
+        OUT_DIR = os.path.join(ROOT, "_build_" + name)
+        LIB = os.path.join(ROOT, "libsib200_%s.so" % name)
+        NVCC_FLAGS = NVCC_FLAGS + list(extra_flags)
+        return build()
+    finally:
+        OUT_DIR, LIB, NVCC_FLAGS = saved
+
+
 def build(force=False, verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]

@@ -130,10 +130,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Optional back-off between polls of the non-critical waiters (TMA producer, epilogue warps):
+// compile-time (-DSIB_SPIN_SLEEP_NS=n, an experiment: the B200s of this pool run the step against the
+// 1 kW power cap, so energy spent spinning costs clock); 0 = poll back to back.
+#ifndef SIB_SPIN_SLEEP_NS
+#define SIB_SPIN_SLEEP_NS 0
+#endif
+
 // Bounded wait: a pipeline bug must trap, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (SIB_SPIN_SLEEP_NS > 0) __nanosleep(SIB_SPIN_SLEEP_NS);
     if (++spins > (1u << 26)) {
       printf("sib: mbarrier wait timeout block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, parity);
