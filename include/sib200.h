@@ -44,6 +44,8 @@ extern "C" {
 #define SIB_ACT_FLAG_PREZEROED 0x100 /* or-ed into sib_bn_bwd_reduce's `act`: `sums` already zero */
 
 const char* sib_last_error(void);
+/* CRC-32C of a HOST buffer (TFRecord framing, records.py); result in *out_host. */
+int sib_crc32c_host(const void* data_host, unsigned long long n, unsigned int* out_host);
 int sib_abi_version(void);
 int sib_device_check(void); /* 0 iff the current device is sm_100 */
 

@@ -223,3 +223,37 @@ extern "C" int sib_device_check(void) {
             minor);
   return 0;
 }
+
+
+// CRC-32C (Castagnoli), slicing-by-8, on HOST memory: the record framing check of the TFRecord reader
+// (records.py; reference create_records.py:84-106 writes the shards through TensorFlow, DALI verifies
+// them when reading, dali_dataloader.py:47-65).  ~1 GB/s per core instead of a per-byte Python loop.
+extern "C" int sib_crc32c_host(const void* data_host, unsigned long long n, unsigned int* out_host) {
+  static uint32_t tab[8][256];
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      tab[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xFF];
+  });
+  SIB_CHECK(out_host != nullptr && (data_host != nullptr || n == 0), "crc32c: null pointer");
+  const unsigned char* p = static_cast<const unsigned char*>(data_host);
+  uint32_t c = 0xFFFFFFFFu;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = tab[7][lo & 0xFF] ^ tab[6][(lo >> 8) & 0xFF] ^ tab[5][(lo >> 16) & 0xFF] ^ tab[4][lo >> 24] ^
+        tab[3][hi & 0xFF] ^ tab[2][(hi >> 8) & 0xFF] ^ tab[1][(hi >> 16) & 0xFF] ^ tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  *out_host = c ^ 0xFFFFFFFFu;
+  return 0;
+}

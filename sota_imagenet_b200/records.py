@@ -40,12 +40,38 @@ def _crc_table():
     return _CRC_TABLE
 
 
-def crc32c(data: bytes) -> int:
+def _crc32c_py(data: bytes) -> int:
+    """Per-byte table walk (the specification; used to pin the native routine in the tests)."""
     tab = _crc_table()
     c = 0xFFFFFFFF
     for b in data:
         c = tab[(c ^ b) & 0xFF] ^ (c >> 8)
     return c ^ 0xFFFFFFFF
+
+
+_CRC_NATIVE = None
+
+
+def crc32c(data: bytes) -> int:
+    """CRC-32C through the library's host routine (slicing-by-8, sib_crc32c_host): verify=True at
+    ImageNet scale is ~1 GB/s per core instead of ~2 MB/s for the Python loop."""
+    global _CRC_NATIVE
+    if _CRC_NATIVE is None:
+        try:
+            import ctypes
+            from . import _lib
+            fn = _lib.load().sib_crc32c_host
+            out = ctypes.c_uint()
+
+            def native(buf):
+                b = bytes(buf)
+                _lib.check(fn(b, len(b), ctypes.byref(out)))
+                return out.value
+            native(b"")
+            _CRC_NATIVE = native
+        except Exception:        # library not built (e.g. no nvcc on a data-preparation host)
+            _CRC_NATIVE = _crc32c_py
+    return _CRC_NATIVE(data)
 
 
 def masked_crc(data: bytes) -> int:

@@ -23,6 +23,11 @@ def _jpeg(rng, h, w, mode="RGB", fmt="JPEG"):
 def test_crc32c_and_example_known_answers():
     assert records.crc32c(b"123456789") == 0xE3069283            # CRC-32C check value
     assert records.crc32c(b"") == 0
+    import numpy as np
+    rng = np.random.RandomState(0)
+    for n in (1, 7, 8, 9, 63, 64, 1000, 4099):                    # native slicing-by-8 == per-byte walk
+        blob = rng.randint(0, 256, size=n, dtype=np.uint8).tobytes()
+        assert records.crc32c(blob) == records._crc32c_py(blob), n
     # masked CRC as TFRecord defines it: rotr15(crc) + 0xa282ead8
     c = 0xE3069283
     assert records.masked_crc(b"123456789") == (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
