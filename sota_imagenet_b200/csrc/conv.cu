@@ -151,7 +151,11 @@ __device__ __forceinline__ void igemm_epilogue(
   // One n-tile per launch (Cout <= BN, all the 56x56 layers): every tile of this CTA covers the
   // same columns, so the per-channel sums are accumulated in this warp's s_part slots for the
   // whole kernel and published once at the end -- no named barrier and no 2*BN atomics per tile.
-  const bool cta_sums = p.stats != nullptr && (p.num_n_tiles == 1 || kGroups == 2);
+  // The same holds with several n-tiles when the launcher made the tile step a multiple of their
+  // number (run_igemm): tile % num_n_tiles is then the same for every tile of this CTA.
+  const bool cta_sums = p.stats != nullptr &&
+                        (p.num_n_tiles == 1 || kGroups == 2 || tile_step % p.num_n_tiles == 0);
+  const int n0_cta = (first_tile % p.num_n_tiles) * BN;      // this CTA's fixed column offset (cta_sums)
   float2 acc1[kChunksPerWarp][4], acc2[kChunksPerWarp][4];
 #pragma unroll
   for (int ci = 0; ci < kChunksPerWarp; ++ci) {
@@ -414,7 +418,7 @@ __device__ __forceinline__ void igemm_epilogue(
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     for (int idx = et; idx < BN / 2; idx += 32 * kEpiWarps) {
       const int kind = idx / (BN / 4), c = (idx - kind * (BN / 4)) * 4;
-      if (c < p.Cout) {
+      if (n0_cta + c < p.Cout) {
         const int chunk = c >> 6;
         const int h = chunk % kHalves, ci = chunk / kHalves, lc = ci * 64 + (c & 63);
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -423,7 +427,7 @@ __device__ __forceinline__ void igemm_epilogue(
           const float4 v = *reinterpret_cast<const float4*>(&s_part[((h * 4 + q) * 2 + kind) * kPartStride + lc]);
           t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
-        red_add_v4(p.stats + kind * p.stat_c + c % p.stat_c, t.x, t.y, t.z, t.w);
+        red_add_v4(p.stats + kind * p.stat_c + (n0_cta + c) % p.stat_c, t.x, t.y, t.z, t.w);
       }
     }
   }
@@ -1496,6 +1500,9 @@ static int launch_igemm(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t 
   }
   int grid = p.num_m_tiles * p.num_n_tiles;
   if (grid > sm_count()) grid = sm_count();
+  // a tile step that is a multiple of the n-tile count pins every CTA to ONE n-tile: its per-channel
+  // sums then live in registers for the whole kernel (no per-tile barrier + atomics, igemm_epilogue)
+  if (p.stats != nullptr && p.num_n_tiles > 1 && grid >= p.num_n_tiles) grid -= grid % p.num_n_tiles;
   SIB_CUDA(launch_pdl(igemm_kernel<BN, STAGES, SLABS, AUX, PRO, CG>, dim3(grid),
                       dim3(igemm_threads(BN, PRO, CG)), smem, stream, tm.a, tm.b, tm.out,
                       tm.res, tm.aux1, tm.aux2, p, pro != nullptr ? *pro : BnPrologue{}));
@@ -1514,6 +1521,7 @@ static int launch_igemm2(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t
   }
   int pairs = (p.num_m_tiles / 2) * p.num_n_tiles;
   if (pairs > sm_count() / 2) pairs = sm_count() / 2;
+  if (p.stats != nullptr && p.num_n_tiles > 1 && pairs >= p.num_n_tiles) pairs -= pairs % p.num_n_tiles;   // (see launch_igemm)
   SIB_CUDA(launch_pdl(igemm2_kernel<BN, STAGES, SLABS, AUX>, dim3(2 * pairs), dim3(kIgemmThreads), smem,
                       stream, tm.a, tm.b, tm.out, tm.res, tm.aux1, tm.aux2, p));
   return 0;
