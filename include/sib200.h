@@ -206,6 +206,17 @@ int sib_scale_add_act(const void* x, const float* mul, const float* add, const v
  * (the ECA gate's backward input, reference model graph: pytorch_tools ECA inside Bottleneck). */
 int sib_act_bwd_reduce(const void* dy, const void* y, const void* x, void* g, float* s1, float* s2,
                        int N, int HW, int C, int act, float slope, void* stream);
+/* The [N][C]-sized algebra of the fused BResNet block tail, one launch per direction.
+ * forward : p = pc * scale + shift, gate = sigmoid(conv1d_k3(p)), gate_k = gate * keep[n] (keep optional),
+ *           mul = gate_k * scale, add = gate_k * shift  (inputs of sib_scale_add_act).
+ * backward: from s1 / s2 of sib_act_bwd_reduce: the ECA filter gradient dw[3] (+=), the pooled-path term
+ *           add_nc = dp / HW and the BatchNorm-backward sums[2][C] (+=) of d = g * gate_k + add_nc. */
+int sib_eca_tail_fwd(const float* pc, const float* scale_shift, const float* w, const float* keep, float* p,
+                     float* gate, float* gate_k, float* mul, float* add, int N, int C, void* stream);
+int sib_eca_tail_bwd(const float* s1, const float* s2, const float* scale_shift, const float* mean_invstd,
+                     const float* pc, const float* p, const float* gate, const float* gate_k,
+                     const float* keep, const float* w, float* add_nc, float* sums, float* dw, int N, int C,
+                     float hw, void* stream);
 /* sib_bn_bwd_apply for an activation-free BatchNorm whose incoming gradient is
  * dy * dy_mul[n][c] + dy_add[n][c]: the gate scale of the block tail folded into the BN backward. */
 int sib_bn_bwd_apply_scaled(const void* dy, const float* dy_mul, const float* dy_add, const void* x,
@@ -270,6 +281,14 @@ int sib_weight_standardize(const float* w, const float* gain, void* out_bf16, fl
                            int out_channels, int fan, float eps, void* stream);
 int sib_weight_standardize_bwd(const float* w, const float* gain, const float* mean_invstd,
                                const float* g, float* dw, int out_channels, int fan, void* stream);
+/* The same two maps for EVERY standardised filter of a parameter arena in one launch each (52 tensors
+ * in BResNet-50): params / shadow / grads are the flat arenas, table_dev an array of n records
+ * {long off; long mi_off; int K; int fan; int block_base; int pad} (one block per output channel),
+ * mean_invstd the flat [sum K][2] buffer; the backward rewrites `grads` in place. */
+int sib_weight_standardize_batch(const float* params, void* shadow_bf16, float* mean_invstd,
+                                 const void* table_dev, int n, int total_blocks, float eps, void* stream);
+int sib_weight_standardize_bwd_batch(const float* params, const float* mean_invstd, float* grads,
+                                     const void* table_dev, int n, int total_blocks, void* stream);
 
 /* ---- data: DALI train pipeline (dali_dataloader.py:65-74,113-123) on synthetic uint8 ---- */
 int sib_rrc_boxes(int* boxes_dev, int B, int H, int W, double min_area, double max_area,

@@ -103,24 +103,35 @@ class ParamArena:
         return (e[1], e[2]) if e is not None else None
 
     def enable_weight_standardization(self, params, eps=1e-7):
+        """One table for all standardised filters: forward (shadow refresh) and backward (gradient
+        transform) are ONE launch each over the flat arenas instead of one per tensor."""
+        import numpy as np
         self.ws_eps = eps
         self.ws_entries = []
-        for p in params:
+        total_k = sum(p.shape[0] for p in params)
+        self.ws_mi = torch.empty((max(total_k, 1), 2), dtype=torch.float32, device=self.device)
+        rec = np.zeros(len(params), dtype=np.dtype([("off", "<i8"), ("mi_off", "<i8"), ("K", "<i4"),
+                                                    ("fan", "<i4"), ("bb", "<i4"), ("pad", "<i4")]))
+        kb = 0
+        for i, p in enumerate(params):
             k = p.shape[0]
-            mi = torch.empty((k, 2), dtype=torch.float32, device=self.device)
-            self.ws_entries.append((p, mi))
+            rec[i] = (self.offset_of[id(p)], kb, k, p.numel() // k, kb, 0)
+            self.ws_entries.append((p, self.ws_mi[kb:kb + k]))
+            kb += k
+        self.ws_blocks = kb
+        self.ws_table = torch.from_numpy(rec.view(np.uint8).copy()).to(self.device)
         self._sig = None
 
     def standardize_shadow(self):
-        for p, mi in self.ws_entries:
-            o, n, k = self.offset_of[id(p)], p.numel(), p.shape[0]
-            ops.weight_standardize(self.flat[o:o + n], self.shadow[o:o + n], mi, k, n // k, self.ws_eps)
+        if self.ws_entries:
+            ops.call("sib_weight_standardize_batch", ops._p(self.flat), ops._p(self.shadow), ops._p(self.ws_mi),
+                     ops._p(self.ws_table), len(self.ws_entries), self.ws_blocks, float(self.ws_eps), ops._stream())
 
     def standardize_grads(self):
         """dL/dw from dL/d(standardised w), in place in the gradient arena (end of backward)."""
-        for p, mi in self.ws_entries:
-            o, n, k = self.offset_of[id(p)], p.numel(), p.shape[0]
-            ops.weight_standardize_bwd(self.flat[o:o + n], mi, self.grad[o:o + n], k, n // k)
+        if self.ws_entries:
+            ops.call("sib_weight_standardize_bwd_batch", ops._p(self.flat), ops._p(self.ws_mi), ops._p(self.grad),
+                     ops._p(self.ws_table), len(self.ws_entries), self.ws_blocks, ops._stream())
 
     def mark_fresh(self):
         """Called by the fused optimizer after it rewrote params + shadow itself."""

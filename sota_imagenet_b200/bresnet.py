@@ -350,15 +350,15 @@ class BBottleneck(SibModule):
         cnt3 = n * h * w * world
         mi3, ss3 = ops.bn_finalize(*args, cnt3, bn3.eps, bn3.momentum)
         pc = ops.chan_reduce(c3, scale=1.0 / (h * w))              # mean_hw of the raw conv output
-        p = torch.addcmul(ss3[1], pc, ss3[0])                       # = mean_hw(bn3(c3)): what ECA pools
-        gate = ops.eca_gate_fwd(p, self.eca.weight.data.view(3).contiguous())
+        keep = None
         if self.keep_prob < 1.0:
             keep = (torch.rand(n, 1, device=c3.device) < self.keep_prob).float() / self.keep_prob
-            gate_k = gate * keep
-        else:
-            keep, gate_k = None, gate
+        # p = mean_hw(bn3(c3)) (what ECA pools), the gate (* keep) and the output pass's coefficients
+        p, gate, gate_k, mul, add = (torch.empty_like(pc) for _ in range(5))
+        ops.call("sib_eca_tail_fwd", ops._p(pc), ops._p(ss3), ops._p(self.eca.weight.data.view(3)), ops._p(keep),
+                 ops._p(p), ops._p(gate), ops._p(gate_k), ops._p(mul), ops._p(add), n, c, ops._stream())
         r, xs, sd = self._shortcut(x, True)
-        out = ops.scale_add_act(c3, gate_k * ss3[0], r, self.act, self.bn1.slope, add=gate_k * ss3[1])
+        out = ops.scale_add_act(c3, mul, r, self.act, self.bn1.slope, add=add)
         tail = (c3, mi3, ss3, cnt3, pc, p, gate, gate_k, keep)
         return out, (x, a1, s1, a2, s2, a2b, sb, ("fused", tail), None, None, xs, sd, out)
 
@@ -369,21 +369,19 @@ class BBottleneck(SibModule):
         n, c, h, w = c3.shape
         hw = float(h * w)
         g, s1, s2 = ops.act_bwd_reduce(_as_act(dout), out, c3, self.act, self.bn1.slope)
-        mean, invstd = mi3[0], mi3[1]
-        # ECA: gated = y3 * gate * keep, y3 = c3 * scale + shift  =>  d/d(gate) = keep * sum_hw g * y3
-        ds = torch.addcmul(ss3[1] * s1, s2, ss3[0])
-        if keep is not None:
-            ds = ds * keep
-        dw = torch.zeros(3, dtype=torch.float32, device=c3.device)
-        dp = ops.eca_gate_bwd(ds.contiguous(), gate, p, self.eca.weight.data.view(3).contiguous(), dw)
-        self.eca._grad(self.eca.weight).view(3).add_(dw)
-        add_nc = dp / hw                                         # pooled path, broadcast over (h, w)
-        # BatchNorm-backward sums of d = g * gate_k + add_nc, from the per-(sample, channel) sums
-        gx = invstd * (s2 - mean * s1)                           # sum_hw g * xhat
-        xh = invstd * hw * (pc - mean)                           # sum_hw xhat
-        sums = torch.stack([(gate_k * s1 + add_nc * hw).sum(0), (gate_k * gx + add_nc * xh).sum(0)]).contiguous()
+        # one small kernel: ECA filter gradient (straight into the gradient arena), the pooled-path term
+        # add_nc = dp / HW, and the BatchNorm-backward sums of d = g * gate_k + add_nc derived from the
+        # per-(sample, channel) sums (sum_hw g * xhat = invstd * (s2 - mean * s1), sum_hw xhat = invstd * HW *
+        # (pc - mean))
+        add_nc = torch.empty_like(s1)
+        sums = ops.new_acc(2, c, c3.device)
+        if not ops._ACC_POOL.owns(sums):
+            sums.zero_()
+        ops.call("sib_eca_tail_bwd", ops._p(s1), ops._p(s2), ops._p(ss3), ops._p(mi3), ops._p(pc), ops._p(p),
+                 ops._p(gate), ops._p(gate_k), ops._p(keep), ops._p(self.eca.weight.data.view(3)), ops._p(add_nc),
+                 ops._p(sums), ops._p(self.eca._grad(self.eca.weight).view(3)), n, c, hw, ops._stream())
         sums = bn3.reduce_sums(sums)
-        dc3 = ops.bn_bwd_apply_scaled(g, gate_k.contiguous(), add_nc.contiguous(), c3, mi3, bn3.weight.data, sums,
+        dc3 = ops.bn_bwd_apply_scaled(g, gate_k, add_nc, c3, mi3, bn3.weight.data, sums,
                                       cnt3, param_grads=bn3.grad_ptrs())
         return g, dc3
 

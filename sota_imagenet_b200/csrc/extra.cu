@@ -331,6 +331,76 @@ __global__ void eca_gate_bwd_kernel(const float* __restrict__ ds, const float* _
   }
 }
 
+// Fused block-tail coefficient kernels (BResNet, bresnet.FUSE_BN3_TAIL): all the [N][C]-sized algebra
+// between the wide passes in ONE launch per direction instead of a dozen elementwise launches.
+//   forward : p = pc * scale + shift (= mean_hw of bn3's output), gate = sigmoid(conv1d_k3(p)),
+//             gate_k = gate * keep[n]; mul = gate_k * scale, add = gate_k * shift for scale_add_act
+__global__ void eca_tail_fwd_kernel(const float* __restrict__ pc, const float* __restrict__ ss,
+                                    const float* __restrict__ w, const float* __restrict__ keep,
+                                    float* __restrict__ p, float* __restrict__ gate,
+                                    float* __restrict__ gate_k, float* __restrict__ mul,
+                                    float* __restrict__ add, int N, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int c = i % C, n = i / C;
+  auto pv = [&](int cc) { return fmaf(pc[n * C + cc], ss[cc], ss[C + cc]); };
+  const float p1 = pv(c);
+  float z = w[1] * p1;
+  if (c > 0) z += w[0] * pv(c - 1);
+  if (c + 1 < C) z += w[2] * pv(c + 1);
+  const float g = 1.f / (1.f + __expf(-z));
+  const float gk = keep != nullptr ? g * keep[n] : g;
+  p[i] = p1;
+  gate[i] = g;
+  gate_k[i] = gk;
+  mul[i] = gk * ss[c];
+  add[i] = gk * ss[C + c];
+}
+
+//   backward: from s1 = sum_hw g, s2 = sum_hw g * c3 (act_bwd_reduce):
+//             ds = (scale * s2 + shift * s1) * keep      (d/d gate of y3 * gate * keep, y3 = c3*scale+shift)
+//             dp = conv1d backward of ds * gate * (1 - gate); dw[k] += sum dz * p[c + k - 1]
+//             add_nc = dp / HW                           (pooled-path gradient w.r.t. y3)
+//             BatchNorm-backward sums of d = g * gate_k + add_nc:
+//               sums[0][c] += gate_k * s1 + add_nc * HW
+//               sums[1][c] += gate_k * invstd * (s2 - mean * s1) + add_nc * invstd * HW * (pc - mean)
+__global__ void eca_tail_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
+                                    const float* __restrict__ ss, const float* __restrict__ mi,
+                                    const float* __restrict__ pc, const float* __restrict__ p,
+                                    const float* __restrict__ gate, const float* __restrict__ gate_k,
+                                    const float* __restrict__ keep, const float* __restrict__ w,
+                                    float* __restrict__ add_nc, float* __restrict__ sums,
+                                    float* __restrict__ dw, int N, int C, float hw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  if (i < N * C) {
+    const int c = i % C, n = i / C;
+    const float kp = keep != nullptr ? keep[n] : 1.f;
+    auto dz = [&](int cc) {
+      const int j = n * C + cc;
+      const float ds = fmaf(ss[cc], s2[j], ss[C + cc] * s1[j]) * kp;
+      const float sv = gate[j];
+      return ds * sv * (1.f - sv);
+    };
+    const float z1 = dz(c);
+    float dp = w[1] * z1;
+    if (c + 1 < C) dp += w[0] * dz(c + 1);
+    if (c > 0) dp += w[2] * dz(c - 1);
+    g1 = z1 * p[i];
+    if (c > 0) g0 = z1 * p[i - 1];
+    if (c + 1 < C) g2 = z1 * p[i + 1];
+    const float a = dp / hw;
+    add_nc[i] = a;
+    const float mean = mi[c], invstd = mi[C + c], gk = gate_k[i];
+    atomicAdd(sums + c, fmaf(gk, s1[i], a * hw));
+    atomicAdd(sums + C + c, fmaf(gk, invstd * (s2[i] - mean * s1[i]), a * invstd * hw * (pc[i] - mean)));
+  }
+  g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(dw + 0, g0); atomicAdd(dw + 1, g1); atomicAdd(dw + 2, g2);
+  }
+}
+
 // y = act(a + b);   backward: g = dy * act'(y)
 __global__ void __launch_bounds__(256)
 add_act_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
@@ -485,6 +555,24 @@ extern "C" int sib_chan_reduce(const void* a, const void* b, float* out, int N, 
   SIB_CHECK(C % 8 == 0, "chan_reduce: C %% 8 != 0");
   dim3 grid((C / 8 + 7) / 8, N);
   chan_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(a), CBF(b), out, HW, C, scale);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int sib_eca_tail_fwd(const float* pc, const float* scale_shift, const float* w, const float* keep,
+                                float* p, float* gate, float* gate_k, float* mul, float* add, int N, int C,
+                                void* stream) {
+  eca_tail_fwd_kernel<<<(N * C + 255) / 256, 256, 0, ST(stream)>>>(pc, scale_shift, w, keep, p, gate, gate_k,
+                                                                   mul, add, N, C);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+// sums [2][C] and dw [3] must be zero on entry (they are accumulated with atomics)
+extern "C" int sib_eca_tail_bwd(const float* s1, const float* s2, const float* scale_shift,
+                                const float* mean_invstd, const float* pc, const float* p, const float* gate,
+                                const float* gate_k, const float* keep, const float* w, float* add_nc,
+                                float* sums, float* dw, int N, int C, float hw, void* stream) {
+  eca_tail_bwd_kernel<<<(N * C + 255) / 256, 256, 0, ST(stream)>>>(s1, s2, scale_shift, mean_invstd, pc, p, gate,
+                                                                   gate_k, keep, w, add_nc, sums, dw, N, C, hw);
   SIB_LAUNCH_CHECK();
   return 0;
 }

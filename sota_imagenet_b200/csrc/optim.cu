@@ -361,6 +361,80 @@ weight_std_bwd_kernel(const float* __restrict__ w, const float* __restrict__ gai
   }
 }
 
+// All weight-standardised filters of an arena in ONE launch (forward and backward): a table maps
+// block ranges to tensors (one block per output channel, as in the per-tensor kernels above).
+struct WsEntry {
+  long off;          // element offset of the tensor inside the flat parameter / shadow / gradient arenas
+  long mi_off;       // offset (in channels) into the flat mean/invstd buffer
+  int K, fan;
+  int block_base;    // first block of this tensor
+  int pad;
+};
+
+__device__ __forceinline__ int ws_find(const WsEntry* __restrict__ tab, int n, int block) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].block_base <= block) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+weight_std_batch_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                        float* __restrict__ mean_invstd, const WsEntry* __restrict__ tab, int n,
+                        float eps) {
+  __shared__ float sh[2][32];
+  const WsEntry e = tab[ws_find(tab, n, blockIdx.x)];
+  const long o = blockIdx.x - e.block_base;
+  const float* wp = w + e.off + o * e.fan;
+  float s = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < e.fan; i += blockDim.x) {
+    const float v = wp[i];
+    s += v;
+    s2 += v * v;
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  s = 0.f; s2 = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) { s += sh[0][i]; s2 += sh[1][i]; }
+  const float mean = s / e.fan;
+  const float var = fmaxf(s2 / e.fan - mean * mean, 0.f);
+  const float invstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) { mean_invstd[2 * (e.mi_off + o)] = mean; mean_invstd[2 * (e.mi_off + o) + 1] = invstd; }
+  __nv_bfloat16* op = out + e.off + o * e.fan;
+  for (int i = threadIdx.x; i < e.fan; i += blockDim.x) op[i] = __float2bfloat16_rn((wp[i] - mean) * invstd);
+}
+
+__global__ void __launch_bounds__(256)
+weight_std_bwd_batch_kernel(const float* __restrict__ w, const float* __restrict__ mean_invstd,
+                            float* __restrict__ g, const WsEntry* __restrict__ tab, int n) {
+  __shared__ float sh[2][32];
+  const WsEntry e = tab[ws_find(tab, n, blockIdx.x)];
+  const long o = blockIdx.x - e.block_base;
+  const float mean = mean_invstd[2 * (e.mi_off + o)], invstd = mean_invstd[2 * (e.mi_off + o) + 1];
+  const float* wp = w + e.off + o * e.fan;
+  float* gp = g + e.off + o * e.fan;
+  float s = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < e.fan; i += blockDim.x) {
+    const float gv = gp[i];
+    s += gv;
+    s2 += gv * ((wp[i] - mean) * invstd);
+  }
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  s = 0.f; s2 = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) { s += sh[0][i]; s2 += sh[1][i]; }
+  for (int i = threadIdx.x; i < e.fan; i += blockDim.x) {
+    const float wh = (wp[i] - mean) * invstd;
+    gp[i] = invstd * (gp[i] - s / e.fan - wh * s2 / e.fan);
+  }
+}
+
 static inline int ew_grid(long n, int threads) {
   long b = (n + threads - 1) / threads;
   long cap = (long)sm_count() * 16;
@@ -446,6 +520,29 @@ extern "C" int sib_weight_standardize(const float* w, const float* gain, void* o
                                       void* stream) {
   weight_std_kernel<<<out_channels, 256, 0, ST(stream)>>>(
       w, gain, static_cast<__nv_bfloat16*>(out_bf16), mean_invstd, fan, eps);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// every standardised filter of an arena in one launch; table_dev: WsEntry[n] (see arena.py)
+extern "C" int sib_weight_standardize_batch(const float* params, void* shadow_bf16, float* mean_invstd,
+                                            const void* table_dev, int n, int total_blocks, float eps,
+                                            void* stream) {
+  if (n <= 0 || total_blocks <= 0) return 0;
+  weight_std_batch_kernel<<<total_blocks, 256, 0, ST(stream)>>>(
+      params, static_cast<__nv_bfloat16*>(shadow_bf16), mean_invstd, static_cast<const WsEntry*>(table_dev), n, eps);
+  SIB_LAUNCH_CHECK();
+  return 0;
+}
+
+// gradient w.r.t. the raw filters from the gradient w.r.t. the standardised ones, in place in the
+// flat gradient arena
+extern "C" int sib_weight_standardize_bwd_batch(const float* params, const float* mean_invstd, float* grads,
+                                                const void* table_dev, int n, int total_blocks,
+                                                void* stream) {
+  if (n <= 0 || total_blocks <= 0) return 0;
+  weight_std_bwd_batch_kernel<<<total_blocks, 256, 0, ST(stream)>>>(params, mean_invstd, grads,
+                                                                    static_cast<const WsEntry*>(table_dev), n);
   SIB_LAUNCH_CHECK();
   return 0;
 }
