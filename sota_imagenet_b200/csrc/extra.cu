@@ -364,40 +364,60 @@ __global__ void eca_tail_fwd_kernel(const float* __restrict__ pc, const float* _
 //             BatchNorm-backward sums of d = g * gate_k + add_nc:
 //               sums[0][c] += gate_k * s1 + add_nc * HW
 //               sums[1][c] += gate_k * invstd * (s2 - mean * s1) + add_nc * invstd * HW * (pc - mean)
-__global__ void eca_tail_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
-                                    const float* __restrict__ ss, const float* __restrict__ mi,
-                                    const float* __restrict__ pc, const float* __restrict__ p,
-                                    const float* __restrict__ gate, const float* __restrict__ gate_k,
-                                    const float* __restrict__ keep, const float* __restrict__ w,
-                                    float* __restrict__ add_nc, float* __restrict__ sums,
-                                    float* __restrict__ dw, int N, int C, float hw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-  if (i < N * C) {
-    const int c = i % C, n = i / C;
-    const float kp = keep != nullptr ? keep[n] : 1.f;
-    auto dz = [&](int cc) {
-      const int j = n * C + cc;
-      const float ds = fmaf(ss[cc], s2[j], ss[C + cc] * s1[j]) * kp;
-      const float sv = gate[j];
-      return ds * sv * (1.f - sv);
-    };
-    const float z1 = dz(c);
-    float dp = w[1] * z1;
-    if (c + 1 < C) dp += w[0] * dz(c + 1);
-    if (c > 0) dp += w[2] * dz(c - 1);
-    g1 = z1 * p[i];
-    if (c > 0) g0 = z1 * p[i - 1];
-    if (c + 1 < C) g2 = z1 * p[i + 1];
-    const float a = dp / hw;
-    add_nc[i] = a;
-    const float mean = mi[c], invstd = mi[C + c], gk = gate_k[i];
-    atomicAdd(sums + c, fmaf(gk, s1[i], a * hw));
-    atomicAdd(sums + C + c, fmaf(gk, invstd * (s2[i] - mean * s1[i]), a * invstd * hw * (pc[i] - mean)));
+__global__ void __launch_bounds__(256)
+eca_tail_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
+                    const float* __restrict__ ss, const float* __restrict__ mi,
+                    const float* __restrict__ pc, const float* __restrict__ p,
+                    const float* __restrict__ gate, const float* __restrict__ gate_k,
+                    const float* __restrict__ keep, const float* __restrict__ w,
+                    float* __restrict__ add_nc, float* __restrict__ sums,
+                    float* __restrict__ dw, int N, int C, float hw) {
+  // a block owns 32 channels for ALL samples (8 sample lanes): the per-channel sums over n are
+  // combined in shared memory and written once -- no same-address atomics
+  __shared__ float red[2][8][32];
+  const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    const float mean = mi[c], invstd = mi[C + c];
+    const float w0 = w[0], w1 = w[1], w2 = w[2];
+    for (int n = nl; n < N; n += 8) {
+      const int i = n * C + c;
+      const float kp = keep != nullptr ? keep[n] : 1.f;
+      auto dz = [&](int cc) {
+        const int j = n * C + cc;
+        const float ds = fmaf(ss[cc], s2[j], ss[C + cc] * s1[j]) * kp;
+        const float sv = gate[j];
+        return ds * sv * (1.f - sv);
+      };
+      const float z1 = dz(c);
+      float dp = w1 * z1;
+      if (c + 1 < C) dp += w0 * dz(c + 1);
+      if (c > 0) dp += w2 * dz(c - 1);
+      g1 = fmaf(z1, p[i], g1);
+      if (c > 0) g0 = fmaf(z1, p[i - 1], g0);
+      if (c + 1 < C) g2 = fmaf(z1, p[i + 1], g2);
+      const float a = dp / hw;
+      add_nc[i] = a;
+      const float gk = gate_k[i];
+      a0 += fmaf(gk, s1[i], a * hw);
+      a1 += fmaf(gk, invstd * (s2[i] - mean * s1[i]), a * invstd * hw * (pc[i] - mean));
+    }
   }
+  red[0][nl][cl] = a0;
+  red[1][nl][cl] = a1;
   g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
-  if ((threadIdx.x & 31) == 0) {
+  if (cl == 0) {
     atomicAdd(dw + 0, g0); atomicAdd(dw + 1, g1); atomicAdd(dw + 2, g2);
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x >> 5;
+    const int cc = blockIdx.x * 32 + cl;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[k][r][cl];
+    if (cc < C) sums[k * C + cc] += t;       // this block is the only writer of these channels
   }
 }
 
@@ -571,8 +591,8 @@ extern "C" int sib_eca_tail_bwd(const float* s1, const float* s2, const float* s
                                 const float* mean_invstd, const float* pc, const float* p, const float* gate,
                                 const float* gate_k, const float* keep, const float* w, float* add_nc,
                                 float* sums, float* dw, int N, int C, float hw, void* stream) {
-  eca_tail_bwd_kernel<<<(N * C + 255) / 256, 256, 0, ST(stream)>>>(s1, s2, scale_shift, mean_invstd, pc, p, gate,
-                                                                   gate_k, keep, w, add_nc, sums, dw, N, C, hw);
+  eca_tail_bwd_kernel<<<(C + 31) / 32, 256, 0, ST(stream)>>>(s1, s2, scale_shift, mean_invstd, pc, p, gate,
+                                                             gate_k, keep, w, add_nc, sums, dw, N, C, hw);
   SIB_LAUNCH_CHECK();
   return 0;
 }
