@@ -100,59 +100,22 @@ augment_kernel(const uint8_t* __restrict__ src, const int* __restrict__ boxes, v
     const float cx = ((float)sx_out + 0.5f) * scx, cy = ((float)oy + 0.5f) * scy;
     const int xlo = (int)floorf(cx - supx), xhi = (int)ceilf(cx + supx);
     const int ylo = (int)floorf(cy - supy), yhi = (int)ceilf(cy + supy);
-    // The triangular filter is separable: the column weights (and clamped source columns) are the
-    // same for every row of the footprint, so they are evaluated once per output pixel (up to 8 taps
-    // in registers: crops up to 3.5x the output size; wider footprints take the generic loop below).
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, wsum = 0.f;
     const uint8_t* img = src + (long)n * SH * SW * 3;
-    const int ntx = xhi - xlo;
-    if (ntx <= 8) {
-      float wxs[8];
-      int offx[8];
-      float wxsum = 0.f;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int xx = xlo + t;
-        const float wx = t < ntx ? fmaxf(0.f, 1.f - fabsf(((float)xx + 0.5f - cx) / supx)) : 0.f;
-        wxs[t] = wx;
-        offx[t] = (min(max(xx, 0), cw - 1) + x0) * 3;
-        wxsum += wx;
-      }
-      for (int yy = ylo; yy < yhi; ++yy) {
-        const float wy = fmaxf(0.f, 1.f - fabsf(((float)yy + 0.5f - cy) / supy));
-        if (wy <= 0.f) continue;
-        const uint8_t* row = img + (long)(min(max(yy, 0), ch - 1) + y0) * SW * 3;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          if (t < ntx && wxs[t] > 0.f) {
-            const uint8_t* px = row + offx[t];
-            r0 = fmaf(wxs[t], (float)px[0], r0);
-            r1 = fmaf(wxs[t], (float)px[1], r1);
-            r2 = fmaf(wxs[t], (float)px[2], r2);
-          }
-        }
-        acc0 = fmaf(wy, r0, acc0);
-        acc1 = fmaf(wy, r1, acc1);
-        acc2 = fmaf(wy, r2, acc2);
-        wsum = fmaf(wy, wxsum, wsum);
-      }
-    } else {
-      for (int yy = ylo; yy < yhi; ++yy) {
-        const float wy = fmaxf(0.f, 1.f - fabsf(((float)yy + 0.5f - cy) / supy));
-        if (wy <= 0.f) continue;
-        const int sy = min(max(yy, 0), ch - 1) + y0;
-        for (int xx = xlo; xx < xhi; ++xx) {
-          const float wx = fmaxf(0.f, 1.f - fabsf(((float)xx + 0.5f - cx) / supx));
-          if (wx <= 0.f) continue;
-          const int sx = min(max(xx, 0), cw - 1) + x0;
-          const uint8_t* px = img + ((long)sy * SW + sx) * 3;
-          const float w = wx * wy;
-          acc0 = fmaf(w, (float)px[0], acc0);
-          acc1 = fmaf(w, (float)px[1], acc1);
-          acc2 = fmaf(w, (float)px[2], acc2);
-          wsum += w;
-        }
+    for (int yy = ylo; yy < yhi; ++yy) {
+      const float wy = fmaxf(0.f, 1.f - fabsf(((float)yy + 0.5f - cy) / supy));
+      if (wy <= 0.f) continue;
+      const int sy = min(max(yy, 0), ch - 1) + y0;
+      for (int xx = xlo; xx < xhi; ++xx) {
+        const float wx = fmaxf(0.f, 1.f - fabsf(((float)xx + 0.5f - cx) / supx));
+        if (wx <= 0.f) continue;
+        const int sx = min(max(xx, 0), cw - 1) + x0;
+        const uint8_t* px = img + ((long)sy * SW + sx) * 3;
+        const float w = wx * wy;
+        acc0 = fmaf(w, (float)px[0], acc0);
+        acc1 = fmaf(w, (float)px[1], acc1);
+        acc2 = fmaf(w, (float)px[2], acc2);
+        wsum += w;
       }
     }
     const float inv = 1.f / wsum;
