@@ -238,6 +238,7 @@ int sib_ce_fwd_bwd(const void* logits, int logits_fp32, const long* labels,
 int sib_sphere_linear_fwd(const float* x, const float* w, float* cosv, float* xn, float* wn,
                           float* xnorm, float* wnorm, int B, int C, int D, int normalize_x,
                           void* stream);
+/* scratch: (B + C) * D floats (d(xn) and d(wn) come out of ONE tensor-core launch) */
 int sib_sphere_linear_bwd(const float* dcos, const float* x_or_xn, const float* wn,
                           const float* xnorm, const float* wnorm, float* dx, float* dw,
                           float* scratch, int B, int C, int D, int normalize_x, void* stream);

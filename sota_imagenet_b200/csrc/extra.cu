@@ -371,17 +371,23 @@ eca_tail_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
                     const float* __restrict__ gate, const float* __restrict__ gate_k,
                     const float* __restrict__ keep, const float* __restrict__ w,
                     float* __restrict__ add_nc, float* __restrict__ sums,
-                    float* __restrict__ dw, int N, int C, float hw) {
-  // a block owns 32 channels for ALL samples (8 sample lanes): the per-channel sums over n are
-  // combined in shared memory and written once -- no same-address atomics
+                    float* __restrict__ dw, int N, int C, float hw, int n_per) {
+  // a block owns 32 channels of a RANGE of samples (blockIdx.y; 8 sample lanes): the per-channel sums
+  // over its samples are combined in shared memory and published with one atomic per (block, channel,
+  // sum) -- at most gridDim.y adds per address; the three filter gradients with 3 atomics per block.
+  // The launcher sizes the grid to ~128 blocks: the former one-block-per-32-channels layout walked all
+  // 256 samples in 32 dependent rounds of global loads (48 us per call on 8-64 blocks).
   __shared__ float red[2][8][32];
+  __shared__ float redw[3][8];
   const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  const int n_begin = blockIdx.y * n_per;
+  const int n_end = min(N, n_begin + n_per);
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, a0 = 0.f, a1 = 0.f;
   if (c < C) {
     const float mean = mi[c], invstd = mi[C + c];
     const float w0 = w[0], w1 = w[1], w2 = w[2];
-    for (int n = nl; n < N; n += 8) {
+    for (int n = n_begin + nl; n < n_end; n += 8) {
       const int i = n * C + c;
       const float kp = keep != nullptr ? keep[n] : 1.f;
       auto dz = [&](int cc) {
@@ -407,9 +413,7 @@ eca_tail_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
   red[0][nl][cl] = a0;
   red[1][nl][cl] = a1;
   g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
-  if (cl == 0) {
-    atomicAdd(dw + 0, g0); atomicAdd(dw + 1, g1); atomicAdd(dw + 2, g2);
-  }
+  if (cl == 0) { redw[0][nl] = g0; redw[1][nl] = g1; redw[2][nl] = g2; }
   __syncthreads();
   if (threadIdx.x < 64) {
     const int k = threadIdx.x >> 5;
@@ -417,7 +421,16 @@ eca_tail_bwd_kernel(const float* __restrict__ s1, const float* __restrict__ s2,
     float t = 0.f;
 #pragma unroll
     for (int r = 0; r < 8; ++r) t += red[k][r][cl];
-    if (cc < C) sums[k * C + cc] += t;       // this block is the only writer of these channels
+    if (cc < C) {
+      if (gridDim.y == 1) sums[k * C + cc] += t;     // only writer of these channels
+      else atomicAdd(sums + k * C + cc, t);
+    }
+  } else if (threadIdx.x < 67) {
+    const int k = threadIdx.x - 64;
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += redw[k][r];
+    atomicAdd(dw + k, t);
   }
 }
 
@@ -458,78 +471,114 @@ act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __rest
   }
 }
 
-// 3x3 stride-1 pad-1 max pool (the anti-aliased stem pools at stride 1, then BlurPool)
-__global__ void __launch_bounds__(256)
-maxpool3x3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                        uint8_t* __restrict__ idx, int N, int H, int W, int C) {
-  const int cvec = C >> 3;
-  const long total = (long)N * H * W * cvec;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cvec);
-    long t = i / cvec;
-    const int q = (int)(t % W); t /= W;
-    const int p = (int)(t % H);
-    const int n = (int)(t / H);
-    float best[8];
-    int bi[8];
+// 3x3 stride-1 pad-1 max pool (the anti-aliased stem pools at stride 1, then BlurPool).
+// A thread owns one 8-channel vector of one image COLUMN over a segment of rows and slides down it:
+// per output row it loads the three pixels of the next input row once, reduces them to a row maximum
+// (+ the tap column that won) and combines the three live row maxima -- 3 loads and ~50 compares per
+// output instead of 9 loads and 72 compares, 32-bit index arithmetic outside the loop.  The winning
+// tap r*3+s is the FIRST maximum in (r, s) scan order (strict >), as torch's max_pool2d indices.
+__device__ __forceinline__ void mp_row_max(const __nv_bfloat16* __restrict__ x, long row_base, int C,
+                                           int q, int W, bool row_ok, float* val, uint32_t& sel) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+  for (int j = 0; j < 8; ++j) val[j] = -INFINITY;
+  sel = 0;                                    // 4 bits per channel: winning column tap s
+  if (!row_ok) return;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int h = p - 1 + r;
-      if (h < 0 || h >= H) continue;
+  for (int s = 0; s < 3; ++s) {
+    const int w = q - 1 + s;
+    if (w < 0 || w >= W) continue;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + row_base + (long)w * C)), f);
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int w = q - 1 + s;
-        if (w < 0 || w >= W) continue;
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long)n * H + h) * W + w) * C + v * 8)), f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (f[j] > best[j]) { best[j] = f[j]; bi[j] = r * 3 + s; }
-      }
-    }
-    stg_stream(y + i * 8, pack8(best));
-    uint2 pk;
-    pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-    pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-    *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    for (int j = 0; j < 8; ++j)
+      if (f[j] > val[j]) { val[j] = f[j]; sel = (sel & ~(0xfu << (4 * j))) | ((uint32_t)s << (4 * j)); }
   }
 }
 
 __global__ void __launch_bounds__(256)
-maxpool3x3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
-                        __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+maxpool3x3s1_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                        uint8_t* __restrict__ idx, int N, int H, int W, int C, int segs, int seg_rows) {
   const int cvec = C >> 3;
-  const long total = (long)N * H * W * cvec;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % cvec);
-    long t = i / cvec;
-    const int w = (int)(t % W); t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
-    float acc[8] = {};
-    for (int r = 0; r < 3; ++r) {
-      const int p = h + 1 - r;            // window (p,q) with tap (r,s) lands on (h,w)
-      if (p < 0 || p >= H) continue;
-      for (int s = 0; s < 3; ++s) {
-        const int q = w + 1 - s;
-        if (q < 0 || q >= W) continue;
-        const long o = ((((long)n * H + p) * W + q) * cvec + v) * 8;
-        const uint2 pk = *reinterpret_cast<const uint2*>(idx + o);
-        float g[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), g);
-        const int tap = r * 3 + s;
+  const int total = N * segs * W * cvec;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % cvec;
+    int t = i / cvec;
+    const int q = t % W; t /= W;
+    const int seg = t % segs;
+    const int n = t / segs;
+    const int p0 = seg * seg_rows, p1 = min(H, p0 + seg_rows);
+    const long img = (long)n * H * W * C + v * 8;          // + (h * W + w) * C
+    float va[8], vb[8], vc[8];
+    uint32_t sa, sb, sc;
+    mp_row_max(x, img + (long)(p0 - 1) * W * C, C, q, W, p0 - 1 >= 0, va, sa);
+    mp_row_max(x, img + (long)p0 * W * C, C, q, W, true, vb, sb);
+    for (int p = p0; p < p1; ++p) {
+      mp_row_max(x, img + (long)(p + 1) * W * C, C, q, W, p + 1 < H, vc, sc);
+      float best[8];
+      uint32_t bi[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int bsel = (j < 4 ? (pk.x >> (8 * j)) : (pk.y >> (8 * (j - 4)))) & 0xff;
-          if (bsel == tap) acc[j] += g[j];
+      for (int j = 0; j < 8; ++j) {
+        best[j] = va[j];
+        bi[j] = (sa >> (4 * j)) & 3u;
+        if (vb[j] > best[j]) { best[j] = vb[j]; bi[j] = 3u + ((sb >> (4 * j)) & 3u); }
+        if (vc[j] > best[j]) { best[j] = vc[j]; bi[j] = 6u + ((sc >> (4 * j)) & 3u); }
+      }
+      const long o = img + ((long)p * W + q) * C;
+      stg_stream(y + o, pack8(best));
+      uint2 pk;
+      pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + o) = pk;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { va[j] = vb[j]; vb[j] = vc[j]; }
+      sa = sb; sb = sc;
+    }
+  }
+}
+
+// Backward, same column-sliding layout: source row p holds, for this output column, three candidate
+// pixels (q = w+1-s); a source whose winning tap is (r, s) sends its gradient to output row p-1+r.
+// Three rolling accumulators (rows p-1, p, p+1); row p-1 is complete once source row p is consumed.
+__global__ void __launch_bounds__(256)
+maxpool3x3s1_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                        __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int segs,
+                        int seg_rows) {
+  const int cvec = C >> 3;
+  const int total = N * segs * W * cvec;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % cvec;
+    int t = i / cvec;
+    const int w = t % W; t /= W;
+    const int seg = t % segs;
+    const int n = t / segs;
+    const int h0 = seg * seg_rows, h1 = min(H, h0 + seg_rows);
+    const long img = (long)n * H * W * C + v * 8;
+    float aa[8] = {}, ab[8] = {}, ac[8];
+    for (int p = h0 - 1; p <= h1; ++p) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ac[j] = 0.f;
+      if (p >= 0 && p < H) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int q = w + 1 - s;
+          if (q < 0 || q >= W) continue;
+          const long o = img + ((long)p * W + q) * C;
+          const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + o));
+          float g[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t tap = ((j < 4 ? (pk.x >> (8 * j)) : (pk.y >> (8 * (j - 4)))) & 0xffu) - (uint32_t)s;
+            aa[j] += tap == 0u ? g[j] : 0.f;      // r = 0 -> output row p - 1
+            ab[j] += tap == 3u ? g[j] : 0.f;      // r = 1 -> row p
+            ac[j] += tap == 6u ? g[j] : 0.f;      // r = 2 -> row p + 1
+          }
         }
       }
+      if (p - 1 >= h0) stg_stream(dx + img + ((long)(p - 1) * W + w) * C, pack8(aa));   // (p - 1 < h1 by the loop bound)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { aa[j] = ab[j]; ab[j] = ac[j]; }
     }
-    stg_stream(dx + i * 8, pack8(acc));
   }
 }
 
@@ -591,8 +640,15 @@ extern "C" int sib_eca_tail_bwd(const float* s1, const float* s2, const float* s
                                 const float* mean_invstd, const float* pc, const float* p, const float* gate,
                                 const float* gate_k, const float* keep, const float* w, float* add_nc,
                                 float* sums, float* dw, int N, int C, float hw, void* stream) {
-  eca_tail_bwd_kernel<<<(C + 31) / 32, 256, 0, ST(stream)>>>(s1, s2, scale_shift, mean_invstd, pc, p, gate,
-                                                             gate_k, keep, w, add_nc, sums, dw, N, C, hw);
+  // ~128 blocks: channel groups x sample ranges (multiples of the 8 sample lanes); SIB_DETERMINISTIC=1
+  // keeps one block per channel group (fixed summation order, no atomics on `sums`)
+  static const bool det = [] { const char* e = getenv("SIB_DETERMINISTIC"); return e && e[0] == '1'; }();
+  const int cg = (C + 31) / 32;
+  int ns = det ? 1 : max(1, min(128 / cg, (N + 7) / 8));
+  const int n_per = ((N + ns - 1) / ns + 7) / 8 * 8;
+  ns = (N + n_per - 1) / n_per;
+  eca_tail_bwd_kernel<<<dim3(cg, ns), 256, 0, ST(stream)>>>(s1, s2, scale_shift, mean_invstd, pc, p, gate,
+                                                            gate_k, keep, w, add_nc, sums, dw, N, C, hw, n_per);
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -646,19 +702,35 @@ extern "C" int sib_act_bwd(const void* dy, const void* y, void* g, long n, int a
   SIB_LAUNCH_CHECK();
   return 0;
 }
+// row segments per image column so that ~600 k threads are in flight (each re-reads 2 halo rows)
+static void maxpool_segments(int N, int H, int W, int C, int* segs, int* seg_rows) {
+  const long cols = (long)N * W * (C / 8);
+  long want = (600000 + cols - 1) / cols;
+  if (want < 1) want = 1;
+  if (want > (H + 7) / 8) want = (H + 7) / 8;          // at least 8 rows per segment
+  *seg_rows = (int)((H + want - 1) / want);
+  *segs = (H + *seg_rows - 1) / *seg_rows;
+}
+
 extern "C" int sib_maxpool3x3s1_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C,
                                     void* stream) {
-  SIB_CHECK(C % 8 == 0, "maxpool: C %% 8 != 0");
-  maxpool3x3s1_fwd_kernel<<<ew_grid((long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(x), BF(y), static_cast<uint8_t*>(idx), N, H, W, C);
+  SIB_CHECK(C % 8 == 0, "maxpool3x3s1: C %% 8 != 0");
+  int segs, seg_rows;
+  maxpool_segments(N, H, W, C, &segs, &seg_rows);
+  SIB_CHECK((long)N * segs * W * (C / 8) < (1l << 31), "maxpool3x3s1: tensor too large for 32-bit indexing");
+  maxpool3x3s1_fwd_kernel<<<ew_grid((long)N * segs * W * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(x), BF(y), static_cast<uint8_t*>(idx), N, H, W, C, segs, seg_rows);
   SIB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sib_maxpool3x3s1_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W,
                                     int C, void* stream) {
-  SIB_CHECK(C % 8 == 0, "maxpool: C %% 8 != 0");
-  maxpool3x3s1_bwd_kernel<<<ew_grid((long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(dy), static_cast<const uint8_t*>(idx), BF(dx), N, H, W, C);
+  SIB_CHECK(C % 8 == 0, "maxpool3x3s1: C %% 8 != 0");
+  int segs, seg_rows;
+  maxpool_segments(N, H, W, C, &segs, &seg_rows);
+  SIB_CHECK((long)N * segs * W * (C / 8) < (1l << 31), "maxpool3x3s1: tensor too large for 32-bit indexing");
+  maxpool3x3s1_bwd_kernel<<<ew_grid((long)N * segs * W * (C / 8), 256), 256, 0, ST(stream)>>>(
+      CBF(dy), static_cast<const uint8_t*>(idx), BF(dx), N, H, W, C, segs, seg_rows);
   SIB_LAUNCH_CHECK();
   return 0;
 }

@@ -5,7 +5,8 @@
 //   * ArcFace (reference angular_losses.py:128-146) and CosFace (angular_losses.py:186-198,
 //     332-333) margins applied to cosine logits inside the same kernel;
 //   * SphereLinearLayer (angular_losses.py:212-214): cos = normalize(x) . normalize(W)^T with
-//     its backward through both normalisations.  fp32 throughout (tiny problem: B x 1000 x 512).
+//     its backward through both normalisations.  fp32 operands and results; the three GEMMs
+//     run on the tensor cores with every operand split into three bf16 terms (tc_gemm_f32x3_kernel).
 #include "common.cuh"
 #include "host.h"
 #include "../../include/sib200.h"
@@ -152,74 +153,250 @@ __global__ void mean_kernel(const float* __restrict__ v, int n, float* __restric
 }
 
 // ---------------------------------------------------------------------------
-// small fp32 GEMM family for the sphere-linear head
-//   C[M][N] = sum_k A(m,k) * B(n,k)      (A: [M][K] or [K][M] via strides, same for B)
+// fp32-accurate GEMM on the tensor cores for the sphere-linear head
+//   C[M][N] = sum_k A(m,k) * B(n,k)      A(m,k) = A[m*a_sm + k*a_sk], B(n,k) = B[n*b_sn + k*b_sk]
+// The operands are fp32 in HBM (unit rows: the cosines feed acos / margins, and the reference's
+// goldens hold them to 1e-6).  Every 8-element run of K is split on the fly into THREE bf16
+// terms x = h + m + l (8 + 8 + 8 significant bits: the split is exact up to 2^-24 |x|), written by
+// ordinary stores into the K-major 128B-swizzled layout a UMMA descriptor expects (row r at
+// r*128 bytes, 16-byte chunk c at position c ^ (r&7)) and published to the async proxy; a k-block's
+// product is the six bf16 MMAs whose weight is >= 2^-16 (l*h, h*l, m*m, m*h, h*m, h*h; tcgen05.mma
+// kind::f16, M = 128, N = 64, K = 16), smallest terms first, in a TMEM accumulator that is
+// CLEARED per k-block: the running sum over k-blocks lives in registers (round-to-nearest fp32
+// adds), because the tensor core's own fp32 accumulation truncates and 100 chained accumulations
+// cost ~1e-6 of the result (measured).  Either stride of an operand may be the contiguous one: the
+// (row, chunk) -> thread mapping follows it, so global reads are coalesced for both orientations
+// (dcos and dcos^T, wn and wn^T) and no transposed copy is ever made.  Two stages and two
+// accumulators: the split of k-block i+1 overlaps the MMAs of k-block i.  Up to two independent
+// problems per launch (blockIdx.z): the backward computes d(xn) and d(wn) with one kernel.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-sgemm_kernel(const float* __restrict__ A, long a_sm, long a_sk, const float* __restrict__ Bm,
-             long b_sn, long b_sk, float* __restrict__ Cm, int M, int N, int K) {
-  __shared__ float As[16][64 + 1];
-  __shared__ float Bs[16][64 + 1];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int kk = i & 15, mm = i >> 4;
-      const int m = m0 + mm, n = n0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < K) ? A[m * a_sm + k * a_sk] : 0.f;
-      Bs[kk][mm] = (n < N && k < K) ? Bm[n * b_sn + k * b_sk] : 0.f;
+struct TcGemm {
+  const float* A; long a_sm, a_sk;
+  const float* B; long b_sn, b_sk;
+  float* C;            // [M][N] row-major
+  int M, N, K;
+};
+struct TcGemmBatch { TcGemm g[2]; };
+
+constexpr int kTcBM = 128, kTcBN = 64, kTcBK = 64, kTcThreads = 256;
+constexpr int kTcABytes = kTcBM * kTcBK * 2;               // one bf16 A tile (h, m or l)
+constexpr int kTcBBytes = kTcBN * kTcBK * 2;
+constexpr int kTcStageBytes = 3 * kTcABytes + 3 * kTcBBytes;   // A h | m | l | B h | m | l
+constexpr int kTcSmem = 2 * kTcStageBytes + 1024;
+constexpr uint32_t kTcTmemCols = 2 * kTcBN;                // two accumulators
+
+// 8 consecutive k of one operand row (zero past the matrix edge)
+__device__ __forceinline__ void tc_load_chunk(const float* __restrict__ src, long s_row, long s_k,
+                                              int row, int nrows, int k0, int K, float* v) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  if (row < nrows && k0 < K) {
+    const float* p = src + (long)row * s_row + (long)k0 * s_k;
+    if (s_k == 1 && k0 + 8 <= K && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      load8f(p, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (k0 + j < K) v[j] = __ldg(p + (long)j * s_k);
     }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
   }
+}
+// ... -> the row's 16-byte chunk `c` of the h, m and l tiles
+__device__ __forceinline__ void tc_split_chunk(const float* v, uint8_t* tiles, int tile_bytes, int r,
+                                               int c) {
+  float h[8], m[8], l[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
-      if (m < M && n < N) Cm[(long)m * N + n] = acc[i][j];
-    }
+  for (int j = 0; j < 8; ++j) {
+    h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+    const float r1 = v[j] - h[j];            // exact in fp32
+    m[j] = __bfloat162float(__float2bfloat16_rn(r1));
+    l[j] = r1 - m[j];                        // exact; rounded to bf16 by pack8
+  }
+  const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(tiles + off) = pack8(h);
+  *reinterpret_cast<uint4*>(tiles + tile_bytes + off) = pack8(m);
+  *reinterpret_cast<uint4*>(tiles + 2 * tile_bytes + off) = pack8(l);
 }
 
-// rows -> unit rows; norm clamp 1e-12 as F.normalize
-__global__ void normalize_rows_kernel(const float* __restrict__ x, float* __restrict__ xn,
-                                      float* __restrict__ norms, int D) {
+__global__ void __launch_bounds__(kTcThreads)
+tc_gemm_f32x3_kernel(const TcGemmBatch batch) {
+  const TcGemm& g = batch.g[blockIdx.z];
+  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
+  if (m0 >= g.M || n0 >= g.N) return;          // (uniform per CTA; nothing allocated yet)
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t done_bar[2];             // the MMAs of the k-block in stage s have retired
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(&done_bar[0], 1);
+      mbar_init(&done_bar[1], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_smem, kTcTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  constexpr uint32_t idesc = umma_idesc_bf16(kTcBM, kTcBN, 0, 0);
+  const bool a_kmajor = g.a_sk == 1, b_kmajor = g.b_sk == 1;
+  const int nkb = (g.K + kTcBK - 1) / kTcBK;
+  // warp w owns TMEM lane quarter w % 4 (32 output rows) and the 32-column half w / 4
+  const int quarter = warp & 3, colh = warp >> 2;
+  const uint32_t t_mine = tmem_base + ((uint32_t)(quarter * 32) << 16) + colh * 32;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  // completion j of done_bar[s] belongs to k-block s + 2j; every thread waits for each one once
+  auto drain = [&](int kb_done) {
+    const int s = kb_done & 1;
+    mbar_wait(&done_bar[s], (kb_done >> 1) & 1);
+    tc_fence_after();
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_mine + s * kTcBN, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+    tc_fence_before();
+  };
+  // software pipeline: the global loads of k-block kb+1 are issued right after the MMAs of kb and
+  // stay in flight (48 registers) across the accumulator drain at the top of the next iteration
+  constexpr int kAPer = kTcBM * 8 / kTcThreads, kBPer = kTcBN * 8 / kTcThreads;
+  float va[kAPer][8], vb[kBPer][8];
+  auto load_block = [&](int kb) {
+    const int k0 = kb * kTcBK;
+#pragma unroll
+    for (int i = 0; i < kAPer; ++i) {
+      const int q = tid + kTcThreads * i;
+      const int r = a_kmajor ? (q >> 3) : (q & (kTcBM - 1));
+      const int c = a_kmajor ? (q & 7) : (q / kTcBM);
+      tc_load_chunk(g.A, g.a_sm, g.a_sk, m0 + r, g.M, k0 + c * 8, g.K, va[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kBPer; ++i) {
+      const int q = tid + kTcThreads * i;
+      const int r = b_kmajor ? (q >> 3) : (q & (kTcBN - 1));
+      const int c = b_kmajor ? (q & 7) : (q / kTcBN);
+      tc_load_chunk(g.B, g.b_sn, g.b_sk, n0 + r, g.N, k0 + c * 8, g.K, vb[i]);
+    }
+  };
+  load_block(0);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb & 1;
+    if (kb >= 2) drain(kb - 2);                 // frees stage s and accumulator s
+    uint8_t* a_t = smem + s * kTcStageBytes;
+    uint8_t* b_t = a_t + 3 * kTcABytes;
+#pragma unroll
+    for (int i = 0; i < kAPer; ++i) {
+      const int q = tid + kTcThreads * i;
+      const int r = a_kmajor ? (q >> 3) : (q & (kTcBM - 1));
+      const int c = a_kmajor ? (q & 7) : (q / kTcBM);
+      tc_split_chunk(va[i], a_t, kTcABytes, r, c);
+    }
+#pragma unroll
+    for (int i = 0; i < kBPer; ++i) {
+      const int q = tid + kTcThreads * i;
+      const int r = b_kmajor ? (q >> 3) : (q & (kTcBN - 1));
+      const int c = b_kmajor ? (q & 7) : (q / kTcBN);
+      tc_split_chunk(vb[i], b_t, kTcBBytes, r, c);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == 0) {                            // converged warp, one elected lane issues
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + s * kTcBN;
+      const uint64_t da = umma_smem_desc(smem_u32(a_t), 16, 1024, kSwizzle128B);
+      const uint64_t db = umma_smem_desc(smem_u32(b_t), 16, 1024, kSwizzle128B);
+      constexpr uint32_t kAT = kTcABytes >> 4, kBT = kTcBBytes >> 4;   // tile strides, 16-byte units
+#pragma unroll
+      for (int k = 0; k < kTcBK / 16; ++k) {    // +32 bytes along K = +2 address units
+        const uint64_t ah = da + 2 * k, am = ah + kAT, al = am + kAT;
+        const uint64_t bh = db + 2 * k, bm = bh + kBT, bl = bm + kBT;
+        umma_bf16_ss_w(d_tmem, al, bh, idesc, k != 0);
+        umma_bf16_ss_w(d_tmem, ah, bl, idesc, 1);
+        umma_bf16_ss_w(d_tmem, am, bm, idesc, 1);
+        umma_bf16_ss_w(d_tmem, am, bh, idesc, 1);
+        umma_bf16_ss_w(d_tmem, ah, bm, idesc, 1);
+        umma_bf16_ss_w(d_tmem, ah, bh, idesc, 1);
+      }
+      umma_commit_w(&done_bar[s]);
+    }
+    if (kb + 1 < nkb) load_block(kb + 1);
+  }
+  if (nkb >= 2) drain(nkb - 2);
+  drain(nkb - 1);
+  {
+    const int m = m0 + quarter * 32 + lane;
+    const int nb = n0 + colh * 32;
+    if (m < g.M) {
+      float* dst = g.C + (long)m * g.N + nb;
+      if (nb + 32 <= g.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < g.N) dst[j] = acc[j];
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTcTmemCols);
+  }
+}
+
+// rows -> unit rows; norm clamp 1e-12 as F.normalize.  Two row sets per launch (x and W).
+struct RowSet {
+  const float* src;
+  float* dst;
+  float* norms;
+  int rows;
+};
+__global__ void normalize_rows_kernel(RowSet s0, RowSet s1, int D) {
   __shared__ float sh[32];
-  const long row = blockIdx.x;
+  long row = blockIdx.x;
+  const RowSet& rs = row < s0.rows ? s0 : s1;
+  if (row >= s0.rows) row -= s0.rows;
+  const float* x = rs.src + row * D;
   float s = 0.f;
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    const float v = x[row * D + i];
+    const float v = x[i];
     s += v * v;
   }
   s = block_reduce(s, sh, false);
   const float nrm = fmaxf(sqrtf(s), 1e-12f);
-  if (threadIdx.x == 0) norms[row] = nrm;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) xn[row * D + i] = x[row * D + i] / nrm;
+  if (threadIdx.x == 0) rs.norms[row] = nrm;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) rs.dst[row * D + i] = x[i] / nrm;
 }
 
-// dx = (dxn - xn * <xn, dxn>) / ||x||
-__global__ void normalize_bwd_kernel(const float* __restrict__ dxn, const float* __restrict__ xn,
-                                     const float* __restrict__ norms, float* __restrict__ dx,
-                                     int D) {
+// dx = (dxn - xn * <xn, dxn>) / ||x||   (rows of x and rows of W in one launch)
+struct RowSetBwd {
+  const float* dxn;
+  const float* xn;
+  const float* norms;
+  float* dx;
+  int rows;
+};
+__global__ void normalize_bwd_kernel(RowSetBwd s0, RowSetBwd s1, int D) {
   __shared__ float sh[32];
-  const long row = blockIdx.x;
+  long row = blockIdx.x;
+  const RowSetBwd& rs = row < s0.rows ? s0 : s1;
+  if (row >= s0.rows) row -= s0.rows;
+  const float* dxn = rs.dxn + row * D;
+  const float* xn = rs.xn + row * D;
   float s = 0.f;
-  for (int i = threadIdx.x; i < D; i += blockDim.x) s += dxn[row * D + i] * xn[row * D + i];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) s += dxn[i] * xn[i];
   s = block_reduce(s, sh, false);
-  const float inv = 1.f / norms[row];
-  for (int i = threadIdx.x; i < D; i += blockDim.x)
-    dx[row * D + i] = (dxn[row * D + i] - xn[row * D + i] * s) * inv;
+  const float inv = 1.f / rs.norms[row];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) rs.dx[row * D + i] = (dxn[i] - xn[i] * s) * inv;
 }
 
 }  // namespace sib
@@ -276,10 +453,22 @@ extern "C" int sib_ce_fwd_bwd(const void* logits, int logits_fp32, const long* l
   return 0;
 }
 
-static int sgemm(const float* A, long a_sm, long a_sk, const float* Bm, long b_sn, long b_sk,
-                 float* Cm, int M, int N, int K, cudaStream_t st) {
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  sgemm_kernel<<<grid, 256, 0, st>>>(A, a_sm, a_sk, Bm, b_sn, b_sk, Cm, M, N, K);
+static int tc_gemm(const TcGemm* probs, int n, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    SIB_CUDA(cudaFuncSetAttribute(tc_gemm_f32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kTcSmem));
+    configured = true;
+  }
+  TcGemmBatch b{};
+  int gx = 0, gy = 0;
+  for (int i = 0; i < n; ++i) {
+    b.g[i] = probs[i];
+    gx = max(gx, (probs[i].N + kTcBN - 1) / kTcBN);
+    gy = max(gy, (probs[i].M + kTcBM - 1) / kTcBM);
+  }
+  if (gx == 0 || gy == 0) return 0;
+  tc_gemm_f32x3_kernel<<<dim3(gx, gy, n), kTcThreads, kTcSmem, st>>>(b);
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -288,34 +477,31 @@ static int sgemm(const float* A, long a_sm, long a_sk, const float* Bm, long b_s
 extern "C" int sib_sphere_linear_fwd(const float* x, const float* w, float* cosv, float* xn,
                                      float* wn, float* xnorm, float* wnorm, int B, int C, int D,
                                      int normalize_x, void* stream) {
-  if (normalize_x) {
-    normalize_rows_kernel<<<B, 128, 0, ST(stream)>>>(x, xn, xnorm, D);
-    SIB_LAUNCH_CHECK();
-  }
-  normalize_rows_kernel<<<C, 128, 0, ST(stream)>>>(w, wn, wnorm, D);
+  const RowSet sx{x, xn, xnorm, normalize_x ? B : 0};
+  const RowSet sw{w, wn, wnorm, C};
+  normalize_rows_kernel<<<sx.rows + sw.rows, 128, 0, ST(stream)>>>(sx, sw, D);
   SIB_LAUNCH_CHECK();
-  return sgemm(normalize_x ? xn : x, D, 1, wn, D, 1, cosv, B, C, D, ST(stream));
+  const TcGemm g{normalize_x ? xn : x, D, 1, wn, D, 1, cosv, B, C, D};
+  return tc_gemm(&g, 1, ST(stream));
 }
 
-// dx[B][D], dw[C][D] from dcos[B][C]; scratch must hold max(B,C)*D floats
+// dx[B][D], dw[C][D] from dcos[B][C]; scratch must hold (B + C) * D floats
 extern "C" int sib_sphere_linear_bwd(const float* dcos, const float* x_or_xn, const float* wn,
                                      const float* xnorm, const float* wnorm, float* dx, float* dw,
                                      float* scratch, int B, int C, int D, int normalize_x,
                                      void* stream) {
-  // d(xn) = dcos . wn   -> [B][D]
-  if (dx != nullptr) {
-    if (normalize_x) {
-      if (int rc = sgemm(dcos, C, 1, wn, 1, D, scratch, B, D, C, ST(stream))) return rc;
-      normalize_bwd_kernel<<<B, 128, 0, ST(stream)>>>(scratch, x_or_xn, xnorm, dx, D);
-      SIB_LAUNCH_CHECK();
-    } else {
-      if (int rc = sgemm(dcos, C, 1, wn, 1, D, dx, B, D, C, ST(stream))) return rc;
-    }
-  }
-  // d(wn) = dcos^T . xn -> [C][D]
-  if (dw != nullptr) {
-    if (int rc = sgemm(dcos, 1, C, x_or_xn, 1, D, scratch, C, D, B, ST(stream))) return rc;
-    normalize_bwd_kernel<<<C, 128, 0, ST(stream)>>>(scratch, wn, wnorm, dw, D);
+  float* dxn = (dx != nullptr && !normalize_x) ? dx : scratch;      // d(xn) = dcos . wn      [B][D]
+  float* dwn = scratch + (long)B * D;                               // d(wn) = dcos^T . xn    [C][D]
+  TcGemm g[2];
+  int n = 0;
+  if (dx != nullptr) g[n++] = TcGemm{dcos, C, 1, wn, 1, D, dxn, B, D, C};
+  if (dw != nullptr) g[n++] = TcGemm{dcos, 1, C, x_or_xn, 1, D, dwn, C, D, B};
+  if (n == 0) return 0;
+  if (int rc = tc_gemm(g, n, ST(stream))) return rc;
+  const RowSetBwd bx{dxn, x_or_xn, xnorm, dx, (dx != nullptr && normalize_x) ? B : 0};
+  const RowSetBwd bw{dwn, wn, wnorm, dw, dw != nullptr ? C : 0};
+  if (bx.rows + bw.rows > 0) {
+    normalize_bwd_kernel<<<bx.rows + bw.rows, 128, 0, ST(stream)>>>(bx, bw, D);
     SIB_LAUNCH_CHECK();
   }
   return 0;

@@ -669,7 +669,7 @@ def sphere_linear_bwd(dcos, saved, need_dx=True, need_dw=True, normalize_x=True)
     c = wn.shape[0]
     dx = torch.empty_like(xn) if need_dx else None
     dw = torch.empty_like(wn) if need_dw else None
-    scratch = torch.empty((max(b, c), d), dtype=torch.float32, device=xn.device)
+    scratch = torch.empty((b + c, d), dtype=torch.float32, device=xn.device)
     call("sib_sphere_linear_bwd", _p(dcos), _p(xn), _p(wn), _p(xnorm), _p(wnorm), _p(dx), _p(dw),
          _p(scratch), b, c, d, int(normalize_x), _stream())
     return dx, dw

@@ -50,6 +50,19 @@ def test_extra_operators_match_torch():
     dm = torch.randn_like(m_ref).bfloat16()
     (dxm,) = torch.autograd.grad(m_ref, xr, dm.float())
     assert (ops.maxpool3x3s1_bwd(ops.to_nhwc_bf16(dm), idx).float() - dxm).abs().max() < 6e-2   # bf16 sum of <= 9 grads
+    # the column-sliding kernels split the rows into segments: odd extents, a short last segment, and
+    # coarse values (many exact ties: the FIRST maximum in scan order must win, as torch's indices)
+    for shape, coarse in (((2, 16, 37, 23), False), ((3, 8, 9, 5), True), ((1, 64, 112, 112), False)):
+        xs = torch.randn(*shape, device="cuda")
+        xs = (xs * 2).round().bfloat16() if coarse else xs.bfloat16()
+        xsr = xs.float().requires_grad_(True)
+        ms_ref = F.max_pool2d(xsr, 3, 1, 1)
+        ms, ids = ops.maxpool3x3s1_fwd(ops.to_nhwc_bf16(xs))
+        assert torch.equal(ms.float(), ms_ref.detach()), shape
+        dms = torch.randn_like(ms_ref).bfloat16()
+        (dxs,) = torch.autograd.grad(ms_ref, xsr, dms.float())
+        got = ops.maxpool3x3s1_bwd(ops.to_nhwc_bf16(dms), ids).float()
+        assert bool(((got - dxs).abs() <= 6e-2 + 8e-3 * dxs.abs()).all()), shape     # bf16 rounding of the sum
     # ECA module fwd + bwd
     from sota_imagenet_b200 import bresnet
     eca_ref = bresnet_ref.ECA().cuda()
