@@ -54,3 +54,16 @@ print("%s %dx%d batch %d: step %.3f ms (events around the whole step), C-ABI cal
       % (which, size, size, B, e0.elapsed_time(e1), tot, len(prof)))
 for name, (ms, n) in sorted(groups.items(), key=lambda kv: -kv[1][0]):
     print("%-34s n=%4d %8.3f ms %5.1f%%" % (name, n, ms, 100 * ms / tot))
+if "--shapes" in sys.argv:
+    # per (entry point, shape) table of the convolution calls: the small integer arguments identify the layer
+    shapes = {}
+    for name, a, s0, s1 in prof:
+        if "conv2d" not in name:
+            continue
+        key = (name,) + tuple(v for v in a if isinstance(v, int) and 0 <= v < 100000)[:12]
+        d = shapes.setdefault(key, [0.0, 0])
+        d[0] += s0.elapsed_time(s1)
+        d[1] += 1
+    print("conv calls by shape (N, H, W, C, K, R, S, stride, pad_h, pad_w, OH, OW ...):")
+    for key, (ms, n) in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:40]:
+        print("%-26s %-52s n=%3d %7.3f ms  %.3f ms/call" % (key[0], key[1:], n, ms, ms / n))

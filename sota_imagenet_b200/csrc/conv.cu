@@ -914,13 +914,16 @@ struct HaloParams {
   const float* mean_invstd;
 };
 
-constexpr int kHaloAStage = 32768;   // region of up to 256 rows x 128 bytes
-
-template <int BN, int BSTAGES, int kHaloAStages>
+// A stage = kALoads im2col loads of 128 padded positions x 128 bytes.  The nine taps read 128 rows
+// starting at up to 2 * pitch + 2, i.e. 2 * pitch + 130 rows in all: two loads (256 rows) serve
+// pitch <= 63 (ResNet's 56x56 / 28x28 layers), three (384 rows) pitch <= 127 (the 112x112 layers of
+// the BResNet deep stem, one output row per tile).
+template <int BN, int BSTAGES, int kHaloAStages, int kALoads = 2>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 halo3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                __nv_bfloat16* __restrict__ out, const HaloParams p) {
   constexpr int kBBytes = BN * kBK * 2;
+  constexpr int kHaloAStage = kALoads * kABytes;
   constexpr uint32_t kTmemCols = 2 * BN;
   constexpr int kGroups = BN == 64 ? 2 : 1;     // epilogue warp groups working on alternate tiles
   constexpr int kEpiWarps = 8;
@@ -974,18 +977,26 @@ halo3x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int h0 = (mt - n_img * p.num_h_tiles) * p.tile_h;
         for (int cb = 0; cb < p.cin_blocks; ++cb) {
           mbar_wait(&a_empty[a_stage], a_phase ^ 1);
-          // The padded region is fetched as two im2col loads of 128 consecutive padded positions
-          // (bounding box = image + 1 pixel of zero-filled border on every side, so the
-          // traversal pitch is W + 2).  The second load may run past the region; those rows only
+          // The padded region is fetched as kALoads im2col loads of 128 consecutive padded
+          // positions (bounding box = image + 1 pixel of zero-filled border on every side, so the
+          // traversal pitch is W + 2).  The last load may run past the region; those rows only
           // feed junk outputs.  (A tiled 4-D box of the same region measured 7x slower per row.)
-          int h1 = h0 - 1 + 128 / p.pitch, w1 = -1 + 128 % p.pitch, n1 = n_img;
-          if (h1 > p.H) { h1 -= p.H + 2; ++n1; }
-          const bool second = n1 < p.N;
-          mbar_arrive_expect_tx(&a_full[a_stage], second ? 2 * kABytes : kABytes);
+          int hj[kALoads], wj[kALoads], nj[kALoads], n_ok = 1;
+#pragma unroll
+          for (int j = 1; j < kALoads; ++j) {
+            hj[j] = h0 - 1 + (128 * j) / p.pitch;
+            wj[j] = -1 + (128 * j) % p.pitch;
+            nj[j] = n_img;
+            if (hj[j] > p.H) { hj[j] -= p.H + 2; ++nj[j]; }
+            if (nj[j] < p.N) ++n_ok;
+          }
+          mbar_arrive_expect_tx(&a_full[a_stage], n_ok * kABytes);
           uint8_t* dst = smem_a + a_stage * kHaloAStage;
           tma_load_im2col_4d(dst, &tmA, &a_full[a_stage], cb * kBK, -1, h0 - 1, n_img, 0, 0);
-          if (second)
-            tma_load_im2col_4d(dst + kABytes, &tmA, &a_full[a_stage], cb * kBK, w1, h1, n1, 0, 0);
+#pragma unroll
+          for (int j = 1; j < kALoads; ++j)
+            if (nj[j] < p.N)
+              tma_load_im2col_4d(dst + j * kABytes, &tmA, &a_full[a_stage], cb * kBK, wj[j], hj[j], nj[j], 0, 0);
           if (++a_stage == kHaloAStages) { a_stage = 0; a_phase ^= 1; }
           if (!p.b_stationary || first) {
             for (int tap = 0; tap < 9; ++tap) {
@@ -1527,20 +1538,20 @@ static int launch_igemm2(const IgemmMaps& tm, const IgemmParams& p, cudaStream_t
   return 0;
 }
 
-template <int BN, int BSTAGES, int kHaloAStages>
+template <int BN, int BSTAGES, int kHaloAStages, int kALoads = 2>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, void* out, const HaloParams& p,
                        cudaStream_t stream) {
-  constexpr int smem = kHaloAStages * kHaloAStage + BSTAGES * BN * kBK * 2 + 8 * kSlabBytes + 1024;
+  constexpr int smem = kHaloAStages * kALoads * kABytes + BSTAGES * BN * kBK * 2 + 8 * kSlabBytes + 1024;
   static_assert(smem + 512 <= 232448, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    SIB_CUDA(cudaFuncSetAttribute(halo3x3_kernel<BN, BSTAGES, kHaloAStages>,
+    SIB_CUDA(cudaFuncSetAttribute(halo3x3_kernel<BN, BSTAGES, kHaloAStages, kALoads>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   int grid = p.N * p.num_h_tiles * p.num_n_tiles;
   if (grid > sm_count()) grid = sm_count();
-  SIB_CUDA(launch_pdl(halo3x3_kernel<BN, BSTAGES, kHaloAStages>, dim3(grid), dim3(kIgemmThreads), smem, stream, tmA,
+  SIB_CUDA(launch_pdl(halo3x3_kernel<BN, BSTAGES, kHaloAStages, kALoads>, dim3(grid), dim3(kIgemmThreads), smem, stream, tmA,
                       tmB, static_cast<__nv_bfloat16*>(out), p));
   return 0;
 }
@@ -1584,8 +1595,9 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
   // 3x3 / stride 1 / pad 1 on 64 or 128 output channels at >= 28 pixel rows: halo-reuse kernel
   {
     const bool geometry = pro == nullptr && so == nullptr && R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && TH == IH &&
-                          TW == IW && Cin % 64 == 0 && IW + 2 <= 63 && residual == nullptr &&
-                          bias == nullptr && (Cout == 64 || Cout == 128) &&
+                          TW == IW && Cin % 64 == 0 && residual == nullptr && bias == nullptr &&
+                          (IW + 2 <= 63 ? (Cout == 64 || Cout == 128)
+                                        : (IW + 2 <= 127 && Cin == 64 && Cout == 64)) &&    // wide rows: weight-stationary variant only
                           (fuse == nullptr || fuse->aux2 == nullptr);
     // measured (B200, batch 256): 64 -> 64 @ 56x56 0.166 -> 0.12 ms; 128 -> 128 @ 28x28 is slower
     // than the im2col kernel (0.104 vs 0.092 ms: the streamed weight k-blocks dominate), so only
@@ -1601,7 +1613,7 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
       h.num_h_tiles = (IH + h.tile_h - 1) / h.tile_h;
       h.num_n_tiles = 1;
       h.cin_blocks = Cin / 64;
-      h.a_bytes = h.pitch * (h.tile_h + 2) * 128;
+      h.a_bytes = h.pitch * (h.tile_h + 2) * 128;    // (informational)
       h.stats = stats;
       if (fuse != nullptr) {
         SIB_CHECK(stats == nullptr && fuse->aux1 && fuse->mean_invstd && fuse->sums,
@@ -1622,6 +1634,7 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
         SIB_CUDA(cudaMemsetAsync(h.stats, 0, sizeof(float) * 2 * Cout, stream));
       if (Cout == 64) {
         h.b_stationary = 9 * h.cin_blocks <= 9;
+        if (h.pitch > 63) return launch_halo<64, 9, 2, 3>(tmA, tmB, out, h, stream);   // 384-row regions, 2 stages
         return launch_halo<64, 9, 3>(tmA, tmB, out, h, stream);
       }
       h.b_stationary = 0;

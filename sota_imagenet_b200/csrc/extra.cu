@@ -20,15 +20,15 @@ static inline int ew_grid(long n, int threads) {
 
 __device__ __forceinline__ float blur_w(int d) { return d == 1 ? 0.5f : 0.25f; }   // [1,2,1]/4
 
+template <typename I>   // I = int when the vector count fits 31 bits (64-bit div/mod is ~10x the cost)
 __global__ void __launch_bounds__(256)
 blurpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                     int W, int C, int OH, int OW) {
   const int cvec = C >> 3;
-  const long total = (long)N * OH * OW * cvec;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
+  const I total = (I)N * OH * OW * cvec;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
-    long t = i / cvec;
+    I t = i / cvec;
     const int q = (int)(t % OW); t /= OW;
     const int p = (int)(t % OH);
     const int n = (int)(t / OH);
@@ -48,19 +48,19 @@ blurpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, f[j], acc[j]);
       }
     }
-    stg_stream(y + i * 8, pack8(acc));
+    stg_stream(y + (long)i * 8, pack8(acc));
   }
 }
 
+template <typename I>   // I = int when the vector count fits 31 bits (64-bit div/mod is ~10x the cost)
 __global__ void __launch_bounds__(256)
 blurpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
                     int H, int W, int C, int OH, int OW) {
   const int cvec = C >> 3;
-  const long total = (long)N * H * W * cvec;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
+  const I total = (I)N * H * W * cvec;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
-    long t = i / cvec;
+    I t = i / cvec;
     const int w = (int)(t % W); t /= W;
     const int h = (int)(t % H);
     const int n = (int)(t / H);
@@ -80,19 +80,19 @@ blurpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restr
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, g[j], acc[j]);
       }
     }
-    stg_stream(dx + i * 8, pack8(acc));
+    stg_stream(dx + (long)i * 8, pack8(acc));
   }
 }
 
+template <typename I>   // I = int when the vector count fits 31 bits (64-bit div/mod is ~10x the cost)
 __global__ void __launch_bounds__(256)
 avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                     int W, int C) {
   const int cvec = C >> 3, OH = H >> 1, OW = W >> 1;
-  const long total = (long)N * OH * OW * cvec;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
+  const I total = (I)N * OH * OW * cvec;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
-    long t = i / cvec;
+    I t = i / cvec;
     const int q = (int)(t % OW); t /= OW;
     const int p = (int)(t % OH);
     const int n = (int)(t / OH);
@@ -108,19 +108,19 @@ avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
       }
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
-    stg_stream(y + i * 8, pack8(acc));
+    stg_stream(y + (long)i * 8, pack8(acc));
   }
 }
 
+template <typename I>   // I = int when the vector count fits 31 bits (64-bit div/mod is ~10x the cost)
 __global__ void __launch_bounds__(256)
 avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
                     int H, int W, int C) {
   const int cvec = C >> 3, OH = H >> 1, OW = W >> 1;
-  const long total = (long)N * H * W * cvec;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
+  const I total = (I)N * H * W * cvec;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
-    long t = i / cvec;
+    I t = i / cvec;
     const int w = (int)(t % W); t /= W;
     const int h = (int)(t % H);
     const int n = (int)(t / H);
@@ -130,7 +130,7 @@ avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
     }
-    stg_stream(dx + i * 8, pack8(g));
+    stg_stream(dx + (long)i * 8, pack8(g));
   }
 }
 
@@ -592,30 +592,34 @@ using namespace sib;
 extern "C" int sib_blurpool_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   SIB_CHECK(C % 8 == 0, "blurpool: C %% 8 != 0");
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  blurpool_fwd_kernel<<<ew_grid((long)N * OH * OW * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(x), BF(y), N, H, W, C, OH, OW);
+  const long total = (long)N * OH * OW * (C / 8);
+  if (total < (1l << 31) - (1l << 24)) blurpool_fwd_kernel<int><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), N, H, W, C, OH, OW);
+  else blurpool_fwd_kernel<long><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), N, H, W, C, OH, OW);
   SIB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sib_blurpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
   SIB_CHECK(C % 8 == 0, "blurpool: C %% 8 != 0");
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  blurpool_bwd_kernel<<<ew_grid((long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(dy), BF(dx), N, H, W, C, OH, OW);
+  const long total = (long)N * H * W * (C / 8);
+  if (total < (1l << 31) - (1l << 24)) blurpool_bwd_kernel<int><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C, OH, OW);
+  else blurpool_bwd_kernel<long><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C, OH, OW);
   SIB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sib_avgpool2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   SIB_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool2: needs C %% 8 == 0 and even H, W");
-  avgpool2_fwd_kernel<<<ew_grid((long)N * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(x), BF(y), N, H, W, C);
+  const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
+  if (total < (1l << 31) - (1l << 24)) avgpool2_fwd_kernel<int><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), N, H, W, C);
+  else avgpool2_fwd_kernel<long><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(x), BF(y), N, H, W, C);
   SIB_LAUNCH_CHECK();
   return 0;
 }
 extern "C" int sib_avgpool2_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
   SIB_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool2: needs C %% 8 == 0 and even H, W");
-  avgpool2_bwd_kernel<<<ew_grid((long)N * H * W * (C / 8), 256), 256, 0, ST(stream)>>>(
-      CBF(dy), BF(dx), N, H, W, C);
+  const long total = (long)N * H * W * (C / 8);
+  if (total < (1l << 31) - (1l << 24)) avgpool2_bwd_kernel<int><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C);
+  else avgpool2_bwd_kernel<long><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C);
   SIB_LAUNCH_CHECK();
   return 0;
 }
@@ -717,7 +721,7 @@ extern "C" int sib_maxpool3x3s1_fwd(const void* x, void* y, void* idx, int N, in
   SIB_CHECK(C % 8 == 0, "maxpool3x3s1: C %% 8 != 0");
   int segs, seg_rows;
   maxpool_segments(N, H, W, C, &segs, &seg_rows);
-  SIB_CHECK((long)N * segs * W * (C / 8) < (1l << 31), "maxpool3x3s1: tensor too large for 32-bit indexing");
+  SIB_CHECK((long)N * segs * W * (C / 8) < (1l << 31) - (1l << 24), "maxpool3x3s1: tensor too large for 32-bit indexing");
   maxpool3x3s1_fwd_kernel<<<ew_grid((long)N * segs * W * (C / 8), 256), 256, 0, ST(stream)>>>(
       CBF(x), BF(y), static_cast<uint8_t*>(idx), N, H, W, C, segs, seg_rows);
   SIB_LAUNCH_CHECK();
@@ -728,7 +732,7 @@ extern "C" int sib_maxpool3x3s1_bwd(const void* dy, const void* idx, void* dx, i
   SIB_CHECK(C % 8 == 0, "maxpool3x3s1: C %% 8 != 0");
   int segs, seg_rows;
   maxpool_segments(N, H, W, C, &segs, &seg_rows);
-  SIB_CHECK((long)N * segs * W * (C / 8) < (1l << 31), "maxpool3x3s1: tensor too large for 32-bit indexing");
+  SIB_CHECK((long)N * segs * W * (C / 8) < (1l << 31) - (1l << 24), "maxpool3x3s1: tensor too large for 32-bit indexing");
   maxpool3x3s1_bwd_kernel<<<ew_grid((long)N * segs * W * (C / 8), 256), 256, 0, ST(stream)>>>(
       CBF(dy), static_cast<const uint8_t*>(idx), BF(dx), N, H, W, C, segs, seg_rows);
   SIB_LAUNCH_CHECK();

@@ -38,6 +38,8 @@ CONV_CASES = [
     (3, 28, 28, 64, 128, 3, 1, 1, 0),                         # chosen automatically at >= 28 columns
     (2, 56, 56, 64, 64, 3, 1, 1, 0),                          # the layer1 shape (2 rows per tile)
     (2, 28, 28, 128, 128, 3, 1, 1, ops.FLAG_NO_HALO),         # same geometry on the im2col kernel
+    (2, 112, 112, 64, 64, 3, 1, 1, 0),                        # wide rows (BResNet deep stem): 384-row regions, 1 row per tile
+    (3, 9, 75, 64, 64, 3, 1, 1, 0),                           # wide rows, odd extents, region loads crossing images
 ]
 
 
