@@ -1490,6 +1490,208 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 }
 
 // ----------------------------------------------------------------------------
+// wgrad of 3x3 / stride 1 / pad 1 filters with 64 output channels: halo reuse on BOTH operands
+// ----------------------------------------------------------------------------
+// The generic kernel above reads X once per filter tap (nine im2col loads per pixel block) and, with
+// 64 output channels, fills only half of its M = 128 tile: ncu shows the 64 -> 64 3x3 layers pinned
+// at the L2 -> SM fabric (1.2 GB moved for 0.2 GB of operands, 0.147 ms against 0.043 ms ideal).
+// Here the reduction runs over PADDED flat positions J of the (H+2) x (W+2) grid of every image
+// (pitch = W+2; both operands are zero on the border, fetched by im2col TMA loads over a bounding box
+// one pixel larger than the image, exactly like the halo fprop kernel):
+//     dW[k][(r,s)][c] = sum_J  X_pad[J + (r-1)*pitch][c] * dY_pad[J + 1 - s][k]
+// so every tap is a pair of ROW-SHIFTED VIEWS of two shared-memory regions that are loaded once per
+// 128 positions.  Both operands are MN-major (a pixel is a 128-byte row, the channels are the M / N
+// index, the pixels the K index), and for MN-major 128B-swizzled descriptors the start address may
+// be advanced by any number of rows AND the leading byte offset (distance between the 64-channel
+// groups of an operand) may be any multiple of 128 bytes (scripts/probes/umma_mn_major_shift_probe.cu:
+// exact for all shifts / offsets) -- the 64-channel groups of one MMA operand can be shifted views:
+//     B (N = 192) = X region at rows +0, +pitch, +2*pitch        (r = 0, 1, 2; LBO = pitch rows)
+//     A (M = 128) = dY region at rows +0, +1                      (s = 1, 0;    LBO = 1 row)
+// One MMA (128 x 192 x 16) therefore produces SIX taps, a second one with A = dY at row -1 (s = 2; its
+// upper half is a don't-care duplicate) the remaining three: 16 MMAs per 128 positions instead of 72
+// N = 64 ones, two operand regions (64 KB) instead of 9 + 3 tiles (96 KB per 64 pixels).
+// Split over position ranges (one CTA per SM), TMA add-reduction of the 9 x 64 x 64 partials into dW.
+struct WgradHaloParams {
+  int N, Cin;
+  int pitch;          // W + 2
+  int P;              // (H + 2) * pitch: padded positions per image
+  long total_pos;     // N * P
+  int total_tiles;    // tiles of 128 positions; tile t covers J in [pitch + 128 t, +128)
+  int tiles_per_cta;
+};
+
+constexpr int kWhTile = 128;                 // positions per tile
+constexpr int kWhChunk = kWhTile * 128;      // bytes of one 128-position load (64 channels)
+
+// kXLoads: 128-position loads of the X region (needs 128 + 2 * pitch rows: 2 for pitch <= 63, 3 for
+// pitch <= 127); the dY region (130 rows) always takes two.
+template <int STAGES, int kXLoads>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ CUtensorMap tmDw, const WgradHaloParams p) {
+  constexpr int kXBytes = kXLoads * kWhChunk;
+  constexpr int kDyBytes = 2 * kWhChunk;
+  constexpr int kStageBytes = kXBytes + kDyBytes;
+  constexpr uint32_t kTmemCols = 512;          // 2 x 192 accumulator columns
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cb = blockIdx.y;                       // 64-channel block of X / of the dW columns
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  int t_end = t_begin + p.tiles_per_cta;
+  if (t_end > p.total_tiles) t_end = p.total_tiles;
+  const int ntiles = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDw);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  griddep_launch();
+  griddep_wait();
+  if (ntiles <= 0) {
+    // nothing to do for this split (uniform across the CTA); fall through to teardown
+  } else if (warp == 0) {
+    // ---- producer: the whole warp walks the tiles; lane 0 issues the TMA loads, a 128-position
+    //      load that would START past the last image is replaced by zeros written by all lanes ----
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* xs = smem + stage * kStageBytes;
+      uint8_t* ds = xs + kXBytes;
+      // X region starts at J0 - pitch = 128 t; the dY region at J0 - 1 = pitch - 1 + 128 t
+      long pos[kXLoads + 2];
+#pragma unroll
+      for (int j = 0; j < kXLoads; ++j) pos[j] = (long)(t + j) * kWhTile;
+      pos[kXLoads] = (long)t * kWhTile + p.pitch - 1;
+      pos[kXLoads + 1] = pos[kXLoads] + kWhTile;
+      int n_tma = 0;
+#pragma unroll
+      for (int j = 0; j < kXLoads + 2; ++j) n_tma += pos[j] < p.total_pos ? 1 : 0;
+#pragma unroll
+      for (int j = 0; j < kXLoads + 2; ++j) {
+        if (pos[j] >= p.total_pos) {
+          uint4* z = reinterpret_cast<uint4*>(j < kXLoads ? xs + j * kWhChunk : ds + (j - kXLoads) * kWhChunk);
+          for (int i = lane; i < kWhChunk / 16; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        }
+      }
+      if (n_tma != kXLoads + 2) {
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[stage], n_tma * kWhChunk);
+#pragma unroll
+        for (int j = 0; j < kXLoads + 2; ++j) {
+          if (pos[j] < p.total_pos) {
+            const int n_img = (int)(pos[j] / p.P);
+            const int rem = (int)(pos[j] - (long)n_img * p.P);
+            const int hp = rem / p.pitch;
+            const int wp = rem - hp * p.pitch;
+            if (j < kXLoads)
+              tma_load_im2col_4d(xs + j * kWhChunk, &tmX, &full_bar[stage], cb * 64, wp - 1, hp - 1, n_img, 0, 0);
+            else
+              tma_load_im2col_4d(ds + (j - kXLoads) * kWhChunk, &tmDy, &full_bar[stage], 0, wp - 1, hp - 1, n_img, 0, 0);
+          }
+        }
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (whole warp converged, one elected lane issues) ----
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, 192, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      mbar_wait_w(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t xs = smem_u32(smem + stage * kStageBytes);
+      const uint32_t ds = xs + kXBytes;
+      // B: X rows +0 / +pitch / +2 pitch  (r = 0, 1, 2);  A1: dY rows +1 / +2 of the region that starts
+      // at J0 - 1, i.e. J + 0 (s = 1) and J + 1 (s = 0);  A2: region row 0 = J - 1 (s = 2) [+ duplicate]
+      const uint64_t b_desc = umma_smem_desc(xs, p.pitch * 128, 1024, kSwizzle128B);
+      const uint64_t a1_desc = umma_smem_desc(ds + 128, 128, 1024, kSwizzle128B);
+      const uint64_t a2_desc = umma_smem_desc(ds, 128, 1024, kSwizzle128B);
+#pragma unroll
+      for (int k = 0; k < kWhTile / 16; ++k) {
+        // 16 positions along K = two 1024-byte groups = +128 in 16-byte address units
+        umma_bf16_ss_w(tmem_base, a1_desc + 128 * k, b_desc + 128 * k, idesc, (i | k) != 0);
+        umma_bf16_ss_w(tmem_base + 192, a2_desc + 128 * k, b_desc + 128 * k, idesc, (i | k) != 0);
+      }
+      umma_commit_w(&empty_bar[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    umma_commit_w(&tmem_full_bar);
+  } else {
+    // ---- epilogue: TMEM -> 128B-swizzled fp32 slabs (the drained operand ring) -> TMA add-reduction ----
+    const int quarter = warp & 3;                   // TMEM lane quarter
+    const int half = quarter >> 1;                  // 0: lanes 0-63, 1: lanes 64-127
+    const int k0 = (quarter & 1) * 32;              // out-channel offset of this warp's 32 rows
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    constexpr int kRedSlabs = 4;
+    static_assert(STAGES * kStageBytes >= 4 * kRedSlabs * kSlabBytes, "ring too small");
+    uint8_t* slabs = smem + (warp - 2) * kRedSlabs * kSlabBytes;
+    int issued = 0;
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+      if (g == 1 && half == 1) break;               // upper half of the second accumulator is a duplicate
+      const int s_tap = g == 0 ? (half == 0 ? 1 : 0) : 2;
+#pragma unroll 1
+      for (int chunk = 0; chunk < 6; ++chunk) {     // (r, 32-column half) = (chunk / 2, chunk % 2)
+        const int r_tap = chunk >> 1;
+        uint8_t* slab = slabs + (issued % kRedSlabs) * kSlabBytes;
+        if (lane == 0) tma_store_wait_read<kRedSlabs - 1>();
+        __syncwarp();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + g * 192 + chunk * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(slab + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmDw, slab, (r_tap * 3 + s_tap) * p.Cin + cb * 64 + (chunk & 1) * 32, k0);
+          tma_store_commit();
+        }
+        ++issued;
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------
 // host launchers
 // ----------------------------------------------------------------------------
 struct IgemmMaps {
@@ -1774,6 +1976,22 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const C
   return 0;
 }
 
+template <int STAGES, int kXLoads>
+static int launch_wgrad_halo(const CUtensorMap& tmDy, const CUtensorMap& tmX, const CUtensorMap& tmDw,
+                             const WgradHaloParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kXLoads + 2) * kWhChunk + 1024;
+  static_assert(smem + 512 <= 232448, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    SIB_CUDA(cudaFuncSetAttribute(wgrad_halo_kernel<STAGES, kXLoads>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  SIB_CUDA(launch_pdl(wgrad_halo_kernel<STAGES, kXLoads>, grid, dim3(kThreads), smem, stream, tmDy, tmX,
+                      tmDw, p));
+  return 0;
+}
+
 }  // namespace sib
 
 using namespace sib;
@@ -1938,10 +2156,36 @@ extern "C" int sib_conv2d_dgrad_s2(const void* dy, const void* w_sub0, const voi
 extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W,
                                 int C, int K, int R, int S, int stride, int pad_h, int pad_w,
                                 int OH, int OW, int flags, void* stream) {
-  (void)flags;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SIB_CHECK(C % 64 == 0, "wgrad: Cin must be a multiple of 64 (got %d)", C);
   SIB_CHECK(K % 8 == 0, "wgrad: Cout must be a multiple of 8 (got %d)", K);
+  static const bool det0 = [] { const char* e = getenv("SIB_DETERMINISTIC"); return e && e[0] == '1'; }();
+  // 3x3 / stride 1 / pad 1 with 64 output channels: halo-reuse kernel (both operands loaded once per
+  // 128 padded positions, six + three taps per MMA pair).  Not in deterministic mode (split reduction).
+  if (R == 3 && S == 3 && stride == 1 && pad_h == 1 && pad_w == 1 && OH == H && OW == W && K == 64 &&
+      W + 2 <= 127 && !det0 && !(flags & SIB_FLAG_NO_HALO)) {
+    WgradHaloParams hp{};
+    hp.N = N;
+    hp.Cin = C;
+    hp.pitch = W + 2;
+    hp.P = (H + 2) * hp.pitch;
+    hp.total_pos = (long)N * hp.P;
+    SIB_CHECK(hp.total_pos < (1l << 31), "wgrad: too many pixels");
+    hp.total_tiles = (int)((hp.total_pos - hp.pitch + kWhTile - 1) / kWhTile);
+    const int cbs = C / 64;
+    int splits = sm_count() / cbs;
+    if (splits < 1) splits = 1;
+    if (splits > hp.total_tiles) splits = hp.total_tiles;
+    hp.tiles_per_cta = (hp.total_tiles + splits - 1) / splits;
+    splits = (hp.total_tiles + hp.tiles_per_cta - 1) / hp.tiles_per_cta;
+    CUtensorMap tmDy, tmX, tmDw;
+    if (int rc = make_tmap_im2col_bf16(&tmDy, dy, N, H, W, K, -1, -1, 1, 1, 1, 1, 64, kWhTile, true)) return rc;
+    if (int rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, C, -1, -1, 1, 1, 1, 1, 64, kWhTile, true)) return rc;
+    if (int rc = make_tmap_2d_f32(&tmDw, dw, K, (uint64_t)9 * C, (uint64_t)9 * C, 32, 32)) return rc;
+    const dim3 grid(splits, cbs, 1);
+    if (hp.pitch <= 63) return launch_wgrad_halo<3, 2>(tmDy, tmX, tmDw, hp, grid, st);
+    return launch_wgrad_halo<2, 3>(tmDy, tmX, tmDw, hp, grid, st);
+  }
   WgradParams p{};
   p.M_total = N * OH * OW;
   p.Cout = K;

@@ -40,6 +40,8 @@ CONV_CASES = [
     (2, 28, 28, 128, 128, 3, 1, 1, ops.FLAG_NO_HALO),         # same geometry on the im2col kernel
     (2, 112, 112, 64, 64, 3, 1, 1, 0),                        # wide rows (BResNet deep stem): 384-row regions, 1 row per tile
     (3, 9, 75, 64, 64, 3, 1, 1, 0),                           # wide rows, odd extents, region loads crossing images
+    (1, 4, 4, 64, 64, 3, 1, 1, 0),                            # halo wgrad: one tile, loads starting past the last image
+    (5, 11, 13, 192, 64, 3, 1, 1, 0),                         # halo wgrad: three input-channel blocks
 ]
 
 
@@ -89,6 +91,11 @@ def test_conv_fprop_dgrad_wgrad(n, h, w, c, k, r, stride, pad, flags):
     assert rel(dw, dw_ref) < 1e-4                       # fp32 accumulation end to end
     ops.conv2d_wgrad(xb, dyb, dw, stride=stride, pad=pad)
     assert rel(dw, 2 * dw_ref) < 1e-4                   # accumulates into dw (zero_grad contract)
+    if r == 3 and stride == 1 and k == 64:
+        # these shapes take the halo-reuse weight-gradient kernel; the generic kernel must agree
+        dw2 = torch.zeros(k, r, r, c, device="cuda").permute(0, 3, 1, 2)
+        ops.conv2d_wgrad(xb, dyb, dw2, stride=stride, pad=pad, flags=ops.FLAG_NO_HALO)
+        assert rel(dw2, dw_ref) < 1e-4
 
 
 PROLOGUE_CASES = [
