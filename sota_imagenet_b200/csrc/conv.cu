@@ -1437,10 +1437,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
       static_assert(STAGES * (kABytesW + kBBytesW) >= 4 * kRedSlabs * kSlabBytes, "ring too small");
       uint8_t* slabs = smem + (warp - 2) * kRedSlabs * kSlabBytes;
       if (k0 + quarter * 32 < p.Cout) {       // warp-uniform: rows past Cout would be clipped anyway
+        // (chunk order rotated by the split index: the splits of one gradient tile finish together and
+        //  would otherwise add into the same 4 KB at the same time)
+        const int nchunks = ncols / 32;
 #pragma unroll 1
-        for (int chunk = 0; chunk < BNC / 32; ++chunk) {
-          if (chunk * 32 >= ncols) break;
-          uint8_t* slab = slabs + (chunk % kRedSlabs) * kSlabBytes;
+        for (int ci = 0; ci < nchunks; ++ci) {
+          const int chunk = (ci + (int)blockIdx.z) % nchunks;
+          uint8_t* slab = slabs + (ci % kRedSlabs) * kSlabBytes;
           if (lane == 0) tma_store_wait_read<kRedSlabs - 1>();
           __syncwarp();
           uint32_t r[32];
@@ -1508,23 +1511,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 //     B (N = 192) = X region at rows +0, +pitch, +2*pitch        (r = 0, 1, 2; LBO = pitch rows)
 //     A (M = 128) = dY region at rows +0, +1                      (s = 1, 0;    LBO = 1 row)
 // One MMA (128 x 192 x 16) therefore produces SIX taps, a second one with A = dY at row -1 (s = 2; its
-// upper half is a don't-care duplicate) the remaining three: 16 MMAs per 128 positions instead of 72
-// N = 64 ones, two operand regions (64 KB) instead of 9 + 3 tiles (96 KB per 64 pixels).
-// Split over position ranges (one CTA per SM), TMA add-reduction of the 9 x 64 x 64 partials into dW.
+// upper half is a don't-care duplicate) the remaining three: two MMAs per 16 positions instead of nine
+// N = 64 ones.  The kernel is bound by the L2 -> SM fabric, so the tile is 240 positions (15 k-steps):
+// the regions (240 + 2 * pitch rows of X, 242 rows of dY) then cost 5 loads of 128 positions = 341
+// bytes per position (pitch <= 72), against 512 with 128-position tiles and 1.5 KB in the generic
+// kernel.  Split over position ranges (one CTA per SM), TMA add-reduction of the 9 x 64 x 64 partials.
 struct WgradHaloParams {
   int N, Cin;
   int pitch;          // W + 2
   int P;              // (H + 2) * pitch: padded positions per image
   long total_pos;     // N * P
-  int total_tiles;    // tiles of 128 positions; tile t covers J in [pitch + 128 t, +128)
+  int total_tiles;    // tiles of kWhTile positions; tile t covers J in [pitch + kWhTile t, +kWhTile)
   int tiles_per_cta;
 };
 
-constexpr int kWhTile = 128;                 // positions per tile
-constexpr int kWhChunk = kWhTile * 128;      // bytes of one 128-position load (64 channels)
+constexpr int kWhTile = 240;                 // positions per tile (15 MMA k-steps)
+constexpr int kWhLoad = 128;                 // positions per im2col TMA load
+constexpr int kWhChunk = kWhLoad * 128;      // bytes of one load (64 channels)
 
-// kXLoads: 128-position loads of the X region (needs 128 + 2 * pitch rows: 2 for pitch <= 63, 3 for
-// pitch <= 127); the dY region (130 rows) always takes two.
+// kXLoads: 128-position loads of the X region (needs 240 + 2 * pitch rows: 3 for pitch <= 72, 4 for
+// pitch <= 127); the dY region (242 rows) always takes two.
 template <int STAGES, int kXLoads>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
@@ -1581,12 +1587,12 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* xs = smem + stage * kStageBytes;
       uint8_t* ds = xs + kXBytes;
-      // X region starts at J0 - pitch = 128 t; the dY region at J0 - 1 = pitch - 1 + 128 t
+      // X region starts at J0 - pitch = kWhTile t; the dY region at J0 - 1 = pitch - 1 + kWhTile t
       long pos[kXLoads + 2];
 #pragma unroll
-      for (int j = 0; j < kXLoads; ++j) pos[j] = (long)(t + j) * kWhTile;
+      for (int j = 0; j < kXLoads; ++j) pos[j] = (long)t * kWhTile + j * kWhLoad;
       pos[kXLoads] = (long)t * kWhTile + p.pitch - 1;
-      pos[kXLoads + 1] = pos[kXLoads] + kWhTile;
+      pos[kXLoads + 1] = pos[kXLoads] + kWhLoad;
       int n_tma = 0;
 #pragma unroll
       for (int j = 0; j < kXLoads + 2; ++j) n_tma += pos[j] < p.total_pos ? 1 : 0;
@@ -1654,31 +1660,32 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     constexpr int kRedSlabs = 4;
     static_assert(STAGES * kStageBytes >= 4 * kRedSlabs * kSlabBytes, "ring too small");
     uint8_t* slabs = smem + (warp - 2) * kRedSlabs * kSlabBytes;
-    int issued = 0;
+    // work list of this warp: (accumulator g, r, 32-column half); the upper lane half of the second
+    // accumulator is a duplicate.  Every CTA starts at a different item: all splits finish their main
+    // loops together, and walking the list in the same order would pile ~150 reductions onto the same
+    // 4 KB of dW at the same time (same-address L2 atomics serialise).
+    const int n_items = half == 0 ? 12 : 6;
 #pragma unroll 1
-    for (int g = 0; g < 2; ++g) {
-      if (g == 1 && half == 1) break;               // upper half of the second accumulator is a duplicate
+    for (int it = 0; it < n_items; ++it) {
+      const int item = (it + (int)blockIdx.x) % n_items;
+      const int g = item / 6, chunk = item - g * 6;
       const int s_tap = g == 0 ? (half == 0 ? 1 : 0) : 2;
-#pragma unroll 1
-      for (int chunk = 0; chunk < 6; ++chunk) {     // (r, 32-column half) = (chunk / 2, chunk % 2)
-        const int r_tap = chunk >> 1;
-        uint8_t* slab = slabs + (issued % kRedSlabs) * kSlabBytes;
-        if (lane == 0) tma_store_wait_read<kRedSlabs - 1>();
-        __syncwarp();
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + g * 192 + chunk * 32, r);
-        tmem_ld_wait();
+      const int r_tap = chunk >> 1;
+      uint8_t* slab = slabs + (it % kRedSlabs) * kSlabBytes;
+      if (lane == 0) tma_store_wait_read<kRedSlabs - 1>();
+      __syncwarp();
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + g * 192 + chunk * 32, r);
+      tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(slab + lane * 128 + ((q ^ (lane & 7)) << 4)) =
-              make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_reduce_add_2d(&tmDw, slab, (r_tap * 3 + s_tap) * p.Cin + cb * 64 + (chunk & 1) * 32, k0);
-          tma_store_commit();
-        }
-        ++issued;
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(slab + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+            make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(&tmDw, slab, (r_tap * 3 + s_tap) * p.Cin + cb * 64 + (chunk & 1) * 32, k0);
+        tma_store_commit();
       }
     }
     if (lane == 0) tma_store_wait<0>();
@@ -2179,12 +2186,12 @@ extern "C" int sib_conv2d_wgrad(const void* x, const void* dy, float* dw, int N,
     hp.tiles_per_cta = (hp.total_tiles + splits - 1) / splits;
     splits = (hp.total_tiles + hp.tiles_per_cta - 1) / hp.tiles_per_cta;
     CUtensorMap tmDy, tmX, tmDw;
-    if (int rc = make_tmap_im2col_bf16(&tmDy, dy, N, H, W, K, -1, -1, 1, 1, 1, 1, 64, kWhTile, true)) return rc;
-    if (int rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, C, -1, -1, 1, 1, 1, 1, 64, kWhTile, true)) return rc;
+    if (int rc = make_tmap_im2col_bf16(&tmDy, dy, N, H, W, K, -1, -1, 1, 1, 1, 1, 64, kWhLoad, true)) return rc;
+    if (int rc = make_tmap_im2col_bf16(&tmX, x, N, H, W, C, -1, -1, 1, 1, 1, 1, 64, kWhLoad, true)) return rc;
     if (int rc = make_tmap_2d_f32(&tmDw, dw, K, (uint64_t)9 * C, (uint64_t)9 * C, 32, 32)) return rc;
     const dim3 grid(splits, cbs, 1);
-    if (hp.pitch <= 63) return launch_wgrad_halo<3, 2>(tmDy, tmX, tmDw, hp, grid, st);
-    return launch_wgrad_halo<2, 3>(tmDy, tmX, tmDw, hp, grid, st);
+    if (hp.pitch <= 72) return launch_wgrad_halo<2, 3>(tmDy, tmX, tmDw, hp, grid, st);
+    return launch_wgrad_halo<2, 4>(tmDy, tmX, tmDw, hp, grid, st);
   }
   WgradParams p{};
   p.M_total = N * OH * OW;
