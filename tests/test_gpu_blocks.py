@@ -172,12 +172,15 @@ def test_bottleneck_fused_bn_prologue_equals_separate_apply(inplanes, planes, st
     # up to that noise: > 99% of the bf16 outputs equal (measured 99.5%), the rest one ulp apart.
     # (The kernel-level test, test_conv_fprop_fused_bn_prologue, feeds both paths the SAME statistics
     #  and asserts exact equality.)
+    # (Gates sit well outside that noise -- one full-suite run in ~25 tripped the former 0.99 / 5e-3 --
+    #  and far inside what a wiring error produces: a wrong padding tap or mask moves the cosine of the
+    #  output below 0.99 and the gradient norms by tens of percent.)
     same = (o0 == o1).float().mean().item()
-    assert same > 0.99 and (o0.float() - o1.float()).abs().max() <= 0.13, same
+    assert same > 0.97 and (o0.float() - o1.float()).abs().max() <= 0.13, same
     assert _cos(o0, o1) > 0.999999
-    assert _cos(dx0, dx1) > 0.9999
+    assert _cos(dx0, dx1) > 0.9995
     for n in gr0:
-        assert _cos(gr0[n], gr1[n]) > 0.9999, (n, _cos(gr0[n], gr1[n]))
-        assert abs(float(gr1[n].norm() / gr0[n].norm()) - 1) < 5e-3, n
+        assert _cos(gr0[n], gr1[n]) > 0.9995, (n, _cos(gr0[n], gr1[n]))
+        assert abs(float(gr1[n].norm() / gr0[n].norm()) - 1) < 1e-2, n
     for n in b0:
         assert torch.allclose(b0[n], b1[n], rtol=1e-3, atol=1e-4), n
