@@ -306,6 +306,51 @@ int sib_augment(const void* src_u8, const int* boxes_dev, void* out, int B, int 
 int sib_val_transform(const void* src_u8, void* out, int B, int SH, int SW, int S,
                       int resize_shorter, float mean, float std, int out_mode, void* stream);
 void sib_val_geometry_host(int SH, int SW, int S, int resize_shorter, int* g4_host);
+/* ---- hybrid JPEG decode (reference dali_dataloader.py:65-72,140-145: fn.decoders.image*(device="mixed"),
+ *      i.e. nvJPEG's hybrid back end): Huffman decoding on the host, dequantisation + IDCT + chroma
+ *      upsampling + YCbCr->RGB on the device, written straight into the packed ragged uint8 buffer.
+ *      Integer arithmetic of the IJG / libjpeg-turbo decoder (islow IDCT, fancy upsampling):
+ *      bit-identical to PIL on the same stream. ---- */
+#define SIB_JPEG_OK 0
+#define SIB_JPEG_NOT_JPEG 1
+#define SIB_JPEG_CORRUPT 2
+#define SIB_JPEG_UNSUPPORTED_PROCESS 3     /* progressive / arithmetic / lossless */
+#define SIB_JPEG_UNSUPPORTED_PRECISION 4   /* not 8-bit */
+#define SIB_JPEG_UNSUPPORTED_COLORSPACE 5  /* CMYK, Adobe RGB, ... */
+#define SIB_JPEG_UNSUPPORTED_SAMPLING 6    /* anything but 4:4:4 / 4:2:2 / 4:2:0 */
+#define SIB_JPEG_UNSUPPORTED_SCANS 7       /* more than one scan */
+typedef struct sib_jpeg_info {
+  long coef_count;               /* int16 coefficients of all components (multiple of 64) */
+  int status;                    /* SIB_JPEG_*: anything but OK means "decode this one elsewhere" */
+  int width, height, ncomp;      /* ncomp 1 (grey) or 3 (YCbCr) */
+  int hs[3], vs[3];              /* sampling factors per component */
+  int hmax, vmax;
+  int mcus_x, mcus_y;
+  int blocks_w[3], blocks_h[3];  /* 8x8 blocks per component, padded to whole MCUs */
+  int restart_interval;
+  unsigned short quant[3][64];   /* quantisation table per component, natural (row-major) order */
+} sib_jpeg_info;
+/* one record per image of a batch (device array): where its coefficients, scratch planes and output live */
+typedef struct sib_jpeg_image {
+  long coef_off[3];              /* first coefficient of component c in the batch buffer (int16 elements) */
+  long plane_off[3];             /* first byte of component c's plane [blocks_h*8][blocks_w*8] in the scratch */
+  long out_off;                  /* first byte of the RGB image [height][width][3] in the output buffer */
+  int width, height, ncomp;
+  int hmax, vmax;
+  int blocks_w[3], blocks_h[3];
+  int pad_;
+  unsigned short quant[3][64];
+} sib_jpeg_image;
+/* host, thread-safe, no CUDA: */
+int sib_jpeg_parse(const unsigned char* data, long size, sib_jpeg_info* info);
+/* coef: info.coef_count int16 values, component after component, blocks in raster order, natural order
+ * inside a block, not dequantised */
+int sib_jpeg_decode_coefficients(const unsigned char* data, long size, short* coef);
+/* device: max_blocks = largest sum of blocks over the components of one image, max_pixels = largest
+ * width*height; planes_dev = scratch for all component planes of the batch */
+int sib_jpeg_idct_rgb(const short* coef_dev, const sib_jpeg_image* images_dev, int B, int max_blocks,
+                      int max_pixels, unsigned char* planes_dev, unsigned char* out_dev, void* stream);
+
 /* ragged batches of real images (records.pack_batch): packed uint8 buffer + per-image byte offsets
  * [B] + {H, W} [B][2]; same arithmetic as sib_rrc_boxes / sib_augment / sib_val_transform with the
  * image base and extent looked up per sample (fn.decoders.image_random_crop + fn.resize on images of

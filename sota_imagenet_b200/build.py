@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 OUT_DIR = os.path.join(ROOT, "_build")
 LIB = os.path.join(ROOT, "libsib200.so")
-SOURCES = ["host.cu", "conv.cu", "norm.cu", "head.cu", "optim.cu", "augment.cu", "extra.cu", "peer.cu", "batchaug.cu"]
+SOURCES = ["host.cu", "conv.cu", "norm.cu", "head.cu", "optim.cu", "augment.cu", "extra.cu", "peer.cu", "batchaug.cu", "jpeg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

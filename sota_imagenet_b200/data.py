@@ -248,9 +248,18 @@ class RecordLoader:
     Same interface as `SyntheticLoader` (`batch_size`, `__len__`, iteration; drop-last)."""
 
     def __init__(self, cfg, reader, train=True, output="nhwc4_bf16", one_hot=True, device="cuda",
-                 decode_workers=8):
-        from . import records
-        self._records = records
+                 decode_workers=8, decode=None):
+        from . import jpeg, records
+        self._records, self._jpeg = records, jpeg
+        # "device": hybrid JPEG decode like the reference's device="mixed" decoders (dali_dataloader.py:65-72,
+        # 140-145) -- Huffman stage on host threads, IDCT / upsampling / colour conversion on the GPU
+        # (jpeg.decode_batch); "host": the whole decoder on host threads (PIL).  Same pixels either way.
+        # Default: "device" on a CUDA device.
+        if decode is None:
+            decode = "device" if str(device).startswith("cuda") else "host"
+        if decode not in ("device", "host"):
+            raise ValueError("decode must be 'device' or 'host'")
+        self.decode = decode
         self.cfg, self.reader, self.train, self.one_hot = cfg, reader, train, one_hot
         self.batch_size, self.num_classes, self.device = cfg.batch_size, cfg.num_classes, device
         self.image_size = cfg.image_size
@@ -272,9 +281,12 @@ class RecordLoader:
         return len(self.reader) // self.batch_size
 
     def _emit(self, samples):
-        buf, offsets, dims, labels = self._records.decode_batch(samples, workers=self.decode_workers,
-                                                                pinned=torch.cuda.is_available())
         dev = self.device
+        if self.decode == "device":
+            buf, offsets, dims, labels = self._jpeg.decode_batch(samples, workers=self.decode_workers, device=dev)
+        else:
+            buf, offsets, dims, labels = self._records.decode_batch(samples, workers=self.decode_workers,
+                                                                    pinned=torch.cuda.is_available())
         buf, offsets, dims = (t.to(dev, non_blocking=True) for t in (buf, offsets, dims))
         labels = labels.to(dev, non_blocking=True)
         if self.train:

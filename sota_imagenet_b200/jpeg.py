@@ -1,0 +1,160 @@
+"""Hybrid JPEG decode of a batch: host Huffman stage -> device IDCT / upsampling / colour conversion.
+
+What the reference reaches through `fn.decoders.image_random_crop(..., device="mixed")` /
+`fn.decoders.image(device="mixed")` (dali_dataloader.py:65-72, 140-145): nvJPEG's hybrid back end
+entropy-decodes on the host and runs the rest of the decoder on the GPU.  Same split here (`csrc/jpeg.cu`):
+
+  parse(data)                      `sib_jpeg_parse`: geometry + quantisation tables, or the reason the
+                                   stream is outside the device subset (progressive, CMYK, ...)
+  decode_coefficients(data, out)   `sib_jpeg_decode_coefficients`: int16 DCT coefficients (thread pool;
+                                   ctypes releases the GIL, the C routine keeps no global state)
+  decode_batch(samples)            ONE pinned coefficient buffer + ONE descriptor table -> H2D ->
+                                   `sib_jpeg_idct_rgb` writes every image as uint8 [H][W][3] into the packed
+                                   ragged buffer (`records.pack_batch` layout) that `sib_rrc_boxes_ragged`
+                                   / `sib_augment_ragged` / `sib_val_transform_ragged` consume.
+
+Streams the device path does not take (`JpegInfo.status != 0`: progressive / arithmetic, 12-bit, CMYK,
+unusual sampling, PNG files of the ImageNet tree) are decoded by `records.decode_image` on the host and
+copied into the same packed buffer; everything downstream is identical.  The pixels are bit-identical
+to PIL / libjpeg-turbo either way.
+"""
+import ctypes
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import _lib
+
+
+class JpegInfo(ctypes.Structure):
+    """sib_jpeg_info (include/sib200.h)"""
+    _fields_ = [("coef_count", ctypes.c_long), ("status", ctypes.c_int), ("width", ctypes.c_int),
+                ("height", ctypes.c_int), ("ncomp", ctypes.c_int), ("hs", ctypes.c_int * 3),
+                ("vs", ctypes.c_int * 3), ("hmax", ctypes.c_int), ("vmax", ctypes.c_int),
+                ("mcus_x", ctypes.c_int), ("mcus_y", ctypes.c_int), ("blocks_w", ctypes.c_int * 3),
+                ("blocks_h", ctypes.c_int * 3), ("restart_interval", ctypes.c_int),
+                ("quant", (ctypes.c_ushort * 64) * 3)]
+
+    def as_dict(self):
+        n = self.ncomp
+        return dict(width=self.width, height=self.height, ncomp=n, hmax=self.hmax, vmax=self.vmax,
+                    blocks_w=list(self.blocks_w)[:n], blocks_h=list(self.blocks_h)[:n],
+                    quant=[np.array(self.quant[c], dtype=np.int64) for c in range(n)])
+
+
+# sib_jpeg_image (include/sib200.h): one record per image of a batch
+IMAGE_DTYPE = np.dtype([("coef_off", "<i8", 3), ("plane_off", "<i8", 3), ("out_off", "<i8"),
+                        ("width", "<i4"), ("height", "<i4"), ("ncomp", "<i4"), ("hmax", "<i4"), ("vmax", "<i4"),
+                        ("blocks_w", "<i4", 3), ("blocks_h", "<i4", 3), ("pad_", "<i4"),
+                        ("quant", "<u2", (3, 64))], align=True)
+assert IMAGE_DTYPE.itemsize == 488
+
+STATUS = {0: "ok", 1: "not a JPEG", 2: "corrupt", 3: "progressive / arithmetic / lossless process",
+          4: "not 8-bit", 5: "colour space (CMYK, Adobe RGB)", 6: "sampling factors", 7: "more than one scan"}
+
+
+def parse(data):
+    """bytes -> JpegInfo; `status == 0` means the device path decodes this stream."""
+    info = JpegInfo()
+    buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+    _lib.check(_lib.load().sib_jpeg_parse(buf, len(data), ctypes.byref(info)))
+    return info
+
+
+def decode_coefficients(data, out=None, info=None):
+    """Host Huffman stage: bytes -> int16 coefficients (flat numpy array, or written into `out`)."""
+    info = info or parse(data)
+    if info.status != 0:
+        raise _lib.SibError("jpeg: stream not decodable on the device path (%s)" % STATUS.get(info.status, info.status))
+    if out is None:
+        out = np.empty(info.coef_count, dtype=np.int16)
+    assert out.dtype == np.int16 and out.size >= info.coef_count and out.flags.c_contiguous
+    buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+    _lib.check(_lib.load().sib_jpeg_decode_coefficients(buf, len(data), ctypes.c_void_p(out.ctypes.data)))
+    return out
+
+
+def plan_batch(infos, fallback_dims):
+    """Layout of one batch: per-image descriptor table (IMAGE_DTYPE), total coefficients, scratch bytes,
+    packed-output offsets / dims (the `records.pack_batch` layout: every image 16-byte aligned)."""
+    n = len(infos)
+    table = np.zeros(n, dtype=IMAGE_DTYPE)
+    dims = np.zeros((n, 2), dtype=np.int32)
+    offsets = np.zeros(n, dtype=np.int64)
+    coef_total = plane_total = out_total = 0
+    max_blocks = max_pixels = 0
+    for i, info in enumerate(infos):
+        if info is None or info.status != 0:
+            h, w = fallback_dims[i]
+        else:
+            h, w = info.height, info.width
+            t = table[i]
+            t["width"], t["height"], t["ncomp"], t["hmax"], t["vmax"] = w, h, info.ncomp, info.hmax, info.vmax
+            blocks = 0
+            for c in range(info.ncomp):
+                bw, bh = info.blocks_w[c], info.blocks_h[c]
+                t["coef_off"][c], t["plane_off"][c] = coef_total, plane_total
+                t["blocks_w"][c], t["blocks_h"][c] = bw, bh
+                t["quant"][c] = np.frombuffer(info.quant[c], dtype=np.uint16)
+                coef_total += bw * bh * 64
+                plane_total += bw * bh * 64
+                blocks += bw * bh
+            t["out_off"] = out_total
+            max_blocks, max_pixels = max(max_blocks, blocks), max(max_pixels, h * w)
+        dims[i] = (h, w)
+        offsets[i] = out_total
+        size = h * w * 3
+        out_total += size + (-size) % 16
+    return dict(table=table, dims=dims, offsets=offsets, coef_total=coef_total, plane_total=plane_total,
+                out_total=out_total, max_blocks=max_blocks, max_pixels=max_pixels)
+
+
+def decode_batch(samples, workers=8, device="cuda", host_decode=None):
+    """samples: list of (encoded bytes, label) -> (packed uint8 device buffer, offsets, dims, labels), the
+    tuple `records.decode_batch(..., canvas=None)` returns, with the buffer already resident on `device`.
+    `host_decode(bytes) -> uint8 [H, W, 3]` takes the streams outside the device subset."""
+    import torch
+    from . import ops, records
+    _lib.require_device()
+    host_decode = host_decode or records.decode_image
+    datas = [s[0] for s in samples]
+    labels = torch.tensor([s[1] for s in samples], dtype=torch.int64)
+    infos = [parse(d) for d in datas]
+    on_device = [i for i, inf in enumerate(infos) if inf.status == 0]
+    on_host = [i for i, inf in enumerate(infos) if inf.status != 0]
+    host_images = {}
+    pool = ThreadPoolExecutor(max_workers=workers) if workers > 1 and len(datas) > 1 else None
+    try:
+        if on_host:
+            dec = list(pool.map(host_decode, [datas[i] for i in on_host])) if pool else \
+                [host_decode(datas[i]) for i in on_host]
+            host_images = dict(zip(on_host, dec))
+        plan = plan_batch(infos, {i: im.shape[:2] for i, im in host_images.items()})
+        coef = torch.empty(max(plan["coef_total"], 1), dtype=torch.int16).pin_memory()
+        coef_np = coef.numpy()
+
+        def huff(i):
+            t = plan["table"][i]
+            decode_coefficients(datas[i], coef_np[int(t["coef_off"][0]):], infos[i])
+
+        if pool:
+            list(pool.map(huff, on_device))
+        else:
+            for i in on_device:
+                huff(i)
+    finally:
+        if pool:
+            pool.shutdown()
+    out = torch.empty(max(plan["out_total"], 1), dtype=torch.uint8, device=device)
+    if on_device:
+        # compact table of the device-decoded images only (the kernels index it by blockIdx.y)
+        table = torch.from_numpy(plan["table"][on_device].view(np.uint8).reshape(len(on_device), -1).copy())
+        table_dev = table.pin_memory().to(device, non_blocking=True)
+        coef_dev = coef.to(device, non_blocking=True)
+        planes = torch.empty(max(plan["plane_total"], 1), dtype=torch.uint8, device=device)
+        ops.jpeg_idct_rgb(coef_dev, table_dev, len(on_device), plan["max_blocks"], plan["max_pixels"], planes, out)
+    for i, im in host_images.items():
+        flat = torch.from_numpy(np.array(im, dtype=np.uint8).reshape(-1))      # (a writable copy)
+        off = int(plan["offsets"][i])
+        out[off:off + flat.numel()].copy_(flat, non_blocking=False)
+    return out, torch.from_numpy(plan["offsets"]), torch.from_numpy(plan["dims"]), labels

@@ -803,6 +803,17 @@ def val_transform_ragged(packed, offsets, dims, size, resize_shorter, mean=127.5
     return out
 
 
+def jpeg_idct_rgb(coef, table, n_images, max_blocks, max_pixels, planes, out):
+    """Device half of the hybrid JPEG decoder (jpeg.decode_batch): int16 coefficients + per-image
+    descriptor table (jpeg.IMAGE_DTYPE records as bytes) -> packed uint8 RGB images in `out`."""
+    _lib.require_device()
+    assert coef.dtype == torch.int16 and coef.is_cuda and table.dtype == torch.uint8 and table.is_cuda
+    assert planes.dtype == torch.uint8 and out.dtype == torch.uint8 and planes.is_cuda and out.is_cuda
+    call("sib_jpeg_idct_rgb", _p(coef), _p(table), int(n_images), int(max_blocks), int(max_pixels), _p(planes),
+         _p(out), _stream())
+    return out
+
+
 def one_hot(labels, num_classes):
     out = torch.empty((labels.shape[0], num_classes), dtype=torch.float32, device=labels.device)
     call("sib_one_hot", _p(labels), _p(out), labels.shape[0], num_classes, _stream())
