@@ -38,7 +38,7 @@ def main(src, out_json, out_summary):
     step = rows[opt[-2] + 1:opt[-1] + 1]
 
     def fam(name):
-        if re.search(r"igemm|wgrad_kernel|halo3x3", name):
+        if re.search(r"igemm|wgrad_|halo3x3", name):
             return "conv"
         if re.search(r"bn_(finalize_apply|bwd_apply|bwd_reduce|apply|stats|act_maxpool)", name):
             return "bn"

@@ -525,30 +525,47 @@ __device__ __forceinline__ int chroma_at(const unsigned char* __restrict__ pl, i
   return (3 * cur + 3 * r0[cx - 1] + r1[cx - 1] + 8) >> 4;
 }
 
-// one thread per output pixel: Y + upsampled Cb / Cr -> RGB (jdcolor.c, 16-bit fixed point)
+// Y + upsampled Cb / Cr -> RGB (jdcolor.c, 16-bit fixed point)
+__device__ __forceinline__ uint32_t jpeg_pixel(const sib_jpeg_image& im, const unsigned char* __restrict__ planes,
+                                               int i, int dw, int dh) {
+  const int y = i / im.width, x = i - y * im.width;
+  const int yy = planes[im.plane_off[0] + (long)y * (im.blocks_w[0] * 8) + x];
+  if (im.ncomp == 1) return (uint32_t)yy * 0x010101u;
+  const int cb = chroma_at(planes + im.plane_off[1], im.blocks_w[1] * 8, dw, dh, im.hmax, im.vmax, x, y) - 128;
+  const int cr = chroma_at(planes + im.plane_off[2], im.blocks_w[2] * 8, dw, dh, im.hmax, im.vmax, x, y) - 128;
+  // FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554, ONE_HALF = 32768
+  const int r = yy + ((91881 * cr + 32768) >> 16);
+  const int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+  const int b = yy + ((116130 * cb + 32768) >> 16);
+  return (uint32_t)clamp255(r) | ((uint32_t)clamp255(g) << 8) | ((uint32_t)clamp255(b) << 16);
+}
+
+// one thread per FOUR consecutive pixels of the packed [H][W][3] image: 12 output bytes = three aligned
+// 32-bit stores (every image starts on a 16-byte boundary); the last 1-3 pixels are written bytewise
 __global__ void __launch_bounds__(256)
 jpeg_rgb_kernel(const sib_jpeg_image* __restrict__ images, const unsigned char* __restrict__ planes,
                 unsigned char* __restrict__ out) {
   const sib_jpeg_image& im = images[blockIdx.y];
   const int npx = im.width * im.height;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
-    const int y = i / im.width, x = i - y * im.width;
-    const int yy = planes[im.plane_off[0] + (long)y * (im.blocks_w[0] * 8) + x];
-    unsigned char* o = out + im.out_off + (long)i * 3;
-    if (im.ncomp == 1) {
-      o[0] = o[1] = o[2] = (unsigned char)yy;
-      continue;
+  const int dw = (im.width + im.hmax - 1) / im.hmax, dh = (im.height + im.vmax - 1) / im.vmax;
+  unsigned char* base = out + im.out_off;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q * 4 < npx; q += gridDim.x * blockDim.x) {
+    const int i0 = q * 4;
+    if (i0 + 4 <= npx) {
+      const uint32_t p0 = jpeg_pixel(im, planes, i0, dw, dh), p1 = jpeg_pixel(im, planes, i0 + 1, dw, dh);
+      const uint32_t p2 = jpeg_pixel(im, planes, i0 + 2, dw, dh), p3 = jpeg_pixel(im, planes, i0 + 3, dw, dh);
+      uint32_t* o = reinterpret_cast<uint32_t*>(base + (long)i0 * 3);
+      o[0] = p0 | (p1 << 24);
+      o[1] = (p1 >> 8) | (p2 << 16);
+      o[2] = (p2 >> 16) | (p3 << 8);
+    } else {
+      for (int i = i0; i < npx; ++i) {
+        const uint32_t px = jpeg_pixel(im, planes, i, dw, dh);
+        base[(long)i * 3] = (unsigned char)px;
+        base[(long)i * 3 + 1] = (unsigned char)(px >> 8);
+        base[(long)i * 3 + 2] = (unsigned char)(px >> 16);
+      }
     }
-    const int dw = (im.width + im.hmax - 1) / im.hmax, dh = (im.height + im.vmax - 1) / im.vmax;
-    const int cb = chroma_at(planes + im.plane_off[1], im.blocks_w[1] * 8, dw, dh, im.hmax, im.vmax, x, y) - 128;
-    const int cr = chroma_at(planes + im.plane_off[2], im.blocks_w[2] * 8, dw, dh, im.hmax, im.vmax, x, y) - 128;
-    // FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554, ONE_HALF = 32768
-    const int r = yy + ((91881 * cr + 32768) >> 16);
-    const int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
-    const int b = yy + ((116130 * cb + 32768) >> 16);
-    o[0] = (unsigned char)clamp255(r);
-    o[1] = (unsigned char)clamp255(g);
-    o[2] = (unsigned char)clamp255(b);
   }
 }
 
@@ -562,7 +579,7 @@ extern "C" int sib_jpeg_idct_rgb(const short* coef_dev, const sib_jpeg_image* im
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   jpeg_idct_kernel<<<dim3((max_blocks + 127) / 128, B), 128, 0, st>>>(coef_dev, images_dev, planes_dev);
   SIB_LAUNCH_CHECK();
-  int gx = (max_pixels + 255) / 256;
+  int gx = (max_pixels / 4 + 256) / 256;
   if (gx > 1024) gx = 1024;
   jpeg_rgb_kernel<<<dim3(gx, B), 256, 0, st>>>(images_dev, planes_dev, out_dev);
   SIB_LAUNCH_CHECK();
