@@ -53,11 +53,16 @@ STATUS = {0: "ok", 1: "not a JPEG", 2: "corrupt", 3: "progressive / arithmetic /
           4: "not 8-bit", 5: "colour space (CMYK, Adobe RGB)", 6: "sampling factors", 7: "more than one scan"}
 
 
+def _as_bytes(data):
+    # ctypes passes a `bytes` object as a pointer to its buffer: no copy, no per-call array type
+    return data if isinstance(data, bytes) else bytes(data)
+
+
 def parse(data):
     """bytes -> JpegInfo; `status == 0` means the device path decodes this stream."""
     info = JpegInfo()
-    buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
-    _lib.check(_lib.load().sib_jpeg_parse(buf, len(data), ctypes.byref(info)))
+    data = _as_bytes(data)
+    _lib.check(_lib.load().sib_jpeg_parse(data, len(data), ctypes.byref(info)))
     return info
 
 
@@ -69,8 +74,8 @@ def decode_coefficients(data, out=None, info=None):
     if out is None:
         out = np.empty(info.coef_count, dtype=np.int16)
     assert out.dtype == np.int16 and out.size >= info.coef_count and out.flags.c_contiguous
-    buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
-    _lib.check(_lib.load().sib_jpeg_decode_coefficients(buf, len(data), ctypes.c_void_p(out.ctypes.data)))
+    data = _as_bytes(data)
+    _lib.check(_lib.load().sib_jpeg_decode_coefficients(data, len(data), ctypes.c_void_p(out.ctypes.data)))
     return out
 
 
@@ -79,34 +84,66 @@ def plan_batch(infos, fallback_dims):
     packed-output offsets / dims (the `records.pack_batch` layout: every image 16-byte aligned)."""
     n = len(infos)
     table = np.zeros(n, dtype=IMAGE_DTYPE)
+    coef_off, plane_off, out_off = table["coef_off"], table["plane_off"], table["out_off"]
+    bws, bhs, quant = table["blocks_w"], table["blocks_h"], table["quant"]
     dims = np.zeros((n, 2), dtype=np.int32)
     offsets = np.zeros(n, dtype=np.int64)
+    head = np.zeros((n, 5), dtype=np.int32)               # width, height, ncomp, hmax, vmax
     coef_total = plane_total = out_total = 0
     max_blocks = max_pixels = 0
     for i, info in enumerate(infos):
         if info is None or info.status != 0:
             h, w = fallback_dims[i]
         else:
-            h, w = info.height, info.width
-            t = table[i]
-            t["width"], t["height"], t["ncomp"], t["hmax"], t["vmax"] = w, h, info.ncomp, info.hmax, info.vmax
+            h, w, nc = info.height, info.width, info.ncomp
+            head[i] = (w, h, nc, info.hmax, info.vmax)
+            bw, bh = info.blocks_w[:nc], info.blocks_h[:nc]
             blocks = 0
-            for c in range(info.ncomp):
-                bw, bh = info.blocks_w[c], info.blocks_h[c]
-                t["coef_off"][c], t["plane_off"][c] = coef_total, plane_total
-                t["blocks_w"][c], t["blocks_h"][c] = bw, bh
-                t["quant"][c] = np.frombuffer(info.quant[c], dtype=np.uint16)
-                coef_total += bw * bh * 64
-                plane_total += bw * bh * 64
-                blocks += bw * bh
-            t["out_off"] = out_total
+            for c in range(nc):
+                coef_off[i, c] = plane_off[i, c] = coef_total       # (one byte of plane per coefficient)
+                coef_total += bw[c] * bh[c] * 64
+                blocks += bw[c] * bh[c]
+            bws[i, :nc], bhs[i, :nc] = bw, bh
+            quant[i] = np.frombuffer(info.quant, dtype=np.uint16).reshape(3, 64)
+            out_off[i] = out_total
             max_blocks, max_pixels = max(max_blocks, blocks), max(max_pixels, h * w)
         dims[i] = (h, w)
         offsets[i] = out_total
         size = h * w * 3
         out_total += size + (-size) % 16
+    plane_total = coef_total
+    for k, name in enumerate(("width", "height", "ncomp", "hmax", "vmax")):
+        table[name] = head[:, k]
     return dict(table=table, dims=dims, offsets=offsets, coef_total=coef_total, plane_total=plane_total,
                 out_total=out_total, max_blocks=max_blocks, max_pixels=max_pixels)
+
+
+class _PinnedRing:
+    """Two grow-only pinned int16 staging buffers used alternately: `cudaHostAlloc` of ~140 MB per batch costs
+    more than the Huffman stage itself, and a buffer may only be rewritten once the H2D copy that read it has
+    completed (its event is waited for on the host before reuse)."""
+
+    def __init__(self):
+        self.slots = [[None, None], [None, None]]      # (tensor, event of the last copy out of it)
+        self.next = 0
+
+    def take(self, n):
+        import torch
+        slot = self.slots[self.next]
+        self.next ^= 1
+        if slot[1] is not None:
+            slot[1].synchronize()
+        if slot[0] is None or slot[0].numel() < n:
+            slot[0] = torch.empty(max(n, 1), dtype=torch.int16).pin_memory()
+        return slot
+
+    def copied(self, slot):
+        import torch
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+
+
+_RING = _PinnedRing()
 
 
 def decode_batch(samples, workers=8, device="cuda", host_decode=None):
@@ -119,6 +156,7 @@ def decode_batch(samples, workers=8, device="cuda", host_decode=None):
     host_decode = host_decode or records.decode_image
     datas = [s[0] for s in samples]
     labels = torch.tensor([s[1] for s in samples], dtype=torch.int64)
+    datas = [_as_bytes(d) for d in datas]
     infos = [parse(d) for d in datas]
     on_device = [i for i, inf in enumerate(infos) if inf.status == 0]
     on_host = [i for i, inf in enumerate(infos) if inf.status != 0]
@@ -130,7 +168,8 @@ def decode_batch(samples, workers=8, device="cuda", host_decode=None):
                 [host_decode(datas[i]) for i in on_host]
             host_images = dict(zip(on_host, dec))
         plan = plan_batch(infos, {i: im.shape[:2] for i, im in host_images.items()})
-        coef = torch.empty(max(plan["coef_total"], 1), dtype=torch.int16).pin_memory()
+        slot = _RING.take(plan["coef_total"])
+        coef = slot[0][:max(plan["coef_total"], 1)]
         coef_np = coef.numpy()
 
         def huff(i):
@@ -151,6 +190,7 @@ def decode_batch(samples, workers=8, device="cuda", host_decode=None):
         table = torch.from_numpy(plan["table"][on_device].view(np.uint8).reshape(len(on_device), -1).copy())
         table_dev = table.pin_memory().to(device, non_blocking=True)
         coef_dev = coef.to(device, non_blocking=True)
+        _RING.copied(slot)
         planes = torch.empty(max(plan["plane_total"], 1), dtype=torch.uint8, device=device)
         ops.jpeg_idct_rgb(coef_dev, table_dev, len(on_device), plan["max_blocks"], plan["max_pixels"], planes, out)
     for i, im in host_images.items():
