@@ -87,10 +87,18 @@ def test_record_loader_device_decode_equals_host_decode(tmp_path):
     for train in (False, True):
         split = "train" if train else "val"
         runs = {}
-        for mode in ("device", "host"):
-            loader = data.RecordLoader(cfg, data.make_reader(cfg, str(root), split), train=train, decode=mode)
-            assert loader.decode == mode
-            runs[mode] = [(x.clone(), t.clone()) for x, t in loader]
-        assert len(runs["device"]) == 2
-        for (xd, td), (xh, th) in zip(runs["device"], runs["host"]):
-            assert torch.equal(xd, xh) and torch.equal(td, th)
+        for mode, prefetch in (("device", 2), ("host", 0), ("device", 0)):
+            loader = data.RecordLoader(cfg, data.make_reader(cfg, str(root), split), train=train, decode=mode,
+                                       prefetch=prefetch)
+            assert loader.decode == mode and loader.prefetch == prefetch
+            runs[(mode, prefetch)] = [(x.clone(), t.clone()) for x, t in loader]
+        assert len(runs[("device", 2)]) == 2
+        for other in (("host", 0), ("device", 0)):          # loader thread + side stream == synchronous == host decode
+            for (xd, td), (xh, th) in zip(runs[("device", 2)], runs[other]):
+                assert torch.equal(xd, xh) and torch.equal(td, th)
+    # a consumer that stops early must not leave the loader thread blocked on its queue
+    loader = data.RecordLoader(cfg, data.make_reader(cfg, str(root), "train"), train=True, prefetch=1)
+    for _ in loader:
+        break
+    import threading
+    assert not [t for t in threading.enumerate() if t.name == "sib-record-loader" and t.is_alive()]
