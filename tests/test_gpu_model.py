@@ -96,8 +96,10 @@ def test_every_parameter_gradient_in_a_damped_regime(slope):
         STRICT gates: all 54 conv / fc weight tensors cosine >= 0.999 and gradient norm within 1 %
         of the whole-network bf16-faithful oracle, >= 0.995 / 1 % of PURE fp32 torchvision; the 107
         BatchNorm / bias vectors (sums over all pixels with heavy cancellation: a BN bias in front
-        of another BN has an almost vanishing true gradient) >= 0.98 / 5 % and >= 0.97 / 5 %.
-        Measured on B200: 0.99952 / 1.7e-3 and 0.988 / 3.2e-2 (faithful), 0.996 and 0.978 (fp32).
+        of another BN has an almost vanishing true gradient) >= 0.97 / 5 % and >= 0.96 / 5 %.
+        Measured on B200: 0.99952 / 1.7e-3 and 0.988 / 3.2e-2 (faithful), 0.996 and 0.978 (fp32);
+        the vector cosines move by ~1e-2 from run to run with the order of the fp32 atomics (the same
+        quantity spans 0.9797 .. 0.9897 in the data-parallel equivalence logs), hence one point of margin.
       * slope = 0 : plain ReLU (the RELU code path), same damping; bf16 storage still flips
         ~0.15 % of the masks per layer, so the gates are looser (measured 0.983 / 3e-3 for the
         weights, 0.974 / 4e-2 .. 1e-1 for the vectors against the faithful oracle) but a missing
@@ -157,7 +159,7 @@ def test_every_parameter_gradient_in_a_damped_regime(slope):
             max(abs(r[2] - 1) for r in grp), max(abs(r[4] - 1) for r in grp)))
     #        (cos, norm dev) vs faithful, (cos, norm dev) vs fp32
     gates = {True: {0.8: (0.999, 1e-2, 0.995, 1e-2), 0.0: (0.97, 1e-2, 0.94, 2e-2)},
-             False: {0.8: (0.98, 5e-2, 0.97, 5e-2), 0.0: (0.95, 1.5e-1, 0.90, 1.5e-1)}}
+             False: {0.8: (0.97, 5e-2, 0.96, 5e-2), 0.0: (0.95, 1.5e-1, 0.90, 1.5e-1)}}
     for name, cf, nf, cr, nr in rows:
         gc, gn, rc, rn = gates[rp[name].dim() > 1][slope]
         assert cf >= gc and abs(nf - 1) < gn, (name, cf, nf)
