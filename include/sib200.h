@@ -338,7 +338,7 @@ typedef struct sib_jpeg_image {
   int width, height, ncomp;
   int hmax, vmax;
   int blocks_w[3], blocks_h[3];
-  int pad_;
+  int mcu_rows;                  /* > 0: only the first mcu_rows MCU rows were decoded (row-limited decode) */
   unsigned short quant[3][64];
 } sib_jpeg_image;
 /* host, thread-safe, no CUDA: */
@@ -346,6 +346,9 @@ int sib_jpeg_parse(const unsigned char* data, long size, sib_jpeg_info* info);
 /* coef: info.coef_count int16 values, component after component, blocks in raster order, natural order
  * inside a block, not dequantised */
 int sib_jpeg_decode_coefficients(const unsigned char* data, long size, short* coef);
+/* the same, stopping after the first mcu_rows rows of MCUs (0 = all): what a random crop that ends above the
+ * bottom of the image needs (ROI decoding of fn.decoders.image_random_crop, dali_dataloader.py:65-72) */
+int sib_jpeg_decode_coefficients_rows(const unsigned char* data, long size, short* coef, int mcu_rows);
 /* device: max_blocks = largest sum of blocks over the components of one image, max_pixels = largest
  * width*height; planes_dev = scratch for all component planes of the batch */
 int sib_jpeg_idct_rgb(const short* coef_dev, const sib_jpeg_image* images_dev, int B, int max_blocks,

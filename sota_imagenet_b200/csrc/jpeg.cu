@@ -316,6 +316,13 @@ extern "C" int sib_jpeg_parse(const unsigned char* data, long size, sib_jpeg_inf
 }
 
 extern "C" int sib_jpeg_decode_coefficients(const unsigned char* data, long size, short* coef) {
+  return sib_jpeg_decode_coefficients_rows(data, size, coef, 0);
+}
+
+// mcu_rows > 0: decode only the first mcu_rows rows of MCUs (a random crop that ends above the bottom of the
+// image does not need the rest: entropy-coded data cannot be skipped, but it need not be read to the end --
+// what fn.decoders.image_random_crop's ROI decoding saves).  Coefficients of later rows are left untouched.
+extern "C" int sib_jpeg_decode_coefficients_rows(const unsigned char* data, long size, short* coef, int mcu_rows) {
   SIB_CHECK(data != nullptr && coef != nullptr, "jpeg_decode_coefficients: null argument");
   ParsedJpeg pj;
   parse_jpeg(data, size, &pj);
@@ -332,18 +339,19 @@ extern "C" int sib_jpeg_decode_coefficients(const unsigned char* data, long size
     dc[c] = &tabs[di];
     ac[c] = &tabs[ai];
   }
-  memset(coef, 0, sizeof(short) * o.coef_count);
+  const int rows_end = (mcu_rows > 0 && mcu_rows < o.mcus_y) ? mcu_rows : o.mcus_y;
   short* base[3];
   long off = 0;
   for (int c = 0; c < o.ncomp; ++c) {
     base[c] = coef + off;
+    memset(base[c], 0, sizeof(short) * (long)o.blocks_w[c] * (rows_end * o.vs[c]) * 64);
     off += (long)o.blocks_w[c] * o.blocks_h[c] * 64;
   }
   BitReader br{data, pj.scan_begin, size, 0ull, 0, false};
   int pred[3] = {0, 0, 0};
   int until_restart = o.restart_interval;
   int next_rst = 0;
-  for (int my = 0; my < o.mcus_y; ++my) {
+  for (int my = 0; my < rows_end; ++my) {
     for (int mx = 0; mx < o.mcus_x; ++mx) {
       if (o.restart_interval && until_restart == 0) {
         // byte-align, expect RSTn, reset the predictors
@@ -468,6 +476,8 @@ jpeg_idct_kernel(const short* __restrict__ coef, const sib_jpeg_image* __restric
   }
   if (c >= im.ncomp) return;
   const int by = b / im.blocks_w[c], bx = b - by * im.blocks_w[c];
+  // row-limited decode: block rows past the decoded MCU rows hold no coefficients (vs_c = blocks_h[c] * vmax / blocks_h[0])
+  if (im.mcu_rows > 0 && by >= im.mcu_rows * (im.blocks_h[c] * im.vmax / im.blocks_h[0])) return;
   const uint4* src = reinterpret_cast<const uint4*>(coef + im.coef_off[c] + (long)b * 64);
   const unsigned short* q = im.quant[c];
   int ws[64];
@@ -546,7 +556,11 @@ __global__ void __launch_bounds__(256)
 jpeg_rgb_kernel(const sib_jpeg_image* __restrict__ images, const unsigned char* __restrict__ planes,
                 unsigned char* __restrict__ out) {
   const sib_jpeg_image& im = images[blockIdx.y];
-  const int npx = im.width * im.height;
+  // row-limited decode: only the decoded luma rows are converted (the last two of them interpolate against
+  // an undecoded chroma row and are inexact; the caller asks for two rows more than it reads)
+  int rows = im.height;
+  if (im.mcu_rows > 0 && im.mcu_rows * 8 * im.vmax < rows) rows = im.mcu_rows * 8 * im.vmax;
+  const int npx = im.width * rows;
   const int dw = (im.width + im.hmax - 1) / im.hmax, dh = (im.height + im.vmax - 1) / im.vmax;
   unsigned char* base = out + im.out_off;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q * 4 < npx; q += gridDim.x * blockDim.x) {

@@ -289,7 +289,19 @@ class RecordLoader:
 
     def _emit(self, samples):
         dev = self.device
-        if self.decode == "device":
+        first = (self._epoch * len(self.reader) + self._seen) * self.world + self.rank * len(samples)
+        boxes = None
+        if self.decode == "device" and self.train:
+            # the crop boxes only need the image sizes (known from the headers): computed on the host by the C
+            # twin of the device routine (bit-identical) BEFORE decoding, so that every stream is entropy-decoded
+            # only down to the row its crop ends in
+            def crop_fn(hw):
+                return [ops.rrc_box_host(int(h), int(w), self.min_area, 1.0, self.seed, first + i)
+                        for i, (h, w) in enumerate(hw.tolist())]
+            buf, offsets, dims, labels, boxes = self._jpeg.decode_batch(samples, workers=self.decode_workers,
+                                                                        device=dev, crop_fn=crop_fn)
+            boxes = boxes.to(dev, non_blocking=True)
+        elif self.decode == "device":
             buf, offsets, dims, labels = self._jpeg.decode_batch(samples, workers=self.decode_workers, device=dev)
         else:
             buf, offsets, dims, labels = self._records.decode_batch(samples, workers=self.decode_workers,
@@ -297,8 +309,8 @@ class RecordLoader:
         buf, offsets, dims = (t.to(dev, non_blocking=True) for t in (buf, offsets, dims))
         labels = labels.to(dev, non_blocking=True)
         if self.train:
-            first = (self._epoch * len(self.reader) + self._seen) * self.world + self.rank * len(samples)
-            boxes = ops.rrc_boxes_ragged(dims, self.min_area, 1.0, self.seed, first, True)
+            if boxes is None:
+                boxes = ops.rrc_boxes_ragged(dims, self.min_area, 1.0, self.seed, first, True)
             data = ops.augment_ragged(buf, offsets, dims, boxes, self.image_size, DATA_MEAN, DATA_STD,
                                       self.out_mode)
             if self.pixel_aug is not None and self.pixel_aug.active:

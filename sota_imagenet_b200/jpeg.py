@@ -45,7 +45,7 @@ class JpegInfo(ctypes.Structure):
 # sib_jpeg_image (include/sib200.h): one record per image of a batch
 IMAGE_DTYPE = np.dtype([("coef_off", "<i8", 3), ("plane_off", "<i8", 3), ("out_off", "<i8"),
                         ("width", "<i4"), ("height", "<i4"), ("ncomp", "<i4"), ("hmax", "<i4"), ("vmax", "<i4"),
-                        ("blocks_w", "<i4", 3), ("blocks_h", "<i4", 3), ("pad_", "<i4"),
+                        ("blocks_w", "<i4", 3), ("blocks_h", "<i4", 3), ("mcu_rows", "<i4"),
                         ("quant", "<u2", (3, 64))], align=True)
 assert IMAGE_DTYPE.itemsize == 488
 
@@ -66,8 +66,16 @@ def parse(data):
     return info
 
 
-def decode_coefficients(data, out=None, info=None):
-    """Host Huffman stage: bytes -> int16 coefficients (flat numpy array, or written into `out`)."""
+def mcu_rows_for(info, luma_rows):
+    """MCU rows a consumer that reads the luma rows [0, luma_rows) needs: two rows of margin because the fancy
+    chroma upsampling of a row interpolates against the next chroma row; 0 = the whole image."""
+    need = -(-(luma_rows + 2) // (8 * info.vmax))
+    return 0 if need >= info.mcus_y else need
+
+
+def decode_coefficients(data, out=None, info=None, mcu_rows=0):
+    """Host Huffman stage: bytes -> int16 coefficients (flat numpy array, or written into `out`); `mcu_rows` > 0
+    stops after that many rows of MCUs (the rest of `out` is left untouched)."""
     info = info or parse(data)
     if info.status != 0:
         raise _lib.SibError("jpeg: stream not decodable on the device path (%s)" % STATUS.get(info.status, info.status))
@@ -75,7 +83,8 @@ def decode_coefficients(data, out=None, info=None):
         out = np.empty(info.coef_count, dtype=np.int16)
     assert out.dtype == np.int16 and out.size >= info.coef_count and out.flags.c_contiguous
     data = _as_bytes(data)
-    _lib.check(_lib.load().sib_jpeg_decode_coefficients(data, len(data), ctypes.c_void_p(out.ctypes.data)))
+    _lib.check(_lib.load().sib_jpeg_decode_coefficients_rows(data, len(data), ctypes.c_void_p(out.ctypes.data),
+                                                             int(mcu_rows)))
     return out
 
 
@@ -146,10 +155,16 @@ class _PinnedRing:
 _RING = _PinnedRing()
 
 
-def decode_batch(samples, workers=8, device="cuda", host_decode=None):
+def decode_batch(samples, workers=8, device="cuda", host_decode=None, crop_fn=None):
     """samples: list of (encoded bytes, label) -> (packed uint8 device buffer, offsets, dims, labels), the
     tuple `records.decode_batch(..., canvas=None)` returns, with the buffer already resident on `device`.
-    `host_decode(bytes) -> uint8 [H, W, 3]` takes the streams outside the device subset."""
+    `host_decode(bytes) -> uint8 [H, W, 3]` takes the streams outside the device subset.
+
+    `crop_fn(dims int32 [B, 2]) -> boxes int32 [B, 5] {x0, y0, w, h, flip}` (host): decode only what the crops
+    read -- the image sizes come from the headers, so the boxes exist before any entropy decoding starts and
+    every stream is decoded only down to the MCU row its crop ends in (ROI decoding of
+    `fn.decoders.image_random_crop`, dali_dataloader.py:65-72); pixels below that row are left undefined.
+    Returns the boxes as a fifth element."""
     import torch
     from . import ops, records
     _lib.require_device()
@@ -168,13 +183,18 @@ def decode_batch(samples, workers=8, device="cuda", host_decode=None):
                 [host_decode(datas[i]) for i in on_host]
             host_images = dict(zip(on_host, dec))
         plan = plan_batch(infos, {i: im.shape[:2] for i, im in host_images.items()})
+        boxes = None
+        if crop_fn is not None:
+            boxes = np.ascontiguousarray(crop_fn(plan["dims"]), dtype=np.int32).reshape(len(datas), 5)
+            for i in on_device:
+                plan["table"]["mcu_rows"][i] = mcu_rows_for(infos[i], int(boxes[i, 1] + boxes[i, 3]))
         slot = _RING.take(plan["coef_total"])
         coef = slot[0][:max(plan["coef_total"], 1)]
         coef_np = coef.numpy()
 
         def huff(i):
             t = plan["table"][i]
-            decode_coefficients(datas[i], coef_np[int(t["coef_off"][0]):], infos[i])
+            decode_coefficients(datas[i], coef_np[int(t["coef_off"][0]):], infos[i], int(t["mcu_rows"]))
 
         if pool:
             list(pool.map(huff, on_device))
@@ -197,4 +217,5 @@ def decode_batch(samples, workers=8, device="cuda", host_decode=None):
         flat = torch.from_numpy(np.array(im, dtype=np.uint8).reshape(-1))      # (a writable copy)
         off = int(plan["offsets"][i])
         out[off:off + flat.numel()].copy_(flat, non_blocking=False)
-    return out, torch.from_numpy(plan["offsets"]), torch.from_numpy(plan["dims"]), labels
+    res = (out, torch.from_numpy(plan["offsets"]), torch.from_numpy(plan["dims"]), labels)
+    return res if crop_fn is None else res + (torch.from_numpy(boxes),)

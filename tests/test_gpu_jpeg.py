@@ -63,6 +63,25 @@ def test_mixed_batch_is_bit_identical_to_pil():
             assert np.array_equal(got, pil_rgb(d)), (i, workers)
 
 
+def test_row_limited_decode_on_device():
+    """`crop_fn`: every stream is decoded only down to the MCU row its crop ends in; the rows the crop reads are
+    bit-identical to PIL, the boxes come back unchanged."""
+    datas = [encode(synth(100, 75, 1), quality=85, subsampling=2), encode(synth(64, 64, 2), quality=90, subsampling=0),
+             encode(synth(120, 90, 3), quality=85, subsampling=1, restart_marker_blocks=5),
+             encode(synth(80, 60, 4).convert("L"), quality=70), encode(synth(40, 40, 5), quality=80, progressive=True),
+             encode(synth(375, 500, 6), quality=92, subsampling=2)]
+    ends = [1, 30, 97, 80, 17, 200]
+
+    def crop_fn(dims):
+        assert dims.tolist() == [[100, 75], [64, 64], [120, 90], [80, 60], [40, 40], [375, 500]]
+        return [[3, max(e - 5, 0), 20, min(e, 5), i & 1] for i, e in enumerate(ends)]       # y0 + h = e
+
+    buf, offsets, dims, labels, boxes = jpeg.decode_batch([(d, 0) for d in datas], workers=2, crop_fn=crop_fn)
+    assert boxes.tolist() == crop_fn(dims.numpy())
+    for i, (got, d) in enumerate(zip(unpack(buf, offsets, dims), datas)):
+        assert np.array_equal(got[:ends[i]], pil_rgb(d)[:ends[i]]), i
+
+
 def test_committed_fixture_on_device():
     g = np.load(GOLD)
     names = sorted({k.split("/")[0] for k in g.files})

@@ -121,3 +121,30 @@ def test_batch_plan_layout():
     assert plan["coef_total"] == infos[0].coef_count + infos[1].coef_count
     assert plan["max_pixels"] == 37 * 53 and plan["max_blocks"] == 48 + 12 + 12
     assert jpeg.IMAGE_DTYPE.itemsize == 488
+
+
+@pytest.mark.parametrize("sub", [0, 1, 2])
+def test_row_limited_decode(sub):
+    """ROI decoding: stopping after the MCU rows a crop needs yields the same coefficients for those rows, leaves
+    the rest of the buffer untouched, and the rows the consumer reads (two rows of margin for the chroma
+    interpolation) come out bit-identical to the full decode."""
+    data = encode(synth(100, 75, seed=sub), quality=85, subsampling=sub, restart_marker_blocks=(4 if sub == 2 else 0))
+    info = jpeg.parse(data)
+    full = jpeg.decode_coefficients(data, info=info)
+    ref = pil_rgb(data)
+    for luma_rows in (1, 13, 14, 15, 16, 47, 98, 99, 100):
+        mr = jpeg.mcu_rows_for(info, luma_rows)
+        assert 0 <= mr < info.mcus_y and (mr == 0 or mr * 8 * info.vmax >= luma_rows + 2)
+        part = np.full(info.coef_count, 12345, dtype=np.int16)
+        jpeg.decode_coefficients(data, part, info, mcu_rows=mr)
+        off = 0
+        for c in range(info.ncomp):
+            n = info.blocks_w[c] * info.blocks_h[c] * 64
+            rows = (mr if mr else info.mcus_y) * info.vs[c]
+            k = info.blocks_w[c] * rows * 64
+            assert np.array_equal(part[off:off + k], full[off:off + k])
+            assert (part[off + k:off + n] == 12345).all()
+            off += n
+        part[part == 12345] = 0
+        got = jpeg_ref.decode_rgb(info.as_dict(), part)
+        assert np.array_equal(got[:luma_rows], ref[:luma_rows]), (sub, luma_rows)
