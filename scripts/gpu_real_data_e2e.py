@@ -63,7 +63,8 @@ def main():
         cfg = SimpleNamespace(image_size=224, batch_size=256, num_classes=1000, min_area=0.08, seed=0,
                               root_data_dir=root, use_tfrecords=False)
         print("%d JPEG files (500x375, q90, 4:2:0), batch 256, %d decode threads, %d host cores" % (n, workers, os.cpu_count()))
-        for decode, prefetch in (("device", 2), ("device", 0), ("host", 2)):
+        run(cfg, root, 4, "device", 0, workers)          # page cache, allocator, pinned staging buffers
+        for decode, prefetch in (("device", 0), ("device", 2), ("host", 0)):
             rate, loss = run(cfg, root, steps, decode, prefetch, workers)
             print("decode=%-6s prefetch=%d : %7.0f images/s end to end (files -> decode -> augment -> ResNet-50 step), loss %.3f"
                   % (decode, prefetch, rate, loss))

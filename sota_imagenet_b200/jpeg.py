@@ -155,7 +155,7 @@ class _PinnedRing:
 _RING = _PinnedRing()
 
 
-def decode_batch(samples, workers=8, device="cuda", host_decode=None, crop_fn=None):
+def decode_batch(samples, workers=8, device="cuda", host_decode=None, crop_fn=None, pool=None):
     """samples: list of (encoded bytes, label) -> (packed uint8 device buffer, offsets, dims, labels), the
     tuple `records.decode_batch(..., canvas=None)` returns, with the buffer already resident on `device`.
     `host_decode(bytes) -> uint8 [H, W, 3]` takes the streams outside the device subset.
@@ -164,19 +164,30 @@ def decode_batch(samples, workers=8, device="cuda", host_decode=None, crop_fn=No
     read -- the image sizes come from the headers, so the boxes exist before any entropy decoding starts and
     every stream is decoded only down to the MCU row its crop ends in (ROI decoding of
     `fn.decoders.image_random_crop`, dali_dataloader.py:65-72); pixels below that row are left undefined.
-    Returns the boxes as a fifth element."""
+    Returns the boxes as a fifth element.  `pool`: a persistent ThreadPoolExecutor (else one is made per call)."""
     import torch
     from . import ops, records
     _lib.require_device()
     host_decode = host_decode or records.decode_image
-    datas = [s[0] for s in samples]
-    labels = torch.tensor([s[1] for s in samples], dtype=torch.int64)
-    datas = [_as_bytes(d) for d in datas]
-    infos = [parse(d) for d in datas]
+    own_pool = pool is None and workers > 1 and len(samples) > 1     # (a loader passes its persistent pool)
+    if own_pool:
+        pool = ThreadPoolExecutor(max_workers=workers)
+
+    def fetch(s):
+        data = _as_bytes(s[0])
+        return data, s[1], parse(data)
+
+    try:
+        got = list(pool.map(fetch, samples)) if pool else [fetch(s) for s in samples]
+    except BaseException:
+        if own_pool:
+            pool.shutdown()
+        raise
+    datas, infos = [g[0] for g in got], [g[2] for g in got]
+    labels = torch.tensor([g[1] for g in got], dtype=torch.int64)
     on_device = [i for i, inf in enumerate(infos) if inf.status == 0]
     on_host = [i for i, inf in enumerate(infos) if inf.status != 0]
     host_images = {}
-    pool = ThreadPoolExecutor(max_workers=workers) if workers > 1 and len(datas) > 1 else None
     try:
         if on_host:
             dec = list(pool.map(host_decode, [datas[i] for i in on_host])) if pool else \
@@ -202,7 +213,7 @@ def decode_batch(samples, workers=8, device="cuda", host_decode=None, crop_fn=No
             for i in on_device:
                 huff(i)
     finally:
-        if pool:
+        if own_pool:
             pool.shutdown()
     out = torch.empty(max(plan["out_total"], 1), dtype=torch.uint8, device=device)
     if on_device:

@@ -19,6 +19,7 @@ to the ragged kernels (`sib_rrc_boxes_ragged`, `sib_augment_ragged`, `sib_val_tr
 import io
 import os
 import struct
+import threading
 
 import numpy as np
 
@@ -61,10 +62,10 @@ def crc32c(data: bytes) -> int:
             import ctypes
             from . import _lib
             fn = _lib.load().sib_crc32c_host
-            out = ctypes.c_uint()
 
             def native(buf):
                 b = bytes(buf)
+                out = ctypes.c_uint()            # per call: readers verify records from several threads
                 _lib.check(fn(b, len(b), ctypes.byref(out)))
                 return out.value
             native(b"")
@@ -244,8 +245,11 @@ def read_index(idx_path):
 
 def read_record(f, offset, size, verify=False):
     """One framed record at (offset, size) of an open binary file -> payload bytes."""
-    f.seek(offset)
-    blob = f.read(size)
+    if isinstance(f, int):
+        blob = os.pread(f, size, offset)         # a file descriptor: positional read, safe from any thread
+    else:
+        f.seek(offset)
+        blob = f.read(size)
     if len(blob) != size:
         raise ValueError("short read: record at %d wants %d bytes" % (offset, size))
     (ln,) = struct.unpack("<Q", blob[:8])
@@ -307,7 +311,8 @@ class TFRecordReader(_ShardedReader):
             per_file = [read_index(str(p)) for p in indexes]
         self.table = [(fi, off, size) for fi, idx in enumerate(per_file) for off, size in idx]
         self.verify = verify
-        self._files = {}
+        self._files = {}                 # file index -> descriptor (os.pread: no shared file position)
+        self._open_lock = threading.Lock()
         super().__init__(len(self.table), **kw)
 
     @classmethod
@@ -322,7 +327,10 @@ class TFRecordReader(_ShardedReader):
         fi, off, size = self.table[i]
         f = self._files.get(fi)
         if f is None:
-            f = self._files[fi] = open(self.paths[fi], "rb")
+            with self._open_lock:
+                f = self._files.get(fi)
+                if f is None:
+                    f = self._files[fi] = os.open(self.paths[fi], os.O_RDONLY)
         ex = parse_example(read_record(f, off, size, self.verify))
         if "image/encoded" not in ex:
             raise ValueError("record %d of %s has no image/encoded feature" % (i, self.paths[fi]))
@@ -331,7 +339,7 @@ class TFRecordReader(_ShardedReader):
 
     def close(self):
         for f in self._files.values():
-            f.close()
+            os.close(f)
         self._files = {}
 
 
@@ -408,13 +416,17 @@ def decode_batch(samples, canvas=None, workers=4, pinned=False):
     labels); canvas=(H, W) -> uniform uint8 [B, H, W, 3] tensor + labels for `GpuAugment`."""
     import torch
     from concurrent.futures import ThreadPoolExecutor
-    datas = [s[0] for s in samples]
-    labels = torch.tensor([s[1] for s in samples], dtype=torch.int64)
-    if workers > 1 and len(datas) > 1:
+
+    def one(s):
+        return decode_image(s[0]), s[1]
+
+    if workers > 1 and len(samples) > 1:
         with ThreadPoolExecutor(max_workers=workers) as ex:      # PIL releases the GIL while decoding
-            images = list(ex.map(decode_image, datas))
+            done = list(ex.map(one, samples))
     else:
-        images = [decode_image(d) for d in datas]
+        done = [one(s) for s in samples]
+    images = [d[0] for d in done]
+    labels = torch.tensor([d[1] for d in done], dtype=torch.int64)
     if canvas is None:
         return pack_batch(images, pinned) + (labels,)
     h, w = canvas

@@ -108,6 +108,14 @@ def test_reader_sharding_and_shuffle(tmp_path):
     b = records.TFRecordReader(paths, None, shard_id=1, num_shards=2, random_shuffle=True, seed=7)   # index rebuilt by scanning
     assert sorted(e0) == list(range(9, 18)) == sorted(e1) and e0 != e1 and e0 != sorted(e0)
     assert [l for _, l in b] == e0
+    # records may be read from worker threads (positional reads: no shared file position; per-call CRC output)
+    from concurrent.futures import ThreadPoolExecutor
+    rd = records.TFRecordReader(paths, idxs, verify=True)
+    eager = list(rd)
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        for _ in range(5):
+            assert list(ex.map(rd.sample, range(18))) == eager
+    rd.close()
 
 
 def test_file_reader_and_decode_pack(tmp_path):
