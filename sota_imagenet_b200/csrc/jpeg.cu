@@ -550,8 +550,58 @@ __device__ __forceinline__ uint32_t jpeg_pixel(const sib_jpeg_image& im, const u
   return (uint32_t)clamp255(r) | ((uint32_t)clamp255(g) << 8) | ((uint32_t)clamp255(b) << 16);
 }
 
+__device__ __forceinline__ uint32_t ycc_pixel(int yy, int cb, int cr) {
+  const int r = yy + ((91881 * cr + 32768) >> 16);
+  const int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+  const int b = yy + ((116130 * cb + 32768) >> 16);
+  return (uint32_t)clamp255(r) | ((uint32_t)clamp255(g) << 8) | ((uint32_t)clamp255(b) << 16);
+}
+
+// Four consecutive pixels (x0 .. x0+3) of ONE row: the chroma samples they interpolate between are
+// cxa .. cxa+3 with cxa = (x0 >> 1) - 1 whatever the parity of x0; the triangle filter's edge cases are
+// exactly "the missing neighbour replicates the sample" ((3v + v + 1) >> 2 = v, (4s + 8) >> 4 = the special
+// first-column formula, ...), so indices are clamped to the real extent and no case split is needed.
+__device__ __forceinline__ void chroma4(const unsigned char* __restrict__ pl, int stride, int dw, int dh, int hmax,
+                                        int vmax, int x0, int y, int* out) {
+  if (hmax == 1) {
+    const unsigned char* row = pl + (long)y * stride + x0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = row[j];
+    return;
+  }
+  const int cxa = (x0 >> 1) - 1;
+  int cs[4];
+  if (vmax == 1) {
+    const unsigned char* row = pl + (long)y * stride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cs[j] = row[min(max(cxa + j, 0), dw - 1)];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + j, k = (x >> 1) - cxa;            // k in 1 .. 3, k + 1 <= 3 for odd x, k - 1 >= 0 for even x
+      out[j] = (x & 1) ? (3 * cs[k] + cs[k + 1] + 2) >> 2 : (3 * cs[k] + cs[k - 1] + 1) >> 2;
+    }
+    return;
+  }
+  const int cy = y >> 1;
+  const int ny = min(max((y & 1) ? cy + 1 : cy - 1, 0), dh - 1);
+  const unsigned char* r0 = pl + (long)cy * stride;
+  const unsigned char* r1 = pl + (long)ny * stride;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = min(max(cxa + j, 0), dw - 1);
+    cs[j] = 3 * r0[c] + r1[c];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int x = x0 + j, k = (x >> 1) - cxa;
+    out[j] = (x & 1) ? (3 * cs[k] + cs[k + 1] + 7) >> 4 : (3 * cs[k] + cs[k - 1] + 8) >> 4;
+  }
+}
+
 // one thread per FOUR consecutive pixels of the packed [H][W][3] image: 12 output bytes = three aligned
-// 32-bit stores (every image starts on a 16-byte boundary); the last 1-3 pixels are written bytewise
+// 32-bit stores (every image starts on a 16-byte boundary).  When the four pixels lie in one row (all but
+// one group per row) the chroma interpolation shares its column sums; groups that straddle a row end and
+// the last 1-3 pixels of the image take the per-pixel route.
 __global__ void __launch_bounds__(256)
 jpeg_rgb_kernel(const sib_jpeg_image* __restrict__ images, const unsigned char* __restrict__ planes,
                 unsigned char* __restrict__ out) {
@@ -560,18 +610,33 @@ jpeg_rgb_kernel(const sib_jpeg_image* __restrict__ images, const unsigned char* 
   // an undecoded chroma row and are inexact; the caller asks for two rows more than it reads)
   int rows = im.height;
   if (im.mcu_rows > 0 && im.mcu_rows * 8 * im.vmax < rows) rows = im.mcu_rows * 8 * im.vmax;
-  const int npx = im.width * rows;
-  const int dw = (im.width + im.hmax - 1) / im.hmax, dh = (im.height + im.vmax - 1) / im.vmax;
+  const int W = im.width, ncomp = im.ncomp, hmax = im.hmax, vmax = im.vmax;
+  const int npx = W * rows;
+  const int dw = (W + hmax - 1) / hmax, dh = (im.height + vmax - 1) / vmax;
+  const int ystride = im.blocks_w[0] * 8, cstride = im.blocks_w[1] * 8;
+  const unsigned char* py = planes + im.plane_off[0];
+  const unsigned char* pcb = planes + im.plane_off[1];
+  const unsigned char* pcr = planes + im.plane_off[2];
   unsigned char* base = out + im.out_off;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q * 4 < npx; q += gridDim.x * blockDim.x) {
     const int i0 = q * 4;
-    if (i0 + 4 <= npx) {
-      const uint32_t p0 = jpeg_pixel(im, planes, i0, dw, dh), p1 = jpeg_pixel(im, planes, i0 + 1, dw, dh);
-      const uint32_t p2 = jpeg_pixel(im, planes, i0 + 2, dw, dh), p3 = jpeg_pixel(im, planes, i0 + 3, dw, dh);
-      uint32_t* o = reinterpret_cast<uint32_t*>(base + (long)i0 * 3);
-      o[0] = p0 | (p1 << 24);
-      o[1] = (p1 >> 8) | (p2 << 16);
-      o[2] = (p2 >> 16) | (p3 << 8);
+    const int y = i0 / W, x0 = i0 - y * W;
+    uint32_t p[4];
+    if (x0 + 4 <= W) {
+      const unsigned char* yrow = py + (long)y * ystride + x0;
+      if (ncomp == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = (uint32_t)yrow[j] * 0x010101u;
+      } else {
+        int cb[4], cr[4];
+        chroma4(pcb, cstride, dw, dh, hmax, vmax, x0, y, cb);
+        chroma4(pcr, cstride, dw, dh, hmax, vmax, x0, y, cr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = ycc_pixel(yrow[j], cb[j] - 128, cr[j] - 128);
+      }
+    } else if (i0 + 4 <= npx) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) p[j] = jpeg_pixel(im, planes, i0 + j, dw, dh);
     } else {
       for (int i = i0; i < npx; ++i) {
         const uint32_t px = jpeg_pixel(im, planes, i, dw, dh);
@@ -579,7 +644,12 @@ jpeg_rgb_kernel(const sib_jpeg_image* __restrict__ images, const unsigned char* 
         base[(long)i * 3 + 1] = (unsigned char)(px >> 8);
         base[(long)i * 3 + 2] = (unsigned char)(px >> 16);
       }
+      continue;
     }
+    uint32_t* o = reinterpret_cast<uint32_t*>(base + (long)i0 * 3);
+    o[0] = p[0] | (p[1] << 24);
+    o[1] = (p[1] >> 8) | (p[2] << 16);
+    o[2] = (p[2] >> 16) | (p[3] << 8);
   }
 }
 
