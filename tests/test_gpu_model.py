@@ -158,8 +158,12 @@ def test_every_parameter_gradient_in_a_damped_regime(slope):
             slope, label, len(grp), min(r[1] for r in grp), min(r[3] for r in grp),
             max(abs(r[2] - 1) for r in grp), max(abs(r[4] - 1) for r in grp)))
     #        (cos, norm dev) vs faithful, (cos, norm dev) vs fp32
-    gates = {True: {0.8: (0.999, 1e-2, 0.995, 1e-2), 0.0: (0.97, 1e-2, 0.94, 2e-2)},
-             False: {0.8: (0.97, 5e-2, 0.96, 5e-2), 0.0: (0.95, 1.5e-1, 0.90, 1.5e-1)}}
+    # The gates sit ~2x outside the spread of 8 consecutive runs on one B200 (the fp32 atomics that sum the BN
+    # statistics arrive in a different order every run): leaky vectors cos 0.9826..0.9886 / 0.978..0.986, norm
+    # 1.3e-2..3.2e-2 / 1.9e-2..3.6e-2; ReLU vectors cos 0.977..0.9795 / 0.950..0.958, norm 3.1e-2..5.2e-2 /
+    # 7.8e-2..1.21e-1 (the former 1.5e-1 tripped once in three full-suite runs); weights move by < 1e-4.
+    gates = {True: {0.8: (0.999, 1e-2, 0.995, 1e-2), 0.0: (0.96, 1e-2, 0.93, 4e-2)},
+             False: {0.8: (0.97, 8e-2, 0.96, 8e-2), 0.0: (0.95, 1.5e-1, 0.90, 2.5e-1)}}
     for name, cf, nf, cr, nr in rows:
         gc, gn, rc, rn = gates[rp[name].dim() > 1][slope]
         assert cf >= gc and abs(nf - 1) < gn, (name, cf, nf)
