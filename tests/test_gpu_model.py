@@ -101,9 +101,9 @@ def test_every_parameter_gradient_in_a_damped_regime(slope):
         the vector cosines move by ~1e-2 from run to run with the order of the fp32 atomics (the same
         quantity spans 0.9797 .. 0.9897 in the data-parallel equivalence logs), hence one point of margin.
       * slope = 0 : plain ReLU (the RELU code path), same damping; bf16 storage still flips
-        ~0.15 % of the masks per layer, so the gates are looser (measured 0.983 / 3e-3 for the
-        weights, 0.974 / 4e-2 .. 1e-1 for the vectors against the faithful oracle) but a missing
-        contribution, a SUM-for-AVG or a swapped tensor fails them by a wide margin."""
+        ~0.15 % of the masks per layer, so the gates are looser (measured 0.983 / 3e-3, occasionally
+        1.2e-2, for the weights, 0.977 / 3e-2 .. 5e-2 for the vectors against the faithful oracle) but a
+        missing contribution, a SUM-for-AVG or a swapped tensor fails them by a wide margin."""
     import copy
     import torch.nn.functional as F
     from sota_imagenet_b200 import losses, models, modules
@@ -162,7 +162,8 @@ def test_every_parameter_gradient_in_a_damped_regime(slope):
     # statistics arrive in a different order every run): leaky vectors cos 0.9826..0.9886 / 0.978..0.986, norm
     # 1.3e-2..3.2e-2 / 1.9e-2..3.6e-2; ReLU vectors cos 0.977..0.9795 / 0.950..0.958, norm 3.1e-2..5.2e-2 /
     # 7.8e-2..1.21e-1 (the former 1.5e-1 tripped once in three full-suite runs); weights move by < 1e-4.
-    gates = {True: {0.8: (0.999, 1e-2, 0.995, 1e-2), 0.0: (0.96, 1e-2, 0.93, 4e-2)},
+    # ReLU weights: norm deviation typically 3e-3, but one run in ~10 reaches 1.2e-2 on a layer1 tensor.
+    gates = {True: {0.8: (0.999, 1e-2, 0.995, 1e-2), 0.0: (0.96, 3e-2, 0.93, 6e-2)},
              False: {0.8: (0.97, 8e-2, 0.96, 8e-2), 0.0: (0.95, 1.5e-1, 0.90, 2.5e-1)}}
     for name, cf, nf, cr, nr in rows:
         gc, gn, rc, rn = gates[rp[name].dim() > 1][slope]
