@@ -604,8 +604,12 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   }
 }
 
-// One block per input row (n, h): 32-bit index math only (the 64-bit divisions of a flat
-// grid-stride loop made this kernel instruction-bound: 340 us against an 87 us HBM time).
+// One block per PAIR of input rows (n, 2a / 2a+1), one thread per 2x2 input quad and 8-channel vector.
+// The quad (2a + dy, 2b + dx) is fed by exactly the four windows (a | a+1, b | b+1): window (a, b) through
+// its taps r, s in {1, 2}, (a, b+1) through s = 0, (a+1, b) through r = 0, (a+1, b+1) through (0, 0) -- nine
+// (window, tap) pairs per channel as before, but four (index, gradient) loads per quad instead of nine and one
+// set of index arithmetic for four outputs (32-bit only: the 64-bit divisions of a flat grid-stride loop once
+// made this kernel instruction-bound, 340 us against an 87 us HBM time; per-pixel gathers left it at 255 us).
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int OH, int OW,
@@ -613,55 +617,69 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
   griddep_launch();
   griddep_wait();
   const int cvec = 1 << cshift;
-  for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
-    const int n = row / H;
-    const int h = row - n * H;
-    // windows (p,q) covering (h,w): p*2-1+r = h  =>  r = h - 2p + 1 in [0,3).  h even: p = h/2
-    // (r = 1); h odd: p = (h-1)/2 (r = 2) and p = (h+1)/2 (r = 0).  All (up to four) candidates
-    // are fetched before any is used so the loads overlap.
-    const int pc[2] = {h >> 1, (h + 1) >> 1};
-    const bool pok[2] = {pc[0] < OH, pc[1] != pc[0] && pc[1] < OH};
-    const size_t prow[2] = {((size_t)n * OH + pc[0]) * OW, ((size_t)n * OH + pc[1]) * OW};
-    __nv_bfloat16* drow = dx + (size_t)row * W * C;
-    for (int item = threadIdx.x; item < (W << cshift); item += blockDim.x) {
-      const int w = item >> cshift;
+  const int HP = (H + 1) >> 1, WP = (W + 1) >> 1;
+  for (int row = blockIdx.x; row < N * HP; row += gridDim.x) {
+    const int n = row / HP;
+    const int a = row - n * HP;
+    const bool pok[2] = {a < OH, a + 1 < OH};
+    const size_t prow[2] = {((size_t)n * OH + a) * OW, ((size_t)n * OH + a + 1) * OW};
+    const bool hok1 = 2 * a + 1 < H;
+    __nv_bfloat16* drow0 = dx + ((size_t)n * H + 2 * a) * W * C;
+    __nv_bfloat16* drow1 = drow0 + (size_t)W * C;
+    for (int item = threadIdx.x; item < (WP << cshift); item += blockDim.x) {
+      const int b = item >> cshift;
       const int v = item & (cvec - 1);
-      const int qc[2] = {w >> 1, (w + 1) >> 1};
-      const bool qok[2] = {qc[0] < OW, qc[1] != qc[0] && qc[1] < OW};
+      const bool qok[2] = {b < OW, b + 1 < OW};
       uint2 pk[4];
       uint4 gv[4];
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
+      for (int pi = 0; pi < 2; ++pi) {
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          if (pok[a] && qok[b]) {
-            const size_t o = (((prow[a] + qc[b]) << cshift) + v) * 8;
-            pk[a * 2 + b] = __ldg(reinterpret_cast<const uint2*>(idx + o));
-            gv[a * 2 + b] = __ldg(reinterpret_cast<const uint4*>(dy + o));
+        for (int qi = 0; qi < 2; ++qi) {
+          pk[pi * 2 + qi] = make_uint2(0xffffffffu, 0xffffffffu);      // no tap matches 0xff
+          gv[pi * 2 + qi] = make_uint4(0, 0, 0, 0);
+          if (pok[pi] && qok[qi]) {
+            const size_t o = (((prow[pi] + b + qi) << cshift) + v) * 8;
+            pk[pi * 2 + qi] = __ldg(reinterpret_cast<const uint2*>(idx + o));
+            gv[pi * 2 + qi] = __ldg(reinterpret_cast<const uint4*>(dy + o));
           }
         }
       }
-      float acc[8];
+      float acc[4][8];                      // [dy * 2 + dx][channel]
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
+        for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          if (pok[a] && qok[b]) {
-            const int k = a * 2 + b;
-            const uint32_t tap = (h - 2 * pc[a] + 1) * 3 + (w - 2 * qc[b] + 1);
-            float g[8];
-            unpack8(gv[k], g);
+      for (int pi = 0; pi < 2; ++pi) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint32_t bsel = ((j < 4 ? (pk[k].x >> (8 * j)) : (pk[k].y >> (8 * (j - 4)))) & 0xffu);
-              if (bsel == tap) acc[j] += g[j];
+        for (int qi = 0; qi < 2; ++qi) {
+          const int k = pi * 2 + qi;
+          float g[8];
+          unpack8(gv[k], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t t = ((j < 4 ? (pk[k].x >> (8 * j)) : (pk[k].y >> (8 * (j - 4)))) & 0xffu);
+            // pixel (2a + d, 2b + e) <- window (a + pi, b + qi) tap (r, s) = (d + 1 - 2 pi, e + 1 - 2 qi)
+#pragma unroll
+            for (int d = pi; d < 2; ++d) {          // pi = 1 only reaches d = 1 (r = 0)
+#pragma unroll
+              for (int e = qi; e < 2; ++e) {
+                const uint32_t tap = (uint32_t)((d + 1 - 2 * pi) * 3 + (e + 1 - 2 * qi));
+                acc[d * 2 + e][j] += t == tap ? g[j] : 0.f;
+              }
             }
           }
         }
       }
-      stg_stream(drow + (size_t)item * 8, pack8(acc));
+      const bool wok1 = 2 * b + 1 < W;
+      const size_t o0 = ((size_t)(2 * b) << cshift) * 8 + (size_t)v * 8;
+      stg_stream(drow0 + o0, pack8(acc[0]));
+      if (wok1) stg_stream(drow0 + o0 + C, pack8(acc[1]));
+      if (hok1) {
+        stg_stream(drow1 + o0, pack8(acc[2]));
+        if (wok1) stg_stream(drow1 + o0 + C, pack8(acc[3]));
+      }
     }
   }
 }
@@ -1110,7 +1128,7 @@ extern "C" int sib_maxpool3x3s2_bwd(const void* dy, const void* idx, void* dx, i
   const int cshift = C % 8 == 0 ? log2_exact(C / 8) : -1;
   SIB_CHECK(cshift >= 0, "maxpool_bwd: C/8 must be a power of two (got C=%d)", C);
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-  int grid = N * H;
+  int grid = N * ((H + 1) / 2);
   if (grid > sm_count() * 64) grid = sm_count() * 64;
   SIB_CUDA(launch_pdl(maxpool_bwd_kernel, dim3(grid), dim3(256), 0, ST(stream),
                       static_cast<const __nv_bfloat16*>(dy), static_cast<const uint8_t*>(idx),

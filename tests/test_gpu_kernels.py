@@ -337,6 +337,18 @@ def test_pooling():
     assert torch.equal(y.float().cpu(), y_ref.detach())
     dx = ops.maxpool3x3s2_bwd(ops.to_nhwc_bf16(dy.cuda()), idx, tuple(x.shape))
     assert rel(dx, dx_ref) < 5e-3
+    # the backward works on 2x2 input quads: odd extents (a last row / column without a partner), one channel
+    # vector, coarse values (exact ties: the first maximum in scan order owns the gradient, as in torch)
+    for shape, coarse in (((2, 64, 31, 27), False), ((3, 8, 9, 7), True), ((2, 16, 1, 5), False), ((1, 64, 112, 112), False)):
+        xs = torch.randn(*shape)
+        xs = ((xs * 2).round() if coarse else xs).bfloat16().float().requires_grad_(True)
+        ys_ref = F.max_pool2d(xs, 3, 2, 1)
+        dys = torch.randn_like(ys_ref).bfloat16().float()
+        (dxs_ref,) = torch.autograd.grad(ys_ref, xs, dys)
+        ys, ids = ops.maxpool3x3s2_fwd(ops.to_nhwc_bf16(xs.detach().cuda()))
+        assert torch.equal(ys.float().cpu(), ys_ref.detach()), shape
+        dxs = ops.maxpool3x3s2_bwd(ops.to_nhwc_bf16(dys.cuda()), ids, tuple(xs.shape))
+        assert bool(((dxs.float().cpu() - dxs_ref).abs() <= 2e-2 + 8e-3 * dxs_ref.abs()).all()), shape
     f = torch.randn(4, 2048, 7, 7).bfloat16().float()
     fb = ops.to_nhwc_bf16(f.cuda())
     assert rel(ops.gap_fwd(fb), f.mean(dim=(2, 3), keepdim=True)) < 5e-3
