@@ -52,38 +52,55 @@ blurpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   }
 }
 
+// Backward of the blur-pool on 2x2 input quads: the quad (2a + d, 2b + e) is fed by the four outputs
+// (a | a+1, b | b+1) -- an even row / column only by its own output through the centre tap (1/2), an odd one by
+// both neighbours through the outer taps (1/4 each) -- so one thread loads four gradients and writes four
+// pixels (the per-pixel gather loaded 1 + 2 + 2 + 4 of them and ran its index arithmetic four times).
 template <typename I>   // I = int when the vector count fits 31 bits (64-bit div/mod is ~10x the cost)
 __global__ void __launch_bounds__(256)
 blurpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
                     int H, int W, int C, int OH, int OW) {
   const int cvec = C >> 3;
-  const I total = (I)N * H * W * cvec;
+  const int HP = (H + 1) >> 1, WP = (W + 1) >> 1;
+  const I total = (I)N * HP * WP * cvec;
   for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
     I t = i / cvec;
-    const int w = (int)(t % W); t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
-    float acc[8] = {};
-    for (int p = (h >> 1); p <= ((h + 1) >> 1); ++p) {
-      if (p >= OH) continue;
-      const int r = h - 2 * p + 1;
-      if (r < 0 || r > 2) continue;
-      for (int q = (w >> 1); q <= ((w + 1) >> 1); ++q) {
-        if (q >= OW) continue;
-        const int s = w - 2 * q + 1;
-        if (s < 0 || s > 2) continue;
-        float g[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((((long)n * OH + p) * OW + q) * cvec + v) * 8)), g);
-        const float wt = blur_w(r) * blur_w(s);
+    const int b = (int)(t % WP); t /= WP;
+    const int a = (int)(t % HP);
+    const int n = (int)(t / HP);
+    float g[2][2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt, g[j], acc[j]);
+    for (int pi = 0; pi < 2; ++pi)
+#pragma unroll
+      for (int qi = 0; qi < 2; ++qi) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[pi][qi][j] = 0.f;
+        if (a + pi < OH && b + qi < OW)
+          unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((((long)n * OH + a + pi) * OW + b + qi) * cvec + v) * 8)),
+                  g[pi][qi]);
       }
+    float o[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // weights as in the forward: blur_w(r) * blur_w(s) with r = 1 for the even row (d = 0), r = 2 / 0 for the
+      // odd row's two outputs; products of 1/2 and 1/4 are exact, the sums are accumulated in the same order
+      // (p ascending, then q ascending) as the per-pixel gather did
+      o[0][j] = 0.25f * g[0][0][j];
+      o[1][j] = fmaf(0.125f, g[0][1][j], 0.125f * g[0][0][j]);
+      o[2][j] = fmaf(0.125f, g[1][0][j], 0.125f * g[0][0][j]);
+      o[3][j] = fmaf(0.0625f, g[1][1][j], fmaf(0.0625f, g[1][0][j], fmaf(0.0625f, g[0][1][j], 0.0625f * g[0][0][j])));
     }
-    stg_stream(dx + (long)i * 8, pack8(acc));
+    const int h = 2 * a, w = 2 * b;
+    __nv_bfloat16* d0 = dx + ((((long)n * H + h) * W + w) * cvec + v) * 8;
+    stg_stream(d0, pack8(o[0]));
+    if (w + 1 < W) stg_stream(d0 + C, pack8(o[1]));
+    if (h + 1 < H) {
+      stg_stream(d0 + (long)W * C, pack8(o[2]));
+      if (w + 1 < W) stg_stream(d0 + (long)W * C + C, pack8(o[3]));
+    }
   }
 }
-
 template <typename I>   // I = int when the vector count fits 31 bits (64-bit div/mod is ~10x the cost)
 __global__ void __launch_bounds__(256)
 avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
@@ -112,25 +129,29 @@ avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   }
 }
 
+// one thread per OUTPUT gradient: one load, four stores (H and W are even)
 template <typename I>   // I = int when the vector count fits 31 bits (64-bit div/mod is ~10x the cost)
 __global__ void __launch_bounds__(256)
 avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N,
                     int H, int W, int C) {
   const int cvec = C >> 3, OH = H >> 1, OW = W >> 1;
-  const I total = (I)N * H * W * cvec;
+  const I total = (I)N * OH * OW * cvec;
   for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
     I t = i / cvec;
-    const int w = (int)(t % W); t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
-    float g[8] = {};
-    if ((h >> 1) < OH && (w >> 1) < OW) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((((long)n * OH + (h >> 1)) * OW + (w >> 1)) * cvec + v) * 8)), g);
+    const int q = (int)(t % OW); t /= OW;
+    const int p = (int)(t % OH);
+    const int n = (int)(t / OH);
+    float g[8];
+    unpack8(ldg_stream(dy + (long)i * 8), g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
-    }
-    stg_stream(dx + (long)i * 8, pack8(g));
+    for (int j = 0; j < 8; ++j) g[j] *= 0.25f;
+    const uint4 o = pack8(g);
+    __nv_bfloat16* d0 = dx + ((((long)n * H + 2 * p) * W + 2 * q) * cvec + v) * 8;
+    stg_stream(d0, o);
+    stg_stream(d0 + C, o);
+    stg_stream(d0 + (long)W * C, o);
+    stg_stream(d0 + (long)W * C + C, o);
   }
 }
 
@@ -601,7 +622,7 @@ extern "C" int sib_blurpool_fwd(const void* x, void* y, int N, int H, int W, int
 extern "C" int sib_blurpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
   SIB_CHECK(C % 8 == 0, "blurpool: C %% 8 != 0");
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
-  const long total = (long)N * H * W * (C / 8);
+  const long total = (long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   if (total < (1l << 31) - (1l << 24)) blurpool_bwd_kernel<int><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C, OH, OW);
   else blurpool_bwd_kernel<long><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C, OH, OW);
   SIB_LAUNCH_CHECK();
@@ -617,7 +638,7 @@ extern "C" int sib_avgpool2_fwd(const void* x, void* y, int N, int H, int W, int
 }
 extern "C" int sib_avgpool2_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
   SIB_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool2: needs C %% 8 == 0 and even H, W");
-  const long total = (long)N * H * W * (C / 8);
+  const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
   if (total < (1l << 31) - (1l << 24)) avgpool2_bwd_kernel<int><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C);
   else avgpool2_bwd_kernel<long><<<ew_grid(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C);
   SIB_LAUNCH_CHECK();

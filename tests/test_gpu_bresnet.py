@@ -39,6 +39,14 @@ def test_extra_operators_match_torch():
     dy = torch.randn_like(y_ref).bfloat16()
     (dx_ref,) = torch.autograd.grad(y_ref, xr, dy.float())
     assert (ops.blurpool_bwd(ops.to_nhwc_bf16(dy), tuple(x.shape)).float() - dx_ref).abs().max() < 2e-2
+    for shape in ((2, 16, 9, 7), (1, 64, 56, 56), (3, 8, 1, 6)):        # the backward works on 2x2 quads: odd extents
+        xs = torch.randn(*shape, device="cuda").bfloat16()
+        xsr = xs.float().requires_grad_(True)
+        ys_ref = blur(xsr)
+        assert (ops.blurpool_fwd(ops.to_nhwc_bf16(xs)).float() - ys_ref).abs().max() < 2e-2, shape
+        dys = torch.randn_like(ys_ref).bfloat16()
+        (dxs_ref,) = torch.autograd.grad(ys_ref, xsr, dys.float())
+        assert (ops.blurpool_bwd(ops.to_nhwc_bf16(dys), tuple(xs.shape)).float() - dxs_ref).abs().max() < 2e-2, shape
     a_ref = F.avg_pool2d(xr, 2, 2)
     assert (ops.avgpool2_fwd(xb).float() - a_ref).abs().max() < 2e-2
     da = torch.randn_like(a_ref).bfloat16()
