@@ -903,7 +903,6 @@ struct HaloParams {
   int num_h_tiles;    // ceil(H / tile_h)
   int num_n_tiles;
   int cin_blocks;
-  int a_bytes;        // bytes of one region load: pitch * (tile_h + 2) * 128
   int b_stationary;   // all weight k-blocks fit the ring: load them once
   float* stats;       // [2][Cout] (fprop: sum, sumsq; fused BN backward: sum g, sum g*xhat) or null
   int fuse;           // 1: fused BN-backward reduction (see IgemmParams)
@@ -1822,7 +1821,6 @@ static int run_igemm(const void* in, const void* w, void* out, const void* resid
       h.num_h_tiles = (IH + h.tile_h - 1) / h.tile_h;
       h.num_n_tiles = 1;
       h.cin_blocks = Cin / 64;
-      h.a_bytes = h.pitch * (h.tile_h + 2) * 128;    // (informational)
       h.stats = stats;
       if (fuse != nullptr) {
         SIB_CHECK(stats == nullptr && fuse->aux1 && fuse->mean_invstd && fuse->sums,

@@ -431,7 +431,7 @@ __device__ __forceinline__ int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 2
 
 // one 1-D pass over (d0 .. d7); results descaled by `shift` with rounding
 __device__ __forceinline__ void idct_1d(int d0, int d1, int d2, int d3, int d4, int d5, int d6, int d7,
-                                        int shift, int* o, bool first_pass) {
+                                        int shift, int* o) {
   // even part
   int z2 = d2, z3 = d6;
   int z1 = (z2 + z3) * FIX_0_541196100;
@@ -451,7 +451,6 @@ __device__ __forceinline__ void idct_1d(int d0, int d1, int d2, int d3, int d4, 
   z3 += z5; z4 += z5;
   tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
   const int rnd = 1 << (shift - 1);
-  (void)first_pass;
   o[0] = (tmp10 + tmp3 + rnd) >> shift;
   o[7] = (tmp10 - tmp3 + rnd) >> shift;
   o[1] = (tmp11 + tmp2 + rnd) >> shift;
@@ -490,7 +489,7 @@ jpeg_idct_kernel(const short* __restrict__ coef, const sib_jpeg_image* __restric
     int o[8];
     idct_1d(cf[col] * q[col], cf[8 + col] * q[8 + col], cf[16 + col] * q[16 + col], cf[24 + col] * q[24 + col],
             cf[32 + col] * q[32 + col], cf[40 + col] * q[40 + col], cf[48 + col] * q[48 + col],
-            cf[56 + col] * q[56 + col], 13 - 2, o, true);
+            cf[56 + col] * q[56 + col], 13 - 2, o);
 #pragma unroll
     for (int r = 0; r < 8; ++r) ws[r * 8 + col] = o[r];
   }
@@ -501,7 +500,7 @@ jpeg_idct_kernel(const short* __restrict__ coef, const sib_jpeg_image* __restric
   for (int r = 0; r < 8; ++r) {
     int o[8];
     idct_1d(ws[r * 8], ws[r * 8 + 1], ws[r * 8 + 2], ws[r * 8 + 3], ws[r * 8 + 4], ws[r * 8 + 5], ws[r * 8 + 6],
-            ws[r * 8 + 7], 13 + 2 + 3, o, false);
+            ws[r * 8 + 7], 13 + 2 + 3, o);
     uint2 pk;
     pk.x = clamp255(o[0] + 128) | (clamp255(o[1] + 128) << 8) | (clamp255(o[2] + 128) << 16) | (clamp255(o[3] + 128) << 24);
     pk.y = clamp255(o[4] + 128) | (clamp255(o[5] + 128) << 8) | (clamp255(o[6] + 128) << 16) | (clamp255(o[7] + 128) << 24);
