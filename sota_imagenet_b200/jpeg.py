@@ -50,7 +50,11 @@ IMAGE_DTYPE = np.dtype([("coef_off", "<i8", 3), ("plane_off", "<i8", 3), ("out_o
 assert IMAGE_DTYPE.itemsize == 488
 
 STATUS = {0: "ok", 1: "not a JPEG", 2: "corrupt", 3: "progressive / arithmetic / lossless process",
-          4: "not 8-bit", 5: "colour space (CMYK, Adobe RGB)", 6: "sampling factors", 7: "more than one scan"}
+          4: "not 8-bit", 5: "colour space (CMYK, Adobe RGB)", 6: "sampling factors", 7: "more than one scan",
+          8: "larger than MAX_PIXELS"}
+# a (corrupt) header may announce up to 65535 x 65535 pixels: such streams go to the host decoder, which has its
+# own decompression-bomb guard, instead of sizing a multi-gigabyte pinned staging buffer here
+MAX_PIXELS = 1 << 26
 
 
 def _as_bytes(data):
@@ -63,6 +67,8 @@ def parse(data):
     info = JpegInfo()
     data = _as_bytes(data)
     _lib.check(_lib.load().sib_jpeg_parse(data, len(data), ctypes.byref(info)))
+    if info.status == 0 and info.width * info.height > MAX_PIXELS:
+        info.status = 8
     return info
 
 

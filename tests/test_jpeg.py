@@ -88,6 +88,10 @@ def test_streams_outside_the_device_subset_are_reported():
     assert jpeg.parse(b.getvalue()).status == 1
     assert jpeg.parse(encode(synth(8, 3), subsampling=2)).status == 6      # chroma rows of 2 samples: not the fancy path
     assert jpeg.parse(b"").status == 1 and jpeg.parse(b"\xff\xd8\xff").status != 0
+    big = bytearray(encode(im, quality=80))
+    sof = big.index(b"\xff\xc0")
+    big[sof + 5:sof + 9] = b"\xff\xff\xff\xff"            # a header announcing 65535 x 65535 pixels
+    assert jpeg.parse(bytes(big)).status == 8
     with pytest.raises(Exception):
         jpeg.decode_coefficients(encode(im, progressive=True))
 
