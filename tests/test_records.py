@@ -235,3 +235,37 @@ def test_record_loader_host_flow_with_oracle_kernels(tmp_path, monkeypatch):
     dm.set_stage(0)
     assert isinstance(dm.loader, data.RecordLoader) and isinstance(dm.val_loader, data.RecordLoader)
     assert dm.val_loader.crop_size == 16 and len(dm.loader) == 3
+
+
+def test_loader_background_iterator():
+    """`RecordLoader._in_thread` (the loader thread of `prefetch > 0`): items arrive in order, an exception in the
+    producer surfaces in the consumer, a consumer that stops early releases the thread."""
+    import threading
+    import time
+    from sota_imagenet_b200 import data
+    assert list(data.RecordLoader._in_thread(lambda: iter(range(50)), 2, "sib-test-iter")) == list(range(50))
+
+    def failing():
+        yield 1
+        raise KeyError("boom")
+
+    it = data.RecordLoader._in_thread(failing, 2, "sib-test-iter")
+    assert next(it) == 1
+    with pytest.raises(KeyError):
+        next(it)
+
+    produced = []
+
+    def endless():
+        i = 0
+        while True:
+            produced.append(i)
+            yield i
+            i += 1
+
+    it = data.RecordLoader._in_thread(endless, 3, "sib-test-iter")
+    assert [next(it) for _ in range(4)] == [0, 1, 2, 3]
+    it.close()                                   # the consumer stops: the producer must not stay blocked
+    time.sleep(0.3)
+    assert not [t for t in threading.enumerate() if t.name == "sib-test-iter" and t.is_alive()]
+    assert len(produced) <= 4 + 3 + 2            # never ran more than the queue depth ahead
